@@ -1,0 +1,189 @@
+/* pggan_b200 — C ABI of the B200-native PGGAN training-step kernels (libpggan_b200.so).
+ *
+ * Drop-in boundary: the reference has no FFI; its hot path is reached through
+ * Python classes (lib/layers.py, lib/blocks.py, pggan/nets.py, pggan/loss.py).  The Python
+ * package `pggan_b200` mirrors those classes and calls ONLY the entry points below, on raw
+ * device pointers owned by the caller (torch tensors).  Every entry point
+ *   - launches asynchronously on the given CUDA stream (cudaStream_t passed as void*),
+ *   - never allocates, frees or synchronises (workspaces are passed in),
+ *   - returns PG_OK or a negative error code; pggan_last_error() gives the message.
+ *
+ * Layouts.  Feature maps are NHWC ("channels_last"): [B][H][W][C], dtype PG_BF16 or PG_F32
+ * (PG_F32 operands run on kind::tf32 tensor-core MMAs; they are stored pre-rounded to tf32).
+ * RGB images, logits, latents, parameters and parameter gradients are fp32 in the reference's
+ * own layouts (NCHW images, OIHW conv weights, [out,in] linear weights).
+ *
+ * Each entry cites the reference code it replaces (file:line in yukyeongleee/pggan).
+ */
+#ifndef PGGAN_B200_H
+#define PGGAN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PG_OK 0
+#define PG_ERR_ARG (-1)
+#define PG_ERR_CUDA (-2)
+#define PG_ERR_UNSUPPORTED (-3)
+
+#define PG_BF16 0
+#define PG_F32 1
+#define PG_F32_RAW 2 /* output-only: fp32 without the tf32 pre-rounding (final logits / images) */
+
+/* conv backend selection (bring-up / debugging): 0 = tcgen05 wherever the shape allows (default),
+ * 1 = force the SIMT direct kernels. */
+#define PG_BACKEND_AUTO 0
+#define PG_BACKEND_SIMT 1
+
+int pggan_version(void);
+const char* pggan_last_error(void);
+int pggan_set_conv_backend(int backend);
+/* number of tcgen05 / SIMT GEMM-class launches since load (evidence for "which path ran") */
+int pggan_launch_counts(int64_t* tcgen05_launches, int64_t* simt_launches, int64_t* other_launches);
+
+/* ------------------------------------------------------------------------------------------
+ * Weight packing.  out[n][t][c] (dtype, c padded with zeros to c_pad) = in[off], fp32 source,
+ *   n = n1*N2 + n2,  off = base + n1*s_n1 + n2*s_n2 + t*s_t + c*s_c   (strides in elements,
+ *   s_t may be negative for the 180-degree flip used by dgrad).
+ * Replaces: the implicit OIHW weight use of nn.Conv2d / nn.Linear in ConstrainedLayer.forward
+ * (lib/layers.py:58-63); exists because the tensor-core kernels want K-major [N][taps*C].
+ */
+int pggan_pack_weight(const float* in, void* out, int dtype, int n1, int n2, int taps, int c, int c_pad,
+                      int64_t base, int64_t s_n1, int64_t s_n2, int64_t s_t, int64_t s_c, void* stream);
+
+/* Inverse for gradients: out_fp32[off] (+)= scale * in_fp32[n][t][c]  (same index map, in is the
+ * dense [N][taps][c_pad] fp32 accumulator written by pggan_conv_wgrad). accumulate: 0 = overwrite. */
+int pggan_unpack_wgrad(const float* in, float* out, int n1, int n2, int taps, int c, int c_pad, int64_t base,
+                       int64_t s_n1, int64_t s_n2, int64_t s_t, int64_t s_c, float scale, int accumulate,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution / linear, forward-style:
+ *   y[b,h,w,n] = post( scale * ( sum_{t,c} x[b, h+dh(t), w+dw(t), c] * wp[n][t][c] + bias[n] ) )
+ *   taps = 9: 3x3, pad 1, (dh,dw) = (t/3-1, t%3-1);  taps = 1: 1x1 / linear (H=W=1).
+ *   post(v) = lrelu(v, slope) then, if mask_src != NULL, v * (mask_src[b,h,w,n] > 0 ? 1 : mask_slope).
+ * Serves fprop, dgrad (flipped/transposed wp) and the grad-of-dgrad fprop.
+ * Replaces: EqualizedConv2d / EqualizedLinear forward = nn.Conv2d|nn.Linear + `x *= self.weight`
+ * (lib/layers.py:58-63) + the following nn.LeakyReLU (lib/blocks.py:127,137,185,192,254) and, for
+ * dgrad, autograd's convolution_backward + leaky_relu_backward.
+ * Tensor-core path (tcgen05 + TMA) needs: H,W powers of two, C*elsize % 128 == 0, N % 16 == 0;
+ * anything else runs the SIMT direct kernel.
+ */
+typedef struct {
+    const void* x;        /* [B,H,W,C]  dtype */
+    const void* wp;       /* [N][taps][C] dtype (pggan_pack_weight) */
+    const float* bias;    /* [N] fp32 or NULL */
+    const void* mask_src; /* [B,H,W,N] dtype or NULL */
+    void* y;              /* [B,H,W,N] out_dtype */
+    int32_t B, H, W, C, N, taps;
+    int32_t dtype, out_dtype;
+    float scale, slope, mask_slope;
+} pg_conv_params;
+int pggan_conv_fprop(const pg_conv_params* p, void* stream);
+
+/* Weight-gradient GEMM:  acc[n][t][c] += sum_{b,h,w} g[b,h,w,n] * x[b, h+dh(t), w+dw(t), c]
+ * acc is a dense fp32 [N][taps][C] accumulator the caller zeroes (split-K uses atomics).
+ * Also the grad-of-dgrad w.r.t. W with operands (g_pre, ggx).
+ * Replaces: autograd convolution_backward (weight) / addmm backward of lib/layers.py:60.
+ */
+typedef struct {
+    const void* g;   /* [B,H,W,N] dtype */
+    const void* x;   /* [B,H,W,C] dtype */
+    float* acc;      /* [N][taps][C] fp32 */
+    int32_t B, H, W, C, N, taps;
+    int32_t dtype;
+} pg_wgrad_params;
+int pggan_conv_wgrad(const pg_wgrad_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Elementwise / reduction kernels on NHWC feature maps (n = element count, m = pixels).
+ */
+/* out = g * (y > 0 ? 1 : slope)      — leaky_relu_backward, lib/blocks.py:127,137,185,192 */
+int pggan_lrelu_mask_mul(const void* g, const void* y, void* out, int64_t n, float slope, int dtype, void* stream);
+/* out[b,2h+i,2w+j,c] = scale * x[b,h,w,c]   — upscale2d, lib/utils.py:106-118 (exact) and avg-pool backward */
+int pggan_upsample2x(const void* x, void* out, int B, int H, int W, int C, float scale, int dtype, void* stream);
+/* out[b,h,w,c] = scale * sum_{i,j<2} x[b,2h+i,2w+j,c]; if blend_with != NULL:
+ * out = (1-alpha)*blend_with + alpha*that   — nn.AvgPool2d(2) lib/blocks.py:193 (+ fade pggan/nets.py:265) */
+int pggan_pool2x2(const void* x, const void* blend_with, void* out, int B, int H, int W, int C, float scale,
+                  float alpha, int dtype, void* stream);
+/* out = sa*a + sb*b (b may be NULL)  — fade-in blends pggan/nets.py:156,265 and their backward */
+int pggan_axpby(const void* a, const void* b, void* out, int64_t n, float sa, float sb, int dtype, void* stream);
+/* y = x * rsqrt(mean_c(x^2) + eps), rnorm[m] saved   — PixelwiseVectorNorm, lib/layers.py:13-14 */
+int pggan_pixelnorm_fwd(const void* x, void* y, float* rnorm, int64_t m, int C, float eps, int dtype, void* stream);
+/* gx = rnorm * (gy - y * mean_c(gy*y)); if act_slope != 1 the LeakyReLU mask (sign of y) is applied too */
+int pggan_pixelnorm_bwd(const void* gy, const void* y, const float* rnorm, void* gx, int64_t m, int C,
+                        float act_slope, int dtype, void* stream);
+/* out[c] (+)= scale * sum_m g[m,c]   — bias gradient of lib/layers.py:60 (bias is He-scaled too) */
+int pggan_colsum(const void* g, float* out, int64_t m, int C, float scale, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 1x1 RGB convolutions (bandwidth kernels; N=3 / K=3 is not tensor-core shaped).
+ */
+/* out[b,h,w,c] = lrelu(scale*(sum_j w[c][j]*p_j + bias[c]), slope), p = img[b,:,h,w] or, if pool,
+ * the 2x2 mean of img[b,:,2h..,2w..].  img fp32 NCHW [B,cimg,Hi,Wi] (cimg <= 4), w fp32 [C][cimg],
+ * out NHWC [B,H,W,C].
+ * — fromRGBBlock lib/blocks.py:285-292 (+ downscale2d lib/utils.py:120-124); also toRGB dgrad. */
+int pggan_rgb_expand(const float* img, const float* w, const float* bias, void* out, int B, int H, int W, int C,
+                     int cimg, int pool, float scale, float slope, int dtype, void* stream);
+/* out[b,j,h,w] = scale*(sum_c w[j][c]*x[b,h,w,c] + bias[j]) fp32 NCHW, w fp32 [cimg][C]; if up, every
+ * value (times up_scale) is written to the 2x2 block of a [B,cimg,2H,2W] output
+ * — toRGBBlock lib/blocks.py:164-170; also fromRGB dgrad (+ avg-pool backward). */
+int pggan_rgb_reduce(const void* x, const float* w, const float* bias, float* out, int B, int H, int W, int C,
+                     int cimg, int up, float scale, float up_scale, int dtype, void* stream);
+/* acc[c][j] += scale * sum_{b,h,w} f[b,h,w,c] * p_j(b,h,w)   (p as in rgb_expand) — 1x1 weight grads */
+int pggan_rgb_wgrad(const void* f, const float* img, float* acc, int B, int H, int W, int C, int cimg, int pool,
+                    float scale, int dtype, void* stream);
+/* fp32 NCHW image fade.  low == NULL: out = (1-a)*up2(avgpool2(x)) + a*x  (pggan/model.py:217-221)
+ *                        low != NULL: out = (1-a)*up2(low) + a*x          (pggan/nets.py:155-156)   */
+int pggan_image_fade(const float* x, const float* low, float* out, int B, int Cimg, int H, int W, float alpha,
+                     void* stream);
+/* out[b,c,h,w] = scale * sum_{2x2} x   (fp32 NCHW) — backward of the RGB up-sampling */
+int pggan_image_pool_sum(const float* x, float* out, int B, int Cimg, int H, int W, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Minibatch standard deviation (lib/blocks.py:204-233): groups of `group` consecutive samples,
+ * unbiased variance, eps inside sqrt, mean over (C,H,W).  x is [B][K] (K = H*W*C, any order).
+ */
+int pggan_mbstd_fwd(const void* x, float* stat, int B, int64_t K, int group, int dtype, void* stream);
+/* gx[i,k] = gs[g] * (x-mu)/(K (n-1) sigma) */
+int pggan_mbstd_bwd(const void* x, const float* gs, void* gx, int B, int64_t K, int group, int dtype, void* stream);
+/* double backward of the above w.r.t. cotangent u (= ggx): ggs[g] and gx2[i,k] */
+int pggan_mbstd_bwd2(const void* x, const void* u, const float* gs, float* ggs, void* gx2, int B, int64_t K,
+                     int group, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * WGAN-GP / R1 reductions over fp32 image gradients g [B][n]  (pggan/loss.py:85-87, lib/loss.py:132-134)
+ */
+/* sumsq[b] = sum_k g[b,k]^2   (caller zeroes sumsq) */
+int pggan_rows_sumsq(const float* g, float* sumsq, int B, int64_t n, void* stream);
+/* out[b,k] = coef[b] * g[b,k] */
+int pggan_rows_scale(const float* g, const float* coef, float* out, int B, int64_t n, void* stream);
+/* fused epilogue on [B] scalars: res[0] = w_gp*sum_b (sqrt(sumsq_b)-1)^2, res[1] = w_drift*sum_b pred_b^2,
+ * coef[b] = w_gp*2*(norm_b-1)/norm_b  (the backward row scale). pred may be NULL. */
+int pggan_gp_finalize(const float* sumsq, const float* pred, float* res, float* coef, int B, float w_gp,
+                      float w_drift, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused multi-tensor Adam (torch.optim.Adam semantics, lib/model.py:95-97, lib/utils.py:72-75).
+ * table: device array of n_tensors entries {param*, grad*, m*, v*, numel}; step: device int64 counter
+ * (incremented by the kernel: CUDA-graph friendly).  grad_scale folds the 1/world_size of the DP mean.
+ */
+typedef struct {
+    float* param;
+    const float* grad;
+    float* exp_avg;
+    float* exp_avg_sq;
+    int64_t numel;
+} pg_adam_entry;
+int pggan_adam_chunk_size(void); /* elements handled per chunk-table entry */
+int pggan_adam_step(const pg_adam_entry* table, int n_tensors, int64_t total_chunks, const int32_t* chunk_tensor,
+                    const int64_t* chunk_offset, int64_t* step, float lr, float beta1, float beta2, float eps,
+                    float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGGAN_B200_H */

@@ -1,0 +1,116 @@
+"""ctypes binding of libpggan_b200.so — the thin C-ABI boundary (include/pggan_b200.h).
+
+There is NO CPU fallback: if the shared library is missing or a call fails, the error is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+
+PG_BF16, PG_F32, PG_F32_RAW = 0, 1, 2
+PG_BACKEND_AUTO, PG_BACKEND_SIMT = 0, 1
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libpggan_b200.so")
+
+
+class ConvParams(Structure):
+    _fields_ = [
+        ("x", c_void_p), ("wp", c_void_p), ("bias", c_void_p), ("mask_src", c_void_p), ("y", c_void_p),
+        ("B", c_int32), ("H", c_int32), ("W", c_int32), ("C", c_int32), ("N", c_int32), ("taps", c_int32),
+        ("dtype", c_int32), ("out_dtype", c_int32),
+        ("scale", c_float), ("slope", c_float), ("mask_slope", c_float),
+    ]
+
+
+class WgradParams(Structure):
+    _fields_ = [
+        ("g", c_void_p), ("x", c_void_p), ("acc", c_void_p),
+        ("B", c_int32), ("H", c_int32), ("W", c_int32), ("C", c_int32), ("N", c_int32), ("taps", c_int32),
+        ("dtype", c_int32),
+    ]
+
+
+class AdamEntry(Structure):
+    _fields_ = [("param", c_void_p), ("grad", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p),
+                ("numel", c_int64)]
+
+
+# name -> (restype, argtypes); exactly the symbols include/pggan_b200.h declares
+SIGNATURES = {
+    "pggan_version": (c_int, []),
+    "pggan_last_error": (c_char_p, []),
+    "pggan_set_conv_backend": (c_int, [c_int]),
+    "pggan_launch_counts": (c_int, [POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]),
+    "pggan_pack_weight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int64, c_int64,
+                                  c_int64, c_int64, c_int64, c_void_p]),
+    "pggan_unpack_wgrad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int64, c_int64, c_int64,
+                                   c_int64, c_int64, c_float, c_int, c_void_p]),
+    "pggan_conv_fprop": (c_int, [POINTER(ConvParams), c_void_p]),
+    "pggan_conv_wgrad": (c_int, [POINTER(WgradParams), c_void_p]),
+    "pggan_lrelu_mask_mul": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_int, c_void_p]),
+    "pggan_upsample2x": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
+    "pggan_pool2x2": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_int,
+                              c_void_p]),
+    "pggan_axpby": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_int, c_void_p]),
+    "pggan_pixelnorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_int, c_void_p]),
+    "pggan_pixelnorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_int, c_void_p]),
+    "pggan_colsum": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_float, c_int, c_void_p]),
+    "pggan_rgb_expand": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                 c_float, c_float, c_int, c_void_p]),
+    "pggan_rgb_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                 c_float, c_float, c_int, c_void_p]),
+    "pggan_rgb_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
+                                c_int, c_void_p]),
+    "pggan_image_fade": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "pggan_image_pool_sum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "pggan_mbstd_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p]),
+    "pggan_mbstd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p]),
+    "pggan_mbstd_bwd2": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int,
+                                 c_void_p]),
+    "pggan_rows_sumsq": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p]),
+    "pggan_rows_scale": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p]),
+    "pggan_gp_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_void_p]),
+    "pggan_adam_chunk_size": (c_int, []),
+    "pggan_adam_step": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float,
+                                c_float, c_float, c_void_p]),
+}
+
+_lib = None
+
+
+class PgganLibraryError(RuntimeError):
+    pass
+
+
+def load(path: str | None = None) -> ctypes.CDLL:
+    """Load the shared library (building nothing: run `python -m pggan_b200.build` or
+    `__graft_entry__.build()` first).  Raises if it is absent — there is no fallback path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = path or os.environ.get("PGGAN_B200_LIB", LIB_PATH)
+    if not os.path.exists(path):
+        raise PgganLibraryError(
+            f"{path} not found: the CUDA extension is not built (python -m pggan_b200.build). "
+            "pggan_b200 has no CPU / PyTorch fallback.")
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().pggan_last_error()
+        raise PgganLibraryError(f"{what} failed (code {rc}): {msg.decode() if msg else '?'}")
+
+
+def launch_counts():
+    a, b, c = c_int64(0), c_int64(0), c_int64(0)
+    load().pggan_launch_counts(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+    return {"tcgen05": a.value, "simt": b.value, "other": c.value}

@@ -1,0 +1,170 @@
+"""PGGAN building blocks — mirror of the PGGAN half of reference lib/blocks.py (:113-292).
+
+Module trees, constructor signatures (including the flipped argument order of the two Progressive
+blocks) and state_dict keys are the reference's; `forward` runs the fused kernels.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .layers import EqualizedConv2d, EqualizedLinear, PixelwiseVectorNorm
+from .utils import downscale2d, upscale2d, num_flat_features  # noqa: F401
+
+
+def _conv_act_norm(layer, x, norm):
+    """conv3x3 -> c*(.+b) -> LeakyReLU(0.2) [-> pixel norm]   (reference lib/blocks.py:119-139)"""
+    x = layer.fused(x, 0.2)
+    if norm is not None:
+        x = norm(x)
+    return x
+
+
+class ProgressiveGeneratorBlock(nn.Module):
+    """reference lib/blocks.py:113-151: [upscale2d] -> (conv3x3 -> LReLU -> PN) x2  (is_first: one conv)"""
+
+    def __init__(self, prev_depth, new_depth, equalized_lr=True, init_bias_to_zero=True, norm=None, is_first=False):
+        super().__init__()
+        block = []
+        if not is_first:
+            block.append(EqualizedConv2d(prev_depth, new_depth, 3, padding=1, equalized=equalized_lr,
+                                         init_bias_to_zero=init_bias_to_zero))
+            block.append(nn.LeakyReLU(0.2))
+            if norm:
+                block.append(norm)
+        block.append(EqualizedConv2d(new_depth, new_depth, 3, padding=1, equalized=equalized_lr,
+                                     init_bias_to_zero=init_bias_to_zero))
+        block.append(nn.LeakyReLU(0.2))
+        if norm:
+            block.append(norm)
+        self.block = nn.Sequential(*block)
+        self.is_first = is_first
+
+    def _convs_and_norm(self):
+        convs = [m for m in self.block if isinstance(m, EqualizedConv2d)]
+        norm = next((m for m in self.block if isinstance(m, PixelwiseVectorNorm)), None)
+        return convs, norm
+
+    def forward(self, x):
+        convs, norm = self._convs_and_norm()
+        if not self.is_first:
+            x = upscale2d(ops.feat(x))
+        for conv in convs:
+            x = _conv_act_norm(conv, x, norm)
+        return x
+
+
+class toRGBBlock(nn.Module):
+    """reference lib/blocks.py:153-170: 1x1 conv C -> output_dim (no activation) [+ upscale2d]"""
+
+    def __init__(self, new_depth, output_dim=3, equalized_lr=True, init_bias_to_zero=True):
+        super().__init__()
+        self.toRGB = EqualizedConv2d(new_depth, output_dim, 1, equalized=equalized_lr,
+                                     init_bias_to_zero=init_bias_to_zero)
+
+    def forward(self, x, apply_upscale=False):
+        m = self.toRGB.module
+        W = m.weight
+        Wc = W.view(W.shape[0], W.shape[1]).t()
+        # the 1x1 conv commutes with nearest up-sampling, so the up-scaled image is written directly
+        return ops.RgbReduce.apply(x, Wc, m.bias, bool(apply_upscale), self.toRGB.scale(), 1.0)
+
+
+class ProgressiveDiscriminatorBlock(nn.Module):
+    """reference lib/blocks.py:173-201: conv3x3(C->C) -> LReLU -> conv3x3(C->Cprev) -> LReLU -> AvgPool2"""
+
+    def __init__(self, new_depth, prev_depth, equalized_lr=True, init_bias_to_zero=True):
+        super().__init__()
+        self.block = nn.Sequential(
+            EqualizedConv2d(new_depth, new_depth, 3, padding=1, equalized=equalized_lr,
+                            init_bias_to_zero=init_bias_to_zero),
+            nn.LeakyReLU(0.2),
+            EqualizedConv2d(new_depth, prev_depth, 3, padding=1, equalized=equalized_lr,
+                            init_bias_to_zero=init_bias_to_zero),
+            nn.LeakyReLU(0.2),
+            nn.AvgPool2d((2, 2)),
+        )
+
+    def forward(self, x, blend_with=None, alpha=1.0):
+        """blend_with/alpha: optional feature-space fade fused with the pooling
+        ((1-alpha)*blend_with + alpha*pool(x), reference pggan/nets.py:262-265)."""
+        x = self.block[0].fused(x, 0.2)
+        x = self.block[2].fused(x, 0.2)
+        if blend_with is not None:
+            return ops.PoolBlend.apply(x, blend_with, float(alpha))
+        return ops.Pool2x2.apply(x, 0.25)
+
+
+def _stddev_channel(x, subgroup_size=4):
+    """the extra channel of reference lib/blocks.py:216-231 as a [N,1,H,W] tensor"""
+    size = x.size()
+    subgroup_size = min(size[0], subgroup_size)
+    if size[0] % subgroup_size != 0:
+        subgroup_size = size[0]
+    if subgroup_size > 1:
+        stat = ops.MbstdStat.apply(x, int(subgroup_size))                 # [N/G] fp32
+        y = stat.repeat_interleave(subgroup_size).view(size[0], 1, 1, 1)
+        return y.expand(size[0], 1, size[2], size[3]).to(x.dtype)
+    return torch.zeros(size[0], 1, size[2], size[3], device=x.device, dtype=x.dtype)
+
+
+def concatenate_stddev_channel(x, subgroup_size=4):
+    """reference lib/blocks.py:204-233: unbiased variance over groups of `subgroup_size` consecutive
+    samples, eps 1e-8 inside the sqrt, mean over (C,H,W); one group of N if N % size != 0; zeros if N == 1."""
+    x = ops.feat(x)
+    return torch.cat([x, _stddev_channel(x, subgroup_size)], dim=1)
+
+
+class LastProgressiveDiscriminatorBlock(nn.Module):
+    """reference lib/blocks.py:236-268: mbstd -> conv3x3(C+1->C)@4x4 -> LReLU -> flatten -> Linear -> LReLU"""
+
+    def __init__(self, depth, equalized_lr=True, init_bias_to_zero=True, apply_minibatch_norm=False):
+        super().__init__()
+        self.conv_list = []
+        entry_dim = depth + 1 if apply_minibatch_norm else depth
+        self.conv = EqualizedConv2d(entry_dim, depth, 3, padding=1, equalized=equalized_lr,
+                                    init_bias_to_zero=init_bias_to_zero)
+        self.linear = EqualizedLinear(depth * 16, depth, equalized=equalized_lr, init_bias_to_zero=init_bias_to_zero)
+        self.activ = nn.LeakyReLU(0.2)
+        self.apply_minibatch_norm = apply_minibatch_norm
+
+    def forward(self, x, subgroup_size=4):
+        x = ops.feat(x)
+        W, b = self.conv.module.weight, self.conv.module.bias
+        if self.apply_minibatch_norm:
+            # the 513-channel input is padded with zero channels up to the MMA K granule; the weight is
+            # zero-padded to match (torch pads/slices, so the gradient of W keeps its [C, C+1, 3, 3] shape)
+            cin = x.shape[1] + 1
+            gran = 64 if x.dtype == torch.bfloat16 else 32
+            cpad = (cin + gran - 1) // gran * gran
+            parts = [x, _stddev_channel(x, subgroup_size)]
+            if cpad > cin:
+                parts.append(torch.zeros(x.shape[0], cpad - cin, x.shape[2], x.shape[3], device=x.device,
+                                         dtype=x.dtype))
+                W = torch.nn.functional.pad(W, (0, 0, 0, 0, 0, cpad - cin))
+            x = torch.cat(parts, dim=1).contiguous(memory_format=torch.channels_last)
+        x = ops.ConvF.apply(x, W, b, self.conv.scale(), 0.2, False)
+        n, c, h, w = x.shape
+        # flatten in the reference's (C,H,W) order == permuting the linear's K axis to our (H,W,C) order
+        x = x.permute(0, 2, 3, 1).reshape(n, h * w * c)
+        Wl = self.linear.module.weight
+        Wl = Wl.view(Wl.shape[0], c, h * w).transpose(1, 2).reshape(Wl.shape[0], h * w * c)
+        x = ops.ConvF.apply(x, Wl, self.linear.module.bias, self.linear.scale(), 0.2, False)
+        return x
+
+
+class fromRGBBlock(nn.Module):
+    """reference lib/blocks.py:271-292: [avg_pool2] -> 1x1 conv 3 -> C -> LReLU(0.2)"""
+
+    def __init__(self, input_dim=3, new_depth=None, equalized_lr=True, init_bias_to_zero=True):
+        super().__init__()
+        self.fromRGB = EqualizedConv2d(input_dim, new_depth, 1, equalized=equalized_lr,
+                                       init_bias_to_zero=init_bias_to_zero)
+        self.activ = nn.LeakyReLU(0.2)
+
+    def forward(self, x, apply_downscale=False):
+        m = self.fromRGB.module
+        W = m.weight
+        return ops.RgbExpand.apply(x, W.view(W.shape[0], W.shape[1]), m.bias, bool(apply_downscale),
+                                   self.fromRGB.scale(), 0.2)

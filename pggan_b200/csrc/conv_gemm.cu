@@ -1,0 +1,399 @@
+// Implicit-GEMM 3x3 / 1x1 convolution and linear layers on tcgen05 tensor cores, fed by TMA.
+//
+//   D[128 pixels x BLOCK_N] (fp32, TMEM) += A[128 pixels x 128 B of K] * B[BLOCK_N x 128 B of K]^T
+//
+// A tile  = a (BW x BH x BB) box of pixels of the NHWC input, one filter tap, one 128-byte channel
+//           chunk: a single 4-D TMA box load whose (w,h) origin is shifted by the tap offset; TMA
+//           zero-fills out-of-bounds coordinates, which IS the conv zero padding (no im2col buffer).
+// B tile  = BLOCK_N rows of the K-major packed weights [N][taps*C].
+// Both land in the canonical SWIZZLE_128B K-major layout that tcgen05.mma consumes directly.
+//
+// Warp roles (192 threads, 1 CTA/SM, persistent over tiles):
+//   warp 0 : TMA producer        (one elected lane)
+//   warp 1 : TMEM allocator + MMA issuer (one elected lane)
+//   warps 2-5 : epilogue — tcgen05.ld the accumulator (double-buffered in TMEM so the next tile's
+//               mainloop overlaps), apply  scale*(acc+bias) -> LeakyReLU -> optional mask, store NHWC.
+//
+// Replaces cuDNN fprop/dgrad behind EqualizedConv2d/EqualizedLinear (reference lib/layers.py:58-63)
+// with the He scale, bias and LeakyReLU (lib/blocks.py:127,137,185,192) folded into the epilogue.
+#include "common.cuh"
+
+#include <atomic>
+
+namespace pg {
+
+extern std::atomic<long long> g_tc_launches, g_simt_launches;
+extern int g_conv_backend;
+
+constexpr int kBlockM = 128;
+constexpr int kABytes = kBlockM * 128;   // one A stage: 128 rows x 128 B
+constexpr int kConvThreads = 192;
+
+template <int BLOCK_N> struct ConvCfg {
+    static constexpr int kBBytes = BLOCK_N * 128;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8);
+    static constexpr int kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct ConvKArgs {
+    const float* bias;
+    const void* mask_src;
+    void* y;
+    int B, H, W, N;
+    int BW, BH, BB;
+    int tiles_w, tiles_h, tiles_b, tiles_n;
+    int kc_per_tap, taps;
+    int out_dtype;
+    float scale, slope, mask_slope;
+};
+
+template <typename T, int BLOCK_N>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                 const ConvKArgs a) {
+    using Cfg = ConvCfg<BLOCK_N>;
+    constexpr bool kTF32 = (sizeof(T) == 4);
+    constexpr int BK = 128 / sizeof(T);           // elements per 128-byte K chunk
+    constexpr int kMmaPerChunk = 4;               // 128 B / 32 B per UMMA K-step
+    constexpr int kStages = Cfg::kStages;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tfull_bar = empty_bar + kStages;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_x);
+        tma_prefetch_desc(&tmap_w);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], 128);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int num_m_tiles = a.tiles_w * a.tiles_h * a.tiles_b;
+    const int num_tiles = num_m_tiles * a.tiles_n;
+    const int num_kc = a.taps * a.kc_per_tap;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int nt = tile % a.tiles_n;
+                const int mt = tile / a.tiles_n;
+                const int w0 = (mt % a.tiles_w) * a.BW;
+                const int h0 = ((mt / a.tiles_w) % a.tiles_h) * a.BH;
+                const int b0 = (mt / (a.tiles_w * a.tiles_h)) * a.BB;
+                const int n0 = nt * BLOCK_N;
+                for (int kc = 0; kc < num_kc; ++kc) {
+                    const int tap = kc / a.kc_per_tap;
+                    const int cc = kc - tap * a.kc_per_tap;
+                    int dh = 0, dw = 0;
+                    if (a.taps == 9) {
+                        dh = tap / 3 - 1;
+                        dw = tap % 3 - 1;
+                    }
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * Cfg::kStageBytes;
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                    tma_load_4d(sa, &tmap_x, &full_bar[stage], cc * BK, w0 + dw, h0 + dh, b0);
+                    tma_load_2d(sa + kABytes, &tmap_w, &full_bar[stage], kc * BK, n0);
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // -------------------------------------------------------------------- MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(kTF32 ? 2 : 1, 0, 0, kBlockM, BLOCK_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                for (int kc = 0; kc < num_kc; ++kc) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+                    const uint64_t adesc = make_smem_desc(sa, 16, 1024);
+                    const uint64_t bdesc = make_smem_desc(sa + kABytes, 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < kMmaPerChunk; ++k) {
+                        // advance 32 bytes along K inside the 128 B swizzle span: +2 in 16-byte units
+                        umma_ss<kTF32>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) != 0);
+                    }
+                    umma_commit(&empty_bar[stage]);     // frees the smem slot when these MMAs retire
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(&tfull_bar[acc]);           // accumulator complete -> epilogue
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------------- epilogue
+        const int q = warp & 3;                        // TMEM lane quarter this warp may read
+        const int row = q * 32 + lane;
+        const int wo = row % a.BW;
+        const int ho = (row / a.BW) % a.BH;
+        const int bo = row / (a.BW * a.BH);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const int nt = tile % a.tiles_n;
+            const int mt = tile / a.tiles_n;
+            const int w0 = (mt % a.tiles_w) * a.BW;
+            const int h0 = ((mt / a.tiles_w) % a.tiles_h) * a.BH;
+            const int b0 = (mt / (a.tiles_w * a.tiles_h)) * a.BB;
+            const int n0 = nt * BLOCK_N;
+            const int b = b0 + bo;
+            const bool valid = b < a.B;
+            const size_t pix = (static_cast<size_t>(b) * a.H + (h0 + ho)) * a.W + (w0 + wo);
+            const size_t off = pix * a.N + n0;
+
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+            for (int j = 0; j < BLOCK_N / 32; ++j) {
+                uint32_t r[32];
+                if constexpr (BLOCK_N >= 32) {
+                    tmem_ld32(taddr + j * 32, r);
+                }
+                tmem_ld_wait();
+                float v[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float t = __uint_as_float(r[i]);
+                    if (a.bias != nullptr) t += __ldg(a.bias + n0 + j * 32 + i);
+                    t *= a.scale;
+                    v[i] = lrelu_f(t, a.slope);
+                }
+                if (valid) {
+                    if (a.mask_src != nullptr) {
+                        const T* mp = reinterpret_cast<const T*>(a.mask_src) + off + j * 32;
+                        constexpr int VN = 16 / sizeof(T);
+#pragma unroll
+                        for (int c = 0; c < 32 / VN; ++c) {
+                            uint4 raw = __ldg(reinterpret_cast<const uint4*>(mp) + c);
+                            const T* mv = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+                            for (int e = 0; e < VN; ++e)
+                                if (!(DT<T>::to_f(mv[e]) > 0.f)) v[c * VN + e] *= a.mask_slope;
+                        }
+                    }
+                    if (a.out_dtype == PG_BF16) {
+                        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(a.y) + off + j * 32;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            uint4 pk;
+                            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                h2[e] = __floats2bfloat162_rn(v[c * 8 + 2 * e], v[c * 8 + 2 * e + 1]);
+                            reinterpret_cast<uint4*>(op)[c] = pk;
+                        }
+                    } else {
+                        float* op = reinterpret_cast<float*>(a.y) + off + j * 32;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            float4 pk;
+                            // fp32 activations are stored pre-rounded to tf32 when they feed another MMA
+                            const bool rnd = kTF32 && a.out_dtype == PG_F32;
+                            pk.x = rnd ? DT<float>::from_f(v[c * 4 + 0]) : v[c * 4 + 0];
+                            pk.y = rnd ? DT<float>::from_f(v[c * 4 + 1]) : v[c * 4 + 1];
+                            pk.z = rnd ? DT<float>::from_f(v[c * 4 + 2]) : v[c * 4 + 2];
+                            pk.w = rnd ? DT<float>::from_f(v[c * 4 + 3]) : v[c * 4 + 3];
+                            reinterpret_cast<float4*>(op)[c] = pk;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------------- SIMT direct kernel
+// One thread per (pixel, 4 consecutive n); any shape.  Bring-up cross-check and the path for
+// shapes the tensor-core kernel does not take (C*elsize % 128 != 0, non power-of-two H/W).
+template <typename T>
+__global__ void conv_direct_kernel(const T* __restrict__ x, const T* __restrict__ wp, const float* __restrict__ bias,
+                                   const T* __restrict__ mask_src, void* __restrict__ y, int B, int H, int W, int C,
+                                   int N, int taps, int out_dtype, float scale, float slope, float mask_slope) {
+    const long long total = static_cast<long long>(B) * H * W * N;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int n = static_cast<int>(idx % N);
+        const long long pix = idx / N;
+        const int w = static_cast<int>(pix % W);
+        const int h = static_cast<int>((pix / W) % H);
+        const int b = static_cast<int>(pix / (static_cast<long long>(W) * H));
+        float acc = 0.f;
+        for (int t = 0; t < taps; ++t) {
+            const int hh = h + (taps == 9 ? t / 3 - 1 : 0);
+            const int ww = w + (taps == 9 ? t % 3 - 1 : 0);
+            if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+            const T* xp = x + ((static_cast<long long>(b) * H + hh) * W + ww) * C;
+            const T* wr = wp + (static_cast<long long>(n) * taps + t) * C;
+            for (int c = 0; c < C; ++c) acc += DT<T>::to_f(xp[c]) * DT<T>::to_f(wr[c]);
+        }
+        if (bias != nullptr) acc += bias[n];
+        float v = lrelu_f(acc * scale, slope);
+        if (mask_src != nullptr && !(DT<T>::to_f(mask_src[idx]) > 0.f)) v *= mask_slope;
+        if (out_dtype == PG_BF16)
+            reinterpret_cast<__nv_bfloat16*>(y)[idx] = __float2bfloat16_rn(v);
+        else
+            reinterpret_cast<float*>(y)[idx] = (sizeof(T) == 4 && out_dtype == PG_F32) ? DT<float>::from_f(v) : v;
+    }
+}
+
+static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+template <typename T, int BLOCK_N>
+static int launch_tc(const pg_conv_params* p, cudaStream_t stream) {
+    using Cfg = ConvCfg<BLOCK_N>;
+    constexpr int BK = 128 / sizeof(T);
+    ConvKArgs a;
+    a.bias = p->bias;
+    a.mask_src = p->mask_src;
+    a.y = p->y;
+    a.B = p->B; a.H = p->H; a.W = p->W; a.N = p->N;
+    a.BW = p->W < 128 ? p->W : 128;
+    a.BH = p->H < (128 / a.BW) ? p->H : (128 / a.BW);
+    a.BB = 128 / (a.BW * a.BH);
+    a.tiles_w = p->W / a.BW;
+    a.tiles_h = p->H / a.BH;
+    a.tiles_b = (p->B + a.BB - 1) / a.BB;
+    a.tiles_n = p->N / BLOCK_N;
+    a.kc_per_tap = p->C / BK;
+    a.taps = p->taps;
+    a.out_dtype = p->out_dtype;
+    a.scale = p->scale; a.slope = p->slope; a.mask_slope = p->mask_slope;
+
+    const uint64_t es = sizeof(T);
+    CUtensorMap tx, tw;
+    {
+        uint64_t dims[4] = {(uint64_t)p->C, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
+        uint64_t strides[3] = {(uint64_t)p->C * es, (uint64_t)p->W * p->C * es, (uint64_t)p->H * p->W * p->C * es};
+        uint32_t box[4] = {(uint32_t)BK, (uint32_t)a.BW, (uint32_t)a.BH, (uint32_t)a.BB};
+        int rc = encode_tmap(&tx, DT<T>::kEnum, 4, p->x, dims, strides, box, 128);
+        if (rc != PG_OK) return rc;
+    }
+    {
+        const uint64_t K = (uint64_t)p->taps * p->C;
+        uint64_t dims[2] = {K, (uint64_t)p->N};
+        uint64_t strides[1] = {K * es};
+        uint32_t box[2] = {(uint32_t)BK, (uint32_t)BLOCK_N};
+        int rc = encode_tmap(&tw, DT<T>::kEnum, 2, p->wp, dims, strides, box, 128);
+        if (rc != PG_OK) return rc;
+    }
+    auto kern = conv_gemm_kernel<T, BLOCK_N>;
+    static bool attr_done = false;   // per template instantiation
+    if (!attr_done) {
+        PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        attr_done = true;
+    }
+    const int num_tiles = a.tiles_w * a.tiles_h * a.tiles_b * a.tiles_n;
+    int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+    kern<<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(tx, tw, a);
+    PG_LAUNCH_CHECK();
+    g_tc_launches++;
+    return PG_OK;
+}
+
+template <typename T>
+static int conv_dispatch(const pg_conv_params* p, cudaStream_t stream) {
+    constexpr int BK = 128 / sizeof(T);
+    const bool tc_ok = g_conv_backend == PG_BACKEND_AUTO && is_pow2(p->H) && is_pow2(p->W) && (p->C % BK == 0) &&
+                       (p->N % 32 == 0) && (p->taps == 1 || p->taps == 9) &&
+                       (reinterpret_cast<uintptr_t>(p->x) % 16 == 0) && (reinterpret_cast<uintptr_t>(p->wp) % 16 == 0) &&
+                       (reinterpret_cast<uintptr_t>(p->y) % 16 == 0) &&
+                       (p->mask_src == nullptr || reinterpret_cast<uintptr_t>(p->mask_src) % 16 == 0);
+    if (tc_ok) {
+        // largest N tile that still yields enough CTAs to occupy the machine
+        const int bw = p->W < 128 ? p->W : 128;
+        const int bh = p->H < (128 / bw) ? p->H : (128 / bw);
+        const int bb = 128 / (bw * bh);
+        const long long m_tiles = (long long)(p->W / bw) * (p->H / bh) * ((p->B + bb - 1) / bb);
+        const int sms = num_sms();
+        int bn = 32;
+        const int cands[4] = {256, 128, 64, 32};
+        for (int i = 0; i < 4; ++i) {
+            if (p->N % cands[i] != 0) continue;
+            bn = cands[i];
+            if (m_tiles * (p->N / cands[i]) >= sms) break;
+        }
+        switch (bn) {
+            case 256: return launch_tc<T, 256>(p, stream);
+            case 128: return launch_tc<T, 128>(p, stream);
+            case 64: return launch_tc<T, 64>(p, stream);
+            default: return launch_tc<T, 32>(p, stream);
+        }
+    }
+    const long long total = (long long)p->B * p->H * p->W * p->N;
+    if (total == 0) return PG_OK;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148LL * 32) blocks = 148LL * 32;
+    conv_direct_kernel<T><<<(int)blocks, 256, 0, stream>>>(
+        reinterpret_cast<const T*>(p->x), reinterpret_cast<const T*>(p->wp), p->bias,
+        reinterpret_cast<const T*>(p->mask_src), p->y, p->B, p->H, p->W, p->C, p->N, p->taps, p->out_dtype, p->scale,
+        p->slope, p->mask_slope);
+    PG_LAUNCH_CHECK();
+    g_simt_launches++;
+    return PG_OK;
+}
+
+}  // namespace pg
+
+extern "C" int pggan_conv_fprop(const pg_conv_params* p, void* stream) {
+    using namespace pg;
+    PG_CHECK(p != nullptr, PG_ERR_ARG, "pggan_conv_fprop: null params");
+    PG_CHECK(p->x && p->wp && p->y, PG_ERR_ARG, "pggan_conv_fprop: null tensor pointer");
+    PG_CHECK(p->B > 0 && p->H > 0 && p->W > 0 && p->C > 0 && p->N > 0, PG_ERR_ARG,
+             "pggan_conv_fprop: bad dims B=%d H=%d W=%d C=%d N=%d", p->B, p->H, p->W, p->C, p->N);
+    PG_CHECK(p->taps == 1 || p->taps == 9, PG_ERR_ARG, "pggan_conv_fprop: taps must be 1 or 9 (got %d)", p->taps);
+    PG_CHECK(p->dtype == PG_BF16 || p->dtype == PG_F32, PG_ERR_ARG, "pggan_conv_fprop: bad dtype %d", p->dtype);
+    PG_CHECK(p->out_dtype == PG_BF16 || p->out_dtype == PG_F32 || p->out_dtype == PG_F32_RAW, PG_ERR_ARG,
+             "pggan_conv_fprop: bad out_dtype %d", p->out_dtype);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (p->dtype == PG_BF16) return conv_dispatch<__nv_bfloat16>(p, s);
+    return conv_dispatch<float>(p, s);
+}

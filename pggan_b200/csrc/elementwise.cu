@@ -1,0 +1,475 @@
+// Vectorised elementwise / reduction kernels on NHWC feature maps: LeakyReLU mask, nearest-2x
+// up-sampling, 2x2 pooling (+ fade blend), axpby, pixel norm fwd/bwd, column sums, weight (un)packing.
+// All are HBM-bound: 16-byte accesses, grid sized in multiples of the SM count, fp32 math.
+#include "common.cuh"
+
+#include <atomic>
+
+namespace pg {
+
+extern std::atomic<long long> g_other_launches;
+
+static inline int ew_grid(long long work_items, int threads) {
+    long long blocks = (work_items + threads - 1) / threads;
+    const long long cap = static_cast<long long>(num_sms()) * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return static_cast<int>(blocks);
+}
+
+template <typename T> struct V16 {
+    static constexpr int N = 16 / sizeof(T);
+    uint4 raw;
+    __device__ __forceinline__ float get(int i) const { return DT<T>::to_f(reinterpret_cast<const T*>(&raw)[i]); }
+    __device__ __forceinline__ void set(int i, float v) { reinterpret_cast<T*>(&raw)[i] = DT<T>::from_f(v); }
+};
+template <typename T> __device__ __forceinline__ V16<T> ld16(const T* p) {
+    V16<T> v;
+    v.raw = __ldg(reinterpret_cast<const uint4*>(p));
+    return v;
+}
+template <typename T> __device__ __forceinline__ void st16(T* p, const V16<T>& v) {
+    *reinterpret_cast<uint4*>(p) = v.raw;
+}
+
+#define GRID_STRIDE(i, n)                                                                      \
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < (n); \
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+
+// ------------------------------------------------------------------------- lrelu mask multiply
+template <typename T>
+__global__ void lrelu_mask_mul_kernel(const T* __restrict__ g, const T* __restrict__ y, T* __restrict__ out,
+                                      long long nvec, long long n, float slope) {
+    constexpr int VN = V16<T>::N;
+    GRID_STRIDE(i, nvec) {
+        V16<T> gv = ld16(g + i * VN), yv = ld16(y + i * VN), o;
+#pragma unroll
+        for (int e = 0; e < VN; ++e) o.set(e, yv.get(e) > 0.f ? gv.get(e) : gv.get(e) * slope);
+        st16(out + i * VN, o);
+    }
+    // scalar tail
+    const long long tail0 = nvec * VN;
+    GRID_STRIDE(i, n - tail0) {
+        const long long k = tail0 + i;
+        const float gv = DT<T>::to_f(g[k]);
+        out[k] = DT<T>::from_f(DT<T>::to_f(y[k]) > 0.f ? gv : gv * slope);
+    }
+}
+
+// --------------------------------------------------------------------------------- axpby
+template <typename T>
+__global__ void axpby_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, long long nvec,
+                             long long n, float sa, float sb) {
+    constexpr int VN = V16<T>::N;
+    GRID_STRIDE(i, nvec) {
+        V16<T> av = ld16(a + i * VN), o;
+        if (b != nullptr) {
+            V16<T> bv = ld16(b + i * VN);
+#pragma unroll
+            for (int e = 0; e < VN; ++e) o.set(e, sa * av.get(e) + sb * bv.get(e));
+        } else {
+#pragma unroll
+            for (int e = 0; e < VN; ++e) o.set(e, sa * av.get(e));
+        }
+        st16(out + i * VN, o);
+    }
+    const long long tail0 = nvec * VN;
+    GRID_STRIDE(i, n - tail0) {
+        const long long k = tail0 + i;
+        float v = sa * DT<T>::to_f(a[k]);
+        if (b != nullptr) v += sb * DT<T>::to_f(b[k]);
+        out[k] = DT<T>::from_f(v);
+    }
+}
+
+// ------------------------------------------------------------------------ upsample / pool
+// one thread per (input pixel, 16-byte channel vector): read once, write the 2x2 block
+template <typename T>
+__global__ void upsample2x_kernel(const T* __restrict__ x, T* __restrict__ out, int B, int H, int W, int CV,
+                                  float scale) {
+    constexpr int VN = V16<T>::N;
+    const long long total = static_cast<long long>(B) * H * W * CV;
+    const long long C = static_cast<long long>(CV) * VN;
+    GRID_STRIDE(i, total) {
+        const int cv = static_cast<int>(i % CV);
+        const long long pix = i / CV;
+        const int w = static_cast<int>(pix % W);
+        const int h = static_cast<int>((pix / W) % H);
+        const long long b = pix / (static_cast<long long>(W) * H);
+        V16<T> v = ld16(x + pix * C + cv * VN);
+        if (scale != 1.f) {
+#pragma unroll
+            for (int e = 0; e < VN; ++e) v.set(e, v.get(e) * scale);
+        }
+        T* o = out + ((b * 2 * H + 2 * h) * 2 * W + 2 * w) * C + cv * VN;
+        st16(o, v);
+        st16(o + C, v);
+        st16(o + 2 * W * C, v);
+        st16(o + 2 * W * C + C, v);
+    }
+}
+
+// one thread per (output pixel, channel vector); x is [B,H,W,C], out [B,H/2,W/2,C]
+template <typename T>
+__global__ void pool2x2_kernel(const T* __restrict__ x, const T* __restrict__ blend, T* __restrict__ out, int B, int H,
+                               int W, int CV, float scale, float alpha) {
+    constexpr int VN = V16<T>::N;
+    const int Ho = H / 2, Wo = W / 2;
+    const long long total = static_cast<long long>(B) * Ho * Wo * CV;
+    const long long C = static_cast<long long>(CV) * VN;
+    GRID_STRIDE(i, total) {
+        const int cv = static_cast<int>(i % CV);
+        const long long pix = i / CV;
+        const int w = static_cast<int>(pix % Wo);
+        const int h = static_cast<int>((pix / Wo) % Ho);
+        const long long b = pix / (static_cast<long long>(Wo) * Ho);
+        const T* p = x + ((b * H + 2 * h) * W + 2 * w) * C + cv * VN;
+        V16<T> v00 = ld16(p), v01 = ld16(p + C), v10 = ld16(p + W * C), v11 = ld16(p + W * C + C), o;
+        if (blend != nullptr) {
+            V16<T> bl = ld16(blend + pix * C + cv * VN);
+#pragma unroll
+            for (int e = 0; e < VN; ++e) {
+                const float s = (((v00.get(e) + v01.get(e)) + v10.get(e)) + v11.get(e)) * scale;
+                o.set(e, (1.f - alpha) * bl.get(e) + alpha * s);
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < VN; ++e) o.set(e, (((v00.get(e) + v01.get(e)) + v10.get(e)) + v11.get(e)) * scale);
+        }
+        st16(out + pix * C + cv * VN, o);
+    }
+}
+
+// --------------------------------------------------------------------------- pixel norm
+// one warp per pixel row of C channels (C % VN == 0); row cached in registers when C <= 32*VN*MAXV
+template <typename T, int MAXV>
+__global__ void pixelnorm_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, float* __restrict__ rnorm,
+                                     long long M, int C, float eps) {
+    constexpr int VN = V16<T>::N;
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+    const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    const int nvec = C / VN;
+    for (long long m = warp0; m < M; m += nwarps) {
+        const T* xr = x + m * C;
+        V16<T> v[MAXV];
+        float ss = 0.f;
+#pragma unroll
+        for (int k = 0; k < MAXV; ++k) {
+            const int vi = lane + 32 * k;
+            if (vi < nvec) {
+                v[k] = ld16(xr + vi * VN);
+#pragma unroll
+                for (int e = 0; e < VN; ++e) ss += v[k].get(e) * v[k].get(e);
+            }
+        }
+        ss = warp_sum(ss);
+        const float r = rsqrtf(ss / C + eps);
+        if (lane == 0 && rnorm != nullptr) rnorm[m] = r;
+        T* yr = y + m * C;
+#pragma unroll
+        for (int k = 0; k < MAXV; ++k) {
+            const int vi = lane + 32 * k;
+            if (vi < nvec) {
+                V16<T> o;
+#pragma unroll
+                for (int e = 0; e < VN; ++e) o.set(e, v[k].get(e) * r);
+                st16(yr + vi * VN, o);
+            }
+        }
+    }
+}
+
+// gx = r * (gy - y * mean_c(gy*y)), then optional LeakyReLU mask by the sign of y
+template <typename T, int MAXV>
+__global__ void pixelnorm_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ y, const float* __restrict__ rnorm,
+                                     T* __restrict__ gx, long long M, int C, float act_slope) {
+    constexpr int VN = V16<T>::N;
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+    const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    const int nvec = C / VN;
+    for (long long m = warp0; m < M; m += nwarps) {
+        V16<T> g[MAXV], yv[MAXV];
+        float dot = 0.f;
+#pragma unroll
+        for (int k = 0; k < MAXV; ++k) {
+            const int vi = lane + 32 * k;
+            if (vi < nvec) {
+                g[k] = ld16(gy + m * C + vi * VN);
+                yv[k] = ld16(y + m * C + vi * VN);
+#pragma unroll
+                for (int e = 0; e < VN; ++e) dot += g[k].get(e) * yv[k].get(e);
+            }
+        }
+        dot = warp_sum(dot) / C;
+        const float r = rnorm[m];
+#pragma unroll
+        for (int k = 0; k < MAXV; ++k) {
+            const int vi = lane + 32 * k;
+            if (vi < nvec) {
+                V16<T> o;
+#pragma unroll
+                for (int e = 0; e < VN; ++e) {
+                    const float yy = yv[k].get(e);
+                    float t = r * (g[k].get(e) - yy * dot);
+                    if (!(yy > 0.f)) t *= act_slope;
+                    o.set(e, t);
+                }
+                st16(gx + m * C + vi * VN, o);
+            }
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------- column sum
+// out[c] += scale * sum_m g[m,c].  Each block owns a slab of rows; threads are (ty row-lane, tx
+// channel-vector lane); per-thread partial sums are combined through shared memory and one
+// atomicAdd per (block, channel) goes to global memory.
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ g, float* __restrict__ out, long long M, int C, float scale,
+                              int TX, long long rows_per_block) {
+    constexpr int VN = V16<T>::N;
+    __shared__ float red[256 * VN];
+    const int CV = C / VN;
+    const int TY = blockDim.x / TX;
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    const long long r0 = blockIdx.x * rows_per_block;
+    long long r1 = r0 + rows_per_block;
+    if (r1 > M) r1 = M;
+    for (int cv0 = 0; cv0 < CV; cv0 += TX) {
+        const int cv = cv0 + tx;
+        float acc[VN];
+#pragma unroll
+        for (int e = 0; e < VN; ++e) acc[e] = 0.f;
+        if (cv < CV) {
+            for (long long m = r0 + ty; m < r1; m += TY) {
+                V16<T> v = ld16(g + m * C + cv * VN);
+#pragma unroll
+                for (int e = 0; e < VN; ++e) acc[e] += v.get(e);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < VN; ++e) red[(ty * TX + tx) * VN + e] = acc[e];
+        __syncthreads();
+        if (ty == 0 && cv < CV) {
+#pragma unroll
+            for (int e = 0; e < VN; ++e) {
+                float t = 0.f;
+                for (int yy = 0; yy < TY; ++yy) t += red[(yy * TX + tx) * VN + e];
+                atomicAdd(out + cv * VN + e, t * scale);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------- weight packing
+template <typename T>
+__global__ void pack_weight_kernel(const float* __restrict__ in, T* __restrict__ out, int n2, int taps, int c, int c_pad,
+                                   long long total, long long base, long long s_n1, long long s_n2, long long s_t,
+                                   long long s_c) {
+    GRID_STRIDE(i, total) {
+        const int cc = static_cast<int>(i % c_pad);
+        const long long r = i / c_pad;
+        const int t = static_cast<int>(r % taps);
+        const long long n = r / taps;
+        float v = 0.f;
+        if (cc < c) v = in[base + (n / n2) * s_n1 + (n % n2) * s_n2 + t * s_t + cc * s_c];
+        out[i] = DT<T>::from_f(v);
+    }
+}
+
+__global__ void unpack_wgrad_kernel(const float* __restrict__ in, float* __restrict__ out, int n2, int taps, int c,
+                                    int c_pad, long long total, long long base, long long s_n1, long long s_n2,
+                                    long long s_t, long long s_c, float scale, int accumulate) {
+    // iterate in OUTPUT-friendly order is impossible in general (arbitrary strides); param-sized, L2-resident
+    GRID_STRIDE(i, total) {
+        const int cc = static_cast<int>(i % c);
+        const long long r = i / c;
+        const int t = static_cast<int>(r % taps);
+        const long long n = r / taps;
+        const float v = in[(n * taps + t) * c_pad + cc] * scale;
+        float* o = out + base + (n / n2) * s_n1 + (n % n2) * s_n2 + t * s_t + cc * s_c;
+        *o = accumulate ? (*o + v) : v;
+    }
+}
+
+}  // namespace pg
+
+using namespace pg;
+
+#define DISPATCH_T(dtype, ...)                                       \
+    do {                                                             \
+        if ((dtype) == PG_BF16) {                                    \
+            using T = __nv_bfloat16;                                 \
+            __VA_ARGS__;                                             \
+        } else if ((dtype) == PG_F32) {                              \
+            using T = float;                                         \
+            __VA_ARGS__;                                             \
+        } else {                                                     \
+            pg::set_error("bad dtype %d", (int)(dtype));             \
+            return PG_ERR_ARG;                                       \
+        }                                                            \
+    } while (0)
+
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" int pggan_lrelu_mask_mul(const void* g, const void* y, void* out, int64_t n, float slope, int dtype,
+                                    void* stream) {
+    PG_CHECK(g && y && out && n >= 0, PG_ERR_ARG, "pggan_lrelu_mask_mul: bad args");
+    PG_CHECK(al16(g) && al16(y) && al16(out), PG_ERR_ARG, "pggan_lrelu_mask_mul: pointers must be 16-byte aligned");
+    if (n == 0) return PG_OK;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    DISPATCH_T(dtype, {
+        const long long nvec = n / V16<T>::N;
+        lrelu_mask_mul_kernel<T><<<ew_grid(nvec + 1, 256), 256, 0, s>>>((const T*)g, (const T*)y, (T*)out, nvec, n, slope);
+    });
+    PG_LAUNCH_CHECK();
+    g_other_launches++;
+    return PG_OK;
+}
+
+extern "C" int pggan_axpby(const void* a, const void* b, void* out, int64_t n, float sa, float sb, int dtype,
+                           void* stream) {
+    PG_CHECK(a && out && n >= 0, PG_ERR_ARG, "pggan_axpby: bad args");
+    PG_CHECK(al16(a) && al16(out) && (b == nullptr || al16(b)), PG_ERR_ARG, "pggan_axpby: pointers must be 16-byte aligned");
+    if (n == 0) return PG_OK;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    DISPATCH_T(dtype, {
+        const long long nvec = n / V16<T>::N;
+        axpby_kernel<T><<<ew_grid(nvec + 1, 256), 256, 0, s>>>((const T*)a, (const T*)b, (T*)out, nvec, n, sa, sb);
+    });
+    PG_LAUNCH_CHECK();
+    g_other_launches++;
+    return PG_OK;
+}
+
+extern "C" int pggan_upsample2x(const void* x, void* out, int B, int H, int W, int C, float scale, int dtype,
+                                void* stream) {
+    PG_CHECK(x && out && B > 0 && H > 0 && W > 0 && C > 0, PG_ERR_ARG, "pggan_upsample2x: bad args");
+    PG_CHECK(al16(x) && al16(out), PG_ERR_ARG, "pggan_upsample2x: pointers must be 16-byte aligned");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    DISPATCH_T(dtype, {
+        PG_CHECK(C % V16<T>::N == 0, PG_ERR_UNSUPPORTED, "pggan_upsample2x: C=%d must be a multiple of %d", C, V16<T>::N);
+        const int CV = C / V16<T>::N;
+        upsample2x_kernel<T><<<ew_grid((long long)B * H * W * CV, 256), 256, 0, s>>>((const T*)x, (T*)out, B, H, W, CV, scale);
+    });
+    PG_LAUNCH_CHECK();
+    g_other_launches++;
+    return PG_OK;
+}
+
+extern "C" int pggan_pool2x2(const void* x, const void* blend_with, void* out, int B, int H, int W, int C, float scale,
+                             float alpha, int dtype, void* stream) {
+    PG_CHECK(x && out && B > 0 && H > 1 && W > 1 && C > 0, PG_ERR_ARG, "pggan_pool2x2: bad args");
+    PG_CHECK(H % 2 == 0 && W % 2 == 0, PG_ERR_ARG, "pggan_pool2x2: H=%d W=%d must be even", H, W);
+    PG_CHECK(al16(x) && al16(out) && (blend_with == nullptr || al16(blend_with)), PG_ERR_ARG,
+             "pggan_pool2x2: pointers must be 16-byte aligned");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    DISPATCH_T(dtype, {
+        PG_CHECK(C % V16<T>::N == 0, PG_ERR_UNSUPPORTED, "pggan_pool2x2: C=%d must be a multiple of %d", C, V16<T>::N);
+        const int CV = C / V16<T>::N;
+        pool2x2_kernel<T><<<ew_grid((long long)B * (H / 2) * (W / 2) * CV, 256), 256, 0, s>>>(
+            (const T*)x, (const T*)blend_with, (T*)out, B, H, W, CV, scale, alpha);
+    });
+    PG_LAUNCH_CHECK();
+    g_other_launches++;
+    return PG_OK;
+}
+
+extern "C" int pggan_pixelnorm_fwd(const void* x, void* y, float* rnorm, int64_t m, int C, float eps, int dtype,
+                                   void* stream) {
+    PG_CHECK(x && y && m >= 0 && C > 0, PG_ERR_ARG, "pggan_pixelnorm_fwd: bad args");
+    PG_CHECK(al16(x) && al16(y), PG_ERR_ARG, "pggan_pixelnorm_fwd: pointers must be 16-byte aligned");
+    if (m == 0) return PG_OK;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    DISPATCH_T(dtype, {
+        constexpr int VN = V16<T>::N;
+        PG_CHECK(C % VN == 0 && C <= 32 * VN * 4, PG_ERR_UNSUPPORTED,
+                 "pggan_pixelnorm_fwd: C=%d must be a multiple of %d and <= %d", C, VN, 32 * VN * 4);
+        const int grid = ew_grid(m * 32, 256);
+        if (C <= 32 * VN)
+            pixelnorm_fwd_kernel<T, 1><<<grid, 256, 0, s>>>((const T*)x, (T*)y, rnorm, m, C, eps);
+        else if (C <= 64 * VN)
+            pixelnorm_fwd_kernel<T, 2><<<grid, 256, 0, s>>>((const T*)x, (T*)y, rnorm, m, C, eps);
+        else
+            pixelnorm_fwd_kernel<T, 4><<<grid, 256, 0, s>>>((const T*)x, (T*)y, rnorm, m, C, eps);
+    });
+    PG_LAUNCH_CHECK();
+    g_other_launches++;
+    return PG_OK;
+}
+
+extern "C" int pggan_pixelnorm_bwd(const void* gy, const void* y, const float* rnorm, void* gx, int64_t m, int C,
+                                   float act_slope, int dtype, void* stream) {
+    PG_CHECK(gy && y && rnorm && gx && m >= 0 && C > 0, PG_ERR_ARG, "pggan_pixelnorm_bwd: bad args");
+    PG_CHECK(al16(gy) && al16(y) && al16(gx), PG_ERR_ARG, "pggan_pixelnorm_bwd: pointers must be 16-byte aligned");
+    if (m == 0) return PG_OK;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    DISPATCH_T(dtype, {
+        constexpr int VN = V16<T>::N;
+        PG_CHECK(C % VN == 0 && C <= 32 * VN * 4, PG_ERR_UNSUPPORTED,
+                 "pggan_pixelnorm_bwd: C=%d must be a multiple of %d and <= %d", C, VN, 32 * VN * 4);
+        const int grid = ew_grid(m * 32, 256);
+        if (C <= 32 * VN)
+            pixelnorm_bwd_kernel<T, 1><<<grid, 256, 0, s>>>((const T*)gy, (const T*)y, rnorm, (T*)gx, m, C, act_slope);
+        else if (C <= 64 * VN)
+            pixelnorm_bwd_kernel<T, 2><<<grid, 256, 0, s>>>((const T*)gy, (const T*)y, rnorm, (T*)gx, m, C, act_slope);
+        else
+            pixelnorm_bwd_kernel<T, 4><<<grid, 256, 0, s>>>((const T*)gy, (const T*)y, rnorm, (T*)gx, m, C, act_slope);
+    });
+    PG_LAUNCH_CHECK();
+    g_other_launches++;
+    return PG_OK;
+}
+
+extern "C" int pggan_colsum(const void* g, float* out, int64_t m, int C, float scale, int dtype, void* stream) {
+    PG_CHECK(g && out && m >= 0 && C > 0, PG_ERR_ARG, "pggan_colsum: bad args");
+    PG_CHECK(al16(g), PG_ERR_ARG, "pggan_colsum: pointer must be 16-byte aligned");
+    if (m == 0) return PG_OK;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    DISPATCH_T(dtype, {
+        constexpr int VN = V16<T>::N;
+        PG_CHECK(C % VN == 0, PG_ERR_UNSUPPORTED, "pggan_colsum: C=%d must be a multiple of %d", C, VN);
+        const int CV = C / VN;
+        int TX = 1;
+        while (TX * 2 <= CV && TX * 2 <= 256) TX *= 2;
+        long long blocks = (m + 63) / 64;
+        const long long cap = (long long)num_sms() * 4;
+        if (blocks > cap) blocks = cap;
+        const long long rows_per_block = (m + blocks - 1) / blocks;
+        const int grid = (int)((m + rows_per_block - 1) / rows_per_block);
+        colsum_kernel<T><<<grid, 256, 0, s>>>((const T*)g, out, m, C, scale, TX, rows_per_block);
+    });
+    PG_LAUNCH_CHECK();
+    g_other_launches++;
+    return PG_OK;
+}
+
+extern "C" int pggan_pack_weight(const float* in, void* out, int dtype, int n1, int n2, int taps, int c, int c_pad,
+                                 int64_t base, int64_t s_n1, int64_t s_n2, int64_t s_t, int64_t s_c, void* stream) {
+    PG_CHECK(in && out && n1 > 0 && n2 > 0 && taps > 0 && c > 0 && c_pad >= c, PG_ERR_ARG, "pggan_pack_weight: bad args");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const long long total = (long long)n1 * n2 * taps * c_pad;
+    DISPATCH_T(dtype, {
+        pack_weight_kernel<T><<<ew_grid(total, 256), 256, 0, s>>>(in, (T*)out, n2, taps, c, c_pad, total, base, s_n1, s_n2,
+                                                                 s_t, s_c);
+    });
+    PG_LAUNCH_CHECK();
+    g_other_launches++;
+    return PG_OK;
+}
+
+extern "C" int pggan_unpack_wgrad(const float* in, float* out, int n1, int n2, int taps, int c, int c_pad, int64_t base,
+                                  int64_t s_n1, int64_t s_n2, int64_t s_t, int64_t s_c, float scale, int accumulate,
+                                  void* stream) {
+    PG_CHECK(in && out && n1 > 0 && n2 > 0 && taps > 0 && c > 0 && c_pad >= c, PG_ERR_ARG, "pggan_unpack_wgrad: bad args");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const long long total = (long long)n1 * n2 * taps * c;
+    unpack_wgrad_kernel<<<ew_grid(total, 256), 256, 0, s>>>(in, out, n2, taps, c, c_pad, total, base, s_n1, s_n2, s_t, s_c,
+                                                            scale, accumulate);
+    PG_LAUNCH_CHECK();
+    g_other_launches++;
+    return PG_OK;
+}

@@ -1,0 +1,149 @@
+// WGAN-GP / R1 reductions over fp32 image gradients and the fused multi-tensor Adam step.
+// Reference: pggan/loss.py:85-87 (per-sample ||grad||_2, (n-1)^2 sum), pggan/loss.py:98-100 (drift),
+// lib/loss.py:132-134 (R1), torch.optim.Adam as configured in lib/model.py:95-97.
+#include "common.cuh"
+
+#include <atomic>
+
+namespace pg {
+extern std::atomic<long long> g_other_launches;
+
+__global__ void rows_sumsq_kernel(const float* __restrict__ g, float* __restrict__ sumsq, long long n,
+                                  long long per_block) {
+    __shared__ float red[32];
+    const int b = blockIdx.y;
+    const float* row = g + static_cast<long long>(b) * n;
+    const long long k0 = blockIdx.x * per_block;
+    long long k1 = k0 + per_block;
+    if (k1 > n) k1 = n;
+    float acc = 0.f;
+    // rows start 16-byte aligned when n % 4 == 0; otherwise fall back to scalar loads
+    if ((n & 3) == 0 && (k0 & 3) == 0) {
+        const long long v1 = k0 + ((k1 - k0) & ~3LL);
+        for (long long k = k0 + 4LL * threadIdx.x; k < v1; k += 4LL * blockDim.x) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(row + k));
+            acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        }
+        for (long long k = v1 + threadIdx.x; k < k1; k += blockDim.x) acc += row[k] * row[k];
+    } else {
+        for (long long k = k0 + threadIdx.x; k < k1; k += blockDim.x) acc += row[k] * row[k];
+    }
+    const float tot = block_sum(acc, red);
+    if (threadIdx.x == 0) atomicAdd(sumsq + b, tot);
+}
+
+__global__ void rows_scale_kernel(const float* __restrict__ g, const float* __restrict__ coef, float* __restrict__ out,
+                                  long long n, long long total) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        out[i] = g[i] * __ldg(coef + i / n);
+}
+
+__global__ void gp_finalize_kernel(const float* __restrict__ sumsq, const float* __restrict__ pred,
+                                   float* __restrict__ res, float* __restrict__ coef, int B, float w_gp, float w_drift) {
+    __shared__ float red[32];
+    float gp = 0.f, dr = 0.f;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        const float nrm = sqrtf(sumsq[b]);
+        gp += (nrm - 1.f) * (nrm - 1.f);
+        if (coef != nullptr) coef[b] = w_gp * 2.f * (nrm - 1.f) / nrm;
+        if (pred != nullptr) dr += pred[b] * pred[b];
+    }
+    gp = block_sum(gp, red);
+    dr = block_sum(dr, red);
+    if (threadIdx.x == 0) {
+        res[0] = gp * w_gp;
+        res[1] = dr * w_drift;
+    }
+}
+
+// ----------------------------------------------------------------------------------------- Adam
+constexpr int kAdamChunk = 16384;    // elements per block
+
+__global__ void adam_kernel(const pg_adam_entry* __restrict__ table, const int32_t* __restrict__ chunk_tensor,
+                            const int64_t* __restrict__ chunk_offset, const int64_t* __restrict__ step, float lr,
+                            float beta1, float beta2, float eps, float grad_scale) {
+    __shared__ float s_c[2];
+    if (threadIdx.x == 0) {
+        const double t = static_cast<double>(*step + 1);
+        s_c[0] = static_cast<float>(1.0 - pow(static_cast<double>(beta1), t));
+        s_c[1] = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), t)));
+    }
+    __syncthreads();
+    const float bc1 = s_c[0], bc2_sqrt = s_c[1];
+    const float step_size = lr / bc1;
+    const pg_adam_entry e = table[chunk_tensor[blockIdx.x]];
+    const int64_t off = chunk_offset[blockIdx.x];
+    int64_t end = off + kAdamChunk;
+    if (end > e.numel) end = e.numel;
+    for (int64_t i = off + threadIdx.x; i < end; i += blockDim.x) {
+        const float g = e.grad[i] * grad_scale;
+        const float m = beta1 * e.exp_avg[i] + (1.f - beta1) * g;
+        const float v = beta2 * e.exp_avg_sq[i] + (1.f - beta2) * g * g;
+        e.exp_avg[i] = m;
+        e.exp_avg_sq[i] = v;
+        const float denom = sqrtf(v) / bc2_sqrt + eps;
+        e.param[i] = e.param[i] - step_size * (m / denom);
+    }
+}
+__global__ void adam_incr_step_kernel(int64_t* step) { *step += 1; }
+
+}  // namespace pg
+
+using namespace pg;
+
+extern "C" int pggan_rows_sumsq(const float* g, float* sumsq, int B, int64_t n, void* stream) {
+    PG_CHECK(g && sumsq && B > 0 && n > 0, PG_ERR_ARG, "pggan_rows_sumsq: bad args");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    long long bx = (n + 8191) / 8192;
+    const long long cap = ((long long)num_sms() * 8 + B - 1) / B;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    long long per_block = (n + bx - 1) / bx;
+    per_block = (per_block + 3) & ~3LL;
+    bx = (n + per_block - 1) / per_block;
+    rows_sumsq_kernel<<<dim3((unsigned)bx, (unsigned)B), 256, 0, s>>>(g, sumsq, n, per_block);
+    PG_LAUNCH_CHECK();
+    g_other_launches++;
+    return PG_OK;
+}
+
+extern "C" int pggan_rows_scale(const float* g, const float* coef, float* out, int B, int64_t n, void* stream) {
+    PG_CHECK(g && coef && out && B > 0 && n > 0, PG_ERR_ARG, "pggan_rows_scale: bad args");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const long long total = (long long)B * n;
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    rows_scale_kernel<<<(int)blocks, 256, 0, s>>>(g, coef, out, n, total);
+    PG_LAUNCH_CHECK();
+    g_other_launches++;
+    return PG_OK;
+}
+
+extern "C" int pggan_gp_finalize(const float* sumsq, const float* pred, float* res, float* coef, int B, float w_gp,
+                                 float w_drift, void* stream) {
+    PG_CHECK(sumsq && res && B > 0, PG_ERR_ARG, "pggan_gp_finalize: bad args");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    gp_finalize_kernel<<<1, 256, 0, s>>>(sumsq, pred, res, coef, B, w_gp, w_drift);
+    PG_LAUNCH_CHECK();
+    g_other_launches++;
+    return PG_OK;
+}
+
+extern "C" int pggan_adam_chunk_size(void) { return pg::kAdamChunk; }
+
+extern "C" int pggan_adam_step(const pg_adam_entry* table, int n_tensors, int64_t total_chunks,
+                               const int32_t* chunk_tensor, const int64_t* chunk_offset, int64_t* step, float lr,
+                               float beta1, float beta2, float eps, float grad_scale, void* stream) {
+    PG_CHECK(table && chunk_tensor && chunk_offset && step && n_tensors > 0 && total_chunks > 0, PG_ERR_ARG,
+             "pggan_adam_step: bad args");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    adam_kernel<<<(unsigned)total_chunks, 256, 0, s>>>(table, chunk_tensor, chunk_offset, step, lr, beta1, beta2, eps,
+                                                       grad_scale);
+    PG_LAUNCH_CHECK();
+    adam_incr_step_kernel<<<1, 1, 0, s>>>(step);
+    PG_LAUNCH_CHECK();
+    g_other_launches += 2;
+    return PG_OK;
+}

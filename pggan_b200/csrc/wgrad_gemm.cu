@@ -1,0 +1,350 @@
+// Weight-gradient GEMM on tcgen05 tensor cores, fed by TMA (split-K over pixels).
+//
+//   acc[n][tap][c] += sum_p g[p][n] * x[p + shift(tap)][c]
+//
+// The reduction runs over pixels, which are the OUTER dimension of both NHWC operands, so both
+// operands are "MN-major" for the tensor core: a stage holds BKP pixels x 128 B of channels per TMA
+// box (SWIZZLE_128B), and the UMMA descriptors walk K (pixels) in 8-row groups (SBO = 1024 B) and
+// MN (channels) in 128-byte spans (LBO = BKP*128 B).  The x box is shifted by the tap offset and
+// TMA's out-of-bounds zero fill provides the conv padding, exactly as in conv_gemm.cu.
+//
+// D tile: 128 output channels (g) x BLOCK_C input channels (x), fp32 in TMEM; epilogue adds the
+// partial sums into the dense fp32 accumulator with vector reductions (red.global.add.v4.f32).
+//
+// Replaces cuDNN wgrad / cuBLAS behind autograd's convolution_backward for
+// EqualizedConv2d/EqualizedLinear (reference lib/layers.py:60) and provides the
+// d/dW term of the double backward.
+#include "common.cuh"
+
+#include <atomic>
+
+namespace pg {
+
+extern std::atomic<long long> g_tc_launches, g_simt_launches;
+extern int g_conv_backend;
+
+constexpr int kWgThreads = 192;
+
+template <typename T, int BLOCK_C> struct WgCfg {
+    static constexpr int ES = sizeof(T);
+    static constexpr int UMMA_K = 32 / ES;             // pixels per MMA
+    static constexpr int BKP = 4 * UMMA_K;             // pixels per stage (64 bf16 / 32 fp32)
+    static constexpr int kGroupBytes = BKP * 128;      // one 128-byte channel span x BKP pixels
+    static constexpr int GA = 128 * ES / 128;          // channel spans of the g tile (128 rows of D)
+    static constexpr int GB = BLOCK_C * ES / 128;      // channel spans of the x tile
+    static constexpr int kStageBytes = (GA + GB) * kGroupBytes;
+    static constexpr int kStages = (196608 / kStageBytes) > 8 ? 8 : (196608 / kStageBytes);
+    static constexpr int kTmemCols = (2 * BLOCK_C < 32) ? 32 : 2 * BLOCK_C;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+    static constexpr int CPS = 128 / ES;               // channels per 128-byte span
+};
+
+struct WgKArgs {
+    float* acc;
+    int B, H, W, C, N, taps;
+    int PW, PH, PB;                 // pixel box of one stage
+    int chunks_w, chunks_h, chunks_b;
+    int tiles_n, tiles_c, splits, chunks_per_split;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <typename T, int BLOCK_C>
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_x,
+                  const WgKArgs a) {
+    using Cfg = WgCfg<T, BLOCK_C>;
+    constexpr bool kTF32 = (sizeof(T) == 4);
+    constexpr int kStages = Cfg::kStages;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tfull_bar = empty_bar + kStages;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_g);
+        tma_prefetch_desc(&tmap_x);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], 128);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int total_chunks = a.chunks_w * a.chunks_h * a.chunks_b;
+    const int num_units = a.taps * a.tiles_n * a.tiles_c * a.splits;
+
+    // unit -> (split, tap, n tile, c tile); c fastest so neighbouring CTAs share the g tile in L2
+    auto decode = [&](int unit, int& ct, int& nt, int& tap, int& k0, int& k1) {
+        ct = unit % a.tiles_c;
+        unit /= a.tiles_c;
+        nt = unit % a.tiles_n;
+        unit /= a.tiles_n;
+        tap = unit % a.taps;
+        const int sp = unit / a.taps;
+        k0 = sp * a.chunks_per_split;
+        k1 = k0 + a.chunks_per_split;
+        if (k1 > total_chunks) k1 = total_chunks;
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+                int ct, nt, tap, k0, k1;
+                decode(unit, ct, nt, tap, k0, k1);
+                int dh = 0, dw = 0;
+                if (a.taps == 9) {
+                    dh = tap / 3 - 1;
+                    dw = tap % 3 - 1;
+                }
+                for (int kc = k0; kc < k1; ++kc) {
+                    const int w0 = (kc % a.chunks_w) * a.PW;
+                    const int h0 = ((kc / a.chunks_w) % a.chunks_h) * a.PH;
+                    const int b0 = (kc / (a.chunks_w * a.chunks_h)) * a.PB;
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * Cfg::kStageBytes;
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+#pragma unroll
+                    for (int gidx = 0; gidx < Cfg::GA; ++gidx)
+                        tma_load_4d(sa + gidx * Cfg::kGroupBytes, &tmap_g, &full_bar[stage],
+                                    nt * 128 + gidx * Cfg::CPS, w0, h0, b0);
+                    uint8_t* sb = sa + Cfg::GA * Cfg::kGroupBytes;
+#pragma unroll
+                    for (int gidx = 0; gidx < Cfg::GB; ++gidx)
+                        tma_load_4d(sb + gidx * Cfg::kGroupBytes, &tmap_x, &full_bar[stage],
+                                    ct * BLOCK_C + gidx * Cfg::CPS, w0 + dw, h0 + dh, b0);
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(kTF32 ? 2 : 1, 1, 1, 128, BLOCK_C);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+                int ct, nt, tap, k0, k1;
+                decode(unit, ct, nt, tap, k0, k1);
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BLOCK_C;
+                for (int kc = k0; kc < k1; ++kc) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+                    const uint32_t sb = sa + Cfg::GA * Cfg::kGroupBytes;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t koff = k * Cfg::UMMA_K * 128;   // UMMA_K pixel rows of 128 B
+                        const uint64_t adesc = make_smem_desc(sa + koff, Cfg::kGroupBytes, 1024);
+                        const uint64_t bdesc = make_smem_desc(sb + koff, Cfg::kGroupBytes, 1024);
+                        umma_ss<kTF32>(d_tmem, adesc, bdesc, idesc, (kc > k0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(&tfull_bar[acc]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        int it = 0;
+        for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+            int ct, nt, tap, k0, k1;
+            decode(unit, ct, nt, tap, k0, k1);
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const int n = nt * 128 + row;
+            const bool valid = (n < a.N) && (k1 > k0);
+            float* dst = a.acc + (static_cast<size_t>(n) * a.taps + tap) * a.C + ct * BLOCK_C;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_C;
+#pragma unroll 1
+            for (int j = 0; j < BLOCK_C / 32; ++j) {
+                __syncwarp();
+                uint32_t r[32];
+                tmem_ld32(taddr + j * 32, r);
+                tmem_ld_wait();
+                if (valid) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        red_add_v4(dst + j * 32 + c * 4, __uint_as_float(r[c * 4 + 0]), __uint_as_float(r[c * 4 + 1]),
+                                   __uint_as_float(r[c * 4 + 2]), __uint_as_float(r[c * 4 + 3]));
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    }
+}
+
+// ----------------------------------------------------------------------------- SIMT direct kernel
+// 16x16 output tile per block, pixels split across blockIdx.x, partial sums via atomics.
+template <typename T>
+__global__ void wgrad_direct_kernel(const T* __restrict__ g, const T* __restrict__ x, float* __restrict__ acc, int B,
+                                    int H, int W, int C, int N, int taps, long long pix_per_block) {
+    __shared__ float gs[16][17], xs[16][17];
+    const long long P = static_cast<long long>(B) * H * W;
+    const long long p0 = blockIdx.x * pix_per_block;
+    long long p1 = p0 + pix_per_block;
+    if (p1 > P) p1 = P;
+    const int tap = blockIdx.y;
+    const int tiles_c = (C + 15) / 16;
+    const int n0 = (blockIdx.z / tiles_c) * 16, c0 = (blockIdx.z % tiles_c) * 16;
+    const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
+    const int dh = taps == 9 ? tap / 3 - 1 : 0, dw = taps == 9 ? tap % 3 - 1 : 0;
+    float sum = 0.f;
+    for (long long p = p0; p < p1; p += 16) {
+        const long long pp = p + ty;
+        float gv = 0.f, xv = 0.f;
+        if (pp < p1) {
+            if (n0 + tx < N) gv = DT<T>::to_f(g[pp * N + n0 + tx]);
+            const int w = static_cast<int>(pp % W), h = static_cast<int>((pp / W) % H);
+            const long long b = pp / (static_cast<long long>(W) * H);
+            const int hh = h + dh, ww = w + dw;
+            if (hh >= 0 && hh < H && ww >= 0 && ww < W && c0 + tx < C)
+                xv = DT<T>::to_f(x[((b * H + hh) * W + ww) * C + c0 + tx]);
+        }
+        __syncthreads();
+        gs[ty][tx] = gv;
+        xs[ty][tx] = xv;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) sum += gs[i][ty] * xs[i][tx];
+    }
+    if (n0 + ty < N && c0 + tx < C) atomicAdd(acc + (static_cast<size_t>(n0 + ty) * taps + tap) * C + c0 + tx, sum);
+}
+
+static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+template <typename T, int BLOCK_C>
+static int launch_wg(const pg_wgrad_params* p, cudaStream_t stream) {
+    using Cfg = WgCfg<T, BLOCK_C>;
+    WgKArgs a;
+    a.acc = p->acc;
+    a.B = p->B; a.H = p->H; a.W = p->W; a.C = p->C; a.N = p->N; a.taps = p->taps;
+    a.PW = p->W < Cfg::BKP ? p->W : Cfg::BKP;
+    a.PH = p->H < (Cfg::BKP / a.PW) ? p->H : (Cfg::BKP / a.PW);
+    a.PB = Cfg::BKP / (a.PW * a.PH);
+    a.chunks_w = p->W / a.PW;
+    a.chunks_h = p->H / a.PH;
+    a.chunks_b = (p->B + a.PB - 1) / a.PB;
+    a.tiles_n = (p->N + 127) / 128;
+    a.tiles_c = p->C / BLOCK_C;
+    const int total_chunks = a.chunks_w * a.chunks_h * a.chunks_b;
+    const int base_units = a.taps * a.tiles_n * a.tiles_c;
+    int splits = (2 * num_sms() + base_units - 1) / base_units;
+    int max_splits = total_chunks / 8;
+    if (max_splits < 1) max_splits = 1;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    a.chunks_per_split = (total_chunks + splits - 1) / splits;
+    a.splits = (total_chunks + a.chunks_per_split - 1) / a.chunks_per_split;
+
+    const uint64_t es = sizeof(T);
+    CUtensorMap tg, tx;
+    uint32_t box[4] = {(uint32_t)Cfg::CPS, (uint32_t)a.PW, (uint32_t)a.PH, (uint32_t)a.PB};
+    {
+        uint64_t dims[4] = {(uint64_t)p->N, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
+        uint64_t strides[3] = {(uint64_t)p->N * es, (uint64_t)p->W * p->N * es, (uint64_t)p->H * p->W * p->N * es};
+        int rc = encode_tmap(&tg, DT<T>::kEnum, 4, p->g, dims, strides, box, 128);
+        if (rc != PG_OK) return rc;
+    }
+    {
+        uint64_t dims[4] = {(uint64_t)p->C, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
+        uint64_t strides[3] = {(uint64_t)p->C * es, (uint64_t)p->W * p->C * es, (uint64_t)p->H * p->W * p->C * es};
+        int rc = encode_tmap(&tx, DT<T>::kEnum, 4, p->x, dims, strides, box, 128);
+        if (rc != PG_OK) return rc;
+    }
+    auto kern = wgrad_gemm_kernel<T, BLOCK_C>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        attr_done = true;
+    }
+    const int num_units = base_units * a.splits;
+    const int grid = num_units < num_sms() ? num_units : num_sms();
+    kern<<<grid, kWgThreads, Cfg::kSmemBytes, stream>>>(tg, tx, a);
+    PG_LAUNCH_CHECK();
+    g_tc_launches++;
+    return PG_OK;
+}
+
+template <typename T>
+static int wgrad_dispatch(const pg_wgrad_params* p, cudaStream_t stream) {
+    constexpr int CPS = 128 / sizeof(T);
+    const bool tc_ok = g_conv_backend == PG_BACKEND_AUTO && is_pow2(p->H) && is_pow2(p->W) && (p->C % CPS == 0) &&
+                       (p->N % 8 == 0) && (reinterpret_cast<uintptr_t>(p->g) % 16 == 0) &&
+                       (reinterpret_cast<uintptr_t>(p->x) % 16 == 0) && (reinterpret_cast<uintptr_t>(p->acc) % 16 == 0);
+    if (tc_ok) {
+        if (p->C % 256 == 0) return launch_wg<T, 256>(p, stream);
+        if (p->C % 128 == 0) return launch_wg<T, 128>(p, stream);
+        if (p->C % 64 == 0) return launch_wg<T, 64>(p, stream);
+        if constexpr (sizeof(T) == 4) {
+            if (p->C % 32 == 0) return launch_wg<T, 32>(p, stream);
+        }
+    }
+    const long long P = (long long)p->B * p->H * p->W;
+    long long pix_per_block = 256;
+    while ((P + pix_per_block - 1) / pix_per_block > 2048) pix_per_block *= 2;
+    dim3 grid((unsigned)((P + pix_per_block - 1) / pix_per_block), (unsigned)p->taps,
+              (unsigned)(((p->N + 15) / 16) * ((p->C + 15) / 16)));
+    wgrad_direct_kernel<T><<<grid, 256, 0, stream>>>(reinterpret_cast<const T*>(p->g), reinterpret_cast<const T*>(p->x),
+                                                      p->acc, p->B, p->H, p->W, p->C, p->N, p->taps, pix_per_block);
+    PG_LAUNCH_CHECK();
+    g_simt_launches++;
+    return PG_OK;
+}
+
+}  // namespace pg
+
+extern "C" int pggan_conv_wgrad(const pg_wgrad_params* p, void* stream) {
+    using namespace pg;
+    PG_CHECK(p != nullptr && p->g && p->x && p->acc, PG_ERR_ARG, "pggan_conv_wgrad: null pointer");
+    PG_CHECK(p->B > 0 && p->H > 0 && p->W > 0 && p->C > 0 && p->N > 0, PG_ERR_ARG,
+             "pggan_conv_wgrad: bad dims B=%d H=%d W=%d C=%d N=%d", p->B, p->H, p->W, p->C, p->N);
+    PG_CHECK(p->taps == 1 || p->taps == 9, PG_ERR_ARG, "pggan_conv_wgrad: taps must be 1 or 9 (got %d)", p->taps);
+    PG_CHECK(p->dtype == PG_BF16 || p->dtype == PG_F32, PG_ERR_ARG, "pggan_conv_wgrad: bad dtype %d", p->dtype);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (p->dtype == PG_BF16) return wgrad_dispatch<__nv_bfloat16>(p, s);
+    return wgrad_dispatch<float>(p, s);
+}

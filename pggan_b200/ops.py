@@ -1,0 +1,681 @@
+"""Kernel wrappers and double-differentiable autograd Functions over libpggan_b200.so.
+
+Every Function's backward is itself built from Functions of this file, so
+``torch.autograd.grad(..., create_graph=True)`` (R1 — reference lib/loss.py:125-135; WGAN-GP —
+reference pggan/loss.py:78-90) can be differentiated again: {fprop, dgrad, wgrad} are closed under
+differentiation, LeakyReLU contributes only its mask, pooling / up-sampling /
+blends are linear, and minibatch-stddev has a true second-order kernel.
+
+Feature maps are channels_last tensors ([B,C,H,W] logical, NHWC physical) in the compute dtype
+(torch.bfloat16, or torch.float32 which runs on kind::tf32 MMAs); images/logits/parameters are fp32.
+"""
+from __future__ import annotations
+
+import contextlib
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+_COMPUTE_DTYPE = torch.bfloat16
+_SKIP_PARAM_GRADS = False      # see input_grad_only()
+
+
+def set_compute_dtype(dtype: torch.dtype) -> None:
+    """torch.bfloat16 (bf16 operands, fp32 accumulate) or torch.float32 (tf32 operands, fp32 accumulate)."""
+    global _COMPUTE_DTYPE
+    if dtype not in (torch.bfloat16, torch.float32):
+        raise ValueError("compute dtype must be torch.bfloat16 or torch.float32 (tf32)")
+    _COMPUTE_DTYPE = dtype
+
+
+def get_compute_dtype() -> torch.dtype:
+    return _COMPUTE_DTYPE
+
+
+@contextlib.contextmanager
+def input_grad_only():
+    """Inside this context the backward of the GEMM-class Functions skips weight/bias gradients.
+    Used around ``autograd.grad(d_out, x_in, create_graph=True)`` in R1/GP, where only the input
+    gradient is requested (a Python autograd.Function cannot see that from ctx.needs_input_grad)."""
+    global _SKIP_PARAM_GRADS
+    prev = _SKIP_PARAM_GRADS
+    _SKIP_PARAM_GRADS = True
+    try:
+        yield
+    finally:
+        _SKIP_PARAM_GRADS = prev
+
+
+# ------------------------------------------------------------------------------------ helpers
+def _enum(dtype: torch.dtype) -> int:
+    if dtype == torch.bfloat16:
+        return L.PG_BF16
+    if dtype == torch.float32:
+        return L.PG_F32
+    raise TypeError(f"unsupported feature dtype {dtype}")
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _s():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(t: torch.Tensor):
+    if not t.is_cuda:
+        raise L.PgganLibraryError("pggan_b200 ops run on CUDA tensors only (no CPU fallback)")
+
+
+def cl(x: torch.Tensor) -> torch.Tensor:
+    """Feature tensor in the kernels' physical layout (NHWC for 4-D, row-major for 2-D)."""
+    if x.dim() == 4:
+        return x.contiguous(memory_format=torch.channels_last)
+    return x.contiguous()
+
+
+def feat(x: torch.Tensor) -> torch.Tensor:
+    """cl() + cast to the compute dtype."""
+    if x.dtype != _COMPUTE_DTYPE:
+        x = x.to(_COMPUTE_DTYPE)
+    return cl(x)
+
+
+def _dims(x: torch.Tensor):
+    if x.dim() == 4:
+        b, c, h, w = x.shape
+        return b, c, h, w
+    if x.dim() == 2:
+        return x.shape[0], x.shape[1], 1, 1
+    raise ValueError(f"expected a 2-D or 4-D feature tensor, got shape {tuple(x.shape)}")
+
+
+def _new_like_layout(x: torch.Tensor, channels: int, dtype: torch.dtype, h=None, w=None) -> torch.Tensor:
+    b, _, hh, ww = _dims(x)
+    h = hh if h is None else h
+    w = ww if w is None else w
+    if x.dim() == 2:
+        return torch.empty((b, channels), dtype=dtype, device=x.device)
+    return torch.empty((b, channels, h, w), dtype=dtype, device=x.device, memory_format=torch.channels_last)
+
+
+# ------------------------------------------------------------------------------ weight packing
+_PACK_CACHE: dict = {}
+
+
+def _pack(W: torch.Tensor, kind: str, dtype: torch.dtype) -> torch.Tensor:
+    """fp32 parameter (OIHW 3x3 or [O,I]) -> K-major packed operand.
+    kind 'f': [O][taps][I] (fprop);  kind 't': [I][taps][O], taps reversed (dgrad = flipped conv)."""
+    _need_cuda(W)
+    cacheable = isinstance(W, torch.nn.Parameter)
+    key = (id(W), W._version, kind, dtype) if cacheable else None
+    if cacheable:
+        hit = _PACK_CACHE.get(key)
+        if hit is not None and hit[0] is W:
+            return hit[1]
+    Wc = W.detach()
+    if Wc.dtype != torch.float32 or not Wc.is_contiguous():
+        Wc = Wc.float().contiguous()
+    O, I = Wc.shape[0], Wc.shape[1]
+    taps = Wc.numel() // (O * I)
+    if kind == "f":
+        out = torch.empty((O, taps * I), dtype=dtype, device=W.device)
+        args = (O, 1, taps, I, I, 0, I * taps, 0, 1, taps)
+    else:
+        out = torch.empty((I, taps * O), dtype=dtype, device=W.device)
+        args = (I, 1, taps, O, O, taps - 1, taps, 0, -1, I * taps)
+    n1, n2, t, c, c_pad, base, s_n1, s_n2, s_t, s_c = args
+    L.check(L.load().pggan_pack_weight(_p(Wc), _p(out), _enum(dtype), n1, n2, t, c, c_pad, base, s_n1, s_n2, s_t,
+                                       s_c, _s()), "pggan_pack_weight")
+    if cacheable:
+        if len(_PACK_CACHE) > 1024:
+            _PACK_CACHE.clear()
+        _PACK_CACHE[key] = (W, out)
+    return out
+
+
+def clear_pack_cache():
+    _PACK_CACHE.clear()
+
+
+# ------------------------------------------------------------------------------- raw kernels
+def k_conv(x, wp, bias, N, taps, scale, slope=1.0, mask_src=None, mask_slope=1.0, raw_out=False):
+    _need_cuda(x)
+    b, c, h, w = _dims(x)
+    out_dtype = torch.float32 if raw_out else x.dtype
+    y = _new_like_layout(x, N, out_dtype)
+    p = L.ConvParams()
+    p.x, p.wp, p.bias, p.mask_src, p.y = x.data_ptr(), wp.data_ptr(), (bias.data_ptr() if bias is not None else None), \
+        (mask_src.data_ptr() if mask_src is not None else None), y.data_ptr()
+    p.B, p.H, p.W, p.C, p.N, p.taps = b, h, w, c, N, taps
+    p.dtype = _enum(x.dtype)
+    p.out_dtype = L.PG_F32_RAW if raw_out else _enum(x.dtype)
+    p.scale, p.slope, p.mask_slope = float(scale), float(slope), float(mask_slope)
+    L.check(L.load().pggan_conv_fprop(ctypes.byref(p), _s()), "pggan_conv_fprop")
+    return y
+
+
+def k_wgrad(g, x, taps, scale, wshape):
+    """returns the weight gradient in the parameter's own fp32 layout (OIHW / [O,I])"""
+    _need_cuda(g)
+    b, n, h, w = _dims(g)
+    c = _dims(x)[1]
+    acc = torch.zeros((n, taps, c), dtype=torch.float32, device=g.device)
+    p = L.WgradParams()
+    p.g, p.x, p.acc = g.data_ptr(), x.data_ptr(), acc.data_ptr()
+    p.B, p.H, p.W, p.C, p.N, p.taps = b, h, w, c, n, taps
+    p.dtype = _enum(g.dtype)
+    L.check(L.load().pggan_conv_wgrad(ctypes.byref(p), _s()), "pggan_conv_wgrad")
+    out = torch.empty(wshape, dtype=torch.float32, device=g.device)
+    L.check(L.load().pggan_unpack_wgrad(_p(acc), _p(out), n, 1, taps, c, c, 0, c * taps, 0, 1, taps, float(scale), 0,
+                                        _s()), "pggan_unpack_wgrad")
+    return out
+
+
+def k_mask_mul(g, y, slope):
+    out = torch.empty_like(g)
+    L.check(L.load().pggan_lrelu_mask_mul(_p(g), _p(y), _p(out), g.numel(), float(slope), _enum(g.dtype), _s()),
+            "pggan_lrelu_mask_mul")
+    return out
+
+
+def k_colsum(g, scale):
+    b, c, h, w = _dims(g)
+    if c % (16 // g.element_size()) != 0:      # e.g. the 1-logit decision layer: a [B,1] column
+        g2 = g.float().reshape(b, c) if g.dim() == 2 else g.float().permute(0, 2, 3, 1).reshape(-1, c)
+        return g2.sum(0) * scale
+    out = torch.zeros((c,), dtype=torch.float32, device=g.device)
+    L.check(L.load().pggan_colsum(_p(g), _p(out), b * h * w, c, float(scale), _enum(g.dtype), _s()), "pggan_colsum")
+    return out
+
+
+def k_upsample(x, scale):
+    b, c, h, w = _dims(x)
+    out = _new_like_layout(x, c, x.dtype, 2 * h, 2 * w)
+    L.check(L.load().pggan_upsample2x(_p(x), _p(out), b, h, w, c, float(scale), _enum(x.dtype), _s()),
+            "pggan_upsample2x")
+    return out
+
+
+def k_pool(x, scale, blend_with=None, alpha=1.0):
+    b, c, h, w = _dims(x)
+    out = _new_like_layout(x, c, x.dtype, h // 2, w // 2)
+    L.check(L.load().pggan_pool2x2(_p(x), _p(blend_with), _p(out), b, h, w, c, float(scale), float(alpha),
+                                   _enum(x.dtype), _s()), "pggan_pool2x2")
+    return out
+
+
+def k_axpby(a, b, sa, sb):
+    out = torch.empty_like(a)
+    L.check(L.load().pggan_axpby(_p(a), _p(b), _p(out), a.numel(), float(sa), float(sb), _enum(a.dtype), _s()),
+            "pggan_axpby")
+    return out
+
+
+# ----------------------------------------------------------------------- GEMM-class Functions
+def _wmeta(W):
+    O, I = W.shape[0], W.shape[1]
+    taps = W.numel() // (O * I)
+    return O, I, taps
+
+
+class ConvF(torch.autograd.Function):
+    """y = lrelu(scale * (conv(x, W) + b), slope)   [fprop; slope = 1 -> linear]"""
+
+    @staticmethod
+    def forward(ctx, x, W, b, scale, slope, raw_out):
+        x = feat(x)
+        O, I, taps = _wmeta(W)
+        bias = None if b is None else b.detach().float().contiguous()
+        y = k_conv(x, _pack(W, "f", x.dtype), bias, O, taps, scale, slope, raw_out=raw_out)
+        ctx.save_for_backward(x, W, y if slope != 1.0 else None)
+        ctx.scale, ctx.slope, ctx.has_bias = scale, slope, b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, W, y = ctx.saved_tensors
+        g = feat(gy)
+        if ctx.slope != 1.0:
+            g = MaskMul.apply(g, y, ctx.slope)
+        gx = gW = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = ConvT.apply(g, W, ctx.scale)
+        if not _SKIP_PARAM_GRADS:
+            if ctx.needs_input_grad[1]:
+                gW = ConvW.apply(g, x, ctx.scale, tuple(W.shape))
+            if ctx.has_bias and ctx.needs_input_grad[2]:
+                gb = ColSum.apply(g, ctx.scale)
+        return gx, gW, gb, None, None, None
+
+
+class ConvT(torch.autograd.Function):
+    """gx = scale * conv_transpose(g, W)   [dgrad: the same kernel on flipped/transposed weights]"""
+
+    @staticmethod
+    def forward(ctx, g, W, scale):
+        g = feat(g)
+        O, I, taps = _wmeta(W)
+        gx = k_conv(g, _pack(W, "t", g.dtype), None, I, taps, scale)
+        ctx.save_for_backward(g, W)
+        ctx.scale = scale
+        return gx
+
+    @staticmethod
+    def backward(ctx, ggx):
+        g, W = ctx.saved_tensors
+        ggx = feat(ggx)
+        dg = dW = None
+        if ctx.needs_input_grad[0]:
+            dg = ConvF.apply(ggx, W, None, ctx.scale, 1.0, False)
+        if ctx.needs_input_grad[1] and not _SKIP_PARAM_GRADS:
+            dW = ConvW.apply(g, ggx, ctx.scale, tuple(W.shape))
+        return dg, dW, None
+
+
+class ConvW(torch.autograd.Function):
+    """gW = scale * wgrad(g, x)   in the parameter's layout"""
+
+    @staticmethod
+    def forward(ctx, g, x, scale, wshape):
+        g, x = feat(g), feat(x)
+        O, I = wshape[0], wshape[1]
+        taps = 1
+        for s in wshape[2:]:
+            taps *= s
+        ctx.save_for_backward(g, x)
+        ctx.scale = scale
+        return k_wgrad(g, x, taps, scale, wshape)
+
+    @staticmethod
+    def backward(ctx, ggW):
+        g, x = ctx.saved_tensors
+        dg = dx = None
+        ggW = ggW.contiguous()
+        if ctx.needs_input_grad[0]:
+            dg = ConvF.apply(x, ggW, None, ctx.scale, 1.0, False)
+        if ctx.needs_input_grad[1]:
+            dx = ConvT.apply(g, ggW, ctx.scale)
+        return dg, dx, None, None
+
+
+class ColSum(torch.autograd.Function):
+    """gb[c] = scale * sum over pixels of g[:, c]"""
+
+    @staticmethod
+    def forward(ctx, g, scale):
+        g = feat(g)
+        ctx.shape, ctx.scale, ctx.dtype = tuple(g.shape), scale, g.dtype
+        return k_colsum(g, scale)
+
+    @staticmethod
+    def backward(ctx, ggb):
+        shape = ctx.shape
+        view = (1, -1, 1, 1) if len(shape) == 4 else (1, -1)
+        return cl((ggb * ctx.scale).to(ctx.dtype).view(view).expand(shape)), None
+
+
+class MaskMul(torch.autograd.Function):
+    """g * (y > 0 ? 1 : slope): LeakyReLU backward from the saved OUTPUT (sign(y) == sign(pre))."""
+
+    @staticmethod
+    def forward(ctx, g, y, slope):
+        g = feat(g)
+        ctx.save_for_backward(y)
+        ctx.slope = slope
+        return k_mask_mul(g, y, slope)
+
+    @staticmethod
+    def backward(ctx, gg):
+        (y,) = ctx.saved_tensors
+        return MaskMul.apply(feat(gg), y, ctx.slope), None, None
+
+
+# ------------------------------------------------------------------ resampling / blend Functions
+class Upsample2x(torch.autograd.Function):
+    """nearest 2x (reference lib/utils.py:106-118), times `scale`"""
+
+    @staticmethod
+    def forward(ctx, x, scale):
+        ctx.scale = scale
+        return k_upsample(feat(x), scale)
+
+    @staticmethod
+    def backward(ctx, g):
+        return Pool2x2.apply(feat(g), ctx.scale), None
+
+
+class Pool2x2(torch.autograd.Function):
+    """scale * (2x2 window sum); scale = 0.25 is nn.AvgPool2d(2) (reference lib/blocks.py:193)"""
+
+    @staticmethod
+    def forward(ctx, x, scale):
+        ctx.scale = scale
+        return k_pool(feat(x), scale)
+
+    @staticmethod
+    def backward(ctx, g):
+        return Upsample2x.apply(feat(g), ctx.scale), None
+
+
+class PoolBlend(torch.autograd.Function):
+    """(1-alpha) * low + alpha * avgpool2(x): D's feature-space fade fused with the pooling
+    (reference lib/blocks.py:193 + pggan/nets.py:262-265)"""
+
+    @staticmethod
+    def forward(ctx, x, low, alpha):
+        ctx.alpha = alpha
+        return k_pool(feat(x), 0.25, blend_with=feat(low), alpha=alpha)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = feat(g)
+        gx = Upsample2x.apply(g, 0.25 * ctx.alpha) if ctx.needs_input_grad[0] else None
+        gl = Scale.apply(g, 1.0 - ctx.alpha) if ctx.needs_input_grad[1] else None
+        return gx, gl, None
+
+
+class Scale(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, s):
+        ctx.s = s
+        return k_axpby(feat(x), None, s, 0.0)
+
+    @staticmethod
+    def backward(ctx, g):
+        return Scale.apply(feat(g), ctx.s), None
+
+
+class Lerp(torch.autograd.Function):
+    """(1-alpha) * a + alpha * b on feature maps"""
+
+    @staticmethod
+    def forward(ctx, a, b, alpha):
+        ctx.alpha = alpha
+        return k_axpby(feat(a), feat(b), 1.0 - alpha, alpha)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = feat(g)
+        ga = Scale.apply(g, 1.0 - ctx.alpha) if ctx.needs_input_grad[0] else None
+        gb = Scale.apply(g, ctx.alpha) if ctx.needs_input_grad[1] else None
+        return ga, gb, None
+
+
+# ---------------------------------------------------------------------------------- pixel norm
+class PixelNorm(torch.autograd.Function):
+    """x * rsqrt(mean_c(x^2) + eps)  (reference lib/layers.py:13-14).  `act_slope` != 1 declares that
+    x is a LeakyReLU output whose mask should be folded into THIS backward (the producing ConvF was
+    then run with its own mask disabled) — sign(y) == sign(x) == sign(pre-activation)."""
+
+    @staticmethod
+    def forward(ctx, x, eps):
+        x = feat(x)
+        b, c, h, w = _dims(x)
+        y = torch.empty_like(x)
+        r = torch.empty((b * h * w,), dtype=torch.float32, device=x.device)
+        L.check(L.load().pggan_pixelnorm_fwd(_p(x), _p(y), _p(r), b * h * w, c, float(eps), _enum(x.dtype), _s()),
+                "pggan_pixelnorm_fwd")
+        ctx.save_for_backward(y, r)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        y, r = ctx.saved_tensors
+        gy = feat(gy)
+        b, c, h, w = _dims(y)
+        gx = torch.empty_like(y)
+        L.check(L.load().pggan_pixelnorm_bwd(_p(gy), _p(y), _p(r), _p(gx), b * h * w, c, 1.0, _enum(y.dtype), _s()),
+                "pggan_pixelnorm_bwd")
+        return gx, None
+
+
+# ------------------------------------------------------------------------------------ RGB 1x1
+def _k_rgb_expand(img, wc, bias, C, pool, scale, slope, dtype):
+    b, cimg, hi, wi = img.shape
+    h, w = (hi // 2, wi // 2) if pool else (hi, wi)
+    out = torch.empty((b, C, h, w), dtype=dtype, device=img.device, memory_format=torch.channels_last)
+    L.check(L.load().pggan_rgb_expand(_p(img), _p(wc), _p(bias), _p(out), b, h, w, C, cimg, int(pool), float(scale),
+                                      float(slope), _enum(dtype), _s()), "pggan_rgb_expand")
+    return out
+
+
+def _k_rgb_reduce(x, wr, bias, cimg, up, scale, up_scale):
+    b, c, h, w = _dims(x)
+    ho, wo = (2 * h, 2 * w) if up else (h, w)
+    out = torch.empty((b, cimg, ho, wo), dtype=torch.float32, device=x.device)
+    L.check(L.load().pggan_rgb_reduce(_p(x), _p(wr), _p(bias), _p(out), b, h, w, c, cimg, int(up), float(scale),
+                                      float(up_scale), _enum(x.dtype), _s()), "pggan_rgb_reduce")
+    return out
+
+
+def _k_rgb_wgrad(f, img, pool, scale):
+    b, c, h, w = _dims(f)
+    cimg = img.shape[1]
+    acc = torch.zeros((c, cimg), dtype=torch.float32, device=f.device)
+    L.check(L.load().pggan_rgb_wgrad(_p(f), _p(img), _p(acc), b, h, w, c, cimg, int(pool), float(scale),
+                                     _enum(f.dtype), _s()), "pggan_rgb_wgrad")
+    return acc
+
+
+def _img(t):
+    return t.float().contiguous()
+
+
+class RgbExpand(torch.autograd.Function):
+    """NHWC[b,h,w,c] = lrelu(scale*(sum_j Wc[c,j]*p_j + bias[c]), slope); p = image pixel or its 2x2 mean.
+    Wc is [C, cimg] fp32.  (fromRGBBlock, reference lib/blocks.py:285-292)"""
+
+    @staticmethod
+    def forward(ctx, img, Wc, bias, pool, scale, slope):
+        img = _img(img)
+        _need_cuda(img)
+        wc = Wc.detach().float().contiguous()
+        bs = None if bias is None else bias.detach().float().contiguous()
+        y = _k_rgb_expand(img, wc, bs, wc.shape[0], pool, scale, slope, _COMPUTE_DTYPE)
+        ctx.save_for_backward(img, Wc, y if slope != 1.0 else None)
+        ctx.pool, ctx.scale, ctx.slope, ctx.has_bias = pool, scale, slope, bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        img, Wc, y = ctx.saved_tensors
+        g = feat(gy)
+        if ctx.slope != 1.0:
+            g = MaskMul.apply(g, y, ctx.slope)
+        gimg = gW = gb = None
+        if ctx.needs_input_grad[0]:
+            gimg = RgbReduce.apply(g, Wc, None, ctx.pool, ctx.scale, 0.25)
+        if not _SKIP_PARAM_GRADS:
+            if ctx.needs_input_grad[1]:
+                gW = RgbWgrad.apply(g, img, ctx.pool, ctx.scale)
+            if ctx.has_bias and ctx.needs_input_grad[2]:
+                gb = ColSum.apply(g, ctx.scale)
+        return gimg, gW, gb, None, None, None
+
+
+class RgbReduce(torch.autograd.Function):
+    """img[b,j,h,w] = scale*(sum_c Wc[c,j]*x[b,h,w,c] + bias[j]); if up, written (times up_scale) to
+    the 2x2 block of a 2x larger image.  (toRGBBlock, reference lib/blocks.py:164-170)"""
+
+    @staticmethod
+    def forward(ctx, x, Wc, bias, up, scale, up_scale):
+        x = feat(x)
+        wr = Wc.detach().float().t().contiguous()          # [cimg, C]
+        bs = None if bias is None else bias.detach().float().contiguous()
+        out = _k_rgb_reduce(x, wr, bs, wr.shape[0], up, scale, up_scale)
+        ctx.save_for_backward(x, Wc)
+        ctx.up, ctx.scale, ctx.up_scale, ctx.has_bias = up, scale, up_scale, bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, Wc = ctx.saved_tensors
+        gout = _img(gout)
+        s = ctx.scale * (4.0 * ctx.up_scale if ctx.up else 1.0)    # adjoint of "write 4 copies * up_scale"
+        gx = gW = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = RgbExpand.apply(gout, Wc, None, ctx.up, s, 1.0)
+        if not _SKIP_PARAM_GRADS:
+            if ctx.needs_input_grad[1]:
+                gW = RgbWgrad.apply(x, gout, ctx.up, s)
+            if ctx.has_bias and ctx.needs_input_grad[2]:
+                gb = gout.sum(dim=(0, 2, 3)) * (ctx.scale * (ctx.up_scale if ctx.up else 1.0))
+        return gx, gW, gb, None, None, None
+
+
+class RgbWgrad(torch.autograd.Function):
+    """gWc[c,j] = scale * sum_pixels f[.,c] * p_j"""
+
+    @staticmethod
+    def forward(ctx, f, img, pool, scale):
+        f, img = feat(f), _img(img)
+        ctx.save_for_backward(f, img)
+        ctx.pool, ctx.scale = pool, scale
+        return _k_rgb_wgrad(f, img, pool, scale)
+
+    @staticmethod
+    def backward(ctx, ggW):
+        f, img = ctx.saved_tensors
+        df = dimg = None
+        if ctx.needs_input_grad[0]:
+            df = RgbExpand.apply(img, ggW, None, ctx.pool, ctx.scale, 1.0)
+        if ctx.needs_input_grad[1]:
+            dimg = RgbReduce.apply(f, ggW, None, ctx.pool, ctx.scale, 0.25)
+        return df, dimg, None, None
+
+
+class ImageFade(torch.autograd.Function):
+    """(1-alpha) * up2(low) + alpha * x on fp32 NCHW images; low=None -> low = avgpool2(x)
+    (G's RGB fade, reference pggan/nets.py:155-156; real-image fade, pggan/model.py:217-221)."""
+
+    @staticmethod
+    def forward(ctx, x, low, alpha):
+        x = _img(x)
+        _need_cuda(x)
+        lo = None if low is None else _img(low)
+        b, c, h, w = x.shape
+        out = torch.empty_like(x)
+        L.check(L.load().pggan_image_fade(_p(x), _p(lo), _p(out), b, c, h, w, float(alpha), _s()), "pggan_image_fade")
+        ctx.alpha, ctx.self_low = alpha, low is None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _img(g)
+        b, c, h, w = g.shape
+        pooled = torch.empty((b, c, h // 2, w // 2), dtype=torch.float32, device=g.device)
+        L.check(L.load().pggan_image_pool_sum(_p(g), _p(pooled), b, c, h, w, 1.0 - ctx.alpha, _s()),
+                "pggan_image_pool_sum")
+        if ctx.self_low:
+            # d/dx of (1-a)*up(pool(x)): up(pooled)/4
+            gx = ctx.alpha * g + pooled.repeat_interleave(2, 2).repeat_interleave(2, 3) * 0.25
+            return gx, None, None
+        return ctx.alpha * g, pooled, None
+
+
+# -------------------------------------------------------------------------- minibatch stddev
+class MbstdStat(torch.autograd.Function):
+    """per-group scalar of reference lib/blocks.py:216-224 (x: [B, ...] features, any layout)"""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        x = feat(x)
+        B = x.shape[0]
+        K = x.numel() // B
+        stat = torch.empty((B // group,), dtype=torch.float32, device=x.device)
+        L.check(L.load().pggan_mbstd_fwd(_p(x), _p(stat), B, K, group, _enum(x.dtype), _s()), "pggan_mbstd_fwd")
+        ctx.save_for_backward(x)
+        ctx.group = group
+        return stat
+
+    @staticmethod
+    def backward(ctx, gs):
+        (x,) = ctx.saved_tensors
+        return MbstdBwd.apply(x, gs.float().contiguous(), ctx.group), None
+
+
+class MbstdBwd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gs, group):
+        B = x.shape[0]
+        K = x.numel() // B
+        gx = torch.empty_like(x)
+        L.check(L.load().pggan_mbstd_bwd(_p(x), _p(gs), _p(gx), B, K, group, _enum(x.dtype), _s()), "pggan_mbstd_bwd")
+        ctx.save_for_backward(x, gs)
+        ctx.group = group
+        return gx
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, u):
+        x, gs = ctx.saved_tensors
+        u = feat(u)
+        B = x.shape[0]
+        K = x.numel() // B
+        ggs = torch.empty_like(gs)
+        gx2 = torch.empty_like(x)
+        L.check(L.load().pggan_mbstd_bwd2(_p(x), _p(u), _p(gs), _p(ggs), _p(gx2), B, K, ctx.group, _enum(x.dtype),
+                                          _s()), "pggan_mbstd_bwd2")
+        return gx2, ggs, None
+
+
+# ------------------------------------------------------------------------- loss reductions
+class RowsSumSq(torch.autograd.Function):
+    """[B, ...] fp32 -> [B] sum of squares (R1: reference lib/loss.py:132-134)"""
+
+    @staticmethod
+    def forward(ctx, g):
+        g = _img(g)
+        _need_cuda(g)
+        B = g.shape[0]
+        out = torch.zeros((B,), dtype=torch.float32, device=g.device)
+        L.check(L.load().pggan_rows_sumsq(_p(g), _p(out), B, g.numel() // B, _s()), "pggan_rows_sumsq")
+        ctx.save_for_backward(g)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout):
+        (g,) = ctx.saved_tensors
+        B = g.shape[0]
+        coef = (2.0 * gout).float().contiguous()
+        out = torch.empty_like(g)
+        L.check(L.load().pggan_rows_scale(_p(g), _p(coef), _p(out), B, g.numel() // B, _s()), "pggan_rows_scale")
+        return out
+
+
+class GradientPenalty(torch.autograd.Function):
+    """w_gp * sum_b (||g_b||_2 - 1)^2 and, fused, w_drift * sum_b pred_b^2 (value only)
+    (reference pggan/loss.py:85-87, 98-100).  Returns a 2-vector [gp, drift]."""
+
+    @staticmethod
+    def forward(ctx, g, pred, w_gp, w_drift):
+        g = _img(g)
+        _need_cuda(g)
+        B = g.shape[0]
+        n = g.numel() // B
+        sumsq = torch.zeros((B,), dtype=torch.float32, device=g.device)
+        coef = torch.empty((B,), dtype=torch.float32, device=g.device)
+        res = torch.empty((2,), dtype=torch.float32, device=g.device)
+        pr = None if pred is None else pred.detach().float().contiguous()
+        L.check(L.load().pggan_rows_sumsq(_p(g), _p(sumsq), B, n, _s()), "pggan_rows_sumsq")
+        L.check(L.load().pggan_gp_finalize(_p(sumsq), _p(pr), _p(res), _p(coef), B, float(w_gp), float(w_drift), _s()),
+                "pggan_gp_finalize")
+        ctx.save_for_backward(g, coef)
+        return res
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gres):
+        g, coef = ctx.saved_tensors
+        B = g.shape[0]
+        c = (coef * gres[0]).contiguous()
+        out = torch.empty_like(g)
+        L.check(L.load().pggan_rows_scale(_p(g), _p(c), _p(out), B, g.numel() // B, _s()), "pggan_rows_scale")
+        return out, None, None, None

@@ -1,0 +1,113 @@
+"""Fused multi-tensor Adam over the live parameters of one network.
+
+torch.optim.Adam semantics as the reference configures it (lib/model.py:95-97: lr_G 1e-4 / lr_D 1e-5,
+betas (beta1, beta2), eps 1e-8, no weight decay, no amsgrad); parameters whose gradient is None are
+skipped exactly like torch skips them (the stale RGB layers of SURVEY.md D16 are simply not registered).
+
+Gradients live in ONE flat fp32 buffer (`p.grad` is a view into it): zero_grad is one memset, the
+data-parallel all-reduce runs on contiguous bucket slices (dist.GradSync), and the update is one
+kernel launch (pggan_adam_step) that also folds the 1/world_size of the gradient mean.
+The step counter lives on the device, so the whole step is CUDA-graph capturable.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Iterable, List
+
+import torch
+
+from . import _lib as L
+from . import ops
+
+
+def _pad4(n: int) -> int:
+    return (n + 3) // 4 * 4
+
+
+class FlatGrads:
+    """one flat gradient buffer for an ordered list of parameters (order = gradient-ready order)"""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter]):
+        self.params: List[torch.nn.Parameter] = [p for p in params]
+        if not self.params:
+            raise ValueError("no parameters")
+        dev = self.params[0].device
+        self.offsets = []
+        off = 0
+        for p in self.params:
+            if p.dtype != torch.float32:
+                raise TypeError("master parameters must be fp32")
+            self.offsets.append(off)
+            off += _pad4(p.numel())
+        self.total = off
+        self.flat = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        self.attach()
+
+    def attach(self):
+        for p, off in zip(self.params, self.offsets):
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+
+    def zero(self):
+        self.flat.zero_()
+        # a backward with create_graph=True (or set_to_none) may have replaced the views: re-attach
+        for p, off in zip(self.params, self.offsets):
+            g = p.grad
+            if g is None or g.data_ptr() != self.flat.data_ptr() + 4 * off:
+                p.grad = self.flat[off:off + p.numel()].view_as(p)
+
+
+class FusedAdam:
+    """drop-in for the two `torch.optim.Adam` objects of reference lib/model.py:95-97"""
+
+    def __init__(self, params, lr, betas=(0.0, 0.99), eps=1e-8, grad_scale=1.0):
+        self.grads = params if isinstance(params, FlatGrads) else FlatGrads(params)
+        self.lr, self.betas, self.eps, self.grad_scale = float(lr), (float(betas[0]), float(betas[1])), float(eps), \
+            float(grad_scale)
+        g = self.grads
+        dev = g.flat.device
+        if dev.type != "cuda":
+            raise L.PgganLibraryError("FusedAdam needs CUDA parameters (no CPU fallback)")
+        self.exp_avg = torch.zeros_like(g.flat)
+        self.exp_avg_sq = torch.zeros_like(g.flat)
+        self.step_count = torch.zeros(1, dtype=torch.int64, device=dev)
+        chunk = L.load().pggan_adam_chunk_size()
+        entries = (L.AdamEntry * len(g.params))()
+        chunk_tensor, chunk_offset = [], []
+        for i, (p, off) in enumerate(zip(g.params, g.offsets)):
+            if not p.is_contiguous():
+                raise ValueError("parameters must be contiguous")
+            entries[i].param = p.data_ptr()
+            entries[i].grad = g.flat.data_ptr() + 4 * off
+            entries[i].exp_avg = self.exp_avg.data_ptr() + 4 * off
+            entries[i].exp_avg_sq = self.exp_avg_sq.data_ptr() + 4 * off
+            entries[i].numel = p.numel()
+            for c0 in range(0, p.numel(), chunk):
+                chunk_tensor.append(i)
+                chunk_offset.append(c0)
+        raw = bytes(entries)
+        self._table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+        self._chunk_tensor = torch.tensor(chunk_tensor, dtype=torch.int32, device=dev)
+        self._chunk_offset = torch.tensor(chunk_offset, dtype=torch.int64, device=dev)
+        self._n_tensors, self._n_chunks = len(g.params), len(chunk_tensor)
+        self._param_ptrs = [p.data_ptr() for p in g.params]
+
+    # torch.optim.Optimizer-like surface used by update_net (reference lib/utils.py:72-75)
+    def zero_grad(self, set_to_none: bool = False):
+        self.grads.zero()
+
+    def step(self):
+        for p, ptr in zip(self.grads.params, self._param_ptrs):
+            if p.data_ptr() != ptr:
+                raise RuntimeError("a parameter was re-allocated after the optimizer was built "
+                                   "(re-create the optimizers after add_block/.to(), as the reference does)")
+        b1, b2 = self.betas
+        L.check(L.load().pggan_adam_step(ctypes.c_void_p(self._table.data_ptr()), self._n_tensors, self._n_chunks,
+                                         ctypes.c_void_p(self._chunk_tensor.data_ptr()),
+                                         ctypes.c_void_p(self._chunk_offset.data_ptr()),
+                                         ctypes.c_void_p(self.step_count.data_ptr()), self.lr, b1, b2, self.eps,
+                                         self.grad_scale, ops._s()), "pggan_adam_step")
+        ops.clear_pack_cache()          # packed bf16/tf32 weight copies are stale now
+
+    def state_dict(self):
+        return {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "step": self.step_count,
+                "lr": self.lr, "betas": self.betas, "eps": self.eps}

@@ -1,0 +1,214 @@
+"""The PGGAN D+G training step and the scale/alpha schedule around it — mirror of
+reference pggan/model.py (ProgressiveGAN.train_step :206-255, schedule :131-204) without the data
+loading, checkpoint and wandb glue (out of scope).
+
+step variants:
+  "L"  the reference's LIVE step: D loss = BCE(real,1)+BCE(fake,0)+R1 (pggan/loss.py:16-27)
+  "W"  the WGAN-GP step of the commented-out caller (pggan/loss.py:29-51), wired as
+       zero_grad -> GP.backward -> loss_D.backward -> Adam, drift reported as a value.
+Both run D forward three times (real, fake, interpolates/R1 graph), G forward twice, and the double
+backward through D.  The G step freezes D's parameters (the reference computes and discards those
+gradients, SURVEY.md D15 — results are identical).
+"""
+from __future__ import annotations
+
+import types
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .dist import GradSync, broadcast_parameters
+from .loss import WGANGPLoss
+from .nets import Discriminator, Generator
+from .optim import FlatGrads, FusedAdam
+
+# reference configs.yaml values on the hot path
+DEFAULT_ARGS = dict(
+    lr_G=1e-4, lr_D=1e-5, beta1=0, beta2=0.99, W_adv=1, W_gp=10, W_drift_D=0.001, batch_per_gpu=16,
+    max_step=2000000, latent_dim=512, input_dim=3, output_dim=3, init_bias_to_zero=True,
+    depths=[512, 512, 512, 512, 256, 128, 64], max_step_at_scale=[10000, 20000, 40000, 80000, 80000, 80000, 80000,
+                                                                  80000, 80000],
+    alpha_jump_start=[-1, 2000, 4000, 10000, 10000, 10000, 10000, 10000, 10000],
+    alpha_jump_interval=[0, 100, 100, 100, 100, 100, 100, 100, 100],
+    alpha_jump_Ntimes=[0, 100, 200, 400, 400, 400, 400, 400, 400],
+    LReLU_slope=0.2, generator_last_activation=None, apply_pixel_norm=True, apply_minibatch_norm=True,
+    equalized_lr=True, decision_layer_size=1, isMaster=False,
+)
+# the paper's CelebA-HQ widths for the 1024^2 configuration
+DEPTHS_1024 = [512, 512, 512, 512, 256, 128, 64, 32, 16]
+
+
+def make_args(**overrides):
+    d = dict(DEFAULT_ARGS)
+    d.update(overrides)
+    return types.SimpleNamespace(**d)
+
+
+class ProgressiveGAN:
+    def __init__(self, args=None, gpu=0, variant: str = "W", data_parallel: Optional[bool] = None,
+                 bucket_bytes: int = 32 << 20):
+        self.args = args if args is not None else make_args()
+        self.gpu = gpu
+        self.device = torch.device("cuda", gpu) if isinstance(gpu, int) else torch.device(gpu)
+        self.variant = variant
+        self.scale_index = 0
+        self.alpha_index = 0
+        self.alpha_jump_value = 0
+        self.next_scale_jump_step = self.args.max_step_at_scale[0]
+        self.next_alpha_jump_step = self.args.alpha_jump_start[0]
+        if data_parallel is None:
+            data_parallel = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self.data_parallel = data_parallel
+        self.world = dist.get_world_size() if data_parallel else 1
+        self.bucket_bytes = bucket_bytes
+        self.initialize_models()
+        self.set_multi_GPU()
+        self.set_optimizers()
+        self.set_loss_collector()
+
+    # ------------------------------------------------------------------ construction (model.py:18-47)
+    def initialize_models(self):
+        a = self.args
+        self.G = Generator(a.latent_dim, a.depths[0], a.init_bias_to_zero, a.LReLU_slope, a.apply_pixel_norm,
+                           a.generator_last_activation, a.output_dim, a.equalized_lr).to(self.device)
+        self.D = Discriminator(a.depths[0], a.init_bias_to_zero, a.LReLU_slope, a.decision_layer_size,
+                               a.apply_minibatch_norm, a.input_dim, a.equalized_lr).to(self.device)
+        self.G.train()
+        self.D.train()
+
+    def set_multi_GPU(self):
+        """intended semantics of reference lib/model.py:74-79: replicas start equal"""
+        if self.data_parallel:
+            broadcast_parameters(self.G)
+            broadcast_parameters(self.D)
+
+    def set_optimizers(self):
+        """reference lib/model.py:95-97; re-created (moments reset) on every scale jump — SURVEY.md D14"""
+        a = self.args
+        for attr in ("sync_G", "sync_D"):
+            if getattr(self, attr, None) is not None:
+                getattr(self, attr).remove()
+        for p in list(self.G.parameters()) + list(self.D.parameters()):
+            p.grad = None
+        gG, gD = FlatGrads(self.G.live_parameters()), FlatGrads(self.D.live_parameters())
+        scale = 1.0 / self.world
+        self.opt_G = FusedAdam(gG, lr=a.lr_G, betas=(float(a.beta1), float(a.beta2)), grad_scale=scale)
+        self.opt_D = FusedAdam(gD, lr=a.lr_D, betas=(float(a.beta1), float(a.beta2)), grad_scale=scale)
+        self.sync_G = GradSync(gG, self.bucket_bytes) if self.data_parallel else None
+        self.sync_D = GradSync(gD, self.bucket_bytes) if self.data_parallel else None
+
+    def set_loss_collector(self):
+        self._loss_collector = WGANGPLoss(self.args)
+
+    @property
+    def loss_collector(self):
+        return self._loss_collector
+
+    # --------------------------------------------------------------------- schedule (model.py:131-204)
+    def reset_solver(self):
+        self.set_optimizers()
+
+    def reset_alpha(self, global_step):
+        self.G.alpha = 0
+        self.D.alpha = 0
+        self.alpha_index = 0
+        self.next_alpha_jump_step = global_step + self.args.alpha_jump_start[self.scale_index]
+        self.alpha_jump_value = 1 / self.args.alpha_jump_Ntimes[self.scale_index]
+
+    def change_scale(self, global_step):
+        self.scale_index += 1
+        self.next_scale_jump_step += self.args.max_step_at_scale[self.scale_index]
+        self.G.add_block(self.args.depths[self.scale_index])
+        self.D.add_block(self.args.depths[self.scale_index])
+        self.G.to(self.device)
+        self.D.to(self.device)
+        self.set_multi_GPU()            # new blocks are random per rank: re-broadcast
+        self.reset_solver()
+        self.reset_alpha(global_step)
+
+    def change_alpha(self, global_step):
+        self.alpha_index += 1
+        self.G.alpha += self.alpha_jump_value
+        self.D.alpha += self.alpha_jump_value
+        self.G.alpha = round(self.G.alpha, 4)
+        self.D.alpha = round(self.D.alpha, 4)
+        if self.alpha_index == self.args.alpha_jump_Ntimes[self.scale_index]:
+            self.next_alpha_jump_step = 0
+        else:
+            self.next_alpha_jump_step = global_step + self.args.alpha_jump_interval[self.scale_index]
+
+    def check_jump(self, global_step):
+        if self.next_scale_jump_step == global_step:
+            self.change_scale(global_step)
+        if self.next_alpha_jump_step == global_step:
+            self.change_alpha(global_step)
+
+    def set_scale(self, scale_index: int, alpha: float):
+        """test/bench helper: grow to `scale_index` and set alpha directly"""
+        while self.scale_index < scale_index:
+            self.scale_index += 1
+            self.G.add_block(self.args.depths[self.scale_index])
+            self.D.add_block(self.args.depths[self.scale_index])
+        self.set_multi_GPU()
+        self.reset_solver()
+        self.G.alpha = alpha
+        self.D.alpha = alpha
+
+    # ------------------------------------------------------------------- the step (model.py:206-255)
+    def train_step(self, img_real, latent_D=None, latent_G=None, eps=None):
+        """img_real: [B,3,R,R] fp32 in [-1,1] on the device.  latent_D/latent_G/eps: optional
+        pre-drawn inputs (device tensors); when None they are drawn on the CPU generator and copied,
+        exactly like the reference (pggan/model.py:226,244; pggan/loss.py:71-73)."""
+        a = self.args
+        lc = self.loss_collector
+        n_samples = len(img_real)
+
+        # ---- Train D ----
+        if self.scale_index:
+            img_real = ops.ImageFade.apply(img_real, None, float(self.D.alpha))     # model.py:217-221
+        img_real = img_real.detach().requires_grad_()
+        pred_real = self.D(img_real)
+        if latent_D is None:
+            latent_D = torch.randn(n_samples, a.latent_dim).to(self.device)
+        img_fake = self.G(latent_D).detach()
+        pred_fake = self.D(img_fake)
+        D_dict = {"img_real": img_real, "img_fake": img_fake, "pred_real": pred_real, "pred_fake": pred_fake}
+        self.opt_D.zero_grad()
+        if self.variant == "L":
+            loss_D = lc.get_loss_D(D_dict)
+        else:
+            lc.get_gradient_penalty(D_dict, self.D, backward=True, eps=eps, lazy=True)   # accumulates into D.grad
+            loss_D = lc.get_loss_D_wgangp_terms(D_dict)
+        if self.sync_D is not None:
+            self.sync_D.arm()
+        loss_D.backward()
+        if self.sync_D is not None:
+            self.sync_D.finish()
+        self.opt_D.step()
+
+        # ---- Train G ----
+        if latent_G is None:
+            latent_G = torch.randn(n_samples, a.latent_dim).to(self.device)
+        d_params = [p for p in self.D.parameters() if p.requires_grad]
+        for p in d_params:
+            p.requires_grad_(False)
+        try:
+            img_fake = self.G(latent_G)
+            pred_fake, _ = self.D(img_fake, True)
+            loss_G = lc.get_loss_G({"pred_fake": pred_fake})
+            self.opt_G.zero_grad()
+            if self.sync_G is not None:
+                self.sync_G.arm()
+            loss_G.backward()
+            if self.sync_G is not None:
+                self.sync_G.finish()
+        finally:
+            for p in d_params:
+                p.requires_grad_(True)
+        self.opt_G.step()
+        return [img_real, img_fake]
+
+    def validation(self):
+        pass

@@ -1,0 +1,342 @@
+"""Kernel-level parity on the GPU: every C-ABI entry point against plain PyTorch fp32 on the same
+inputs (inputs pre-rounded to the compute dtype so only accumulation order / output rounding differ)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+DT = [torch.bfloat16, torch.float32]
+# output rounding: bf16 has 8 mantissa bits (rms rel err ~2^-9/sqrt(3)), tf32 10 bits
+TOL = {torch.bfloat16: 4e-3, torch.float32: 6e-4}
+
+
+@pytest.fixture(autouse=True)
+def _setup():
+    import pggan_b200  # noqa: F401
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    yield
+    from pggan_b200 import _lib
+    _lib.load().pggan_set_conv_backend(0)
+    import pggan_b200 as pg
+    pg.set_compute_dtype(torch.bfloat16)
+
+
+def rnd(t, dtype):
+    """round to the operand precision the tensor core sees, keep fp32 storage"""
+    if dtype == torch.bfloat16:
+        return t.to(torch.bfloat16).float()
+    # tf32: 10 explicit mantissa bits, round to nearest
+    i = t.contiguous().view(torch.int32)
+    i = (i + 0x1000) & ~0x1FFF
+    return i.view(torch.float32)
+
+
+def to_feat(t, dtype):
+    return t.to(dtype).contiguous(memory_format=torch.channels_last) if t.dim() == 4 else t.to(dtype).contiguous()
+
+
+CONV_SHAPES = [
+    # B, H, W, Cin, Cout, taps
+    (2, 8, 8, 64, 64, 9),
+    (3, 4, 4, 512, 512, 9),        # ragged batch tile (BB=8 > B)
+    (2, 32, 32, 128, 256, 9),
+    (1, 64, 64, 64, 128, 9),
+    (1, 8, 128, 64, 64, 9),        # W == tile width
+    (2, 16, 16, 576, 512, 9),      # K chunk count not a power of two (mbstd-padded layer shape)
+    (5, 1, 1, 512, 8192, 1),       # latent linear
+    (64, 1, 1, 8192, 512, 1),      # D linear
+    (2, 16, 16, 256, 32, 9),       # N tile 32
+]
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("backend", [0, 1])
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+def test_conv_fprop(shape, backend, dtype):
+    from pggan_b200 import ops, _lib
+    import pggan_b200 as pg
+    B, H, W, Ci, Co, taps = shape
+    if backend == 1 and B * H * W * Co * Ci * taps > 3e9:
+        pytest.skip("SIMT cross-check kept to small shapes")
+    pg.set_compute_dtype(dtype)
+    _lib.load().pggan_set_conv_backend(backend)
+    before = _lib.launch_counts()
+    dev = "cuda"
+    k = 3 if taps == 9 else 1
+    x = rnd(torch.randn(B, Ci, H, W, device=dev), dtype)
+    w = rnd(torch.randn(Co, Ci, k, k, device=dev), dtype)
+    b = torch.randn(Co, device=dev)
+    scale = (2.0 / (Ci * taps)) ** 0.5
+    ref = F.leaky_relu((F.conv2d(x, w, b, padding=k // 2)) * scale, 0.2)
+    if taps == 1:
+        y = ops.ConvF.apply(x.view(B, Ci), w.view(Co, Ci), b, scale, 0.2, False)
+        ref = ref.view(B, Co)
+    else:
+        y = ops.ConvF.apply(to_feat(x, dtype), w, b, scale, 0.2, False)
+    torch.cuda.synchronize()
+    after = _lib.launch_counts()
+    if backend == 0:
+        assert after["tcgen05"] > before["tcgen05"], "tensor-core path did not run"
+    else:
+        assert after["simt"] > before["simt"]
+    assert y.dtype == dtype
+    assert rel_l2(y.float(), ref) < TOL[dtype], rel_l2(y.float(), ref)
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_conv_mask_and_raw_out(dtype):
+    from pggan_b200 import ops
+    import pggan_b200 as pg
+    pg.set_compute_dtype(dtype)
+    B, H, W, Ci, Co = 2, 16, 16, 64, 128
+    x = rnd(torch.randn(B, Ci, H, W, device="cuda"), dtype)
+    w = rnd(torch.randn(Co, Ci, 3, 3, device="cuda"), dtype)
+    ysrc = torch.randn(B, Co, H, W, device="cuda")
+    wp = ops._pack(w, "f", dtype)
+    y = ops.k_conv(to_feat(x, dtype), wp, None, Co, 9, 0.05, 1.0, mask_src=to_feat(ysrc, dtype), mask_slope=0.2)
+    ref = F.conv2d(x, w, None, padding=1) * 0.05
+    ref = torch.where(to_feat(ysrc, dtype).float() > 0, ref, ref * 0.2)
+    assert rel_l2(y.float(), ref) < TOL[dtype]
+    yr = ops.k_conv(to_feat(x, dtype), wp, None, Co, 9, 0.05, 1.0, raw_out=True)
+    assert yr.dtype == torch.float32
+    assert rel_l2(yr, F.conv2d(x, w, None, padding=1) * 0.05) < 2e-5
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("backend", [0, 1])
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+def test_conv_dgrad_wgrad(shape, backend, dtype):
+    """first-order backward of ConvF = ConvT (dgrad) + ConvW (wgrad) + ColSum (bias)"""
+    from pggan_b200 import ops, _lib
+    import pggan_b200 as pg
+    B, H, W, Ci, Co, taps = shape
+    if backend == 1 and B * H * W * Co * Ci * taps > 1e9:
+        pytest.skip("SIMT cross-check kept to small shapes")
+    pg.set_compute_dtype(dtype)
+    _lib.load().pggan_set_conv_backend(backend)
+    dev = "cuda"
+    k = 3 if taps == 9 else 1
+    x = rnd(torch.randn(B, Ci, H, W, device=dev), dtype)
+    w = rnd(torch.randn(Co, Ci, k, k, device=dev), dtype)
+    b = torch.randn(Co, device=dev)
+    gy = rnd(torch.randn(B, Co, H, W, device=dev), dtype)
+    scale = (2.0 / (Ci * taps)) ** 0.5
+    xr, wr, br = x.clone().requires_grad_(), w.clone().requires_grad_(), b.clone().requires_grad_()
+    (F.conv2d(xr, wr, br, padding=k // 2) * scale).backward(gy)
+    xm, wm, bm = x.clone().requires_grad_(), w.clone().requires_grad_(), b.clone().requires_grad_()
+    if taps == 1:
+        y = ops.ConvF.apply(xm.view(B, Ci), wm.view(Co, Ci), bm, scale, 1.0, False)
+        y.backward(gy.view(B, Co).to(y.dtype))
+    else:
+        y = ops.ConvF.apply(xm, wm, bm, scale, 1.0, False)
+        y.backward(to_feat(gy, dtype))
+    assert rel_l2(xm.grad, xr.grad) < TOL[dtype], ("dgrad", rel_l2(xm.grad, xr.grad))
+    assert rel_l2(wm.grad, wr.grad) < 1e-4 if dtype == torch.float32 else rel_l2(wm.grad, wr.grad) < 1e-4, \
+        ("wgrad", rel_l2(wm.grad, wr.grad))
+    assert rel_l2(bm.grad, br.grad) < 1e-4, ("bias", rel_l2(bm.grad, br.grad))
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_conv_double_backward(dtype):
+    """grad-of-grad through ConvF -> MaskMul -> ConvT, as R1 / WGAN-GP use it"""
+    from pggan_b200 import ops
+    import pggan_b200 as pg
+    pg.set_compute_dtype(dtype)
+    B, H, W, Ci, Co = 2, 8, 8, 64, 64
+    x = rnd(torch.randn(B, Ci, H, W, device="cuda"), dtype)
+    w = rnd(torch.randn(Co, Ci, 3, 3, device="cuda") * 0.1, dtype)
+    b = torch.randn(Co, device="cuda") * 0.1
+
+    def run(fn):
+        xx, ww, bb = x.clone().requires_grad_(), w.clone().requires_grad_(), b.clone().requires_grad_()
+        y = fn(xx, ww, bb)
+        (g,) = torch.autograd.grad(y.float().sum(), xx, create_graph=True)
+        (g.float() ** 2).sum().backward()
+        return g.detach().float(), ww.grad, xx.grad
+
+    g_ref, gw_ref, _ = run(lambda xx, ww, bb: F.leaky_relu(F.conv2d(xx, ww, bb, padding=1) * 0.1, 0.2))
+    g_my, gw_my, _ = run(lambda xx, ww, bb: ops.ConvF.apply(xx, ww, bb, 0.1, 0.2, False))
+    assert rel_l2(g_my, g_ref) < 2 * TOL[dtype]
+    assert rel_l2(gw_my, gw_ref) < 4 * TOL[dtype], rel_l2(gw_my, gw_ref)
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_elementwise(dtype):
+    from pggan_b200 import ops
+    import pggan_b200 as pg
+    pg.set_compute_dtype(dtype)
+    B, C, H, W = 3, 64, 8, 16
+    x = to_feat(rnd(torch.randn(B, C, H, W, device="cuda"), dtype), dtype)
+    y = to_feat(rnd(torch.randn(B, C, H, W, device="cuda"), dtype), dtype)
+    # mask mul
+    out = ops.k_mask_mul(x, y, 0.2)
+    ref = torch.where(y.float() > 0, x.float(), x.float() * 0.2)
+    assert rel_l2(out.float(), ref) < TOL[dtype]
+    # upsample: exact indexing
+    up = ops.k_upsample(x, 1.0)
+    assert torch.equal(up, x.repeat_interleave(2, 2).repeat_interleave(2, 3))
+    assert up.is_contiguous(memory_format=torch.channels_last)
+    # pool
+    pl = ops.k_pool(x, 0.25)
+    assert rel_l2(pl.float(), F.avg_pool2d(x.float(), 2)) < TOL[dtype]
+    low = to_feat(rnd(torch.randn(B, C, H // 2, W // 2, device="cuda"), dtype), dtype)
+    pb = ops.k_pool(x, 0.25, blend_with=low, alpha=0.3)
+    assert rel_l2(pb.float(), 0.7 * low.float() + 0.3 * F.avg_pool2d(x.float(), 2)) < TOL[dtype]
+    # axpby
+    ab = ops.k_axpby(x, y, 0.25, 0.75)
+    assert rel_l2(ab.float(), 0.25 * x.float() + 0.75 * y.float()) < TOL[dtype]
+    # colsum
+    cs = ops.k_colsum(x, 0.5)
+    assert rel_l2(cs, 0.5 * x.float().sum(dim=(0, 2, 3))) < 1e-5
+    # Upsample/Pool autograd pair
+    xr = x.float().clone().requires_grad_()
+    (ops.Upsample2x.apply(xr, 1.0).float() * up.float()).sum().backward()
+    assert rel_l2(xr.grad, 4 * F.avg_pool2d(up.float(), 2)) < 2 * TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("C", [16, 64, 512])
+def test_pixelnorm(C, dtype):
+    from pggan_b200 import ops
+    import pggan_b200 as pg
+    pg.set_compute_dtype(dtype)
+    x = rnd(torch.randn(4, C, 8, 8, device="cuda"), dtype)
+    xr = x.clone().requires_grad_()
+    ref = xr * torch.rsqrt((xr ** 2).mean(dim=1, keepdim=True) + 1e-8)
+    g = rnd(torch.randn_like(x), dtype)
+    ref.backward(g)
+    xm = x.clone().requires_grad_()
+    y = ops.PixelNorm.apply(xm, 1e-8)
+    y.backward(to_feat(g, dtype))
+    assert rel_l2(y.float(), ref) < TOL[dtype]
+    assert rel_l2(xm.grad, xr.grad) < 3 * TOL[dtype], rel_l2(xm.grad, xr.grad)
+    # 2-D latent path
+    z = torch.randn(6, 512, device="cuda")
+    assert rel_l2(ops.PixelNorm.apply(z, 1e-8).float(), z * torch.rsqrt((z ** 2).mean(1, keepdim=True) + 1e-8)) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("C", [16, 128])
+def test_rgb_ops(C, dtype):
+    from pggan_b200 import ops
+    import pggan_b200 as pg
+    pg.set_compute_dtype(dtype)
+    B, R = 3, 16
+    img = torch.rand(B, 3, R, R, device="cuda") * 2 - 1
+    Wf = torch.randn(C, 3, device="cuda")
+    bf = torch.randn(C, device="cuda")
+    for pool in (False, True):
+        ir, wr, br = img.clone().requires_grad_(), Wf.clone().requires_grad_(), bf.clone().requires_grad_()
+        src = F.avg_pool2d(ir, 2) if pool else ir
+        ref = F.leaky_relu(F.conv2d(src, wr.view(C, 3, 1, 1), br) * 0.7, 0.2)
+        g = torch.randn_like(ref)
+        ref.backward(g)
+        im, wm, bm = img.clone().requires_grad_(), Wf.clone().requires_grad_(), bf.clone().requires_grad_()
+        y = ops.RgbExpand.apply(im, wm, bm, pool, 0.7, 0.2)
+        y.backward(to_feat(g, dtype))
+        assert rel_l2(y.float(), ref) < TOL[dtype]
+        assert rel_l2(im.grad, ir.grad) < 3 * TOL[dtype], ("expand gimg", pool, rel_l2(im.grad, ir.grad))
+        assert rel_l2(wm.grad, wr.grad) < 3 * TOL[dtype], ("expand gW", pool, rel_l2(wm.grad, wr.grad))
+        assert rel_l2(bm.grad, br.grad) < 3 * TOL[dtype]
+    x = rnd(torch.randn(B, C, R, R, device="cuda"), dtype)
+    Wt = torch.randn(3, C, device="cuda")
+    bt = torch.randn(3, device="cuda")
+    for up in (False, True):
+        xr, wr, br = x.clone().requires_grad_(), Wt.clone().requires_grad_(), bt.clone().requires_grad_()
+        ref = F.conv2d(xr, wr.view(3, C, 1, 1), br) * 0.3
+        if up:
+            ref = ref.repeat_interleave(2, 2).repeat_interleave(2, 3)
+        g = torch.randn_like(ref)
+        ref.backward(g)
+        xm, wm, bm = x.clone().requires_grad_(), Wt.clone().requires_grad_(), bt.clone().requires_grad_()
+        y = ops.RgbReduce.apply(to_feat(xm, dtype), wm.t(), bm, up, 0.3, 1.0)
+        y.backward(g)
+        assert y.dtype == torch.float32 and rel_l2(y, ref) < 1e-5
+        assert rel_l2(xm.grad, xr.grad) < 2 * TOL[dtype], ("reduce gx", up)
+        assert rel_l2(wm.grad, wr.grad) < 2 * TOL[dtype], ("reduce gW", up, rel_l2(wm.grad, wr.grad))
+        assert rel_l2(bm.grad, br.grad) < 1e-4
+    # fades: exact fp32 formulas
+    low = torch.randn(B, 3, R // 2, R // 2, device="cuda")
+    out = ops.ImageFade.apply(img, low, 0.3)
+    assert rel_l2(out, 0.7 * low.repeat_interleave(2, 2).repeat_interleave(2, 3) + 0.3 * img) < 1e-6
+    out = ops.ImageFade.apply(img, None, 0.3)
+    ref = 0.7 * F.interpolate(F.avg_pool2d(img, 2), scale_factor=2, mode="nearest") + 0.3 * img
+    assert rel_l2(out, ref) < 1e-6
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("B,group", [(8, 4), (4, 4), (6, 6), (3, 3)])
+def test_mbstd(B, group, dtype):
+    from pggan_b200 import ops
+    import pggan_b200 as pg
+    pg.set_compute_dtype(dtype)
+    C = 64
+    x = rnd(torch.randn(B, C, 4, 4, device="cuda"), dtype)
+
+    def ref_stat(t):
+        y = t.reshape(B // group, group, -1)
+        return torch.sqrt(y.var(dim=1, unbiased=True) + 1e-8).mean(dim=1)
+
+    xr = x.clone().requires_grad_()
+    wgt = torch.randn(B // group, device="cuda")
+    s_ref = ref_stat(xr)
+    (g_ref,) = torch.autograd.grad((s_ref * wgt).sum(), xr, create_graph=True)
+    u = torch.randn_like(x)
+    (g_ref * u).sum().backward()
+    xm = x.clone().requires_grad_()
+    s = ops.MbstdStat.apply(to_feat(xm, dtype), group)
+    (g_my,) = torch.autograd.grad((s * wgt).sum(), xm, create_graph=True)
+    (g_my.float() * u).sum().backward()
+    assert rel_l2(s, s_ref) < 1e-4
+    assert rel_l2(g_my.float(), g_ref) < 3 * TOL[dtype]
+    assert rel_l2(xm.grad, xr.grad) < 6 * TOL[dtype], rel_l2(xm.grad, xr.grad)
+
+
+def test_gp_reduce_and_r1():
+    from pggan_b200 import ops
+    B, n = 5, 3 * 32 * 32
+    g = torch.randn(B, 3, 32, 32, device="cuda") * 0.02
+    pred = torch.randn(B, device="cuda")
+    gr = g.clone().requires_grad_()
+    norms = (gr.view(B, -1) ** 2).sum(1).sqrt()
+    ref = ((norms - 1) ** 2).sum() * 10.0
+    ref.backward()
+    gm = g.clone().requires_grad_()
+    res = ops.GradientPenalty.apply(gm, pred, 10.0, 0.001)
+    res[0].backward()
+    assert rel_l2(res[0], ref) < 1e-5
+    assert rel_l2(res[1], (pred ** 2).sum() * 0.001) < 1e-5
+    assert rel_l2(gm.grad, gr.grad) < 1e-5
+    gm2 = g.clone().requires_grad_()
+    (0.5 * ops.RowsSumSq.apply(gm2).mean(0)).backward()
+    assert rel_l2(gm2.grad, g / B) < 1e-5
+    # odd row length (scalar path)
+    h = torch.randn(3, 1001, device="cuda")
+    assert rel_l2(ops.RowsSumSq.apply(h), (h ** 2).sum(1)) < 1e-5
+
+
+def test_fused_adam_matches_torch():
+    from pggan_b200 import FusedAdam
+    torch.manual_seed(1)
+    shapes = [(512, 512, 3, 3), (512,), (3, 64, 1, 1), (1, 512), (1,), (70000,)]
+    mine = [torch.nn.Parameter(torch.randn(s, device="cuda")) for s in shapes]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in mine]
+    opt_m = FusedAdam(mine, lr=1e-3, betas=(0.0, 0.99))
+    opt_r = torch.optim.Adam(ref, lr=1e-3, betas=(0.0, 0.99))
+    for step in range(4):
+        opt_m.zero_grad()
+        opt_r.zero_grad()
+        for pm, pr in zip(mine, ref):
+            g = torch.randn_like(pm)
+            pm.grad.add_(g)
+            pr.grad = g.clone()
+        opt_m.step()
+        opt_r.step()
+    for pm, pr in zip(mine, ref):
+        assert rel_l2(pm, pr) < 1e-6
+    assert int(opt_m.step_count.item()) == 4

@@ -1,0 +1,170 @@
+"""Network / loss / step parity on the GPU: pggan_b200 modules (CUDA kernels through the C ABI)
+against the oracle (oracle/pggan_oracle.py, fp32 PyTorch) on identical weights and inputs.
+
+Tolerances are BASELINE.json's: G images and D logits <= 1e-3 relative L2 in fp32/TF32 and <= 1e-2 in
+bf16; gradient-penalty value <= 1e-3 relative (TF32) — relative L2 over the whole tensor."""
+import pytest
+import torch
+
+from conftest import rel_l2
+from gpu_util import build_pair, req, grads_by_name
+from oracle import pggan_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+OUT_TOL = {torch.float32: 1e-3, torch.bfloat16: 1e-2}
+GRAD_TOL = {torch.float32: 3e-3, torch.bfloat16: 3e-2}
+
+
+@pytest.fixture(autouse=True)
+def _setup():
+    import pggan_b200 as pg
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    pg.set_compute_dtype(torch.bfloat16)
+
+
+def _check_param_grads(mine, ref_params, tol, what):
+    worst = 0.0
+    for k, g in mine.items():
+        gr = ref_params[k].grad
+        if gr is None:
+            assert g is None or float(g.abs().max()) == 0.0, (what, k)
+            continue
+        assert g is not None, (what, k)
+        den = float(gr.norm())
+        if den < 1e-12:
+            continue
+        e = rel_l2(g, gr)
+        worst = max(worst, e)
+        assert e < tol, (what, k, e)
+    return worst
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("scale,alpha,width,batch", [(0, 0.0, 512, 8), (1, 0.5, 512, 8), (3, 0.5, 512, 8),
+                                                     (2, 1.0, 64, 6), (5, 0.3, 64, 4)])
+def test_forward_and_first_order(scale, alpha, width, batch, dtype):
+    import pggan_b200 as pg
+    pg.set_compute_dtype(dtype)
+    depths = [width] * (scale + 1)
+    latent = width
+    G, D, g_sd, d_sd = build_pair(scale, depths, latent, seed=scale)
+    G.alpha = D.alpha = alpha
+    res = 4 * 2 ** scale
+    torch.manual_seed(100 + scale)
+    z = torch.randn(batch, latent, device="cuda")
+    x = torch.rand(batch, 3, res, res, device="cuda") * 2 - 1
+
+    gp_, dp_ = req(g_sd), req(d_sd)
+    img_ref = O.generator_forward(gp_, z, alpha)
+    xr = x.clone().requires_grad_()
+    logit_ref, feat_ref = O.discriminator_forward(dp_, xr, alpha, True)
+
+    img = G(z)
+    xm = x.clone().requires_grad_()
+    logit, feat = D(xm, True)
+    assert img.dtype == torch.float32 and img.shape == img_ref.shape
+    assert logit.dtype == torch.float32 and logit.shape == (batch, 1)
+    e_img, e_logit, e_feat = rel_l2(img, img_ref), rel_l2(logit, logit_ref), rel_l2(feat, feat_ref)
+    print(f"\n[{dtype}] scale {scale} width {width}: img {e_img:.2e} logit {e_logit:.2e} feat {e_feat:.2e}")
+    assert e_img < OUT_TOL[dtype], e_img
+    assert e_logit < OUT_TOL[dtype], e_logit
+    assert e_feat < OUT_TOL[dtype], e_feat
+
+    # first-order gradients of both networks
+    wimg = torch.randn_like(img_ref)
+    (img_ref * wimg).sum().backward()
+    (img * wimg).sum().backward()
+    wg = _check_param_grads(grads_by_name(G), gp_, GRAD_TOL[dtype], "G")
+    wl = torch.randn_like(logit_ref)
+    (logit_ref * wl).sum().backward()
+    (logit * wl).sum().backward()
+    wd = _check_param_grads(grads_by_name(D), dp_, GRAD_TOL[dtype], "D")
+    e_gx = rel_l2(xm.grad, xr.grad)
+    print(f"    worst param-grad err G {wg:.2e} D {wd:.2e}; dD/dx {e_gx:.2e}")
+    assert e_gx < GRAD_TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("scale,width,batch", [(0, 512, 8), (2, 512, 8), (3, 64, 4)])
+def test_r1_and_gradient_penalty(scale, width, batch, dtype):
+    """the double backward through D: value and accumulated D parameter gradients"""
+    import pggan_b200 as pg
+    pg.set_compute_dtype(dtype)
+    alpha = 0.5 if scale else 0.0
+    depths = [width] * (scale + 1)
+    G, D, g_sd, d_sd = build_pair(scale, depths, width, seed=10 + scale)
+    G.alpha = D.alpha = alpha
+    res = 4 * 2 ** scale
+    torch.manual_seed(7)
+    x = torch.rand(batch, 3, res, res, device="cuda") * 2 - 1
+    fake = torch.rand(batch, 3, res, res, device="cuda") * 2 - 1
+    eps = torch.rand(batch, 1)
+    args = pg.make_args()
+    lc = pg.WGANGPLoss(args)
+
+    # ---- WGAN-GP (reference pggan/loss.py:54-92)
+    dp_ = req(d_sd)
+    xr = x.clone().requires_grad_()
+    gp_ref = O.gradient_penalty(lambda t: O.discriminator_forward(dp_, t, alpha), xr, fake, 10.0, eps=eps)
+    xm = x.clone().requires_grad_()
+    D.zero_grad()
+    gp = lc.get_gradient_penalty({"img_real": xm, "img_fake": fake, "pred_real": D(xm)}, D, backward=True, eps=eps)
+    e_gp = abs(gp - float(gp_ref)) / abs(float(gp_ref))
+    tol_v = 1e-3 if dtype == torch.float32 else 1e-2
+    worst = _check_param_grads(grads_by_name(D), dp_, 5 * GRAD_TOL[dtype], "GP")
+    print(f"\n[{dtype}] scale {scale} width {width}: GP {gp:.5f} vs {float(gp_ref):.5f} rel {e_gp:.2e}; "
+          f"worst D-grad err {worst:.2e}")
+    assert e_gp < tol_v, e_gp
+    assert D.decision_layer.module.bias.grad is None or float(D.decision_layer.module.bias.grad.abs().max()) == 0.0
+
+    # ---- live loss: BCE + R1 (reference pggan/loss.py:16-27)
+    dp_ = req(d_sd)
+    xr = x.clone().requires_grad_()
+    ld = O.loss_D_live(O.discriminator_forward(dp_, xr, alpha), O.discriminator_forward(dp_, fake, alpha), xr)
+    ld["L_D"].backward()
+    xm = x.clone().requires_grad_()
+    D.zero_grad()
+    L_D = lc.get_loss_D({"pred_real": D(xm), "pred_fake": D(fake), "img_real": xm, "img_fake": fake})
+    L_D.backward()
+    e_l = rel_l2(L_D, ld["L_D"])
+    worst = _check_param_grads(grads_by_name(D), dp_, 5 * GRAD_TOL[dtype], "R1")
+    print(f"    live L_D rel {e_l:.2e}; worst D-grad err {worst:.2e}")
+    assert e_l < tol_v
+    assert abs(lc.loss_dict["L_D"] - round(float(ld["L_D"]), 4)) < max(2e-3, 1e-2 * abs(float(ld["L_D"])))
+
+
+@pytest.mark.parametrize("variant", ["W", "L"])
+@pytest.mark.parametrize("scale,width,batch", [(0, 64, 8), (2, 64, 8)])
+def test_train_step_matches_oracle(scale, width, batch, variant):
+    """one full D+G step (pggan/model.py:206-255) in tf32 mode: parameter deltas after Adam"""
+    import pggan_b200 as pg
+    pg.set_compute_dtype(torch.float32)
+    alpha = 0.5 if scale else 0.0
+    depths = [width] * (scale + 1)
+    args = pg.make_args(latent_dim=width, depths=depths)
+    tr = pg.ProgressiveGAN(args, 0, variant=variant)
+    tr.set_scale(scale, alpha)
+    g_sd = {k: v.detach().clone() for k, v in tr.G.state_dict().items()}
+    d_sd = {k: v.detach().clone() for k, v in tr.D.state_dict().items()}
+    otr = O.OracleTrainer(g_sd, d_sd, alpha=alpha, variant=variant, latent_dim=width)
+    res = 4 * 2 ** scale
+    torch.manual_seed(3)
+    img = torch.rand(batch, 3, res, res, device="cuda") * 2 - 1
+    z_d = torch.randn(batch, width, device="cuda")
+    z_g = torch.randn(batch, width, device="cuda")
+    eps = torch.rand(batch, 1)
+    otr.train_step(img, z_d=z_d, z_g=z_g, eps=eps)
+    tr.train_step(img, latent_D=z_d, latent_G=z_g, eps=eps.cuda())
+    assert abs(tr.loss_collector.loss_dict["L_G"] - otr.loss_dict["L_G"]) < 2e-3 * max(1.0, abs(otr.loss_dict["L_G"]))
+    if variant == "W":
+        assert abs(tr.loss_collector.loss_dict["L_D_gp"] - otr.loss_dict["L_D_gp"]) < 2e-3 * abs(otr.loss_dict["L_D_gp"])
+    for name, mod, ref, sd0, lr in (("G", tr.G, otr.g, g_sd, 1e-4), ("D", tr.D, otr.d, d_sd, 1e-5)):
+        for k, p in mod.named_parameters():
+            d_my = p.detach() - sd0[k]
+            d_ref = ref[k].detach() - sd0[k]
+            # Adam's first step is lr*g/(|g|+eps): compare where the reference gradient is not ~0
+            bad = ((d_my - d_ref).abs() > 0.3 * lr).float().mean().item()
+            assert bad < 0.03, (name, k, bad)

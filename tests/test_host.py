@@ -1,0 +1,69 @@
+"""Host-side logic that needs no GPU: module tree / state_dict keys, the C-ABI library loads and
+exports every declared symbol, schedule bookkeeping."""
+import os
+import re
+
+import torch
+
+from oracle import pggan_oracle as O
+
+
+def test_state_dict_keys_match_reference_layout():
+    """Appendix C of SURVEY.md: key names/shapes of the reference at scale 3"""
+    import pggan_b200 as pg
+    G = pg.Generator(512, 512)
+    D = pg.Discriminator(512, apply_minibatch_norm=True)
+    for d in (512, 512, 256):
+        G.add_block(d)
+        D.add_block(d)
+    gk, dk = G.state_dict(), D.state_dict()
+    assert gk["latent_format_layer.module.weight"].shape == (8192, 512)
+    assert gk["first_block.block.0.module.weight"].shape == (512, 512, 3, 3)
+    assert gk["blocks.2.block.0.module.weight"].shape == (256, 512, 3, 3)
+    assert gk["blocks.2.block.3.module.bias"].shape == (256,)
+    assert gk["toRGB_blocks.3.toRGB.module.weight"].shape == (3, 256, 1, 1)
+    assert dk["fromRGB_blocks.3.fromRGB.module.weight"].shape == (256, 3, 1, 1)
+    assert dk["blocks.2.block.0.module.weight"].shape == (256, 256, 3, 3)
+    assert dk["blocks.2.block.2.module.weight"].shape == (512, 256, 3, 3)
+    assert dk["minibatch_normalization_block.conv.module.weight"].shape == (512, 513, 3, 3)
+    assert dk["minibatch_normalization_block.linear.module.weight"].shape == (512, 8192)
+    assert dk["decision_layer.module.weight"].shape == (1, 512)
+    assert set(gk) == set(O.init_generator_sd(512, [512, 512, 512, 256], 3))
+    assert set(dk) == set(O.init_discriminator_sd([512, 512, 512, 256], 3))
+
+
+def test_library_exports_every_declared_symbol():
+    from pggan_b200 import _lib
+    lib = _lib.load()                      # raises if the .so is missing: there is no fallback
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "pggan_b200.h")).read()
+    declared = set(re.findall(r"\b(pggan_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.pggan_version() >= 100
+
+
+def test_ops_refuse_cpu_tensors():
+    import pytest
+    import pggan_b200 as pg
+    conv = pg.EqualizedConv2d(64, 64, 3, padding=1)
+    with pytest.raises(Exception):
+        conv(torch.randn(1, 64, 4, 4))
+
+
+def test_schedule_matches_reference_bookkeeping():
+    """check_jump / change_alpha arithmetic of reference pggan/model.py:176-204, without kernels"""
+    import pggan_b200 as pg
+    tr = pg.ProgressiveGAN.__new__(pg.ProgressiveGAN)
+    tr.args = pg.make_args()
+    tr.scale_index = 1
+    tr.alpha_index = 0
+    tr.G = type("X", (), {"alpha": 0})()
+    tr.D = type("X", (), {"alpha": 0})()
+    tr.alpha_jump_value = 1 / tr.args.alpha_jump_Ntimes[1]
+    tr.next_alpha_jump_step = 2000
+    tr.next_scale_jump_step = 10 ** 9
+    for step in range(2000, 2000 + 100 * 100 + 1):
+        tr.check_jump(step)
+    assert tr.alpha_index == 100 and abs(tr.G.alpha - 1.0) < 1e-9 and tr.next_alpha_jump_step == 0
