@@ -9,7 +9,7 @@
  *   - returns PG_OK or a negative error code; pggan_last_error() gives the message.
  *
  * Layouts.  Feature maps are NHWC ("channels_last"): [B][H][W][C], dtype PG_BF16 or PG_F32
- * (PG_F32 operands run on kind::tf32 tensor-core MMAs; they are stored pre-rounded to tf32).
+ * (PG_F32 operands run on kind::tf32 tensor-core MMAs; the Python layer feeds them as 3xTF32 splits).
  * RGB images, logits, latents, parameters and parameter gradients are fp32 in the reference's
  * own layouts (NCHW images, OIHW conv weights, [out,in] linear weights).
  *
@@ -31,7 +31,7 @@ extern "C" {
 
 #define PG_BF16 0
 #define PG_F32 1
-#define PG_F32_RAW 2 /* output-only: fp32 without the tf32 pre-rounding (final logits / images) */
+#define PG_F32_RAW 2 /* output-only: fp32 result from any operand dtype (final logits / images) */
 
 /* conv backend selection (bring-up / debugging): 0 = tcgen05 wherever the shape allows (default),
  * 1 = force the SIMT direct kernels. */
@@ -60,6 +60,12 @@ int pggan_unpack_wgrad(const float* in, float* out, int n1, int n2, int taps, in
                        int64_t s_n1, int64_t s_n2, int64_t s_t, int64_t s_c, float scale, int accumulate,
                        void* stream);
 
+/* fp32 mode = 3xTF32.  The tensor core truncates fp32 operands to tf32 (hi); this writes three copies
+ * of in [m][c], one of them (slot lo_slot) holding lo = x - trunc_tf32(x), concatenated along channels
+ * ([m][3c]) or along rows ([3m][c]).  A GEMM over (x,x,x_lo) x (w,w_lo,w) then yields
+ * hi*hi + hi*lo + lo*hi, i.e. fp32-class products, with the unchanged tensor-core kernels. */
+int pggan_split3(const float* in, float* out, int64_t m, int c, int along_channels, int lo_slot, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution / linear, forward-style:
  *   y[b,h,w,n] = post( scale * ( sum_{t,c} x[b, h+dh(t), w+dw(t), c] * wp[n][t][c] + bias[n] ) )
@@ -81,6 +87,10 @@ typedef struct {
     int32_t B, H, W, C, N, taps;
     int32_t dtype, out_dtype;
     float scale, slope, mask_slope;
+    /* PG_F32 only — 3xTF32 workspaces the tensor-core path fills with pggan_split3:
+     * ws_x: 3*B*H*W*C floats, ws_w: 3*N*taps*C floats (ignored by the SIMT path / PG_BF16). */
+    void* ws_x;
+    void* ws_w;
 } pg_conv_params;
 int pggan_conv_fprop(const pg_conv_params* p, void* stream);
 
@@ -95,6 +105,9 @@ typedef struct {
     float* acc;      /* [N][taps][C] fp32 */
     int32_t B, H, W, C, N, taps;
     int32_t dtype;
+    /* PG_F32 only — 3xTF32 workspaces: ws_g: 3*B*H*W*N floats, ws_x: 3*B*H*W*C floats */
+    void* ws_g;
+    void* ws_x;
 } pg_wgrad_params;
 int pggan_conv_wgrad(const pg_wgrad_params* p, void* stream);
 

@@ -40,6 +40,33 @@ import torch.nn.functional as F
 Tensor = torch.Tensor
 StateDict = Dict[str, Tensor]
 
+# ---------------------------------------------------------------------------- emulation
+# emulate(torch.bfloat16) makes the network functions below round tensors to bf16 at exactly the
+# points where the CUDA path stores bf16 (weights of every tensor-core GEMM, every feature map written
+# to HBM) while all arithmetic stays fp32 — i.e. "the reference's algorithm evaluated on bf16-rounded
+# operands with fp32 accumulation".  With it, LeakyReLU masks agree with the CUDA path, so gradients
+# can be compared tightly (against the plain fp32 oracle, gradient parity is limited by mask flips:
+# rel err ~ 0.8*sqrt(fraction of flipped pre-activation signs)).
+_EMU = None
+
+
+class emulate:
+    def __init__(self, dtype):
+        self.dtype = dtype
+
+    def __enter__(self):
+        global _EMU
+        self.prev = _EMU
+        _EMU = self.dtype if self.dtype in (torch.bfloat16, torch.float16) else None
+
+    def __exit__(self, *a):
+        global _EMU
+        _EMU = self.prev
+
+
+def _q(t: Tensor) -> Tensor:
+    return t if _EMU is None else t.to(_EMU).float()
+
 
 # --------------------------------------------------------------------------- layers
 def he_constant(weight: Tensor) -> float:
@@ -107,21 +134,27 @@ def count_blocks(sd: StateDict) -> int:
 def generator_forward(sd: StateDict, z: Tensor, alpha: float, slope: float = 0.2,
                       apply_pixel_norm: bool = True) -> Tensor:
     nb = count_blocks(sd)
-    pn = pixel_norm if apply_pixel_norm else (lambda t: t)
-    x = pn(z)
+    pn = (lambda t: _q(pixel_norm(t))) if apply_pixel_norm else (lambda t: t)
+
+    def conv_act(t, prefix, pad, sl):
+        w, b = _p(sd, prefix)
+        return _q(lrelu(eq_conv2d(t, _q(w), b, pad), sl))
+
+    x = pn(_q(z))
     x = x.reshape(x.shape[0], -1)
-    x = lrelu(eq_linear(x, *_p(sd, "latent_format_layer")), slope)
+    w, b = _p(sd, "latent_format_layer")
+    x = _q(lrelu(eq_linear(x, _q(w), b), slope))
     x = x.reshape(x.shape[0], -1, 4, 4)
     x = pn(x)
-    x = pn(lrelu(eq_conv2d(x, *_p(sd, "first_block.block.0"), 1), 0.2))
+    x = pn(conv_act(x, "first_block.block.0", 1, 0.2))
     x_up = None
     if nb == 1:
         x_up = upscale2d(eq_conv2d(x, *_p(sd, f"toRGB_blocks.{nb - 1}.toRGB"), 0))
     second = 3 if apply_pixel_norm else 2          # Sequential index of the 2nd conv
     for i in range(nb):
         x = upscale2d(x)
-        x = pn(lrelu(eq_conv2d(x, *_p(sd, f"blocks.{i}.block.0"), 1), 0.2))
-        x = pn(lrelu(eq_conv2d(x, *_p(sd, f"blocks.{i}.block.{second}"), 1), 0.2))
+        x = pn(conv_act(x, f"blocks.{i}.block.0", 1, 0.2))
+        x = pn(conv_act(x, f"blocks.{i}.block.{second}", 1, 0.2))
         if i == nb - 2:
             x_up = upscale2d(eq_conv2d(x, *_p(sd, f"toRGB_blocks.{nb - 1}.toRGB"), 0))
     x = eq_conv2d(x, *_p(sd, f"toRGB_blocks.{nb}.toRGB"), 0)
@@ -133,24 +166,32 @@ def generator_forward(sd: StateDict, z: Tensor, alpha: float, slope: float = 0.2
 def discriminator_forward(sd: StateDict, x: Tensor, alpha: float, get_feature: bool = False,
                           apply_minibatch_norm: bool = True):
     nb = count_blocks(sd)
+
+    def conv_act(t, prefix, pad):
+        w, b = _p(sd, prefix)
+        return _q(lrelu(eq_conv2d(t, _q(w), b, pad), 0.2))
+
     x_down = None
-    if nb:
-        x_down = lrelu(eq_conv2d(downscale2d(x), *_p(sd, f"fromRGB_blocks.{nb - 1}.fromRGB"), 0), 0.2)
-    x = lrelu(eq_conv2d(x, *_p(sd, f"fromRGB_blocks.{nb}.fromRGB"), 0), 0.2)
+    if nb:      # the RGB 1x1 layers run in fp32 on fp32 weights; only their output is stored rounded
+        x_down = _q(lrelu(eq_conv2d(downscale2d(x), *_p(sd, f"fromRGB_blocks.{nb - 1}.fromRGB"), 0), 0.2))
+    x = _q(lrelu(eq_conv2d(x, *_p(sd, f"fromRGB_blocks.{nb}.fromRGB"), 0), 0.2))
     merge = nb > 0
     for i in reversed(range(nb)):
-        x = lrelu(eq_conv2d(x, *_p(sd, f"blocks.{i}.block.0"), 1), 0.2)
-        x = lrelu(eq_conv2d(x, *_p(sd, f"blocks.{i}.block.2"), 1), 0.2)
+        x = conv_act(x, f"blocks.{i}.block.0", 1)
+        x = conv_act(x, f"blocks.{i}.block.2", 1)
         x = F.avg_pool2d(x, (2, 2))
         if merge:
             merge = False
             x = (1 - alpha) * x_down + alpha * x
+        x = _q(x)
     if apply_minibatch_norm:
-        x = mbstd_concat(x, 4)
-    x = lrelu(eq_conv2d(x, *_p(sd, "minibatch_normalization_block.conv"), 1), 0.2)
+        x = _q(mbstd_concat(x, 4))
+    x = conv_act(x, "minibatch_normalization_block.conv", 1)
     x = x.reshape(x.shape[0], -1)
-    x = lrelu(eq_linear(x, *_p(sd, "minibatch_normalization_block.linear")), 0.2)
-    out = eq_linear(x, *_p(sd, "decision_layer"))
+    w, b = _p(sd, "minibatch_normalization_block.linear")
+    x = _q(lrelu(eq_linear(x, _q(w), b), 0.2))
+    w, b = _p(sd, "decision_layer")
+    out = eq_linear(x, _q(w), b)
     return (out, x) if get_feature else out
 
 

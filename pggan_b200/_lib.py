@@ -21,6 +21,7 @@ class ConvParams(Structure):
         ("B", c_int32), ("H", c_int32), ("W", c_int32), ("C", c_int32), ("N", c_int32), ("taps", c_int32),
         ("dtype", c_int32), ("out_dtype", c_int32),
         ("scale", c_float), ("slope", c_float), ("mask_slope", c_float),
+        ("ws_x", c_void_p), ("ws_w", c_void_p),
     ]
 
 
@@ -29,6 +30,7 @@ class WgradParams(Structure):
         ("g", c_void_p), ("x", c_void_p), ("acc", c_void_p),
         ("B", c_int32), ("H", c_int32), ("W", c_int32), ("C", c_int32), ("N", c_int32), ("taps", c_int32),
         ("dtype", c_int32),
+        ("ws_g", c_void_p), ("ws_x", c_void_p),
     ]
 
 
@@ -47,6 +49,7 @@ SIGNATURES = {
                                   c_int64, c_int64, c_int64, c_void_p]),
     "pggan_unpack_wgrad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int64, c_int64, c_int64,
                                    c_int64, c_int64, c_float, c_int, c_void_p]),
+    "pggan_split3": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
     "pggan_conv_fprop": (c_int, [POINTER(ConvParams), c_void_p]),
     "pggan_conv_wgrad": (c_int, [POINTER(WgradParams), c_void_p]),
     "pggan_lrelu_mask_mul": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_int, c_void_p]),

@@ -53,7 +53,8 @@ int encode_tmap(CUtensorMap* map, int dtype, int rank, const void* base, const u
     EncodeTiledFn fn = get_encode_fn();
     PG_CHECK(fn != nullptr, PG_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+    CUtensorMapSwizzle sw = swizzle_bytes == 12832 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                            : swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                             : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                             : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
                                                   : CU_TENSOR_MAP_SWIZZLE_NONE;

@@ -37,6 +37,9 @@ int num_sms();
 int encode_tmap(CUtensorMap* map, int dtype, int rank, const void* base, const uint64_t* dims,
                 const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
 
+// 3xTF32 operand split (elementwise.cu); see pggan_split3 in the header
+int split3_launch(const float* in, float* out, long long m, int c, int along_channels, int lo_slot, cudaStream_t s);
+
 inline int dtype_size(int dt) { return dt == PG_BF16 ? 2 : 4; }
 
 // ------------------------------------------------------------------------------ dtypes
@@ -49,13 +52,9 @@ template <> struct DT<__nv_bfloat16> {
 template <> struct DT<float> {
     static constexpr int kEnum = PG_F32;
     static __device__ __forceinline__ float to_f(float v) { return v; }
-    // fp32 activations feed kind::tf32 MMAs, which ignore the low 13 mantissa bits: round to
-    // nearest here so the truncation in the tensor core is exact (no systematic shrink).
-    static __device__ __forceinline__ float from_f(float v) {
-        uint32_t r;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-        return __uint_as_float(r);
-    }
+    // fp32 feature maps are stored UNROUNDED: the fp32 mode runs every GEMM as 3xTF32
+    // (hi*hi + hi*lo + lo*hi, see pggan_split3) so the tensor core's truncation to tf32 is compensated.
+    static __device__ __forceinline__ float from_f(float v) { return v; }
 };
 
 // 16-byte vector of T
@@ -208,13 +207,14 @@ __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t adesc, uint64_
 //   K-major  operand: rows of 128 B (one swizzle span of K), 8-row groups SBO bytes apart.
 //   MN-major operand: rows of 128 B (64 bf16 / 32 tf32 along MN), 8 K-rows per group SBO bytes apart,
 //                     successive 128 B MN spans LBO bytes apart.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type = 2 /* SWIZZLE_128B */) {
     uint64_t d = 0;
     d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
     d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= 1ull << 46;   // descriptor version (Blackwell)
-    d |= 2ull << 61;   // layout type: SWIZZLE_128B
+    d |= static_cast<uint64_t>(layout_type) << 61;   // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
     return d;
 }
 // Instruction descriptor for kind::f16 / kind::tf32, fp32 accumulate, dense.

@@ -227,12 +227,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
                             float4 pk;
-                            // fp32 activations are stored pre-rounded to tf32 when they feed another MMA
-                            const bool rnd = kTF32 && a.out_dtype == PG_F32;
-                            pk.x = rnd ? DT<float>::from_f(v[c * 4 + 0]) : v[c * 4 + 0];
-                            pk.y = rnd ? DT<float>::from_f(v[c * 4 + 1]) : v[c * 4 + 1];
-                            pk.z = rnd ? DT<float>::from_f(v[c * 4 + 2]) : v[c * 4 + 2];
-                            pk.w = rnd ? DT<float>::from_f(v[c * 4 + 3]) : v[c * 4 + 3];
+                            pk.x = v[c * 4 + 0];
+                            pk.y = v[c * 4 + 1];
+                            pk.z = v[c * 4 + 2];
+                            pk.w = v[c * 4 + 3];
                             reinterpret_cast<float4*>(op)[c] = pk;
                         }
                     }
@@ -281,7 +279,7 @@ __global__ void conv_direct_kernel(const T* __restrict__ x, const T* __restrict_
         if (out_dtype == PG_BF16)
             reinterpret_cast<__nv_bfloat16*>(y)[idx] = __float2bfloat16_rn(v);
         else
-            reinterpret_cast<float*>(y)[idx] = (sizeof(T) == 4 && out_dtype == PG_F32) ? DT<float>::from_f(v) : v;
+            reinterpret_cast<float*>(y)[idx] = v;
     }
 }
 
@@ -340,14 +338,30 @@ static int launch_tc(const pg_conv_params* p, cudaStream_t stream) {
 }
 
 template <typename T>
-static int conv_dispatch(const pg_conv_params* p, cudaStream_t stream) {
+static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream) {
     constexpr int BK = 128 / sizeof(T);
-    const bool tc_ok = g_conv_backend == PG_BACKEND_AUTO && is_pow2(p->H) && is_pow2(p->W) && (p->C % BK == 0) &&
-                       (p->N % 32 == 0) && (p->taps == 1 || p->taps == 9) &&
+    constexpr bool kF32 = sizeof(T) == 4;
+    pg_conv_params local = *p_in;
+    const pg_conv_params* p = &local;
+    // fp32 runs as 3xTF32: K is tripled ((x,x,x_lo) . (w,w_lo,w)) through caller-provided workspaces
+    const int Ceff = kF32 ? 3 * p->C : p->C;
+    const bool tc_ok = g_conv_backend == PG_BACKEND_AUTO && is_pow2(p->H) && is_pow2(p->W) && (Ceff % BK == 0) &&
+                       (p->N % 32 == 0) && (p->taps == 1 || p->taps == 9) && (!kF32 || (p->C % 4 == 0 && p->ws_x && p->ws_w)) &&
                        (reinterpret_cast<uintptr_t>(p->x) % 16 == 0) && (reinterpret_cast<uintptr_t>(p->wp) % 16 == 0) &&
                        (reinterpret_cast<uintptr_t>(p->y) % 16 == 0) &&
                        (p->mask_src == nullptr || reinterpret_cast<uintptr_t>(p->mask_src) % 16 == 0);
     if (tc_ok) {
+        if (kF32) {
+            int rc = split3_launch(reinterpret_cast<const float*>(p->x), reinterpret_cast<float*>(p->ws_x),
+                                   (long long)p->B * p->H * p->W, p->C, 1, 2, stream);
+            if (rc != PG_OK) return rc;
+            rc = split3_launch(reinterpret_cast<const float*>(p->wp), reinterpret_cast<float*>(p->ws_w),
+                               (long long)p->N * p->taps, p->C, 1, 1, stream);
+            if (rc != PG_OK) return rc;
+            local.x = p->ws_x;
+            local.wp = p->ws_w;
+            local.C = Ceff;
+        }
         // largest N tile that still yields enough CTAs to occupy the machine
         const int bw = p->W < 128 ? p->W : 128;
         const int bh = p->H < (128 / bw) ? p->H : (128 / bw);

@@ -295,6 +295,31 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ in, float* __restr
     }
 }
 
+// ------------------------------------------------------------------------------ 3xTF32 operand split
+// in [M][C] fp32 -> three copies, one of which holds lo = x - trunc_tf32(x) (the tensor core truncates
+// fp32 operands to tf32, so the plain copies act as hi).  Concatenated along channels ([M][3C]) for the
+// K-major operands of the fprop-style GEMM, or along rows ([3M][C]) for the pixel-reduction of wgrad.
+__global__ void split3_kernel(const float* __restrict__ in, float* __restrict__ out, long long M, int CV,
+                              int along_channels, int lo_slot) {
+    const long long total = M * CV;
+    const long long C = 4LL * CV;
+    GRID_STRIDE(i, total) {
+        const long long m = i / CV;
+        const int cv = static_cast<int>(i % CV);
+        const float4 v = __ldg(reinterpret_cast<const float4*>(in + m * C) + cv);
+        float4 lo;
+        lo.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+        lo.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+        lo.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+        lo.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+#pragma unroll
+        for (int slot = 0; slot < 3; ++slot) {
+            float* dst = along_channels ? out + m * 3 * C + slot * C + cv * 4 : out + (slot * M + m) * C + cv * 4;
+            *reinterpret_cast<float4*>(dst) = (slot == lo_slot) ? lo : v;
+        }
+    }
+}
+
 }  // namespace pg
 
 using namespace pg;
@@ -472,4 +497,20 @@ extern "C" int pggan_unpack_wgrad(const float* in, float* out, int n1, int n2, i
     PG_LAUNCH_CHECK();
     g_other_launches++;
     return PG_OK;
+}
+
+namespace pg {
+int split3_launch(const float* in, float* out, long long m, int c, int along_channels, int lo_slot, cudaStream_t s) {
+    PG_CHECK(in && out && m > 0 && c > 0 && c % 4 == 0 && lo_slot >= 0 && lo_slot < 3, PG_ERR_ARG,
+             "pggan_split3: bad args (c=%d must be a multiple of 4)", c);
+    PG_CHECK(al16(in) && al16(out), PG_ERR_ARG, "pggan_split3: pointers must be 16-byte aligned");
+    split3_kernel<<<ew_grid(m * (c / 4), 256), 256, 0, s>>>(in, out, m, c / 4, along_channels, lo_slot);
+    PG_LAUNCH_CHECK();
+    g_other_launches++;
+    return PG_OK;
+}
+}  // namespace pg
+
+extern "C" int pggan_split3(const float* in, float* out, int64_t m, int c, int along_channels, int lo_slot, void* stream) {
+    return pg::split3_launch(in, out, m, c, along_channels, lo_slot, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -162,8 +162,10 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint32_t koff = k * Cfg::UMMA_K * 128;   // UMMA_K pixel rows of 128 B
-                        const uint64_t adesc = make_smem_desc(sa + koff, Cfg::kGroupBytes, 1024);
-                        const uint64_t bdesc = make_smem_desc(sb + koff, Cfg::kGroupBytes, 1024);
+                        // bf16: SWIZZLE_128B, 8-row K groups 1024 B apart; tf32 MN-major operands only exist in
+                        // the 32-byte-atom flavour: SWIZZLE_128B_BASE32B, 4-row K groups 512 B apart
+                        const uint64_t adesc = make_smem_desc(sa + koff, Cfg::kGroupBytes, kTF32 ? 512 : 1024, kTF32 ? 1 : 2);
+                        const uint64_t bdesc = make_smem_desc(sb + koff, Cfg::kGroupBytes, kTF32 ? 512 : 1024, kTF32 ? 1 : 2);
                         umma_ss<kTF32>(d_tmem, adesc, bdesc, idesc, (kc > k0 || k > 0) ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[stage]);
@@ -286,13 +288,13 @@ static int launch_wg(const pg_wgrad_params* p, cudaStream_t stream) {
     {
         uint64_t dims[4] = {(uint64_t)p->N, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
         uint64_t strides[3] = {(uint64_t)p->N * es, (uint64_t)p->W * p->N * es, (uint64_t)p->H * p->W * p->N * es};
-        int rc = encode_tmap(&tg, DT<T>::kEnum, 4, p->g, dims, strides, box, 128);
+        int rc = encode_tmap(&tg, DT<T>::kEnum, 4, p->g, dims, strides, box, sizeof(T) == 4 ? 12832 : 128);
         if (rc != PG_OK) return rc;
     }
     {
         uint64_t dims[4] = {(uint64_t)p->C, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
         uint64_t strides[3] = {(uint64_t)p->C * es, (uint64_t)p->W * p->C * es, (uint64_t)p->H * p->W * p->C * es};
-        int rc = encode_tmap(&tx, DT<T>::kEnum, 4, p->x, dims, strides, box, 128);
+        int rc = encode_tmap(&tx, DT<T>::kEnum, 4, p->x, dims, strides, box, sizeof(T) == 4 ? 12832 : 128);
         if (rc != PG_OK) return rc;
     }
     auto kern = wgrad_gemm_kernel<T, BLOCK_C>;
@@ -310,12 +312,26 @@ static int launch_wg(const pg_wgrad_params* p, cudaStream_t stream) {
 }
 
 template <typename T>
-static int wgrad_dispatch(const pg_wgrad_params* p, cudaStream_t stream) {
+static int wgrad_dispatch(const pg_wgrad_params* p_in, cudaStream_t stream) {
     constexpr int CPS = 128 / sizeof(T);
+    constexpr bool kF32 = sizeof(T) == 4;
+    pg_wgrad_params local = *p_in;
+    const pg_wgrad_params* p = &local;
     const bool tc_ok = g_conv_backend == PG_BACKEND_AUTO && is_pow2(p->H) && is_pow2(p->W) && (p->C % CPS == 0) &&
-                       (p->N % 8 == 0) && (reinterpret_cast<uintptr_t>(p->g) % 16 == 0) &&
+                       (p->N % 8 == 0) && (!kF32 || (p->ws_g && p->ws_x)) && (reinterpret_cast<uintptr_t>(p->g) % 16 == 0) &&
                        (reinterpret_cast<uintptr_t>(p->x) % 16 == 0) && (reinterpret_cast<uintptr_t>(p->acc) % 16 == 0);
     if (tc_ok) {
+        if (kF32) {
+            // 3xTF32 along the pixel reduction: (g, g_lo, g) and (x, x, x_lo) stacked along the batch
+            const long long M = (long long)p->B * p->H * p->W;
+            int rc = split3_launch(reinterpret_cast<const float*>(p->g), reinterpret_cast<float*>(p->ws_g), M, p->N, 0, 1, stream);
+            if (rc != PG_OK) return rc;
+            rc = split3_launch(reinterpret_cast<const float*>(p->x), reinterpret_cast<float*>(p->ws_x), M, p->C, 0, 2, stream);
+            if (rc != PG_OK) return rc;
+            local.g = p->ws_g;
+            local.x = p->ws_x;
+            local.B = 3 * p->B;
+        }
         if (p->C % 256 == 0) return launch_wg<T, 256>(p, stream);
         if (p->C % 128 == 0) return launch_wg<T, 128>(p, stream);
         if (p->C % 64 == 0) return launch_wg<T, 64>(p, stream);

@@ -21,6 +21,26 @@ from . import _lib as L
 
 _COMPUTE_DTYPE = torch.bfloat16
 _SKIP_PARAM_GRADS = False      # see input_grad_only()
+PROFILE = None                 # bench.py sets a dict: (kind, shape) -> [(start_event, end_event), ...]
+
+
+class _Timed:
+    """CUDA-event bracket on the launch stream around one GEMM-class launch (only when PROFILE is set)"""
+
+    def __init__(self, kind, shape):
+        self.key = (kind, shape) if PROFILE is not None else None
+
+    def __enter__(self):
+        if self.key is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *a):
+        if self.key is not None:
+            self.e1.record()
+            PROFILE.setdefault(self.key, []).append((self.e0, self.e1))
 
 
 def set_compute_dtype(dtype: torch.dtype) -> None:
@@ -155,7 +175,13 @@ def k_conv(x, wp, bias, N, taps, scale, slope=1.0, mask_src=None, mask_slope=1.0
     p.dtype = _enum(x.dtype)
     p.out_dtype = L.PG_F32_RAW if raw_out else _enum(x.dtype)
     p.scale, p.slope, p.mask_slope = float(scale), float(slope), float(mask_slope)
-    L.check(L.load().pggan_conv_fprop(ctypes.byref(p), _s()), "pggan_conv_fprop")
+    ws = None
+    if x.dtype == torch.float32:          # fp32 mode = 3xTF32: the library splits operands into these
+        ws = (torch.empty(3 * x.numel(), dtype=torch.float32, device=x.device),
+              torch.empty(3 * wp.numel(), dtype=torch.float32, device=x.device))
+        p.ws_x, p.ws_w = ws[0].data_ptr(), ws[1].data_ptr()
+    with _Timed("conv_gemm", (b, h, w, c, N, taps)):
+        L.check(L.load().pggan_conv_fprop(ctypes.byref(p), _s()), "pggan_conv_fprop")
     return y
 
 
@@ -169,7 +195,13 @@ def k_wgrad(g, x, taps, scale, wshape):
     p.g, p.x, p.acc = g.data_ptr(), x.data_ptr(), acc.data_ptr()
     p.B, p.H, p.W, p.C, p.N, p.taps = b, h, w, c, n, taps
     p.dtype = _enum(g.dtype)
-    L.check(L.load().pggan_conv_wgrad(ctypes.byref(p), _s()), "pggan_conv_wgrad")
+    ws = None
+    if g.dtype == torch.float32:
+        ws = (torch.empty(3 * g.numel(), dtype=torch.float32, device=g.device),
+              torch.empty(3 * x.numel(), dtype=torch.float32, device=g.device))
+        p.ws_g, p.ws_x = ws[0].data_ptr(), ws[1].data_ptr()
+    with _Timed("wgrad_gemm", (b, h, w, c, n, taps)):
+        L.check(L.load().pggan_conv_wgrad(ctypes.byref(p), _s()), "pggan_conv_wgrad")
     out = torch.empty(wshape, dtype=torch.float32, device=g.device)
     L.check(L.load().pggan_unpack_wgrad(_p(acc), _p(out), n, 1, taps, c, c, 0, c * taps, 0, 1, taps, float(scale), 0,
                                         _s()), "pggan_unpack_wgrad")
