@@ -137,14 +137,42 @@ def run_ours(args):
     }
     devb = {k: v.to(dev) for k, v in host.items()}
 
-    def step_resident():
+    def step_eager():
         tr.train_step(devb["img"], latent_D=devb["z_d"], latent_G=devb["z_g"], eps=devb["eps"])
+
+    # launches per step, counted on an eager step with the library's own counters
+    for _ in range(2):
+        step_eager()
+    torch.cuda.synchronize()
+    c0 = _lib.launch_counts()
+    step_eager()
+    torch.cuda.synchronize()
+    c1 = _lib.launch_counts()
+    launches_per_step = {k: c1[k] - c0[k] for k in c1}
+
+    replay, graph_err = None, None
+    if args.graph and world == 1:
+        try:
+            replay = tr.capture(batch)
+        except Exception as e:          # fall back to eager launches, and say so in the JSON line
+            graph_err = f"{type(e).__name__}: {e}"[:200]
+            replay = None
+            torch.cuda.synchronize()
+
+    def step_resident():
+        if replay is not None:
+            replay()                    # inputs already sit in the graph's static device buffers
+        else:
+            step_eager()
 
     loss_host = torch.empty(3, dtype=torch.float32).pin_memory()
 
     def step_e2e():
-        d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        tr.train_step(d["img"], latent_D=d["z_d"], latent_G=d["z_g"], eps=d["eps"])
+        if replay is not None:
+            replay(host["img"], host["z_d"], host["z_g"], host["eps"])     # pinned host -> static device buffers
+        else:
+            d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+            tr.train_step(d["img"], latent_D=d["z_d"], latent_G=d["z_g"], eps=d["eps"])
         ld = dict.items(tr.loss_collector.loss_dict)
         vals = {k: v for k, v in ld}
         t = torch.stack([vals["L_D"].float().reshape(()), vals["L_G"].float().reshape(()),
@@ -178,13 +206,6 @@ def run_ours(args):
         step_resident()
     torch.cuda.synchronize()
 
-    # launches per step (counted once, outside the timed region, with the library's own counters)
-    c0 = _lib.launch_counts()
-    step_resident()
-    torch.cuda.synchronize()
-    c1 = _lib.launch_counts()
-    launches_per_step = {k: c1[k] - c0[k] for k in c1}
-
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -203,7 +224,7 @@ def run_ours(args):
     if rank == 0:
         ops.PROFILE = {}
         for _ in range(max(1, min(3, args.steps))):
-            step_resident()
+            step_eager()
         torch.cuda.synchronize()
         prof, ops.PROFILE = ops.PROFILE, None
         agg = {}
@@ -239,7 +260,8 @@ def run_ours(args):
             "dtype": "bf16" if dtype == torch.bfloat16 else "fp32(3xTF32)", "data": "synthetic",
             "config": {"workload": args.workload, "resolution": res, "batch_per_gpu": batch, "alpha": alpha,
                        "step_variant": args.variant, "latent_dim": 512, "depths": depths,
-                       "parallelism": f"dp{world}", "cuda_graph": False,
+                       "parallelism": f"dp{world}", "cuda_graph": replay is not None,
+                       **({"cuda_graph_error": graph_err} if graph_err else {}),
                        "l2_note": "per-step working set (activations of 3 D + 2 G passes and their gradients) is "
                                   "several GB, far above the 126 MB L2; no explicit flush",
                        "flop_count": f"{gflop_img} GFLOP/img (BASELINE.md W-minimal: D wgrad skipped in the G step)"},
@@ -319,8 +341,9 @@ def main():
     ap.add_argument("--variant", default="W", choices=["W", "L"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=0)
-    ap.add_argument("--cpu-sample", type=int, default=4)
+    ap.add_argument("--cpu-sample", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch eagerly instead of a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

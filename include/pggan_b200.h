@@ -45,20 +45,25 @@ int pggan_set_conv_backend(int backend);
 int pggan_launch_counts(int64_t* tcgen05_launches, int64_t* simt_launches, int64_t* other_launches);
 
 /* ------------------------------------------------------------------------------------------
- * Weight packing.  out[n][t][c] (dtype, c padded with zeros to c_pad) = in[off], fp32 source,
- *   n = n1*N2 + n2,  off = base + n1*s_n1 + n2*s_n2 + t*s_t + c*s_c   (strides in elements,
- *   s_t may be negative for the 180-degree flip used by dgrad).
- * Replaces: the implicit OIHW weight use of nn.Conv2d / nn.Linear in ConstrainedLayer.forward
- * (lib/layers.py:58-63); exists because the tensor-core kernels want K-major [N][taps*C].
+ * Weight packing.  The tensor-core kernels want K-major operands [n][t][c]; parameters stay in the
+ * reference's layouts (OIHW conv, [out,in] linear).  A pg_pack_map describes where logical element
+ * (n,t,c) lives in the fp32 parameter:
+ *     off = base + n1*s_n1 + n2*s_n2 + t*s_t + c1*s_c1 + c2*s_c2,   n = n1*n2_len + n2,  c = c1*c2_len + c2
+ * (strides in elements; s_t < 0 gives the 180-degree tap flip of dgrad; the two-level n / c indices
+ * express the NCHW<->NHWC flatten permutations of the two big linear layers; rows >= n_valid and
+ * columns >= c_valid are zero padding, e.g. the 513 -> 576 channel pad of the minibatch-stddev conv).
+ * Replaces: the implicit weight use of nn.Conv2d / nn.Linear in ConstrainedLayer.forward
+ * (lib/layers.py:58-63).
  */
-int pggan_pack_weight(const float* in, void* out, int dtype, int n1, int n2, int taps, int c, int c_pad,
-                      int64_t base, int64_t s_n1, int64_t s_n2, int64_t s_t, int64_t s_c, void* stream);
-
-/* Inverse for gradients: out_fp32[off] (+)= scale * in_fp32[n][t][c]  (same index map, in is the
- * dense [N][taps][c_pad] fp32 accumulator written by pggan_conv_wgrad). accumulate: 0 = overwrite. */
-int pggan_unpack_wgrad(const float* in, float* out, int n1, int n2, int taps, int c, int c_pad, int64_t base,
-                       int64_t s_n1, int64_t s_n2, int64_t s_t, int64_t s_c, float scale, int accumulate,
-                       void* stream);
+typedef struct {
+    int32_t n_total, n_valid, n2, taps, c_total, c_valid, c2;
+    int64_t base, s_n1, s_n2, s_t, s_c1, s_c2;
+} pg_pack_map;
+/* out[n][t][c] (dtype) = in[off(n,t,c)] or 0 in the padding */
+int pggan_pack_weight(const float* in, void* out, int dtype, const pg_pack_map* map, void* stream);
+/* gradients back: out_fp32[off(n,t,c)] (+)= scale * in_fp32[n][t][c] for the valid (n,c); `in` is the dense
+ * [n_total][taps][c_total] fp32 accumulator written by pggan_conv_wgrad. accumulate: 0 = overwrite. */
+int pggan_unpack_wgrad(const float* in, float* out, const pg_pack_map* map, float scale, int accumulate, void* stream);
 
 /* fp32 mode = 3xTF32.  The tensor core truncates fp32 operands to tf32 (hi); this writes three copies
  * of in [m][c], one of them (slot lo_slot) holding lo = x - trunc_tf32(x), concatenated along channels
@@ -126,9 +131,14 @@ int pggan_pool2x2(const void* x, const void* blend_with, void* out, int B, int H
 int pggan_axpby(const void* a, const void* b, void* out, int64_t n, float sa, float sb, int dtype, void* stream);
 /* y = x * rsqrt(mean_c(x^2) + eps), rnorm[m] saved   — PixelwiseVectorNorm, lib/layers.py:13-14 */
 int pggan_pixelnorm_fwd(const void* x, void* y, float* rnorm, int64_t m, int C, float eps, int dtype, void* stream);
-/* gx = rnorm * (gy - y * mean_c(gy*y)); if act_slope != 1 the LeakyReLU mask (sign of y) is applied too */
+/* gx = rnorm * (gy - y * mean_c(gy*y)); if act_slope != 1 the LeakyReLU mask (sign of y) is applied too;
+ * if colsum != NULL also colsum[c] += cs_scale * sum_m gx[m,c] (the bias gradient, same pass) */
 int pggan_pixelnorm_bwd(const void* gy, const void* y, const float* rnorm, void* gx, int64_t m, int C,
-                        float act_slope, int dtype, void* stream);
+                        float act_slope, float* colsum, float cs_scale, int dtype, void* stream);
+/* fused LeakyReLU backward + bias gradient: out = g * (y > 0 ? 1 : slope) (y NULL: out = g; out NULL: no
+ * store) and colsum[c] += scale * sum_m out[m,c] (colsum NULL: none).  C/vec must divide 256. */
+int pggan_mask_colsum(const void* g, const void* y, void* out, float* colsum, int64_t m, int C, float slope,
+                      float scale, int dtype, void* stream);
 /* out[c] (+)= scale * sum_m g[m,c]   — bias gradient of lib/layers.py:60 (bias is He-scaled too) */
 int pggan_colsum(const void* g, float* out, int64_t m, int C, float scale, int dtype, void* stream);
 
@@ -146,9 +156,10 @@ int pggan_rgb_expand(const float* img, const float* w, const float* bias, void* 
  * — toRGBBlock lib/blocks.py:164-170; also fromRGB dgrad (+ avg-pool backward). */
 int pggan_rgb_reduce(const void* x, const float* w, const float* bias, float* out, int B, int H, int W, int C,
                      int cimg, int up, float scale, float up_scale, int dtype, void* stream);
-/* acc[c][j] += scale * sum_{b,h,w} f[b,h,w,c] * p_j(b,h,w)   (p as in rgb_expand) — 1x1 weight grads */
-int pggan_rgb_wgrad(const void* f, const float* img, float* acc, int B, int H, int W, int C, int cimg, int pool,
-                    float scale, int dtype, void* stream);
+/* acc[c][j] += scale * sum_{b,h,w} f[b,h,w,c] * p_j(b,h,w)   (p as in rgb_expand) — 1x1 weight grads;
+ * if bsum != NULL also bsum[c] += scale * sum f[b,h,w,c] (the bias gradient, same pass). */
+int pggan_rgb_wgrad(const void* f, const float* img, float* acc, float* bsum, int B, int H, int W, int C, int cimg,
+                    int pool, float scale, int dtype, void* stream);
 /* fp32 NCHW image fade.  low == NULL: out = (1-a)*up2(avgpool2(x)) + a*x  (pggan/model.py:217-221)
  *                        low != NULL: out = (1-a)*up2(low) + a*x          (pggan/nets.py:155-156)   */
 int pggan_image_fade(const float* x, const float* low, float* out, int B, int Cimg, int H, int W, float alpha,

@@ -34,6 +34,13 @@ class WgradParams(Structure):
     ]
 
 
+class PackMap(Structure):
+    _fields_ = [("n_total", c_int32), ("n_valid", c_int32), ("n2", c_int32), ("taps", c_int32),
+                ("c_total", c_int32), ("c_valid", c_int32), ("c2", c_int32),
+                ("base", c_int64), ("s_n1", c_int64), ("s_n2", c_int64), ("s_t", c_int64), ("s_c1", c_int64),
+                ("s_c2", c_int64)]
+
+
 class AdamEntry(Structure):
     _fields_ = [("param", c_void_p), ("grad", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p),
                 ("numel", c_int64)]
@@ -45,10 +52,8 @@ SIGNATURES = {
     "pggan_last_error": (c_char_p, []),
     "pggan_set_conv_backend": (c_int, [c_int]),
     "pggan_launch_counts": (c_int, [POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]),
-    "pggan_pack_weight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int64, c_int64,
-                                  c_int64, c_int64, c_int64, c_void_p]),
-    "pggan_unpack_wgrad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int64, c_int64, c_int64,
-                                   c_int64, c_int64, c_float, c_int, c_void_p]),
+    "pggan_pack_weight": (c_int, [c_void_p, c_void_p, c_int, POINTER(PackMap), c_void_p]),
+    "pggan_unpack_wgrad": (c_int, [c_void_p, c_void_p, POINTER(PackMap), c_float, c_int, c_void_p]),
     "pggan_split3": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
     "pggan_conv_fprop": (c_int, [POINTER(ConvParams), c_void_p]),
     "pggan_conv_wgrad": (c_int, [POINTER(WgradParams), c_void_p]),
@@ -58,14 +63,17 @@ SIGNATURES = {
                               c_void_p]),
     "pggan_axpby": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_int, c_void_p]),
     "pggan_pixelnorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_int, c_void_p]),
-    "pggan_pixelnorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_int, c_void_p]),
+    "pggan_pixelnorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p, c_float,
+                                    c_int, c_void_p]),
+    "pggan_mask_colsum": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_float, c_int,
+                                  c_void_p]),
     "pggan_colsum": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_float, c_int, c_void_p]),
     "pggan_rgb_expand": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_float, c_float, c_int, c_void_p]),
     "pggan_rgb_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_float, c_float, c_int, c_void_p]),
-    "pggan_rgb_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
-                                c_int, c_void_p]),
+    "pggan_rgb_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                c_float, c_int, c_void_p]),
     "pggan_image_fade": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "pggan_image_pool_sum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "pggan_mbstd_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p]),

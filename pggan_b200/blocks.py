@@ -15,6 +15,8 @@ from .utils import downscale2d, upscale2d, num_flat_features  # noqa: F401
 
 def _conv_act_norm(layer, x, norm):
     """conv3x3 -> c*(.+b) -> LeakyReLU(0.2) [-> pixel norm]   (reference lib/blocks.py:119-139)"""
+    if isinstance(norm, PixelwiseVectorNorm):
+        return layer.fused(x, 0.2, pixel_norm_eps=1e-8)
     x = layer.fused(x, 0.2)
     if norm is not None:
         x = norm(x)
@@ -132,9 +134,10 @@ class LastProgressiveDiscriminatorBlock(nn.Module):
     def forward(self, x, subgroup_size=4):
         x = ops.feat(x)
         W, b = self.conv.module.weight, self.conv.module.bias
+        layout = None
         if self.apply_minibatch_norm:
-            # the 513-channel input is padded with zero channels up to the MMA K granule; the weight is
-            # zero-padded to match (torch pads/slices, so the gradient of W keeps its [C, C+1, 3, 3] shape)
+            # the (C+1)-channel input is padded with zero channels up to the MMA K granule; the weight
+            # packing pads to match (layout "pad_c"), so W and its gradient keep their [C, C+1, 3, 3] shape
             cin = x.shape[1] + 1
             gran = 64 if x.dtype == torch.bfloat16 else 32
             cpad = (cin + gran - 1) // gran * gran
@@ -142,15 +145,15 @@ class LastProgressiveDiscriminatorBlock(nn.Module):
             if cpad > cin:
                 parts.append(torch.zeros(x.shape[0], cpad - cin, x.shape[2], x.shape[3], device=x.device,
                                          dtype=x.dtype))
-                W = torch.nn.functional.pad(W, (0, 0, 0, 0, 0, cpad - cin))
+                layout = ("pad_c", cpad)
             x = torch.cat(parts, dim=1).contiguous(memory_format=torch.channels_last)
-        x = ops.ConvF.apply(x, W, b, self.conv.scale(), 0.2, False)
+        x = ops.ConvF.apply(x, W, b, self.conv.scale(), 0.2, False, layout)
         n, c, h, w = x.shape
-        # flatten in the reference's (C,H,W) order == permuting the linear's K axis to our (H,W,C) order
+        # flatten: the reference flattens NCHW (c,h,w); our activations are NHWC, so the linear's K axis is
+        # read in (h,w,c) order through the packing map ("lin_in_perm") instead of permuting the tensor
         x = x.permute(0, 2, 3, 1).reshape(n, h * w * c)
-        Wl = self.linear.module.weight
-        Wl = Wl.view(Wl.shape[0], c, h * w).transpose(1, 2).reshape(Wl.shape[0], h * w * c)
-        x = ops.ConvF.apply(x, Wl, self.linear.module.bias, self.linear.scale(), 0.2, False)
+        lin = self.linear.module
+        x = ops.ConvF.apply(x, lin.weight, lin.bias, self.linear.scale(), 0.2, False, ("lin_in_perm", c))
         return x
 
 

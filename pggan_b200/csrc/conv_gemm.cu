@@ -368,12 +368,20 @@ static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream) {
         const int bb = 128 / (bw * bh);
         const long long m_tiles = (long long)(p->W / bw) * (p->H / bh) * ((p->B + bb - 1) / bb);
         const int sms = num_sms();
+        // N tile: minimise (waves over the SMs) x (per-tile cost).  Per-tile cost is the MMA time (~N) until the
+        // fixed 16 KB A-tile shared-memory read per k-step dominates (N <= 64).
         int bn = 32;
+        double best = 1e30;
         const int cands[4] = {256, 128, 64, 32};
+        const double cost[4] = {1.0, 0.56, 0.36, 0.30};
         for (int i = 0; i < 4; ++i) {
             if (p->N % cands[i] != 0) continue;
-            bn = cands[i];
-            if (m_tiles * (p->N / cands[i]) >= sms) break;
+            const long long tiles = m_tiles * (p->N / cands[i]);
+            const double t = (double)((tiles + sms - 1) / sms) * cost[i];
+            if (t < best - 1e-9) {
+                best = t;
+                bn = cands[i];
+            }
         }
         switch (bn) {
             case 256: return launch_tc<T, 256>(p, stream);

@@ -180,15 +180,24 @@ __global__ void pixelnorm_fwd_kernel(const T* __restrict__ x, T* __restrict__ y,
     }
 }
 
-// gx = r * (gy - y * mean_c(gy*y)), then optional LeakyReLU mask by the sign of y
+// gx = r * (gy - y * mean_c(gy*y)), then optional LeakyReLU mask by the sign of y; optionally the
+// bias gradient colsum[c] += cs_scale * sum_m gx[m,c] in the same pass (lanes own fixed channel vectors)
 template <typename T, int MAXV>
-__global__ void pixelnorm_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ y, const float* __restrict__ rnorm,
-                                     T* __restrict__ gx, long long M, int C, float act_slope) {
+__global__ void __launch_bounds__(256)
+pixelnorm_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ y, const float* __restrict__ rnorm,
+                     T* __restrict__ gx, long long M, int C, float act_slope, float* __restrict__ colsum,
+                     float cs_scale) {
     constexpr int VN = V16<T>::N;
-    const int lane = threadIdx.x & 31;
+    __shared__ float red[8][32 * VN + 1];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
     const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
     const int nvec = C / VN;
+    float cs[MAXV][VN];
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k)
+#pragma unroll
+        for (int e = 0; e < VN; ++e) cs[k][e] = 0.f;
     for (long long m = warp0; m < M; m += nwarps) {
         V16<T> g[MAXV], yv[MAXV];
         float dot = 0.f;
@@ -215,9 +224,82 @@ __global__ void pixelnorm_bwd_kernel(const T* __restrict__ gy, const T* __restri
                     float t = r * (g[k].get(e) - yy * dot);
                     if (!(yy > 0.f)) t *= act_slope;
                     o.set(e, t);
+                    cs[k][e] += o.get(e);        // sum what is stored (rounded), as a separate pass would
                 }
                 st16(gx + m * C + vi * VN, o);
             }
+        }
+    }
+    if (colsum != nullptr) {
+#pragma unroll
+        for (int k = 0; k < MAXV; ++k) {
+            __syncthreads();
+#pragma unroll
+            for (int e = 0; e < VN; ++e) red[wid][lane * VN + e] = cs[k][e];
+            __syncthreads();
+            const int nw = blockDim.x >> 5;
+            for (int o = threadIdx.x; o < 32 * VN; o += blockDim.x) {
+                const int vi = o / VN + 32 * k;
+                if (vi < nvec) {
+                    float t = 0.f;
+                    for (int w2 = 0; w2 < nw; ++w2) t += red[w2][o];
+                    atomicAdd(colsum + vi * VN + (o % VN), t * cs_scale);
+                }
+            }
+        }
+    }
+}
+
+// out = g * mask(y) (y may be NULL: plain copy-free column sum) and colsum[c] += scale * sum_m out[m,c].
+// Thread (ty row lane, tx channel-vector lane, fixed per thread); 4 rows in flight per thread.
+template <typename T>
+__global__ void __launch_bounds__(256)
+mask_colsum_kernel(const T* __restrict__ g, const T* __restrict__ y, T* __restrict__ out, float* __restrict__ colsum,
+                   long long M, int C, float slope, float scale, int TX, long long rows_per_block) {
+    constexpr int VN = V16<T>::N;
+    __shared__ float red[256 * VN];
+    const int TY = blockDim.x / TX;
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    const long long r0 = blockIdx.x * rows_per_block;
+    long long r1 = r0 + rows_per_block;
+    if (r1 > M) r1 = M;
+    float acc[VN];
+#pragma unroll
+    for (int e = 0; e < VN; ++e) acc[e] = 0.f;
+    for (long long m = r0 + ty; m < r1; m += 4LL * TY) {
+        V16<T> gv[4], yv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long mm = m + static_cast<long long>(u) * TY;
+            if (mm < r1) {
+                gv[u] = ld16(g + mm * C + tx * VN);
+                if (y != nullptr) yv[u] = ld16(y + mm * C + tx * VN);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long mm = m + static_cast<long long>(u) * TY;
+            if (mm < r1) {
+                V16<T> o;
+#pragma unroll
+                for (int e = 0; e < VN; ++e) {
+                    float t = gv[u].get(e);
+                    if (y != nullptr && !(yv[u].get(e) > 0.f)) t *= slope;
+                    o.set(e, t);
+                    acc[e] += o.get(e);
+                }
+                if (out != nullptr) st16(out + mm * C + tx * VN, o);
+            }
+        }
+    }
+    if (colsum != nullptr) {
+#pragma unroll
+        for (int e = 0; e < VN; ++e) red[threadIdx.x * VN + e] = acc[e];
+        __syncthreads();
+        for (int o = threadIdx.x; o < TX * VN; o += blockDim.x) {
+            float t = 0.f;
+            for (int yy = 0; yy < TY; ++yy) t += red[yy * TX * VN + o];
+            atomicAdd(colsum + o, t * scale);
         }
     }
 }
@@ -265,32 +347,38 @@ __global__ void colsum_kernel(const T* __restrict__ g, float* __restrict__ out, 
 }
 
 // ---------------------------------------------------------------------------- weight packing
+// logical operand [n][t][c]  <->  parameter memory: off = base + n1*s_n1 + n2*s_n2 + t*s_t + c1*s_c1 + c2*s_c2
+// with n = n1*N2 + n2, c = c1*C2 + c2; rows n >= n_valid and columns c >= c_valid are zero padding.
+struct PackMap {
+    int n_total, n_valid, n2, taps, c_total, c_valid, c2;
+    long long base, s_n1, s_n2, s_t, s_c1, s_c2;
+};
+__device__ __forceinline__ long long pack_off(const PackMap& m, int n, int t, int c) {
+    return m.base + (n / m.n2) * m.s_n1 + (n % m.n2) * m.s_n2 + t * m.s_t + (c / m.c2) * m.s_c1 + (c % m.c2) * m.s_c2;
+}
+
 template <typename T>
-__global__ void pack_weight_kernel(const float* __restrict__ in, T* __restrict__ out, int n2, int taps, int c, int c_pad,
-                                   long long total, long long base, long long s_n1, long long s_n2, long long s_t,
-                                   long long s_c) {
+__global__ void pack_weight_kernel(const float* __restrict__ in, T* __restrict__ out, PackMap m, long long total) {
     GRID_STRIDE(i, total) {
-        const int cc = static_cast<int>(i % c_pad);
-        const long long r = i / c_pad;
-        const int t = static_cast<int>(r % taps);
-        const long long n = r / taps;
+        const int c = static_cast<int>(i % m.c_total);
+        const long long r = i / m.c_total;
+        const int t = static_cast<int>(r % m.taps);
+        const int n = static_cast<int>(r / m.taps);
         float v = 0.f;
-        if (cc < c) v = in[base + (n / n2) * s_n1 + (n % n2) * s_n2 + t * s_t + cc * s_c];
+        if (n < m.n_valid && c < m.c_valid) v = in[pack_off(m, n, t, c)];
         out[i] = DT<T>::from_f(v);
     }
 }
 
-__global__ void unpack_wgrad_kernel(const float* __restrict__ in, float* __restrict__ out, int n2, int taps, int c,
-                                    int c_pad, long long total, long long base, long long s_n1, long long s_n2,
-                                    long long s_t, long long s_c, float scale, int accumulate) {
-    // iterate in OUTPUT-friendly order is impossible in general (arbitrary strides); param-sized, L2-resident
+__global__ void unpack_wgrad_kernel(const float* __restrict__ in, float* __restrict__ out, PackMap m, long long total,
+                                    float scale, int accumulate) {
     GRID_STRIDE(i, total) {
-        const int cc = static_cast<int>(i % c);
-        const long long r = i / c;
-        const int t = static_cast<int>(r % taps);
-        const long long n = r / taps;
-        const float v = in[(n * taps + t) * c_pad + cc] * scale;
-        float* o = out + base + (n / n2) * s_n1 + (n % n2) * s_n2 + t * s_t + cc * s_c;
+        const int c = static_cast<int>(i % m.c_valid);
+        const long long r = i / m.c_valid;
+        const int t = static_cast<int>(r % m.taps);
+        const int n = static_cast<int>(r / m.taps);
+        const float v = in[(static_cast<long long>(n) * m.taps + t) * m.c_total + c] * scale;
+        float* o = out + pack_off(m, n, t, c);
         *o = accumulate ? (*o + v) : v;
     }
 }
@@ -427,7 +515,7 @@ extern "C" int pggan_pixelnorm_fwd(const void* x, void* y, float* rnorm, int64_t
 }
 
 extern "C" int pggan_pixelnorm_bwd(const void* gy, const void* y, const float* rnorm, void* gx, int64_t m, int C,
-                                   float act_slope, int dtype, void* stream) {
+                                   float act_slope, float* colsum, float cs_scale, int dtype, void* stream) {
     PG_CHECK(gy && y && rnorm && gx && m >= 0 && C > 0, PG_ERR_ARG, "pggan_pixelnorm_bwd: bad args");
     PG_CHECK(al16(gy) && al16(y) && al16(gx), PG_ERR_ARG, "pggan_pixelnorm_bwd: pointers must be 16-byte aligned");
     if (m == 0) return PG_OK;
@@ -436,13 +524,39 @@ extern "C" int pggan_pixelnorm_bwd(const void* gy, const void* y, const float* r
         constexpr int VN = V16<T>::N;
         PG_CHECK(C % VN == 0 && C <= 32 * VN * 4, PG_ERR_UNSUPPORTED,
                  "pggan_pixelnorm_bwd: C=%d must be a multiple of %d and <= %d", C, VN, 32 * VN * 4);
-        const int grid = ew_grid(m * 32, 256);
+        const int grid = ew_grid(m * 32 / 4 + 1, 256);      // ~4 rows per warp
         if (C <= 32 * VN)
-            pixelnorm_bwd_kernel<T, 1><<<grid, 256, 0, s>>>((const T*)gy, (const T*)y, rnorm, (T*)gx, m, C, act_slope);
+            pixelnorm_bwd_kernel<T, 1><<<grid, 256, 0, s>>>((const T*)gy, (const T*)y, rnorm, (T*)gx, m, C, act_slope, colsum, cs_scale);
         else if (C <= 64 * VN)
-            pixelnorm_bwd_kernel<T, 2><<<grid, 256, 0, s>>>((const T*)gy, (const T*)y, rnorm, (T*)gx, m, C, act_slope);
+            pixelnorm_bwd_kernel<T, 2><<<grid, 256, 0, s>>>((const T*)gy, (const T*)y, rnorm, (T*)gx, m, C, act_slope, colsum, cs_scale);
         else
-            pixelnorm_bwd_kernel<T, 4><<<grid, 256, 0, s>>>((const T*)gy, (const T*)y, rnorm, (T*)gx, m, C, act_slope);
+            pixelnorm_bwd_kernel<T, 4><<<grid, 256, 0, s>>>((const T*)gy, (const T*)y, rnorm, (T*)gx, m, C, act_slope, colsum, cs_scale);
+    });
+    PG_LAUNCH_CHECK();
+    g_other_launches++;
+    return PG_OK;
+}
+
+extern "C" int pggan_mask_colsum(const void* g, const void* y, void* out, float* colsum, int64_t m, int C, float slope,
+                                 float scale, int dtype, void* stream) {
+    PG_CHECK(g && m >= 0 && C > 0 && (out || colsum), PG_ERR_ARG, "pggan_mask_colsum: bad args");
+    PG_CHECK(al16(g) && (!y || al16(y)) && (!out || al16(out)), PG_ERR_ARG, "pggan_mask_colsum: pointers must be 16-byte aligned");
+    if (m == 0) return PG_OK;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    DISPATCH_T(dtype, {
+        constexpr int VN = V16<T>::N;
+        PG_CHECK(C % VN == 0 && (C / VN) <= 256 && 256 % (C / VN) == 0, PG_ERR_UNSUPPORTED,
+                 "pggan_mask_colsum: C/%d = %d must divide 256", VN, C / VN);
+        const int TX = C / VN, TY = 256 / TX;
+        long long rpb = (long long)TY * 16;
+        long long blocks = (m + rpb - 1) / rpb;
+        const long long cap = (long long)num_sms() * 16;
+        if (blocks > cap) {
+            blocks = cap;
+            rpb = (m + blocks - 1) / blocks;
+        }
+        const int grid = (int)((m + rpb - 1) / rpb);
+        mask_colsum_kernel<T><<<grid, 256, 0, s>>>((const T*)g, (const T*)y, (T*)out, colsum, m, C, slope, scale, TX, rpb);
     });
     PG_LAUNCH_CHECK();
     g_other_launches++;
@@ -472,28 +586,39 @@ extern "C" int pggan_colsum(const void* g, float* out, int64_t m, int C, float s
     return PG_OK;
 }
 
-extern "C" int pggan_pack_weight(const float* in, void* out, int dtype, int n1, int n2, int taps, int c, int c_pad,
-                                 int64_t base, int64_t s_n1, int64_t s_n2, int64_t s_t, int64_t s_c, void* stream) {
-    PG_CHECK(in && out && n1 > 0 && n2 > 0 && taps > 0 && c > 0 && c_pad >= c, PG_ERR_ARG, "pggan_pack_weight: bad args");
+static int make_map(PackMap& m, const pg_pack_map* p, const char* who) {
+    PG_CHECK(p != nullptr, PG_ERR_ARG, "%s: null map", who);
+    PG_CHECK(p->n_total > 0 && p->n_valid > 0 && p->n_valid <= p->n_total && p->n2 > 0 && p->taps > 0 && p->c_total > 0 &&
+                 p->c_valid > 0 && p->c_valid <= p->c_total && p->c2 > 0,
+             PG_ERR_ARG, "%s: bad map", who);
+    m.n_total = p->n_total; m.n_valid = p->n_valid; m.n2 = p->n2; m.taps = p->taps;
+    m.c_total = p->c_total; m.c_valid = p->c_valid; m.c2 = p->c2;
+    m.base = p->base; m.s_n1 = p->s_n1; m.s_n2 = p->s_n2; m.s_t = p->s_t; m.s_c1 = p->s_c1; m.s_c2 = p->s_c2;
+    return PG_OK;
+}
+
+extern "C" int pggan_pack_weight(const float* in, void* out, int dtype, const pg_pack_map* map, void* stream) {
+    PG_CHECK(in && out, PG_ERR_ARG, "pggan_pack_weight: null pointer");
+    PackMap m;
+    int rc = make_map(m, map, "pggan_pack_weight");
+    if (rc != PG_OK) return rc;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    const long long total = (long long)n1 * n2 * taps * c_pad;
-    DISPATCH_T(dtype, {
-        pack_weight_kernel<T><<<ew_grid(total, 256), 256, 0, s>>>(in, (T*)out, n2, taps, c, c_pad, total, base, s_n1, s_n2,
-                                                                 s_t, s_c);
-    });
+    const long long total = (long long)m.n_total * m.taps * m.c_total;
+    DISPATCH_T(dtype, { pack_weight_kernel<T><<<ew_grid(total, 256), 256, 0, s>>>(in, (T*)out, m, total); });
     PG_LAUNCH_CHECK();
     g_other_launches++;
     return PG_OK;
 }
 
-extern "C" int pggan_unpack_wgrad(const float* in, float* out, int n1, int n2, int taps, int c, int c_pad, int64_t base,
-                                  int64_t s_n1, int64_t s_n2, int64_t s_t, int64_t s_c, float scale, int accumulate,
+extern "C" int pggan_unpack_wgrad(const float* in, float* out, const pg_pack_map* map, float scale, int accumulate,
                                   void* stream) {
-    PG_CHECK(in && out && n1 > 0 && n2 > 0 && taps > 0 && c > 0 && c_pad >= c, PG_ERR_ARG, "pggan_unpack_wgrad: bad args");
+    PG_CHECK(in && out, PG_ERR_ARG, "pggan_unpack_wgrad: null pointer");
+    PackMap m;
+    int rc = make_map(m, map, "pggan_unpack_wgrad");
+    if (rc != PG_OK) return rc;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    const long long total = (long long)n1 * n2 * taps * c;
-    unpack_wgrad_kernel<<<ew_grid(total, 256), 256, 0, s>>>(in, out, n2, taps, c, c_pad, total, base, s_n1, s_n2, s_t, s_c,
-                                                            scale, accumulate);
+    const long long total = (long long)m.n_valid * m.taps * m.c_valid;
+    unpack_wgrad_kernel<<<ew_grid(total, 256), 256, 0, s>>>(in, out, m, total, scale, accumulate);
     PG_LAUNCH_CHECK();
     g_other_launches++;
     return PG_OK;

@@ -44,22 +44,27 @@ __device__ __forceinline__ void load_pixel(const float* __restrict__ img, int ci
 }
 
 // ------------------------------------------------------------------------------ expand (cimg -> C)
+// Thread = one 16-byte channel vector (fixed for the whole kernel: its weights/bias live in registers)
+// x a strided set of pixels; a block covers 256/TX consecutive pixels per iteration, so a warp writes
+// 512 contiguous bytes.  TX = C/VN must divide 256.
 template <typename T>
-__global__ void rgb_expand_kernel(const float* __restrict__ img, const float* __restrict__ w,
-                                  const float* __restrict__ bias, T* __restrict__ out, int B, int H, int W, int C,
-                                  int cimg, int pool, float scale, float slope) {
+__global__ void __launch_bounds__(256)
+rgb_expand_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias,
+                  T* __restrict__ out, int B, int H, int W, int C, int cimg, int pool, float scale, float slope,
+                  int TX) {
     constexpr int VN = RV<T>::N;
-    extern __shared__ float sw[];          // [C][cimg] weights then [C] bias
-    float* sb = sw + C * cimg;
-    for (int i = threadIdx.x; i < C * cimg; i += blockDim.x) sw[i] = w[i];
-    for (int i = threadIdx.x; i < C; i += blockDim.x) sb[i] = bias ? bias[i] : 0.f;
-    __syncthreads();
-    const int CV = C / VN;
-    const long long total = static_cast<long long>(B) * H * W * CV;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int cv = static_cast<int>(i % CV);
-        const long long pix = i / CV;
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX, TY = blockDim.x / TX;
+    float wr[VN][kMaxImgC], br[VN];
+#pragma unroll
+    for (int e = 0; e < VN; ++e) {
+        const int c = tx * VN + e;
+#pragma unroll
+        for (int j = 0; j < kMaxImgC; ++j) wr[e][j] = j < cimg ? __ldg(w + c * cimg + j) * scale : 0.f;
+        br[e] = bias ? __ldg(bias + c) * scale : 0.f;
+    }
+    const long long P = static_cast<long long>(B) * H * W;
+    for (long long pix = static_cast<long long>(blockIdx.x) * TY + ty; pix < P;
+         pix += static_cast<long long>(gridDim.x) * TY) {
         const int ww = static_cast<int>(pix % W);
         const int hh = static_cast<int>((pix / W) % H);
         const long long b = pix / (static_cast<long long>(W) * H);
@@ -68,127 +73,146 @@ __global__ void rgb_expand_kernel(const float* __restrict__ img, const float* __
         RV<T> o;
 #pragma unroll
         for (int e = 0; e < VN; ++e) {
-            const int c = cv * VN + e;
-            float acc = 0.f;
-            for (int j = 0; j < cimg; ++j) acc += sw[c * cimg + j] * p[j];
-            o.set(e, lrelu_f((acc + sb[c]) * scale, slope));
+            float acc = br[e];
+#pragma unroll
+            for (int j = 0; j < kMaxImgC; ++j) acc += wr[e][j] * p[j];
+            o.set(e, lrelu_f(acc, slope));
         }
-        *reinterpret_cast<uint4*>(out + pix * C + cv * VN) = o.raw;
+        *reinterpret_cast<uint4*>(out + pix * C + tx * VN) = o.raw;
     }
 }
 
 // ------------------------------------------------------------------------------ reduce (C -> cimg)
-// LP lanes cooperate on one pixel (LP = power of two <= 32); a warp covers 32/LP pixels per step.
-template <typename T>
-__global__ void rgb_reduce_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                                  float* __restrict__ out, int B, int H, int W, int C, int cimg, int up, float scale,
-                                  float up_scale, int LP) {
+// LP lanes (power of two <= 32) cooperate on one pixel; each lane keeps the weights of its channel
+// vectors in registers (NV = C/(VN*LP) vectors, <= 2 for C <= 512) and a warp handles 32/LP pixels x
+// UNR pixels per iteration so several 16-byte loads are in flight per lane.
+template <typename T, int NV>
+__global__ void __launch_bounds__(256)
+rgb_reduce_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                  float* __restrict__ out, int B, int H, int W, int C, int cimg, int up, float scale, float up_scale,
+                  int LP) {
     constexpr int VN = RV<T>::N;
-    extern __shared__ float sw[];          // [cimg][C]
-    for (int i = threadIdx.x; i < C * cimg; i += blockDim.x) sw[i] = w[i];
-    __syncthreads();
-    const int CV = C / VN;
+    constexpr int UNR = 4;
     const int lane = threadIdx.x & 31;
-    const int sub = lane % LP;             // lane within the pixel group
-    const int grp = lane / LP;             // which pixel of this warp's batch
-    const int ppw = 32 / LP;               // pixels per warp step
+    const int sub = lane % LP, grp = lane / LP, ppw = 32 / LP;
+    float wr[NV][VN][kMaxImgC];
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int e = 0; e < VN; ++e)
+#pragma unroll
+            for (int j = 0; j < kMaxImgC; ++j) {
+                const int c = (sub + v * LP) * VN + e;
+                wr[v][e][j] = (j < cimg && c < C) ? __ldg(w + j * C + c) : 0.f;
+            }
     const long long P = static_cast<long long>(B) * H * W;
     const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
     const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-    for (long long base = warp0 * ppw; base < P; base += nwarps * ppw) {
-        const long long pix = base + grp;
-        float acc[kMaxImgC] = {0.f, 0.f, 0.f, 0.f};
-        if (pix < P) {
-            for (int cv = sub; cv < CV; cv += LP) {
-                RV<T> v;
-                v.raw = __ldg(reinterpret_cast<const uint4*>(x + pix * C + cv * VN));
+    for (long long base = warp0 * ppw * UNR; base < P; base += nwarps * ppw * UNR) {
+        RV<T> v[UNR][NV];
 #pragma unroll
-                for (int e = 0; e < VN; ++e) {
-                    const float xv = v.get(e);
+        for (int u = 0; u < UNR; ++u) {
+            const long long pix = base + u * ppw + grp;
 #pragma unroll
-                    for (int j = 0; j < kMaxImgC; ++j)
-                        if (j < cimg) acc[j] += xv * sw[j * C + cv * VN + e];
-                }
+            for (int k = 0; k < NV; ++k) {
+                const int cv = sub + k * LP;
+                if (pix < P && cv * VN < C)
+                    v[u][k].raw = __ldg(reinterpret_cast<const uint4*>(x + pix * C + cv * VN));
+                else
+                    v[u][k].raw = make_uint4(0, 0, 0, 0);
             }
         }
 #pragma unroll
-        for (int j = 0; j < kMaxImgC; ++j)
-            for (int o = LP >> 1; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
-        if (pix < P && sub < cimg) {
-            float v = 0.f;
+        for (int u = 0; u < UNR; ++u) {
+            const long long pix = base + u * ppw + grp;
+            float acc[kMaxImgC] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k < NV; ++k)
+#pragma unroll
+                for (int e = 0; e < VN; ++e) {
+                    const float xv = v[u][k].get(e);
+#pragma unroll
+                    for (int j = 0; j < kMaxImgC; ++j) acc[j] += xv * wr[k][e][j];
+                }
 #pragma unroll
             for (int j = 0; j < kMaxImgC; ++j)
-                if (j == sub) v = acc[j];
-            v = (v + (bias ? __ldg(bias + sub) : 0.f)) * scale;
-            const int ww = static_cast<int>(pix % W);
-            const int hh = static_cast<int>((pix / W) % H);
-            const long long b = pix / (static_cast<long long>(W) * H);
-            if (!up) {
-                out[((b * cimg + sub) * H + hh) * W + ww] = v;
-            } else {
-                v *= up_scale;
-                float* o = out + ((b * cimg + sub) * 2 * H + 2 * hh) * 2 * W + 2 * ww;
-                *reinterpret_cast<float2*>(o) = make_float2(v, v);
-                *reinterpret_cast<float2*>(o + 2 * W) = make_float2(v, v);
+                for (int o = LP >> 1; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+            if (pix < P && sub < cimg) {
+                float r = 0.f;
+#pragma unroll
+                for (int j = 0; j < kMaxImgC; ++j)
+                    if (j == sub) r = acc[j];
+                r = (r + (bias ? __ldg(bias + sub) : 0.f)) * scale;
+                const int ww = static_cast<int>(pix % W);
+                const int hh = static_cast<int>((pix / W) % H);
+                const long long b = pix / (static_cast<long long>(W) * H);
+                if (!up) {
+                    out[((b * cimg + sub) * H + hh) * W + ww] = r;
+                } else {
+                    r *= up_scale;
+                    float* o = out + ((b * cimg + sub) * 2 * H + 2 * hh) * 2 * W + 2 * ww;
+                    *reinterpret_cast<float2*>(o) = make_float2(r, r);
+                    *reinterpret_cast<float2*>(o + 2 * W) = make_float2(r, r);
+                }
             }
         }
     }
 }
 
 // ------------------------------------------------------------------------------ 1x1 weight gradient
-// acc[c][j] += scale * sum_p f[p,c] * img_j(p).  Threads (ty pixel-lane, tx channel-vector lane).
+// acc[c][j] += scale * sum_p f[p,c] * img_j(p), and (optionally) bsum[c] += scale * sum_p f[p,c].
+// Threads (ty pixel lane, tx channel-vector lane, fixed per thread); each block owns a slab of pixels,
+// 4 pixels per thread in flight; partials are combined in shared memory, one atomicAdd per (block, c, j).
 template <typename T>
-__global__ void rgb_wgrad_kernel(const T* __restrict__ f, const float* __restrict__ img, float* __restrict__ acc, int B,
-                                 int H, int W, int C, int cimg, int pool, float scale, int TX,
-                                 long long pix_per_block) {
+__global__ void __launch_bounds__(256)
+rgb_wgrad_kernel(const T* __restrict__ f, const float* __restrict__ img, float* __restrict__ acc,
+                 float* __restrict__ bsum, int B, int H, int W, int C, int cimg, int pool, float scale, int TX,
+                 long long pix_per_block) {
     constexpr int VN = RV<T>::N;
-    extern __shared__ float red[];         // [blockDim][VN*kMaxImgC]
-    const int CV = C / VN;
+    constexpr int NA = kMaxImgC + 1;
+    extern __shared__ float red[];         // [blockDim][VN*NA]
     const int TY = blockDim.x / TX;
     const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
     const long long P = static_cast<long long>(B) * H * W;
     const long long p0 = blockIdx.x * pix_per_block;
     long long p1 = p0 + pix_per_block;
     if (p1 > P) p1 = P;
-    for (int cv0 = 0; cv0 < CV; cv0 += TX) {
-        const int cv = cv0 + tx;
-        float a[VN][kMaxImgC];
+    float a[VN][NA];
 #pragma unroll
-        for (int e = 0; e < VN; ++e)
+    for (int e = 0; e < VN; ++e)
 #pragma unroll
-            for (int j = 0; j < kMaxImgC; ++j) a[e][j] = 0.f;
-        if (cv < CV) {
-            for (long long pix = p0 + ty; pix < p1; pix += TY) {
-                const int ww = static_cast<int>(pix % W);
-                const int hh = static_cast<int>((pix / W) % H);
-                const long long b = pix / (static_cast<long long>(W) * H);
-                float p[kMaxImgC];
-                load_pixel(img, cimg, pool, b, hh, ww, H, W, p);
-                RV<T> v;
-                v.raw = __ldg(reinterpret_cast<const uint4*>(f + pix * C + cv * VN));
+        for (int j = 0; j < NA; ++j) a[e][j] = 0.f;
+    for (long long pix = p0 + ty; pix < p1; pix += TY) {
+        const int ww = static_cast<int>(pix % W);
+        const int hh = static_cast<int>((pix / W) % H);
+        const long long b = pix / (static_cast<long long>(W) * H);
+        float p[kMaxImgC];
+        load_pixel(img, cimg, pool, b, hh, ww, H, W, p);
+        RV<T> v;
+        v.raw = __ldg(reinterpret_cast<const uint4*>(f + pix * C + tx * VN));
 #pragma unroll
-                for (int e = 0; e < VN; ++e) {
-                    const float fv = v.get(e);
+        for (int e = 0; e < VN; ++e) {
+            const float fv = v.get(e);
 #pragma unroll
-                    for (int j = 0; j < kMaxImgC; ++j) a[e][j] += fv * p[j];
-                }
-            }
+            for (int j = 0; j < kMaxImgC; ++j) a[e][j] += fv * p[j];
+            a[e][kMaxImgC] += fv;
         }
-        __syncthreads();
+    }
 #pragma unroll
-        for (int e = 0; e < VN; ++e)
+    for (int e = 0; e < VN; ++e)
 #pragma unroll
-            for (int j = 0; j < kMaxImgC; ++j) red[(threadIdx.x * VN + e) * kMaxImgC + j] = a[e][j];
-        __syncthreads();
-        if (ty == 0 && cv < CV) {
-#pragma unroll
-            for (int e = 0; e < VN; ++e)
-                for (int j = 0; j < cimg; ++j) {
-                    float t = 0.f;
-                    for (int yy = 0; yy < TY; ++yy) t += red[((yy * TX + tx) * VN + e) * kMaxImgC + j];
-                    atomicAdd(acc + (cv * VN + e) * cimg + j, t * scale);
-                }
-        }
+        for (int j = 0; j < NA; ++j) red[(threadIdx.x * VN + e) * NA + j] = a[e][j];
+    __syncthreads();
+    // TX*VN*NA outputs per block, reduced over TY by the first threads
+    for (int o = threadIdx.x; o < TX * VN * NA; o += blockDim.x) {
+        const int j = o % NA;
+        const int ce = o / NA;            // tx*VN + e
+        float t = 0.f;
+        for (int yy = 0; yy < TY; ++yy) t += red[((yy * TX) * VN + ce) * NA + j];
+        if (j < cimg)
+            atomicAdd(acc + ce * cimg + j, t * scale);
+        else if (j == kMaxImgC && bsum != nullptr)
+            atomicAdd(bsum + ce, t * scale);
     }
 }
 
@@ -247,25 +271,54 @@ static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) 
 
 using namespace pg;
 
+static inline int pow2_le(int v, int cap) {
+    int r = 1;
+    while (r * 2 <= v && r * 2 <= cap) r *= 2;
+    return r;
+}
+
 extern "C" int pggan_rgb_expand(const float* img, const float* w, const float* bias, void* out, int B, int H, int W,
                                 int C, int cimg, int pool, float scale, float slope, int dtype, void* stream) {
     PG_CHECK(img && w && out && B > 0 && H > 0 && W > 0 && C > 0, PG_ERR_ARG, "pggan_rgb_expand: bad args");
     PG_CHECK(cimg >= 1 && cimg <= kMaxImgC, PG_ERR_UNSUPPORTED, "pggan_rgb_expand: cimg=%d must be 1..4", cimg);
     PG_CHECK(al16(out) && (!pool || (reinterpret_cast<uintptr_t>(img) & 7) == 0), PG_ERR_ARG,
              "pggan_rgb_expand: misaligned pointer");
+    PG_CHECK(dtype == PG_BF16 || dtype == PG_F32, PG_ERR_ARG, "pggan_rgb_expand: bad dtype %d", dtype);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    const size_t smem = (size_t)C * (cimg + 1) * sizeof(float);
-    PG_CHECK(smem <= 48 * 1024, PG_ERR_UNSUPPORTED, "pggan_rgb_expand: C=%d too large", C);
-    if (dtype == PG_BF16) {
-        PG_CHECK(C % 8 == 0, PG_ERR_UNSUPPORTED, "pggan_rgb_expand: C=%d must be a multiple of 8", C);
-        rgb_expand_kernel<__nv_bfloat16><<<grid_for((long long)B * H * W * (C / 8), 256, 8), 256, smem, s>>>(
-            img, w, bias, (__nv_bfloat16*)out, B, H, W, C, cimg, pool, scale, slope);
-    } else if (dtype == PG_F32) {
-        PG_CHECK(C % 4 == 0, PG_ERR_UNSUPPORTED, "pggan_rgb_expand: C=%d must be a multiple of 4", C);
-        rgb_expand_kernel<float><<<grid_for((long long)B * H * W * (C / 4), 256, 8), 256, smem, s>>>(
-            img, w, bias, (float*)out, B, H, W, C, cimg, pool, scale, slope);
-    } else {
-        PG_CHECK(false, PG_ERR_ARG, "pggan_rgb_expand: bad dtype %d", dtype);
+    const int vn = dtype == PG_BF16 ? 8 : 4;
+    PG_CHECK(C % vn == 0, PG_ERR_UNSUPPORTED, "pggan_rgb_expand: C=%d must be a multiple of %d", C, vn);
+    const int TX = C / vn;
+    PG_CHECK(TX <= 256 && 256 % TX == 0, PG_ERR_UNSUPPORTED,
+             "pggan_rgb_expand: C/%d = %d must divide 256 (power-of-two channel counts up to %d)", vn, TX, 256 * vn);
+    const long long P = (long long)B * H * W;
+    const int TY = 256 / TX;
+    const int grid = grid_for((P + TY - 1) / TY * 256 / 4 + 1, 256, 8);     // ~4 pixels per thread
+    if (dtype == PG_BF16)
+        rgb_expand_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(img, w, bias, (__nv_bfloat16*)out, B, H, W, C, cimg, pool,
+                                                            scale, slope, TX);
+    else
+        rgb_expand_kernel<float><<<grid, 256, 0, s>>>(img, w, bias, (float*)out, B, H, W, C, cimg, pool, scale, slope, TX);
+    PG_LAUNCH_CHECK();
+    g_other_launches++;
+    return PG_OK;
+}
+
+template <typename T>
+static int rgb_reduce_launch(const void* x, const float* w, const float* bias, float* out, int B, int H, int W, int C,
+                             int cimg, int up, float scale, float up_scale, cudaStream_t s) {
+    constexpr int VN = 16 / sizeof(T);
+    const int CV = C / VN;
+    int LP = pow2_le(CV < 4 ? 4 : CV, 32);      // >= cimg lanes are needed to write the outputs
+    const int nv = (CV + LP - 1) / LP;
+    PG_CHECK(nv <= 4, PG_ERR_UNSUPPORTED, "pggan_rgb_reduce: C=%d too large (max %d)", C, 4 * 32 * VN);
+    const long long P = (long long)B * H * W;
+    const long long warps = (P + (32 / LP) * 4 - 1) / ((32 / LP) * 4);
+    const int grid = grid_for(warps * 32, 256, 8);
+    const T* xp = reinterpret_cast<const T*>(x);
+    switch (nv) {
+        case 1: rgb_reduce_kernel<T, 1><<<grid, 256, 0, s>>>(xp, w, bias, out, B, H, W, C, cimg, up, scale, up_scale, LP); break;
+        case 2: rgb_reduce_kernel<T, 2><<<grid, 256, 0, s>>>(xp, w, bias, out, B, H, W, C, cimg, up, scale, up_scale, LP); break;
+        default: rgb_reduce_kernel<T, 4><<<grid, 256, 0, s>>>(xp, w, bias, out, B, H, W, C, cimg, up, scale, up_scale, LP); break;
     }
     PG_LAUNCH_CHECK();
     g_other_launches++;
@@ -278,31 +331,17 @@ extern "C" int pggan_rgb_reduce(const void* x, const float* w, const float* bias
     PG_CHECK(cimg >= 1 && cimg <= kMaxImgC, PG_ERR_UNSUPPORTED, "pggan_rgb_reduce: cimg=%d must be 1..4", cimg);
     PG_CHECK(al16(x) && (!up || (reinterpret_cast<uintptr_t>(out) & 7) == 0), PG_ERR_ARG,
              "pggan_rgb_reduce: misaligned pointer");
-    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    const size_t smem = (size_t)C * cimg * sizeof(float);
-    PG_CHECK(smem <= 48 * 1024, PG_ERR_UNSUPPORTED, "pggan_rgb_reduce: C=%d too large", C);
-    const int vn = dtype == PG_BF16 ? 8 : 4;
     PG_CHECK(dtype == PG_BF16 || dtype == PG_F32, PG_ERR_ARG, "pggan_rgb_reduce: bad dtype %d", dtype);
+    const int vn = dtype == PG_BF16 ? 8 : 4;
     PG_CHECK(C % vn == 0, PG_ERR_UNSUPPORTED, "pggan_rgb_reduce: C=%d must be a multiple of %d", C, vn);
-    const int CV = C / vn;
-    int LP = 4;                                   // >= cimg lanes are needed to write the outputs
-    while (LP * 2 <= CV && LP * 2 <= 32) LP *= 2;
-    const long long P = (long long)B * H * W;
-    const long long warps = (P + (32 / LP) - 1) / (32 / LP);
-    const int grid = grid_for(warps * 32, 256, 8);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (dtype == PG_BF16)
-        rgb_reduce_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>((const __nv_bfloat16*)x, w, bias, out, B, H, W, C, cimg, up,
-                                                               scale, up_scale, LP);
-    else
-        rgb_reduce_kernel<float><<<grid, 256, smem, s>>>((const float*)x, w, bias, out, B, H, W, C, cimg, up, scale,
-                                                       up_scale, LP);
-    PG_LAUNCH_CHECK();
-    g_other_launches++;
-    return PG_OK;
+        return rgb_reduce_launch<__nv_bfloat16>(x, w, bias, out, B, H, W, C, cimg, up, scale, up_scale, s);
+    return rgb_reduce_launch<float>(x, w, bias, out, B, H, W, C, cimg, up, scale, up_scale, s);
 }
 
-extern "C" int pggan_rgb_wgrad(const void* f, const float* img, float* acc, int B, int H, int W, int C, int cimg,
-                               int pool, float scale, int dtype, void* stream) {
+extern "C" int pggan_rgb_wgrad(const void* f, const float* img, float* acc, float* bsum, int B, int H, int W, int C,
+                               int cimg, int pool, float scale, int dtype, void* stream) {
     PG_CHECK(f && img && acc && B > 0 && H > 0 && W > 0 && C > 0, PG_ERR_ARG, "pggan_rgb_wgrad: bad args");
     PG_CHECK(cimg >= 1 && cimg <= kMaxImgC, PG_ERR_UNSUPPORTED, "pggan_rgb_wgrad: cimg=%d must be 1..4", cimg);
     PG_CHECK(al16(f) && (!pool || (reinterpret_cast<uintptr_t>(img) & 7) == 0), PG_ERR_ARG,
@@ -311,22 +350,30 @@ extern "C" int pggan_rgb_wgrad(const void* f, const float* img, float* acc, int 
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const int vn = dtype == PG_BF16 ? 8 : 4;
     PG_CHECK(C % vn == 0, PG_ERR_UNSUPPORTED, "pggan_rgb_wgrad: C=%d must be a multiple of %d", C, vn);
-    const int CV = C / vn;
-    const int threads = 128;
-    int TX = 1;
-    while (TX * 2 <= CV && TX * 2 <= threads) TX *= 2;
+    const int TX = C / vn;
+    PG_CHECK(TX <= 256 && 256 % TX == 0, PG_ERR_UNSUPPORTED, "pggan_rgb_wgrad: C/%d = %d must divide 256", vn, TX);
     const long long P = (long long)B * H * W;
-    long long blocks = (P + 255) / 256;
-    const long long cap = (long long)num_sms() * 4;
-    if (blocks > cap) blocks = cap;
-    const long long ppb = (P + blocks - 1) / blocks;
+    const int TY = 256 / TX;
+    long long ppb = (long long)TY * 16;                   // 16 pixels per thread
+    long long blocks = (P + ppb - 1) / ppb;
+    const long long cap = (long long)num_sms() * 16;
+    if (blocks > cap) {
+        blocks = cap;
+        ppb = (P + blocks - 1) / blocks;
+    }
     const int grid = (int)((P + ppb - 1) / ppb);
-    const size_t smem = (size_t)threads * vn * kMaxImgC * sizeof(float);
-    if (dtype == PG_BF16)
-        rgb_wgrad_kernel<__nv_bfloat16><<<grid, threads, smem, s>>>((const __nv_bfloat16*)f, img, acc, B, H, W, C, cimg, pool,
-                                                                 scale, TX, ppb);
-    else
-        rgb_wgrad_kernel<float><<<grid, threads, smem, s>>>((const float*)f, img, acc, B, H, W, C, cimg, pool, scale, TX, ppb);
+    const size_t smem = (size_t)256 * vn * (kMaxImgC + 1) * sizeof(float);
+    if (dtype == PG_BF16) {
+        static bool attr = false;
+        if (!attr) {
+            PG_CUDA(cudaFuncSetAttribute(rgb_wgrad_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+            attr = true;
+        }
+        rgb_wgrad_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>((const __nv_bfloat16*)f, img, acc, bsum, B, H, W, C, cimg,
+                                                              pool, scale, TX, ppb);
+    } else {
+        rgb_wgrad_kernel<float><<<grid, 256, smem, s>>>((const float*)f, img, acc, bsum, B, H, W, C, cimg, pool, scale, TX, ppb);
+    }
     PG_LAUNCH_CHECK();
     g_other_launches++;
     return PG_OK;

@@ -53,13 +53,14 @@ class ConstrainedLayer(nn.Module):
     def scale(self) -> float:
         return float(self.weight) if self.equalized else 1.0
 
-    def fused(self, x, slope=1.0, raw_out=False):
+    def fused(self, x, slope=1.0, raw_out=False, pixel_norm_eps=None, layout=None):
+        """lrelu(c*(W x + b), slope) [+ pixel norm if pixel_norm_eps is given] on the fused kernels"""
         m = self.module
         W, b = m.weight, m.bias
         c = self.scale()
         if isinstance(m, nn.Linear):
             x2 = x.reshape(x.shape[0], -1) if x.dim() != 2 else x
-            return ops.ConvF.apply(x2, W, b, c, float(slope), raw_out)
+            return ops.ConvF.apply(x2, W, b, c, float(slope), raw_out, layout)
         if not isinstance(m, nn.Conv2d):
             raise TypeError("ConstrainedLayer supports nn.Conv2d and nn.Linear modules")
         k = m.kernel_size[0]
@@ -72,7 +73,9 @@ class ConstrainedLayer(nn.Module):
             if slope != 1.0:
                 raise NotImplementedError("toRGB-shaped 1x1 convolutions have no fused activation")
             return ops.RgbReduce.apply(x, W.view(W.shape[0], W.shape[1]).t(), b, False, c, 1.0)
-        return ops.ConvF.apply(x, W, b, c, float(slope), raw_out)
+        if pixel_norm_eps is not None:
+            return ops.ConvActPN.apply(x, W, b, c, float(slope), float(pixel_norm_eps), layout)
+        return ops.ConvF.apply(x, W, b, c, float(slope), raw_out, layout)
 
     def forward(self, x):
         return self.fused(x, 1.0)

@@ -85,12 +85,17 @@ class Generator(nn.Module):
         # output rows of the weight ((c,h,w) -> (h,w,c)); views only, so gradients map back for free
         lin = self.latent_format_layer.module
         C0 = self.first_depth
-        Wp = lin.weight.view(C0, 16, lin.weight.shape[1]).transpose(0, 1).reshape(16 * C0, lin.weight.shape[1])
-        bp = lin.bias.view(C0, 16).t().reshape(16 * C0)
-        x = ops.ConvF.apply(x, Wp, bp, self.latent_format_layer.scale(), float(self.leakyRelu.negative_slope), False)
-        x = x.view(x.shape[0], 4, 4, C0).permute(0, 3, 1, 2)           # [B,C,4,4] logical, NHWC physical
+        slope = float(self.leakyRelu.negative_slope)
+        layout = ("lin_out_perm", C0)
         if pn is not None:
+            # pixel norm over the C0 channels of each of the 16 positions == over each contiguous C0 chunk
+            # of the (h,w,c)-ordered output: run the fused conv+act+PN on a [B*16, C0] view
+            x = ops.ConvF.apply(x, lin.weight, lin.bias, self.latent_format_layer.scale(), slope, False, layout)
+            x = x.view(x.shape[0], 4, 4, C0).permute(0, 3, 1, 2)       # [B,C,4,4] logical, NHWC physical
             x = pn(x)
+        else:
+            x = ops.ConvF.apply(x, lin.weight, lin.bias, self.latent_format_layer.scale(), slope, False, layout)
+            x = x.view(x.shape[0], 4, 4, C0).permute(0, 3, 1, 2)
         x = self.first_block(x)
         low = None
         nb = len(self.blocks)

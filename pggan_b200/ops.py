@@ -124,15 +124,52 @@ def _new_like_layout(x: torch.Tensor, channels: int, dtype: torch.dtype, h=None,
 
 
 # ------------------------------------------------------------------------------ weight packing
+# A "layout" says how the logical GEMM operand [N][taps][C] of a layer maps onto its fp32 parameter:
+#   None / ("oihw",)        OIHW conv weight or [O,I] linear weight as they are
+#   ("pad_c", Cp)           OIHW conv whose input has Cp >= I channels (zero padded: the 513->576 mbstd conv)
+#   ("lin_out_perm", C0)    [C0*16, K] linear whose OUTPUT rows are consumed in (h,w,c) order (G's format layer)
+#   ("lin_in_perm", C)      [O, C*16] linear whose INPUT columns arrive in (h,w,c) order (D's 8192->512 layer)
 _PACK_CACHE: dict = {}
 
 
-def _pack(W: torch.Tensor, kind: str, dtype: torch.dtype) -> torch.Tensor:
-    """fp32 parameter (OIHW 3x3 or [O,I]) -> K-major packed operand.
-    kind 'f': [O][taps][I] (fprop);  kind 't': [I][taps][O], taps reversed (dgrad = flipped conv)."""
+def _maps(wshape, layout):
+    """-> (N, C, taps, fmap, tmap): logical dims of the fprop GEMM and the pg_pack_map argument tuples
+    (n_total, n_valid, n2, taps, c_total, c_valid, c2, base, s_n1, s_n2, s_t, s_c1, s_c2) for the
+    fprop operand [N][taps][C] and the dgrad operand [C][taps][N] (taps reversed)."""
+    O, I = int(wshape[0]), int(wshape[1])
+    T = 1
+    for d in wshape[2:]:
+        T *= int(d)
+    kind = layout[0] if layout else "oihw"
+    if kind == "oihw":
+        return O, I, T, (O, O, 1, T, I, I, 1, 0, I * T, 0, 1, T, 0), (I, I, 1, T, O, O, 1, T - 1, T, 0, -1, I * T, 0)
+    if kind == "pad_c":
+        Cp = int(layout[1])
+        return O, Cp, T, (O, O, 1, T, Cp, I, 1, 0, I * T, 0, 1, T, 0), (Cp, I, 1, T, O, O, 1, T - 1, T, 0, -1, I * T, 0)
+    if kind == "lin_out_perm":
+        C0 = int(layout[1])
+        S = O // C0          # 16 spatial positions; parameter row r = c*S + hw, logical n = hw*C0 + c
+        return O, I, 1, (O, O, C0, 1, I, I, 1, 0, I, S * I, 0, 1, 0), (I, I, 1, 1, O, O, C0, 0, 1, 0, 0, I, S * I)
+    if kind == "lin_in_perm":
+        C = int(layout[1])
+        S = I // C           # parameter column j = c*S + hw, logical k = hw*C + c
+        return O, I, 1, (O, O, 1, 1, I, I, C, 0, I, 0, 0, 1, S), (I, I, C, 1, O, O, 1, 0, 1, S, 0, I, 0)
+    raise ValueError(f"unknown weight layout {layout}")
+
+
+def _packmap(args):
+    m = L.PackMap()
+    (m.n_total, m.n_valid, m.n2, m.taps, m.c_total, m.c_valid, m.c2, m.base, m.s_n1, m.s_n2, m.s_t, m.s_c1,
+     m.s_c2) = args
+    return m
+
+
+def _pack(W: torch.Tensor, kind: str, dtype: torch.dtype, layout=None) -> torch.Tensor:
+    """fp32 parameter -> K-major packed operand in `dtype`; kind 'f' = fprop [N][taps*C], 't' = dgrad
+    [C][taps*N] with the taps reversed.  Cached per (parameter, version) for nn.Parameters."""
     _need_cuda(W)
     cacheable = isinstance(W, torch.nn.Parameter)
-    key = (id(W), W._version, kind, dtype) if cacheable else None
+    key = (id(W), W._version, kind, dtype, layout) if cacheable else None
     if cacheable:
         hit = _PACK_CACHE.get(key)
         if hit is not None and hit[0] is W:
@@ -140,17 +177,11 @@ def _pack(W: torch.Tensor, kind: str, dtype: torch.dtype) -> torch.Tensor:
     Wc = W.detach()
     if Wc.dtype != torch.float32 or not Wc.is_contiguous():
         Wc = Wc.float().contiguous()
-    O, I = Wc.shape[0], Wc.shape[1]
-    taps = Wc.numel() // (O * I)
-    if kind == "f":
-        out = torch.empty((O, taps * I), dtype=dtype, device=W.device)
-        args = (O, 1, taps, I, I, 0, I * taps, 0, 1, taps)
-    else:
-        out = torch.empty((I, taps * O), dtype=dtype, device=W.device)
-        args = (I, 1, taps, O, O, taps - 1, taps, 0, -1, I * taps)
-    n1, n2, t, c, c_pad, base, s_n1, s_n2, s_t, s_c = args
-    L.check(L.load().pggan_pack_weight(_p(Wc), _p(out), _enum(dtype), n1, n2, t, c, c_pad, base, s_n1, s_n2, s_t,
-                                       s_c, _s()), "pggan_pack_weight")
+    N, C, T, fmap, tmap = _maps(Wc.shape, layout)
+    args = fmap if kind == "f" else tmap
+    out = torch.empty((args[0], args[3] * args[4]), dtype=dtype, device=W.device)
+    m = _packmap(args)
+    L.check(L.load().pggan_pack_weight(_p(Wc), _p(out), _enum(dtype), ctypes.byref(m), _s()), "pggan_pack_weight")
     if cacheable:
         if len(_PACK_CACHE) > 1024:
             _PACK_CACHE.clear()
@@ -158,8 +189,15 @@ def _pack(W: torch.Tensor, kind: str, dtype: torch.dtype) -> torch.Tensor:
     return out
 
 
-def clear_pack_cache():
-    _PACK_CACHE.clear()
+def clear_pack_cache(params=None):
+    """drop packed copies (all, or only those of `params`) — called by the optimizer after it has
+    updated the parameters in place through the Adam kernel"""
+    if params is None:
+        _PACK_CACHE.clear()
+        return
+    ids = {id(p) for p in params}
+    for k in [k for k in _PACK_CACHE if k[0] in ids]:
+        del _PACK_CACHE[k]
 
 
 # ------------------------------------------------------------------------------- raw kernels
@@ -185,11 +223,14 @@ def k_conv(x, wp, bias, N, taps, scale, slope=1.0, mask_src=None, mask_slope=1.0
     return y
 
 
-def k_wgrad(g, x, taps, scale, wshape):
-    """returns the weight gradient in the parameter's own fp32 layout (OIHW / [O,I])"""
+def k_wgrad(g, x, scale, wshape, layout=None):
+    """returns the weight gradient in the parameter's own fp32 layout"""
     _need_cuda(g)
     b, n, h, w = _dims(g)
     c = _dims(x)[1]
+    N, C, taps, fmap, _ = _maps(wshape, layout)
+    if (n, c) != (N, C):
+        raise ValueError(f"wgrad operand channels ({n},{c}) do not match the layer ({N},{C})")
     acc = torch.zeros((n, taps, c), dtype=torch.float32, device=g.device)
     p = L.WgradParams()
     p.g, p.x, p.acc = g.data_ptr(), x.data_ptr(), acc.data_ptr()
@@ -202,10 +243,30 @@ def k_wgrad(g, x, taps, scale, wshape):
         p.ws_g, p.ws_x = ws[0].data_ptr(), ws[1].data_ptr()
     with _Timed("wgrad_gemm", (b, h, w, c, n, taps)):
         L.check(L.load().pggan_conv_wgrad(ctypes.byref(p), _s()), "pggan_conv_wgrad")
-    out = torch.empty(wshape, dtype=torch.float32, device=g.device)
-    L.check(L.load().pggan_unpack_wgrad(_p(acc), _p(out), n, 1, taps, c, c, 0, c * taps, 0, 1, taps, float(scale), 0,
-                                        _s()), "pggan_unpack_wgrad")
+    pad = fmap[1] < fmap[0] or fmap[5] < fmap[4]
+    out = (torch.zeros if pad else torch.empty)(tuple(wshape), dtype=torch.float32, device=g.device)
+    m = _packmap(fmap)
+    L.check(L.load().pggan_unpack_wgrad(_p(acc), _p(out), ctypes.byref(m), float(scale), 0, _s()), "pggan_unpack_wgrad")
     return out
+
+
+def k_mask_colsum(g, y, slope, want_out, colsum_scale):
+    """fused LeakyReLU backward (+ bias gradient): returns (g*mask(y) or None, colsum or None)"""
+    b, c, h, w = _dims(g)
+    vn = 16 // g.element_size()
+    if c % vn != 0 or (c // vn) > 256 or 256 % (c // vn) != 0:          # odd widths: two plain passes
+        out = k_mask_mul(g, y, slope) if (want_out and y is not None) else (g if want_out else None)
+        src = out if out is not None else (k_mask_mul(g, y, slope) if y is not None else g)
+        return out, (k_colsum(src, colsum_scale) if colsum_scale is not None else None)
+    out = torch.empty_like(g) if (want_out and y is not None) else None
+    cs = torch.zeros((c,), dtype=torch.float32, device=g.device) if colsum_scale is not None else None
+    if out is None and cs is None:
+        return (g if want_out else None), None
+    L.check(L.load().pggan_mask_colsum(_p(g), _p(y), _p(out), _p(cs), b * h * w, c, float(slope),
+                                       float(colsum_scale or 0.0), _enum(g.dtype), _s()), "pggan_mask_colsum")
+    if want_out and out is None:
+        out = g
+    return out, cs
 
 
 def k_mask_mul(g, y, slope):
@@ -249,52 +310,107 @@ def k_axpby(a, b, sa, sb):
 
 
 # ----------------------------------------------------------------------- GEMM-class Functions
-def _wmeta(W):
-    O, I = W.shape[0], W.shape[1]
-    taps = W.numel() // (O * I)
-    return O, I, taps
+def _perm_bias(b, layout, inverse=False):
+    """bias of a ("lin_out_perm", C0) layer in logical (h,w,c) order, or a logical gradient back"""
+    if b is None or not layout or layout[0] != "lin_out_perm":
+        return b
+    C0 = int(layout[1])
+    S = b.numel() // C0
+    return b.view(S, C0).t().reshape(-1) if inverse else b.view(C0, S).t().reshape(-1)
 
 
 class ConvF(torch.autograd.Function):
     """y = lrelu(scale * (conv(x, W) + b), slope)   [fprop; slope = 1 -> linear]"""
 
     @staticmethod
-    def forward(ctx, x, W, b, scale, slope, raw_out):
+    def forward(ctx, x, W, b, scale, slope, raw_out, layout=None):
         x = feat(x)
-        O, I, taps = _wmeta(W)
-        bias = None if b is None else b.detach().float().contiguous()
-        y = k_conv(x, _pack(W, "f", x.dtype), bias, O, taps, scale, slope, raw_out=raw_out)
+        N, C, taps, _, _ = _maps(W.shape, layout)
+        bias = None if b is None else _perm_bias(b.detach().float(), layout).contiguous()
+        y = k_conv(x, _pack(W, "f", x.dtype, layout), bias, N, taps, scale, slope, raw_out=raw_out)
         ctx.save_for_backward(x, W, y if slope != 1.0 else None)
-        ctx.scale, ctx.slope, ctx.has_bias = scale, slope, b is not None
+        ctx.scale, ctx.slope, ctx.has_bias, ctx.layout = scale, slope, b is not None, layout
         return y
 
     @staticmethod
     def backward(ctx, gy):
         x, W, y = ctx.saved_tensors
         g = feat(gy)
-        if ctx.slope != 1.0:
-            g = MaskMul.apply(g, y, ctx.slope)
+        need_w = ctx.needs_input_grad[1] and not _SKIP_PARAM_GRADS
+        need_b = ctx.has_bias and ctx.needs_input_grad[2] and not _SKIP_PARAM_GRADS
         gx = gW = gb = None
-        if ctx.needs_input_grad[0]:
-            gx = ConvT.apply(g, W, ctx.scale)
-        if not _SKIP_PARAM_GRADS:
-            if ctx.needs_input_grad[1]:
-                gW = ConvW.apply(g, x, ctx.scale, tuple(W.shape))
-            if ctx.has_bias and ctx.needs_input_grad[2]:
+        if torch.is_grad_enabled():
+            # create_graph=True: stay composable (every piece is a differentiable Function)
+            if ctx.slope != 1.0:
+                g = MaskMul.apply(g, y, ctx.slope)
+            if need_b:
                 gb = ColSum.apply(g, ctx.scale)
-        return gx, gW, gb, None, None, None
+        else:
+            # plain backward: LeakyReLU mask and bias gradient in one pass over g
+            g, gb = k_mask_colsum(g, y if ctx.slope != 1.0 else None, ctx.slope, True,
+                                  ctx.scale if need_b else None)
+        if gb is not None:
+            gb = _perm_bias(gb, ctx.layout, inverse=True)
+        if ctx.needs_input_grad[0]:
+            gx = ConvT.apply(g, W, ctx.scale, ctx.layout)
+        if need_w:
+            gW = ConvW.apply(g, x, ctx.scale, tuple(W.shape), ctx.layout)
+        return gx, gW, gb, None, None, None, None
+
+
+class ConvActPN(torch.autograd.Function):
+    """G's  conv3x3 -> c*(.+b) -> LeakyReLU -> pixel norm  (reference lib/blocks.py:119-139 with
+    lib/layers.py:13-14): two kernels forward (GEMM with fused bias/He/LReLU epilogue, pixel norm) and a
+    backward whose first pass fuses pixel-norm backward, the LeakyReLU mask (sign(y_pn) == sign(pre))
+    and the bias gradient.  The generator is never differentiated twice."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, scale, slope, eps, layout=None):
+        x = feat(x)
+        N, C, taps, _, _ = _maps(W.shape, layout)
+        bias = None if b is None else _perm_bias(b.detach().float(), layout).contiguous()
+        a = k_conv(x, _pack(W, "f", x.dtype, layout), bias, N, taps, scale, slope)
+        bb, c, h, w = _dims(a)
+        y = torch.empty_like(a)
+        r = torch.empty((bb * h * w,), dtype=torch.float32, device=a.device)
+        L.check(L.load().pggan_pixelnorm_fwd(_p(a), _p(y), _p(r), bb * h * w, c, float(eps), _enum(a.dtype), _s()),
+                "pggan_pixelnorm_fwd")
+        ctx.save_for_backward(x, W, y, r)
+        ctx.scale, ctx.slope, ctx.has_bias, ctx.layout = scale, slope, b is not None, layout
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        x, W, y, r = ctx.saved_tensors
+        gy = feat(gy)
+        bb, c, h, w = _dims(y)
+        need_b = ctx.has_bias and ctx.needs_input_grad[2] and not _SKIP_PARAM_GRADS
+        g = torch.empty_like(y)
+        gb = torch.zeros((c,), dtype=torch.float32, device=y.device) if need_b else None
+        L.check(L.load().pggan_pixelnorm_bwd(_p(gy), _p(y), _p(r), _p(g), bb * h * w, c, float(ctx.slope), _p(gb),
+                                             float(ctx.scale), _enum(y.dtype), _s()), "pggan_pixelnorm_bwd")
+        gx = gW = None
+        if ctx.needs_input_grad[0]:
+            N, C, taps, _, _ = _maps(W.shape, ctx.layout)
+            gx = k_conv(g, _pack(W, "t", g.dtype, ctx.layout), None, C, taps, ctx.scale)
+        if ctx.needs_input_grad[1] and not _SKIP_PARAM_GRADS:
+            gW = k_wgrad(g, x, ctx.scale, tuple(W.shape), ctx.layout)
+        if gb is not None:
+            gb = _perm_bias(gb, ctx.layout, inverse=True)
+        return gx, gW, gb, None, None, None, None
 
 
 class ConvT(torch.autograd.Function):
     """gx = scale * conv_transpose(g, W)   [dgrad: the same kernel on flipped/transposed weights]"""
 
     @staticmethod
-    def forward(ctx, g, W, scale):
+    def forward(ctx, g, W, scale, layout=None):
         g = feat(g)
-        O, I, taps = _wmeta(W)
-        gx = k_conv(g, _pack(W, "t", g.dtype), None, I, taps, scale)
+        N, C, taps, _, _ = _maps(W.shape, layout)
+        gx = k_conv(g, _pack(W, "t", g.dtype, layout), None, C, taps, scale)
         ctx.save_for_backward(g, W)
-        ctx.scale = scale
+        ctx.scale, ctx.layout = scale, layout
         return gx
 
     @staticmethod
@@ -303,25 +419,21 @@ class ConvT(torch.autograd.Function):
         ggx = feat(ggx)
         dg = dW = None
         if ctx.needs_input_grad[0]:
-            dg = ConvF.apply(ggx, W, None, ctx.scale, 1.0, False)
+            dg = ConvF.apply(ggx, W, None, ctx.scale, 1.0, False, ctx.layout)
         if ctx.needs_input_grad[1] and not _SKIP_PARAM_GRADS:
-            dW = ConvW.apply(g, ggx, ctx.scale, tuple(W.shape))
-        return dg, dW, None
+            dW = ConvW.apply(g, ggx, ctx.scale, tuple(W.shape), ctx.layout)
+        return dg, dW, None, None
 
 
 class ConvW(torch.autograd.Function):
     """gW = scale * wgrad(g, x)   in the parameter's layout"""
 
     @staticmethod
-    def forward(ctx, g, x, scale, wshape):
+    def forward(ctx, g, x, scale, wshape, layout=None):
         g, x = feat(g), feat(x)
-        O, I = wshape[0], wshape[1]
-        taps = 1
-        for s in wshape[2:]:
-            taps *= s
         ctx.save_for_backward(g, x)
-        ctx.scale = scale
-        return k_wgrad(g, x, taps, scale, wshape)
+        ctx.scale, ctx.layout = scale, layout
+        return k_wgrad(g, x, scale, wshape, layout)
 
     @staticmethod
     def backward(ctx, ggW):
@@ -329,10 +441,10 @@ class ConvW(torch.autograd.Function):
         dg = dx = None
         ggW = ggW.contiguous()
         if ctx.needs_input_grad[0]:
-            dg = ConvF.apply(x, ggW, None, ctx.scale, 1.0, False)
+            dg = ConvF.apply(x, ggW, None, ctx.scale, 1.0, False, ctx.layout)
         if ctx.needs_input_grad[1]:
-            dx = ConvT.apply(g, ggW, ctx.scale)
-        return dg, dx, None, None
+            dx = ConvT.apply(g, ggW, ctx.scale, ctx.layout)
+        return dg, dx, None, None, None
 
 
 class ColSum(torch.autograd.Function):
@@ -462,8 +574,8 @@ class PixelNorm(torch.autograd.Function):
         gy = feat(gy)
         b, c, h, w = _dims(y)
         gx = torch.empty_like(y)
-        L.check(L.load().pggan_pixelnorm_bwd(_p(gy), _p(y), _p(r), _p(gx), b * h * w, c, 1.0, _enum(y.dtype), _s()),
-                "pggan_pixelnorm_bwd")
+        L.check(L.load().pggan_pixelnorm_bwd(_p(gy), _p(y), _p(r), _p(gx), b * h * w, c, 1.0, None, 0.0,
+                                             _enum(y.dtype), _s()), "pggan_pixelnorm_bwd")
         return gx, None
 
 
@@ -486,13 +598,14 @@ def _k_rgb_reduce(x, wr, bias, cimg, up, scale, up_scale):
     return out
 
 
-def _k_rgb_wgrad(f, img, pool, scale):
+def _k_rgb_wgrad(f, img, pool, scale, want_bias=False):
     b, c, h, w = _dims(f)
     cimg = img.shape[1]
     acc = torch.zeros((c, cimg), dtype=torch.float32, device=f.device)
-    L.check(L.load().pggan_rgb_wgrad(_p(f), _p(img), _p(acc), b, h, w, c, cimg, int(pool), float(scale),
+    bs = torch.zeros((c,), dtype=torch.float32, device=f.device) if want_bias else None
+    L.check(L.load().pggan_rgb_wgrad(_p(f), _p(img), _p(acc), _p(bs), b, h, w, c, cimg, int(pool), float(scale),
                                      _enum(f.dtype), _s()), "pggan_rgb_wgrad")
-    return acc
+    return (acc, bs) if want_bias else acc
 
 
 def _img(t):
@@ -518,16 +631,30 @@ class RgbExpand(torch.autograd.Function):
     def backward(ctx, gy):
         img, Wc, y = ctx.saved_tensors
         g = feat(gy)
-        if ctx.slope != 1.0:
-            g = MaskMul.apply(g, y, ctx.slope)
+        need_w = ctx.needs_input_grad[1] and not _SKIP_PARAM_GRADS
+        need_b = ctx.has_bias and ctx.needs_input_grad[2] and not _SKIP_PARAM_GRADS
         gimg = gW = gb = None
-        if ctx.needs_input_grad[0]:
-            gimg = RgbReduce.apply(g, Wc, None, ctx.pool, ctx.scale, 0.25)
-        if not _SKIP_PARAM_GRADS:
-            if ctx.needs_input_grad[1]:
+        if torch.is_grad_enabled():
+            if ctx.slope != 1.0:
+                g = MaskMul.apply(g, y, ctx.slope)
+            if ctx.needs_input_grad[0]:
+                gimg = RgbReduce.apply(g, Wc, None, ctx.pool, ctx.scale, 0.25)
+            if need_w:
                 gW = RgbWgrad.apply(g, img, ctx.pool, ctx.scale)
-            if ctx.has_bias and ctx.needs_input_grad[2]:
+            if need_b:
                 gb = ColSum.apply(g, ctx.scale)
+            return gimg, gW, gb, None, None, None
+        if ctx.slope != 1.0:
+            g = k_mask_mul(g, y, ctx.slope)
+        if ctx.needs_input_grad[0]:
+            wr = Wc.detach().float().t().contiguous()
+            gimg = _k_rgb_reduce(g, wr, None, wr.shape[0], ctx.pool, ctx.scale, 0.25)
+        if need_w or need_b:                   # weight and bias gradients share one pass over g
+            gW, gb = _k_rgb_wgrad(g, img, ctx.pool, ctx.scale, want_bias=True)
+            if not need_w:
+                gW = None
+            if not need_b:
+                gb = None
         return gimg, gW, gb, None, None, None
 
 

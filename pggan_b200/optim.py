@@ -106,7 +106,7 @@ class FusedAdam:
                                          ctypes.c_void_p(self._chunk_offset.data_ptr()),
                                          ctypes.c_void_p(self.step_count.data_ptr()), self.lr, b1, b2, self.eps,
                                          self.grad_scale, ops._s()), "pggan_adam_step")
-        ops.clear_pack_cache()          # packed bf16/tf32 weight copies are stale now
+        ops.clear_pack_cache(self.grads.params)     # packed bf16/tf32 copies of THESE weights are stale now
 
     def state_dict(self):
         return {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "step": self.step_count,

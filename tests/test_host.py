@@ -67,3 +67,52 @@ def test_schedule_matches_reference_bookkeeping():
     for step in range(2000, 2000 + 100 * 100 + 1):
         tr.check_jump(step)
     assert tr.alpha_index == 100 and abs(tr.G.alpha - 1.0) < 1e-9 and tr.next_alpha_jump_step == 0
+
+
+def _emulate_pack(W, args):
+    """numpy-free emulation of pack_weight_kernel's index map (pggan_b200/csrc/elementwise.cu)"""
+    n_total, n_valid, n2, taps, c_total, c_valid, c2, base, s_n1, s_n2, s_t, s_c1, s_c2 = args
+    flat = W.reshape(-1)
+    n = torch.arange(n_total).view(-1, 1, 1)
+    t = torch.arange(taps).view(1, -1, 1)
+    c = torch.arange(c_total).view(1, 1, -1)
+    off = base + (n // n2) * s_n1 + (n % n2) * s_n2 + t * s_t + (c // c2) * s_c1 + (c % c2) * s_c2
+    valid = (n < n_valid) & (c < c_valid) & (t >= 0)
+    out = torch.zeros(n_total, taps, c_total)
+    out[valid.expand_as(out)] = flat[off[valid.expand_as(off)]]
+    return out
+
+
+def test_weight_layout_maps():
+    """the pg_pack_map tuples of ops._maps against explicit torch permutations"""
+    from pggan_b200 import ops
+    torch.manual_seed(0)
+    # OIHW 3x3: fprop [O][kh*3+kw][I]; dgrad [I][flipped tap][O]
+    W = torch.randn(6, 5, 3, 3)
+    N, C, T, fm, tm = ops._maps(W.shape, None)
+    assert (N, C, T) == (6, 5, 9)
+    assert torch.equal(_emulate_pack(W, fm), W.permute(0, 2, 3, 1).reshape(6, 9, 5))
+    assert torch.equal(_emulate_pack(W, tm), W.flip(2, 3).permute(1, 2, 3, 0).reshape(5, 9, 6))
+    # padded input channels (the 513 -> 576 mbstd conv)
+    N, C, T, fm, tm = ops._maps(W.shape, ("pad_c", 8))
+    f = _emulate_pack(W, fm)
+    assert f.shape == (6, 9, 8) and torch.equal(f[:, :, :5], W.permute(0, 2, 3, 1).reshape(6, 9, 5)) and f[:, :, 5:].abs().sum() == 0
+    t = _emulate_pack(W, tm)
+    assert t.shape == (8, 9, 6) and torch.equal(t[:5], W.flip(2, 3).permute(1, 2, 3, 0).reshape(5, 9, 6)) and t[5:].abs().sum() == 0
+    # G's format layer: rows (c,hw) consumed as (hw,c)
+    C0, S, K = 4, 16, 7
+    W = torch.randn(C0 * S, K)
+    N, C, T, fm, tm = ops._maps(W.shape, ("lin_out_perm", C0))
+    Wp = W.view(C0, S, K).transpose(0, 1).reshape(S * C0, K)
+    assert torch.equal(_emulate_pack(W, fm)[:, 0, :], Wp)
+    assert torch.equal(_emulate_pack(W, tm)[:, 0, :], Wp.t())
+    b = torch.randn(C0 * S)
+    assert torch.equal(ops._perm_bias(b, ("lin_out_perm", C0)), b.view(C0, S).t().reshape(-1))
+    assert torch.equal(ops._perm_bias(ops._perm_bias(b, ("lin_out_perm", C0)), ("lin_out_perm", C0), inverse=True), b)
+    # D's linear: columns (c,hw) read as (hw,c)
+    O, Cc = 3, 5
+    W = torch.randn(O, Cc * S)
+    N, C, T, fm, tm = ops._maps(W.shape, ("lin_in_perm", Cc))
+    Wl = W.view(O, Cc, S).transpose(1, 2).reshape(O, S * Cc)
+    assert torch.equal(_emulate_pack(W, fm)[:, 0, :], Wl)
+    assert torch.equal(_emulate_pack(W, tm)[:, 0, :], Wl.t())
