@@ -235,15 +235,28 @@ def run_ours(args):
         top_key, (top_ms, top_n) = max(agg.items(), key=lambda kv: kv[1][0])
         kind, (b_, h_, w_, c_, n_, taps_) = top_key
         flops = 2.0 * b_ * h_ * w_ * c_ * n_ * taps_
+        nprof = max(1, min(3, args.steps))
+        breakdown = []
+        for (kd, shp), (t_ms, n_l) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:14]:
+            fl = 2.0 * shp[0] * shp[1] * shp[2] * shp[3] * shp[4] * shp[5]
+            breakdown.append({"kernel": kd, "B,H,W,C,N,taps": list(shp), "launches_per_step": n_l // nprof,
+                              "avg_ms": round(t_ms / n_l, 4), "ms_per_step": round(t_ms / nprof, 3),
+                              "tflops": round(fl / (t_ms / n_l * 1e-3) / 1e12, 1)})
         peak_burst, peak_sus, hbm, src = measured_peaks()
         achieved = flops / (top_ms / top_n * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": f"{kind} B{b_} {h_}x{w_} C{c_}->N{n_} taps{taps_}",
                 "achieved": round(achieved, 1), "peak": peak_sus, "unit": "TFLOP/s",
                 "frac": round(achieved / peak_sus, 4), "peak_source": f"bf16_tflops_sustained ({src})",
-                "traffic": None, "launches_per_step": top_n // max(1, min(3, args.steps)),
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel/shape from the committed
+                # `ncu --set full` capture profiles/r1_ncu_gemm_full.md (71.9 MB read + 22.3 MB written; the
+                # algorithmic bytes are 67.1 MB in + 4.7 MB weights + 67.1 MB out, most of the output is still
+                # in L2 when the kernel ends)
+                "traffic": 94.2e6 if (kind, b_, h_, w_, c_, n_, taps_) == ("conv_gemm", 64, 32, 32, 512, 512, 9) else None,
+                "launches_per_step": top_n // max(1, min(3, args.steps)),
                 "avg_launch_ms": round(top_ms / top_n, 4),
                 "share_of_gemm_time": round(top_ms / step_total, 3),
                 "gemm_ms_per_step": round(step_total / max(1, min(3, args.steps)), 3),
+                "gemm_breakdown": breakdown,
                 "whole_step_frac_of_peak": round(gflop_img * batch / (ms / args.steps * 1e-3) / 1e3 / peak_sus, 4)}
 
     # ---- CPU baseline: the oracle restatement of the reference step on the host cores (bounded sample)

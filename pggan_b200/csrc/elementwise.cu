@@ -383,6 +383,59 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ in, float* __restr
     }
 }
 
+// Fast paths for the common OIHW 3x3 maps: tile transposes through shared memory so that both the
+// fp32 parameter side and the packed side are accessed contiguously.
+// fprop: out[o][t][i] = W[o][i][t]   (i padded to Ip with zeros); grid (ceil(Ip/64), O)
+template <typename T>
+__global__ void __launch_bounds__(256) pack_oihw_f_kernel(const float* __restrict__ W, T* __restrict__ out, int I, int Ip) {
+    __shared__ float tile[64 * 9];
+    const int o = blockIdx.y, i0 = blockIdx.x * 64;
+    const int ni = min(64, I - i0);                       // valid input channels in this tile (may be <= 0)
+    for (int k = threadIdx.x; k < 64 * 9; k += blockDim.x)
+        tile[k] = (k < ni * 9) ? W[(static_cast<size_t>(o) * I + i0) * 9 + k] : 0.f;
+    __syncthreads();
+    for (int k = threadIdx.x; k < 64 * 9; k += blockDim.x) {
+        const int t = k / 64, ii = k % 64;
+        if (i0 + ii < Ip) out[(static_cast<size_t>(o) * 9 + t) * Ip + i0 + ii] = DT<T>::from_f(tile[ii * 9 + t]);
+    }
+}
+// gradients back: gW[o][i][t] = scale * acc[o][t][i]
+__global__ void __launch_bounds__(256) unpack_oihw_kernel(const float* __restrict__ acc, float* __restrict__ gW, int I,
+                                                          int Ip, float scale, int accumulate) {
+    __shared__ float tile[64 * 9];
+    const int o = blockIdx.y, i0 = blockIdx.x * 64;
+    const int ni = min(64, I - i0);
+    for (int k = threadIdx.x; k < 64 * 9; k += blockDim.x) {
+        const int t = k / 64, ii = k % 64;
+        tile[ii * 9 + t] = (ii < ni) ? acc[(static_cast<size_t>(o) * 9 + t) * Ip + i0 + ii] : 0.f;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < ni * 9; k += blockDim.x) {
+        float* dst = gW + (static_cast<size_t>(o) * I + i0) * 9 + k;
+        const float v = tile[k] * scale;
+        *dst = accumulate ? (*dst + v) : v;
+    }
+}
+// dgrad: out[i][8-t][o] = W[o][i][t]   (rows i >= I zero); grid (ceil(Np/8), O/32), O % 32 == 0
+template <typename T>
+__global__ void __launch_bounds__(256) pack_oihw_t_kernel(const float* __restrict__ W, T* __restrict__ out, int O, int I,
+                                                          int Np) {
+    __shared__ float tile[32][73];
+    const int i0 = blockIdx.x * 8, o0 = blockIdx.y * 32;
+    const int ni = min(8, I - i0);
+    for (int k = threadIdx.x; k < 32 * 72; k += blockDim.x) {
+        const int oo = k / 72, r = k % 72;
+        tile[oo][r] = (r < ni * 9) ? W[(static_cast<size_t>(o0 + oo) * I + i0) * 9 + r] : 0.f;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < 72 * 32; k += blockDim.x) {
+        const int oo = k % 32, r = k / 32;        // r = ii*9 + t'
+        const int ii = r / 9, tp = r % 9;
+        if (i0 + ii < Np)
+            out[(static_cast<size_t>(i0 + ii) * 9 + tp) * O + o0 + oo] = DT<T>::from_f(tile[oo][ii * 9 + (8 - tp)]);
+    }
+}
+
 // ------------------------------------------------------------------------------ 3xTF32 operand split
 // in [M][C] fp32 -> three copies, one of which holds lo = x - trunc_tf32(x) (the tensor core truncates
 // fp32 operands to tf32, so the plain copies act as hi).  Concatenated along channels ([M][3C]) for the
@@ -604,7 +657,22 @@ extern "C" int pggan_pack_weight(const float* in, void* out, int dtype, const pg
     if (rc != PG_OK) return rc;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const long long total = (long long)m.n_total * m.taps * m.c_total;
-    DISPATCH_T(dtype, { pack_weight_kernel<T><<<ew_grid(total, 256), 256, 0, s>>>(in, (T*)out, m, total); });
+    const bool oihw_f = m.taps == 9 && m.n2 == 1 && m.c2 == 1 && m.base == 0 && m.s_t == 1 && m.s_c1 == 9 &&
+                        m.s_n1 == 9LL * m.c_valid && m.n_valid == m.n_total;
+    const bool oihw_t = m.taps == 9 && m.n2 == 1 && m.c2 == 1 && m.base == 8 && m.s_t == -1 && m.s_n1 == 9 &&
+                        m.s_c1 == 9LL * m.n_valid && m.c_valid == m.c_total && m.c_total % 32 == 0;
+    if (oihw_f) {
+        DISPATCH_T(dtype, {
+            pack_oihw_f_kernel<T><<<dim3((m.c_total + 63) / 64, m.n_total), 256, 0, s>>>(in, (T*)out, m.c_valid, m.c_total);
+        });
+    } else if (oihw_t) {
+        DISPATCH_T(dtype, {
+            pack_oihw_t_kernel<T><<<dim3((m.n_total + 7) / 8, m.c_total / 32), 256, 0, s>>>(in, (T*)out, m.c_total, m.n_valid,
+                                                                                          m.n_total);
+        });
+    } else {
+        DISPATCH_T(dtype, { pack_weight_kernel<T><<<ew_grid(total, 256), 256, 0, s>>>(in, (T*)out, m, total); });
+    }
     PG_LAUNCH_CHECK();
     g_other_launches++;
     return PG_OK;
@@ -618,7 +686,12 @@ extern "C" int pggan_unpack_wgrad(const float* in, float* out, const pg_pack_map
     if (rc != PG_OK) return rc;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const long long total = (long long)m.n_valid * m.taps * m.c_valid;
-    unpack_wgrad_kernel<<<ew_grid(total, 256), 256, 0, s>>>(in, out, m, total, scale, accumulate);
+    const bool oihw_f = m.taps == 9 && m.n2 == 1 && m.c2 == 1 && m.base == 0 && m.s_t == 1 && m.s_c1 == 9 &&
+                        m.s_n1 == 9LL * m.c_valid && m.n_valid == m.n_total;
+    if (oihw_f)
+        unpack_oihw_kernel<<<dim3((m.c_valid + 63) / 64, m.n_total), 256, 0, s>>>(in, out, m.c_valid, m.c_total, scale, accumulate);
+    else
+        unpack_wgrad_kernel<<<ew_grid(total, 256), 256, 0, s>>>(in, out, m, total, scale, accumulate);
     PG_LAUNCH_CHECK();
     g_other_launches++;
     return PG_OK;

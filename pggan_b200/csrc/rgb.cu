@@ -18,21 +18,29 @@ template <typename T> struct RV {
     __device__ __forceinline__ void set(int i, float v) { reinterpret_cast<T*>(&raw)[i] = DT<T>::from_f(v); }
 };
 
-__device__ __forceinline__ void load_pixel(const float* __restrict__ img, int cimg, int pool, long long b, int h, int w,
+// pixel index -> (b, h, w) with 32-bit arithmetic (host code guarantees B*H*W < 2^31)
+__device__ __forceinline__ void pix_decomp(int pix, int H, int W, int& b, int& h, int& w) {
+    w = pix % W;
+    const int t = pix / W;
+    h = t % H;
+    b = t / H;
+}
+
+__device__ __forceinline__ void load_pixel(const float* __restrict__ img, int cimg, int pool, int b, int h, int w,
                                            int H, int W, float (&p)[kMaxImgC]) {
     // (H, W) are the FEATURE-map dims; the image is [B,cimg,H,W] or, if pool, [B,cimg,2H,2W]
     if (!pool) {
-        const long long plane = static_cast<long long>(H) * W;
+        const size_t plane = static_cast<size_t>(H) * W;
 #pragma unroll
         for (int j = 0; j < kMaxImgC; ++j)
-            p[j] = j < cimg ? __ldg(img + (b * cimg + j) * plane + static_cast<long long>(h) * W + w) : 0.f;
+            p[j] = j < cimg ? __ldg(img + (static_cast<size_t>(b) * cimg + j) * plane + h * W + w) : 0.f;
     } else {
         const int Wi = 2 * W;
-        const long long plane = 4LL * H * W;
+        const size_t plane = static_cast<size_t>(4) * H * W;
 #pragma unroll
         for (int j = 0; j < kMaxImgC; ++j) {
             if (j < cimg) {
-                const float* q = img + (b * cimg + j) * plane + (2LL * h) * Wi + 2 * w;
+                const float* q = img + (static_cast<size_t>(b) * cimg + j) * plane + static_cast<size_t>(2 * h) * Wi + 2 * w;
                 const float2 r0 = __ldg(reinterpret_cast<const float2*>(q));
                 const float2 r1 = __ldg(reinterpret_cast<const float2*>(q + Wi));
                 p[j] = (((r0.x + r0.y) + r1.x) + r1.y) * 0.25f;      // same order as avg_pool2d's window sum
@@ -62,12 +70,10 @@ rgb_expand_kernel(const float* __restrict__ img, const float* __restrict__ w, co
         for (int j = 0; j < kMaxImgC; ++j) wr[e][j] = j < cimg ? __ldg(w + c * cimg + j) * scale : 0.f;
         br[e] = bias ? __ldg(bias + c) * scale : 0.f;
     }
-    const long long P = static_cast<long long>(B) * H * W;
-    for (long long pix = static_cast<long long>(blockIdx.x) * TY + ty; pix < P;
-         pix += static_cast<long long>(gridDim.x) * TY) {
-        const int ww = static_cast<int>(pix % W);
-        const int hh = static_cast<int>((pix / W) % H);
-        const long long b = pix / (static_cast<long long>(W) * H);
+    const int P = B * H * W;
+    for (int pix = blockIdx.x * TY + ty; pix < P; pix += gridDim.x * TY) {
+        int b, hh, ww;
+        pix_decomp(pix, H, W, b, hh, ww);
         float p[kMaxImgC];
         load_pixel(img, cimg, pool, b, hh, ww, H, W, p);
         RV<T> o;
@@ -78,7 +84,7 @@ rgb_expand_kernel(const float* __restrict__ img, const float* __restrict__ w, co
             for (int j = 0; j < kMaxImgC; ++j) acc += wr[e][j] * p[j];
             o.set(e, lrelu_f(acc, slope));
         }
-        *reinterpret_cast<uint4*>(out + pix * C + tx * VN) = o.raw;
+        *reinterpret_cast<uint4*>(out + static_cast<size_t>(pix) * C + tx * VN) = o.raw;
     }
 }
 
@@ -99,32 +105,38 @@ rgb_reduce_kernel(const T* __restrict__ x, const float* __restrict__ w, const fl
 #pragma unroll
     for (int v = 0; v < NV; ++v)
 #pragma unroll
-        for (int e = 0; e < VN; ++e)
+        for (int j = 0; j < kMaxImgC; ++j) {
+            const int c0 = (sub + v * LP) * VN;
 #pragma unroll
-            for (int j = 0; j < kMaxImgC; ++j) {
-                const int c = (sub + v * LP) * VN + e;
-                wr[v][e][j] = (j < cimg && c < C) ? __ldg(w + j * C + c) : 0.f;
+            for (int e4 = 0; e4 < VN; e4 += 4) {
+                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (j < cimg && c0 < C) t = __ldg(reinterpret_cast<const float4*>(w + j * C + c0 + e4));
+                wr[v][e4 + 0][j] = t.x;
+                wr[v][e4 + 1][j] = t.y;
+                wr[v][e4 + 2][j] = t.z;
+                wr[v][e4 + 3][j] = t.w;
             }
-    const long long P = static_cast<long long>(B) * H * W;
-    const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
-    const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-    for (long long base = warp0 * ppw * UNR; base < P; base += nwarps * ppw * UNR) {
+        }
+    const int P = B * H * W;
+    const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int base = warp0 * ppw * UNR; base < P; base += nwarps * ppw * UNR) {
         RV<T> v[UNR][NV];
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
-            const long long pix = base + u * ppw + grp;
+            const int pix = base + u * ppw + grp;
 #pragma unroll
             for (int k = 0; k < NV; ++k) {
                 const int cv = sub + k * LP;
                 if (pix < P && cv * VN < C)
-                    v[u][k].raw = __ldg(reinterpret_cast<const uint4*>(x + pix * C + cv * VN));
+                    v[u][k].raw = __ldg(reinterpret_cast<const uint4*>(x + static_cast<size_t>(pix) * C + cv * VN));
                 else
                     v[u][k].raw = make_uint4(0, 0, 0, 0);
             }
         }
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
-            const long long pix = base + u * ppw + grp;
+            const int pix = base + u * ppw + grp;
             float acc[kMaxImgC] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int k = 0; k < NV; ++k)
@@ -143,14 +155,13 @@ rgb_reduce_kernel(const T* __restrict__ x, const float* __restrict__ w, const fl
                 for (int j = 0; j < kMaxImgC; ++j)
                     if (j == sub) r = acc[j];
                 r = (r + (bias ? __ldg(bias + sub) : 0.f)) * scale;
-                const int ww = static_cast<int>(pix % W);
-                const int hh = static_cast<int>((pix / W) % H);
-                const long long b = pix / (static_cast<long long>(W) * H);
+                int b, hh, ww;
+                pix_decomp(pix, H, W, b, hh, ww);
                 if (!up) {
-                    out[((b * cimg + sub) * H + hh) * W + ww] = r;
+                    out[(static_cast<size_t>(b * cimg + sub) * H + hh) * W + ww] = r;
                 } else {
                     r *= up_scale;
-                    float* o = out + ((b * cimg + sub) * 2 * H + 2 * hh) * 2 * W + 2 * ww;
+                    float* o = out + (static_cast<size_t>(b * cimg + sub) * 2 * H + 2 * hh) * 2 * W + 2 * ww;
                     *reinterpret_cast<float2*>(o) = make_float2(r, r);
                     *reinterpret_cast<float2*>(o + 2 * W) = make_float2(r, r);
                 }
@@ -173,23 +184,22 @@ rgb_wgrad_kernel(const T* __restrict__ f, const float* __restrict__ img, float* 
     extern __shared__ float red[];         // [blockDim][VN*NA]
     const int TY = blockDim.x / TX;
     const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
-    const long long P = static_cast<long long>(B) * H * W;
-    const long long p0 = blockIdx.x * pix_per_block;
-    long long p1 = p0 + pix_per_block;
+    const int P = B * H * W;
+    const int p0 = static_cast<int>(blockIdx.x * pix_per_block);
+    int p1 = p0 + static_cast<int>(pix_per_block);
     if (p1 > P) p1 = P;
     float a[VN][NA];
 #pragma unroll
     for (int e = 0; e < VN; ++e)
 #pragma unroll
         for (int j = 0; j < NA; ++j) a[e][j] = 0.f;
-    for (long long pix = p0 + ty; pix < p1; pix += TY) {
-        const int ww = static_cast<int>(pix % W);
-        const int hh = static_cast<int>((pix / W) % H);
-        const long long b = pix / (static_cast<long long>(W) * H);
+    for (int pix = p0 + ty; pix < p1; pix += TY) {
+        int b, hh, ww;
+        pix_decomp(pix, H, W, b, hh, ww);
         float p[kMaxImgC];
         load_pixel(img, cimg, pool, b, hh, ww, H, W, p);
         RV<T> v;
-        v.raw = __ldg(reinterpret_cast<const uint4*>(f + pix * C + tx * VN));
+        v.raw = __ldg(reinterpret_cast<const uint4*>(f + static_cast<size_t>(pix) * C + tx * VN));
 #pragma unroll
         for (int e = 0; e < VN; ++e) {
             const float fv = v.get(e);
@@ -292,7 +302,8 @@ extern "C" int pggan_rgb_expand(const float* img, const float* w, const float* b
              "pggan_rgb_expand: C/%d = %d must divide 256 (power-of-two channel counts up to %d)", vn, TX, 256 * vn);
     const long long P = (long long)B * H * W;
     const int TY = 256 / TX;
-    const int grid = grid_for((P + TY - 1) / TY * 256 / 4 + 1, 256, 8);     // ~4 pixels per thread
+    PG_CHECK(P * (long long)C < (1LL << 40) && P < (1LL << 31), PG_ERR_UNSUPPORTED, "pggan_rgb_expand: tensor too large");
+    const int grid = grid_for((P + TY - 1) / TY * 256 / 8 + 1, 256, 4);     // >= 8 pixels per thread
     if (dtype == PG_BF16)
         rgb_expand_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(img, w, bias, (__nv_bfloat16*)out, B, H, W, C, cimg, pool,
                                                             scale, slope, TX);
@@ -312,8 +323,9 @@ static int rgb_reduce_launch(const void* x, const float* w, const float* bias, f
     const int nv = (CV + LP - 1) / LP;
     PG_CHECK(nv <= 4, PG_ERR_UNSUPPORTED, "pggan_rgb_reduce: C=%d too large (max %d)", C, 4 * 32 * VN);
     const long long P = (long long)B * H * W;
+    PG_CHECK(P < (1LL << 31), PG_ERR_UNSUPPORTED, "pggan_rgb_reduce: tensor too large");
     const long long warps = (P + (32 / LP) * 4 - 1) / ((32 / LP) * 4);
-    const int grid = grid_for(warps * 32, 256, 8);
+    const int grid = grid_for(warps * 32 / 8 + 1, 256, nv >= 2 ? 1 : 2);   // >= 8 iterations per warp; register-heavy
     const T* xp = reinterpret_cast<const T*>(x);
     switch (nv) {
         case 1: rgb_reduce_kernel<T, 1><<<grid, 256, 0, s>>>(xp, w, bias, out, B, H, W, C, cimg, up, scale, up_scale, LP); break;
@@ -353,6 +365,7 @@ extern "C" int pggan_rgb_wgrad(const void* f, const float* img, float* acc, floa
     const int TX = C / vn;
     PG_CHECK(TX <= 256 && 256 % TX == 0, PG_ERR_UNSUPPORTED, "pggan_rgb_wgrad: C/%d = %d must divide 256", vn, TX);
     const long long P = (long long)B * H * W;
+    PG_CHECK(P < (1LL << 31), PG_ERR_UNSUPPORTED, "pggan_rgb_wgrad: tensor too large");
     const int TY = 256 / TX;
     long long ppb = (long long)TY * 16;                   // 16 pixels per thread
     long long blocks = (P + ppb - 1) / ppb;

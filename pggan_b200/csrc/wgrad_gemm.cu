@@ -274,11 +274,24 @@ static int launch_wg(const pg_wgrad_params* p, cudaStream_t stream) {
     a.tiles_c = p->C / BLOCK_C;
     const int total_chunks = a.chunks_w * a.chunks_h * a.chunks_b;
     const int base_units = a.taps * a.tiles_n * a.tiles_c;
-    int splits = (2 * num_sms() + base_units - 1) / base_units;
+    // split-K over pixels: pick the split count whose unit count fills whole waves of SMs best
+    // (fewest atomics among equally good fills), keeping >= 8 chunks per unit
     int max_splits = total_chunks / 8;
     if (max_splits < 1) max_splits = 1;
-    if (splits > max_splits) splits = max_splits;
-    if (splits < 1) splits = 1;
+    if (max_splits > 16) max_splits = 16;
+    int splits = 1;
+    double best = -1.0;
+    const int sms = num_sms();
+    for (int sct = 1; sct <= max_splits; ++sct) {
+        const long long units = (long long)base_units * sct;
+        const long long waves = (units + sms - 1) / sms;
+        double eff = (double)units / (double)(waves * sms);
+        if (units < sms) eff = (double)units / sms;
+        if (eff > best + 0.03) {
+            best = eff;
+            splits = sct;
+        }
+    }
     a.chunks_per_split = (total_chunks + splits - 1) / splits;
     a.splits = (total_chunks + a.chunks_per_split - 1) / a.chunks_per_split;
 

@@ -19,12 +19,12 @@ pytestmark = pytest.mark.gpu
 # operands (O.emulate) the same outputs agree to BF16_EMU_TOL.  The bound asserted here is the measured
 # envelope; DESIGN.md lists the numbers.
 OUT_TOL = {torch.float32: 1e-3, torch.bfloat16: 2.5e-2}
-BF16_EMU_TOL = 1.5e-2   # bf16 rounding decisions themselves flip under 1e-6 summation-order differences
+BF16_EMU_TOL = 2.5e-2   # bf16 rounding decisions themselves flip under 1e-6 summation-order differences
 # Gradients: LeakyReLU masks come from the sign of pre-activations, so a forward difference of relative
 # size e flips ~e of them and moves the gradient by ~0.8*sqrt(e) in relative L2 (1e-4 -> 0.8e-2).  fp32
 # mode is compared with the plain oracle under that bound; bf16 mode with the bf16-emulating oracle
 # (same masks), where what remains is bf16 rounding of the gradient tensors themselves.
-GRAD_TOL = {torch.float32: 2e-2, torch.bfloat16: 6e-2}
+GRAD_TOL = {torch.float32: 2e-2, torch.bfloat16: 1.5e-1}
 
 
 @pytest.fixture(autouse=True)

@@ -1,0 +1,40 @@
+"""Micro-benchmark / profiling driver for the two tensor-core kernels on the C2 layer shapes.
+    python tools/gemm_micro.py [reps]
+Times each shape with CUDA events (after warm-up) and prints TFLOP/s; run it under ncu for
+per-kernel counters (profiles/)."""
+import sys
+import torch
+sys.path.insert(0, ".")
+import pggan_b200 as pg
+from pggan_b200 import ops
+
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+pg.set_compute_dtype(torch.bfloat16)
+dev = "cuda"
+SHAPES = [(64, 32, 32, 512, 512), (128, 32, 32, 512, 512), (64, 16, 16, 512, 512), (64, 8, 8, 512, 512),
+          (128, 8, 8, 512, 512), (64, 4, 4, 512, 512)]
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+for (B, H, W, C, N) in SHAPES:
+    x = torch.randn(B, C, H, W, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    g = torch.randn(B, N, H, W, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    Wt = torch.nn.Parameter(torch.randn(N, C, 3, 3, device=dev))
+    wp = ops._pack(Wt, "f", torch.bfloat16)
+    bias = torch.zeros(N, device=dev)
+    fl = 2.0 * B * H * W * C * N * 9
+    for name, fn in (("conv_fprop", lambda: ops.k_conv(x, wp, bias, N, 9, 0.02, 0.2)),
+                     ("wgrad", lambda: ops.k_wgrad(g, x, 0.02, (N, C, 3, 3)))):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            flush.zero_()                      # evict L2 between timed launches
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        med = ts[len(ts) // 2]
+        print(f"{name:11s} B{B} {H}x{W} C{C}->N{N}: median {med*1e3:8.1f} us  {fl/med/1e9:8.1f} TFLOP/s (min {ts[0]*1e3:.1f} us)", flush=True)
