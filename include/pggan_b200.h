@@ -61,9 +61,11 @@ typedef struct {
 } pg_pack_map;
 /* out[n][t][c] (dtype) = in[off(n,t,c)] or 0 in the padding */
 int pggan_pack_weight(const float* in, void* out, int dtype, const pg_pack_map* map, void* stream);
-/* gradients back: out_fp32[off(n,t,c)] (+)= scale * in_fp32[n][t][c] for the valid (n,c); `in` is the dense
- * [n_total][taps][c_total] fp32 accumulator written by pggan_conv_wgrad. accumulate: 0 = overwrite. */
-int pggan_unpack_wgrad(const float* in, float* out, const pg_pack_map* map, float scale, int accumulate, void* stream);
+/* gradients back: out_fp32[off(n,t,c)] (+)= scale * sum_s in_fp32[s][n][t][c] for the valid (n,c); `in` holds
+ * the `slices` dense [n_total][taps][c_total] fp32 partial-sum slices written by pggan_conv_wgrad.
+ * accumulate: 0 = overwrite, 1 = add to what `out` holds (gradient accumulation straight into .grad). */
+int pggan_unpack_wgrad(const float* in, float* out, const pg_pack_map* map, int slices, float scale, int accumulate,
+                       void* stream);
 
 /* fp32 mode = 3xTF32.  The tensor core truncates fp32 operands to tf32 (hi); this writes three copies
  * of in [m][c], one of them (slot lo_slot) holding lo = x - trunc_tf32(x), concatenated along channels
@@ -99,8 +101,9 @@ typedef struct {
 } pg_conv_params;
 int pggan_conv_fprop(const pg_conv_params* p, void* stream);
 
-/* Weight-gradient GEMM:  acc[n][t][c] += sum_{b,h,w} g[b,h,w,n] * x[b, h+dh(t), w+dw(t), c]
- * acc is a dense fp32 [N][taps][C] accumulator the caller zeroes (split-K uses atomics).
+/* Weight-gradient GEMM:  sum_s acc[s][n][t][c] = sum_{b,h,w} g[b,h,w,n] * x[b, h+dh(t), w+dw(t), c]
+ * acc holds pggan_conv_wgrad_slices(p) dense fp32 [N][taps][C] slices (split-K over pixels writes one slice per
+ * split with plain stores); the call defines every element, nothing needs pre-zeroing.
  * Also the grad-of-dgrad w.r.t. W with operands (g_pre, ggx).
  * Replaces: autograd convolution_backward (weight) / addmm backward of lib/layers.py:60.
  */
@@ -115,6 +118,7 @@ typedef struct {
     void* ws_x;
 } pg_wgrad_params;
 int pggan_conv_wgrad(const pg_wgrad_params* p, void* stream);
+int pggan_conv_wgrad_slices(const pg_wgrad_params* p); /* how many slices the call above will write (>= 1) */
 
 /* ------------------------------------------------------------------------------------------
  * Elementwise / reduction kernels on NHWC feature maps (n = element count, m = pixels).

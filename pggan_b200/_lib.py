@@ -53,10 +53,11 @@ SIGNATURES = {
     "pggan_set_conv_backend": (c_int, [c_int]),
     "pggan_launch_counts": (c_int, [POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]),
     "pggan_pack_weight": (c_int, [c_void_p, c_void_p, c_int, POINTER(PackMap), c_void_p]),
-    "pggan_unpack_wgrad": (c_int, [c_void_p, c_void_p, POINTER(PackMap), c_float, c_int, c_void_p]),
+    "pggan_unpack_wgrad": (c_int, [c_void_p, c_void_p, POINTER(PackMap), c_int, c_float, c_int, c_void_p]),
     "pggan_split3": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
     "pggan_conv_fprop": (c_int, [POINTER(ConvParams), c_void_p]),
     "pggan_conv_wgrad": (c_int, [POINTER(WgradParams), c_void_p]),
+    "pggan_conv_wgrad_slices": (c_int, [POINTER(WgradParams)]),
     "pggan_lrelu_mask_mul": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_int, c_void_p]),
     "pggan_upsample2x": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "pggan_pool2x2": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_int,

@@ -371,13 +371,15 @@ __global__ void pack_weight_kernel(const float* __restrict__ in, T* __restrict__
 }
 
 __global__ void unpack_wgrad_kernel(const float* __restrict__ in, float* __restrict__ out, PackMap m, long long total,
-                                    float scale, int accumulate) {
+                                    float scale, int accumulate, int slices, long long slice_elems) {
     GRID_STRIDE(i, total) {
         const int c = static_cast<int>(i % m.c_valid);
         const long long r = i / m.c_valid;
         const int t = static_cast<int>(r % m.taps);
         const int n = static_cast<int>(r / m.taps);
-        const float v = in[(static_cast<long long>(n) * m.taps + t) * m.c_total + c] * scale;
+        float v = 0.f;
+        for (int sl = 0; sl < slices; ++sl) v += in[sl * slice_elems + (static_cast<long long>(n) * m.taps + t) * m.c_total + c];
+        v *= scale;
         float* o = out + pack_off(m, n, t, c);
         *o = accumulate ? (*o + v) : v;
     }
@@ -401,13 +403,17 @@ __global__ void __launch_bounds__(256) pack_oihw_f_kernel(const float* __restric
 }
 // gradients back: gW[o][i][t] = scale * acc[o][t][i]
 __global__ void __launch_bounds__(256) unpack_oihw_kernel(const float* __restrict__ acc, float* __restrict__ gW, int I,
-                                                          int Ip, float scale, int accumulate) {
+                                                          int Ip, float scale, int accumulate, int slices,
+                                                          long long slice_elems) {
     __shared__ float tile[64 * 9];
     const int o = blockIdx.y, i0 = blockIdx.x * 64;
     const int ni = min(64, I - i0);
     for (int k = threadIdx.x; k < 64 * 9; k += blockDim.x) {
         const int t = k / 64, ii = k % 64;
-        tile[ii * 9 + t] = (ii < ni) ? acc[(static_cast<size_t>(o) * 9 + t) * Ip + i0 + ii] : 0.f;
+        float v = 0.f;
+        if (ii < ni)
+            for (int sl = 0; sl < slices; ++sl) v += acc[sl * slice_elems + (static_cast<size_t>(o) * 9 + t) * Ip + i0 + ii];
+        tile[ii * 9 + t] = v;
     }
     __syncthreads();
     for (int k = threadIdx.x; k < ni * 9; k += blockDim.x) {
@@ -678,9 +684,9 @@ extern "C" int pggan_pack_weight(const float* in, void* out, int dtype, const pg
     return PG_OK;
 }
 
-extern "C" int pggan_unpack_wgrad(const float* in, float* out, const pg_pack_map* map, float scale, int accumulate,
-                                  void* stream) {
-    PG_CHECK(in && out, PG_ERR_ARG, "pggan_unpack_wgrad: null pointer");
+extern "C" int pggan_unpack_wgrad(const float* in, float* out, const pg_pack_map* map, int slices, float scale,
+                                  int accumulate, void* stream) {
+    PG_CHECK(in && out && slices >= 1, PG_ERR_ARG, "pggan_unpack_wgrad: bad args");
     PackMap m;
     int rc = make_map(m, map, "pggan_unpack_wgrad");
     if (rc != PG_OK) return rc;
@@ -688,10 +694,12 @@ extern "C" int pggan_unpack_wgrad(const float* in, float* out, const pg_pack_map
     const long long total = (long long)m.n_valid * m.taps * m.c_valid;
     const bool oihw_f = m.taps == 9 && m.n2 == 1 && m.c2 == 1 && m.base == 0 && m.s_t == 1 && m.s_c1 == 9 &&
                         m.s_n1 == 9LL * m.c_valid && m.n_valid == m.n_total;
+    const long long slice_elems = (long long)m.n_total * m.taps * m.c_total;
     if (oihw_f)
-        unpack_oihw_kernel<<<dim3((m.c_valid + 63) / 64, m.n_total), 256, 0, s>>>(in, out, m.c_valid, m.c_total, scale, accumulate);
+        unpack_oihw_kernel<<<dim3((m.c_valid + 63) / 64, m.n_total), 256, 0, s>>>(in, out, m.c_valid, m.c_total, scale, accumulate,
+                                                                               slices, slice_elems);
     else
-        unpack_wgrad_kernel<<<ew_grid(total, 256), 256, 0, s>>>(in, out, m, total, scale, accumulate);
+        unpack_wgrad_kernel<<<ew_grid(total, 256), 256, 0, s>>>(in, out, m, total, scale, accumulate, slices, slice_elems);
     PG_LAUNCH_CHECK();
     g_other_launches++;
     return PG_OK;

@@ -8,8 +8,9 @@
 // MN (channels) in 128-byte spans (LBO = BKP*128 B).  The x box is shifted by the tap offset and
 // TMA's out-of-bounds zero fill provides the conv padding, exactly as in conv_gemm.cu.
 //
-// D tile: 128 output channels (g) x BLOCK_C input channels (x), fp32 in TMEM; epilogue adds the
-// partial sums into the dense fp32 accumulator with vector reductions (red.global.add.v4.f32).
+// D tile: 128 output channels (g) x BLOCK_C input channels (x), fp32 in TMEM.  Split-K partial sums go
+// to per-split slices of the accumulator with plain vector stores (no atomics, no pre-zeroing);
+// pggan_unpack_wgrad sums the slices while it scales/transposes into the parameter layout.
 //
 // Replaces cuDNN wgrad / cuBLAS behind autograd's convolution_backward for
 // EqualizedConv2d/EqualizedLinear (reference lib/layers.py:60) and provides the
@@ -41,10 +42,12 @@ template <typename T, int BLOCK_C> struct WgCfg {
 
 struct WgKArgs {
     float* acc;
+    long long slice_elems;          // N*taps*C: split s writes its partial sums to acc + s*slice_elems
     int B, H, W, C, N, taps;
     int PW, PH, PB;                 // pixel box of one stage
     int chunks_w, chunks_h, chunks_b;
     int tiles_n, tiles_c, splits, chunks_per_split;
+    int span5d;                     // 1: tensor maps are 5-D (channel spans are the 5th dim): one TMA box per operand
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -93,13 +96,13 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
     const int num_units = a.taps * a.tiles_n * a.tiles_c * a.splits;
 
     // unit -> (split, tap, n tile, c tile); c fastest so neighbouring CTAs share the g tile in L2
-    auto decode = [&](int unit, int& ct, int& nt, int& tap, int& k0, int& k1) {
+    auto decode = [&](int unit, int& ct, int& nt, int& tap, int& k0, int& k1, int& sp) {
         ct = unit % a.tiles_c;
         unit /= a.tiles_c;
         nt = unit % a.tiles_n;
         unit /= a.tiles_n;
         tap = unit % a.taps;
-        const int sp = unit / a.taps;
+        sp = unit / a.taps;
         k0 = sp * a.chunks_per_split;
         k1 = k0 + a.chunks_per_split;
         if (k1 > total_chunks) k1 = total_chunks;
@@ -110,8 +113,8 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
             int stage = 0;
             uint32_t phase = 0;
             for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-                int ct, nt, tap, k0, k1;
-                decode(unit, ct, nt, tap, k0, k1);
+                int ct, nt, tap, k0, k1, sp;
+                decode(unit, ct, nt, tap, k0, k1, sp);
                 int dh = 0, dw = 0;
                 if (a.taps == 9) {
                     dh = tap / 3 - 1;
@@ -124,15 +127,23 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * Cfg::kStageBytes;
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-#pragma unroll
-                    for (int gidx = 0; gidx < Cfg::GA; ++gidx)
-                        tma_load_4d(sa + gidx * Cfg::kGroupBytes, &tmap_g, &full_bar[stage],
-                                    nt * 128 + gidx * Cfg::CPS, w0, h0, b0);
                     uint8_t* sb = sa + Cfg::GA * Cfg::kGroupBytes;
+                    if (a.span5d) {
+                        // one box per operand: the channel spans are the outermost box dimension, so the box lands
+                        // span-major ([span][pixel][128 B]) — the same smem image as the per-span loads below, with
+                        // 2 TMA instructions per stage instead of GA+GB (the single producer thread was issue-bound)
+                        tma_load_5d(sa, &tmap_g, &full_bar[stage], 0, w0, h0, b0, nt * Cfg::GA);
+                        tma_load_5d(sb, &tmap_x, &full_bar[stage], 0, w0 + dw, h0 + dh, b0, ct * Cfg::GB);
+                    } else {
 #pragma unroll
-                    for (int gidx = 0; gidx < Cfg::GB; ++gidx)
-                        tma_load_4d(sb + gidx * Cfg::kGroupBytes, &tmap_x, &full_bar[stage],
-                                    ct * BLOCK_C + gidx * Cfg::CPS, w0 + dw, h0 + dh, b0);
+                        for (int gidx = 0; gidx < Cfg::GA; ++gidx)
+                            tma_load_4d(sa + gidx * Cfg::kGroupBytes, &tmap_g, &full_bar[stage],
+                                        nt * 128 + gidx * Cfg::CPS, w0, h0, b0);
+#pragma unroll
+                        for (int gidx = 0; gidx < Cfg::GB; ++gidx)
+                            tma_load_4d(sb + gidx * Cfg::kGroupBytes, &tmap_x, &full_bar[stage],
+                                        ct * BLOCK_C + gidx * Cfg::CPS, w0 + dw, h0 + dh, b0);
+                    }
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1;
@@ -147,8 +158,8 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
             uint32_t phase = 0;
             int it = 0;
             for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
-                int ct, nt, tap, k0, k1;
-                decode(unit, ct, nt, tap, k0, k1);
+                int ct, nt, tap, k0, k1, sp;
+                decode(unit, ct, nt, tap, k0, k1, sp);
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -182,13 +193,13 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
         const int row = q * 32 + lane;
         int it = 0;
         for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
-            int ct, nt, tap, k0, k1;
-            decode(unit, ct, nt, tap, k0, k1);
+            int ct, nt, tap, k0, k1, sp;
+            decode(unit, ct, nt, tap, k0, k1, sp);
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const int n = nt * 128 + row;
             const bool valid = (n < a.N) && (k1 > k0);
-            float* dst = a.acc + (static_cast<size_t>(n) * a.taps + tap) * a.C + ct * BLOCK_C;
+            float* dst = a.acc + sp * a.slice_elems + (static_cast<size_t>(n) * a.taps + tap) * a.C + ct * BLOCK_C;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_C;
@@ -198,11 +209,12 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
                 uint32_t r[32];
                 tmem_ld32(taddr + j * 32, r);
                 tmem_ld_wait();
-                if (valid) {
+                if (valid) {     // every (split, tap, n, c) element is owned by exactly one unit: plain stores
 #pragma unroll
                     for (int c = 0; c < 8; ++c)
-                        red_add_v4(dst + j * 32 + c * 4, __uint_as_float(r[c * 4 + 0]), __uint_as_float(r[c * 4 + 1]),
-                                   __uint_as_float(r[c * 4 + 2]), __uint_as_float(r[c * 4 + 3]));
+                        *reinterpret_cast<float4*>(dst + j * 32 + c * 4) =
+                            make_float4(__uint_as_float(r[c * 4 + 0]), __uint_as_float(r[c * 4 + 1]),
+                                        __uint_as_float(r[c * 4 + 2]), __uint_as_float(r[c * 4 + 3]));
                 }
             }
             tc_fence_before();
@@ -259,11 +271,11 @@ __global__ void wgrad_direct_kernel(const T* __restrict__ g, const T* __restrict
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 template <typename T, int BLOCK_C>
-static int launch_wg(const pg_wgrad_params* p, cudaStream_t stream) {
+static void plan_wg(const pg_wgrad_params* p, WgKArgs& a) {
     using Cfg = WgCfg<T, BLOCK_C>;
-    WgKArgs a;
     a.acc = p->acc;
     a.B = p->B; a.H = p->H; a.W = p->W; a.C = p->C; a.N = p->N; a.taps = p->taps;
+    a.slice_elems = (long long)p->N * p->taps * p->C;
     a.PW = p->W < Cfg::BKP ? p->W : Cfg::BKP;
     a.PH = p->H < (Cfg::BKP / a.PW) ? p->H : (Cfg::BKP / a.PW);
     a.PB = Cfg::BKP / (a.PW * a.PH);
@@ -275,10 +287,10 @@ static int launch_wg(const pg_wgrad_params* p, cudaStream_t stream) {
     const int total_chunks = a.chunks_w * a.chunks_h * a.chunks_b;
     const int base_units = a.taps * a.tiles_n * a.tiles_c;
     // split-K over pixels: pick the split count whose unit count fills whole waves of SMs best
-    // (fewest atomics among equally good fills), keeping >= 8 chunks per unit
+    // (fewest slices among equally good fills), keeping >= 8 chunks per unit
     int max_splits = total_chunks / 8;
     if (max_splits < 1) max_splits = 1;
-    if (max_splits > 16) max_splits = 16;
+    if (max_splits > 8) max_splits = 8;
     int splits = 1;
     double best = -1.0;
     const int sms = num_sms();
@@ -286,7 +298,6 @@ static int launch_wg(const pg_wgrad_params* p, cudaStream_t stream) {
         const long long units = (long long)base_units * sct;
         const long long waves = (units + sms - 1) / sms;
         double eff = (double)units / (double)(waves * sms);
-        if (units < sms) eff = (double)units / sms;
         if (eff > best + 0.03) {
             best = eff;
             splits = sct;
@@ -294,21 +305,49 @@ static int launch_wg(const pg_wgrad_params* p, cudaStream_t stream) {
     }
     a.chunks_per_split = (total_chunks + splits - 1) / splits;
     a.splits = (total_chunks + a.chunks_per_split - 1) / a.chunks_per_split;
+}
 
+template <typename T, int BLOCK_C>
+static int launch_wg(const pg_wgrad_params* p, cudaStream_t stream) {
+    using Cfg = WgCfg<T, BLOCK_C>;
+    WgKArgs a;
+    plan_wg<T, BLOCK_C>(p, a);
+    const int base_units = a.taps * a.tiles_n * a.tiles_c;
     const uint64_t es = sizeof(T);
     CUtensorMap tg, tx;
-    uint32_t box[4] = {(uint32_t)Cfg::CPS, (uint32_t)a.PW, (uint32_t)a.PH, (uint32_t)a.PB};
-    {
-        uint64_t dims[4] = {(uint64_t)p->N, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
-        uint64_t strides[3] = {(uint64_t)p->N * es, (uint64_t)p->W * p->N * es, (uint64_t)p->H * p->W * p->N * es};
-        int rc = encode_tmap(&tg, DT<T>::kEnum, 4, p->g, dims, strides, box, sizeof(T) == 4 ? 12832 : 128);
-        if (rc != PG_OK) return rc;
-    }
-    {
-        uint64_t dims[4] = {(uint64_t)p->C, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
-        uint64_t strides[3] = {(uint64_t)p->C * es, (uint64_t)p->W * p->C * es, (uint64_t)p->H * p->W * p->C * es};
-        int rc = encode_tmap(&tx, DT<T>::kEnum, 4, p->x, dims, strides, box, sizeof(T) == 4 ? 12832 : 128);
-        if (rc != PG_OK) return rc;
+    const int sw = sizeof(T) == 4 ? 12832 : 128;
+    a.span5d = (p->N % Cfg::CPS == 0 && p->C % Cfg::CPS == 0) ? 1 : 0;
+    if (a.span5d) {
+        // dims: (channel within span, w, h, b, span); the span stride is one 128-byte span
+        const uint64_t span_bytes = 128;
+        {
+            uint64_t dims[5] = {(uint64_t)Cfg::CPS, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B, (uint64_t)(p->N / Cfg::CPS)};
+            uint64_t strides[4] = {(uint64_t)p->N * es, (uint64_t)p->W * p->N * es, (uint64_t)p->H * p->W * p->N * es, span_bytes};
+            uint32_t box[5] = {(uint32_t)Cfg::CPS, (uint32_t)a.PW, (uint32_t)a.PH, (uint32_t)a.PB, (uint32_t)Cfg::GA};
+            int rc = encode_tmap(&tg, DT<T>::kEnum, 5, p->g, dims, strides, box, sw);
+            if (rc != PG_OK) return rc;
+        }
+        {
+            uint64_t dims[5] = {(uint64_t)Cfg::CPS, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B, (uint64_t)(p->C / Cfg::CPS)};
+            uint64_t strides[4] = {(uint64_t)p->C * es, (uint64_t)p->W * p->C * es, (uint64_t)p->H * p->W * p->C * es, span_bytes};
+            uint32_t box[5] = {(uint32_t)Cfg::CPS, (uint32_t)a.PW, (uint32_t)a.PH, (uint32_t)a.PB, (uint32_t)Cfg::GB};
+            int rc = encode_tmap(&tx, DT<T>::kEnum, 5, p->x, dims, strides, box, sw);
+            if (rc != PG_OK) return rc;
+        }
+    } else {
+        uint32_t box[4] = {(uint32_t)Cfg::CPS, (uint32_t)a.PW, (uint32_t)a.PH, (uint32_t)a.PB};
+        {
+            uint64_t dims[4] = {(uint64_t)p->N, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
+            uint64_t strides[3] = {(uint64_t)p->N * es, (uint64_t)p->W * p->N * es, (uint64_t)p->H * p->W * p->N * es};
+            int rc = encode_tmap(&tg, DT<T>::kEnum, 4, p->g, dims, strides, box, sw);
+            if (rc != PG_OK) return rc;
+        }
+        {
+            uint64_t dims[4] = {(uint64_t)p->C, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
+            uint64_t strides[3] = {(uint64_t)p->C * es, (uint64_t)p->W * p->C * es, (uint64_t)p->H * p->W * p->C * es};
+            int rc = encode_tmap(&tx, DT<T>::kEnum, 4, p->x, dims, strides, box, sw);
+            if (rc != PG_OK) return rc;
+        }
     }
     auto kern = wgrad_gemm_kernel<T, BLOCK_C>;
     static bool attr_done = false;
@@ -324,15 +363,36 @@ static int launch_wg(const pg_wgrad_params* p, cudaStream_t stream) {
     return PG_OK;
 }
 
+template <typename T, int BLOCK_C>
+static int slices_wg(const pg_wgrad_params* p) {
+    WgKArgs a;
+    plan_wg<T, BLOCK_C>(p, a);
+    return a.splits;
+}
+
+// slices_out != nullptr: only report how many partial-sum slices the launch would write (no launch)
 template <typename T>
-static int wgrad_dispatch(const pg_wgrad_params* p_in, cudaStream_t stream) {
+static int wgrad_dispatch(const pg_wgrad_params* p_in, cudaStream_t stream, int* slices_out) {
     constexpr int CPS = 128 / sizeof(T);
     constexpr bool kF32 = sizeof(T) == 4;
     pg_wgrad_params local = *p_in;
     const pg_wgrad_params* p = &local;
     const bool tc_ok = g_conv_backend == PG_BACKEND_AUTO && is_pow2(p->H) && is_pow2(p->W) && (p->C % CPS == 0) &&
-                       (p->N % 8 == 0) && (!kF32 || (p->ws_g && p->ws_x)) && (reinterpret_cast<uintptr_t>(p->g) % 16 == 0) &&
+                       (p->N % 8 == 0) && (!kF32 || slices_out || (p->ws_g && p->ws_x)) &&
+                       (reinterpret_cast<uintptr_t>(p->g) % 16 == 0) &&
                        (reinterpret_cast<uintptr_t>(p->x) % 16 == 0) && (reinterpret_cast<uintptr_t>(p->acc) % 16 == 0);
+    if (tc_ok && slices_out) {
+        if (kF32) local.B = 3 * p->B;
+        if (p->C % 256 == 0) *slices_out = slices_wg<T, 256>(p);
+        else if (p->C % 128 == 0) *slices_out = slices_wg<T, 128>(p);
+        else if (p->C % 64 == 0) *slices_out = slices_wg<T, 64>(p);
+        else *slices_out = slices_wg<T, 32>(p);
+        return PG_OK;
+    }
+    if (slices_out) {
+        *slices_out = 1;
+        return PG_OK;
+    }
     if (tc_ok) {
         if (kF32) {
             // 3xTF32 along the pixel reduction: (g, g_lo, g) and (x, x, x_lo) stacked along the batch
@@ -352,6 +412,8 @@ static int wgrad_dispatch(const pg_wgrad_params* p_in, cudaStream_t stream) {
             if (p->C % 32 == 0) return launch_wg<T, 32>(p, stream);
         }
     }
+    // SIMT path: one slice, partial sums meet through atomics on a zeroed accumulator
+    PG_CUDA(cudaMemsetAsync(p->acc, 0, sizeof(float) * (size_t)p->N * p->taps * p->C, stream));
     const long long P = (long long)p->B * p->H * p->W;
     long long pix_per_block = 256;
     while ((P + pix_per_block - 1) / pix_per_block > 2048) pix_per_block *= 2;
@@ -374,6 +436,21 @@ extern "C" int pggan_conv_wgrad(const pg_wgrad_params* p, void* stream) {
     PG_CHECK(p->taps == 1 || p->taps == 9, PG_ERR_ARG, "pggan_conv_wgrad: taps must be 1 or 9 (got %d)", p->taps);
     PG_CHECK(p->dtype == PG_BF16 || p->dtype == PG_F32, PG_ERR_ARG, "pggan_conv_wgrad: bad dtype %d", p->dtype);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    if (p->dtype == PG_BF16) return wgrad_dispatch<__nv_bfloat16>(p, s);
-    return wgrad_dispatch<float>(p, s);
+    if (p->dtype == PG_BF16) return wgrad_dispatch<__nv_bfloat16>(p, s, nullptr);
+    return wgrad_dispatch<float>(p, s, nullptr);
+}
+
+extern "C" int pggan_conv_wgrad_slices(const pg_wgrad_params* p) {
+    using namespace pg;
+    if (p == nullptr || p->B <= 0 || p->H <= 0 || p->W <= 0 || p->C <= 0 || p->N <= 0) return 1;
+    int slices = 1;
+    pg_wgrad_params q = *p;
+    if (!q.g) q.g = reinterpret_cast<const void*>(uintptr_t(256));      // alignment checks only
+    if (!q.x) q.x = reinterpret_cast<const void*>(uintptr_t(256));
+    if (!q.acc) q.acc = reinterpret_cast<float*>(uintptr_t(256));
+    if (q.dtype == PG_BF16)
+        wgrad_dispatch<__nv_bfloat16>(&q, nullptr, &slices);
+    else if (q.dtype == PG_F32)
+        wgrad_dispatch<float>(&q, nullptr, &slices);
+    return slices;
 }

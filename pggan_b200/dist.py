@@ -55,6 +55,10 @@ class GradSync:
         self._launched: List[bool] = []
         self._handles = []
         self._hooks = [p.register_post_accumulate_grad_hook(self._hook) for p in grads.params]
+        if self.world > 1:
+            # bucket readiness relies on autograd's post-accumulate hooks: keep gradients on the autograd path
+            from . import ops
+            ops.unregister_grad_sink(grads.params)
 
     # ------------------------------------------------------------------------------------
     def arm(self):

@@ -69,6 +69,39 @@ def input_grad_only():
         _SKIP_PARAM_GRADS = prev
 
 
+# ------------------------------------------------------------------------------- gradient sinks
+# Parameters registered here (by optim.FlatGrads) own a persistent fp32 `.grad` view into a flat buffer.
+# In a plain backward (no create_graph) the GEMM-class Functions then ACCUMULATE weight / bias gradients
+# straight into that view (pggan_unpack_wgrad accumulate=1, atomics of the bias column sums) and return
+# None to autograd: no temporary gradient tensor, no AccumulateGrad add kernel, no zero-fill.
+# Not used under data parallelism (GradSync needs autograd's post-accumulate hooks for bucket readiness).
+_GRAD_SINK: dict = {}
+
+
+def register_grad_sink(params):
+    import weakref
+    for p in params:
+        _GRAD_SINK[id(p)] = weakref.ref(p)
+
+
+def unregister_grad_sink(params):
+    for p in params:
+        _GRAD_SINK.pop(id(p), None)
+
+
+def _sink(p):
+    """the parameter's .grad if gradients may be accumulated into it in place, else None"""
+    if p is None:
+        return None
+    ref = _GRAD_SINK.get(id(p))
+    if ref is None or ref() is not p:
+        return None
+    g = p.grad
+    if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.shape != p.shape:
+        return None
+    return g
+
+
 # ------------------------------------------------------------------------------------ helpers
 def _enum(dtype: torch.dtype) -> int:
     if dtype == torch.bfloat16:
@@ -223,19 +256,21 @@ def k_conv(x, wp, bias, N, taps, scale, slope=1.0, mask_src=None, mask_slope=1.0
     return y
 
 
-def k_wgrad(g, x, scale, wshape, layout=None):
-    """returns the weight gradient in the parameter's own fp32 layout"""
+def k_wgrad(g, x, scale, wshape, layout=None, accumulate_into=None):
+    """weight gradient in the parameter's own fp32 layout: a new tensor, or added into `accumulate_into`"""
     _need_cuda(g)
     b, n, h, w = _dims(g)
     c = _dims(x)[1]
     N, C, taps, fmap, _ = _maps(wshape, layout)
     if (n, c) != (N, C):
         raise ValueError(f"wgrad operand channels ({n},{c}) do not match the layer ({N},{C})")
-    acc = torch.zeros((n, taps, c), dtype=torch.float32, device=g.device)
     p = L.WgradParams()
-    p.g, p.x, p.acc = g.data_ptr(), x.data_ptr(), acc.data_ptr()
+    p.g, p.x = g.data_ptr(), x.data_ptr()
     p.B, p.H, p.W, p.C, p.N, p.taps = b, h, w, c, n, taps
     p.dtype = _enum(g.dtype)
+    slices = L.load().pggan_conv_wgrad_slices(ctypes.byref(p))
+    acc = torch.empty((slices, n, taps, c), dtype=torch.float32, device=g.device)
+    p.acc = acc.data_ptr()
     ws = None
     if g.dtype == torch.float32:
         ws = (torch.empty(3 * g.numel(), dtype=torch.float32, device=g.device),
@@ -243,30 +278,42 @@ def k_wgrad(g, x, scale, wshape, layout=None):
         p.ws_g, p.ws_x = ws[0].data_ptr(), ws[1].data_ptr()
     with _Timed("wgrad_gemm", (b, h, w, c, n, taps)):
         L.check(L.load().pggan_conv_wgrad(ctypes.byref(p), _s()), "pggan_conv_wgrad")
+    m = _packmap(fmap)
+    if accumulate_into is not None:
+        L.check(L.load().pggan_unpack_wgrad(_p(acc), _p(accumulate_into), ctypes.byref(m), slices, float(scale), 1,
+                                            _s()), "pggan_unpack_wgrad")
+        return None
     pad = fmap[1] < fmap[0] or fmap[5] < fmap[4]
     out = (torch.zeros if pad else torch.empty)(tuple(wshape), dtype=torch.float32, device=g.device)
-    m = _packmap(fmap)
-    L.check(L.load().pggan_unpack_wgrad(_p(acc), _p(out), ctypes.byref(m), float(scale), 0, _s()), "pggan_unpack_wgrad")
+    L.check(L.load().pggan_unpack_wgrad(_p(acc), _p(out), ctypes.byref(m), slices, float(scale), 0, _s()),
+            "pggan_unpack_wgrad")
     return out
 
 
-def k_mask_colsum(g, y, slope, want_out, colsum_scale):
-    """fused LeakyReLU backward (+ bias gradient): returns (g*mask(y) or None, colsum or None)"""
+def k_mask_colsum(g, y, slope, want_out, colsum_scale, colsum_into=None):
+    """fused LeakyReLU backward (+ bias gradient): returns (g*mask(y) or None, colsum or None).
+    colsum_into: an fp32 [C] tensor the column sums are ADDED to (then the second result is None)."""
     b, c, h, w = _dims(g)
     vn = 16 // g.element_size()
     if c % vn != 0 or (c // vn) > 256 or 256 % (c // vn) != 0:          # odd widths: two plain passes
         out = k_mask_mul(g, y, slope) if (want_out and y is not None) else (g if want_out else None)
         src = out if out is not None else (k_mask_mul(g, y, slope) if y is not None else g)
-        return out, (k_colsum(src, colsum_scale) if colsum_scale is not None else None)
+        cs = k_colsum(src, colsum_scale) if colsum_scale is not None else None
+        if cs is not None and colsum_into is not None:
+            colsum_into.add_(cs)
+            cs = None
+        return out, cs
     out = torch.empty_like(g) if (want_out and y is not None) else None
-    cs = torch.zeros((c,), dtype=torch.float32, device=g.device) if colsum_scale is not None else None
+    cs = None
+    if colsum_scale is not None:
+        cs = colsum_into if colsum_into is not None else torch.zeros((c,), dtype=torch.float32, device=g.device)
     if out is None and cs is None:
         return (g if want_out else None), None
     L.check(L.load().pggan_mask_colsum(_p(g), _p(y), _p(out), _p(cs), b * h * w, c, float(slope),
                                        float(colsum_scale or 0.0), _enum(g.dtype), _s()), "pggan_mask_colsum")
     if want_out and out is None:
         out = g
-    return out, cs
+    return out, (None if colsum_into is not None else cs)
 
 
 def k_mask_mul(g, y, slope):
@@ -330,6 +377,7 @@ class ConvF(torch.autograd.Function):
         y = k_conv(x, _pack(W, "f", x.dtype, layout), bias, N, taps, scale, slope, raw_out=raw_out)
         ctx.save_for_backward(x, W, y if slope != 1.0 else None)
         ctx.scale, ctx.slope, ctx.has_bias, ctx.layout = scale, slope, b is not None, layout
+        ctx.bias_param = b if isinstance(b, torch.nn.Parameter) else None
         return y
 
     @staticmethod
@@ -346,9 +394,18 @@ class ConvF(torch.autograd.Function):
             if need_b:
                 gb = ColSum.apply(g, ctx.scale)
         else:
-            # plain backward: LeakyReLU mask and bias gradient in one pass over g
+            # plain backward: LeakyReLU mask and bias gradient in one pass over g; gradients of registered
+            # parameters are accumulated in place (see _GRAD_SINK)
+            b_sink = _sink(ctx.bias_param) if (need_b and not (ctx.layout and ctx.layout[0] == "lin_out_perm")) else None
             g, gb = k_mask_colsum(g, y if ctx.slope != 1.0 else None, ctx.slope, True,
-                                  ctx.scale if need_b else None)
+                                  ctx.scale if need_b else None, colsum_into=b_sink)
+            if gb is not None:
+                gb = _perm_bias(gb, ctx.layout, inverse=True)
+            if ctx.needs_input_grad[0]:
+                gx = ConvT.apply(g, W, ctx.scale, ctx.layout)
+            if need_w:
+                gW = k_wgrad(g, x, ctx.scale, tuple(W.shape), ctx.layout, accumulate_into=_sink(W))
+            return gx, gW, gb, None, None, None, None
         if gb is not None:
             gb = _perm_bias(gb, ctx.layout, inverse=True)
         if ctx.needs_input_grad[0]:
@@ -377,6 +434,7 @@ class ConvActPN(torch.autograd.Function):
                 "pggan_pixelnorm_fwd")
         ctx.save_for_backward(x, W, y, r)
         ctx.scale, ctx.slope, ctx.has_bias, ctx.layout = scale, slope, b is not None, layout
+        ctx.bias_param = b if isinstance(b, torch.nn.Parameter) else None
         return y
 
     @staticmethod
@@ -387,7 +445,10 @@ class ConvActPN(torch.autograd.Function):
         bb, c, h, w = _dims(y)
         need_b = ctx.has_bias and ctx.needs_input_grad[2] and not _SKIP_PARAM_GRADS
         g = torch.empty_like(y)
-        gb = torch.zeros((c,), dtype=torch.float32, device=y.device) if need_b else None
+        b_sink = _sink(ctx.bias_param) if (need_b and not (ctx.layout and ctx.layout[0] == "lin_out_perm")) else None
+        gb = None
+        if need_b:
+            gb = b_sink if b_sink is not None else torch.zeros((c,), dtype=torch.float32, device=y.device)
         L.check(L.load().pggan_pixelnorm_bwd(_p(gy), _p(y), _p(r), _p(g), bb * h * w, c, float(ctx.slope), _p(gb),
                                              float(ctx.scale), _enum(y.dtype), _s()), "pggan_pixelnorm_bwd")
         gx = gW = None
@@ -395,8 +456,10 @@ class ConvActPN(torch.autograd.Function):
             N, C, taps, _, _ = _maps(W.shape, ctx.layout)
             gx = k_conv(g, _pack(W, "t", g.dtype, ctx.layout), None, C, taps, ctx.scale)
         if ctx.needs_input_grad[1] and not _SKIP_PARAM_GRADS:
-            gW = k_wgrad(g, x, ctx.scale, tuple(W.shape), ctx.layout)
-        if gb is not None:
+            gW = k_wgrad(g, x, ctx.scale, tuple(W.shape), ctx.layout, accumulate_into=_sink(W))
+        if b_sink is not None:
+            gb = None
+        elif gb is not None:
             gb = _perm_bias(gb, ctx.layout, inverse=True)
         return gx, gW, gb, None, None, None, None
 

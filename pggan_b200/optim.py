@@ -42,6 +42,8 @@ class FlatGrads:
         self.total = off
         self.flat = torch.zeros(self.total, dtype=torch.float32, device=dev)
         self.attach()
+        if dev.type == "cuda":
+            ops.register_grad_sink(self.params)      # kernels may accumulate straight into these views
 
     def attach(self):
         for p, off in zip(self.params, self.offsets):
