@@ -151,7 +151,7 @@ def run_ours(args):
     launches_per_step = {k: c1[k] - c0[k] for k in c1}
 
     replay, graph_err = None, None
-    if args.graph and world == 1:
+    if args.graph and (world == 1 or not args.no_graph_dp):
         try:
             replay = tr.capture(batch)
         except Exception as e:          # fall back to eager launches, and say so in the JSON line
@@ -221,11 +221,14 @@ def run_ours(args):
 
     # ---- per-kernel timing of the GEMM-class launches over real steps (CUDA events on the launch stream)
     roof = None
+    # every rank runs these steps (they contain collectives); only rank 0 records the events
+    nprof = max(1, min(3, args.steps))
     if rank == 0:
         ops.PROFILE = {}
-        for _ in range(max(1, min(3, args.steps))):
-            step_eager()
-        torch.cuda.synchronize()
+    for _ in range(nprof):
+        step_eager()
+    torch.cuda.synchronize()
+    if rank == 0:
         prof, ops.PROFILE = ops.PROFILE, None
         agg = {}
         for key, evs in prof.items():
@@ -235,7 +238,6 @@ def run_ours(args):
         top_key, (top_ms, top_n) = max(agg.items(), key=lambda kv: kv[1][0])
         kind, (b_, h_, w_, c_, n_, taps_) = top_key
         flops = 2.0 * b_ * h_ * w_ * c_ * n_ * taps_
-        nprof = max(1, min(3, args.steps))
         breakdown = []
         for (kd, shp), (t_ms, n_l) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:14]:
             fl = 2.0 * shp[0] * shp[1] * shp[2] * shp[3] * shp[4] * shp[5]
@@ -252,10 +254,10 @@ def run_ours(args):
                 # algorithmic bytes are 67.1 MB in + 4.7 MB weights + 67.1 MB out, most of the output is still
                 # in L2 when the kernel ends)
                 "traffic": 94.2e6 if (kind, b_, h_, w_, c_, n_, taps_) == ("conv_gemm", 64, 32, 32, 512, 512, 9) else None,
-                "launches_per_step": top_n // max(1, min(3, args.steps)),
+                "launches_per_step": top_n // nprof,
                 "avg_launch_ms": round(top_ms / top_n, 4),
                 "share_of_gemm_time": round(top_ms / step_total, 3),
-                "gemm_ms_per_step": round(step_total / max(1, min(3, args.steps)), 3),
+                "gemm_ms_per_step": round(step_total / nprof, 3),
                 "gemm_breakdown": breakdown,
                 "whole_step_frac_of_peak": round(gflop_img * batch / (ms / args.steps * 1e-3) / 1e3 / peak_sus, 4)}
 
@@ -287,9 +289,19 @@ def run_ours(args):
         }
         print(json.dumps(out), flush=True)
     if world > 1:
+        import gc
         import torch.distributed as dist
+        sys.stdout.flush()
+        # drop the captured graph (it holds NCCL work) before leaving; destroy_process_group() after a graph
+        # that captured collectives was seen to hang, so the ranks leave through a barrier + hard exit
+        replay = None
+        tr._graph = None
+        gc.collect()
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 # ------------------------------------------------------------------------- reference / CPU arm
@@ -357,6 +369,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch eagerly instead of a CUDA graph")
+    ap.add_argument("--no-graph-dp", action="store_true", help="under data parallelism launch eagerly (default: the "
+                    "NCCL all-reduces are captured inside the CUDA graph too)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
