@@ -19,6 +19,7 @@
 #include "common.cuh"
 
 #include <atomic>
+#include <stdlib.h>
 
 namespace pg {
 
@@ -382,6 +383,10 @@ static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream) {
                 best = t;
                 bn = cands[i];
             }
+        }
+        if (const char* f = getenv("PGGAN_FORCE_BN")) {      // tuning experiments only
+            const int v = atoi(f);
+            if ((v == 32 || v == 64 || v == 128 || v == 256) && p->N % v == 0) bn = v;
         }
         switch (bn) {
             case 256: return launch_tc<T, 256>(p, stream);

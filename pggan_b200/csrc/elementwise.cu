@@ -385,57 +385,65 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ in, float* __restr
     }
 }
 
-// Fast paths for the common OIHW 3x3 maps: tile transposes through shared memory so that both the
-// fp32 parameter side and the packed side are accessed contiguously.
-// fprop: out[o][t][i] = W[o][i][t]   (i padded to Ip with zeros); grid (ceil(Ip/64), O)
+// Fast paths for the common OIHW 3x3 maps: one output channel (or a tile of them) per block, staged
+// through shared memory so both the fp32 parameter side and the packed side are accessed contiguously
+// with 16-byte transactions and enough bytes in flight per block.
+constexpr int kPackMaxI = 1024;         // fast paths handle up to 1024 (padded) input channels
+
+// fprop: out[o][t][i] = W[o][i][t]   (i padded to Ip with zeros); grid (O), dynamic smem 9*Ip floats
 template <typename T>
 __global__ void __launch_bounds__(256) pack_oihw_f_kernel(const float* __restrict__ W, T* __restrict__ out, int I, int Ip) {
-    __shared__ float tile[64 * 9];
-    const int o = blockIdx.y, i0 = blockIdx.x * 64;
-    const int ni = min(64, I - i0);                       // valid input channels in this tile (may be <= 0)
-    for (int k = threadIdx.x; k < 64 * 9; k += blockDim.x)
-        tile[k] = (k < ni * 9) ? W[(static_cast<size_t>(o) * I + i0) * 9 + k] : 0.f;
+    extern __shared__ float tile[];                        // [9][Ip]
+    const int o = blockIdx.x;
+    const float* src = W + static_cast<size_t>(o) * I * 9;
+    for (int k = threadIdx.x; k < 9 * Ip; k += blockDim.x) tile[k] = 0.f;
     __syncthreads();
-    for (int k = threadIdx.x; k < 64 * 9; k += blockDim.x) {
-        const int t = k / 64, ii = k % 64;
-        if (i0 + ii < Ip) out[(static_cast<size_t>(o) * 9 + t) * Ip + i0 + ii] = DT<T>::from_f(tile[ii * 9 + t]);
+    for (int k = threadIdx.x; k < I * 9; k += blockDim.x) {     // k = i*9 + t, contiguous in the parameter
+        const int i = k / 9, t = k - i * 9;
+        tile[t * Ip + i] = src[k];
     }
+    __syncthreads();
+    T* dst = out + static_cast<size_t>(o) * 9 * Ip;
+    for (int k = threadIdx.x; k < 9 * Ip; k += blockDim.x) dst[k] = DT<T>::from_f(tile[k]);
 }
-// gradients back: gW[o][i][t] = scale * acc[o][t][i]
+// gradients back: gW[o][i][t] (+)= scale * sum_s acc[s][o][t][i]; grid (O), dynamic smem 9*Ip floats
 __global__ void __launch_bounds__(256) unpack_oihw_kernel(const float* __restrict__ acc, float* __restrict__ gW, int I,
                                                           int Ip, float scale, int accumulate, int slices,
                                                           long long slice_elems) {
-    __shared__ float tile[64 * 9];
-    const int o = blockIdx.y, i0 = blockIdx.x * 64;
-    const int ni = min(64, I - i0);
-    for (int k = threadIdx.x; k < 64 * 9; k += blockDim.x) {
-        const int t = k / 64, ii = k % 64;
-        float v = 0.f;
-        if (ii < ni)
-            for (int sl = 0; sl < slices; ++sl) v += acc[sl * slice_elems + (static_cast<size_t>(o) * 9 + t) * Ip + i0 + ii];
-        tile[ii * 9 + t] = v;
+    extern __shared__ float tile[];                        // [9][Ip]
+    const int o = blockIdx.x;
+    const int nvec = 9 * Ip / 4;                           // Ip % 4 == 0 on this path
+    const float4* src = reinterpret_cast<const float4*>(acc + static_cast<size_t>(o) * 9 * Ip);
+    for (int k = threadIdx.x; k < nvec; k += blockDim.x) {
+        float4 v = __ldg(src + k);
+        for (int sl = 1; sl < slices; ++sl) {
+            const float4 u = __ldg(reinterpret_cast<const float4*>(acc + sl * slice_elems + static_cast<size_t>(o) * 9 * Ip) + k);
+            v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+        }
+        reinterpret_cast<float4*>(tile)[k] = v;
     }
     __syncthreads();
-    for (int k = threadIdx.x; k < ni * 9; k += blockDim.x) {
-        float* dst = gW + (static_cast<size_t>(o) * I + i0) * 9 + k;
-        const float v = tile[k] * scale;
-        *dst = accumulate ? (*dst + v) : v;
+    float* dst = gW + static_cast<size_t>(o) * I * 9;
+    for (int k = threadIdx.x; k < I * 9; k += blockDim.x) {
+        const int i = k / 9, t = k - i * 9;
+        const float v = tile[t * Ip + i] * scale;
+        dst[k] = accumulate ? (dst[k] + v) : v;
     }
 }
-// dgrad: out[i][8-t][o] = W[o][i][t]   (rows i >= I zero); grid (ceil(Np/8), O/32), O % 32 == 0
+// dgrad: out[i][8-t][o] = W[o][i][t]   (rows i >= I zero); grid (ceil(Np/8), O/64), O % 64 == 0
 template <typename T>
 __global__ void __launch_bounds__(256) pack_oihw_t_kernel(const float* __restrict__ W, T* __restrict__ out, int O, int I,
                                                           int Np) {
-    __shared__ float tile[32][73];
-    const int i0 = blockIdx.x * 8, o0 = blockIdx.y * 32;
+    __shared__ float tile[64][73];
+    const int i0 = blockIdx.x * 8, o0 = blockIdx.y * 64;
     const int ni = min(8, I - i0);
-    for (int k = threadIdx.x; k < 32 * 72; k += blockDim.x) {
+    for (int k = threadIdx.x; k < 64 * 72; k += blockDim.x) {
         const int oo = k / 72, r = k % 72;
         tile[oo][r] = (r < ni * 9) ? W[(static_cast<size_t>(o0 + oo) * I + i0) * 9 + r] : 0.f;
     }
     __syncthreads();
-    for (int k = threadIdx.x; k < 72 * 32; k += blockDim.x) {
-        const int oo = k % 32, r = k / 32;        // r = ii*9 + t'
+    for (int k = threadIdx.x; k < 72 * 64; k += blockDim.x) {
+        const int oo = k % 64, r = k / 64;        // r = ii*9 + t'
         const int ii = r / 9, tp = r % 9;
         if (i0 + ii < Np)
             out[(static_cast<size_t>(i0 + ii) * 9 + tp) * O + o0 + oo] = DT<T>::from_f(tile[oo][ii * 9 + (8 - tp)]);
@@ -664,16 +672,16 @@ extern "C" int pggan_pack_weight(const float* in, void* out, int dtype, const pg
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const long long total = (long long)m.n_total * m.taps * m.c_total;
     const bool oihw_f = m.taps == 9 && m.n2 == 1 && m.c2 == 1 && m.base == 0 && m.s_t == 1 && m.s_c1 == 9 &&
-                        m.s_n1 == 9LL * m.c_valid && m.n_valid == m.n_total;
+                        m.s_n1 == 9LL * m.c_valid && m.n_valid == m.n_total && m.c_total <= kPackMaxI;
     const bool oihw_t = m.taps == 9 && m.n2 == 1 && m.c2 == 1 && m.base == 8 && m.s_t == -1 && m.s_n1 == 9 &&
-                        m.s_c1 == 9LL * m.n_valid && m.c_valid == m.c_total && m.c_total % 32 == 0;
+                        m.s_c1 == 9LL * m.n_valid && m.c_valid == m.c_total && m.c_total % 64 == 0;
     if (oihw_f) {
         DISPATCH_T(dtype, {
-            pack_oihw_f_kernel<T><<<dim3((m.c_total + 63) / 64, m.n_total), 256, 0, s>>>(in, (T*)out, m.c_valid, m.c_total);
+            pack_oihw_f_kernel<T><<<m.n_total, 256, 9 * m.c_total * sizeof(float), s>>>(in, (T*)out, m.c_valid, m.c_total);
         });
     } else if (oihw_t) {
         DISPATCH_T(dtype, {
-            pack_oihw_t_kernel<T><<<dim3((m.n_total + 7) / 8, m.c_total / 32), 256, 0, s>>>(in, (T*)out, m.c_total, m.n_valid,
+            pack_oihw_t_kernel<T><<<dim3((m.n_total + 7) / 8, m.c_total / 64), 256, 0, s>>>(in, (T*)out, m.c_total, m.n_valid,
                                                                                           m.n_total);
         });
     } else {
@@ -693,11 +701,12 @@ extern "C" int pggan_unpack_wgrad(const float* in, float* out, const pg_pack_map
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const long long total = (long long)m.n_valid * m.taps * m.c_valid;
     const bool oihw_f = m.taps == 9 && m.n2 == 1 && m.c2 == 1 && m.base == 0 && m.s_t == 1 && m.s_c1 == 9 &&
-                        m.s_n1 == 9LL * m.c_valid && m.n_valid == m.n_total;
+                        m.s_n1 == 9LL * m.c_valid && m.n_valid == m.n_total && m.c_total <= kPackMaxI && m.c_total % 4 == 0 &&
+                        al16(in);
     const long long slice_elems = (long long)m.n_total * m.taps * m.c_total;
     if (oihw_f)
-        unpack_oihw_kernel<<<dim3((m.c_valid + 63) / 64, m.n_total), 256, 0, s>>>(in, out, m.c_valid, m.c_total, scale, accumulate,
-                                                                               slices, slice_elems);
+        unpack_oihw_kernel<<<m.n_total, 256, 9 * m.c_total * sizeof(float), s>>>(in, out, m.c_valid, m.c_total, scale, accumulate,
+                                                                              slices, slice_elems);
     else
         unpack_wgrad_kernel<<<ew_grid(total, 256), 256, 0, s>>>(in, out, m, total, scale, accumulate, slices, slice_elems);
     PG_LAUNCH_CHECK();

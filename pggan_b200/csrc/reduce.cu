@@ -76,14 +76,39 @@ __global__ void adam_kernel(const pg_adam_entry* __restrict__ table, const int32
     const int64_t off = chunk_offset[blockIdx.x];
     int64_t end = off + kAdamChunk;
     if (end > e.numel) end = e.numel;
-    for (int64_t i = off + threadIdx.x; i < end; i += blockDim.x) {
-        const float g = e.grad[i] * grad_scale;
-        const float m = beta1 * e.exp_avg[i] + (1.f - beta1) * g;
-        const float v = beta2 * e.exp_avg_sq[i] + (1.f - beta2) * g * g;
+    auto upd = [&](float& p, float g, float& m, float& v) {
+        g *= grad_scale;
+        m = beta1 * m + (1.f - beta1) * g;
+        v = beta2 * v + (1.f - beta2) * g * g;
+        const float denom = sqrtf(v) / bc2_sqrt + eps;
+        p = p - step_size * (m / denom);
+    };
+    const bool vec = ((reinterpret_cast<uintptr_t>(e.param) | reinterpret_cast<uintptr_t>(e.grad) |
+                       reinterpret_cast<uintptr_t>(e.exp_avg) | reinterpret_cast<uintptr_t>(e.exp_avg_sq)) & 15) == 0;
+    int64_t i0 = off;
+    if (vec) {                                        // chunk offsets are multiples of 4 elements
+        const int64_t vend = off + ((end - off) & ~int64_t(3));
+        for (int64_t i = off + 4 * threadIdx.x; i < vend; i += 4 * blockDim.x) {
+            float4 p = *reinterpret_cast<float4*>(e.param + i);
+            const float4 g = __ldg(reinterpret_cast<const float4*>(e.grad + i));
+            float4 m = *reinterpret_cast<float4*>(e.exp_avg + i);
+            float4 v = *reinterpret_cast<float4*>(e.exp_avg_sq + i);
+            upd(p.x, g.x, m.x, v.x);
+            upd(p.y, g.y, m.y, v.y);
+            upd(p.z, g.z, m.z, v.z);
+            upd(p.w, g.w, m.w, v.w);
+            *reinterpret_cast<float4*>(e.param + i) = p;
+            *reinterpret_cast<float4*>(e.exp_avg + i) = m;
+            *reinterpret_cast<float4*>(e.exp_avg_sq + i) = v;
+        }
+        i0 = vend;
+    }
+    for (int64_t i = i0 + threadIdx.x; i < end; i += blockDim.x) {
+        float p = e.param[i], m = e.exp_avg[i], v = e.exp_avg_sq[i];
+        upd(p, e.grad[i], m, v);
+        e.param[i] = p;
         e.exp_avg[i] = m;
         e.exp_avg_sq[i] = v;
-        const float denom = sqrtf(v) / bc2_sqrt + eps;
-        e.param[i] = e.param[i] - step_size * (m / denom);
     }
 }
 __global__ void adam_incr_step_kernel(int64_t* step) { *step += 1; }

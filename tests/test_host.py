@@ -116,3 +116,43 @@ def test_weight_layout_maps():
     Wl = W.view(O, Cc, S).transpose(1, 2).reshape(O, S * Cc)
     assert torch.equal(_emulate_pack(W, fm)[:, 0, :], Wl)
     assert torch.equal(_emulate_pack(W, tm)[:, 0, :], Wl.t())
+
+
+def test_reference_import_paths_resolve_to_this_package():
+    import importlib
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "pggan_b200", "compat"))
+    try:
+        for m in ("lib", "lib.layers", "pggan", "pggan.nets"):
+            sys.modules.pop(m, None)
+        layers = importlib.import_module("lib.layers")
+        nets = importlib.import_module("pggan.nets")
+        import pggan_b200
+        assert layers.EqualizedConv2d is pggan_b200.EqualizedConv2d
+        assert nets.Generator is pggan_b200.Generator
+        assert importlib.import_module("lib.custom_layers").EqualizedLinear is not None
+        assert importlib.import_module("pggan.loss").WGANGPLoss is pggan_b200.WGANGPLoss
+    finally:
+        sys.path.pop(0)
+        for m in [k for k in sys.modules if k == "lib" or k.startswith("lib.") or k == "pggan" or k.startswith("pggan.")]:
+            sys.modules.pop(m, None)
+
+
+def test_checkpoint_roundtrip_reference_format(tmp_path):
+    import types
+    import pggan_b200 as pg
+    from pggan_b200 import checkpoint
+    G = pg.Generator(32, 32)
+    G.add_block(32)
+    args = types.SimpleNamespace(save_root=str(tmp_path), run_id="run0", ckpt_id="run0")
+    opt = torch.optim.Adam(G.parameters(), lr=1e-4, betas=(0.0, 0.99))
+    checkpoint.save_checkpoint(args, G, opt, "G", 7, extra={"scale_index": 1, "alpha_G": 0.25})
+    G2 = pg.Generator(32, 32)
+    D2 = pg.Discriminator(32, apply_minibatch_norm=True)
+    checkpoint.grow_to_checkpoint(G2, D2, [32, 32], 1)
+    ck = checkpoint.load_checkpoint(args, G2, None, "G", 7)
+    assert ck["scale_index"] == 1 and ck["global_step"] == 7
+    for (k1, v1), (k2, v2) in zip(G.state_dict().items(), G2.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1, v2)
