@@ -264,7 +264,7 @@ def run_ours(args):
     # ---- CPU baseline: the oracle restatement of the reference step on the host cores (bounded sample)
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(args.workload, args.variant, sample_batch=args.cpu_sample, steps=1)
+        cpu = cpu_baseline(args.workload, args.variant, sample_batch=args.cpu_sample, steps=2)
 
     if rank == 0:
         n_img = batch * world * args.steps
@@ -366,7 +366,7 @@ def main():
     ap.add_argument("--variant", default="W", choices=["W", "L"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=0)
-    ap.add_argument("--cpu-sample", type=int, default=32)
+    ap.add_argument("--cpu-sample", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch eagerly instead of a CUDA graph")
     ap.add_argument("--no-graph-dp", action="store_true", help="under data parallelism launch eagerly (default: the "

@@ -390,44 +390,56 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ in, float* __restr
 // with 16-byte transactions and enough bytes in flight per block.
 constexpr int kPackMaxI = 1024;         // fast paths handle up to 1024 (padded) input channels
 
-// fprop: out[o][t][i] = W[o][i][t]   (i padded to Ip with zeros); grid (O), dynamic smem 9*Ip floats
+// fprop: out[o][t][i] = W[o][i][t]   (i padded to Ip with zeros); grid (O), dynamic smem 9*I floats.
+// The parameter row is copied linearly (stride-9 reads from the tile are bank-conflict free: 9 is odd).
 template <typename T>
 __global__ void __launch_bounds__(256) pack_oihw_f_kernel(const float* __restrict__ W, T* __restrict__ out, int I, int Ip) {
-    extern __shared__ float tile[];                        // [9][Ip]
+    extern __shared__ float tile[];                        // [I][9] exactly as in the parameter
     const int o = blockIdx.x;
     const float* src = W + static_cast<size_t>(o) * I * 9;
-    for (int k = threadIdx.x; k < 9 * Ip; k += blockDim.x) tile[k] = 0.f;
-    __syncthreads();
-    for (int k = threadIdx.x; k < I * 9; k += blockDim.x) {     // k = i*9 + t, contiguous in the parameter
-        const int i = k / 9, t = k - i * 9;
-        tile[t * Ip + i] = src[k];
+    const int n = I * 9;
+    if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        for (int k = threadIdx.x; k < n / 4; k += blockDim.x)
+            reinterpret_cast<float4*>(tile)[k] = __ldg(reinterpret_cast<const float4*>(src) + k);
+    } else {
+        for (int k = threadIdx.x; k < n; k += blockDim.x) tile[k] = src[k];
     }
     __syncthreads();
     T* dst = out + static_cast<size_t>(o) * 9 * Ip;
-    for (int k = threadIdx.x; k < 9 * Ip; k += blockDim.x) dst[k] = DT<T>::from_f(tile[k]);
+    for (int k = threadIdx.x; k < 9 * Ip; k += blockDim.x) {
+        const int t = k / Ip, i = k - t * Ip;
+        dst[k] = DT<T>::from_f(i < I ? tile[i * 9 + t] : 0.f);
+    }
 }
-// gradients back: gW[o][i][t] (+)= scale * sum_s acc[s][o][t][i]; grid (O), dynamic smem 9*Ip floats
+// gradients back: gW[o][i][t] (+)= scale * sum_s acc[s][o][t][i]; grid (O), dynamic smem 9*I floats
 __global__ void __launch_bounds__(256) unpack_oihw_kernel(const float* __restrict__ acc, float* __restrict__ gW, int I,
                                                           int Ip, float scale, int accumulate, int slices,
                                                           long long slice_elems) {
-    extern __shared__ float tile[];                        // [9][Ip]
+    extern __shared__ float tile[];                        // [I][9]
     const int o = blockIdx.x;
-    const int nvec = 9 * Ip / 4;                           // Ip % 4 == 0 on this path
-    const float4* src = reinterpret_cast<const float4*>(acc + static_cast<size_t>(o) * 9 * Ip);
-    for (int k = threadIdx.x; k < nvec; k += blockDim.x) {
-        float4 v = __ldg(src + k);
-        for (int sl = 1; sl < slices; ++sl) {
-            const float4 u = __ldg(reinterpret_cast<const float4*>(acc + sl * slice_elems + static_cast<size_t>(o) * 9 * Ip) + k);
-            v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+    const float* src = acc + static_cast<size_t>(o) * 9 * Ip;
+    for (int k = threadIdx.x; k < 9 * Ip; k += blockDim.x) {
+        const int t = k / Ip, i = k - t * Ip;
+        if (i < I) {
+            float v = __ldg(src + k);
+            for (int sl = 1; sl < slices; ++sl) v += __ldg(src + sl * slice_elems + k);
+            tile[i * 9 + t] = v * scale;
         }
-        reinterpret_cast<float4*>(tile)[k] = v;
     }
     __syncthreads();
     float* dst = gW + static_cast<size_t>(o) * I * 9;
-    for (int k = threadIdx.x; k < I * 9; k += blockDim.x) {
-        const int i = k / 9, t = k - i * 9;
-        const float v = tile[t * Ip + i] * scale;
-        dst[k] = accumulate ? (dst[k] + v) : v;
+    const int n = I * 9;
+    if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        for (int k = threadIdx.x; k < n / 4; k += blockDim.x) {
+            float4 v = reinterpret_cast<const float4*>(tile)[k];
+            if (accumulate) {
+                const float4 u = reinterpret_cast<const float4*>(dst)[k];
+                v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+            }
+            reinterpret_cast<float4*>(dst)[k] = v;
+        }
+    } else {
+        for (int k = threadIdx.x; k < n; k += blockDim.x) dst[k] = accumulate ? (dst[k] + tile[k]) : tile[k];
     }
 }
 // dgrad: out[i][8-t][o] = W[o][i][t]   (rows i >= I zero); grid (ceil(Np/8), O/64), O % 64 == 0
@@ -677,7 +689,7 @@ extern "C" int pggan_pack_weight(const float* in, void* out, int dtype, const pg
                         m.s_c1 == 9LL * m.n_valid && m.c_valid == m.c_total && m.c_total % 64 == 0;
     if (oihw_f) {
         DISPATCH_T(dtype, {
-            pack_oihw_f_kernel<T><<<m.n_total, 256, 9 * m.c_total * sizeof(float), s>>>(in, (T*)out, m.c_valid, m.c_total);
+            pack_oihw_f_kernel<T><<<m.n_total, 256, 9 * m.c_valid * sizeof(float), s>>>(in, (T*)out, m.c_valid, m.c_total);
         });
     } else if (oihw_t) {
         DISPATCH_T(dtype, {
@@ -701,11 +713,10 @@ extern "C" int pggan_unpack_wgrad(const float* in, float* out, const pg_pack_map
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const long long total = (long long)m.n_valid * m.taps * m.c_valid;
     const bool oihw_f = m.taps == 9 && m.n2 == 1 && m.c2 == 1 && m.base == 0 && m.s_t == 1 && m.s_c1 == 9 &&
-                        m.s_n1 == 9LL * m.c_valid && m.n_valid == m.n_total && m.c_total <= kPackMaxI && m.c_total % 4 == 0 &&
-                        al16(in);
+                        m.s_n1 == 9LL * m.c_valid && m.n_valid == m.n_total && m.c_total <= kPackMaxI;
     const long long slice_elems = (long long)m.n_total * m.taps * m.c_total;
     if (oihw_f)
-        unpack_oihw_kernel<<<m.n_total, 256, 9 * m.c_total * sizeof(float), s>>>(in, out, m.c_valid, m.c_total, scale, accumulate,
+        unpack_oihw_kernel<<<m.n_total, 256, 9 * m.c_valid * sizeof(float), s>>>(in, out, m.c_valid, m.c_total, scale, accumulate,
                                                                               slices, slice_elems);
     else
         unpack_wgrad_kernel<<<ew_grid(total, 256), 256, 0, s>>>(in, out, m, total, scale, accumulate, slices, slice_elems);
