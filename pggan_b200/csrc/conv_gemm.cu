@@ -250,6 +250,210 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     }
 }
 
+// ------------------------------------------------------------------- swapped orientation (N <= 128)
+// tcgen05.mma reads its A operand from shared memory at a fixed ~128 cycles per instruction (M = 128
+// rows x 32 B), which only the N = 256 shape hides: with pixels on M, a layer with 64 / 128 output
+// channels runs the tensor pipe at 25 % / 50 %.  For those layers the roles are swapped:
+//   D[128 output channels x 256 pixels] += A[128 weight rows x 128 B of K] * B[256 pixels x 128 B of K]^T
+// (A = packed weights, rows beyond N zero-filled by TMA; B = one 256-pixel TMA box, shifted per tap).
+// The accumulator is channel-major (TMEM lane = channel), so the epilogue transposes 32-pixel slabs
+// through shared memory and writes NHWC rows with coalesced 16-byte stores.
+constexpr int kSwPix = 256;
+constexpr int kSwABytes = 128 * 128;
+constexpr int kSwBBytes = kSwPix * 128;
+constexpr int kSwStageBytes = kSwABytes + kSwBBytes;
+constexpr int kSwStages = 4;
+constexpr int kSwStagingBytes = 32 * 128 * 4;     // 32 pixels x 128 channels x fp32
+constexpr int kSwSmemBytes = kSwStages * kSwStageBytes + kSwStagingBytes + 1024 + 256;
+
+template <typename T>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_gemm_swapped_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                         const ConvKArgs a) {
+    constexpr bool kTF32 = (sizeof(T) == 4);
+    constexpr int BK = 128 / sizeof(T);
+    constexpr int kStages = kSwStages;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* staging = smem + kStages * kSwStageBytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kSwStagingBytes);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tfull_bar = empty_bar + kStages;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_x);
+        tma_prefetch_desc(&tmap_w);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], 128);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int num_m_tiles = a.tiles_w * a.tiles_h * a.tiles_b;      // pixel tiles (256 pixels each)
+    const int num_tiles = num_m_tiles * a.tiles_n;                  // x channel tiles (128 channels each)
+    const int num_kc = a.taps * a.kc_per_tap;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int nt = tile % a.tiles_n;
+                const int mt = tile / a.tiles_n;
+                const int w0 = (mt % a.tiles_w) * a.BW;
+                const int h0 = ((mt / a.tiles_w) % a.tiles_h) * a.BH;
+                const int b0 = (mt / (a.tiles_w * a.tiles_h)) * a.BB;
+                for (int kc = 0; kc < num_kc; ++kc) {
+                    const int tap = kc / a.kc_per_tap;
+                    const int cc = kc - tap * a.kc_per_tap;
+                    int dh = 0, dw = 0;
+                    if (a.taps == 9) {
+                        dh = tap / 3 - 1;
+                        dw = tap % 3 - 1;
+                    }
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * kSwStageBytes;
+                    mbar_arrive_expect_tx(&full_bar[stage], kSwStageBytes);
+                    tma_load_2d(sa, &tmap_w, &full_bar[stage], kc * BK, nt * 128);
+                    tma_load_4d(sa + kSwABytes, &tmap_x, &full_bar[stage], cc * BK, w0 + dw, h0 + dh, b0);
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(kTF32 ? 2 : 1, 0, 0, 128, kSwPix);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * kSwPix;
+                for (int kc = 0; kc < num_kc; ++kc) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * kSwStageBytes);
+                    const uint64_t adesc = make_smem_desc(sa, 16, 1024);
+                    const uint64_t bdesc = make_smem_desc(sa + kSwABytes, 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_ss<kTF32>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) != 0);
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(&tfull_bar[acc]);
+            }
+        }
+    } else {
+        // epilogue: thread = one output channel (TMEM lane); 8 slabs of 32 pixels per tile
+        const int q = warp & 3;
+        const int cl = q * 32 + lane;                       // channel within the 128-channel tile
+        const int et = threadIdx.x - 64;                    // 0..127 among the epilogue threads
+        const int osz = (a.out_dtype == PG_BF16) ? 2 : 4;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const int nt = tile % a.tiles_n;
+            const int mt = tile / a.tiles_n;
+            const int w0 = (mt % a.tiles_w) * a.BW;
+            const int h0 = ((mt / a.tiles_w) % a.tiles_h) * a.BH;
+            const int b0 = (mt / (a.tiles_w * a.tiles_h)) * a.BB;
+            const int n0 = nt * 128;
+            const int cvalid = (a.N - n0) < 128 ? (a.N - n0) : 128;
+            const float bias = (a.bias != nullptr && cl < cvalid) ? __ldg(a.bias + n0 + cl) : 0.f;
+            const int row_bytes = cvalid * osz;             // one pixel's channel slice in the output
+            const int vec_per_row = row_bytes / 16;
+
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kSwPix;
+#pragma unroll 1
+            for (int j = 0; j < kSwPix / 32; ++j) {
+                __syncwarp();
+                uint32_t r[32];
+                tmem_ld32(taddr + j * 32, r);
+                tmem_ld_wait();
+                // transpose through smem: staging[pixel p][channel cl]
+                if (cl < cvalid) {
+                    if (osz == 2) {
+                        __nv_bfloat16* st = reinterpret_cast<__nv_bfloat16*>(staging);
+#pragma unroll
+                        for (int p = 0; p < 32; ++p)
+                            st[p * cvalid + cl] = __float2bfloat16_rn(lrelu_f((__uint_as_float(r[p]) + bias) * a.scale, a.slope));
+                    } else {
+                        float* st = reinterpret_cast<float*>(staging);
+#pragma unroll
+                        for (int p = 0; p < 32; ++p)
+                            st[p * cvalid + cl] = lrelu_f((__uint_as_float(r[p]) + bias) * a.scale, a.slope);
+                    }
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                // coalesced store of the 32 x cvalid slab (+ optional LeakyReLU mask of the saved activation)
+                for (int v = et; v < 32 * vec_per_row; v += 128) {
+                    const int p = v / vec_per_row, vv = v - p * vec_per_row;
+                    const int row = j * 32 + p;
+                    const int wo = row % a.BW;
+                    const int ho = (row / a.BW) % a.BH;
+                    const int b = b0 + row / (a.BW * a.BH);
+                    if (b >= a.B) continue;
+                    const size_t pix = (static_cast<size_t>(b) * a.H + (h0 + ho)) * a.W + (w0 + wo);
+                    uint4 val = *reinterpret_cast<const uint4*>(staging + static_cast<size_t>(p) * row_bytes + vv * 16);
+                    if (a.mask_src != nullptr) {
+                        constexpr int VN = 16 / sizeof(T);
+                        const uint4 mraw = __ldg(reinterpret_cast<const uint4*>(
+                            reinterpret_cast<const T*>(a.mask_src) + pix * a.N + n0) + vv * (16 / osz) / VN);
+                        // mask_src has the operand dtype T; out has osz bytes/elem: only the T == out case is used
+                        if (osz == static_cast<int>(sizeof(T))) {
+                            T* ov = reinterpret_cast<T*>(&val);
+                            const T* mv = reinterpret_cast<const T*>(&mraw);
+#pragma unroll
+                            for (int e = 0; e < VN; ++e)
+                                if (!(DT<T>::to_f(mv[e]) > 0.f)) ov[e] = DT<T>::from_f(DT<T>::to_f(ov[e]) * a.mask_slope);
+                        }
+                    }
+                    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(a.y) + (pix * a.N + n0) * osz + vv * 16) = val;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
 // ------------------------------------------------------------------------- SIMT direct kernel
 // One thread per (pixel, 4 consecutive n); any shape.  Bring-up cross-check and the path for
 // shapes the tensor-core kernel does not take (C*elsize % 128 != 0, non power-of-two H/W).
@@ -339,6 +543,56 @@ static int launch_tc(const pg_conv_params* p, cudaStream_t stream) {
 }
 
 template <typename T>
+static int launch_swapped(const pg_conv_params* p, cudaStream_t stream) {
+    constexpr int BK = 128 / sizeof(T);
+    ConvKArgs a;
+    a.bias = p->bias;
+    a.mask_src = p->mask_src;
+    a.y = p->y;
+    a.B = p->B; a.H = p->H; a.W = p->W; a.N = p->N;
+    a.BW = p->W < kSwPix ? p->W : kSwPix;
+    a.BH = p->H < (kSwPix / a.BW) ? p->H : (kSwPix / a.BW);
+    a.BB = kSwPix / (a.BW * a.BH);
+    a.tiles_w = p->W / a.BW;
+    a.tiles_h = p->H / a.BH;
+    a.tiles_b = (p->B + a.BB - 1) / a.BB;
+    a.tiles_n = (p->N + 127) / 128;
+    a.kc_per_tap = p->C / BK;
+    a.taps = p->taps;
+    a.out_dtype = p->out_dtype;
+    a.scale = p->scale; a.slope = p->slope; a.mask_slope = p->mask_slope;
+    const uint64_t es = sizeof(T);
+    CUtensorMap tx, tw;
+    {
+        uint64_t dims[4] = {(uint64_t)p->C, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
+        uint64_t strides[3] = {(uint64_t)p->C * es, (uint64_t)p->W * p->C * es, (uint64_t)p->H * p->W * p->C * es};
+        uint32_t box[4] = {(uint32_t)BK, (uint32_t)a.BW, (uint32_t)a.BH, (uint32_t)a.BB};
+        int rc = encode_tmap(&tx, DT<T>::kEnum, 4, p->x, dims, strides, box, 128);
+        if (rc != PG_OK) return rc;
+    }
+    {
+        const uint64_t K = (uint64_t)p->taps * p->C;
+        uint64_t dims[2] = {K, (uint64_t)p->N};
+        uint64_t strides[1] = {K * es};
+        uint32_t box[2] = {(uint32_t)BK, 128u};
+        int rc = encode_tmap(&tw, DT<T>::kEnum, 2, p->wp, dims, strides, box, 128);
+        if (rc != PG_OK) return rc;
+    }
+    auto kern = conv_gemm_swapped_kernel<T>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSwSmemBytes));
+        attr_done = true;
+    }
+    const int num_tiles = a.tiles_w * a.tiles_h * a.tiles_b * a.tiles_n;
+    const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+    kern<<<grid, kConvThreads, kSwSmemBytes, stream>>>(tx, tw, a);
+    PG_LAUNCH_CHECK();
+    g_tc_launches++;
+    return PG_OK;
+}
+
+template <typename T>
 static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream) {
     constexpr int BK = 128 / sizeof(T);
     constexpr bool kF32 = sizeof(T) == 4;
@@ -363,6 +617,14 @@ static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream) {
             local.wp = p->ws_w;
             local.C = Ceff;
         }
+        // few output channels: swapped orientation (channels on M, 256 pixels on N) keeps the tensor pipe fed
+        const int osz = (p->out_dtype == PG_BF16) ? 2 : 4;
+        const bool mask_ok = p->mask_src == nullptr || osz == (int)sizeof(T);
+        static const bool no_swap = getenv("PGGAN_NO_SWAP") != nullptr;
+        // (its transposing epilogue costs a fixed ~5k cycles per 128x256 tile: only worth it when K is long enough)
+        if (!no_swap && p->N <= 128 && (long long)p->C * p->taps >= 1152 && (p->N * osz) % 16 == 0 && mask_ok &&
+            (long long)p->B * p->H * p->W >= 2 * kSwPix)
+            return launch_swapped<T>(p, stream);
         // largest N tile that still yields enough CTAs to occupy the machine
         const int bw = p->W < 128 ? p->W : 128;
         const int bh = p->H < (128 / bw) ? p->H : (128 / bw);

@@ -48,6 +48,9 @@ struct WgKArgs {
     int chunks_w, chunks_h, chunks_b;
     int tiles_n, tiles_c, splits, chunks_per_split;
     int span5d;                     // 1: tensor maps are 5-D (channel spans are the 5th dim): one TMA box per operand
+    int tpu;                        // taps per unit: C < BLOCK_C layers stack tpu = BLOCK_C/C shifted x tiles side by
+                                    // side along the MMA N dimension (one g tile feeds several taps at full N = 256)
+    int tap_groups;                 // ceil(taps / tpu)
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -93,7 +96,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
     const uint32_t tmem_base = *tmem_slot;
 
     const int total_chunks = a.chunks_w * a.chunks_h * a.chunks_b;
-    const int num_units = a.taps * a.tiles_n * a.tiles_c * a.splits;
+    const int num_units = a.tap_groups * a.tiles_n * a.tiles_c * a.splits;
 
     // unit -> (split, tap, n tile, c tile); c fastest so neighbouring CTAs share the g tile in L2
     auto decode = [&](int unit, int& ct, int& nt, int& tap, int& k0, int& k1, int& sp) {
@@ -101,8 +104,8 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
         unit /= a.tiles_c;
         nt = unit % a.tiles_n;
         unit /= a.tiles_n;
-        tap = unit % a.taps;
-        sp = unit / a.taps;
+        tap = unit % a.tap_groups;          // tap group (== tap when tpu == 1)
+        sp = unit / a.tap_groups;
         k0 = sp * a.chunks_per_split;
         k1 = k0 + a.chunks_per_split;
         if (k1 > total_chunks) k1 = total_chunks;
@@ -116,7 +119,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
                 int ct, nt, tap, k0, k1, sp;
                 decode(unit, ct, nt, tap, k0, k1, sp);
                 int dh = 0, dw = 0;
-                if (a.taps == 9) {
+                if (a.taps == 9 && a.tpu == 1) {
                     dh = tap / 3 - 1;
                     dw = tap % 3 - 1;
                 }
@@ -128,7 +131,19 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
                     uint8_t* sa = smem + stage * Cfg::kStageBytes;
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
                     uint8_t* sb = sa + Cfg::GA * Cfg::kGroupBytes;
-                    if (a.span5d) {
+                    if (a.span5d && a.tpu > 1) {
+                        // tap stacking: tpu shifted x boxes (each all C channels = GB/tpu spans) fill the N = BLOCK_C tile
+                        tma_load_5d(sa, &tmap_g, &full_bar[stage], 0, w0, h0, b0, nt * Cfg::GA);
+                        const int spans = Cfg::GB / a.tpu;
+                        for (int j = 0; j < a.tpu; ++j) {
+                            const int t = tap * a.tpu + j;
+                            // taps past the filter (last group) are loaded fully out of bounds: zero fill
+                            const int bb = (t < a.taps) ? b0 : (a.B + a.PB);
+                            const int tdh = (a.taps == 9 && t < a.taps) ? t / 3 - 1 : 0;
+                            const int tdw = (a.taps == 9 && t < a.taps) ? t % 3 - 1 : 0;
+                            tma_load_5d(sb + j * spans * Cfg::kGroupBytes, &tmap_x, &full_bar[stage], 0, w0 + tdw, h0 + tdh, bb, 0);
+                        }
+                    } else if (a.span5d) {
                         // one box per operand: the channel spans are the outermost box dimension, so the box lands
                         // span-major ([span][pixel][128 B]) — the same smem image as the per-span loads below, with
                         // 2 TMA instructions per stage instead of GA+GB (the single producer thread was issue-bound)
@@ -199,7 +214,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
             const uint32_t acc_phase = (it >> 1) & 1;
             const int n = nt * 128 + row;
             const bool valid = (n < a.N) && (k1 > k0);
-            float* dst = a.acc + sp * a.slice_elems + (static_cast<size_t>(n) * a.taps + tap) * a.C + ct * BLOCK_C;
+            float* slice = a.acc + sp * a.slice_elems;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_C;
@@ -209,10 +224,17 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
                 uint32_t r[32];
                 tmem_ld32(taddr + j * 32, r);
                 tmem_ld_wait();
-                if (valid) {     // every (split, tap, n, c) element is owned by exactly one unit: plain stores
+                // accumulator column -> (tap, input channel): stacked taps own C consecutive columns each
+                int t = tap, c0 = ct * BLOCK_C + j * 32;
+                if (a.tpu > 1) {
+                    t = tap * a.tpu + (j * 32) / a.C;
+                    c0 = (j * 32) % a.C;
+                }
+                if (valid && t < a.taps) {     // every (split, tap, n, c) element is owned by exactly one unit: plain stores
+                    float* dst = slice + (static_cast<size_t>(n) * a.taps + t) * a.C + c0;
 #pragma unroll
                     for (int c = 0; c < 8; ++c)
-                        *reinterpret_cast<float4*>(dst + j * 32 + c * 4) =
+                        *reinterpret_cast<float4*>(dst + c * 4) =
                             make_float4(__uint_as_float(r[c * 4 + 0]), __uint_as_float(r[c * 4 + 1]),
                                         __uint_as_float(r[c * 4 + 2]), __uint_as_float(r[c * 4 + 3]));
                 }
@@ -283,14 +305,21 @@ static void plan_wg(const pg_wgrad_params* p, WgKArgs& a) {
     a.chunks_h = p->H / a.PH;
     a.chunks_b = (p->B + a.PB - 1) / a.PB;
     a.tiles_n = (p->N + 127) / 128;
-    a.tiles_c = p->C / BLOCK_C;
+    a.tpu = 1;
+    if (p->C < BLOCK_C && BLOCK_C % p->C == 0 && p->C % Cfg::CPS == 0 && p->N % Cfg::CPS == 0) a.tpu = BLOCK_C / p->C;
+    if (a.tpu > p->taps) a.tpu = p->taps;
+    a.tap_groups = (p->taps + a.tpu - 1) / a.tpu;
+    a.tiles_c = a.tpu > 1 ? 1 : p->C / BLOCK_C;
     const int total_chunks = a.chunks_w * a.chunks_h * a.chunks_b;
-    const int base_units = a.taps * a.tiles_n * a.tiles_c;
+    const int base_units = a.tap_groups * a.tiles_n * a.tiles_c;
     // split-K over pixels: pick the split count whose unit count fills whole waves of SMs best
     // (fewest slices among equally good fills), keeping >= 8 chunks per unit
     int max_splits = total_chunks / 8;
     if (max_splits < 1) max_splits = 1;
-    if (max_splits > 8) max_splits = 8;
+    if (max_splits > 128) max_splits = 128;
+    // every split writes its own fp32 slice: keep the slices within 64 MB
+    const long long slice_bytes = a.slice_elems * 4;
+    while (max_splits > 1 && (long long)max_splits * slice_bytes > (64LL << 20)) --max_splits;
     int splits = 1;
     double best = -1.0;
     const int sms = num_sms();
@@ -312,7 +341,7 @@ static int launch_wg(const pg_wgrad_params* p, cudaStream_t stream) {
     using Cfg = WgCfg<T, BLOCK_C>;
     WgKArgs a;
     plan_wg<T, BLOCK_C>(p, a);
-    const int base_units = a.taps * a.tiles_n * a.tiles_c;
+    const int base_units = a.tap_groups * a.tiles_n * a.tiles_c;
     const uint64_t es = sizeof(T);
     CUtensorMap tg, tx;
     const int sw = sizeof(T) == 4 ? 12832 : 128;
@@ -330,7 +359,8 @@ static int launch_wg(const pg_wgrad_params* p, cudaStream_t stream) {
         {
             uint64_t dims[5] = {(uint64_t)Cfg::CPS, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B, (uint64_t)(p->C / Cfg::CPS)};
             uint64_t strides[4] = {(uint64_t)p->C * es, (uint64_t)p->W * p->C * es, (uint64_t)p->H * p->W * p->C * es, span_bytes};
-            uint32_t box[5] = {(uint32_t)Cfg::CPS, (uint32_t)a.PW, (uint32_t)a.PH, (uint32_t)a.PB, (uint32_t)Cfg::GB};
+            uint32_t box[5] = {(uint32_t)Cfg::CPS, (uint32_t)a.PW, (uint32_t)a.PH, (uint32_t)a.PB,
+                               (uint32_t)(a.tpu > 1 ? Cfg::GB / a.tpu : Cfg::GB)};
             int rc = encode_tmap(&tx, DT<T>::kEnum, 5, p->x, dims, strides, box, sw);
             if (rc != PG_OK) return rc;
         }
@@ -383,7 +413,8 @@ static int wgrad_dispatch(const pg_wgrad_params* p_in, cudaStream_t stream, int*
                        (reinterpret_cast<uintptr_t>(p->x) % 16 == 0) && (reinterpret_cast<uintptr_t>(p->acc) % 16 == 0);
     if (tc_ok && slices_out) {
         if (kF32) local.B = 3 * p->B;
-        if (p->C % 256 == 0) *slices_out = slices_wg<T, 256>(p);
+        const bool stack = p->taps > 1 && p->C < 256 && 256 % p->C == 0 && p->C % CPS == 0 && p->N % CPS == 0;
+        if (p->C % 256 == 0 || stack) *slices_out = slices_wg<T, 256>(p);
         else if (p->C % 128 == 0) *slices_out = slices_wg<T, 128>(p);
         else if (p->C % 64 == 0) *slices_out = slices_wg<T, 64>(p);
         else *slices_out = slices_wg<T, 32>(p);
@@ -405,7 +436,8 @@ static int wgrad_dispatch(const pg_wgrad_params* p_in, cudaStream_t stream, int*
             local.x = p->ws_x;
             local.B = 3 * p->B;
         }
-        if (p->C % 256 == 0) return launch_wg<T, 256>(p, stream);
+        const bool stack = p->taps > 1 && p->C < 256 && 256 % p->C == 0 && p->C % CPS == 0 && p->N % CPS == 0;
+        if (p->C % 256 == 0 || stack) return launch_wg<T, 256>(p, stream);
         if (p->C % 128 == 0) return launch_wg<T, 128>(p, stream);
         if (p->C % 64 == 0) return launch_wg<T, 64>(p, stream);
         if constexpr (sizeof(T) == 4) {

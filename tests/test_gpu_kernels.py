@@ -49,6 +49,10 @@ CONV_SHAPES = [
     (5, 1, 1, 512, 8192, 1),       # latent linear
     (64, 1, 1, 8192, 512, 1),      # D linear
     (2, 16, 16, 256, 32, 9),       # N tile 32
+    (4, 32, 32, 128, 64, 9),       # swapped orientation (N <= 128): 64 output channels, wgrad stacks 2 taps
+    (3, 16, 16, 64, 128, 9),       # swapped, ragged batch; wgrad stacks 4 taps of the 64-channel input
+    (2, 64, 64, 64, 64, 9),        # the 256^2-stage layer shape (64 -> 64)
+    (9, 8, 8, 64, 128, 9),         # swapped with a partially filled 256-pixel box in the batch dimension
 ]
 
 

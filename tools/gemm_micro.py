@@ -13,6 +13,9 @@ pg.set_compute_dtype(torch.bfloat16)
 dev = "cuda"
 SHAPES = [(64, 32, 32, 512, 512), (128, 32, 32, 512, 512), (64, 16, 16, 512, 512), (64, 8, 8, 512, 512),
           (128, 8, 8, 512, 512), (64, 4, 4, 512, 512)]
+if len(sys.argv) > 2 and sys.argv[2] == "c4":       # the 128^2 / 256^2 stage layer shapes (B, H, W, Cin, Cout)
+    SHAPES = [(16, 256, 256, 64, 64), (16, 256, 256, 128, 64), (16, 256, 256, 64, 128), (16, 128, 128, 128, 128),
+              (16, 128, 128, 256, 128), (16, 128, 128, 128, 256), (16, 64, 64, 256, 256)]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 for (B, H, W, C, N) in SHAPES:
     x = torch.randn(B, C, H, W, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
