@@ -38,6 +38,8 @@ WORKLOADS = {
     "c2_32x32_b64_fade": (3, 64, [512, 512, 512, 512], 229.9),
     "c3_128x128_b32": (5, 32, [512, 512, 512, 512, 256, 128], 752.0),
     "c4_256x256_b16": (6, 16, [512, 512, 512, 512, 256, 128, 64], 1013.2),
+    # paper CelebA-HQ widths
+    "c5_1024x1024_b4": (8, 4, [512, 512, 512, 512, 256, 128, 64, 32, 16], 1537.0),
 }
 METRIC = "train imgs/sec (D+G step incl. WGAN-GP)"
 

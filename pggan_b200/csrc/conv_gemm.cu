@@ -27,13 +27,16 @@ extern std::atomic<long long> g_tc_launches, g_simt_launches;
 extern int g_conv_backend;
 
 constexpr int kBlockM = 128;
-constexpr int kABytes = kBlockM * 128;   // one A stage: 128 rows x 128 B
 constexpr int kConvThreads = 192;
 
-template <int BLOCK_N> struct ConvCfg {
-    static constexpr int kBBytes = BLOCK_N * 128;
-    static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8);
+// SPAN = bytes of K per chunk = the TMA/UMMA swizzle span: 128 normally; 64 / 32 for layers whose channel
+// count times element size is only 64 / 32 bytes (the 32- and 16-channel stages of the 1024^2 network)
+template <int BLOCK_N, int SPAN = 128> struct ConvCfg {
+    static constexpr int kABytesS = kBlockM * SPAN;
+    static constexpr int kBBytes = BLOCK_N * SPAN;
+    static constexpr int kStageBytes = kABytesS + kBBytes;
+    static constexpr int kStagesRaw = 196608 / kStageBytes;
+    static constexpr int kStages = SPAN == 128 ? ((BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8)) : (kStagesRaw > 8 ? 8 : kStagesRaw);
     static constexpr int kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
@@ -50,15 +53,18 @@ struct ConvKArgs {
     float scale, slope, mask_slope;
 };
 
-template <typename T, int BLOCK_N>
+template <typename T, int BLOCK_N, int SPAN = 128>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                  const ConvKArgs a) {
-    using Cfg = ConvCfg<BLOCK_N>;
+    using Cfg = ConvCfg<BLOCK_N, SPAN>;
     constexpr bool kTF32 = (sizeof(T) == 4);
-    constexpr int BK = 128 / sizeof(T);           // elements per 128-byte K chunk
-    constexpr int kMmaPerChunk = 4;               // 128 B / 32 B per UMMA K-step
+    constexpr int BK = SPAN / sizeof(T);          // elements per K chunk (one swizzle span)
+    constexpr int kMmaPerChunk = SPAN / 32;       // 32 B per UMMA K-step
     constexpr int kStages = Cfg::kStages;
+    constexpr int kABytes = Cfg::kABytesS;        // shadows the 128-byte-span constant
+    constexpr uint32_t kLayout = SPAN == 128 ? 2u : (SPAN == 64 ? 4u : 6u);     // SWIZZLE_128B / 64B / 32B
+    constexpr uint32_t kSBO = 8 * SPAN;           // 8-row core-matrix groups
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -143,11 +149,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-                    const uint64_t adesc = make_smem_desc(sa, 16, 1024);
-                    const uint64_t bdesc = make_smem_desc(sa + kABytes, 16, 1024);
+                    const uint64_t adesc = make_smem_desc(sa, 16, kSBO, kLayout);
+                    const uint64_t bdesc = make_smem_desc(sa + kABytes, 16, kSBO, kLayout);
 #pragma unroll
                     for (int k = 0; k < kMmaPerChunk; ++k) {
-                        // advance 32 bytes along K inside the 128 B swizzle span: +2 in 16-byte units
+                        // advance 32 bytes along K inside the swizzle span: +2 in 16-byte units
                         umma_ss<kTF32>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) != 0);
                     }
                     umma_commit(&empty_bar[stage]);     // frees the smem slot when these MMAs retire
@@ -184,27 +190,31 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
+            constexpr int CH = BLOCK_N >= 32 ? 32 : 16;      // accumulator columns handled per step
 #pragma unroll 1
-            for (int j = 0; j < BLOCK_N / 32; ++j) {
+            for (int j = 0; j < BLOCK_N / CH; ++j) {
+                __syncwarp();
                 uint32_t r[32];
-                if constexpr (BLOCK_N >= 32) {
+                if constexpr (CH == 32) {
                     tmem_ld32(taddr + j * 32, r);
+                } else {
+                    tmem_ld16(taddr + j * 16, r);
                 }
                 tmem_ld_wait();
                 float v[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
+                for (int i = 0; i < CH; ++i) {
                     float t = __uint_as_float(r[i]);
-                    if (a.bias != nullptr) t += __ldg(a.bias + n0 + j * 32 + i);
+                    if (a.bias != nullptr) t += __ldg(a.bias + n0 + j * CH + i);
                     t *= a.scale;
                     v[i] = lrelu_f(t, a.slope);
                 }
                 if (valid) {
                     if (a.mask_src != nullptr) {
-                        const T* mp = reinterpret_cast<const T*>(a.mask_src) + off + j * 32;
+                        const T* mp = reinterpret_cast<const T*>(a.mask_src) + off + j * CH;
                         constexpr int VN = 16 / sizeof(T);
 #pragma unroll
-                        for (int c = 0; c < 32 / VN; ++c) {
+                        for (int c = 0; c < CH / VN; ++c) {
                             uint4 raw = __ldg(reinterpret_cast<const uint4*>(mp) + c);
                             const T* mv = reinterpret_cast<const T*>(&raw);
 #pragma unroll
@@ -213,9 +223,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         }
                     }
                     if (a.out_dtype == PG_BF16) {
-                        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(a.y) + off + j * 32;
+                        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(a.y) + off + j * CH;
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
+                        for (int c = 0; c < CH / 8; ++c) {
                             uint4 pk;
                             __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
 #pragma unroll
@@ -224,9 +234,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                             reinterpret_cast<uint4*>(op)[c] = pk;
                         }
                     } else {
-                        float* op = reinterpret_cast<float*>(a.y) + off + j * 32;
+                        float* op = reinterpret_cast<float*>(a.y) + off + j * CH;
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) {
+                        for (int c = 0; c < CH / 4; ++c) {
                             float4 pk;
                             pk.x = v[c * 4 + 0];
                             pk.y = v[c * 4 + 1];
@@ -490,10 +500,10 @@ __global__ void conv_direct_kernel(const T* __restrict__ x, const T* __restrict_
 
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
-template <typename T, int BLOCK_N>
+template <typename T, int BLOCK_N, int SPAN = 128>
 static int launch_tc(const pg_conv_params* p, cudaStream_t stream) {
-    using Cfg = ConvCfg<BLOCK_N>;
-    constexpr int BK = 128 / sizeof(T);
+    using Cfg = ConvCfg<BLOCK_N, SPAN>;
+    constexpr int BK = SPAN / sizeof(T);
     ConvKArgs a;
     a.bias = p->bias;
     a.mask_src = p->mask_src;
@@ -517,7 +527,7 @@ static int launch_tc(const pg_conv_params* p, cudaStream_t stream) {
         uint64_t dims[4] = {(uint64_t)p->C, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
         uint64_t strides[3] = {(uint64_t)p->C * es, (uint64_t)p->W * p->C * es, (uint64_t)p->H * p->W * p->C * es};
         uint32_t box[4] = {(uint32_t)BK, (uint32_t)a.BW, (uint32_t)a.BH, (uint32_t)a.BB};
-        int rc = encode_tmap(&tx, DT<T>::kEnum, 4, p->x, dims, strides, box, 128);
+        int rc = encode_tmap(&tx, DT<T>::kEnum, 4, p->x, dims, strides, box, SPAN);
         if (rc != PG_OK) return rc;
     }
     {
@@ -525,10 +535,10 @@ static int launch_tc(const pg_conv_params* p, cudaStream_t stream) {
         uint64_t dims[2] = {K, (uint64_t)p->N};
         uint64_t strides[1] = {K * es};
         uint32_t box[2] = {(uint32_t)BK, (uint32_t)BLOCK_N};
-        int rc = encode_tmap(&tw, DT<T>::kEnum, 2, p->wp, dims, strides, box, 128);
+        int rc = encode_tmap(&tw, DT<T>::kEnum, 2, p->wp, dims, strides, box, SPAN);
         if (rc != PG_OK) return rc;
     }
-    auto kern = conv_gemm_kernel<T, BLOCK_N>;
+    auto kern = conv_gemm_kernel<T, BLOCK_N, SPAN>;
     static bool attr_done = false;   // per template instantiation
     if (!attr_done) {
         PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -594,14 +604,15 @@ static int launch_swapped(const pg_conv_params* p, cudaStream_t stream) {
 
 template <typename T>
 static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream) {
-    constexpr int BK = 128 / sizeof(T);
     constexpr bool kF32 = sizeof(T) == 4;
     pg_conv_params local = *p_in;
     const pg_conv_params* p = &local;
     // fp32 runs as 3xTF32: K is tripled ((x,x,x_lo) . (w,w_lo,w)) through caller-provided workspaces
     const int Ceff = kF32 ? 3 * p->C : p->C;
-    const bool tc_ok = g_conv_backend == PG_BACKEND_AUTO && is_pow2(p->H) && is_pow2(p->W) && (Ceff % BK == 0) &&
-                       (p->N % 32 == 0) && (p->taps == 1 || p->taps == 9) && (!kF32 || (p->C % 4 == 0 && p->ws_x && p->ws_w)) &&
+    const int cbytes = Ceff * (int)sizeof(T);
+    const int span = cbytes % 128 == 0 ? 128 : (cbytes % 64 == 0 ? 64 : (cbytes % 32 == 0 ? 32 : 0));
+    const bool tc_ok = g_conv_backend == PG_BACKEND_AUTO && is_pow2(p->H) && is_pow2(p->W) && span != 0 &&
+                       (p->N % 16 == 0) && (p->taps == 1 || p->taps == 9) && (!kF32 || (p->C % 4 == 0 && p->ws_x && p->ws_w)) &&
                        (reinterpret_cast<uintptr_t>(p->x) % 16 == 0) && (reinterpret_cast<uintptr_t>(p->wp) % 16 == 0) &&
                        (reinterpret_cast<uintptr_t>(p->y) % 16 == 0) &&
                        (p->mask_src == nullptr || reinterpret_cast<uintptr_t>(p->mask_src) % 16 == 0);
@@ -622,7 +633,7 @@ static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream) {
         const bool mask_ok = p->mask_src == nullptr || osz == (int)sizeof(T);
         static const bool no_swap = getenv("PGGAN_NO_SWAP") != nullptr;
         // (its transposing epilogue costs a fixed ~5k cycles per 128x256 tile: only worth it when K is long enough)
-        if (!no_swap && p->N <= 128 && (long long)p->C * p->taps >= 1152 && (p->N * osz) % 16 == 0 && mask_ok &&
+        if (!no_swap && span == 128 && p->N <= 128 && (long long)p->C * p->taps >= 1152 && (p->N * osz) % 16 == 0 && mask_ok &&
             (long long)p->B * p->H * p->W >= 2 * kSwPix)
             return launch_swapped<T>(p, stream);
         // largest N tile that still yields enough CTAs to occupy the machine
@@ -633,11 +644,22 @@ static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream) {
         const int sms = num_sms();
         // N tile: minimise (waves over the SMs) x (per-tile cost).  Per-tile cost is the MMA time (~N) until the
         // fixed 16 KB A-tile shared-memory read per k-step dominates (N <= 64).
-        int bn = 32;
+        if (span != 128) {
+            // narrow layers (C*elsize = 64 or 32 bytes): N is small too, one N tile covers it
+            if (span == 64) {
+                if (p->N % 64 == 0) return launch_tc<T, 64, 64>(p, stream);
+                if (p->N % 32 == 0) return launch_tc<T, 32, 64>(p, stream);
+                return launch_tc<T, 16, 64>(p, stream);
+            }
+            if (p->N % 64 == 0) return launch_tc<T, 64, 32>(p, stream);
+            if (p->N % 32 == 0) return launch_tc<T, 32, 32>(p, stream);
+            return launch_tc<T, 16, 32>(p, stream);
+        }
+        int bn = 16;
         double best = 1e30;
-        const int cands[4] = {256, 128, 64, 32};
-        const double cost[4] = {1.0, 0.56, 0.36, 0.30};
-        for (int i = 0; i < 4; ++i) {
+        const int cands[5] = {256, 128, 64, 32, 16};
+        const double cost[5] = {1.0, 0.56, 0.36, 0.30, 0.28};
+        for (int i = 0; i < 5; ++i) {
             if (p->N % cands[i] != 0) continue;
             const long long tiles = m_tiles * (p->N / cands[i]);
             const double t = (double)((tiles + sms - 1) / sms) * cost[i];
@@ -648,13 +670,14 @@ static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream) {
         }
         if (const char* f = getenv("PGGAN_FORCE_BN")) {      // tuning experiments only
             const int v = atoi(f);
-            if ((v == 32 || v == 64 || v == 128 || v == 256) && p->N % v == 0) bn = v;
+            if ((v == 16 || v == 32 || v == 64 || v == 128 || v == 256) && p->N % v == 0) bn = v;
         }
         switch (bn) {
             case 256: return launch_tc<T, 256>(p, stream);
             case 128: return launch_tc<T, 128>(p, stream);
             case 64: return launch_tc<T, 64>(p, stream);
-            default: return launch_tc<T, 32>(p, stream);
+            case 32: return launch_tc<T, 32>(p, stream);
+            default: return launch_tc<T, 16>(p, stream);
         }
     }
     const long long total = (long long)p->B * p->H * p->W * p->N;

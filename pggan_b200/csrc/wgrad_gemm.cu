@@ -290,6 +290,86 @@ __global__ void wgrad_direct_kernel(const T* __restrict__ g, const T* __restrict
     if (n0 + ty < N && c0 + tx < C) atomicAdd(acc + (static_cast<size_t>(n0 + ty) * taps + tap) * C + c0 + tx, sum);
 }
 
+// ------------------------------------------------------------------ SIMT kernel for tiny channel counts
+// 3x3 weight gradient when both channel counts are <= 32 (the 512^2 / 1024^2 stages).  These layers are
+// bandwidth-shaped: a block stages one image-row segment of g and the 3 neighbouring rows of x in
+// shared memory; a thread owns one input channel c and 4 output channels n for all 9 taps (36 fp32
+// accumulators, 13 shared loads per 36 FMAs) over a strided subset of the segment's pixels.
+template <typename T, int TW, int NT>
+__global__ void __launch_bounds__(256)
+wgrad_small_kernel(const T* __restrict__ g, const T* __restrict__ x, float* __restrict__ acc, int B, int H, int W, int C,
+                   int N) {
+    extern __shared__ float sm[];
+    float* sg = sm;                                   // [TW][N]
+    float* sx = sm + TW * N;                          // [3][TW + 2][C]
+    constexpr int VN = 16 / sizeof(T);
+    const int tpl = C * (N / NT);                     // threads per pixel lane
+    const int PL = blockDim.x / tpl;                  // pixel lanes
+    const int lane_id = threadIdx.x / tpl;
+    const int tt = threadIdx.x % tpl;
+    const int c = tt % C, n0 = (tt / C) * NT;
+    float a[NT][9];
+#pragma unroll
+    for (int i = 0; i < NT; ++i)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) a[i][t] = 0.f;
+    const int segs_w = (W + TW - 1) / TW;
+    const long long nseg = static_cast<long long>(B) * H * segs_w;
+    const int xrow = (TW + 2) * C;                    // floats per staged x row
+    for (long long sidx = blockIdx.x; sidx < nseg; sidx += gridDim.x) {
+        const int sw = static_cast<int>(sidx % segs_w);
+        const int h = static_cast<int>((sidx / segs_w) % H);
+        const long long b = sidx / (static_cast<long long>(segs_w) * H);
+        const int w0 = sw * TW;
+        const int tw = (W - w0) < TW ? (W - w0) : TW;
+        __syncthreads();
+        // g: tw*N contiguous elements; x: three rows of (tw+2)*C contiguous elements (NHWC), 16-byte vectors
+        const T* gsrc = g + ((b * H + h) * W + w0) * N;
+        for (int k = threadIdx.x; k < tw * N / VN; k += blockDim.x) {
+            const uint4 raw = __ldg(reinterpret_cast<const uint4*>(gsrc) + k);
+            const T* v = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+            for (int e = 0; e < VN; ++e) sg[k * VN + e] = DT<T>::to_f(v[e]);
+        }
+        const int nvx = xrow / VN;
+        for (int k = threadIdx.x; k < 3 * nvx; k += blockDim.x) {
+            const int r = k / nvx, kv = k - r * nvx;
+            const int hh = h + r - 1;
+            const int px = (kv * VN) / C;             // staged pixel index (0 = w0-1); C % VN == 0 so a vector stays in one pixel
+            const int ww = w0 + px - 1;
+            uint4 raw = make_uint4(0, 0, 0, 0);
+            if (hh >= 0 && hh < H && ww >= 0 && ww < W && px < tw + 2)
+                raw = __ldg(reinterpret_cast<const uint4*>(x + ((b * H + hh) * W + ww) * C + (kv * VN) % C));
+            const T* v = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+            for (int e = 0; e < VN; ++e) sx[r * xrow + kv * VN + e] = DT<T>::to_f(v[e]);
+        }
+        __syncthreads();
+        if (lane_id < PL) {
+            for (int p = lane_id; p < tw; p += PL) {
+                float gv[NT];
+#pragma unroll
+                for (int i = 0; i < NT; i += 4) {
+                    const float4 t4 = *reinterpret_cast<const float4*>(sg + p * N + n0 + i);
+                    gv[i] = t4.x; gv[i + 1] = t4.y; gv[i + 2] = t4.z; gv[i + 3] = t4.w;
+                }
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    const float xv = sx[(t / 3) * xrow + (p + (t % 3)) * C + c];
+#pragma unroll
+                    for (int i = 0; i < NT; ++i) a[i][t] += gv[i] * xv;
+                }
+            }
+        }
+    }
+    if (lane_id < PL) {
+#pragma unroll
+        for (int i = 0; i < NT; ++i)
+#pragma unroll
+            for (int t = 0; t < 9; ++t) atomicAdd(acc + (static_cast<size_t>(n0 + i) * 9 + t) * C + c, a[i][t]);
+    }
+}
+
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 template <typename T, int BLOCK_C>
@@ -446,6 +526,24 @@ static int wgrad_dispatch(const pg_wgrad_params* p_in, cudaStream_t stream, int*
     }
     // SIMT path: one slice, partial sums meet through atomics on a zeroed accumulator
     PG_CUDA(cudaMemsetAsync(p->acc, 0, sizeof(float) * (size_t)p->N * p->taps * p->C, stream));
+    constexpr int VNT = 16 / sizeof(T);
+    if (p->taps == 9 && p->N <= 64 && p->C <= 32 && p->N % 8 == 0 && p->C % VNT == 0 && p->N % VNT == 0 &&
+        (reinterpret_cast<uintptr_t>(p->g) % 16 == 0) && (reinterpret_cast<uintptr_t>(p->x) % 16 == 0)) {
+        constexpr int TW = 64;
+        const size_t smem = (size_t)(TW * p->N + 3 * (TW + 2) * p->C) * sizeof(float);
+        const long long nseg = (long long)p->B * p->H * ((p->W + TW - 1) / TW);
+        long long grid = (long long)num_sms() * 4;
+        if (grid > nseg) grid = nseg;
+        const T* gp = reinterpret_cast<const T*>(p->g);
+        const T* xp = reinterpret_cast<const T*>(p->x);
+        if (p->C * (p->N / 4) <= 256)
+            wgrad_small_kernel<T, TW, 4><<<(int)grid, 256, smem, stream>>>(gp, xp, p->acc, p->B, p->H, p->W, p->C, p->N);
+        else
+            wgrad_small_kernel<T, TW, 8><<<(int)grid, 256, smem, stream>>>(gp, xp, p->acc, p->B, p->H, p->W, p->C, p->N);
+        PG_LAUNCH_CHECK();
+        g_simt_launches++;
+        return PG_OK;
+    }
     const long long P = (long long)p->B * p->H * p->W;
     long long pix_per_block = 256;
     while ((P + pix_per_block - 1) / pix_per_block > 2048) pix_per_block *= 2;

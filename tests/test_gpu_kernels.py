@@ -53,6 +53,11 @@ CONV_SHAPES = [
     (3, 16, 16, 64, 128, 9),       # swapped, ragged batch; wgrad stacks 4 taps of the 64-channel input
     (2, 64, 64, 64, 64, 9),        # the 256^2-stage layer shape (64 -> 64)
     (9, 8, 8, 64, 128, 9),         # swapped with a partially filled 256-pixel box in the batch dimension
+    (2, 64, 64, 32, 32, 9),        # 64-byte K span (32 bf16 channels): the 512^2-stage shapes
+    (2, 64, 64, 16, 16, 9),        # 32-byte K span, N tile 16: the 1024^2-stage shapes
+    (1, 128, 128, 32, 16, 9),
+    (2, 32, 32, 16, 32, 9),
+    (2, 32, 32, 32, 64, 9),
 ]
 
 
