@@ -197,3 +197,48 @@ def test_train_step_matches_oracle(scale, width, batch, variant):
             # Adam's first step is lr*g/(|g|+eps): compare where the reference gradient is not ~0
             bad = ((d_my - d_ref).abs() > 0.3 * lr).float().mean().item()
             assert bad < 0.03, (name, k, bad)
+
+
+@pytest.mark.parametrize("name,scale,depths,batch", [
+    ("C4 256x256", 6, [512, 512, 512, 512, 256, 128, 64], 4),
+    ("C5 1024x1024 (paper widths)", 8, [512, 512, 512, 512, 256, 128, 64, 32, 16], 2),
+])
+def test_full_size_configs_fp32(name, scale, depths, batch):
+    """BASELINE configs 4 and 5 at their real widths/resolutions (small batch): G images, D logits and the
+    WGAN-GP value against the oracle in fp32 mode, plus a size-independent property — D is positively
+    homogeneous-free but its input gradient chain is linear in the seed: grad(2*sum D) == 2*grad(sum D)."""
+    import pggan_b200 as pg
+    pg.set_compute_dtype(torch.float32)
+    alpha = 0.5
+    G, D, g_sd, d_sd = build_pair(scale, depths, 512, seed=40 + scale)
+    G.alpha = D.alpha = alpha
+    res = 4 * 2 ** scale
+    torch.manual_seed(5)
+    z = torch.randn(batch, 512, device="cuda")
+    x = torch.rand(batch, 3, res, res, device="cuda") * 2 - 1
+    with torch.no_grad():
+        img_ref = O.generator_forward(g_sd, z, alpha)
+        logit_ref = O.discriminator_forward(d_sd, x, alpha)
+        img = G(z)
+        logit = D(x)
+    e_img, e_logit = rel_l2(img, img_ref), rel_l2(logit, logit_ref)
+    print(f"\n{name}: img {e_img:.2e} logit {e_logit:.2e}")
+    assert img.shape == (batch, 3, res, res)
+    assert e_img < 1e-3 and e_logit < 1e-3
+    # gradient penalty value (double backward through every resolution stage)
+    eps = torch.rand(batch, 1)
+    fake = img.detach()
+    gp_ref = O.gradient_penalty(lambda t: O.discriminator_forward(d_sd, t, alpha), x.clone().requires_grad_(), fake,
+                                10.0, eps=eps, backward=False)
+    lc = pg.WGANGPLoss(pg.make_args())
+    xm = x.clone().requires_grad_()
+    gp = lc.get_gradient_penalty({"img_real": xm, "img_fake": fake, "pred_real": logit}, D, backward=True, eps=eps)
+    e_gp = abs(gp - float(gp_ref)) / abs(float(gp_ref))
+    print(f"    GP {gp:.4f} vs {float(gp_ref):.4f} rel {e_gp:.2e}")
+    assert e_gp < 1e-3
+    # linearity of the first-order chain in its seed
+    xa = x.clone().requires_grad_()
+    (g1,) = torch.autograd.grad(D(xa).sum(), xa)
+    xb = x.clone().requires_grad_()
+    (g2,) = torch.autograd.grad(2.0 * D(xb).sum(), xb)
+    assert rel_l2(g2, 2.0 * g1) < 1e-5
