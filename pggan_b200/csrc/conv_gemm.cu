@@ -26,6 +26,10 @@ namespace pg {
 extern std::atomic<long long> g_tc_launches, g_simt_launches;
 extern int g_conv_backend;
 
+// conv_rows.cu: smem-resident input rows, nine shifted views (narrow layers on wide images)
+bool conv_rows_supported(const pg_conv_params* p);
+int conv_rows_launch(const pg_conv_params* p, cudaStream_t stream);
+
 constexpr int kBlockM = 128;
 constexpr int kConvThreads = 192;
 
@@ -628,6 +632,9 @@ static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream) {
             local.wp = p->ws_w;
             local.C = Ceff;
         }
+        // narrow layers on wide images: input rows resident in smem, taps as shifted views (conv_rows.cu)
+        static const bool no_rows = getenv("PGGAN_NO_ROWS") != nullptr;
+        if (!kF32 && !no_rows && conv_rows_supported(p)) return conv_rows_launch(p, stream);
         // few output channels: swapped orientation (channels on M, 256 pixels on N) keeps the tensor pipe fed
         const int osz = (p->out_dtype == PG_BF16) ? 2 : 4;
         const bool mask_ok = p->mask_src == nullptr || osz == (int)sizeof(T);

@@ -58,6 +58,15 @@ CONV_SHAPES = [
     (1, 128, 128, 32, 16, 9),
     (2, 32, 32, 16, 32, 9),
     (2, 32, 32, 32, 64, 9),
+    # conv_rows kernel (W % 128 == 0, C*2 bytes = one swizzle span): smem-resident rows, taps as shifted views
+    (2, 32, 128, 64, 64, 9),       # 128-byte span, one segment per row
+    (3, 64, 256, 64, 64, 9),       # two 128-pixel segments per row, strips cut at image ends
+    (1, 128, 128, 64, 128, 9),     # N = 128 (ring of 5 rows)
+    (2, 64, 256, 32, 32, 9),       # 64-byte span
+    (1, 256, 512, 32, 64, 9),
+    (1, 64, 1024, 16, 16, 9),      # 32-byte span, N tile 16
+    (2, 128, 256, 16, 32, 9),
+    (1, 4, 128, 64, 16, 9),        # shortest strip
 ]
 
 

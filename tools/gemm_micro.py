@@ -16,6 +16,9 @@ SHAPES = [(64, 32, 32, 512, 512), (128, 32, 32, 512, 512), (64, 16, 16, 512, 512
 if len(sys.argv) > 2 and sys.argv[2] == "c4":       # the 128^2 / 256^2 stage layer shapes (B, H, W, Cin, Cout)
     SHAPES = [(16, 256, 256, 64, 64), (16, 256, 256, 128, 64), (16, 256, 256, 64, 128), (16, 128, 128, 128, 128),
               (16, 128, 128, 256, 128), (16, 128, 128, 128, 256), (16, 64, 64, 256, 256)]
+if len(sys.argv) > 2 and sys.argv[2] == "narrow":   # the 256^2 / 512^2 / 1024^2 narrow layers (conv_rows.cu)
+    SHAPES = [(16, 256, 256, 64, 64), (16, 256, 256, 64, 128), (4, 512, 512, 32, 32), (4, 512, 512, 32, 64),
+              (4, 512, 512, 64, 32), (4, 1024, 1024, 16, 16), (4, 1024, 1024, 16, 32), (4, 1024, 1024, 32, 16)]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 for (B, H, W, C, N) in SHAPES:
     x = torch.randn(B, C, H, W, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
@@ -40,4 +43,6 @@ for (B, H, W, C, N) in SHAPES:
             ts.append(e0.elapsed_time(e1))
         ts.sort()
         med = ts[len(ts) // 2]
-        print(f"{name:11s} B{B} {H}x{W} C{C}->N{N}: median {med*1e3:8.1f} us  {fl/med/1e9:8.1f} TFLOP/s (min {ts[0]*1e3:.1f} us)", flush=True)
+        byt = 2.0 * B * H * W * (C + N)
+        print(f"{name:11s} B{B} {H}x{W} C{C}->N{N}: median {med*1e3:8.1f} us  {fl/med/1e9:8.1f} TFLOP/s  "
+              f"{byt/med/1e6:7.0f} GB/s (min {ts[0]*1e3:.1f} us)", flush=True)
