@@ -487,6 +487,94 @@ __global__ void split3_kernel(const float* __restrict__ in, float* __restrict__ 
     }
 }
 
+// narrow feature maps (C/VN = LP <= 16 vectors per pixel, LP a power of two): LP lanes per pixel, 32/LP pixels
+// per warp, so every lane of a load instruction is live (the warp-per-pixel kernels above leave 30 of 32 lanes
+// idle at C = 16: 131 / 357 us per 1024^2 map where the HBM floor is 41 / 61 us)
+template <typename T>
+__global__ void __launch_bounds__(256)
+pixelnorm_fwd_small_kernel(const T* __restrict__ x, T* __restrict__ y, float* __restrict__ rnorm, long long M, int C,
+                           float eps, int LP) {
+    constexpr int VN = V16<T>::N;
+    const long long nvec_total = M * LP;
+    const float inv_c = 1.f / C;
+    GRID_STRIDE(i, (nvec_total + 31) / 32 * 32) {           // whole warps stay converged for the shuffles
+        const bool live = i < nvec_total;
+        V16<T> v;
+        float ss = 0.f;
+        if (live) {
+            v = ld16(x + i * VN);
+#pragma unroll
+            for (int e = 0; e < VN; ++e) ss += v.get(e) * v.get(e);
+        }
+        for (int o = LP >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        if (live) {
+            const float r = rsqrtf(ss * inv_c + eps);
+            if (rnorm != nullptr && (i % LP) == 0) rnorm[i / LP] = r;
+            V16<T> o;
+#pragma unroll
+            for (int e = 0; e < VN; ++e) o.set(e, v.get(e) * r);
+            st16(y + i * VN, o);
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+pixelnorm_bwd_small_kernel(const T* __restrict__ gy, const T* __restrict__ y, const float* __restrict__ rnorm,
+                           T* __restrict__ gx, long long M, int C, float act_slope, float* __restrict__ colsum,
+                           float cs_scale, int LP) {
+    constexpr int VN = V16<T>::N;
+    __shared__ float red[8][16 * VN];
+    const long long nvec_total = M * LP;
+    const float inv_c = 1.f / C;
+    float cs[VN];
+#pragma unroll
+    for (int e = 0; e < VN; ++e) cs[e] = 0.f;
+    // the grid stride is a multiple of 32 and of LP, so a lane always owns the same channel vector (lane % LP)
+    GRID_STRIDE(i, (nvec_total + 31) / 32 * 32) {
+        const bool live = i < nvec_total;
+        V16<T> g, yv;
+        float dot = 0.f;
+        if (live) {
+            g = ld16(gy + i * VN);
+            yv = ld16(y + i * VN);
+#pragma unroll
+            for (int e = 0; e < VN; ++e) dot += g.get(e) * yv.get(e);
+        }
+        for (int o = LP >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        if (live) {
+            dot *= inv_c;
+            const float r = rnorm[i / LP];
+            V16<T> o;
+#pragma unroll
+            for (int e = 0; e < VN; ++e) {
+                const float yy = yv.get(e);
+                float t = r * (g.get(e) - yy * dot);
+                if (!(yy > 0.f)) t *= act_slope;
+                o.set(e, t);
+                cs[e] += o.get(e);
+            }
+            st16(gx + i * VN, o);
+        }
+    }
+    if (colsum != nullptr) {
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+        for (int e = 0; e < VN; ++e)
+            for (int o = 16; o >= LP; o >>= 1) cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], o);
+        if (lane < LP)
+#pragma unroll
+            for (int e = 0; e < VN; ++e) red[wid][lane * VN + e] = cs[e];
+        __syncthreads();
+        const int nw = blockDim.x >> 5;
+        for (int o = threadIdx.x; o < LP * VN; o += blockDim.x) {
+            float t = 0.f;
+            for (int w2 = 0; w2 < nw; ++w2) t += red[w2][o];
+            atomicAdd(colsum + o, t * cs_scale);
+        }
+    }
+}
+
 }  // namespace pg
 
 using namespace pg;
@@ -580,6 +668,13 @@ extern "C" int pggan_pixelnorm_fwd(const void* x, void* y, float* rnorm, int64_t
         constexpr int VN = V16<T>::N;
         PG_CHECK(C % VN == 0 && C <= 32 * VN * 4, PG_ERR_UNSUPPORTED,
                  "pggan_pixelnorm_fwd: C=%d must be a multiple of %d and <= %d", C, VN, 32 * VN * 4);
+        const int lp = C / VN;
+        if (lp <= 16 && (lp & (lp - 1)) == 0) {
+            pixelnorm_fwd_small_kernel<T><<<ew_grid(m * lp, 256), 256, 0, s>>>((const T*)x, (T*)y, rnorm, m, C, eps, lp);
+            PG_LAUNCH_CHECK();
+            g_other_launches++;
+            return PG_OK;
+        }
         const int grid = ew_grid(m * 32, 256);
         if (C <= 32 * VN)
             pixelnorm_fwd_kernel<T, 1><<<grid, 256, 0, s>>>((const T*)x, (T*)y, rnorm, m, C, eps);
@@ -603,6 +698,14 @@ extern "C" int pggan_pixelnorm_bwd(const void* gy, const void* y, const float* r
         constexpr int VN = V16<T>::N;
         PG_CHECK(C % VN == 0 && C <= 32 * VN * 4, PG_ERR_UNSUPPORTED,
                  "pggan_pixelnorm_bwd: C=%d must be a multiple of %d and <= %d", C, VN, 32 * VN * 4);
+        const int lp = C / VN;
+        if (lp <= 16 && (lp & (lp - 1)) == 0) {
+            pixelnorm_bwd_small_kernel<T><<<ew_grid(m * lp / 4 + 1, 256), 256, 0, s>>>(
+                (const T*)gy, (const T*)y, rnorm, (T*)gx, m, C, act_slope, colsum, cs_scale, lp);
+            PG_LAUNCH_CHECK();
+            g_other_launches++;
+            return PG_OK;
+        }
         const int grid = ew_grid(m * 32 / 4 + 1, 256);      // ~4 rows per warp
         if (C <= 32 * VN)
             pixelnorm_bwd_kernel<T, 1><<<grid, 256, 0, s>>>((const T*)gy, (const T*)y, rnorm, (T*)gx, m, C, act_slope, colsum, cs_scale);

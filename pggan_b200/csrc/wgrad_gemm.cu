@@ -18,11 +18,17 @@
 #include "common.cuh"
 
 #include <atomic>
+#include <stdlib.h>
 
 namespace pg {
 
 extern std::atomic<long long> g_tc_launches, g_simt_launches;
 extern int g_conv_backend;
+
+// wgrad_rows.cu: narrow layers on wide images (all nine taps in one MMA over smem-resident rows)
+bool wgrad_rows_supported(const pg_wgrad_params* p);
+int wgrad_rows_slices(const pg_wgrad_params* p);
+int wgrad_rows_launch(const pg_wgrad_params* p, cudaStream_t stream);
 
 constexpr int kWgThreads = 192;
 
@@ -491,6 +497,18 @@ static int wgrad_dispatch(const pg_wgrad_params* p_in, cudaStream_t stream, int*
                        (p->N % 8 == 0) && (!kF32 || slices_out || (p->ws_g && p->ws_x)) &&
                        (reinterpret_cast<uintptr_t>(p->g) % 16 == 0) &&
                        (reinterpret_cast<uintptr_t>(p->x) % 16 == 0) && (reinterpret_cast<uintptr_t>(p->acc) % 16 == 0);
+    if constexpr (!kF32) {
+        static const bool no_rows = getenv("PGGAN_NO_WROWS") != nullptr;
+        const bool rows_ok = g_conv_backend == PG_BACKEND_AUTO && (reinterpret_cast<uintptr_t>(p->g) % 16 == 0) &&
+                             (reinterpret_cast<uintptr_t>(p->x) % 16 == 0) && (reinterpret_cast<uintptr_t>(p->acc) % 16 == 0);
+        if (rows_ok && !no_rows && wgrad_rows_supported(p)) {
+            if (slices_out) {
+                *slices_out = wgrad_rows_slices(p);
+                return PG_OK;
+            }
+            return wgrad_rows_launch(p, stream);
+        }
+    }
     if (tc_ok && slices_out) {
         if (kF32) local.B = 3 * p->B;
         const bool stack = p->taps > 1 && p->C < 256 && 256 % p->C == 0 && p->C % CPS == 0 && p->N % CPS == 0;

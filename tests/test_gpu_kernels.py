@@ -67,6 +67,10 @@ CONV_SHAPES = [
     (1, 64, 1024, 16, 16, 9),      # 32-byte span, N tile 16
     (2, 128, 256, 16, 32, 9),
     (1, 4, 128, 64, 16, 9),        # shortest strip
+    (2, 32, 128, 32, 16, 9),       # wgrad_rows: remaining (C, N) span combinations
+    (1, 16, 128, 16, 64, 9),
+    (1, 8, 256, 64, 32, 9),
+    (5, 64, 128, 16, 16, 9),       # more strips than one per CTA range boundary
 ]
 
 
