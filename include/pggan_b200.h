@@ -100,6 +100,14 @@ typedef struct {
     void* ws_w;
 } pg_conv_params;
 int pggan_conv_fprop(const pg_conv_params* p, void* stream);
+/* which kernel pggan_conv_fprop would run this shape on (pointers may be NULL): lets the host decide where fusing a
+ * LeakyReLU backward into the dgrad epilogue (mask_src) is free (PLAIN / ROWS: one output row per thread) and where
+ * it is not (SWAPPED: transposing, instruction-bound epilogue). */
+#define PG_CONV_KIND_SIMT 0
+#define PG_CONV_KIND_PLAIN 1
+#define PG_CONV_KIND_SWAPPED 2
+#define PG_CONV_KIND_ROWS 3
+int pggan_conv_kernel_kind(const pg_conv_params* p);
 
 /* Weight-gradient GEMM:  sum_s acc[s][n][t][c] = sum_{b,h,w} g[b,h,w,n] * x[b, h+dh(t), w+dw(t), c]
  * acc holds pggan_conv_wgrad_slices(p) dense fp32 [N][taps][C] slices (split-K over pixels writes one slice per
@@ -127,6 +135,11 @@ int pggan_conv_wgrad_slices(const pg_wgrad_params* p); /* how many slices the ca
 int pggan_lrelu_mask_mul(const void* g, const void* y, void* out, int64_t n, float slope, int dtype, void* stream);
 /* out[b,2h+i,2w+j,c] = scale * x[b,h,w,c]   — upscale2d, lib/utils.py:106-118 (exact) and avg-pool backward */
 int pggan_upsample2x(const void* x, void* out, int B, int H, int W, int C, float scale, int dtype, void* stream);
+/* the same fused with a LeakyReLU backward: out = up2(scale*x) * (mask_src > 0 ? 1 : slope), mask_src [B,2H,2W,C]
+ * — backward of "conv -> LeakyReLU -> AvgPool2d" (lib/blocks.py:192-193) in one pass instead of
+ * avg_pool2d_backward + leaky_relu_backward */
+int pggan_upsample2x_mask(const void* x, const void* mask_src, void* out, int B, int H, int W, int C, float scale,
+                          float slope, int dtype, void* stream);
 /* out[b,h,w,c] = scale * sum_{i,j<2} x[b,2h+i,2w+j,c]; if blend_with != NULL:
  * out = (1-alpha)*blend_with + alpha*that   — nn.AvgPool2d(2) lib/blocks.py:193 (+ fade pggan/nets.py:265) */
 int pggan_pool2x2(const void* x, const void* blend_with, void* out, int B, int H, int W, int C, float scale,

@@ -10,6 +10,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 
 PG_BF16, PG_F32, PG_F32_RAW = 0, 1, 2
 PG_BACKEND_AUTO, PG_BACKEND_SIMT = 0, 1
+PG_CONV_KIND_SIMT, PG_CONV_KIND_PLAIN, PG_CONV_KIND_SWAPPED, PG_CONV_KIND_ROWS = 0, 1, 2, 3
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libpggan_b200.so")
@@ -56,10 +57,13 @@ SIGNATURES = {
     "pggan_unpack_wgrad": (c_int, [c_void_p, c_void_p, POINTER(PackMap), c_int, c_float, c_int, c_void_p]),
     "pggan_split3": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
     "pggan_conv_fprop": (c_int, [POINTER(ConvParams), c_void_p]),
+    "pggan_conv_kernel_kind": (c_int, [POINTER(ConvParams)]),
     "pggan_conv_wgrad": (c_int, [POINTER(WgradParams), c_void_p]),
     "pggan_conv_wgrad_slices": (c_int, [POINTER(WgradParams)]),
     "pggan_lrelu_mask_mul": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_int, c_void_p]),
     "pggan_upsample2x": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
+    "pggan_upsample2x_mask": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_int,
+                                      c_void_p]),
     "pggan_pool2x2": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_int,
                               c_void_p]),
     "pggan_axpby": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_int, c_void_p]),

@@ -88,14 +88,26 @@ class ProgressiveDiscriminatorBlock(nn.Module):
             nn.AvgPool2d((2, 2)),
         )
 
-    def forward(self, x, blend_with=None, alpha=1.0):
+    def first_dgrad_fuses_mask(self, batch, h, w) -> bool:
+        """may the producer of this block's input (a fromRGB block) defer its LeakyReLU mask to conv1's dgrad?"""
+        c1 = self.block[0].module
+        return ops.dgrad_mask_fusable(batch, h, w, c1.in_channels, c1.out_channels)
+
+    def forward(self, x, blend_with=None, alpha=1.0, x_act_slope=None):
         """blend_with/alpha: optional feature-space fade fused with the pooling
-        ((1-alpha)*blend_with + alpha*pool(x), reference pggan/nets.py:262-265)."""
-        x = self.block[0].fused(x, 0.2)
-        x = self.block[2].fused(x, 0.2)
+        ((1-alpha)*blend_with + alpha*pool(x), reference pggan/nets.py:262-265).
+        x_act_slope: x comes straight from a fromRGB block run with defer_mask=True.
+        The three LeakyReLU backward passes of the block are fused away: conv1's mask is applied in conv2's dgrad
+        epilogue, conv2's in the pooling backward, fromRGB's (if any) in conv1's dgrad epilogue."""
+        # ...where that epilogue is free; a dgrad that runs on the swapped-orientation kernel keeps the separate pass
+        b, _, h, w = x.shape
+        c2 = self.block[2].module
+        fuse2 = ops.dgrad_mask_fusable(b, h, w, c2.in_channels, c2.out_channels)
+        x = self.block[0].fused(x, 0.2, x_act_slope=x_act_slope, defer_mask=fuse2)
+        x = self.block[2].fused(x, 0.2, x_act_slope=0.2 if fuse2 else None, defer_mask=True)
         if blend_with is not None:
-            return ops.PoolBlend.apply(x, blend_with, float(alpha))
-        return ops.Pool2x2.apply(x, 0.25)
+            return ops.PoolBlend.apply(x, blend_with, float(alpha), 0.2)
+        return ops.Pool2x2.apply(x, 0.25, 0.2)
 
 
 def _stddev_channel(x, subgroup_size=4):
@@ -166,8 +178,8 @@ class fromRGBBlock(nn.Module):
                                        init_bias_to_zero=init_bias_to_zero)
         self.activ = nn.LeakyReLU(0.2)
 
-    def forward(self, x, apply_downscale=False):
+    def forward(self, x, apply_downscale=False, defer_mask=False):
         m = self.fromRGB.module
         W = m.weight
         return ops.RgbExpand.apply(x, W.view(W.shape[0], W.shape[1]), m.bias, bool(apply_downscale),
-                                   self.fromRGB.scale(), 0.2)
+                                   self.fromRGB.scale(), 0.2, bool(defer_mask))

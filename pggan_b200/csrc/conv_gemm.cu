@@ -191,10 +191,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             const size_t pix = (static_cast<size_t>(b) * a.H + (h0 + ho)) * a.W + (w0 + wo);
             const size_t off = pix * a.N + n0;
 
+            constexpr int CH = BLOCK_N >= 32 ? 32 : 16;      // accumulator columns handled per step
+            constexpr int VN = 16 / sizeof(T);
+            constexpr int MV = CH / VN;                      // 16-byte mask vectors per step
+            // the dgrad mask (a saved activation, same layout as y) is fetched one step AHEAD of its use — the first
+            // step's vectors before the wait on the accumulator — so its global-load latency hides behind the MMAs
+            const bool masked = valid && a.mask_src != nullptr;
+            uint4 mcur[MV];
+            if (masked) {
+                const uint4* mp = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(a.mask_src) + off);
+#pragma unroll
+                for (int c = 0; c < MV; ++c) mcur[c] = __ldg(mp + c);
+            }
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
-            constexpr int CH = BLOCK_N >= 32 ? 32 : 16;      // accumulator columns handled per step
 #pragma unroll 1
             for (int j = 0; j < BLOCK_N / CH; ++j) {
                 __syncwarp();
@@ -203,6 +214,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     tmem_ld32(taddr + j * 32, r);
                 } else {
                     tmem_ld16(taddr + j * 16, r);
+                }
+                uint4 mnxt[MV];
+                if (masked && j + 1 < BLOCK_N / CH) {
+                    const uint4* mp = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(a.mask_src) + off + (j + 1) * CH);
+#pragma unroll
+                    for (int c = 0; c < MV; ++c) mnxt[c] = __ldg(mp + c);
                 }
                 tmem_ld_wait();
                 float v[32];
@@ -214,17 +231,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     v[i] = lrelu_f(t, a.slope);
                 }
                 if (valid) {
-                    if (a.mask_src != nullptr) {
-                        const T* mp = reinterpret_cast<const T*>(a.mask_src) + off + j * CH;
-                        constexpr int VN = 16 / sizeof(T);
+                    if (masked) {
 #pragma unroll
-                        for (int c = 0; c < CH / VN; ++c) {
-                            uint4 raw = __ldg(reinterpret_cast<const uint4*>(mp) + c);
-                            const T* mv = reinterpret_cast<const T*>(&raw);
+                        for (int c = 0; c < MV; ++c) {
+                            const T* mv = reinterpret_cast<const T*>(&mcur[c]);
 #pragma unroll
                             for (int e = 0; e < VN; ++e)
                                 if (!(DT<T>::to_f(mv[e]) > 0.f)) v[c * VN + e] *= a.mask_slope;
                         }
+#pragma unroll
+                        for (int c = 0; c < MV; ++c) mcur[c] = mnxt[c];
                     }
                     if (a.out_dtype == PG_BF16) {
                         __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(a.y) + off + j * CH;
@@ -403,6 +419,29 @@ conv_gemm_swapped_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
             const int row_bytes = cvalid * osz;             // one pixel's channel slice in the output
             const int vec_per_row = row_bytes / 16;
 
+            // dgrad mask vectors of a slab are fetched one slab ahead (slab 0 before the accumulator wait), so the
+            // global-load latency is off the store loop's critical path
+            constexpr int MAXI = sizeof(T) == 2 ? 4 : 8;    // 16-byte vectors per thread per slab (<= 32*32/128)
+            const bool masked = a.mask_src != nullptr && osz == static_cast<int>(sizeof(T));
+            auto load_masks = [&](int j, uint4 (&m)[MAXI]) {
+#pragma unroll
+                for (int i = 0; i < MAXI; ++i) {
+                    const int v = et + i * 128;
+                    if (v < 32 * vec_per_row) {
+                        const int p = v / vec_per_row, vv = v - p * vec_per_row;
+                        const int row = j * 32 + p;
+                        const int wo = row % a.BW;
+                        const int ho = (row / a.BW) % a.BH;
+                        const int b = b0 + row / (a.BW * a.BH);
+                        if (b < a.B) {
+                            const size_t pix = (static_cast<size_t>(b) * a.H + (h0 + ho)) * a.W + (w0 + wo);
+                            m[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(a.mask_src) + pix * a.N + n0) + vv);
+                        }
+                    }
+                }
+            };
+            uint4 mcur[MAXI], mnxt[MAXI];
+            if (masked) load_masks(0, mcur);
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kSwPix;
@@ -411,6 +450,7 @@ conv_gemm_swapped_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
                 __syncwarp();
                 uint32_t r[32];
                 tmem_ld32(taddr + j * 32, r);
+                if (masked && j + 1 < kSwPix / 32) load_masks(j + 1, mnxt);
                 tmem_ld_wait();
                 // transpose through smem: staging[pixel p][channel cl]
                 if (cl < cvalid) {
@@ -427,8 +467,12 @@ conv_gemm_swapped_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
                     }
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
-                // coalesced store of the 32 x cvalid slab (+ optional LeakyReLU mask of the saved activation)
-                for (int v = et; v < 32 * vec_per_row; v += 128) {
+                // coalesced store of the 32 x cvalid slab (+ optional LeakyReLU mask of the saved activation;
+                // mask_src has the operand dtype T, so only the out dtype == T case is masked)
+#pragma unroll
+                for (int i = 0; i < 2 * MAXI; ++i) {        // fp32 output of bf16 operands has twice the vectors
+                    const int v = et + i * 128;
+                    if (v >= 32 * vec_per_row) break;
                     const int p = v / vec_per_row, vv = v - p * vec_per_row;
                     const int row = j * 32 + p;
                     const int wo = row % a.BW;
@@ -437,20 +481,19 @@ conv_gemm_swapped_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
                     if (b >= a.B) continue;
                     const size_t pix = (static_cast<size_t>(b) * a.H + (h0 + ho)) * a.W + (w0 + wo);
                     uint4 val = *reinterpret_cast<const uint4*>(staging + static_cast<size_t>(p) * row_bytes + vv * 16);
-                    if (a.mask_src != nullptr) {
+                    if (masked && i < MAXI) {
                         constexpr int VN = 16 / sizeof(T);
-                        const uint4 mraw = __ldg(reinterpret_cast<const uint4*>(
-                            reinterpret_cast<const T*>(a.mask_src) + pix * a.N + n0) + vv * (16 / osz) / VN);
-                        // mask_src has the operand dtype T; out has osz bytes/elem: only the T == out case is used
-                        if (osz == static_cast<int>(sizeof(T))) {
-                            T* ov = reinterpret_cast<T*>(&val);
-                            const T* mv = reinterpret_cast<const T*>(&mraw);
+                        T* ov = reinterpret_cast<T*>(&val);
+                        const T* mv = reinterpret_cast<const T*>(&mcur[i < MAXI ? i : 0]);
 #pragma unroll
-                            for (int e = 0; e < VN; ++e)
-                                if (!(DT<T>::to_f(mv[e]) > 0.f)) ov[e] = DT<T>::from_f(DT<T>::to_f(ov[e]) * a.mask_slope);
-                        }
+                        for (int e = 0; e < VN; ++e)
+                            if (!(DT<T>::to_f(mv[e]) > 0.f)) ov[e] = DT<T>::from_f(DT<T>::to_f(ov[e]) * a.mask_slope);
                     }
                     *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(a.y) + (pix * a.N + n0) * osz + vv * 16) = val;
+                }
+                if (masked) {
+#pragma unroll
+                    for (int i = 0; i < MAXI; ++i) mcur[i] = mnxt[i];
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
             }
@@ -607,7 +650,8 @@ static int launch_swapped(const pg_conv_params* p, cudaStream_t stream) {
 }
 
 template <typename T>
-static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream) {
+static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream, int* kind_out = nullptr) {
+    // kind_out != nullptr: only report which kernel the shape would run on (PG_CONV_KIND_*), no launch
     constexpr bool kF32 = sizeof(T) == 4;
     pg_conv_params local = *p_in;
     const pg_conv_params* p = &local;
@@ -620,6 +664,22 @@ static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream) {
                        (reinterpret_cast<uintptr_t>(p->x) % 16 == 0) && (reinterpret_cast<uintptr_t>(p->wp) % 16 == 0) &&
                        (reinterpret_cast<uintptr_t>(p->y) % 16 == 0) &&
                        (p->mask_src == nullptr || reinterpret_cast<uintptr_t>(p->mask_src) % 16 == 0);
+    if (kind_out != nullptr) {
+        *kind_out = PG_CONV_KIND_SIMT;
+        if (tc_ok) {
+            const int osz_k = (p->out_dtype == PG_BF16) ? 2 : 4;
+            static const bool no_rows_k = getenv("PGGAN_NO_ROWS") != nullptr;
+            static const bool no_swap_k = getenv("PGGAN_NO_SWAP") != nullptr;
+            if (!kF32 && !no_rows_k && conv_rows_supported(p))
+                *kind_out = PG_CONV_KIND_ROWS;
+            else if (!no_swap_k && span == 128 && p->N <= 128 && (long long)Ceff * p->taps >= 1152 && (p->N * osz_k) % 16 == 0 &&
+                     (long long)p->B * p->H * p->W >= 2 * kSwPix)
+                *kind_out = PG_CONV_KIND_SWAPPED;
+            else
+                *kind_out = PG_CONV_KIND_PLAIN;
+        }
+        return PG_OK;
+    }
     if (tc_ok) {
         if (kF32) {
             int rc = split3_launch(reinterpret_cast<const float*>(p->x), reinterpret_cast<float*>(p->ws_x),
@@ -701,6 +761,26 @@ static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream) {
 }
 
 }  // namespace pg
+
+extern "C" int pggan_conv_kernel_kind(const pg_conv_params* p) {
+    using namespace pg;
+    if (p == nullptr || p->B <= 0 || p->H <= 0 || p->W <= 0 || p->C <= 0 || p->N <= 0) return PG_CONV_KIND_SIMT;
+    pg_conv_params q = *p;
+    // alignment checks only: absent pointers count as aligned
+    if (!q.x) q.x = reinterpret_cast<const void*>(uintptr_t(256));
+    if (!q.wp) q.wp = reinterpret_cast<const void*>(uintptr_t(256));
+    if (!q.y) q.y = reinterpret_cast<void*>(uintptr_t(256));
+    if (q.dtype == PG_F32) {
+        if (!q.ws_x) q.ws_x = reinterpret_cast<void*>(uintptr_t(256));
+        if (!q.ws_w) q.ws_w = reinterpret_cast<void*>(uintptr_t(256));
+    }
+    int kind = PG_CONV_KIND_SIMT;
+    if (q.dtype == PG_BF16)
+        conv_dispatch<__nv_bfloat16>(&q, nullptr, &kind);
+    else if (q.dtype == PG_F32)
+        conv_dispatch<float>(&q, nullptr, &kind);
+    return kind;
+}
 
 extern "C" int pggan_conv_fprop(const pg_conv_params* p, void* stream) {
     using namespace pg;

@@ -196,10 +196,19 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 const uint32_t acc = it % ACC;
                 const size_t pix = (static_cast<size_t>(b) * a.H + (y0 + i)) * a.W + seg * kRowPix + r;
                 const size_t off = pix * a.N;
+                constexpr int CH = BLOCK_N >= 32 ? 32 : 16;
+                constexpr int MV = CH / 8;                   // 16-byte mask vectors per step
+                // dgrad mask: fetched one step ahead of its use (the first step's before the accumulator wait)
+                const bool masked = a.mask_src != nullptr;
+                uint4 mcur[MV];
+                if (masked) {
+                    const uint4* mp = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(a.mask_src) + off);
+#pragma unroll
+                    for (int c = 0; c < MV; ++c) mcur[c] = __ldg(mp + c);
+                }
                 mbar_wait(&tfull_bar[acc], (it / ACC) & 1);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
-                constexpr int CH = BLOCK_N >= 32 ? 32 : 16;
 #pragma unroll 1
                 for (int j = 0; j < BLOCK_N / CH; ++j) {
                     __syncwarp();
@@ -208,6 +217,12 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         tmem_ld32(taddr + j * 32, rr);
                     } else {
                         tmem_ld16(taddr + j * 16, rr);
+                    }
+                    uint4 mnxt[MV];
+                    if (masked && j + 1 < BLOCK_N / CH) {
+                        const uint4* mp = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(a.mask_src) + off + (j + 1) * CH);
+#pragma unroll
+                        for (int c = 0; c < MV; ++c) mnxt[c] = __ldg(mp + c);
                     }
                     tmem_ld_wait();
                     float v[32];
@@ -218,16 +233,16 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         t *= a.scale;
                         v[e] = lrelu_f(t, a.slope);
                     }
-                    if (a.mask_src != nullptr) {
-                        const T* mp = reinterpret_cast<const T*>(a.mask_src) + off + j * CH;
+                    if (masked) {
 #pragma unroll
-                        for (int c = 0; c < CH / 8; ++c) {
-                            uint4 raw = __ldg(reinterpret_cast<const uint4*>(mp) + c);
-                            const T* mv = reinterpret_cast<const T*>(&raw);
+                        for (int c = 0; c < MV; ++c) {
+                            const T* mv = reinterpret_cast<const T*>(&mcur[c]);
 #pragma unroll
                             for (int e = 0; e < 8; ++e)
                                 if (!(__bfloat162float(mv[e]) > 0.f)) v[c * 8 + e] *= a.mask_slope;
                         }
+#pragma unroll
+                        for (int c = 0; c < MV; ++c) mcur[c] = mnxt[c];
                     }
                     if (a.out_dtype == PG_BF16) {
                         __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(a.y) + off + j * CH;

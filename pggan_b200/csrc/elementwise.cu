@@ -85,8 +85,8 @@ __global__ void axpby_kernel(const T* __restrict__ a, const T* __restrict__ b, T
 // ------------------------------------------------------------------------ upsample / pool
 // one thread per (input pixel, 16-byte channel vector): read once, write the 2x2 block
 template <typename T>
-__global__ void upsample2x_kernel(const T* __restrict__ x, T* __restrict__ out, int B, int H, int W, int CV,
-                                  float scale) {
+__global__ void upsample2x_kernel(const T* __restrict__ x, const T* __restrict__ mask_src, T* __restrict__ out, int B,
+                                  int H, int W, int CV, float scale, float slope) {
     constexpr int VN = V16<T>::N;
     const long long total = static_cast<long long>(B) * H * W * CV;
     const long long C = static_cast<long long>(CV) * VN;
@@ -101,11 +101,26 @@ __global__ void upsample2x_kernel(const T* __restrict__ x, T* __restrict__ out, 
 #pragma unroll
             for (int e = 0; e < VN; ++e) v.set(e, v.get(e) * scale);
         }
-        T* o = out + ((b * 2 * H + 2 * h) * 2 * W + 2 * w) * C + cv * VN;
-        st16(o, v);
-        st16(o + C, v);
-        st16(o + 2 * W * C, v);
-        st16(o + 2 * W * C + C, v);
+        const long long ooff = ((b * 2 * H + 2 * h) * 2 * W + 2 * w) * C + cv * VN;
+        T* o = out + ooff;
+        if (mask_src == nullptr) {
+            st16(o, v);
+            st16(o + C, v);
+            st16(o + 2 * W * C, v);
+            st16(o + 2 * W * C + C, v);
+        } else {
+            // avg-pool backward fused with the LeakyReLU backward of the pooled activation (mask_src = that
+            // activation, full resolution): out = up(x) * (mask_src > 0 ? 1 : slope)
+            const long long offs[4] = {0, C, 2 * W * C, 2 * W * C + C};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const V16<T> mv = ld16(mask_src + ooff + offs[k]);
+                V16<T> r;
+#pragma unroll
+                for (int e = 0; e < VN; ++e) r.set(e, mv.get(e) > 0.f ? v.get(e) : v.get(e) * slope);
+                st16(o + offs[k], r);
+            }
+        }
     }
 }
 
@@ -414,21 +429,36 @@ __global__ void __launch_bounds__(256) pack_oihw_f_kernel(const float* __restric
 // gradients back: gW[o][i][t] (+)= scale * sum_s acc[s][o][t][i]; grid (O), dynamic smem 9*I floats
 __global__ void __launch_bounds__(256) unpack_oihw_kernel(const float* __restrict__ acc, float* __restrict__ gW, int I,
                                                           int Ip, float scale, int accumulate, int slices,
-                                                          long long slice_elems) {
+                                                          long long slice_elems, int slices_per_block) {
     extern __shared__ float tile[];                        // [I][9]
     const int o = blockIdx.x;
     const float* src = acc + static_cast<size_t>(o) * 9 * Ip;
+    // many slices (wgrad_rows writes one per CTA): blockIdx.y owns a group of slices and the groups meet through
+    // atomics on gW (the caller has zeroed it when accumulate == 0)
+    const int sl0 = blockIdx.y * slices_per_block;
+    const int sl1 = (sl0 + slices_per_block < slices) ? (sl0 + slices_per_block) : slices;
     for (int k = threadIdx.x; k < 9 * Ip; k += blockDim.x) {
         const int t = k / Ip, i = k - t * Ip;
         if (i < I) {
-            float v = __ldg(src + k);
-            for (int sl = 1; sl < slices; ++sl) v += __ldg(src + sl * slice_elems + k);
-            tile[i * 9 + t] = v * scale;
+            float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+            int sl = sl0;
+            for (; sl + 4 <= sl1; sl += 4) {
+                v0 += __ldg(src + (sl + 0) * slice_elems + k);
+                v1 += __ldg(src + (sl + 1) * slice_elems + k);
+                v2 += __ldg(src + (sl + 2) * slice_elems + k);
+                v3 += __ldg(src + (sl + 3) * slice_elems + k);
+            }
+            for (; sl < sl1; ++sl) v0 += __ldg(src + sl * slice_elems + k);
+            tile[i * 9 + t] = ((v0 + v1) + (v2 + v3)) * scale;
         }
     }
     __syncthreads();
     float* dst = gW + static_cast<size_t>(o) * I * 9;
     const int n = I * 9;
+    if (gridDim.y > 1) {
+        for (int k = threadIdx.x; k < n; k += blockDim.x) atomicAdd(dst + k, tile[k]);
+        return;
+    }
     if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
         for (int k = threadIdx.x; k < n / 4; k += blockDim.x) {
             float4 v = reinterpret_cast<const float4*>(tile)[k];
@@ -625,19 +655,31 @@ extern "C" int pggan_axpby(const void* a, const void* b, void* out, int64_t n, f
     return PG_OK;
 }
 
-extern "C" int pggan_upsample2x(const void* x, void* out, int B, int H, int W, int C, float scale, int dtype,
-                                void* stream) {
-    PG_CHECK(x && out && B > 0 && H > 0 && W > 0 && C > 0, PG_ERR_ARG, "pggan_upsample2x: bad args");
-    PG_CHECK(al16(x) && al16(out), PG_ERR_ARG, "pggan_upsample2x: pointers must be 16-byte aligned");
+static int upsample2x_impl(const void* x, const void* mask_src, void* out, int B, int H, int W, int C, float scale,
+                           float slope, int dtype, void* stream, const char* who) {
+    PG_CHECK(x && out && B > 0 && H > 0 && W > 0 && C > 0, PG_ERR_ARG, "%s: bad args", who);
+    PG_CHECK(al16(x) && al16(out) && (!mask_src || al16(mask_src)), PG_ERR_ARG, "%s: pointers must be 16-byte aligned", who);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     DISPATCH_T(dtype, {
-        PG_CHECK(C % V16<T>::N == 0, PG_ERR_UNSUPPORTED, "pggan_upsample2x: C=%d must be a multiple of %d", C, V16<T>::N);
+        PG_CHECK(C % V16<T>::N == 0, PG_ERR_UNSUPPORTED, "%s: C=%d must be a multiple of %d", who, C, V16<T>::N);
         const int CV = C / V16<T>::N;
-        upsample2x_kernel<T><<<ew_grid((long long)B * H * W * CV, 256), 256, 0, s>>>((const T*)x, (T*)out, B, H, W, CV, scale);
+        upsample2x_kernel<T><<<ew_grid((long long)B * H * W * CV, 256), 256, 0, s>>>((const T*)x, (const T*)mask_src, (T*)out,
+                                                                                     B, H, W, CV, scale, slope);
     });
     PG_LAUNCH_CHECK();
     g_other_launches++;
     return PG_OK;
+}
+
+extern "C" int pggan_upsample2x(const void* x, void* out, int B, int H, int W, int C, float scale, int dtype,
+                                void* stream) {
+    return upsample2x_impl(x, nullptr, out, B, H, W, C, scale, 1.f, dtype, stream, "pggan_upsample2x");
+}
+
+extern "C" int pggan_upsample2x_mask(const void* x, const void* mask_src, void* out, int B, int H, int W, int C,
+                                     float scale, float slope, int dtype, void* stream) {
+    PG_CHECK(mask_src != nullptr, PG_ERR_ARG, "pggan_upsample2x_mask: null mask_src");
+    return upsample2x_impl(x, mask_src, out, B, H, W, C, scale, slope, dtype, stream, "pggan_upsample2x_mask");
 }
 
 extern "C" int pggan_pool2x2(const void* x, const void* blend_with, void* out, int B, int H, int W, int C, float scale,
@@ -818,10 +860,16 @@ extern "C" int pggan_unpack_wgrad(const float* in, float* out, const pg_pack_map
     const bool oihw_f = m.taps == 9 && m.n2 == 1 && m.c2 == 1 && m.base == 0 && m.s_t == 1 && m.s_c1 == 9 &&
                         m.s_n1 == 9LL * m.c_valid && m.n_valid == m.n_total && m.c_total <= kPackMaxI;
     const long long slice_elems = (long long)m.n_total * m.taps * m.c_total;
-    if (oihw_f)
-        unpack_oihw_kernel<<<m.n_total, 256, 9 * m.c_valid * sizeof(float), s>>>(in, out, m.c_valid, m.c_total, scale, accumulate,
-                                                                              slices, slice_elems);
-    else
+    if (oihw_f) {
+        int spb = slices, groups = 1;
+        if (slices > 32 && m.n_total < 2 * num_sms()) {      // few, long reductions: spread the slices over the SMs
+            spb = 16;
+            groups = (slices + spb - 1) / spb;
+            if (!accumulate) PG_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)m.n_total * 9 * m.c_valid, s));
+        }
+        unpack_oihw_kernel<<<dim3(m.n_total, groups), 256, 9 * m.c_valid * sizeof(float), s>>>(
+            in, out, m.c_valid, m.c_total, scale, accumulate, slices, slice_elems, spb);
+    } else
         unpack_wgrad_kernel<<<ew_grid(total, 256), 256, 0, s>>>(in, out, m, total, scale, accumulate, slices, slice_elems);
     PG_LAUNCH_CHECK();
     g_other_launches++;

@@ -53,8 +53,10 @@ class ConstrainedLayer(nn.Module):
     def scale(self) -> float:
         return float(self.weight) if self.equalized else 1.0
 
-    def fused(self, x, slope=1.0, raw_out=False, pixel_norm_eps=None, layout=None):
-        """lrelu(c*(W x + b), slope) [+ pixel norm if pixel_norm_eps is given] on the fused kernels"""
+    def fused(self, x, slope=1.0, raw_out=False, pixel_norm_eps=None, layout=None, x_act_slope=None,
+              defer_mask=False):
+        """lrelu(c*(W x + b), slope) [+ pixel norm if pixel_norm_eps is given] on the fused kernels.
+        x_act_slope / defer_mask: LeakyReLU-backward fusion hints, see ops.ConvF."""
         m = self.module
         W, b = m.weight, m.bias
         c = self.scale()
@@ -68,14 +70,14 @@ class ConstrainedLayer(nn.Module):
                 or m.padding != (k // 2, k // 2) or k not in (1, 3):
             raise NotImplementedError("only 3x3/pad 1 and 1x1/pad 0 stride-1 convolutions are on the PGGAN path")
         if k == 1 and W.shape[1] <= 4:                       # fromRGB-shaped: image in, features out
-            return ops.RgbExpand.apply(x, W.view(W.shape[0], W.shape[1]), b, False, c, float(slope))
+            return ops.RgbExpand.apply(x, W.view(W.shape[0], W.shape[1]), b, False, c, float(slope), bool(defer_mask))
         if k == 1 and W.shape[0] <= 4:                       # toRGB-shaped: features in, image out
             if slope != 1.0:
                 raise NotImplementedError("toRGB-shaped 1x1 convolutions have no fused activation")
             return ops.RgbReduce.apply(x, W.view(W.shape[0], W.shape[1]).t(), b, False, c, 1.0)
         if pixel_norm_eps is not None:
             return ops.ConvActPN.apply(x, W, b, c, float(slope), float(pixel_norm_eps), layout)
-        return ops.ConvF.apply(x, W, b, c, float(slope), raw_out, layout)
+        return ops.ConvF.apply(x, W, b, c, float(slope), raw_out, layout, x_act_slope, bool(defer_mask))
 
     def forward(self, x):
         return self.fused(x, 1.0)

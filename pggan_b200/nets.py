@@ -167,12 +167,14 @@ class Discriminator(nn.Module):
         x_down = None
         if len(self.blocks):
             x_down = self.fromRGB_blocks[-2](img, apply_downscale=True)
-        x = self.fromRGB_blocks[-1](img)
+        # with blocks present, fromRGB's LeakyReLU backward is applied by the first block's conv1 dgrad epilogue
+        fuse_rgb = len(self.blocks) > 0 and self.blocks[-1].first_dgrad_fuses_mask(img.shape[0], img.shape[2], img.shape[3])
+        x = self.fromRGB_blocks[-1](img, defer_mask=fuse_rgb)
         apply_merge = len(self.blocks) > 0
         for block in reversed(self.blocks):
             if apply_merge:
                 apply_merge = False
-                x = block(x, blend_with=x_down, alpha=float(self.alpha))
+                x = block(x, blend_with=x_down, alpha=float(self.alpha), x_act_slope=0.2 if fuse_rgb else None)
             else:
                 x = block(x)
         x = self.minibatch_normalization_block(x)

@@ -256,6 +256,26 @@ def k_conv(x, wp, bias, N, taps, scale, slope=1.0, mask_src=None, mask_slope=1.0
     return y
 
 
+_KIND_CACHE: dict = {}
+
+
+def dgrad_mask_fusable(batch, h, w, fwd_in_channels, fwd_out_channels, taps=9, dtype=None) -> bool:
+    """True if the dgrad of a (fwd_in_channels -> fwd_out_channels) conv at this size runs on a kernel whose epilogue
+    applies a LeakyReLU-backward mask for free (see pggan_conv_kernel_kind); the blocks use it to decide whether a
+    producer may defer its mask to this layer's dgrad."""
+    dtype = dtype or _COMPUTE_DTYPE
+    key = (batch, h, w, fwd_in_channels, fwd_out_channels, taps, dtype)
+    hit = _KIND_CACHE.get(key)
+    if hit is None:
+        p = L.ConvParams()
+        p.B, p.H, p.W, p.C, p.N, p.taps = batch, h, w, fwd_out_channels, fwd_in_channels, taps     # dgrad: roles swapped
+        p.dtype = _enum(dtype)
+        p.out_dtype = _enum(dtype)
+        hit = L.load().pggan_conv_kernel_kind(ctypes.byref(p)) in (L.PG_CONV_KIND_PLAIN, L.PG_CONV_KIND_ROWS)
+        _KIND_CACHE[key] = hit
+    return hit
+
+
 def k_wgrad(g, x, scale, wshape, layout=None, accumulate_into=None):
     """weight gradient in the parameter's own fp32 layout: a new tensor, or added into `accumulate_into`"""
     _need_cuda(g)
@@ -333,9 +353,13 @@ def k_colsum(g, scale):
     return out
 
 
-def k_upsample(x, scale):
+def k_upsample(x, scale, mask_src=None, slope=1.0):
     b, c, h, w = _dims(x)
     out = _new_like_layout(x, c, x.dtype, 2 * h, 2 * w)
+    if mask_src is not None:
+        L.check(L.load().pggan_upsample2x_mask(_p(x), _p(mask_src), _p(out), b, h, w, c, float(scale), float(slope),
+                                               _enum(x.dtype), _s()), "pggan_upsample2x_mask")
+        return out
     L.check(L.load().pggan_upsample2x(_p(x), _p(out), b, h, w, c, float(scale), _enum(x.dtype), _s()),
             "pggan_upsample2x")
     return out
@@ -367,16 +391,24 @@ def _perm_bias(b, layout, inverse=False):
 
 
 class ConvF(torch.autograd.Function):
-    """y = lrelu(scale * (conv(x, W) + b), slope)   [fprop; slope = 1 -> linear]"""
+    """y = lrelu(scale * (conv(x, W) + b), slope)   [fprop; slope = 1 -> linear]
+
+    LeakyReLU-backward fusion (the mask is sign(stored activation), so whoever holds the activation can apply it):
+      x_act_slope : x is the LeakyReLU output of a producer that was run with defer_mask=True; this layer's dgrad
+                    epilogue then applies that producer's mask to gx (no separate leaky_relu_backward pass).
+      defer_mask  : the consumer of y applies THIS layer's mask (a ConvF with x_act_slope, or a pooling Function
+                    with act_slope): the incoming gradient is already masked and y need not be saved."""
 
     @staticmethod
-    def forward(ctx, x, W, b, scale, slope, raw_out, layout=None):
+    def forward(ctx, x, W, b, scale, slope, raw_out, layout=None, x_act_slope=None, defer_mask=False):
         x = feat(x)
         N, C, taps, _, _ = _maps(W.shape, layout)
         bias = None if b is None else _perm_bias(b.detach().float(), layout).contiguous()
         y = k_conv(x, _pack(W, "f", x.dtype, layout), bias, N, taps, scale, slope, raw_out=raw_out)
-        ctx.save_for_backward(x, W, y if slope != 1.0 else None)
+        ctx.mask_here = slope != 1.0 and not defer_mask
+        ctx.save_for_backward(x, W, y if ctx.mask_here else None)
         ctx.scale, ctx.slope, ctx.has_bias, ctx.layout = scale, slope, b is not None, layout
+        ctx.x_act_slope = x_act_slope
         ctx.bias_param = b if isinstance(b, torch.nn.Parameter) else None
         return y
 
@@ -387,9 +419,10 @@ class ConvF(torch.autograd.Function):
         need_w = ctx.needs_input_grad[1] and not _SKIP_PARAM_GRADS
         need_b = ctx.has_bias and ctx.needs_input_grad[2] and not _SKIP_PARAM_GRADS
         gx = gW = gb = None
+        xm, xs = (x, ctx.x_act_slope) if ctx.x_act_slope is not None else (None, 1.0)
         if torch.is_grad_enabled():
             # create_graph=True: stay composable (every piece is a differentiable Function)
-            if ctx.slope != 1.0:
+            if ctx.mask_here:
                 g = MaskMul.apply(g, y, ctx.slope)
             if need_b:
                 gb = ColSum.apply(g, ctx.scale)
@@ -397,22 +430,22 @@ class ConvF(torch.autograd.Function):
             # plain backward: LeakyReLU mask and bias gradient in one pass over g; gradients of registered
             # parameters are accumulated in place (see _GRAD_SINK)
             b_sink = _sink(ctx.bias_param) if (need_b and not (ctx.layout and ctx.layout[0] == "lin_out_perm")) else None
-            g, gb = k_mask_colsum(g, y if ctx.slope != 1.0 else None, ctx.slope, True,
+            g, gb = k_mask_colsum(g, y if ctx.mask_here else None, ctx.slope, True,
                                   ctx.scale if need_b else None, colsum_into=b_sink)
             if gb is not None:
                 gb = _perm_bias(gb, ctx.layout, inverse=True)
             if ctx.needs_input_grad[0]:
-                gx = ConvT.apply(g, W, ctx.scale, ctx.layout)
+                gx = ConvT.apply(g, W, ctx.scale, ctx.layout, xm, xs)
             if need_w:
                 gW = k_wgrad(g, x, ctx.scale, tuple(W.shape), ctx.layout, accumulate_into=_sink(W))
-            return gx, gW, gb, None, None, None, None
+            return gx, gW, gb, None, None, None, None, None, None
         if gb is not None:
             gb = _perm_bias(gb, ctx.layout, inverse=True)
         if ctx.needs_input_grad[0]:
-            gx = ConvT.apply(g, W, ctx.scale, ctx.layout)
+            gx = ConvT.apply(g, W, ctx.scale, ctx.layout, xm, xs)
         if need_w:
             gW = ConvW.apply(g, x, ctx.scale, tuple(W.shape), ctx.layout)
-        return gx, gW, gb, None, None, None, None
+        return gx, gW, gb, None, None, None, None, None, None
 
 
 class ConvActPN(torch.autograd.Function):
@@ -468,24 +501,28 @@ class ConvT(torch.autograd.Function):
     """gx = scale * conv_transpose(g, W)   [dgrad: the same kernel on flipped/transposed weights]"""
 
     @staticmethod
-    def forward(ctx, g, W, scale, layout=None):
+    def forward(ctx, g, W, scale, layout=None, mask_src=None, mask_slope=1.0):
+        """mask_src: gx is additionally multiplied by (mask_src > 0 ? 1 : mask_slope) in the GEMM epilogue
+        (the LeakyReLU backward of the layer that produced this conv's input)."""
         g = feat(g)
         N, C, taps, _, _ = _maps(W.shape, layout)
-        gx = k_conv(g, _pack(W, "t", g.dtype, layout), None, C, taps, scale)
-        ctx.save_for_backward(g, W)
-        ctx.scale, ctx.layout = scale, layout
+        gx = k_conv(g, _pack(W, "t", g.dtype, layout), None, C, taps, scale, mask_src=mask_src, mask_slope=mask_slope)
+        ctx.save_for_backward(g, W, mask_src)
+        ctx.scale, ctx.layout, ctx.mask_slope = scale, layout, mask_slope
         return gx
 
     @staticmethod
     def backward(ctx, ggx):
-        g, W = ctx.saved_tensors
+        g, W, mask_src = ctx.saved_tensors
         ggx = feat(ggx)
+        if mask_src is not None:
+            ggx = MaskMul.apply(ggx, mask_src, ctx.mask_slope)
         dg = dW = None
         if ctx.needs_input_grad[0]:
             dg = ConvF.apply(ggx, W, None, ctx.scale, 1.0, False, ctx.layout)
         if ctx.needs_input_grad[1] and not _SKIP_PARAM_GRADS:
             dW = ConvW.apply(g, ggx, ctx.scale, tuple(W.shape), ctx.layout)
-        return dg, dW, None, None
+        return dg, dW, None, None, None, None
 
 
 class ConvW(torch.autograd.Function):
@@ -556,34 +593,66 @@ class Upsample2x(torch.autograd.Function):
         return Pool2x2.apply(feat(g), ctx.scale), None
 
 
-class Pool2x2(torch.autograd.Function):
-    """scale * (2x2 window sum); scale = 0.25 is nn.AvgPool2d(2) (reference lib/blocks.py:193)"""
+class UpsampleMask(torch.autograd.Function):
+    """scale * up2(g) * (y > 0 ? 1 : slope): avg-pool backward fused with the LeakyReLU backward of the pooled
+    activation y (one pass instead of two)"""
 
     @staticmethod
-    def forward(ctx, x, scale):
-        ctx.scale = scale
-        return k_pool(feat(x), scale)
+    def forward(ctx, g, y, scale, slope):
+        ctx.save_for_backward(y)
+        ctx.scale, ctx.slope = scale, slope
+        return k_upsample(feat(g), scale, mask_src=y, slope=slope)
+
+    @staticmethod
+    def backward(ctx, gg):
+        (y,) = ctx.saved_tensors
+        return Pool2x2.apply(MaskMul.apply(feat(gg), y, ctx.slope), ctx.scale), None, None, None
+
+
+class Pool2x2(torch.autograd.Function):
+    """scale * (2x2 window sum); scale = 0.25 is nn.AvgPool2d(2) (reference lib/blocks.py:193).
+    act_slope: x is the LeakyReLU output of a ConvF run with defer_mask=True — its mask is applied here, in backward."""
+
+    @staticmethod
+    def forward(ctx, x, scale, act_slope=None):
+        x = feat(x)
+        ctx.scale, ctx.act_slope = scale, act_slope
+        if act_slope is not None:
+            ctx.save_for_backward(x)
+        return k_pool(x, scale)
 
     @staticmethod
     def backward(ctx, g):
-        return Upsample2x.apply(feat(g), ctx.scale), None
+        if ctx.act_slope is not None:
+            (x,) = ctx.saved_tensors
+            return UpsampleMask.apply(feat(g), x, ctx.scale, ctx.act_slope), None, None
+        return Upsample2x.apply(feat(g), ctx.scale), None, None
 
 
 class PoolBlend(torch.autograd.Function):
     """(1-alpha) * low + alpha * avgpool2(x): D's feature-space fade fused with the pooling
-    (reference lib/blocks.py:193 + pggan/nets.py:262-265)"""
+    (reference lib/blocks.py:193 + pggan/nets.py:262-265).  act_slope as in Pool2x2."""
 
     @staticmethod
-    def forward(ctx, x, low, alpha):
-        ctx.alpha = alpha
-        return k_pool(feat(x), 0.25, blend_with=feat(low), alpha=alpha)
+    def forward(ctx, x, low, alpha, act_slope=None):
+        x = feat(x)
+        ctx.alpha, ctx.act_slope = alpha, act_slope
+        if act_slope is not None:
+            ctx.save_for_backward(x)
+        return k_pool(x, 0.25, blend_with=feat(low), alpha=alpha)
 
     @staticmethod
     def backward(ctx, g):
         g = feat(g)
-        gx = Upsample2x.apply(g, 0.25 * ctx.alpha) if ctx.needs_input_grad[0] else None
+        gx = None
+        if ctx.needs_input_grad[0]:
+            if ctx.act_slope is not None:
+                (x,) = ctx.saved_tensors
+                gx = UpsampleMask.apply(g, x, 0.25 * ctx.alpha, ctx.act_slope)
+            else:
+                gx = Upsample2x.apply(g, 0.25 * ctx.alpha)
         gl = Scale.apply(g, 1.0 - ctx.alpha) if ctx.needs_input_grad[1] else None
-        return gx, gl, None
+        return gx, gl, None, None
 
 
 class Scale(torch.autograd.Function):
@@ -680,13 +749,15 @@ class RgbExpand(torch.autograd.Function):
     Wc is [C, cimg] fp32.  (fromRGBBlock, reference lib/blocks.py:285-292)"""
 
     @staticmethod
-    def forward(ctx, img, Wc, bias, pool, scale, slope):
+    def forward(ctx, img, Wc, bias, pool, scale, slope, defer_mask=False):
+        """defer_mask: the consumer (a ConvF with x_act_slope) applies this layer's LeakyReLU mask in its dgrad"""
         img = _img(img)
         _need_cuda(img)
         wc = Wc.detach().float().contiguous()
         bs = None if bias is None else bias.detach().float().contiguous()
         y = _k_rgb_expand(img, wc, bs, wc.shape[0], pool, scale, slope, _COMPUTE_DTYPE)
-        ctx.save_for_backward(img, Wc, y if slope != 1.0 else None)
+        ctx.mask_here = slope != 1.0 and not defer_mask
+        ctx.save_for_backward(img, Wc, y if ctx.mask_here else None)
         ctx.pool, ctx.scale, ctx.slope, ctx.has_bias = pool, scale, slope, bias is not None
         return y
 
@@ -698,7 +769,7 @@ class RgbExpand(torch.autograd.Function):
         need_b = ctx.has_bias and ctx.needs_input_grad[2] and not _SKIP_PARAM_GRADS
         gimg = gW = gb = None
         if torch.is_grad_enabled():
-            if ctx.slope != 1.0:
+            if ctx.mask_here:
                 g = MaskMul.apply(g, y, ctx.slope)
             if ctx.needs_input_grad[0]:
                 gimg = RgbReduce.apply(g, Wc, None, ctx.pool, ctx.scale, 0.25)
@@ -706,8 +777,8 @@ class RgbExpand(torch.autograd.Function):
                 gW = RgbWgrad.apply(g, img, ctx.pool, ctx.scale)
             if need_b:
                 gb = ColSum.apply(g, ctx.scale)
-            return gimg, gW, gb, None, None, None
-        if ctx.slope != 1.0:
+            return gimg, gW, gb, None, None, None, None
+        if ctx.mask_here:
             g = k_mask_mul(g, y, ctx.slope)
         if ctx.needs_input_grad[0]:
             wr = Wc.detach().float().t().contiguous()
@@ -718,7 +789,7 @@ class RgbExpand(torch.autograd.Function):
                 gW = None
             if not need_b:
                 gb = None
-        return gimg, gW, gb, None, None, None
+        return gimg, gW, gb, None, None, None, None
 
 
 class RgbReduce(torch.autograd.Function):

@@ -109,11 +109,13 @@ def test_conv_fprop(shape, backend, dtype):
 
 
 @pytest.mark.parametrize("dtype", DT)
-def test_conv_mask_and_raw_out(dtype):
+@pytest.mark.parametrize("shape", [(2, 16, 16, 64, 128), (1, 32, 128, 64, 64), (1, 16, 256, 16, 32), (2, 32, 32, 128, 64)])
+def test_conv_mask_and_raw_out(shape, dtype):
+    """epilogue mask (dgrad fused with a LeakyReLU backward) and fp32 raw output on the plain, rows and swapped kernels"""
     from pggan_b200 import ops
     import pggan_b200 as pg
     pg.set_compute_dtype(dtype)
-    B, H, W, Ci, Co = 2, 16, 16, 64, 128
+    B, H, W, Ci, Co = shape
     x = rnd(torch.randn(B, Ci, H, W, device="cuda"), dtype)
     w = rnd(torch.randn(Co, Ci, 3, 3, device="cuda"), dtype)
     ysrc = torch.randn(B, Co, H, W, device="cuda")
