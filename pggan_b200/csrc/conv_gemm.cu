@@ -725,7 +725,9 @@ static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream, int* k
         int bn = 16;
         double best = 1e30;
         const int cands[5] = {256, 128, 64, 32, 16};
-        const double cost[5] = {1.0, 0.56, 0.36, 0.30, 0.28};
+        // measured (tools/sweep_bn.sh, 32^2 512->512): 1510 / 915 / 497 / 256 TFLOP/s for N = 256 / 128 / 64 / 32, i.e. a
+        // tile's time barely shrinks with N (the 128-row A operand read paces every MMA)
+        const double cost[5] = {1.0, 0.83, 0.76, 0.74, 0.73};
         for (int i = 0; i < 5; ++i) {
             if (p->N % cands[i] != 0) continue;
             const long long tiles = m_tiles * (p->N / cands[i]);

@@ -16,10 +16,20 @@
 //   * accumulators are 4-deep in TMEM; 4 epilogue warps apply bias/He scale/LeakyReLU/(dgrad mask) and store NHWC.
 // Each input byte is read from L2/HBM ~once (+ 2 halo rows per strip, + 2 halo pixels per row).
 //
+// Pixel grouping (J = 4 for 16 channels, J = 2 for 32): one tcgen05.mma costs ~128 cycles whatever its N (the 128-row
+// A operand is read from smem at 32 B/clk), so a 16-channel layer issuing 9 MMAs of K = 16 per 128 pixels is bound by
+// the MMA count.  With J > 1 the NHWC tensor is VIEWED as [B][H][W/J][J*C = 64]: an MMA row is a group of J pixels,
+// its N dimension the J*N outputs of the group, and the filter becomes a 3 x 3 filter over groups whose [J*N x 64]
+// tiles are Toeplitz expansions of the 3x3 weights (built in smem at kernel start).  The left / right group taps
+// only touch one pixel of the neighbour group, so only those K-steps are issued: 3*(J+2)*C/16 MMAs per 128*J pixels
+// instead of 9*J*C/16 — 2x fewer at C = 16, 1.5x at C = 32 — and the same epilogue (a thread stores J*N contiguous
+// channels-of-the-group = the NHWC bytes of J pixels).
+//
 // Replaces the same reference code as conv_gemm.cu (EqualizedConv2d 3x3 fprop / dgrad, lib/layers.py:58-63,86-89).
 #include "common.cuh"
 
 #include <atomic>
+#include <stdlib.h>
 
 namespace pg {
 
@@ -32,7 +42,9 @@ struct RowsKArgs {
     const float* bias;
     const void* mask_src;
     void* y;
-    int B, H, W, N, C;
+    const __nv_bfloat16* wp;   // packed [Nr][9][Cr] weights (only read by the grouped variant)
+    int Nr;                    // real output channels (bias index = column % Nr)
+    int B, H, W, N, C;         // in GROUP units when J > 1: W = pixels/J per row, N = J*Nr, C = 64
     int nseg;                // W / 128
     long long total;         // B * nseg * H row segments
     long long per_cta;
@@ -59,10 +71,11 @@ template <int SPAN, int BLOCK_N> struct RowsCfg {
     static_assert(kTmemCols <= 512, "TMEM");
 };
 
-template <int SPAN, int BLOCK_N>
+template <int SPAN, int BLOCK_N, int J = 1>
 __global__ void __launch_bounds__(kRowsThreads, 1)
 conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                  const RowsKArgs a) {
+    static_assert(J == 1 || SPAN == 128, "pixel groups fill one 128-byte span");
     using Cfg = RowsCfg<SPAN, BLOCK_N>;
     using T = __nv_bfloat16;
     constexpr int R = Cfg::kRing;
@@ -102,6 +115,29 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    if constexpr (J > 1) {
+        // Toeplitz weight tiles, written straight into the SWIZZLE_128B K-major layout (16-byte chunk q of row r
+        // lives at chunk q ^ (r & 7)); tile t = (dy, group tap gx), row = (pixel j of the group, n),
+        // K = (pixel j' of the input group, c):  w[n][dy][dx][c] with dx = gx*J + j' - j + 1 if that is a tap
+        constexpr int CS = 4 / J;                        // 32-byte K-steps per real pixel (C/16)
+        constexpr int Cr = 64 / J;
+        const int Nr = BLOCK_N / J;
+        for (int idx = threadIdx.x; idx < 9 * BLOCK_N * 8; idx += kRowsThreads) {
+            const int qq = idx & 7;
+            const int row = (idx >> 3) % BLOCK_N;
+            const int t = idx / (8 * BLOCK_N);
+            const int dy = t / 3, gx = t % 3 - 1;
+            const int j = row / Nr, n = row - j * Nr;
+            const int k = qq >> 1, half = qq & 1;
+            const int jp = k / CS, cs = k - jp * CS;
+            const int dx = gx * J + jp - j + 1;
+            uint4 val = make_uint4(0, 0, 0, 0);
+            if (dx >= 0 && dx <= 2)
+                val = __ldg(reinterpret_cast<const uint4*>(a.wp + (static_cast<size_t>(n) * 9 + dy * 3 + dx) * Cr + cs * 16 + half * 8));
+            *reinterpret_cast<uint4*>(sw + t * kWTile + row * 128 + ((qq ^ (row & 7)) << 4)) = val;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy stores -> UMMA (async proxy) reads
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -114,8 +150,10 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0 && u_begin < u_end) {
-            mbar_arrive_expect_tx(w_bar, Cfg::kWBytes);
-            for (int t = 0; t < 9; ++t) tma_load_2d(sw + t * kWTile, &tmap_w, w_bar, t * a.C, 0);
+            if constexpr (J == 1) {
+                mbar_arrive_expect_tx(w_bar, Cfg::kWBytes);
+                for (int t = 0; t < 9; ++t) tma_load_2d(sw + t * kWTile, &tmap_w, w_bar, t * a.C, 0);
+            }
             uint32_t L = 0;                 // running count of input rows loaded
             long long u = u_begin;
             while (u < u_end) {
@@ -138,8 +176,10 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         // -------------------------------------------------------------------- MMA issuer
         if (lane == 0 && u_begin < u_end) {
             constexpr uint32_t idesc = make_idesc(1, 0, 0, kRowPix, BLOCK_N);
-            mbar_wait(w_bar, 0);
-            tc_fence_after();
+            if constexpr (J == 1) {
+                mbar_wait(w_bar, 0);
+                tc_fence_after();
+            }
             const uint32_t sw_addr = smem_u32(sw);
             const uint32_t ring_addr = smem_u32(ring);
             uint32_t L = 0, it = 0;
@@ -165,9 +205,14 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         for (int dx = 0; dx < 3; ++dx) {
                             const uint64_t adesc = make_smem_desc(row_addr + dx * SPAN, 16, kSBO, kLayout);
                             const uint64_t bdesc = make_smem_desc(sw_addr + (dy * 3 + dx) * kWTile, 16, kSBO, kLayout);
+                            // grouped: the left / right group taps only reach the neighbour group's last / first pixel
+                            constexpr int CSK = J > 1 ? 4 / J : kMmaPerTap;
+                            const int k0 = (J > 1 && dx == 0) ? kMmaPerTap - CSK : 0;
+                            const int k1 = (J > 1 && dx == 2) ? CSK : kMmaPerTap;
 #pragma unroll
                             for (int k = 0; k < kMmaPerTap; ++k)
-                                umma_ss<false>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (dy | dx | k) != 0);
+                                if (k >= k0 && k < k1)
+                                    umma_ss<false>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (dy | dx | (k - k0)) != 0);
                         }
                     }
                     umma_commit(&tfull_bar[acc]);
@@ -229,7 +274,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #pragma unroll
                     for (int e = 0; e < CH; ++e) {
                         float t = __uint_as_float(rr[e]);
-                        if (a.bias != nullptr) t += __ldg(a.bias + j * CH + e);
+                        if (a.bias != nullptr) t += __ldg(a.bias + ((j * CH + e) & (a.Nr - 1)));
                         t *= a.scale;
                         v[e] = lrelu_f(t, a.slope);
                     }
@@ -283,13 +328,21 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     }
 }
 
-template <int SPAN, int BLOCK_N>
-static int launch_rows(const pg_conv_params* p, cudaStream_t stream) {
+template <int SPAN, int BLOCK_N, int J = 1>
+static int launch_rows(const pg_conv_params* p_in, cudaStream_t stream) {
     using Cfg = RowsCfg<SPAN, BLOCK_N>;
+    // J > 1: the same memory viewed as [B][H][W/J][J*C] -> [B][H][W/J][J*N]
+    pg_conv_params view = *p_in;
+    view.W = p_in->W / J;
+    view.C = p_in->C * J;
+    view.N = p_in->N * J;
+    const pg_conv_params* p = &view;
     RowsKArgs a;
     a.bias = p->bias;
     a.mask_src = p->mask_src;
     a.y = p->y;
+    a.wp = reinterpret_cast<const __nv_bfloat16*>(p->wp);
+    a.Nr = p_in->N;
     a.B = p->B; a.H = p->H; a.W = p->W; a.N = p->N; a.C = p->C;
     a.nseg = p->W / kRowPix;
     a.total = static_cast<long long>(p->B) * a.nseg * p->H;
@@ -308,15 +361,17 @@ static int launch_rows(const pg_conv_params* p, cudaStream_t stream) {
         int rc = encode_tmap(&tx, PG_BF16, 4, p->x, dims, strides, box, SPAN);
         if (rc != PG_OK) return rc;
     }
-    {
+    if (J == 1) {
         const uint64_t K = 9ull * p->C;
         uint64_t dims[2] = {K, (uint64_t)p->N};
         uint64_t strides[1] = {K * 2};
         uint32_t box[2] = {(uint32_t)p->C, (uint32_t)BLOCK_N};
         int rc = encode_tmap(&tw, PG_BF16, 2, p->wp, dims, strides, box, SPAN);
         if (rc != PG_OK) return rc;
+    } else {
+        tw = tx;                      // unused by the grouped variant (it builds its weight tiles itself)
     }
-    auto kern = conv_rows_kernel<SPAN, BLOCK_N>;
+    auto kern = conv_rows_kernel<SPAN, BLOCK_N, J>;
     static bool attr_done = false;
     if (!attr_done) {
         PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -337,6 +392,18 @@ bool conv_rows_supported(const pg_conv_params* p) {
 
 int conv_rows_launch(const pg_conv_params* p, cudaStream_t stream) {
     const int span = p->C * 2;
+    // pixel grouping for 16 / 32 channels when the grouped row still splits into 128-group segments
+    static const bool no_group = getenv("PGGAN_NO_GROUP") != nullptr;
+    if (!no_group && span < 128) {
+        const int J = 128 / span;
+        // (J*N = 128 measured slower than ungrouped: 147 KB of weight tiles leave a 4-row ring and a long epilogue)
+        if (p->W % (128 * J) == 0 && p->N * J <= 64) {
+            const int np = p->N * J;
+            if (J == 4 && np == 64) return launch_rows<128, 64, 4>(p, stream);
+            if (J == 2 && np == 32) return launch_rows<128, 32, 2>(p, stream);
+            if (J == 2 && np == 64) return launch_rows<128, 64, 2>(p, stream);
+        }
+    }
 #define PG_ROWS_CASE(S, BN) \
     if (span == S && p->N == BN) return launch_rows<S, BN>(p, stream);
     PG_ROWS_CASE(128, 16) PG_ROWS_CASE(128, 32) PG_ROWS_CASE(128, 64) PG_ROWS_CASE(128, 128)

@@ -71,34 +71,20 @@ rgb_expand_kernel(const float* __restrict__ img, const float* __restrict__ w, co
         br[e] = bias ? __ldg(bias + c) * scale : 0.f;
     }
     const int P = B * H * W;
-    constexpr int UNR = 4;                 // pixels in flight per thread: the image loads of all four are issued first
-    const int stride = gridDim.x * TY;
-    for (int pix0 = blockIdx.x * TY + ty; pix0 < P; pix0 += UNR * stride) {
-        float p[UNR][kMaxImgC];
+    for (int pix = blockIdx.x * TY + ty; pix < P; pix += gridDim.x * TY) {
+        int b, hh, ww;
+        pix_decomp(pix, H, W, b, hh, ww);
+        float p[kMaxImgC];
+        load_pixel(img, cimg, pool, b, hh, ww, H, W, p);
+        RV<T> o;
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-            const int pix = pix0 + u * stride;
-            if (pix < P) {
-                int b, hh, ww;
-                pix_decomp(pix, H, W, b, hh, ww);
-                load_pixel(img, cimg, pool, b, hh, ww, H, W, p[u]);
-            }
+        for (int e = 0; e < VN; ++e) {
+            float acc = br[e];
+#pragma unroll
+            for (int j = 0; j < kMaxImgC; ++j) acc += wr[e][j] * p[j];
+            o.set(e, lrelu_f(acc, slope));
         }
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-            const int pix = pix0 + u * stride;
-            if (pix < P) {
-                RV<T> o;
-#pragma unroll
-                for (int e = 0; e < VN; ++e) {
-                    float acc = br[e];
-#pragma unroll
-                    for (int j = 0; j < kMaxImgC; ++j) acc += wr[e][j] * p[u][j];
-                    o.set(e, lrelu_f(acc, slope));
-                }
-                *reinterpret_cast<uint4*>(out + static_cast<size_t>(pix) * C + tx * VN) = o.raw;
-            }
-        }
+        *reinterpret_cast<uint4*>(out + static_cast<size_t>(pix) * C + tx * VN) = o.raw;
     }
 }
 
@@ -112,7 +98,7 @@ rgb_reduce_kernel(const T* __restrict__ x, const float* __restrict__ w, const fl
                   float* __restrict__ out, int B, int H, int W, int C, int cimg, int up, float scale, float up_scale,
                   int LP) {
     constexpr int VN = RV<T>::N;
-    constexpr int UNR = NV == 1 ? 8 : 4;       // 16-byte loads in flight per lane: 8 (NV = 1) / 8 (NV = 2) / 16
+    constexpr int UNR = 4;
     const int lane = threadIdx.x & 31;
     const int sub = lane % LP, grp = lane / LP, ppw = 32 / LP;
     float wr[NV][VN][kMaxImgC];
@@ -207,33 +193,19 @@ rgb_wgrad_kernel(const T* __restrict__ f, const float* __restrict__ img, float* 
     for (int e = 0; e < VN; ++e)
 #pragma unroll
         for (int j = 0; j < NA; ++j) a[e][j] = 0.f;
-    constexpr int UNR = 4;                 // pixels in flight per thread (the kernel is latency-bound otherwise)
-    for (int pix0 = p0 + ty; pix0 < p1; pix0 += UNR * TY) {
-        float p[UNR][kMaxImgC];
-        RV<T> v[UNR];
+    for (int pix = p0 + ty; pix < p1; pix += TY) {
+        int b, hh, ww;
+        pix_decomp(pix, H, W, b, hh, ww);
+        float p[kMaxImgC];
+        load_pixel(img, cimg, pool, b, hh, ww, H, W, p);
+        RV<T> v;
+        v.raw = __ldg(reinterpret_cast<const uint4*>(f + static_cast<size_t>(pix) * C + tx * VN));
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-            const int pix = pix0 + u * TY;
-            if (pix < p1) {
-                int b, hh, ww;
-                pix_decomp(pix, H, W, b, hh, ww);
-                load_pixel(img, cimg, pool, b, hh, ww, H, W, p[u]);
-                v[u].raw = __ldg(reinterpret_cast<const uint4*>(f + static_cast<size_t>(pix) * C + tx * VN));
-            } else {
-                v[u].raw = make_uint4(0, 0, 0, 0);
+        for (int e = 0; e < VN; ++e) {
+            const float fv = v.get(e);
 #pragma unroll
-                for (int j = 0; j < kMaxImgC; ++j) p[u][j] = 0.f;
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-#pragma unroll
-            for (int e = 0; e < VN; ++e) {
-                const float fv = v[u].get(e);
-#pragma unroll
-                for (int j = 0; j < kMaxImgC; ++j) a[e][j] += fv * p[u][j];
-                a[e][kMaxImgC] += fv;
-            }
+            for (int j = 0; j < kMaxImgC; ++j) a[e][j] += fv * p[j];
+            a[e][kMaxImgC] += fv;
         }
     }
 #pragma unroll
@@ -352,8 +324,7 @@ static int rgb_reduce_launch(const void* x, const float* w, const float* bias, f
     PG_CHECK(nv <= 4, PG_ERR_UNSUPPORTED, "pggan_rgb_reduce: C=%d too large (max %d)", C, 4 * 32 * VN);
     const long long P = (long long)B * H * W;
     PG_CHECK(P < (1LL << 31), PG_ERR_UNSUPPORTED, "pggan_rgb_reduce: tensor too large");
-    const int unr = nv == 1 ? 8 : 4;
-    const long long warps = (P + (32 / LP) * unr - 1) / ((32 / LP) * unr);
+    const long long warps = (P + (32 / LP) * 4 - 1) / ((32 / LP) * 4);
     const int grid = grid_for(warps * 32 / 8 + 1, 256, nv >= 2 ? 1 : 2);   // >= 8 iterations per warp; register-heavy
     const T* xp = reinterpret_cast<const T*>(x);
     switch (nv) {
@@ -398,7 +369,7 @@ extern "C" int pggan_rgb_wgrad(const void* f, const float* img, float* acc, floa
     const int TY = 256 / TX;
     long long ppb = (long long)TY * 16;                   // 16 pixels per thread
     long long blocks = (P + ppb - 1) / ppb;
-    const long long cap = (long long)num_sms() * 16;
+    const long long cap = (long long)num_sms() * 16;     // (measured: fewer, longer blocks are slower here)
     if (blocks > cap) {
         blocks = cap;
         ppb = (P + blocks - 1) / blocks;

@@ -71,6 +71,9 @@ CONV_SHAPES = [
     (1, 16, 128, 16, 64, 9),
     (1, 8, 256, 64, 32, 9),
     (5, 64, 128, 16, 16, 9),       # more strips than one per CTA range boundary
+    (1, 8, 512, 32, 32, 9),        # conv_rows pixel groups: J = 2, N' = 64
+    (2, 16, 256, 32, 16, 9),       # J = 2, N' = 32
+    (1, 32, 512, 16, 16, 9),       # J = 4, N' = 64
 ]
 
 
