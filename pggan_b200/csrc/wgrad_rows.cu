@@ -41,7 +41,11 @@ template <int XSPAN, int GSPAN> struct WrCfg {
     static constexpr int kSpansPerA = 128 / C;                       // dx values covered by one M = 128 operand
     static constexpr int kNumA = (3 + kSpansPerA - 1) / kSpansPerA;  // MMAs per 16-pixel step (2 for C = 64)
     static constexpr int NCOLS = 3 * NCH;
-    static constexpr int kTmemRaw = kNumA * NCOLS;
+    // MMAs into ONE accumulator are a dependent chain; small-N MMAs are then paced by the accumulate latency, not by
+    // tensor work.  kSets independent accumulator sets are used round-robin over the 16-pixel steps and summed in the
+    // epilogue (as many as fit in TMEM, up to 4)
+    static constexpr int kSets = (4 * kNumA * NCOLS <= 512) ? 4 : ((2 * kNumA * NCOLS <= 512) ? 2 : 1);
+    static constexpr int kTmemRaw = kSets * kNumA * NCOLS;
     static constexpr int kTmemCols = kTmemRaw <= 32 ? 32 : (kTmemRaw <= 64 ? 64 : (kTmemRaw <= 128 ? 128 : (kTmemRaw <= 256 ? 256 : 512)));
     // x row pitch: 128 + 2 halo + the extra pixels the unused high spans reach into, rounded to 128 bytes
     static constexpr int kXPixRaw = 128 + kNumA * kSpansPerA;
@@ -166,7 +170,8 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                         for (int aa = 0; aa < Cfg::kNumA; ++aa) {
                             const uint64_t adesc = make_smem_desc(sx + (16 * k + aa * Cfg::kSpansPerA) * XSPAN, XSPAN,
                                                                   8 * XSPAN, kLayoutX);
-                            umma_ss<false>(tmem_base + aa * NCOLS, adesc, bdesc, idesc, (first && k == 0) ? 0u : 1u);
+                            umma_ss<false>(tmem_base + ((k % Cfg::kSets) * Cfg::kNumA + aa) * NCOLS, adesc, bdesc, idesc,
+                                           (first && k < Cfg::kSets) ? 0u : 1u);
                         }
                     }
                     first = false;
@@ -199,6 +204,14 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                 uint32_t r[32];
                 tmem_ld16(taddr + j * 16, r);
                 tmem_ld_wait();
+#pragma unroll
+                for (int st = 1; st < Cfg::kSets; ++st) {          // add the other accumulator sets
+                    uint32_t r2[32];
+                    tmem_ld16(taddr + st * Cfg::kNumA * NCOLS + j * 16, r2);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(r2[e]));
+                }
                 const int i = (j * 16) / NCH;          // g row of the stack: dy = 2 - i
                 const int n0 = (j * 16) % NCH;
                 if (dx < 3 && u_begin < u_end) {
