@@ -106,7 +106,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
+        if (elect_one()) {    // (not lane == 0: ptxas keeps descriptors in uniform registers only under elect.sync)
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -138,7 +138,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         }
     } else if (warp == 1) {
         // -------------------------------------------------------------------- MMA issuer
-        if (lane == 0) {
+        if (elect_one()) {    // (not lane == 0: ptxas keeps descriptors in uniform registers only under elect.sync)
             constexpr uint32_t idesc = make_idesc(kTF32 ? 2 : 1, 0, 0, kBlockM, BLOCK_N);
             int stage = 0;
             uint32_t phase = 0;
@@ -340,7 +340,7 @@ conv_gemm_swapped_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
     const int num_kc = a.taps * a.kc_per_tap;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {    // (not lane == 0: ptxas keeps descriptors in uniform registers only under elect.sync)
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -370,7 +370,7 @@ conv_gemm_swapped_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {    // (not lane == 0: ptxas keeps descriptors in uniform registers only under elect.sync)
             constexpr uint32_t idesc = make_idesc(kTF32 ? 2 : 1, 0, 0, 128, kSwPix);
             int stage = 0;
             uint32_t phase = 0;

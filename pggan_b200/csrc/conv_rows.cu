@@ -149,7 +149,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
-        if (lane == 0 && u_begin < u_end) {
+        if (u_begin < u_end && elect_one()) {
             if constexpr (J == 1) {
                 mbar_arrive_expect_tx(w_bar, Cfg::kWBytes);
                 for (int t = 0; t < 9; ++t) tma_load_2d(sw + t * kWTile, &tmap_w, w_bar, t * a.C, 0);
@@ -174,7 +174,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         }
     } else if (warp == 1) {
         // -------------------------------------------------------------------- MMA issuer
-        if (lane == 0 && u_begin < u_end) {
+        if (u_begin < u_end && elect_one()) {
             constexpr uint32_t idesc = make_idesc(1, 0, 0, kRowPix, BLOCK_N);
             if constexpr (J == 1) {
                 mbar_wait(w_bar, 0);

@@ -118,7 +118,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
     };
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {    // (not lane == 0: ptxas keeps descriptors in uniform registers only under elect.sync)
             int stage = 0;
             uint32_t phase = 0;
             for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
@@ -173,7 +173,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {    // (not lane == 0: ptxas keeps descriptors in uniform registers only under elect.sync)
             constexpr uint32_t idesc = make_idesc(kTF32 ? 2 : 1, 1, 1, 128, BLOCK_C);
             int stage = 0;
             uint32_t phase = 0;

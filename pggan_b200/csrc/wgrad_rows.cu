@@ -108,7 +108,7 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
+        if (elect_one()) {    // (not lane == 0: ptxas keeps descriptors in uniform registers only under elect.sync)
             uint32_t LX = 0, LG = 0;
             auto load_g = [&](int yrow, int b, int seg) {         // yrow < 0: a zero row (fully out of bounds)
                 const uint32_t slot = LG % R;
@@ -143,7 +143,7 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         }
     } else if (warp == 1) {
         // -------------------------------------------------------------------- MMA issuer
-        if (lane == 0) {
+        if (elect_one()) {    // (not lane == 0: ptxas keeps descriptors in uniform registers only under elect.sync)
             constexpr uint32_t idesc = make_idesc(1, 1, 1, 128, NCOLS);
             const uint32_t xring_addr = smem_u32(xring), gring_addr = smem_u32(gring);
             uint32_t LX = 0, LG = 0;
