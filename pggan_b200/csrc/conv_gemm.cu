@@ -31,7 +31,8 @@ bool conv_rows_supported(const pg_conv_params* p);
 int conv_rows_launch(const pg_conv_params* p, cudaStream_t stream);
 
 constexpr int kBlockM = 128;
-constexpr int kConvThreads = 192;
+constexpr int kConvThreads = 192;          // swapped kernel: TMA warp, MMA warp, 4 epilogue warps
+constexpr int kConvThreadsPlain = 320;     // plain kernel: 2 x 4 epilogue warps taking alternate tiles
 
 // SPAN = bytes of K per chunk = the TMA/UMMA swizzle span: 128 normally; 64 / 32 for layers whose channel
 // count times element size is only 64 / 32 bytes (the 32- and 16-channel stages of the 1024^2 network)
@@ -58,7 +59,7 @@ struct ConvKArgs {
 };
 
 template <typename T, int BLOCK_N, int SPAN = 128>
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(kConvThreadsPlain, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                  const ConvKArgs a) {
     using Cfg = ConvCfg<BLOCK_N, SPAN>;
@@ -176,8 +177,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const int wo = row % a.BW;
         const int ho = (row / a.BW) % a.BH;
         const int bo = row / (a.BW * a.BH);
+        // one epilogue warp per SM sub-partition is latency-bound on short-K layers (the epilogue of a 128 x N tile
+        // is ~N/32 x 450 dependent instructions): two groups of four warps drain the two TMEM accumulators concurrently
+        const int egroup = (warp - 2) >> 2;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            if ((it & 1) != egroup) continue;
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const int nt = tile % a.tiles_n;
@@ -593,7 +598,7 @@ static int launch_tc(const pg_conv_params* p, cudaStream_t stream) {
     }
     const int num_tiles = a.tiles_w * a.tiles_h * a.tiles_b * a.tiles_n;
     int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-    kern<<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(tx, tw, a);
+    kern<<<grid, kConvThreadsPlain, Cfg::kSmemBytes, stream>>>(tx, tw, a);
     PG_LAUNCH_CHECK();
     g_tc_launches++;
     return PG_OK;

@@ -35,7 +35,7 @@ namespace pg {
 
 extern std::atomic<long long> g_tc_launches;
 
-constexpr int kRowsThreads = 192;
+constexpr int kRowsThreads = 320;     // TMA warp, MMA warp, 2 x 4 epilogue warps (the groups take alternate output rows)
 constexpr int kRowPix = 128;          // output pixels per row segment = MMA M
 
 struct RowsKArgs {
@@ -228,6 +228,9 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         // ---------------------------------------------------------------------- epilogue
         const int q = warp & 3;
         const int r = q * 32 + lane;                   // pixel within the 128-pixel row segment = TMEM lane
+        // a lone warp per SM sub-partition leaves the epilogue latency-bound (ncu: ~900 dependent instructions per
+        // row per warp); two groups of four warps take alternate rows, each accumulator still sees 128 arrivals
+        const uint32_t egroup = (warp - 2) >> 2;
         uint32_t it = 0;
         long long u = u_begin;
         while (u < u_end) {
@@ -238,6 +241,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             const int b = static_cast<int>(col / a.nseg);
             const int seg = static_cast<int>(col - static_cast<long long>(b) * a.nseg);
             for (int i = 0; i < th; ++i, ++it) {
+                if ((it & 1u) != egroup) continue;
                 const uint32_t acc = it % ACC;
                 const size_t pix = (static_cast<size_t>(b) * a.H + (y0 + i)) * a.W + seg * kRowPix + r;
                 const size_t off = pix * a.N;

@@ -26,13 +26,15 @@ issue_kernel(long long* out, int N, int nacc, int issuers, int iters, int a_rows
     const uint32_t tmem = *slot;
     if (warp < issuers && (use_elect ? elect_one() : (lane == 0))) {
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(128 >> 4) << 24);
-        const uint64_t adesc = make_smem_desc(smem_u32(smem) + a_rows_shift * 128, 16, 1024, 2);
+        const uint64_t adesc = make_smem_desc(smem_u32(smem), 16, 1024, 2);
         const uint64_t bdesc = make_smem_desc(smem_u32(smem) + 32768, 16, 1024, 2);
         const long long t0 = clock64();
         const uint32_t d0 = tmem + ((warp * nacc) * N) % 512, d1 = tmem + ((warp * nacc + (nacc - 1)) * N) % 512;
+        // a_rows_shift != 0: every MMA reads a DIFFERENT 4 KB A tile (walks 8 tiles) — does the A fetch set the pace?
         for (int i = 0; i < iters; i += 2) {
-            umma_ss<false>(d0, adesc, bdesc, idesc, 1);
-            umma_ss<false>(d1, adesc + 2, bdesc + 2, idesc, 1);
+            const uint64_t ao = a_rows_shift ? static_cast<uint64_t>(((i >> 1) & 7) * 256) : 0ull;
+            umma_ss<false>(d0, adesc + ao, bdesc, idesc, 1);
+            umma_ss<false>(d1, adesc + ao + 2, bdesc + 2, idesc, 1);
         }
         const long long t1 = clock64();
         umma_commit(&done[warp]);
@@ -54,20 +56,21 @@ int main() {
     cudaMalloc(&dout, 148 * 4 * 8);
     cudaFuncSetAttribute(issue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 70000);
     const int iters = 2000;
-    for (int use_elect : {0, 1})
+    for (int use_elect : {1})
+    for (int walk : {0, 1})
     for (int grid : {148})
         for (int N : {16, 64, 128, 256})
             for (int issuers : {1, 2})
                 for (int nacc : {1, 2}) {
                     if (issuers * nacc * N > 512) continue;
                     cudaMemset(dout, 0, 148 * 4 * 8);
-                    issue_kernel<<<grid, 128, 70000>>>(dout, N, nacc, issuers, iters, 0, use_elect);
+                    issue_kernel<<<grid, 128, 70000>>>(dout, N, nacc, issuers, iters, walk, use_elect);
                     cudaError_t e = cudaDeviceSynchronize();
                     if (e != cudaSuccess) { printf("cuda error %s\n", cudaGetErrorString(e)); return 1; }
                     long long h[4];
                     cudaMemcpy(h, dout, sizeof(h), cudaMemcpyDeviceToHost);
-                    printf("elect %d grid %3d N %3d issuers %d nacc %d : issue %.1f cyc/MMA, complete %.1f cyc/MMA (per issuer; x%d MMAs in flight total)\n",
-                           use_elect, grid, N, issuers, nacc, (double)h[0] / iters, (double)h[1] / iters, issuers);
+                    printf("walkA %d elect %d grid %3d N %3d issuers %d nacc %d : issue %.1f cyc/MMA, complete %.1f cyc/MMA (per issuer; x%d MMAs in flight total)\n",
+                           walk, use_elect, grid, N, issuers, nacc, (double)h[0] / iters, (double)h[1] / iters, issuers);
                 }
     return 0;
 }
