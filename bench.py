@@ -54,46 +54,72 @@ def measured_peaks():
 
 
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi clocks / throttle reasons DURING the timed region: the sampler is started before the warm-up (so
+    nvidia-smi is already streaming when the timed steps begin), every sample carries nvidia-smi's own timestamp, and
+    only the samples between mark_begin() and mark_end() are reported."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.proc = None
         self.idx = gpu_index
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
 
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
         except Exception:
             self.proc.kill()
             out = ""
-        clocks, mx, reasons = [], None, set()
+        import datetime
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for line in out.strip().splitlines():
             f = [t.strip() for t in line.split(",")]
-            if len(f) < 6:
+            if len(f) < 7:
                 continue
             try:
-                clocks.append(float(f[0]))
-                mx = float(f[1])
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), f[3:7]))
             except ValueError:
                 continue
-            for n, v in zip(names, f[2:6]):
+        inside = [r for r in rows if self.t0 is not None and self.t0 <= r[0] <= (self.t1 or r[0])]
+        note = None
+        if not inside and rows and self.t0 is not None:
+            # timed region shorter than the sampling period: take the samples closest to it (warm-up steps of the
+            # same workload run right before it, so these are under the same load)
+            rows.sort(key=lambda r: abs(r[0] - 0.5 * (self.t0 + (self.t1 or self.t0))))
+            inside = rows[:3]
+            note = "timed region shorter than the 20 ms sampling period: nearest samples (warm-up of the same step)"
+        clocks = [r[1] for r in inside]
+        reasons = set()
+        for r in inside:
+            for n, v in zip(names, r[3]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        return {"sm_mhz": statistics.median(clocks) if clocks else None, "sm_max_mhz": mx,
-                "reasons": sorted(reasons), "samples": len(clocks)}
+        res = {"sm_mhz": statistics.median(clocks) if clocks else None, "sm_max_mhz": inside[0][2] if inside else None,
+               "reasons": sorted(reasons), "samples": len(clocks)}
+        if note:
+            res["note"] = note
+        return res
 
 
 def dist_setup(n_gpus: int):
@@ -204,14 +230,16 @@ def run_ours(args):
         return ms
 
     warm = max(args.warmup, 3)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(warm):
         step_resident()
     torch.cuda.synchronize()
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.mark_begin()
     ms = timed(step_resident, args.steps)
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
 
     for _ in range(2):

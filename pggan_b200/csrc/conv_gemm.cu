@@ -552,6 +552,11 @@ __global__ void conv_direct_kernel(const T* __restrict__ x, const T* __restrict_
 
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
+// swapped orientation (256 pixels on the MMA N dimension) vs the plain kernel with a small N tile, measured on the
+// 128^2 / 256^2 layer shapes after the issue fix: 128->64 266 vs 285 us, 256->128 132 vs 156 us (swapped wins),
+// 128->128 116 vs 89 us (plain wins): the transposing epilogue needs K >= 1152 at N <= 64, K >= 2304 at N = 128
+static bool swap_pays(int n, long long k) { return (n <= 64 && k >= 1152) || (n <= 128 && k >= 2304); }
+
 template <typename T, int BLOCK_N, int SPAN = 128>
 static int launch_tc(const pg_conv_params* p, cudaStream_t stream) {
     using Cfg = ConvCfg<BLOCK_N, SPAN>;
@@ -677,7 +682,7 @@ static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream, int* k
             static const bool no_swap_k = getenv("PGGAN_NO_SWAP") != nullptr;
             if (!kF32 && !no_rows_k && conv_rows_supported(p))
                 *kind_out = PG_CONV_KIND_ROWS;
-            else if (!no_swap_k && span == 128 && p->N <= 128 && (long long)Ceff * p->taps >= 1152 && (p->N * osz_k) % 16 == 0 &&
+            else if (!no_swap_k && span == 128 && swap_pays(p->N, (long long)Ceff * p->taps) && (p->N * osz_k) % 16 == 0 &&
                      (long long)p->B * p->H * p->W >= 2 * kSwPix)
                 *kind_out = PG_CONV_KIND_SWAPPED;
             else
@@ -705,7 +710,7 @@ static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream, int* k
         const bool mask_ok = p->mask_src == nullptr || osz == (int)sizeof(T);
         static const bool no_swap = getenv("PGGAN_NO_SWAP") != nullptr;
         // (its transposing epilogue costs a fixed ~5k cycles per 128x256 tile: only worth it when K is long enough)
-        if (!no_swap && span == 128 && p->N <= 128 && (long long)p->C * p->taps >= 1152 && (p->N * osz) % 16 == 0 && mask_ok &&
+        if (!no_swap && span == 128 && swap_pays(p->N, (long long)p->C * p->taps) && (p->N * osz) % 16 == 0 && mask_ok &&
             (long long)p->B * p->H * p->W >= 2 * kSwPix)
             return launch_swapped<T>(p, stream);
         // largest N tile that still yields enough CTAs to occupy the machine
@@ -732,7 +737,8 @@ static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream, int* k
         const int cands[5] = {256, 128, 64, 32, 16};
         // measured (tools/sweep_bn.sh, 32^2 512->512): 1510 / 915 / 497 / 256 TFLOP/s for N = 256 / 128 / 64 / 32, i.e. a
         // tile's time barely shrinks with N (the 128-row A operand read paces every MMA)
-        const double cost[5] = {1.0, 0.83, 0.76, 0.74, 0.73};
+        // re-measured after the elect.sync issue fix: 1525 / 1094 / 599 TFLOP/s for N = 256 / 128 / 64
+        const double cost[5] = {1.0, 0.70, 0.64, 0.62, 0.60};
         for (int i = 0; i < 5; ++i) {
             if (p->N % cands[i] != 0) continue;
             const long long tiles = m_tiles * (p->N / cands[i]);
