@@ -26,7 +26,7 @@ namespace pg {
 
 extern std::atomic<long long> g_tc_launches;
 
-constexpr int kWrThreads = 192;
+constexpr int kWrThreads = 224;      // TMA warp, MMA warp, 4 epilogue warps, second MMA warp
 
 struct WrKArgs {
     float* acc;
@@ -45,6 +45,9 @@ template <int XSPAN, int GSPAN> struct WrCfg {
     // tensor work.  kSets independent accumulator sets are used round-robin over the 16-pixel steps and summed in the
     // epilogue (as many as fit in TMEM, up to 4)
     static constexpr int kSets = (4 * kNumA * NCOLS <= 512) ? 4 : ((2 * kNumA * NCOLS <= 512) ? 2 : 1);
+    // one issuing thread sustains an MMA every ~62 cycles (tools/probe_issue.cu), two issuing warps ~40-48: with
+    // >= 2 accumulator sets the 16-pixel steps are split even / odd between two MMA warps
+    static constexpr int kIssuers = kSets >= 2 ? 2 : 1;
     static constexpr int kTmemRaw = kSets * kNumA * NCOLS;
     static constexpr int kTmemCols = kTmemRaw <= 32 ? 32 : (kTmemRaw <= 64 ? 64 : (kTmemRaw <= 128 ? 128 : (kTmemRaw <= 256 ? 256 : 512)));
     // x row pitch: 128 + 2 halo + the extra pixels the unused high spans reach into, rounded to 128 bytes
@@ -90,11 +93,11 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         tma_prefetch_desc(&tmap_g);
         for (int s = 0; s < R; ++s) {
             mbar_init(&xfull[s], 1);
-            mbar_init(&xempty[s], 1);
+            mbar_init(&xempty[s], Cfg::kIssuers);
             mbar_init(&gfull[s], 1);
-            mbar_init(&gempty[s], 1);
+            mbar_init(&gempty[s], Cfg::kIssuers);
         }
-        mbar_init(tfull, 1);
+        mbar_init(tfull, Cfg::kIssuers);
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -141,8 +144,9 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                 u = strip_end;
             }
         }
-    } else if (warp == 1) {
-        // -------------------------------------------------------------------- MMA issuer
+    } else if (warp == 1 || (warp == 6 && Cfg::kIssuers == 2)) {
+        // -------------------------------------------------------------------- MMA issuer(s)
+        const int iss = warp == 1 ? 0 : 1;
         if (elect_one()) {    // (not lane == 0: ptxas keeps descriptors in uniform registers only under elect.sync)
             constexpr uint32_t idesc = make_idesc(1, 1, 1, 128, NCOLS);
             const uint32_t xring_addr = smem_u32(xring), gring_addr = smem_u32(gring);
@@ -165,6 +169,7 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                     const uint32_t sg = gring_addr + ((LG + m) % R) * kGSlot;     // rows m, m+1, m+2 follow physically
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
+                        if (Cfg::kIssuers == 2 && (k & 1) != iss) continue;
                         const uint64_t bdesc = make_smem_desc(sg + 16 * k * GSPAN, kGSlot, 8 * GSPAN, kLayoutG);
 #pragma unroll
                         for (int aa = 0; aa < Cfg::kNumA; ++aa) {
@@ -186,7 +191,7 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             }
             umma_commit(tfull);
         }
-    } else {
+    } else if (warp >= 2 && warp <= 5) {
         // ---------------------------------------------------- epilogue: once, this CTA's partial-sum slice
         const int q = warp & 3;
         const int L = q * 32 + lane;                   // TMEM lane = (dx within the operand, c)
