@@ -437,24 +437,29 @@ __global__ void __launch_bounds__(256) unpack_oihw_kernel(const float* __restric
     // atomics on gW (the caller has zeroed it when accumulate == 0)
     const int sl0 = blockIdx.y * slices_per_block;
     const int sl1 = (sl0 + slices_per_block < slices) ? (sl0 + slices_per_block) : slices;
-    for (int k = threadIdx.x; k < 9 * Ip; k += blockDim.x) {
-        const int t = k / Ip, i = k - t * Ip;
-        if (i < I) {
-            float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
-            int sl = sl0;
-            for (; sl + 4 <= sl1; sl += 4) {
-                v0 += __ldg(src + (sl + 0) * slice_elems + k);
-                v1 += __ldg(src + (sl + 1) * slice_elems + k);
-                v2 += __ldg(src + (sl + 2) * slice_elems + k);
-                v3 += __ldg(src + (sl + 3) * slice_elems + k);
-            }
-            for (; sl < sl1; ++sl) v0 += __ldg(src + sl * slice_elems + k);
-            tile[i * 9 + t] = ((v0 + v1) + (v2 + v3)) * scale;
+    // blockIdx.z owns a chunk of input channels (more blocks in flight on the wide layers: 512 rows alone leave
+    // most of the machine idle)
+    const int cb = (I + gridDim.z - 1) / gridDim.z;
+    const int i0 = blockIdx.z * cb;
+    const int ni = (I - i0) < cb ? (I - i0) : cb;
+    if (ni <= 0) return;
+    for (int k = threadIdx.x; k < 9 * ni; k += blockDim.x) {
+        const int t = k / ni, ii = k - t * ni;
+        const int ks = t * Ip + i0 + ii;
+        float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+        int sl = sl0;
+        for (; sl + 4 <= sl1; sl += 4) {
+            v0 += __ldg(src + (sl + 0) * slice_elems + ks);
+            v1 += __ldg(src + (sl + 1) * slice_elems + ks);
+            v2 += __ldg(src + (sl + 2) * slice_elems + ks);
+            v3 += __ldg(src + (sl + 3) * slice_elems + ks);
         }
+        for (; sl < sl1; ++sl) v0 += __ldg(src + sl * slice_elems + ks);
+        tile[ii * 9 + t] = ((v0 + v1) + (v2 + v3)) * scale;
     }
     __syncthreads();
-    float* dst = gW + static_cast<size_t>(o) * I * 9;
-    const int n = I * 9;
+    float* dst = gW + (static_cast<size_t>(o) * I + i0) * 9;
+    const int n = ni * 9;
     if (gridDim.y > 1) {
         for (int k = threadIdx.x; k < n; k += blockDim.x) atomicAdd(dst + k, tile[k]);
         return;
@@ -867,7 +872,9 @@ extern "C" int pggan_unpack_wgrad(const float* in, float* out, const pg_pack_map
             groups = (slices + spb - 1) / spb;
             if (!accumulate) PG_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)m.n_total * 9 * m.c_valid, s));
         }
-        unpack_oihw_kernel<<<dim3(m.n_total, groups), 256, 9 * m.c_valid * sizeof(float), s>>>(
+        int zchunks = 1;                 // channel chunks of >= 128 (a multiple of 4 keeps the float4 path)
+        while (zchunks < 4 && m.c_valid / (zchunks * 2) >= 128 && m.c_valid % (zchunks * 2 * 4) == 0) zchunks *= 2;
+        unpack_oihw_kernel<<<dim3(m.n_total, groups, zchunks), 256, 9 * m.c_valid * sizeof(float), s>>>(
             in, out, m.c_valid, m.c_total, scale, accumulate, slices, slice_elems, spb);
     } else
         unpack_wgrad_kernel<<<ew_grid(total, 256), 256, 0, s>>>(in, out, m, total, scale, accumulate, slices, slice_elems);

@@ -1,4 +1,5 @@
-"""One launch each of the smem-resident-rows kernels (conv_rows / wgrad_rows) on the narrow-layer shapes, bracketed
+"""One launch each of the smem-resident-rows kernels (conv_rows / wgrad_rows) on the narrow-layer shapes and of the
+main conv_gemm / wgrad_gemm kernels on the 32^2 512->512 layer (the bench line's dominant kernel), bracketed
 by cudaProfilerStart/Stop so that `ncu --profile-from-start off` captures exactly these:
     ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/prof_rows python tools/ncu_rows.py
 """
@@ -10,7 +11,7 @@ from pggan_b200 import ops
 
 pg.set_compute_dtype(torch.bfloat16)
 dev = "cuda"
-SHAPES = [(16, 256, 256, 64, 64), (4, 1024, 1024, 16, 16), (4, 512, 512, 32, 32)]
+SHAPES = [(16, 256, 256, 64, 64), (4, 1024, 1024, 16, 16), (4, 512, 512, 32, 32), (64, 32, 32, 512, 512)]
 work = []
 for (B, H, W, C, N) in SHAPES:
     x = torch.randn(B, C, H, W, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
