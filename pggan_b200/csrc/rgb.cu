@@ -446,7 +446,7 @@ extern "C" int pggan_rgb_expand(const float* img, const float* w, const float* b
     const int TY = 256 / TX;
     PG_CHECK(P * (long long)C < (1LL << 40) && P < (1LL << 31), PG_ERR_UNSUPPORTED, "pggan_rgb_expand: tensor too large");
     const int CVn = C / vn;
-    if (cimg <= 3 && (CVn == 2 || CVn == 4 || CVn == 8)) {
+    if (cimg <= 3 && (CVn == 2 || CVn == 4)) {       // (measured: at C = 64 the vector-lane kernel below is faster, 67 vs 98 us)
         const int g2 = grid_for(P, 256, 8);
 #define PG_EXPAND_PIX(TT, CVV) rgb_expand_pixel_kernel<TT, CVV><<<g2, 256, 0, s>>>(img, w, bias, (TT*)out, B, H, W, cimg, pool, scale, slope)
         if (dtype == PG_BF16) {
@@ -533,7 +533,7 @@ extern "C" int pggan_rgb_wgrad(const void* f, const float* img, float* acc, floa
     PG_CHECK(TX <= 256 && 256 % TX == 0, PG_ERR_UNSUPPORTED, "pggan_rgb_wgrad: C/%d = %d must divide 256", vn, TX);
     const long long P = (long long)B * H * W;
     PG_CHECK(P < (1LL << 31), PG_ERR_UNSUPPORTED, "pggan_rgb_wgrad: tensor too large");
-    if (cimg <= 3 && (TX == 2 || TX == 4)) {
+    if (cimg <= 3 && TX == 2) {                      // (C = 32 needs 128 accumulators per thread: 203 registers, slower)
         const int g2 = grid_for(P / 8 + 1, 256, 4);      // >= 8 pixels per thread, <= 4 blocks per SM
         if (dtype == PG_BF16) {
             if (TX == 2) rgb_wgrad_pixel_kernel<__nv_bfloat16, 2><<<g2, 256, 0, s>>>((const __nv_bfloat16*)f, img, acc, bsum, B, H, W, cimg, pool, scale);
