@@ -147,7 +147,7 @@ def run_ours(args):
     scale, batch, depths, gflop_img = WORKLOADS[args.workload]
     if args.batch:
         batch = args.batch
-    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    dtype = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[args.dtype]
     pg.set_compute_dtype(dtype)
     torch.manual_seed(1234 + rank)
     targs = pg.make_args(latent_dim=512, depths=depths)
@@ -302,7 +302,7 @@ def run_ours(args):
             "metric": METRIC, "value": round(n_img / (ms * 1e-3), 2), "unit": "img/s", "n_gpus": world,
             "steps": args.steps, "warmup": warm, "ms_per_step": round(ms / args.steps, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if dtype == torch.bfloat16 else "fp32(3xTF32)", "data": "synthetic",
+            "dtype": {torch.bfloat16: "bf16", torch.float16: "fp16", torch.float32: "fp32(3xTF32)"}[dtype], "data": "synthetic",
             "config": {"workload": args.workload, "resolution": res, "batch_per_gpu": batch, "alpha": alpha,
                        "step_variant": args.variant, "latent_dim": 512, "depths": depths,
                        "parallelism": f"dp{world}", "cuda_graph": replay is not None,
@@ -394,7 +394,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2_32x32_b64_fade", choices=sorted(WORKLOADS))
     ap.add_argument("--variant", default="W", choices=["W", "L"])
-    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -8,7 +8,7 @@
  *   - never allocates, frees or synchronises (workspaces are passed in),
  *   - returns PG_OK or a negative error code; pggan_last_error() gives the message.
  *
- * Layouts.  Feature maps are NHWC ("channels_last"): [B][H][W][C], dtype PG_BF16 or PG_F32
+ * Layouts.  Feature maps are NHWC ("channels_last"): [B][H][W][C], dtype PG_BF16, PG_F16 or PG_F32
  * (PG_F32 operands run on kind::tf32 tensor-core MMAs; the Python layer feeds them as 3xTF32 splits).
  * RGB images, logits, latents, parameters and parameter gradients are fp32 in the reference's
  * own layouts (NCHW images, OIHW conv weights, [out,in] linear weights).
@@ -32,6 +32,8 @@ extern "C" {
 #define PG_BF16 0
 #define PG_F32 1
 #define PG_F32_RAW 2 /* output-only: fp32 result from any operand dtype (final logits / images) */
+#define PG_F16 3     /* IEEE half operands / feature maps: same kernels and speed as PG_BF16, 11-bit significand
+                      * (meets the 1e-2 forward bar that bf16's 8 bits miss beyond 16x16), 5-bit exponent */
 
 /* conv backend selection (bring-up / debugging): 0 = tcgen05 wherever the shape allows (default),
  * 1 = force the SIMT direct kernels. */

@@ -8,7 +8,7 @@ import ctypes
 import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
 
-PG_BF16, PG_F32, PG_F32_RAW = 0, 1, 2
+PG_BF16, PG_F32, PG_F32_RAW, PG_F16 = 0, 1, 2, 3
 PG_BACKEND_AUTO, PG_BACKEND_SIMT = 0, 1
 PG_CONV_KIND_SIMT, PG_CONV_KIND_PLAIN, PG_CONV_KIND_SWAPPED, PG_CONV_KIND_ROWS = 0, 1, 2, 3
 

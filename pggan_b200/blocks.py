@@ -151,7 +151,7 @@ class LastProgressiveDiscriminatorBlock(nn.Module):
             # the (C+1)-channel input is padded with zero channels up to the MMA K granule; the weight
             # packing pads to match (layout "pad_c"), so W and its gradient keep their [C, C+1, 3, 3] shape
             cin = x.shape[1] + 1
-            gran = 64 if x.dtype == torch.bfloat16 else 32
+            gran = 64 if x.element_size() == 2 else 32
             cpad = (cin + gran - 1) // gran * gran
             parts = [x, _stddev_channel(x, subgroup_size)]
             if cpad > cin:

@@ -58,7 +58,9 @@ int encode_tmap(CUtensorMap* map, int dtype, int rank, const void* base, const u
                             : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                             : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
                                                   : CU_TENSOR_MAP_SWIZZLE_NONE;
-    CUtensorMapDataType dt = dtype == PG_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    CUtensorMapDataType dt = dtype == PG_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                             : dtype == PG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                               : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     CUresult r = fn(map, dt, (cuuint32_t)rank, const_cast<void*>(base), (const cuuint64_t*)dims,
                     (const cuuint64_t*)strides_bytes, (const cuuint32_t*)box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

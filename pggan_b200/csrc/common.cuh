@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -40,7 +41,8 @@ int encode_tmap(CUtensorMap* map, int dtype, int rank, const void* base, const u
 // 3xTF32 operand split (elementwise.cu); see pggan_split3 in the header
 int split3_launch(const float* in, float* out, long long m, int c, int along_channels, int lo_slot, cudaStream_t s);
 
-inline int dtype_size(int dt) { return dt == PG_BF16 ? 2 : 4; }
+inline int dtype_size(int dt) { return (dt == PG_BF16 || dt == PG_F16) ? 2 : 4; }
+__host__ __device__ inline bool is16(int dt) { return dt == PG_BF16 || dt == PG_F16; }
 
 // ------------------------------------------------------------------------------ dtypes
 template <typename T> struct DT;
@@ -48,6 +50,11 @@ template <> struct DT<__nv_bfloat16> {
     static constexpr int kEnum = PG_BF16;
     static __device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
     static __device__ __forceinline__ __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
+};
+template <> struct DT<__half> {
+    static constexpr int kEnum = PG_F16;
+    static __device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
+    static __device__ __forceinline__ __half from_f(float v) { return __float2half_rn(v); }
 };
 template <> struct DT<float> {
     static constexpr int kEnum = PG_F32;
@@ -61,6 +68,36 @@ template <> struct DT<float> {
 template <typename T> struct Vec16 { static constexpr int kN = 16 / sizeof(T); };
 
 __device__ __forceinline__ float lrelu_f(float v, float slope) { return v > 0.f ? v : v * slope; }
+
+// The tensor-core kernels are instantiated once for 16-bit operands (T = __nv_bfloat16) and told at run time whether
+// the bits are bf16 or IEEE half (both are kind::f16 MMAs at the same rate): only three things depend on the format.
+//   1. the instruction-descriptor operand format (0 = f16, 1 = bf16)          -> fmt16()
+//   2. packing two fp32 results into one 32-bit word                          -> pack16()
+//   3. the LeakyReLU-mask test "x > 0" on a stored activation: both formats are sign-magnitude, so it is the
+//      signed-integer test on the raw 16 bits                                 -> pos16()
+__host__ __device__ inline uint32_t fmt16(int dt) { return dt == PG_F16 ? 0u : 1u; }
+__device__ __forceinline__ uint32_t pack16(float a, float b, bool f16) {
+    if (f16) {
+        __half2 h = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ bool pos16(uint16_t bits) { return static_cast<int16_t>(bits) > 0; }
+__device__ __forceinline__ uint16_t cvt16(float v, bool f16) {
+    if (f16) return __half_as_ushort(__float2half_rn(v));
+    return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+}
+__device__ __forceinline__ float f16bits_to_f(uint16_t bits, bool f16) {
+    if (f16) return __half2float(__ushort_as_half(bits));
+    return __uint_as_float(static_cast<uint32_t>(bits) << 16);
+}
+// "stored activation > 0" for a vector element of type T (16-bit: raw sign-magnitude test; fp32: the comparison)
+template <typename T> __device__ __forceinline__ bool act_pos(const T& v) {
+    if constexpr (sizeof(T) == 2) return pos16(*reinterpret_cast<const uint16_t*>(&v));
+    else return v > 0.f;
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -55,6 +55,7 @@ struct ConvKArgs {
     int tiles_w, tiles_h, tiles_b, tiles_n;
     int kc_per_tap, taps;
     int out_dtype;
+    int f16;                 // 16-bit operands / outputs are IEEE half (else bf16); see common.cuh fmt16()
     float scale, slope, mask_slope;
 };
 
@@ -140,7 +141,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     } else if (warp == 1) {
         // -------------------------------------------------------------------- MMA issuer
         if (elect_one()) {    // (not lane == 0: ptxas keeps descriptors in uniform registers only under elect.sync)
-            constexpr uint32_t idesc = make_idesc(kTF32 ? 2 : 1, 0, 0, kBlockM, BLOCK_N);
+            const uint32_t idesc = make_idesc(kTF32 ? 2 : (a.f16 ? 0 : 1), 0, 0, kBlockM, BLOCK_N);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -242,20 +243,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                             const T* mv = reinterpret_cast<const T*>(&mcur[c]);
 #pragma unroll
                             for (int e = 0; e < VN; ++e)
-                                if (!(DT<T>::to_f(mv[e]) > 0.f)) v[c * VN + e] *= a.mask_slope;
+                                if (!act_pos(mv[e])) v[c * VN + e] *= a.mask_slope;
                         }
 #pragma unroll
                         for (int c = 0; c < MV; ++c) mcur[c] = mnxt[c];
                     }
-                    if (a.out_dtype == PG_BF16) {
-                        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(a.y) + off + j * CH;
+                    if (is16(a.out_dtype)) {
+                        uint16_t* op = reinterpret_cast<uint16_t*>(a.y) + off + j * CH;
+                        const bool f16 = a.f16 != 0;
 #pragma unroll
                         for (int c = 0; c < CH / 8; ++c) {
                             uint4 pk;
-                            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+                            uint32_t* h2 = reinterpret_cast<uint32_t*>(&pk);
 #pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                h2[e] = __floats2bfloat162_rn(v[c * 8 + 2 * e], v[c * 8 + 2 * e + 1]);
+                            for (int e = 0; e < 4; ++e) h2[e] = pack16(v[c * 8 + 2 * e], v[c * 8 + 2 * e + 1], f16);
                             reinterpret_cast<uint4*>(op)[c] = pk;
                         }
                     } else {
@@ -376,7 +377,7 @@ conv_gemm_swapped_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
         }
     } else if (warp == 1) {
         if (elect_one()) {    // (not lane == 0: ptxas keeps descriptors in uniform registers only under elect.sync)
-            constexpr uint32_t idesc = make_idesc(kTF32 ? 2 : 1, 0, 0, 128, kSwPix);
+            const uint32_t idesc = make_idesc(kTF32 ? 2 : (a.f16 ? 0 : 1), 0, 0, 128, kSwPix);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -408,7 +409,8 @@ conv_gemm_swapped_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
         const int q = warp & 3;
         const int cl = q * 32 + lane;                       // channel within the 128-channel tile
         const int et = threadIdx.x - 64;                    // 0..127 among the epilogue threads
-        const int osz = (a.out_dtype == PG_BF16) ? 2 : 4;
+        const int osz = is16(a.out_dtype) ? 2 : 4;
+        const bool f16 = a.f16 != 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -460,10 +462,10 @@ conv_gemm_swapped_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
                 // transpose through smem: staging[pixel p][channel cl]
                 if (cl < cvalid) {
                     if (osz == 2) {
-                        __nv_bfloat16* st = reinterpret_cast<__nv_bfloat16*>(staging);
+                        uint16_t* st = reinterpret_cast<uint16_t*>(staging);
 #pragma unroll
                         for (int p = 0; p < 32; ++p)
-                            st[p * cvalid + cl] = __float2bfloat16_rn(lrelu_f((__uint_as_float(r[p]) + bias) * a.scale, a.slope));
+                            st[p * cvalid + cl] = cvt16(lrelu_f((__uint_as_float(r[p]) + bias) * a.scale, a.slope), f16);
                     } else {
                         float* st = reinterpret_cast<float*>(staging);
 #pragma unroll
@@ -492,7 +494,14 @@ conv_gemm_swapped_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
                         const T* mv = reinterpret_cast<const T*>(&mcur[i < MAXI ? i : 0]);
 #pragma unroll
                         for (int e = 0; e < VN; ++e)
-                            if (!(DT<T>::to_f(mv[e]) > 0.f)) ov[e] = DT<T>::from_f(DT<T>::to_f(ov[e]) * a.mask_slope);
+                            if (!act_pos(mv[e])) {
+                                if constexpr (sizeof(T) == 2) {
+                                    uint16_t* ob = reinterpret_cast<uint16_t*>(&ov[e]);
+                                    *ob = cvt16(f16bits_to_f(*ob, f16) * a.mask_slope, f16);
+                                } else {
+                                    ov[e] = ov[e] * a.mask_slope;
+                                }
+                            }
                     }
                     *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(a.y) + (pix * a.N + n0) * osz + vv * 16) = val;
                 }
@@ -543,10 +552,13 @@ __global__ void conv_direct_kernel(const T* __restrict__ x, const T* __restrict_
         if (bias != nullptr) acc += bias[n];
         float v = lrelu_f(acc * scale, slope);
         if (mask_src != nullptr && !(DT<T>::to_f(mask_src[idx]) > 0.f)) v *= mask_slope;
-        if (out_dtype == PG_BF16)
-            reinterpret_cast<__nv_bfloat16*>(y)[idx] = __float2bfloat16_rn(v);
-        else
-            reinterpret_cast<float*>(y)[idx] = v;
+        if constexpr (sizeof(T) == 2) {
+            if (is16(out_dtype)) {
+                reinterpret_cast<T*>(y)[idx] = DT<T>::from_f(v);
+                continue;
+            }
+        }
+        reinterpret_cast<float*>(y)[idx] = v;
     }
 }
 
@@ -576,6 +588,7 @@ static int launch_tc(const pg_conv_params* p, cudaStream_t stream) {
     a.kc_per_tap = p->C / BK;
     a.taps = p->taps;
     a.out_dtype = p->out_dtype;
+    a.f16 = p->dtype == PG_F16;
     a.scale = p->scale; a.slope = p->slope; a.mask_slope = p->mask_slope;
 
     const uint64_t es = sizeof(T);
@@ -584,7 +597,7 @@ static int launch_tc(const pg_conv_params* p, cudaStream_t stream) {
         uint64_t dims[4] = {(uint64_t)p->C, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
         uint64_t strides[3] = {(uint64_t)p->C * es, (uint64_t)p->W * p->C * es, (uint64_t)p->H * p->W * p->C * es};
         uint32_t box[4] = {(uint32_t)BK, (uint32_t)a.BW, (uint32_t)a.BH, (uint32_t)a.BB};
-        int rc = encode_tmap(&tx, DT<T>::kEnum, 4, p->x, dims, strides, box, SPAN);
+        int rc = encode_tmap(&tx, p->dtype, 4, p->x, dims, strides, box, SPAN);
         if (rc != PG_OK) return rc;
     }
     {
@@ -592,7 +605,7 @@ static int launch_tc(const pg_conv_params* p, cudaStream_t stream) {
         uint64_t dims[2] = {K, (uint64_t)p->N};
         uint64_t strides[1] = {K * es};
         uint32_t box[2] = {(uint32_t)BK, (uint32_t)BLOCK_N};
-        int rc = encode_tmap(&tw, DT<T>::kEnum, 2, p->wp, dims, strides, box, SPAN);
+        int rc = encode_tmap(&tw, p->dtype, 2, p->wp, dims, strides, box, SPAN);
         if (rc != PG_OK) return rc;
     }
     auto kern = conv_gemm_kernel<T, BLOCK_N, SPAN>;
@@ -627,6 +640,7 @@ static int launch_swapped(const pg_conv_params* p, cudaStream_t stream) {
     a.kc_per_tap = p->C / BK;
     a.taps = p->taps;
     a.out_dtype = p->out_dtype;
+    a.f16 = p->dtype == PG_F16;
     a.scale = p->scale; a.slope = p->slope; a.mask_slope = p->mask_slope;
     const uint64_t es = sizeof(T);
     CUtensorMap tx, tw;
@@ -634,7 +648,7 @@ static int launch_swapped(const pg_conv_params* p, cudaStream_t stream) {
         uint64_t dims[4] = {(uint64_t)p->C, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
         uint64_t strides[3] = {(uint64_t)p->C * es, (uint64_t)p->W * p->C * es, (uint64_t)p->H * p->W * p->C * es};
         uint32_t box[4] = {(uint32_t)BK, (uint32_t)a.BW, (uint32_t)a.BH, (uint32_t)a.BB};
-        int rc = encode_tmap(&tx, DT<T>::kEnum, 4, p->x, dims, strides, box, 128);
+        int rc = encode_tmap(&tx, p->dtype, 4, p->x, dims, strides, box, 128);
         if (rc != PG_OK) return rc;
     }
     {
@@ -642,7 +656,7 @@ static int launch_swapped(const pg_conv_params* p, cudaStream_t stream) {
         uint64_t dims[2] = {K, (uint64_t)p->N};
         uint64_t strides[1] = {K * es};
         uint32_t box[2] = {(uint32_t)BK, 128u};
-        int rc = encode_tmap(&tw, DT<T>::kEnum, 2, p->wp, dims, strides, box, 128);
+        int rc = encode_tmap(&tw, p->dtype, 2, p->wp, dims, strides, box, 128);
         if (rc != PG_OK) return rc;
     }
     auto kern = conv_gemm_swapped_kernel<T>;
@@ -677,7 +691,7 @@ static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream, int* k
     if (kind_out != nullptr) {
         *kind_out = PG_CONV_KIND_SIMT;
         if (tc_ok) {
-            const int osz_k = (p->out_dtype == PG_BF16) ? 2 : 4;
+            const int osz_k = is16(p->out_dtype) ? 2 : 4;
             static const bool no_rows_k = getenv("PGGAN_NO_ROWS") != nullptr;
             static const bool no_swap_k = getenv("PGGAN_NO_SWAP") != nullptr;
             if (!kF32 && !no_rows_k && conv_rows_supported(p))
@@ -706,7 +720,7 @@ static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream, int* k
         static const bool no_rows = getenv("PGGAN_NO_ROWS") != nullptr;
         if (!kF32 && !no_rows && conv_rows_supported(p)) return conv_rows_launch(p, stream);
         // few output channels: swapped orientation (channels on M, 256 pixels on N) keeps the tensor pipe fed
-        const int osz = (p->out_dtype == PG_BF16) ? 2 : 4;
+        const int osz = is16(p->out_dtype) ? 2 : 4;
         const bool mask_ok = p->mask_src == nullptr || osz == (int)sizeof(T);
         static const bool no_swap = getenv("PGGAN_NO_SWAP") != nullptr;
         // (its transposing epilogue costs a fixed ~5k cycles per 128x256 tile: only worth it when K is long enough)
@@ -764,10 +778,16 @@ static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream, int* k
     if (total == 0) return PG_OK;
     long long blocks = (total + 255) / 256;
     if (blocks > 148LL * 32) blocks = 148LL * 32;
-    conv_direct_kernel<T><<<(int)blocks, 256, 0, stream>>>(
-        reinterpret_cast<const T*>(p->x), reinterpret_cast<const T*>(p->wp), p->bias,
-        reinterpret_cast<const T*>(p->mask_src), p->y, p->B, p->H, p->W, p->C, p->N, p->taps, p->out_dtype, p->scale,
-        p->slope, p->mask_slope);
+    if (p->dtype == PG_F16)        // the SIMT kernel does arithmetic on the values: it needs the real element type
+        conv_direct_kernel<__half><<<(int)blocks, 256, 0, stream>>>(
+            reinterpret_cast<const __half*>(p->x), reinterpret_cast<const __half*>(p->wp), p->bias,
+            reinterpret_cast<const __half*>(p->mask_src), p->y, p->B, p->H, p->W, p->C, p->N, p->taps, p->out_dtype,
+            p->scale, p->slope, p->mask_slope);
+    else
+        conv_direct_kernel<T><<<(int)blocks, 256, 0, stream>>>(
+            reinterpret_cast<const T*>(p->x), reinterpret_cast<const T*>(p->wp), p->bias,
+            reinterpret_cast<const T*>(p->mask_src), p->y, p->B, p->H, p->W, p->C, p->N, p->taps, p->out_dtype, p->scale,
+            p->slope, p->mask_slope);
     PG_LAUNCH_CHECK();
     g_simt_launches++;
     return PG_OK;
@@ -788,7 +808,7 @@ extern "C" int pggan_conv_kernel_kind(const pg_conv_params* p) {
         if (!q.ws_w) q.ws_w = reinterpret_cast<void*>(uintptr_t(256));
     }
     int kind = PG_CONV_KIND_SIMT;
-    if (q.dtype == PG_BF16)
+    if (is16(q.dtype))
         conv_dispatch<__nv_bfloat16>(&q, nullptr, &kind);
     else if (q.dtype == PG_F32)
         conv_dispatch<float>(&q, nullptr, &kind);
@@ -802,10 +822,10 @@ extern "C" int pggan_conv_fprop(const pg_conv_params* p, void* stream) {
     PG_CHECK(p->B > 0 && p->H > 0 && p->W > 0 && p->C > 0 && p->N > 0, PG_ERR_ARG,
              "pggan_conv_fprop: bad dims B=%d H=%d W=%d C=%d N=%d", p->B, p->H, p->W, p->C, p->N);
     PG_CHECK(p->taps == 1 || p->taps == 9, PG_ERR_ARG, "pggan_conv_fprop: taps must be 1 or 9 (got %d)", p->taps);
-    PG_CHECK(p->dtype == PG_BF16 || p->dtype == PG_F32, PG_ERR_ARG, "pggan_conv_fprop: bad dtype %d", p->dtype);
-    PG_CHECK(p->out_dtype == PG_BF16 || p->out_dtype == PG_F32 || p->out_dtype == PG_F32_RAW, PG_ERR_ARG,
+    PG_CHECK(p->dtype == PG_BF16 || p->dtype == PG_F16 || p->dtype == PG_F32, PG_ERR_ARG, "pggan_conv_fprop: bad dtype %d", p->dtype);
+    PG_CHECK(p->out_dtype == p->dtype || p->out_dtype == PG_F32 || p->out_dtype == PG_F32_RAW, PG_ERR_ARG,
              "pggan_conv_fprop: bad out_dtype %d", p->out_dtype);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    if (p->dtype == PG_BF16) return conv_dispatch<__nv_bfloat16>(p, s);
+    if (is16(p->dtype)) return conv_dispatch<__nv_bfloat16>(p, s);      // bf16 and f16 share the 16-bit instantiation
     return conv_dispatch<float>(p, s);
 }

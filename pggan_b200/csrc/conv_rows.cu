@@ -49,6 +49,7 @@ struct RowsKArgs {
     long long total;         // B * nseg * H row segments
     long long per_cta;
     int out_dtype;
+    int f16;                 // 16-bit operands / outputs are IEEE half (else bf16)
     float scale, slope, mask_slope;
 };
 
@@ -175,7 +176,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     } else if (warp == 1) {
         // -------------------------------------------------------------------- MMA issuer
         if (u_begin < u_end && elect_one()) {
-            constexpr uint32_t idesc = make_idesc(1, 0, 0, kRowPix, BLOCK_N);
+            const uint32_t idesc = make_idesc(a.f16 ? 0 : 1, 0, 0, kRowPix, BLOCK_N);
             if constexpr (J == 1) {
                 mbar_wait(w_bar, 0);
                 tc_fence_after();
@@ -285,23 +286,23 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     if (masked) {
 #pragma unroll
                         for (int c = 0; c < MV; ++c) {
-                            const T* mv = reinterpret_cast<const T*>(&mcur[c]);
+                            const uint16_t* mv = reinterpret_cast<const uint16_t*>(&mcur[c]);
 #pragma unroll
                             for (int e = 0; e < 8; ++e)
-                                if (!(__bfloat162float(mv[e]) > 0.f)) v[c * 8 + e] *= a.mask_slope;
+                                if (!pos16(mv[e])) v[c * 8 + e] *= a.mask_slope;
                         }
 #pragma unroll
                         for (int c = 0; c < MV; ++c) mcur[c] = mnxt[c];
                     }
-                    if (a.out_dtype == PG_BF16) {
-                        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(a.y) + off + j * CH;
+                    if (is16(a.out_dtype)) {
+                        uint16_t* op = reinterpret_cast<uint16_t*>(a.y) + off + j * CH;
+                        const bool f16 = a.f16 != 0;
 #pragma unroll
                         for (int c = 0; c < CH / 8; ++c) {
                             uint4 pk;
-                            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+                            uint32_t* h2 = reinterpret_cast<uint32_t*>(&pk);
 #pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                h2[e] = __floats2bfloat162_rn(v[c * 8 + 2 * e], v[c * 8 + 2 * e + 1]);
+                            for (int e = 0; e < 4; ++e) h2[e] = pack16(v[c * 8 + 2 * e], v[c * 8 + 2 * e + 1], f16);
                             reinterpret_cast<uint4*>(op)[c] = pk;
                         }
                     } else {
@@ -351,6 +352,7 @@ static int launch_rows(const pg_conv_params* p_in, cudaStream_t stream) {
     a.nseg = p->W / kRowPix;
     a.total = static_cast<long long>(p->B) * a.nseg * p->H;
     a.out_dtype = p->out_dtype;
+    a.f16 = p->dtype == PG_F16;
     a.scale = p->scale; a.slope = p->slope; a.mask_slope = p->mask_slope;
     const int sms = num_sms();
     long long grid = a.total < sms ? a.total : sms;
@@ -362,7 +364,7 @@ static int launch_rows(const pg_conv_params* p_in, cudaStream_t stream) {
         uint64_t dims[4] = {(uint64_t)p->C, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
         uint64_t strides[3] = {(uint64_t)p->C * 2, (uint64_t)p->W * p->C * 2, (uint64_t)p->H * p->W * p->C * 2};
         uint32_t box[4] = {(uint32_t)p->C, (uint32_t)RowsGeom<SPAN>::kPW, 1u, 1u};
-        int rc = encode_tmap(&tx, PG_BF16, 4, p->x, dims, strides, box, SPAN);
+        int rc = encode_tmap(&tx, p->dtype, 4, p->x, dims, strides, box, SPAN);
         if (rc != PG_OK) return rc;
     }
     if (J == 1) {
@@ -370,7 +372,7 @@ static int launch_rows(const pg_conv_params* p_in, cudaStream_t stream) {
         uint64_t dims[2] = {K, (uint64_t)p->N};
         uint64_t strides[1] = {K * 2};
         uint32_t box[2] = {(uint32_t)p->C, (uint32_t)BLOCK_N};
-        int rc = encode_tmap(&tw, PG_BF16, 2, p->wp, dims, strides, box, SPAN);
+        int rc = encode_tmap(&tw, p->dtype, 2, p->wp, dims, strides, box, SPAN);
         if (rc != PG_OK) return rc;
     } else {
         tw = tx;                      // unused by the grouped variant (it builds its weight tiles itself)
@@ -390,7 +392,7 @@ static int launch_rows(const pg_conv_params* p_in, cudaStream_t stream) {
 // true if the layer is in this kernel's envelope (the caller has checked pointer alignment and dtype bf16)
 bool conv_rows_supported(const pg_conv_params* p) {
     const int cbytes = p->C * 2;
-    return p->dtype == PG_BF16 && p->taps == 9 && (cbytes == 128 || cbytes == 64 || cbytes == 32) &&
+    return is16(p->dtype) && p->taps == 9 && (cbytes == 128 || cbytes == 64 || cbytes == 32) &&
            p->W % kRowPix == 0 && p->H >= 4 && (p->N == 16 || p->N == 32 || p->N == 64 || p->N == 128);
 }
 

@@ -619,6 +619,9 @@ using namespace pg;
         if ((dtype) == PG_BF16) {                                    \
             using T = __nv_bfloat16;                                 \
             __VA_ARGS__;                                             \
+        } else if ((dtype) == PG_F16) {                              \
+            using T = __half;                                        \
+            __VA_ARGS__;                                             \
         } else if ((dtype) == PG_F32) {                              \
             using T = float;                                         \
             __VA_ARGS__;                                             \

@@ -147,8 +147,8 @@ __global__ void mbstd_bwd2_kernel(const T* __restrict__ x, const T* __restrict__
 
 static int mb_check(const char* name, int B, int64_t K, int group, int dtype) {
     PG_CHECK(B > 0 && K > 0 && group > 1 && B % group == 0, PG_ERR_ARG, "%s: bad B=%d group=%d", name, B, group);
-    PG_CHECK(dtype == PG_BF16 || dtype == PG_F32, PG_ERR_ARG, "%s: bad dtype %d", name, dtype);
-    const int vn = dtype == PG_BF16 ? 8 : 4;
+    PG_CHECK(dtype == PG_BF16 || dtype == PG_F16 || dtype == PG_F32, PG_ERR_ARG, "%s: bad dtype %d", name, dtype);
+    const int vn = is16(dtype) ? 8 : 4;
     PG_CHECK(K % vn == 0, PG_ERR_UNSUPPORTED, "%s: K=%lld must be a multiple of %d", name, (long long)K, vn);
     return PG_OK;
 }
@@ -171,6 +171,8 @@ extern "C" int pggan_mbstd_fwd(const void* x, float* stat, int B, int64_t K, int
     PG_CUDA(cudaMemsetAsync(stat, 0, sizeof(float) * (B / group), s));
     if (dtype == PG_BF16)
         mbstd_fwd_kernel<__nv_bfloat16><<<mb_grid(K, 8, B / group), 256, 0, s>>>((const __nv_bfloat16*)x, stat, K, group);
+    else if (dtype == PG_F16)
+        mbstd_fwd_kernel<__half><<<mb_grid(K, 8, B / group), 256, 0, s>>>((const __half*)x, stat, K, group);
     else
         mbstd_fwd_kernel<float><<<mb_grid(K, 4, B / group), 256, 0, s>>>((const float*)x, stat, K, group);
     PG_LAUNCH_CHECK();
@@ -187,6 +189,8 @@ extern "C" int pggan_mbstd_bwd(const void* x, const float* gs, void* gx, int B, 
     if (dtype == PG_BF16)
         mbstd_bwd_kernel<__nv_bfloat16><<<mb_grid(K, 8, B / group), 256, 0, s>>>((const __nv_bfloat16*)x, gs,
                                                                               (__nv_bfloat16*)gx, K, group);
+    else if (dtype == PG_F16)
+        mbstd_bwd_kernel<__half><<<mb_grid(K, 8, B / group), 256, 0, s>>>((const __half*)x, gs, (__half*)gx, K, group);
     else
         mbstd_bwd_kernel<float><<<mb_grid(K, 4, B / group), 256, 0, s>>>((const float*)x, gs, (float*)gx, K, group);
     PG_LAUNCH_CHECK();
@@ -204,6 +208,9 @@ extern "C" int pggan_mbstd_bwd2(const void* x, const void* u, const float* gs, f
     if (dtype == PG_BF16)
         mbstd_bwd2_kernel<__nv_bfloat16><<<mb_grid(K, 8, B / group), 256, 0, s>>>(
             (const __nv_bfloat16*)x, (const __nv_bfloat16*)u, gs, ggs, (__nv_bfloat16*)gx2, K, group);
+    else if (dtype == PG_F16)
+        mbstd_bwd2_kernel<__half><<<mb_grid(K, 8, B / group), 256, 0, s>>>((const __half*)x, (const __half*)u, gs, ggs,
+                                                                         (__half*)gx2, K, group);
     else
         mbstd_bwd2_kernel<float><<<mb_grid(K, 4, B / group), 256, 0, s>>>((const float*)x, (const float*)u, gs, ggs,
                                                                         (float*)gx2, K, group);

@@ -435,9 +435,9 @@ extern "C" int pggan_rgb_expand(const float* img, const float* w, const float* b
     PG_CHECK(cimg >= 1 && cimg <= kMaxImgC, PG_ERR_UNSUPPORTED, "pggan_rgb_expand: cimg=%d must be 1..4", cimg);
     PG_CHECK(al16(out) && (!pool || (reinterpret_cast<uintptr_t>(img) & 7) == 0), PG_ERR_ARG,
              "pggan_rgb_expand: misaligned pointer");
-    PG_CHECK(dtype == PG_BF16 || dtype == PG_F32, PG_ERR_ARG, "pggan_rgb_expand: bad dtype %d", dtype);
+    PG_CHECK(dtype == PG_BF16 || dtype == PG_F16 || dtype == PG_F32, PG_ERR_ARG, "pggan_rgb_expand: bad dtype %d", dtype);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    const int vn = dtype == PG_BF16 ? 8 : 4;
+    const int vn = is16(dtype) ? 8 : 4;
     PG_CHECK(C % vn == 0, PG_ERR_UNSUPPORTED, "pggan_rgb_expand: C=%d must be a multiple of %d", C, vn);
     const int TX = C / vn;
     PG_CHECK(TX <= 256 && 256 % TX == 0, PG_ERR_UNSUPPORTED,
@@ -446,25 +446,21 @@ extern "C" int pggan_rgb_expand(const float* img, const float* w, const float* b
     const int TY = 256 / TX;
     PG_CHECK(P * (long long)C < (1LL << 40) && P < (1LL << 31), PG_ERR_UNSUPPORTED, "pggan_rgb_expand: tensor too large");
     const int CVn = C / vn;
-    if (cimg <= 3 && (CVn == 2 || CVn == 4)) {       // (measured: at C = 64 the vector-lane kernel below is faster, 67 vs 98 us)
-        const int g2 = grid_for(P, 256, 8);
-#define PG_EXPAND_PIX(TT, CVV) rgb_expand_pixel_kernel<TT, CVV><<<g2, 256, 0, s>>>(img, w, bias, (TT*)out, B, H, W, cimg, pool, scale, slope)
-        if (dtype == PG_BF16) {
-            if (CVn == 2) PG_EXPAND_PIX(__nv_bfloat16, 2); else if (CVn == 4) PG_EXPAND_PIX(__nv_bfloat16, 4); else PG_EXPAND_PIX(__nv_bfloat16, 8);
-        } else {
-            if (CVn == 2) PG_EXPAND_PIX(float, 2); else if (CVn == 4) PG_EXPAND_PIX(float, 4); else PG_EXPAND_PIX(float, 8);
-        }
-#undef PG_EXPAND_PIX
-        PG_LAUNCH_CHECK();
-        g_other_launches++;
-        return PG_OK;
-    }
+    const int g2 = grid_for(P, 256, 8);
     const int grid = grid_for((P + TY - 1) / TY * 256 / 8 + 1, 256, 4);     // >= 8 pixels per thread
-    if (dtype == PG_BF16)
-        rgb_expand_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(img, w, bias, (__nv_bfloat16*)out, B, H, W, C, cimg, pool,
-                                                            scale, slope, TX);
-    else
-        rgb_expand_kernel<float><<<grid, 256, 0, s>>>(img, w, bias, (float*)out, B, H, W, C, cimg, pool, scale, slope, TX);
+    auto launch = [&](auto tag) {
+        using TT = decltype(tag);
+        // thread-per-pixel for C <= 32 (measured: at C = 64 the vector-lane kernel is faster, 67 vs 98 us)
+        if (cimg <= 3 && CVn == 2)
+            rgb_expand_pixel_kernel<TT, 2><<<g2, 256, 0, s>>>(img, w, bias, (TT*)out, B, H, W, cimg, pool, scale, slope);
+        else if (cimg <= 3 && CVn == 4)
+            rgb_expand_pixel_kernel<TT, 4><<<g2, 256, 0, s>>>(img, w, bias, (TT*)out, B, H, W, cimg, pool, scale, slope);
+        else
+            rgb_expand_kernel<TT><<<grid, 256, 0, s>>>(img, w, bias, (TT*)out, B, H, W, C, cimg, pool, scale, slope, TX);
+    };
+    if (dtype == PG_BF16) launch(__nv_bfloat16());
+    else if (dtype == PG_F16) launch(__half());
+    else launch(float());
     PG_LAUNCH_CHECK();
     g_other_launches++;
     return PG_OK;
@@ -510,12 +506,13 @@ extern "C" int pggan_rgb_reduce(const void* x, const float* w, const float* bias
     PG_CHECK(cimg >= 1 && cimg <= kMaxImgC, PG_ERR_UNSUPPORTED, "pggan_rgb_reduce: cimg=%d must be 1..4", cimg);
     PG_CHECK(al16(x) && (!up || (reinterpret_cast<uintptr_t>(out) & 7) == 0), PG_ERR_ARG,
              "pggan_rgb_reduce: misaligned pointer");
-    PG_CHECK(dtype == PG_BF16 || dtype == PG_F32, PG_ERR_ARG, "pggan_rgb_reduce: bad dtype %d", dtype);
-    const int vn = dtype == PG_BF16 ? 8 : 4;
+    PG_CHECK(dtype == PG_BF16 || dtype == PG_F16 || dtype == PG_F32, PG_ERR_ARG, "pggan_rgb_reduce: bad dtype %d", dtype);
+    const int vn = is16(dtype) ? 8 : 4;
     PG_CHECK(C % vn == 0, PG_ERR_UNSUPPORTED, "pggan_rgb_reduce: C=%d must be a multiple of %d", C, vn);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (dtype == PG_BF16)
         return rgb_reduce_launch<__nv_bfloat16>(x, w, bias, out, B, H, W, C, cimg, up, scale, up_scale, s);
+    if (dtype == PG_F16) return rgb_reduce_launch<__half>(x, w, bias, out, B, H, W, C, cimg, up, scale, up_scale, s);
     return rgb_reduce_launch<float>(x, w, bias, out, B, H, W, C, cimg, up, scale, up_scale, s);
 }
 
@@ -525,27 +522,14 @@ extern "C" int pggan_rgb_wgrad(const void* f, const float* img, float* acc, floa
     PG_CHECK(cimg >= 1 && cimg <= kMaxImgC, PG_ERR_UNSUPPORTED, "pggan_rgb_wgrad: cimg=%d must be 1..4", cimg);
     PG_CHECK(al16(f) && (!pool || (reinterpret_cast<uintptr_t>(img) & 7) == 0), PG_ERR_ARG,
              "pggan_rgb_wgrad: misaligned pointer");
-    PG_CHECK(dtype == PG_BF16 || dtype == PG_F32, PG_ERR_ARG, "pggan_rgb_wgrad: bad dtype %d", dtype);
+    PG_CHECK(dtype == PG_BF16 || dtype == PG_F16 || dtype == PG_F32, PG_ERR_ARG, "pggan_rgb_wgrad: bad dtype %d", dtype);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    const int vn = dtype == PG_BF16 ? 8 : 4;
+    const int vn = is16(dtype) ? 8 : 4;
     PG_CHECK(C % vn == 0, PG_ERR_UNSUPPORTED, "pggan_rgb_wgrad: C=%d must be a multiple of %d", C, vn);
     const int TX = C / vn;
     PG_CHECK(TX <= 256 && 256 % TX == 0, PG_ERR_UNSUPPORTED, "pggan_rgb_wgrad: C/%d = %d must divide 256", vn, TX);
     const long long P = (long long)B * H * W;
     PG_CHECK(P < (1LL << 31), PG_ERR_UNSUPPORTED, "pggan_rgb_wgrad: tensor too large");
-    if (cimg <= 3 && TX == 2) {                      // (C = 32 needs 128 accumulators per thread: 203 registers, slower)
-        const int g2 = grid_for(P / 8 + 1, 256, 4);      // >= 8 pixels per thread, <= 4 blocks per SM
-        if (dtype == PG_BF16) {
-            if (TX == 2) rgb_wgrad_pixel_kernel<__nv_bfloat16, 2><<<g2, 256, 0, s>>>((const __nv_bfloat16*)f, img, acc, bsum, B, H, W, cimg, pool, scale);
-            else rgb_wgrad_pixel_kernel<__nv_bfloat16, 4><<<g2, 256, 0, s>>>((const __nv_bfloat16*)f, img, acc, bsum, B, H, W, cimg, pool, scale);
-        } else {
-            if (TX == 2) rgb_wgrad_pixel_kernel<float, 2><<<g2, 256, 0, s>>>((const float*)f, img, acc, bsum, B, H, W, cimg, pool, scale);
-            else rgb_wgrad_pixel_kernel<float, 4><<<g2, 256, 0, s>>>((const float*)f, img, acc, bsum, B, H, W, cimg, pool, scale);
-        }
-        PG_LAUNCH_CHECK();
-        g_other_launches++;
-        return PG_OK;
-    }
     const int TY = 256 / TX;
     long long ppb = (long long)TY * 16;                   // 16 pixels per thread
     long long blocks = (P + ppb - 1) / ppb;
@@ -556,17 +540,28 @@ extern "C" int pggan_rgb_wgrad(const void* f, const float* img, float* acc, floa
     }
     const int grid = (int)((P + ppb - 1) / ppb);
     const size_t smem = (size_t)256 * vn * (kMaxImgC + 1) * sizeof(float);
-    if (dtype == PG_BF16) {
-        static bool attr = false;
-        if (!attr) {
-            PG_CUDA(cudaFuncSetAttribute(rgb_wgrad_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-            attr = true;
+    const int g2 = grid_for(P / 8 + 1, 256, 4);          // pixel kernel: >= 8 pixels per thread, <= 4 blocks per SM
+    cudaError_t attr_err = cudaSuccess;
+    auto launch = [&](auto tag) {
+        using TT = decltype(tag);
+        // thread-per-pixel-stream for C = 16 (C = 32 would need 128 accumulators per thread: 203 registers, slower)
+        if (cimg <= 3 && TX == 2) {
+            rgb_wgrad_pixel_kernel<TT, 2><<<g2, 256, 0, s>>>((const TT*)f, img, acc, bsum, B, H, W, cimg, pool, scale);
+            return;
         }
-        rgb_wgrad_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>((const __nv_bfloat16*)f, img, acc, bsum, B, H, W, C, cimg,
-                                                              pool, scale, TX, ppb);
-    } else {
-        rgb_wgrad_kernel<float><<<grid, 256, smem, s>>>((const float*)f, img, acc, bsum, B, H, W, C, cimg, pool, scale, TX, ppb);
-    }
+        if (smem > 48 * 1024) {
+            static bool attr = false;        // per element type (the lambda body is instantiated per TT)
+            if (!attr) {
+                attr_err = cudaFuncSetAttribute(rgb_wgrad_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+                attr = true;
+            }
+        }
+        rgb_wgrad_kernel<TT><<<grid, 256, smem, s>>>((const TT*)f, img, acc, bsum, B, H, W, C, cimg, pool, scale, TX, ppb);
+    };
+    if (dtype == PG_BF16) launch(__nv_bfloat16());
+    else if (dtype == PG_F16) launch(__half());
+    else launch(float());
+    PG_CUDA(attr_err);
     PG_LAUNCH_CHECK();
     g_other_launches++;
     return PG_OK;

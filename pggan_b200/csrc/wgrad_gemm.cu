@@ -53,6 +53,7 @@ struct WgKArgs {
     int PW, PH, PB;                 // pixel box of one stage
     int chunks_w, chunks_h, chunks_b;
     int tiles_n, tiles_c, splits, chunks_per_split;
+    int f16;                        // 16-bit operands are IEEE half (else bf16)
     int span5d;                     // 1: tensor maps are 5-D (channel spans are the 5th dim): one TMA box per operand
     int tpu;                        // taps per unit: C < BLOCK_C layers stack tpu = BLOCK_C/C shifted x tiles side by
                                     // side along the MMA N dimension (one g tile feeds several taps at full N = 256)
@@ -174,7 +175,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
         }
     } else if (warp == 1) {
         if (elect_one()) {    // (not lane == 0: ptxas keeps descriptors in uniform registers only under elect.sync)
-            constexpr uint32_t idesc = make_idesc(kTF32 ? 2 : 1, 1, 1, 128, BLOCK_C);
+            const uint32_t idesc = make_idesc(kTF32 ? 2 : (a.f16 ? 0 : 1), 1, 1, 128, BLOCK_C);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -431,6 +432,7 @@ static int launch_wg(const pg_wgrad_params* p, cudaStream_t stream) {
     const uint64_t es = sizeof(T);
     CUtensorMap tg, tx;
     const int sw = sizeof(T) == 4 ? 12832 : 128;
+    a.f16 = p->dtype == PG_F16;
     a.span5d = (p->N % Cfg::CPS == 0 && p->C % Cfg::CPS == 0) ? 1 : 0;
     if (a.span5d) {
         // dims: (channel within span, w, h, b, span); the span stride is one 128-byte span
@@ -439,7 +441,7 @@ static int launch_wg(const pg_wgrad_params* p, cudaStream_t stream) {
             uint64_t dims[5] = {(uint64_t)Cfg::CPS, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B, (uint64_t)(p->N / Cfg::CPS)};
             uint64_t strides[4] = {(uint64_t)p->N * es, (uint64_t)p->W * p->N * es, (uint64_t)p->H * p->W * p->N * es, span_bytes};
             uint32_t box[5] = {(uint32_t)Cfg::CPS, (uint32_t)a.PW, (uint32_t)a.PH, (uint32_t)a.PB, (uint32_t)Cfg::GA};
-            int rc = encode_tmap(&tg, DT<T>::kEnum, 5, p->g, dims, strides, box, sw);
+            int rc = encode_tmap(&tg, p->dtype == PG_F16 ? PG_F16 : DT<T>::kEnum, 5, p->g, dims, strides, box, sw);
             if (rc != PG_OK) return rc;
         }
         {
@@ -447,7 +449,7 @@ static int launch_wg(const pg_wgrad_params* p, cudaStream_t stream) {
             uint64_t strides[4] = {(uint64_t)p->C * es, (uint64_t)p->W * p->C * es, (uint64_t)p->H * p->W * p->C * es, span_bytes};
             uint32_t box[5] = {(uint32_t)Cfg::CPS, (uint32_t)a.PW, (uint32_t)a.PH, (uint32_t)a.PB,
                                (uint32_t)(a.tpu > 1 ? Cfg::GB / a.tpu : Cfg::GB)};
-            int rc = encode_tmap(&tx, DT<T>::kEnum, 5, p->x, dims, strides, box, sw);
+            int rc = encode_tmap(&tx, p->dtype == PG_F16 ? PG_F16 : DT<T>::kEnum, 5, p->x, dims, strides, box, sw);
             if (rc != PG_OK) return rc;
         }
     } else {
@@ -455,13 +457,13 @@ static int launch_wg(const pg_wgrad_params* p, cudaStream_t stream) {
         {
             uint64_t dims[4] = {(uint64_t)p->N, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
             uint64_t strides[3] = {(uint64_t)p->N * es, (uint64_t)p->W * p->N * es, (uint64_t)p->H * p->W * p->N * es};
-            int rc = encode_tmap(&tg, DT<T>::kEnum, 4, p->g, dims, strides, box, sw);
+            int rc = encode_tmap(&tg, p->dtype == PG_F16 ? PG_F16 : DT<T>::kEnum, 4, p->g, dims, strides, box, sw);
             if (rc != PG_OK) return rc;
         }
         {
             uint64_t dims[4] = {(uint64_t)p->C, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
             uint64_t strides[3] = {(uint64_t)p->C * es, (uint64_t)p->W * p->C * es, (uint64_t)p->H * p->W * p->C * es};
-            int rc = encode_tmap(&tx, DT<T>::kEnum, 4, p->x, dims, strides, box, sw);
+            int rc = encode_tmap(&tx, p->dtype == PG_F16 ? PG_F16 : DT<T>::kEnum, 4, p->x, dims, strides, box, sw);
             if (rc != PG_OK) return rc;
         }
     }
@@ -484,6 +486,42 @@ static int slices_wg(const pg_wgrad_params* p) {
     WgKArgs a;
     plan_wg<T, BLOCK_C>(p, a);
     return a.splits;
+}
+
+// SIMT kernels do arithmetic on the element values: templated on the REAL element type (the tensor-core path serves
+// bf16 and f16 from one 16-bit instantiation)
+template <typename T>
+static int wgrad_simt(const pg_wgrad_params* p, cudaStream_t stream) {
+    // SIMT path: one slice, partial sums meet through atomics on a zeroed accumulator
+    PG_CUDA(cudaMemsetAsync(p->acc, 0, sizeof(float) * (size_t)p->N * p->taps * p->C, stream));
+    constexpr int VNT = 16 / sizeof(T);
+    if (p->taps == 9 && p->N <= 64 && p->C <= 32 && p->N % 8 == 0 && p->C % VNT == 0 && p->N % VNT == 0 &&
+        (reinterpret_cast<uintptr_t>(p->g) % 16 == 0) && (reinterpret_cast<uintptr_t>(p->x) % 16 == 0)) {
+        constexpr int TW = 64;
+        const size_t smem = (size_t)(TW * p->N + 3 * (TW + 2) * p->C) * sizeof(float);
+        const long long nseg = (long long)p->B * p->H * ((p->W + TW - 1) / TW);
+        long long grid = (long long)num_sms() * 4;
+        if (grid > nseg) grid = nseg;
+        const T* gp = reinterpret_cast<const T*>(p->g);
+        const T* xp = reinterpret_cast<const T*>(p->x);
+        if (p->C * (p->N / 4) <= 256)
+            wgrad_small_kernel<T, TW, 4><<<(int)grid, 256, smem, stream>>>(gp, xp, p->acc, p->B, p->H, p->W, p->C, p->N);
+        else
+            wgrad_small_kernel<T, TW, 8><<<(int)grid, 256, smem, stream>>>(gp, xp, p->acc, p->B, p->H, p->W, p->C, p->N);
+        PG_LAUNCH_CHECK();
+        g_simt_launches++;
+        return PG_OK;
+    }
+    const long long P = (long long)p->B * p->H * p->W;
+    long long pix_per_block = 256;
+    while ((P + pix_per_block - 1) / pix_per_block > 2048) pix_per_block *= 2;
+    dim3 grid((unsigned)((P + pix_per_block - 1) / pix_per_block), (unsigned)p->taps,
+              (unsigned)(((p->N + 15) / 16) * ((p->C + 15) / 16)));
+    wgrad_direct_kernel<T><<<grid, 256, 0, stream>>>(reinterpret_cast<const T*>(p->g), reinterpret_cast<const T*>(p->x),
+                                                      p->acc, p->B, p->H, p->W, p->C, p->N, p->taps, pix_per_block);
+    PG_LAUNCH_CHECK();
+    g_simt_launches++;
+    return PG_OK;
 }
 
 // slices_out != nullptr: only report how many partial-sum slices the launch would write (no launch)
@@ -542,36 +580,8 @@ static int wgrad_dispatch(const pg_wgrad_params* p_in, cudaStream_t stream, int*
             if (p->C % 32 == 0) return launch_wg<T, 32>(p, stream);
         }
     }
-    // SIMT path: one slice, partial sums meet through atomics on a zeroed accumulator
-    PG_CUDA(cudaMemsetAsync(p->acc, 0, sizeof(float) * (size_t)p->N * p->taps * p->C, stream));
-    constexpr int VNT = 16 / sizeof(T);
-    if (p->taps == 9 && p->N <= 64 && p->C <= 32 && p->N % 8 == 0 && p->C % VNT == 0 && p->N % VNT == 0 &&
-        (reinterpret_cast<uintptr_t>(p->g) % 16 == 0) && (reinterpret_cast<uintptr_t>(p->x) % 16 == 0)) {
-        constexpr int TW = 64;
-        const size_t smem = (size_t)(TW * p->N + 3 * (TW + 2) * p->C) * sizeof(float);
-        const long long nseg = (long long)p->B * p->H * ((p->W + TW - 1) / TW);
-        long long grid = (long long)num_sms() * 4;
-        if (grid > nseg) grid = nseg;
-        const T* gp = reinterpret_cast<const T*>(p->g);
-        const T* xp = reinterpret_cast<const T*>(p->x);
-        if (p->C * (p->N / 4) <= 256)
-            wgrad_small_kernel<T, TW, 4><<<(int)grid, 256, smem, stream>>>(gp, xp, p->acc, p->B, p->H, p->W, p->C, p->N);
-        else
-            wgrad_small_kernel<T, TW, 8><<<(int)grid, 256, smem, stream>>>(gp, xp, p->acc, p->B, p->H, p->W, p->C, p->N);
-        PG_LAUNCH_CHECK();
-        g_simt_launches++;
-        return PG_OK;
-    }
-    const long long P = (long long)p->B * p->H * p->W;
-    long long pix_per_block = 256;
-    while ((P + pix_per_block - 1) / pix_per_block > 2048) pix_per_block *= 2;
-    dim3 grid((unsigned)((P + pix_per_block - 1) / pix_per_block), (unsigned)p->taps,
-              (unsigned)(((p->N + 15) / 16) * ((p->C + 15) / 16)));
-    wgrad_direct_kernel<T><<<grid, 256, 0, stream>>>(reinterpret_cast<const T*>(p->g), reinterpret_cast<const T*>(p->x),
-                                                      p->acc, p->B, p->H, p->W, p->C, p->N, p->taps, pix_per_block);
-    PG_LAUNCH_CHECK();
-    g_simt_launches++;
-    return PG_OK;
+    if (p->dtype == PG_F16) return wgrad_simt<__half>(p, stream);
+    return wgrad_simt<T>(p, stream);
 }
 
 }  // namespace pg
@@ -582,9 +592,9 @@ extern "C" int pggan_conv_wgrad(const pg_wgrad_params* p, void* stream) {
     PG_CHECK(p->B > 0 && p->H > 0 && p->W > 0 && p->C > 0 && p->N > 0, PG_ERR_ARG,
              "pggan_conv_wgrad: bad dims B=%d H=%d W=%d C=%d N=%d", p->B, p->H, p->W, p->C, p->N);
     PG_CHECK(p->taps == 1 || p->taps == 9, PG_ERR_ARG, "pggan_conv_wgrad: taps must be 1 or 9 (got %d)", p->taps);
-    PG_CHECK(p->dtype == PG_BF16 || p->dtype == PG_F32, PG_ERR_ARG, "pggan_conv_wgrad: bad dtype %d", p->dtype);
+    PG_CHECK(p->dtype == PG_BF16 || p->dtype == PG_F16 || p->dtype == PG_F32, PG_ERR_ARG, "pggan_conv_wgrad: bad dtype %d", p->dtype);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    if (p->dtype == PG_BF16) return wgrad_dispatch<__nv_bfloat16>(p, s, nullptr);
+    if (is16(p->dtype)) return wgrad_dispatch<__nv_bfloat16>(p, s, nullptr);
     return wgrad_dispatch<float>(p, s, nullptr);
 }
 
@@ -596,7 +606,7 @@ extern "C" int pggan_conv_wgrad_slices(const pg_wgrad_params* p) {
     if (!q.g) q.g = reinterpret_cast<const void*>(uintptr_t(256));      // alignment checks only
     if (!q.x) q.x = reinterpret_cast<const void*>(uintptr_t(256));
     if (!q.acc) q.acc = reinterpret_cast<float*>(uintptr_t(256));
-    if (q.dtype == PG_BF16)
+    if (is16(q.dtype))
         wgrad_dispatch<__nv_bfloat16>(&q, nullptr, &slices);
     else if (q.dtype == PG_F32)
         wgrad_dispatch<float>(&q, nullptr, &slices);

@@ -33,6 +33,7 @@ struct WrKArgs {
     long long slice_elems;
     int B, H, W, C, N;
     int nseg;
+    int f16;                 // operands are IEEE half (else bf16)
     long long total, per_cta;
 };
 
@@ -148,7 +149,7 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         // -------------------------------------------------------------------- MMA issuer(s)
         const int iss = warp == 1 ? 0 : 1;
         if (elect_one()) {    // (not lane == 0: ptxas keeps descriptors in uniform registers only under elect.sync)
-            constexpr uint32_t idesc = make_idesc(1, 1, 1, 128, NCOLS);
+            const uint32_t idesc = make_idesc(a.f16 ? 0 : 1, 1, 1, 128, NCOLS);
             const uint32_t xring_addr = smem_u32(xring), gring_addr = smem_u32(gring);
             uint32_t LX = 0, LG = 0;
             bool first = true;
@@ -250,7 +251,7 @@ static void wr_plan(const pg_wgrad_params* p, long long& total, long long& per_c
 
 bool wgrad_rows_supported(const pg_wgrad_params* p) {
     auto ok = [](int v) { return v == 16 || v == 32 || v == 64; };
-    return p->dtype == PG_BF16 && p->taps == 9 && p->W % 128 == 0 && p->H >= 2 && ok(p->C) && ok(p->N);
+    return is16(p->dtype) && p->taps == 9 && p->W % 128 == 0 && p->H >= 2 && ok(p->C) && ok(p->N);
 }
 
 int wgrad_rows_slices(const pg_wgrad_params* p) {
@@ -268,6 +269,7 @@ static int launch_wr(const pg_wgrad_params* p, cudaStream_t stream) {
     a.slice_elems = static_cast<long long>(p->N) * 9 * p->C;
     a.B = p->B; a.H = p->H; a.W = p->W; a.C = p->C; a.N = p->N;
     a.nseg = p->W / 128;
+    a.f16 = p->dtype == PG_F16;
     int grid;
     wr_plan(p, a.total, a.per_cta, grid);
     CUtensorMap tx, tg;
@@ -275,14 +277,14 @@ static int launch_wr(const pg_wgrad_params* p, cudaStream_t stream) {
         uint64_t dims[4] = {(uint64_t)p->C, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
         uint64_t strides[3] = {(uint64_t)p->C * 2, (uint64_t)p->W * p->C * 2, (uint64_t)p->H * p->W * p->C * 2};
         uint32_t box[4] = {(uint32_t)p->C, (uint32_t)Cfg::kXPW, 1u, 1u};
-        int rc = encode_tmap(&tx, PG_BF16, 4, p->x, dims, strides, box, XSPAN);
+        int rc = encode_tmap(&tx, p->dtype, 4, p->x, dims, strides, box, XSPAN);
         if (rc != PG_OK) return rc;
     }
     {
         uint64_t dims[4] = {(uint64_t)p->N, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
         uint64_t strides[3] = {(uint64_t)p->N * 2, (uint64_t)p->W * p->N * 2, (uint64_t)p->H * p->W * p->N * 2};
         uint32_t box[4] = {(uint32_t)p->N, 128u, 1u, 1u};
-        int rc = encode_tmap(&tg, PG_BF16, 4, p->g, dims, strides, box, GSPAN);
+        int rc = encode_tmap(&tg, p->dtype, 4, p->g, dims, strides, box, GSPAN);
         if (rc != PG_OK) return rc;
     }
     auto kern = wgrad_rows_kernel<XSPAN, GSPAN>;

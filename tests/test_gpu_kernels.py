@@ -8,10 +8,10 @@ from conftest import rel_l2
 
 pytestmark = pytest.mark.gpu
 
-DT = [torch.bfloat16, torch.float32]
-# bf16: outputs are rounded to 8 significant bits (rms rel err ~2e-3); fp32 mode is 3xTF32 (fp32-class)
-# (tensor-core fp32 accumulation truncates: ~2^-24 per MMA step, so long K drifts to ~1e-4)
-TOL = {torch.bfloat16: 4e-3, torch.float32: 2e-4}
+DT = [torch.bfloat16, torch.float32, torch.float16]
+# bf16: outputs are rounded to 8 significant bits (rms rel err ~2e-3), fp16: 11 bits (~2.5e-4); fp32 mode is 3xTF32
+# (fp32-class; tensor-core fp32 accumulation truncates: ~2^-24 per MMA step, so long K drifts to ~1e-4)
+TOL = {torch.bfloat16: 4e-3, torch.float32: 2e-4, torch.float16: 6e-4}
 
 
 @pytest.fixture(autouse=True)
@@ -29,8 +29,8 @@ def _setup():
 
 def rnd(t, dtype):
     """round to the operand precision the tensor core sees, keep fp32 storage"""
-    if dtype == torch.bfloat16:
-        return t.to(torch.bfloat16).float()
+    if dtype in (torch.bfloat16, torch.float16):
+        return t.to(dtype).float()
     return t          # fp32 mode takes full fp32 operands (3xTF32)
 
 
