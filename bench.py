@@ -309,7 +309,10 @@ def run_ours(args):
                        **({"cuda_graph_error": graph_err} if graph_err else {}),
                        "l2_note": "per-step working set (activations of 3 D + 2 G passes and their gradients) is "
                                   "several GB, far above the 126 MB L2; no explicit flush",
-                       "flop_count": f"{gflop_img} GFLOP/img (BASELINE.md W-minimal: D wgrad skipped in the G step)"},
+                       "flop_count": f"{gflop_img} GFLOP/img (BASELINE.md W-minimal: D wgrad skipped in the G step)",
+                       "precision_note": "bf16 is the default (BASELINE config); --dtype fp16 runs the same kernels at "
+                                         "the same speed with an 11-bit significand (forward parity 1e-3 instead of "
+                                         "1e-2, DESIGN.md section 5)"},
             "clocks": clocks,
             "e2e": {"value": round(n_img / (ms_e2e * 1e-3), 2), "unit": "img/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e / args.steps, 3)},
