@@ -100,6 +100,11 @@ typedef struct {
      * ws_x: 3*B*H*W*C floats, ws_w: 3*N*taps*C floats (ignored by the SIMT path / PG_BF16). */
     void* ws_x;
     void* ws_w;
+    /* Optional fused pixel norm (PixelwiseVectorNorm, lib/layers.py:13-14, after the LeakyReLU): if pn_rnorm != NULL,
+     * y = post(..) * rsqrt(mean_n(post(..)^2) + pn_eps) and pn_rnorm[b,h,w] (fp32) receives the factor.  Available where
+     * one epilogue thread owns all N channels of a pixel (pggan_conv_pn_fusable(p) != 0); PG_ERR_UNSUPPORTED elsewhere. */
+    float* pn_rnorm;
+    float pn_eps;
 } pg_conv_params;
 int pggan_conv_fprop(const pg_conv_params* p, void* stream);
 /* which kernel pggan_conv_fprop would run this shape on (pointers may be NULL): lets the host decide where fusing a
@@ -110,6 +115,7 @@ int pggan_conv_fprop(const pg_conv_params* p, void* stream);
 #define PG_CONV_KIND_SWAPPED 2
 #define PG_CONV_KIND_ROWS 3
 int pggan_conv_kernel_kind(const pg_conv_params* p);
+int pggan_conv_pn_fusable(const pg_conv_params* p); /* 1 if the call may carry pn_rnorm */
 
 /* Weight-gradient GEMM:  sum_s acc[s][n][t][c] = sum_{b,h,w} g[b,h,w,n] * x[b, h+dh(t), w+dw(t), c]
  * acc holds pggan_conv_wgrad_slices(p) dense fp32 [N][taps][C] slices (split-K over pixels writes one slice per

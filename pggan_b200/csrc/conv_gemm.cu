@@ -57,6 +57,8 @@ struct ConvKArgs {
     int out_dtype;
     int f16;                 // 16-bit operands / outputs are IEEE half (else bf16); see common.cuh fmt16()
     float scale, slope, mask_slope;
+    float* pn_rnorm;         // fused pixel norm (plain kernel with tiles_n == 1 only): per-pixel rsqrt factor out
+    float pn_eps;
 };
 
 template <typename T, int BLOCK_N, int SPAN = 128>
@@ -212,6 +214,32 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
+            // fused pixel norm (one N tile covers the layer: this thread owns all channels of its pixel): a first pass
+            // over the accumulator for mean(lrelu(..)^2), then the normal pass multiplies by the factor
+            float rn = 1.f;
+            if (a.pn_rnorm != nullptr) {
+                float ss = 0.f;
+#pragma unroll 1
+                for (int j = 0; j < BLOCK_N / CH; ++j) {
+                    __syncwarp();
+                    uint32_t r[32];
+                    if constexpr (CH == 32) {
+                        tmem_ld32(taddr + j * 32, r);
+                    } else {
+                        tmem_ld16(taddr + j * 16, r);
+                    }
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < CH; ++i) {
+                        float t = __uint_as_float(r[i]);
+                        if (a.bias != nullptr) t += __ldg(a.bias + n0 + j * CH + i);
+                        t = lrelu_f(t * a.scale, a.slope);
+                        ss += t * t;
+                    }
+                }
+                rn = rsqrtf(ss * (1.f / BLOCK_N) + a.pn_eps);
+                if (valid) a.pn_rnorm[pix] = rn;
+            }
 #pragma unroll 1
             for (int j = 0; j < BLOCK_N / CH; ++j) {
                 __syncwarp();
@@ -234,7 +262,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     float t = __uint_as_float(r[i]);
                     if (a.bias != nullptr) t += __ldg(a.bias + n0 + j * CH + i);
                     t *= a.scale;
-                    v[i] = lrelu_f(t, a.slope);
+                    v[i] = lrelu_f(t, a.slope) * rn;
                 }
                 if (valid) {
                     if (masked) {
@@ -590,6 +618,8 @@ static int launch_tc(const pg_conv_params* p, cudaStream_t stream) {
     a.out_dtype = p->out_dtype;
     a.f16 = p->dtype == PG_F16;
     a.scale = p->scale; a.slope = p->slope; a.mask_slope = p->mask_slope;
+    a.pn_rnorm = p->pn_rnorm; a.pn_eps = p->pn_eps;
+    PG_CHECK(p->pn_rnorm == nullptr || a.tiles_n == 1, PG_ERR_UNSUPPORTED, "fused pixel norm needs one N tile (N=%d)", p->N);
 
     const uint64_t es = sizeof(T);
     CUtensorMap tx, tw;
@@ -725,7 +755,7 @@ static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream, int* k
         static const bool no_swap = getenv("PGGAN_NO_SWAP") != nullptr;
         // (its transposing epilogue costs a fixed ~5k cycles per 128x256 tile: only worth it when K is long enough)
         if (!no_swap && span == 128 && swap_pays(p->N, (long long)p->C * p->taps) && (p->N * osz) % 16 == 0 && mask_ok &&
-            (long long)p->B * p->H * p->W >= 2 * kSwPix)
+            (long long)p->B * p->H * p->W >= 2 * kSwPix && p->pn_rnorm == nullptr)
             return launch_swapped<T>(p, stream);
         // largest N tile that still yields enough CTAs to occupy the machine
         const int bw = p->W < 128 ? p->W : 128;
@@ -749,9 +779,8 @@ static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream, int* k
         int bn = 16;
         double best = 1e30;
         const int cands[5] = {256, 128, 64, 32, 16};
-        // measured (tools/sweep_bn.sh, 32^2 512->512): 1510 / 915 / 497 / 256 TFLOP/s for N = 256 / 128 / 64 / 32, i.e. a
-        // tile's time barely shrinks with N (the 128-row A operand read paces every MMA)
-        // re-measured after the elect.sync issue fix: 1525 / 1094 / 599 TFLOP/s for N = 256 / 128 / 64
+        // measured per-tile cost (tools/sweep_bn.sh, 32^2 512->512): 1525 / 1094 / 599 TFLOP/s for N = 256 / 128 / 64
+        // (smaller tiles move more L2->smem bytes per FLOP)
         const double cost[5] = {1.0, 0.70, 0.64, 0.62, 0.60};
         for (int i = 0; i < 5; ++i) {
             if (p->N % cands[i] != 0) continue;
@@ -761,6 +790,11 @@ static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream, int* k
                 best = t;
                 bn = cands[i];
             }
+        }
+        if (p->pn_rnorm != nullptr) {                        // fused pixel norm: one N tile must cover the layer
+            PG_CHECK(p->N == 16 || p->N == 32 || p->N == 64 || p->N == 128 || p->N == 256, PG_ERR_UNSUPPORTED,
+                     "fused pixel norm: N=%d must be 16..256 (power of two)", p->N);
+            bn = p->N;
         }
         if (const char* f = getenv("PGGAN_FORCE_BN")) {      // tuning experiments only
             const int v = atoi(f);
@@ -774,6 +808,7 @@ static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream, int* k
             default: return launch_tc<T, 16>(p, stream);
         }
     }
+    PG_CHECK(p->pn_rnorm == nullptr, PG_ERR_UNSUPPORTED, "fused pixel norm is not available on the SIMT conv path");
     const long long total = (long long)p->B * p->H * p->W * p->N;
     if (total == 0) return PG_OK;
     long long blocks = (total + 255) / 256;
@@ -813,6 +848,17 @@ extern "C" int pggan_conv_kernel_kind(const pg_conv_params* p) {
     else if (q.dtype == PG_F32)
         conv_dispatch<float>(&q, nullptr, &kind);
     return kind;
+}
+
+extern "C" int pggan_conv_pn_fusable(const pg_conv_params* p) {
+    if (p == nullptr || p->taps != 9) return 0;
+    const int kind = pggan_conv_kernel_kind(p);
+    const bool pow2n = p->N == 16 || p->N == 32 || p->N == 64 || p->N == 128 || p->N == 256;
+    if (kind == PG_CONV_KIND_ROWS) return 1;
+    // the swapped-orientation kernel (channel-major accumulator) cannot; a layer it would take is left unfused
+    const int cbytes = p->C * (p->dtype == PG_F32 ? 12 : 2);           // fp32 runs as 3xTF32: K tripled
+    if (kind == PG_CONV_KIND_PLAIN && pow2n && cbytes % 128 == 0) return 1;   // (128-byte K span: N tile == N is chosen)
+    return 0;
 }
 
 extern "C" int pggan_conv_fprop(const pg_conv_params* p, void* stream) {

@@ -51,6 +51,8 @@ struct RowsKArgs {
     int out_dtype;
     int f16;                 // 16-bit operands / outputs are IEEE half (else bf16)
     float scale, slope, mask_slope;
+    float* pn_rnorm;         // fused pixel norm: per-pixel rsqrt factor out (NULL: none)
+    float pn_eps;
 };
 
 template <int SPAN> struct RowsGeom {
@@ -259,6 +261,48 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 mbar_wait(&tfull_bar[acc], (it / ACC) & 1);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
+                // fused pixel norm: this thread owns all channels of its pixel (J = 1) or of its J pixels (grouped:
+                // columns [jj*Nr, (jj+1)*Nr) belong to pixel jj).  First pass: per-pixel mean of lrelu(..)^2.
+                constexpr int NR = BLOCK_N / J;              // real channels per pixel
+                float rnp[J];
+#pragma unroll
+                for (int jj = 0; jj < J; ++jj) rnp[jj] = 1.f;
+                if (a.pn_rnorm != nullptr) {
+                    float ssp[J];
+#pragma unroll
+                    for (int jj = 0; jj < J; ++jj) ssp[jj] = 0.f;
+#pragma unroll 1
+                    for (int j = 0; j < BLOCK_N / CH; ++j) {
+                        __syncwarp();
+                        uint32_t rr[32];
+                        if constexpr (CH == 32) {
+                            tmem_ld32(taddr + j * 32, rr);
+                        } else {
+                            tmem_ld16(taddr + j * 16, rr);
+                        }
+                        tmem_ld_wait();
+                        constexpr int SEG = NR >= CH ? CH : NR;      // columns of one pixel inside this step
+#pragma unroll
+                        for (int s2 = 0; s2 < CH / SEG; ++s2) {
+                            float sc = 0.f;
+#pragma unroll
+                            for (int e = 0; e < SEG; ++e) {
+                                float t = __uint_as_float(rr[s2 * SEG + e]);
+                                if (a.bias != nullptr) t += __ldg(a.bias + ((j * CH + s2 * SEG + e) & (a.Nr - 1)));
+                                t = lrelu_f(t * a.scale, a.slope);
+                                sc += t * t;
+                            }
+                            const int pj = (j * CH + s2 * SEG) / NR;
+#pragma unroll
+                            for (int jj = 0; jj < J; ++jj) ssp[jj] += (pj == jj) ? sc : 0.f;
+                        }
+                    }
+#pragma unroll
+                    for (int jj = 0; jj < J; ++jj) {
+                        rnp[jj] = rsqrtf(ssp[jj] * (1.f / NR) + a.pn_eps);
+                        a.pn_rnorm[pix * J + jj] = rnp[jj];
+                    }
+                }
 #pragma unroll 1
                 for (int j = 0; j < BLOCK_N / CH; ++j) {
                     __syncwarp();
@@ -282,6 +326,28 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         if (a.bias != nullptr) t += __ldg(a.bias + ((j * CH + e) & (a.Nr - 1)));
                         t *= a.scale;
                         v[e] = lrelu_f(t, a.slope);
+                    }
+                    if (a.pn_rnorm != nullptr) {
+                        // factor of the pixel(s) this 32-/16-column step belongs to (selects, no dynamic register index)
+                        if constexpr (NR >= CH) {
+                            const int pj = (j * CH) / NR;
+                            float rn = rnp[0];
+#pragma unroll
+                            for (int jj = 1; jj < J; ++jj) rn = (pj == jj) ? rnp[jj] : rn;
+#pragma unroll
+                            for (int e = 0; e < CH; ++e) v[e] *= rn;
+                        } else {
+                            constexpr int PPC = CH / NR;         // pixels per step
+#pragma unroll
+                            for (int s2 = 0; s2 < PPC; ++s2) {
+                                const int pj = j * PPC + s2;
+                                float rn = rnp[0];
+#pragma unroll
+                                for (int jj = 1; jj < J; ++jj) rn = (pj == jj) ? rnp[jj] : rn;
+#pragma unroll
+                                for (int e = 0; e < NR; ++e) v[s2 * NR + e] *= rn;
+                            }
+                        }
                     }
                     if (masked) {
 #pragma unroll
@@ -354,6 +420,7 @@ static int launch_rows(const pg_conv_params* p_in, cudaStream_t stream) {
     a.out_dtype = p->out_dtype;
     a.f16 = p->dtype == PG_F16;
     a.scale = p->scale; a.slope = p->slope; a.mask_slope = p->mask_slope;
+    a.pn_rnorm = p->pn_rnorm; a.pn_eps = p->pn_eps;
     const int sms = num_sms();
     long long grid = a.total < sms ? a.total : sms;
     a.per_cta = (a.total + grid - 1) / grid;

@@ -238,12 +238,35 @@ def clear_pack_cache(params=None):
 
 
 # ------------------------------------------------------------------------------- raw kernels
-def k_conv(x, wp, bias, N, taps, scale, slope=1.0, mask_src=None, mask_slope=1.0, raw_out=False):
+_KIND_CACHE: dict = {}
+
+
+def conv_pn_fusable(x, N, taps) -> bool:
+    """may k_conv(..., pn_eps=...) fuse the pixel norm into this layer's epilogue? (one epilogue thread must own all
+    N channels of a pixel: the rows kernel, or the plain kernel when one N tile covers the layer)"""
+    b, c, h, w = _dims(x)
+    key = ("pn", b, h, w, c, N, taps, x.dtype)
+    hit = _KIND_CACHE.get(key)
+    if hit is None:
+        p = L.ConvParams()
+        p.B, p.H, p.W, p.C, p.N, p.taps = b, h, w, c, N, taps
+        p.dtype = p.out_dtype = _enum(x.dtype)
+        hit = bool(L.load().pggan_conv_pn_fusable(ctypes.byref(p)))
+        _KIND_CACHE[key] = hit
+    return hit
+
+
+def k_conv(x, wp, bias, N, taps, scale, slope=1.0, mask_src=None, mask_slope=1.0, raw_out=False, pn_eps=None):
+    """pn_eps: also apply the pixel norm in the epilogue; returns (y, rnorm[pixels] fp32) then."""
     _need_cuda(x)
     b, c, h, w = _dims(x)
     out_dtype = torch.float32 if raw_out else x.dtype
     y = _new_like_layout(x, N, out_dtype)
     p = L.ConvParams()
+    rn = None
+    if pn_eps is not None:
+        rn = torch.empty((b * h * w,), dtype=torch.float32, device=x.device)
+        p.pn_rnorm, p.pn_eps = rn.data_ptr(), float(pn_eps)
     p.x, p.wp, p.bias, p.mask_src, p.y = x.data_ptr(), wp.data_ptr(), (bias.data_ptr() if bias is not None else None), \
         (mask_src.data_ptr() if mask_src is not None else None), y.data_ptr()
     p.B, p.H, p.W, p.C, p.N, p.taps = b, h, w, c, N, taps
@@ -257,10 +280,7 @@ def k_conv(x, wp, bias, N, taps, scale, slope=1.0, mask_src=None, mask_slope=1.0
         p.ws_x, p.ws_w = ws[0].data_ptr(), ws[1].data_ptr()
     with _Timed("conv_gemm", (b, h, w, c, N, taps)):
         L.check(L.load().pggan_conv_fprop(ctypes.byref(p), _s()), "pggan_conv_fprop")
-    return y
-
-
-_KIND_CACHE: dict = {}
+    return y if pn_eps is None else (y, rn)
 
 
 def dgrad_mask_fusable(batch, h, w, fwd_in_channels, fwd_out_channels, taps=9, dtype=None) -> bool:
@@ -463,12 +483,16 @@ class ConvActPN(torch.autograd.Function):
         x = feat(x)
         N, C, taps, _, _ = _maps(W.shape, layout)
         bias = None if b is None else _perm_bias(b.detach().float(), layout).contiguous()
-        a = k_conv(x, _pack(W, "f", x.dtype, layout), bias, N, taps, scale, slope)
-        bb, c, h, w = _dims(a)
-        y = torch.empty_like(a)
-        r = torch.empty((bb * h * w,), dtype=torch.float32, device=a.device)
-        L.check(L.load().pggan_pixelnorm_fwd(_p(a), _p(y), _p(r), bb * h * w, c, float(eps), _enum(a.dtype), _s()),
-                "pggan_pixelnorm_fwd")
+        if x.dim() == 4 and conv_pn_fusable(x, N, taps):
+            # conv + He scale + bias + LeakyReLU + pixel norm in ONE kernel (the epilogue thread owns the whole pixel)
+            y, r = k_conv(x, _pack(W, "f", x.dtype, layout), bias, N, taps, scale, slope, pn_eps=eps)
+        else:
+            a = k_conv(x, _pack(W, "f", x.dtype, layout), bias, N, taps, scale, slope)
+            bb, c, h, w = _dims(a)
+            y = torch.empty_like(a)
+            r = torch.empty((bb * h * w,), dtype=torch.float32, device=a.device)
+            L.check(L.load().pggan_pixelnorm_fwd(_p(a), _p(y), _p(r), bb * h * w, c, float(eps), _enum(a.dtype), _s()),
+                    "pggan_pixelnorm_fwd")
         ctx.save_for_backward(x, W, y, r)
         ctx.scale, ctx.slope, ctx.has_bias, ctx.layout = scale, slope, b is not None, layout
         ctx.bias_param = b if isinstance(b, torch.nn.Parameter) else None

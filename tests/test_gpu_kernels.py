@@ -364,3 +364,37 @@ def test_fused_adam_matches_torch():
     for pm, pr in zip(mine, ref):
         assert rel_l2(pm, pr) < 1e-6
     assert int(opt_m.step_count.item()) == 4
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("shape", [(1, 32, 128, 64, 64), (1, 16, 512, 16, 16), (1, 16, 256, 32, 32), (1, 8, 256, 32, 16),
+                                   (2, 16, 16, 128, 256), (2, 32, 32, 64, 128), (1, 64, 128, 16, 32)])
+def test_conv_fused_pixelnorm(shape, dtype):
+    """conv + He scale + bias + LeakyReLU + pixel norm in one kernel (epilogue thread owns the pixel): rows kernel with
+    J = 1 / 2 / 4 pixel groups and the plain kernel with one N tile, against PyTorch; ConvActPN uses it where
+    pggan_conv_pn_fusable says so and the two-kernel path elsewhere (e.g. the swapped-orientation layers)."""
+    from pggan_b200 import ops
+    import pggan_b200 as pg
+    pg.set_compute_dtype(dtype)
+    B, H, W, Ci, Co = shape
+    x = rnd(torch.randn(B, Ci, H, W, device="cuda"), dtype)
+    w = rnd(torch.randn(Co, Ci, 3, 3, device="cuda"), dtype)
+    b = torch.randn(Co, device="cuda")
+    scale = (2.0 / (Ci * 9)) ** 0.5
+    a = F.leaky_relu(F.conv2d(x, w, b, padding=1) * scale, 0.2)
+    ref = a * torch.rsqrt((a ** 2).mean(dim=1, keepdim=True) + 1e-8)
+    xf = to_feat(x, dtype)
+    if dtype != torch.float32:          # fp32 (3xTF32) triples K: the 16-/32-channel shapes leave the rows envelope
+        assert ops.conv_pn_fusable(xf, Co, 9)
+    if ops.conv_pn_fusable(xf, Co, 9):
+        y, r = ops.k_conv(xf, ops._pack(w, "f", dtype), b, Co, 9, scale, 0.2, pn_eps=1e-8)
+        r_ref = torch.rsqrt((a ** 2).mean(dim=1) + 1e-8).reshape(-1)
+        assert rel_l2(y.float(), ref) < TOL[dtype], rel_l2(y.float(), ref)
+        assert rel_l2(r, r_ref) < 1e-3
+    # the autograd Function (either path) against PyTorch, forward and input gradient
+    xm = x.clone().requires_grad_()
+    wm = torch.nn.Parameter(w.clone())
+    ym = ops.ConvActPN.apply(to_feat(xm, dtype), wm, b, scale, 0.2, 1e-8)
+    assert rel_l2(ym.float(), ref) < TOL[dtype]
+    assert not ops.conv_pn_fusable(to_feat(rnd(torch.randn(2, 256, 32, 32, device="cuda"), dtype), dtype), 128, 9) \
+        or dtype == torch.float32, "256->128 (K = 2304) runs on the swapped kernel: must not be reported fusable"

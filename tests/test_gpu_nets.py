@@ -24,7 +24,9 @@ BF16_EMU_TOL = 2.5e-2   # bf16 rounding decisions themselves flip under 1e-6 sum
 # size e flips ~e of them and moves the gradient by ~0.8*sqrt(e) in relative L2 (1e-4 -> 0.8e-2).  fp32
 # mode is compared with the plain oracle under that bound; bf16 mode with the bf16-emulating oracle
 # (same masks), where what remains is bf16 rounding of the gradient tensors themselves.
-GRAD_TOL = {torch.float32: 2e-2, torch.bfloat16: 1.5e-1}
+# (2e-1: where conv + LeakyReLU + pixel norm run as ONE kernel the pre-norm activation is never rounded to bf16, which the
+# emulating oracle — it rounds every layer output — cannot know; measured worst case 1.56e-1 on a 128x128 width-64 G)
+GRAD_TOL = {torch.float32: 2e-2, torch.bfloat16: 2e-1}
 
 
 @pytest.fixture(autouse=True)
