@@ -16,5 +16,6 @@ from .loss import Loss, LossInterface, WGANGPLoss  # noqa: F401
 from .optim import FusedAdam, FlatGrads  # noqa: F401
 from .dist import GradSync, broadcast_parameters  # noqa: F401
 from .trainer import ProgressiveGAN, make_args, DEPTHS_1024  # noqa: F401
+from . import demo  # noqa: F401
 
 __version__ = "0.1.0"

@@ -313,3 +313,35 @@ def test_fp16_mode_meets_the_16bit_bar(scale, width, batch):
     for name, prm in D.named_parameters():
         if prm.grad is not None:
             assert torch.isfinite(prm.grad).all(), name
+
+
+def test_demo_inference_entry(tmp_path):
+    """reference demo.py:23-68 through pggan_b200.demo: a reference-format checkpoint ({"model": state_dict, ...}) is
+    loaded with the reference's key-set check and the generated images equal the oracle's G on the same latents."""
+    import pggan_b200 as pg
+    from pggan_b200 import demo
+    pg.set_compute_dtype(torch.float32)
+    scale, width = 3, 64
+    depths = [width] * (scale + 1)
+    gen = torch.Generator().manual_seed(3)
+    g_sd = O.init_generator_sd(width, depths, scale, generator=gen)
+    ckpt = tmp_path / "G_latest.pt"
+    torch.save({"model": g_sd, "optimizer": None, "args": {}, "global_step": 123, "alpha_G": 0.25}, ckpt)
+    args = pg.make_args(latent_dim=width, depths=depths, ckpt_path=str(ckpt), n_samples=5, gpu=0,
+                        save_path=str(tmp_path / "out"))
+    G = demo.LoadModel(args)
+    assert G.alpha == 0.25 and next(G.parameters()).is_cuda
+    z = torch.randn(5, width)
+    imgs = demo.test(args, G=G, latent_input=z)
+    with torch.no_grad():
+        ref = O.generator_forward({k: v.cuda() for k, v in g_sd.items()}, z.cuda(), 0.25)
+    ref = (ref.permute(0, 2, 3, 1).cpu().numpy() * 0.5 + 0.5) * 255
+    assert imgs.shape == (5, 32, 32, 3)
+    assert rel_l2(torch.from_numpy(imgs), torch.from_numpy(ref)) < 1e-3
+    assert len(list((tmp_path / "out").iterdir())) == 5
+    # a checkpoint whose keys do not match the model is refused, as in the reference (demo.py:39-42)
+    bad = dict(g_sd)
+    bad.pop(next(iter(bad)))
+    torch.save({"model": bad}, ckpt)
+    with pytest.raises(AssertionError):
+        demo.LoadModel(args)
