@@ -276,14 +276,28 @@ def run_ours(args):
                               "tflops": round(fl / (t_ms / n_l * 1e-3) / 1e12, 1)})
         peak_burst, peak_sus, hbm, src = measured_peaks()
         achieved = flops / (top_ms / top_n * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": f"{kind} B{b_} {h_}x{w_} C{c_}->N{n_} taps{taps_}",
-                "achieved": round(achieved, 1), "peak": peak_sus, "unit": "TFLOP/s",
-                "frac": round(achieved / peak_sus, 4), "peak_source": f"bf16_tflops_sustained ({src})",
+        # algorithmic bytes of the launch: activations in + out once (16-bit), packed weights once; wgrad reads g and x
+        es = 2 if dtype != torch.float32 else 4
+        pix = b_ * h_ * w_
+        abytes = es * pix * (c_ + n_) + (es if kind == "conv_gemm" else 4) * taps_ * c_ * n_
+        ridge = peak_sus * 1e12 / (hbm * 1e9)               # FLOP per byte where the two roofs meet
+        hbm_bound = flops / abytes < ridge
+        achieved_gbs = abytes / (top_ms / top_n * 1e-3) / 1e9
+        roof = {"bound": "hbm" if hbm_bound else "tensor",
+                "kernel": f"{kind} B{b_} {h_}x{w_} C{c_}->N{n_} taps{taps_}",
+                "achieved": round(achieved_gbs if hbm_bound else achieved, 1), "peak": hbm if hbm_bound else peak_sus,
+                "unit": "GB/s" if hbm_bound else "TFLOP/s",
+                "frac": round((achieved_gbs / hbm) if hbm_bound else (achieved / peak_sus), 4),
+                "peak_source": (f"hbm_gbs ({src})" if hbm_bound else f"bf16_tflops_sustained ({src})"),
+                "arithmetic_intensity_flop_per_byte": round(flops / abytes, 1), "algorithmic_bytes": abytes,
+                "achieved_tflops": round(achieved, 1),
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel/shape from the committed
                 # `ncu --set full` capture profiles/r1_ncu_gemm_full.md (71.9 MB read + 22.3 MB written; the
                 # algorithmic bytes are 67.1 MB in + 4.7 MB weights + 67.1 MB out, most of the output is still
                 # in L2 when the kernel ends)
-                "traffic": 94.2e6 if (kind, b_, h_, w_, c_, n_, taps_) == ("conv_gemm", 64, 32, 32, 512, 512, 9) else None,
+                # (and profiles/r1_ncu_rows.md for the 1024^2 16->16 conv_rows launch: 139.8 MB read + 82.1 MB written)
+                "traffic": {("conv_gemm", 64, 32, 32, 512, 512, 9): 94.2e6,
+                            ("conv_gemm", 4, 1024, 1024, 16, 16, 9): 221.9e6}.get((kind, b_, h_, w_, c_, n_, taps_)),
                 "launches_per_step": top_n // nprof,
                 "avg_launch_ms": round(top_ms / top_n, 4),
                 "share_of_gemm_time": round(top_ms / step_total, 3),
