@@ -36,13 +36,17 @@ constexpr int kConvThreadsPlain = 320;     // plain kernel: 2 x 4 epilogue warps
 
 // SPAN = bytes of K per chunk = the TMA/UMMA swizzle span: 128 normally; 64 / 32 for layers whose channel
 // count times element size is only 64 / 32 bytes (the 32- and 16-channel stages of the 1024^2 network)
-template <int BLOCK_N, int SPAN = 128> struct ConvCfg {
-    static constexpr int kABytesS = kBlockM * SPAN;
+// MT = 128-pixel M tiles per CTA tile.  MT = 2 with BLOCK_N = 128 gives a 256 x 128 tile: two MMAs per K-step share the
+// weight tile, so the L2->smem bytes per FLOP equal those of the 128 x 256 tile (a 128 x 128 tile moves 1.33x more and
+// measured 1 094 vs 1 525 TFLOP/s on the 32^2 layer); used for the big N = 128 layers of the 128^2 / 256^2 stages.
+template <int BLOCK_N, int SPAN = 128, int MT = 1> struct ConvCfg {
+    static constexpr int kABytesS = MT * kBlockM * SPAN;
     static constexpr int kBBytes = BLOCK_N * SPAN;
     static constexpr int kStageBytes = kABytesS + kBBytes;
     static constexpr int kStagesRaw = 196608 / kStageBytes;
-    static constexpr int kStages = SPAN == 128 ? ((BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8)) : (kStagesRaw > 8 ? 8 : kStagesRaw);
-    static constexpr int kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
+    static constexpr int kStages = SPAN == 128 ? ((MT * BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8)) : (kStagesRaw > 8 ? 8 : kStagesRaw);
+    static constexpr int kTmemCols = (2 * MT * BLOCK_N < 32) ? 32 : 2 * MT * BLOCK_N;
+    static_assert(2 * MT * BLOCK_N <= 512, "TMEM");
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -61,11 +65,11 @@ struct ConvKArgs {
     float pn_eps;
 };
 
-template <typename T, int BLOCK_N, int SPAN = 128>
+template <typename T, int BLOCK_N, int SPAN = 128, int MT = 1>
 __global__ void __launch_bounds__(kConvThreadsPlain, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                  const ConvKArgs a) {
-    using Cfg = ConvCfg<BLOCK_N, SPAN>;
+    using Cfg = ConvCfg<BLOCK_N, SPAN, MT>;
     constexpr bool kTF32 = (sizeof(T) == 4);
     constexpr int BK = SPAN / sizeof(T);          // elements per K chunk (one swizzle span)
     constexpr int kMmaPerChunk = SPAN / 32;       // 32 B per UMMA K-step
@@ -152,7 +156,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 const uint32_t acc_phase = (it >> 1) & 1;
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                const uint32_t d_tmem = tmem_base + acc * (MT * BLOCK_N);
                 for (int kc = 0; kc < num_kc; ++kc) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
@@ -161,8 +165,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     const uint64_t bdesc = make_smem_desc(sa + kABytes, 16, kSBO, kLayout);
 #pragma unroll
                     for (int k = 0; k < kMmaPerChunk; ++k) {
-                        // advance 32 bytes along K inside the swizzle span: +2 in 16-byte units
-                        umma_ss<kTF32>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) != 0);
+                        // advance 32 bytes along K inside the swizzle span: +2 in 16-byte units; M tile m starts
+                        // 128 rows further down the A box and owns its own BLOCK_N accumulator columns
+#pragma unroll
+                        for (int m = 0; m < MT; ++m)
+                            umma_ss<kTF32>(d_tmem + m * BLOCK_N, adesc + 2 * k + m * ((kBlockM * SPAN) >> 4), bdesc + 2 * k,
+                                           idesc, (kc | k) != 0);
                     }
                     umma_commit(&empty_bar[stage]);     // frees the smem slot when these MMAs retire
                     if (++stage == kStages) {
@@ -176,10 +184,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     } else {
         // ---------------------------------------------------------------------- epilogue
         const int q = warp & 3;                        // TMEM lane quarter this warp may read
-        const int row = q * 32 + lane;
-        const int wo = row % a.BW;
-        const int ho = (row / a.BW) % a.BH;
-        const int bo = row / (a.BW * a.BH);
         // one epilogue warp per SM sub-partition is latency-bound on short-K layers (the epilogue of a 128 x N tile
         // is ~N/32 x 450 dependent instructions): two groups of four warps drain the two TMEM accumulators concurrently
         const int egroup = (warp - 2) >> 2;
@@ -194,6 +198,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             const int h0 = ((mt / a.tiles_w) % a.tiles_h) * a.BH;
             const int b0 = (mt / (a.tiles_w * a.tiles_h)) * a.BB;
             const int n0 = nt * BLOCK_N;
+#pragma unroll 1
+            for (int m = 0; m < MT; ++m) {                   // this thread's row in each 128-pixel M tile of the box
+            const int row = m * kBlockM + q * 32 + lane;
+            const int wo = row % a.BW;
+            const int ho = (row / a.BW) % a.BH;
+            const int bo = row / (a.BW * a.BH);
             const int b = b0 + bo;
             const bool valid = b < a.B;
             const size_t pix = (static_cast<size_t>(b) * a.H + (h0 + ho)) * a.W + (w0 + wo);
@@ -213,7 +223,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             }
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * (MT * BLOCK_N) + m * BLOCK_N;
             // fused pixel norm (one N tile covers the layer: this thread owns all channels of its pixel): a first pass
             // over the accumulator for mean(lrelu(..)^2), then the normal pass multiplies by the factor
             float rn = 1.f;
@@ -301,6 +311,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     }
                 }
             }
+            }   // m
             tc_fence_before();
             mbar_arrive(&tempty_bar[acc]);
         }
@@ -595,20 +606,34 @@ static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 // swapped orientation (256 pixels on the MMA N dimension) vs the plain kernel with a small N tile, measured on the
 // 128^2 / 256^2 layer shapes after the issue fix: 128->64 266 vs 285 us, 256->128 132 vs 156 us (swapped wins),
 // 128->128 116 vs 89 us (plain wins): the transposing epilogue needs K >= 1152 at N <= 64, K >= 2304 at N = 128
-static bool swap_pays(int n, long long k) { return (n <= 64 && k >= 1152) || (n <= 128 && k >= 2304); }
+// (with the 256 x 128 tile of the plain kernel the N = 128 case goes the other way too — 256->128: 126 vs 132 us — so a
+// big N = 128 layer never swaps; `big` = that tile shape applies)
+static bool swap_pays(int n, long long k, bool big) {
+    return (n <= 64 && k >= 1152) || (n <= 128 && k >= 2304 && !(n == 128 && big));
+}
+// the 256 x 128 tile (MT = 2) applies to N % 128 == 0 layers with at least 4 tiles per SM
+static bool m2_applies(const pg_conv_params* p, int sms) {
+    const int bw = p->W < 128 ? p->W : 128;
+    const int bh = p->H < (128 / bw) ? p->H : (128 / bw);
+    const int bb = 128 / (bw * bh);
+    const long long m_tiles = (long long)(p->W / bw) * (p->H / bh) * ((p->B + bb - 1) / bb);
+    return p->N % 128 == 0 && m_tiles * (p->N / 128) >= 4LL * sms && (long long)p->W * p->H * p->B >= 512 &&
+           (p->W >= 256 || (256 % p->W == 0));
+}
 
-template <typename T, int BLOCK_N, int SPAN = 128>
+template <typename T, int BLOCK_N, int SPAN = 128, int MT = 1>
 static int launch_tc(const pg_conv_params* p, cudaStream_t stream) {
-    using Cfg = ConvCfg<BLOCK_N, SPAN>;
+    using Cfg = ConvCfg<BLOCK_N, SPAN, MT>;
+    constexpr int kTileM = MT * kBlockM;
     constexpr int BK = SPAN / sizeof(T);
     ConvKArgs a;
     a.bias = p->bias;
     a.mask_src = p->mask_src;
     a.y = p->y;
     a.B = p->B; a.H = p->H; a.W = p->W; a.N = p->N;
-    a.BW = p->W < 128 ? p->W : 128;
-    a.BH = p->H < (128 / a.BW) ? p->H : (128 / a.BW);
-    a.BB = 128 / (a.BW * a.BH);
+    a.BW = p->W < kTileM ? p->W : kTileM;
+    a.BH = p->H < (kTileM / a.BW) ? p->H : (kTileM / a.BW);
+    a.BB = kTileM / (a.BW * a.BH);
     a.tiles_w = p->W / a.BW;
     a.tiles_h = p->H / a.BH;
     a.tiles_b = (p->B + a.BB - 1) / a.BB;
@@ -638,7 +663,7 @@ static int launch_tc(const pg_conv_params* p, cudaStream_t stream) {
         int rc = encode_tmap(&tw, p->dtype, 2, p->wp, dims, strides, box, SPAN);
         if (rc != PG_OK) return rc;
     }
-    auto kern = conv_gemm_kernel<T, BLOCK_N, SPAN>;
+    auto kern = conv_gemm_kernel<T, BLOCK_N, SPAN, MT>;
     static bool attr_done = false;   // per template instantiation
     if (!attr_done) {
         PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -726,7 +751,7 @@ static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream, int* k
             static const bool no_swap_k = getenv("PGGAN_NO_SWAP") != nullptr;
             if (!kF32 && !no_rows_k && conv_rows_supported(p))
                 *kind_out = PG_CONV_KIND_ROWS;
-            else if (!no_swap_k && span == 128 && swap_pays(p->N, (long long)Ceff * p->taps) && (p->N * osz_k) % 16 == 0 &&
+            else if (!no_swap_k && span == 128 && swap_pays(p->N, (long long)Ceff * p->taps, m2_applies(p, num_sms())) && (p->N * osz_k) % 16 == 0 &&
                      (long long)p->B * p->H * p->W >= 2 * kSwPix)
                 *kind_out = PG_CONV_KIND_SWAPPED;
             else
@@ -754,7 +779,7 @@ static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream, int* k
         const bool mask_ok = p->mask_src == nullptr || osz == (int)sizeof(T);
         static const bool no_swap = getenv("PGGAN_NO_SWAP") != nullptr;
         // (its transposing epilogue costs a fixed ~5k cycles per 128x256 tile: only worth it when K is long enough)
-        if (!no_swap && span == 128 && swap_pays(p->N, (long long)p->C * p->taps) && (p->N * osz) % 16 == 0 && mask_ok &&
+        if (!no_swap && span == 128 && swap_pays(p->N, (long long)p->C * p->taps, m2_applies(p, num_sms())) && (p->N * osz) % 16 == 0 && mask_ok &&
             (long long)p->B * p->H * p->W >= 2 * kSwPix && p->pn_rnorm == nullptr)
             return launch_swapped<T>(p, stream);
         // largest N tile that still yields enough CTAs to occupy the machine
@@ -800,6 +825,9 @@ static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream, int* k
             const int v = atoi(f);
             if ((v == 16 || v == 32 || v == 64 || v == 128 || v == 256) && p->N % v == 0) bn = v;
         }
+        // N tile 128 on a big layer: 256 x 128 tiles (two MMAs per K-step share the weight tile)
+        static const bool no_m2 = getenv("PGGAN_NO_M2") != nullptr;
+        if (bn == 128 && !no_m2 && m2_applies(p, sms)) return launch_tc<T, 128, 128, 2>(p, stream);
         switch (bn) {
             case 256: return launch_tc<T, 256>(p, stream);
             case 128: return launch_tc<T, 128>(p, stream);
