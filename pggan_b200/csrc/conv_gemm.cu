@@ -32,7 +32,7 @@ int conv_rows_launch(const pg_conv_params* p, cudaStream_t stream);
 
 constexpr int kBlockM = 128;
 constexpr int kConvThreads = 192;          // swapped kernel: TMA warp, MMA warp, 4 epilogue warps
-constexpr int kConvThreadsPlain = 320;     // plain kernel: 2 x 4 epilogue warps taking alternate tiles
+constexpr int kConvThreadsPlain = 352;     // plain kernel: 2 x 4 epilogue warps taking alternate tiles + a second MMA warp
 
 // SPAN = bytes of K per chunk = the TMA/UMMA swizzle span: 128 normally; 64 / 32 for layers whose channel
 // count times element size is only 64 / 32 bytes (the 32- and 16-channel stages of the 1024^2 network)
@@ -44,7 +44,8 @@ template <int BLOCK_N, int SPAN = 128, int MT = 1> struct ConvCfg {
     static constexpr int kBBytes = BLOCK_N * SPAN;
     static constexpr int kStageBytes = kABytesS + kBBytes;
     static constexpr int kStagesRaw = 196608 / kStageBytes;
-    static constexpr int kStages = SPAN == 128 ? ((MT * BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8)) : (kStagesRaw > 8 ? 8 : kStagesRaw);
+    static constexpr int kStagesWant = SPAN == 128 ? ((MT * BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8)) : 8;
+    static constexpr int kStages = kStagesRaw < kStagesWant ? kStagesRaw : kStagesWant;
     static constexpr int kTmemCols = (2 * MT * BLOCK_N < 32) ? 32 : 2 * MT * BLOCK_N;
     static_assert(2 * MT * BLOCK_N <= 512, "TMEM");
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -92,12 +93,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_x);
         tma_prefetch_desc(&tmap_w);
+        // MT = 2: each 128-pixel M tile has its own MMA warp (one issuing thread sustains an MMA per ~62 cycles, two
+        // reach ~48 at N = 64: tools/probe_issue.cu), so a smem stage / an accumulator is released by MT commits
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], MT);
         }
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tfull_bar[s], MT);
             mbar_init(&tempty_bar[s], 128);
         }
         fence_mbar_init();
@@ -144,8 +147,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 }
             }
         }
-    } else if (warp == 1) {
-        // -------------------------------------------------------------------- MMA issuer
+    } else if (warp == 1 || (warp == 10 && MT == 2)) {
+        // -------------------------------------------------------------------- MMA issuer(s): M tile `mi`
+        const int mi = warp == 1 ? 0 : 1;
         if (elect_one()) {    // (not lane == 0: ptxas keeps descriptors in uniform registers only under elect.sync)
             const uint32_t idesc = make_idesc(kTF32 ? 2 : (a.f16 ? 0 : 1), 0, 0, kBlockM, BLOCK_N);
             int stage = 0;
@@ -167,10 +171,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     for (int k = 0; k < kMmaPerChunk; ++k) {
                         // advance 32 bytes along K inside the swizzle span: +2 in 16-byte units; M tile m starts
                         // 128 rows further down the A box and owns its own BLOCK_N accumulator columns
-#pragma unroll
-                        for (int m = 0; m < MT; ++m)
-                            umma_ss<kTF32>(d_tmem + m * BLOCK_N, adesc + 2 * k + m * ((kBlockM * SPAN) >> 4), bdesc + 2 * k,
-                                           idesc, (kc | k) != 0);
+                        umma_ss<kTF32>(d_tmem + mi * BLOCK_N, adesc + 2 * k + mi * ((kBlockM * SPAN) >> 4), bdesc + 2 * k,
+                                       idesc, (kc | k) != 0);
                     }
                     umma_commit(&empty_bar[stage]);     // frees the smem slot when these MMAs retire
                     if (++stage == kStages) {
@@ -181,7 +183,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 umma_commit(&tfull_bar[acc]);           // accumulator complete -> epilogue
             }
         }
-    } else {
+    } else if (warp >= 2 && warp < 10) {
         // ---------------------------------------------------------------------- epilogue
         const int q = warp & 3;                        // TMEM lane quarter this warp may read
         // one epilogue warp per SM sub-partition is latency-bound on short-K layers (the epilogue of a 128 x N tile
@@ -609,15 +611,16 @@ static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 // (with the 256 x 128 tile of the plain kernel the N = 128 case goes the other way too — 256->128: 126 vs 132 us — so a
 // big N = 128 layer never swaps; `big` = that tile shape applies)
 static bool swap_pays(int n, long long k, bool big) {
-    return (n <= 64 && k >= 1152) || (n <= 128 && k >= 2304 && !(n == 128 && big));
+    if (big && (n == 128 || n == 64)) return false;      // 256 x N tiles: 128->64 @256^2 189 us vs 266 us swapped
+    return (n <= 64 && k >= 1152) || (n <= 128 && k >= 2304);
 }
 // the 256 x 128 tile (MT = 2) applies to N % 128 == 0 layers with at least 4 tiles per SM
-static bool m2_applies(const pg_conv_params* p, int sms) {
+static bool m2_applies(const pg_conv_params* p, int sms, int bn = 128) {
     const int bw = p->W < 128 ? p->W : 128;
     const int bh = p->H < (128 / bw) ? p->H : (128 / bw);
     const int bb = 128 / (bw * bh);
     const long long m_tiles = (long long)(p->W / bw) * (p->H / bh) * ((p->B + bb - 1) / bb);
-    return p->N % 128 == 0 && m_tiles * (p->N / 128) >= 4LL * sms && (long long)p->W * p->H * p->B >= 512 &&
+    return p->N % bn == 0 && m_tiles * (p->N / bn) >= 4LL * sms && (long long)p->W * p->H * p->B >= 512 &&
            (p->W >= 256 || (256 % p->W == 0));
 }
 
@@ -751,7 +754,7 @@ static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream, int* k
             static const bool no_swap_k = getenv("PGGAN_NO_SWAP") != nullptr;
             if (!kF32 && !no_rows_k && conv_rows_supported(p))
                 *kind_out = PG_CONV_KIND_ROWS;
-            else if (!no_swap_k && span == 128 && swap_pays(p->N, (long long)Ceff * p->taps, m2_applies(p, num_sms())) && (p->N * osz_k) % 16 == 0 &&
+            else if (!no_swap_k && span == 128 && swap_pays(p->N, (long long)Ceff * p->taps, m2_applies(p, num_sms(), p->N == 64 ? 64 : 128)) && (p->N * osz_k) % 16 == 0 &&
                      (long long)p->B * p->H * p->W >= 2 * kSwPix)
                 *kind_out = PG_CONV_KIND_SWAPPED;
             else
@@ -779,7 +782,7 @@ static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream, int* k
         const bool mask_ok = p->mask_src == nullptr || osz == (int)sizeof(T);
         static const bool no_swap = getenv("PGGAN_NO_SWAP") != nullptr;
         // (its transposing epilogue costs a fixed ~5k cycles per 128x256 tile: only worth it when K is long enough)
-        if (!no_swap && span == 128 && swap_pays(p->N, (long long)p->C * p->taps, m2_applies(p, num_sms())) && (p->N * osz) % 16 == 0 && mask_ok &&
+        if (!no_swap && span == 128 && swap_pays(p->N, (long long)p->C * p->taps, m2_applies(p, num_sms(), p->N == 64 ? 64 : 128)) && (p->N * osz) % 16 == 0 && mask_ok &&
             (long long)p->B * p->H * p->W >= 2 * kSwPix && p->pn_rnorm == nullptr)
             return launch_swapped<T>(p, stream);
         // largest N tile that still yields enough CTAs to occupy the machine
@@ -828,6 +831,7 @@ static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream, int* k
         // N tile 128 on a big layer: 256 x 128 tiles (two MMAs per K-step share the weight tile)
         static const bool no_m2 = getenv("PGGAN_NO_M2") != nullptr;
         if (bn == 128 && !no_m2 && m2_applies(p, sms)) return launch_tc<T, 128, 128, 2>(p, stream);
+        if (bn == 64 && !no_m2 && m2_applies(p, sms, 64)) return launch_tc<T, 64, 128, 2>(p, stream);
         switch (bn) {
             case 256: return launch_tc<T, 256>(p, stream);
             case 128: return launch_tc<T, 128>(p, stream);
