@@ -930,14 +930,20 @@ extern "C" int pggan_unpack_wgrad(const float* in, float* out, const pg_pack_map
                         m.s_n1 == 9LL * m.c_valid && m.n_valid == m.n_total && m.c_total <= kPackMaxI;
     const long long slice_elems = (long long)m.n_total * m.taps * m.c_total;
     if (oihw_f) {
-        int spb = slices, groups = 1;
-        if (slices > 32 && m.n_total < 2 * num_sms()) {      // few, long reductions: spread the slices over the SMs
-            spb = 16;
-            groups = (slices + spb - 1) / spb;
-            if (!accumulate) PG_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)m.n_total * 9 * m.c_valid, s));
-        }
         int zchunks = 1;                 // channel chunks of >= 128 (a multiple of 4 keeps the float4 path)
         while (zchunks < 4 && m.c_valid / (zchunks * 2) >= 128 && m.c_valid % (zchunks * 2 * 4) == 0) zchunks *= 2;
+        // few output rows but several slices (narrow layers: ncu showed 64 blocks summing 29 slices in 38 us): split
+        // the slices over enough blocks to cover the machine twice; the slice groups meet through atomics
+        int spb = slices, groups = 1;
+        const int want_blocks = 2 * num_sms();
+        if (slices >= 4 && m.n_total * zchunks < want_blocks) {
+            groups = (want_blocks + m.n_total * zchunks - 1) / (m.n_total * zchunks);
+            if (groups > slices) groups = slices;
+            spb = (slices + groups - 1) / groups;
+            groups = (slices + spb - 1) / spb;
+            if (groups > 1 && !accumulate)
+                PG_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)m.n_total * 9 * m.c_valid, s));
+        }
         unpack_oihw_kernel<<<dim3(m.n_total, groups, zchunks), 256, 9 * m.c_valid * sizeof(float), s>>>(
             in, out, m.c_valid, m.c_total, scale, accumulate, slices, slice_elems, spb);
     } else

@@ -12,6 +12,8 @@ from pggan_b200 import ops
 pg.set_compute_dtype(torch.bfloat16)
 dev = "cuda"
 SHAPES = [(16, 256, 256, 64, 64), (4, 1024, 1024, 16, 16), (4, 512, 512, 32, 32), (64, 32, 32, 512, 512)]
+if len(sys.argv) > 1 and sys.argv[1] == "c4":       # the mid-width layers of the 128^2 / 256^2 stages (256 x N tiles)
+    SHAPES = [(16, 256, 256, 128, 64), (16, 128, 128, 128, 128), (16, 128, 128, 256, 128)]
 work = []
 for (B, H, W, C, N) in SHAPES:
     x = torch.randn(B, C, H, W, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
