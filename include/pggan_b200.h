@@ -45,6 +45,10 @@ const char* pggan_last_error(void);
 int pggan_set_conv_backend(int backend);
 /* number of tcgen05 / SIMT GEMM-class launches since load (evidence for "which path ran") */
 int pggan_launch_counts(int64_t* tcgen05_launches, int64_t* simt_launches, int64_t* other_launches);
+/* sizeof() of the parameter structs as this library was compiled — a binding checks its own struct layout against
+ * these before the first call (a short struct would make the library read past the caller's buffer). */
+int pggan_sizeof_conv_params(void);
+int pggan_sizeof_wgrad_params(void);
 
 /* ------------------------------------------------------------------------------------------
  * Weight packing.  The tensor-core kernels want K-major operands [n][t][c]; parameters stay in the
@@ -105,6 +109,10 @@ typedef struct {
      * one epilogue thread owns all N channels of a pixel (pggan_conv_pn_fusable(p) != 0); PG_ERR_UNSUPPORTED elsewhere. */
     float* pn_rnorm;
     float pn_eps;
+    /* Operand format of wp when it differs from `dtype` (mixed precision: fp16 activations and weights, bf16 gradient
+     * tensors — a dgrad runs bf16 x fp16): 0 = same as dtype, else PG_BF16+1 / PG_F16+1.  Both are kind::f16 MMAs; the
+     * A and B operand formats are independent fields of the tcgen05 instruction descriptor. */
+    int32_t w_fmt;
 } pg_conv_params;
 int pggan_conv_fprop(const pg_conv_params* p, void* stream);
 /* which kernel pggan_conv_fprop would run this shape on (pointers may be NULL): lets the host decide where fusing a
@@ -132,6 +140,9 @@ typedef struct {
     /* PG_F32 only — 3xTF32 workspaces: ws_g: 3*B*H*W*N floats, ws_x: 3*B*H*W*C floats */
     void* ws_g;
     void* ws_x;
+    /* format of x when it differs from `dtype` (= the format of g): 0 = same, else PG_BF16+1 / PG_F16+1 (mixed precision:
+     * g is a bf16 gradient tensor, x an fp16 activation) */
+    int32_t x_fmt;
 } pg_wgrad_params;
 int pggan_conv_wgrad(const pg_wgrad_params* p, void* stream);
 int pggan_conv_wgrad_slices(const pg_wgrad_params* p); /* how many slices the call above will write (>= 1) */
@@ -139,27 +150,35 @@ int pggan_conv_wgrad_slices(const pg_wgrad_params* p); /* how many slices the ca
 /* ------------------------------------------------------------------------------------------
  * Elementwise / reduction kernels on NHWC feature maps (n = element count, m = pixels).
  */
+/* A coefficient that may depend on the fade-in alpha (Generator.alpha / Discriminator.alpha, pggan/model.py:146-147,
+ * 179-182): value = c0 + c1 * (*alpha), or c0 when alpha == NULL.  `alpha` points to ONE fp32 in device memory that the
+ * kernel reads when it runs, so a captured CUDA graph follows change_alpha() without being captured again. */
+typedef struct {
+    float c0, c1;
+    const float* alpha;
+} pg_coef;
 /* out = g * (y > 0 ? 1 : slope)      — leaky_relu_backward, lib/blocks.py:127,137,185,192 */
 int pggan_lrelu_mask_mul(const void* g, const void* y, void* out, int64_t n, float slope, int dtype, void* stream);
 /* out[b,2h+i,2w+j,c] = scale * x[b,h,w,c]   — upscale2d, lib/utils.py:106-118 (exact) and avg-pool backward */
-int pggan_upsample2x(const void* x, void* out, int B, int H, int W, int C, float scale, int dtype, void* stream);
+int pggan_upsample2x(const void* x, void* out, int B, int H, int W, int C, pg_coef scale, int dtype, void* stream);
 /* the same fused with a LeakyReLU backward: out = up2(scale*x) * (mask_src > 0 ? 1 : slope), mask_src [B,2H,2W,C]
  * — backward of "conv -> LeakyReLU -> AvgPool2d" (lib/blocks.py:192-193) in one pass instead of
  * avg_pool2d_backward + leaky_relu_backward */
-int pggan_upsample2x_mask(const void* x, const void* mask_src, void* out, int B, int H, int W, int C, float scale,
+int pggan_upsample2x_mask(const void* x, const void* mask_src, void* out, int B, int H, int W, int C, pg_coef scale,
                           float slope, int dtype, void* stream);
 /* out[b,h,w,c] = scale * sum_{i,j<2} x[b,2h+i,2w+j,c]; if blend_with != NULL:
  * out = (1-alpha)*blend_with + alpha*that   — nn.AvgPool2d(2) lib/blocks.py:193 (+ fade pggan/nets.py:265) */
-int pggan_pool2x2(const void* x, const void* blend_with, void* out, int B, int H, int W, int C, float scale,
-                  float alpha, int dtype, void* stream);
+int pggan_pool2x2(const void* x, const void* blend_with, void* out, int B, int H, int W, int C, pg_coef scale,
+                  pg_coef alpha, int dtype, void* stream);
 /* out = sa*a + sb*b (b may be NULL)  — fade-in blends pggan/nets.py:156,265 and their backward */
-int pggan_axpby(const void* a, const void* b, void* out, int64_t n, float sa, float sb, int dtype, void* stream);
+int pggan_axpby(const void* a, const void* b, void* out, int64_t n, pg_coef sa, pg_coef sb, int dtype, void* stream);
 /* y = x * rsqrt(mean_c(x^2) + eps), rnorm[m] saved   — PixelwiseVectorNorm, lib/layers.py:13-14 */
 int pggan_pixelnorm_fwd(const void* x, void* y, float* rnorm, int64_t m, int C, float eps, int dtype, void* stream);
 /* gx = rnorm * (gy - y * mean_c(gy*y)); if act_slope != 1 the LeakyReLU mask (sign of y) is applied too;
- * if colsum != NULL also colsum[c] += cs_scale * sum_m gx[m,c] (the bias gradient, same pass) */
+ * if colsum != NULL also colsum[c] += cs_scale * sum_m gx[m,c] (the bias gradient, same pass).
+ * dtype: format of gy / gx; y_dtype: format of the saved activation y (mixed precision: bf16 gradients, fp16 y) */
 int pggan_pixelnorm_bwd(const void* gy, const void* y, const float* rnorm, void* gx, int64_t m, int C,
-                        float act_slope, float* colsum, float cs_scale, int dtype, void* stream);
+                        float act_slope, float* colsum, float cs_scale, int dtype, int y_dtype, void* stream);
 /* fused LeakyReLU backward + bias gradient: out = g * (y > 0 ? 1 : slope) (y NULL: out = g; out NULL: no
  * store) and colsum[c] += scale * sum_m out[m,c] (colsum NULL: none).  C/vec must divide 256. */
 int pggan_mask_colsum(const void* g, const void* y, void* out, float* colsum, int64_t m, int C, float slope,
@@ -187,21 +206,23 @@ int pggan_rgb_wgrad(const void* f, const float* img, float* acc, float* bsum, in
                     int pool, float scale, int dtype, void* stream);
 /* fp32 NCHW image fade.  low == NULL: out = (1-a)*up2(avgpool2(x)) + a*x  (pggan/model.py:217-221)
  *                        low != NULL: out = (1-a)*up2(low) + a*x          (pggan/nets.py:155-156)   */
-int pggan_image_fade(const float* x, const float* low, float* out, int B, int Cimg, int H, int W, float alpha,
+int pggan_image_fade(const float* x, const float* low, float* out, int B, int Cimg, int H, int W, pg_coef alpha,
                      void* stream);
 /* out[b,c,h,w] = scale * sum_{2x2} x   (fp32 NCHW) — backward of the RGB up-sampling */
-int pggan_image_pool_sum(const float* x, float* out, int B, int Cimg, int H, int W, float scale, void* stream);
+int pggan_image_pool_sum(const float* x, float* out, int B, int Cimg, int H, int W, pg_coef scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Minibatch standard deviation (lib/blocks.py:204-233): groups of `group` consecutive samples,
  * unbiased variance, eps inside sqrt, mean over (C,H,W).  x is [B][K] (K = H*W*C, any order).
  */
 int pggan_mbstd_fwd(const void* x, float* stat, int B, int64_t K, int group, int dtype, void* stream);
-/* gx[i,k] = gs[g] * (x-mu)/(K (n-1) sigma) */
-int pggan_mbstd_bwd(const void* x, const float* gs, void* gx, int B, int64_t K, int group, int dtype, void* stream);
+/* gx[i,k] = gs[g] * (x-mu)/(K (n-1) sigma).  dtype: format of x; g_dtype: format of the gradient tensors (gx here;
+ * u and gx2 below) — they differ in the mixed-precision mode */
+int pggan_mbstd_bwd(const void* x, const float* gs, void* gx, int B, int64_t K, int group, int dtype, int g_dtype,
+                    void* stream);
 /* double backward of the above w.r.t. cotangent u (= ggx): ggs[g] and gx2[i,k] */
 int pggan_mbstd_bwd2(const void* x, const void* u, const float* gs, float* ggs, void* gx2, int B, int64_t K,
-                     int group, int dtype, void* stream);
+                     int group, int dtype, int g_dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * WGAN-GP / R1 reductions over fp32 image gradients g [B][n]  (pggan/loss.py:85-87, lib/loss.py:132-134)

@@ -24,6 +24,7 @@ class ConvParams(Structure):
         ("scale", c_float), ("slope", c_float), ("mask_slope", c_float),
         ("ws_x", c_void_p), ("ws_w", c_void_p),
         ("pn_rnorm", c_void_p), ("pn_eps", c_float),
+        ("w_fmt", c_int32),
     ]
 
 
@@ -33,6 +34,7 @@ class WgradParams(Structure):
         ("B", c_int32), ("H", c_int32), ("W", c_int32), ("C", c_int32), ("N", c_int32), ("taps", c_int32),
         ("dtype", c_int32),
         ("ws_g", c_void_p), ("ws_x", c_void_p),
+        ("x_fmt", c_int32),
     ]
 
 
@@ -41,6 +43,11 @@ class PackMap(Structure):
                 ("c_total", c_int32), ("c_valid", c_int32), ("c2", c_int32),
                 ("base", c_int64), ("s_n1", c_int64), ("s_n2", c_int64), ("s_t", c_int64), ("s_c1", c_int64),
                 ("s_c2", c_int64)]
+
+
+class Coef(Structure):
+    """pg_coef: value = c0 + c1 * (*alpha); alpha = device pointer to one fp32 (or NULL -> c0)"""
+    _fields_ = [("c0", c_float), ("c1", c_float), ("alpha", c_void_p)]
 
 
 class AdamEntry(Structure):
@@ -54,6 +61,8 @@ SIGNATURES = {
     "pggan_last_error": (c_char_p, []),
     "pggan_set_conv_backend": (c_int, [c_int]),
     "pggan_launch_counts": (c_int, [POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]),
+    "pggan_sizeof_conv_params": (c_int, []),
+    "pggan_sizeof_wgrad_params": (c_int, []),
     "pggan_pack_weight": (c_int, [c_void_p, c_void_p, c_int, POINTER(PackMap), c_void_p]),
     "pggan_unpack_wgrad": (c_int, [c_void_p, c_void_p, POINTER(PackMap), c_int, c_float, c_int, c_void_p]),
     "pggan_split3": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
@@ -63,15 +72,15 @@ SIGNATURES = {
     "pggan_conv_wgrad": (c_int, [POINTER(WgradParams), c_void_p]),
     "pggan_conv_wgrad_slices": (c_int, [POINTER(WgradParams)]),
     "pggan_lrelu_mask_mul": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_int, c_void_p]),
-    "pggan_upsample2x": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
-    "pggan_upsample2x_mask": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_int,
+    "pggan_upsample2x": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, Coef, c_int, c_void_p]),
+    "pggan_upsample2x_mask": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, Coef, c_float, c_int,
                                       c_void_p]),
-    "pggan_pool2x2": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_int,
+    "pggan_pool2x2": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, Coef, Coef, c_int,
                               c_void_p]),
-    "pggan_axpby": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_int, c_void_p]),
+    "pggan_axpby": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, Coef, Coef, c_int, c_void_p]),
     "pggan_pixelnorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_int, c_void_p]),
     "pggan_pixelnorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p, c_float,
-                                    c_int, c_void_p]),
+                                    c_int, c_int, c_void_p]),
     "pggan_mask_colsum": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_float, c_int,
                                   c_void_p]),
     "pggan_colsum": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_float, c_int, c_void_p]),
@@ -81,11 +90,11 @@ SIGNATURES = {
                                  c_float, c_float, c_int, c_void_p]),
     "pggan_rgb_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                 c_float, c_int, c_void_p]),
-    "pggan_image_fade": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
-    "pggan_image_pool_sum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "pggan_image_fade": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, Coef, c_void_p]),
+    "pggan_image_pool_sum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, Coef, c_void_p]),
     "pggan_mbstd_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p]),
-    "pggan_mbstd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p]),
-    "pggan_mbstd_bwd2": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int,
+    "pggan_mbstd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int, c_void_p]),
+    "pggan_mbstd_bwd2": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int,
                                  c_void_p]),
     "pggan_rows_sumsq": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p]),
     "pggan_rows_scale": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p]),
@@ -118,6 +127,11 @@ def load(path: str | None = None) -> ctypes.CDLL:
         fn = getattr(lib, name)          # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
+    # the parameter structs of this binding must be the ones the library was compiled with
+    for struct, fn in ((ConvParams, lib.pggan_sizeof_conv_params), (WgradParams, lib.pggan_sizeof_wgrad_params)):
+        if ctypes.sizeof(struct) != fn():
+            raise PgganLibraryError(f"{path}: sizeof({struct.__name__}) is {fn()} in the library but "
+                                    f"{ctypes.sizeof(struct)} in this binding - rebuild (python -m pggan_b200.build)")
     _lib = lib
     return lib
 

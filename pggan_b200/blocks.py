@@ -51,7 +51,7 @@ class ProgressiveGeneratorBlock(nn.Module):
     def forward(self, x):
         convs, norm = self._convs_and_norm()
         if not self.is_first:
-            x = upscale2d(ops.feat(x))
+            x = ops.Upsample2x.apply(x, 1.0)                   # upscale2d, lib/utils.py:106-118
         for conv in convs:
             x = _conv_act_norm(conv, x, norm)
         return x
@@ -106,7 +106,7 @@ class ProgressiveDiscriminatorBlock(nn.Module):
         x = self.block[0].fused(x, 0.2, x_act_slope=x_act_slope, defer_mask=fuse2)
         x = self.block[2].fused(x, 0.2, x_act_slope=0.2 if fuse2 else None, defer_mask=True)
         if blend_with is not None:
-            return ops.PoolBlend.apply(x, blend_with, float(alpha), 0.2)
+            return ops.PoolBlend.apply(x, blend_with, alpha if isinstance(alpha, ops.AlphaRef) else float(alpha), 0.2)
         return ops.Pool2x2.apply(x, 0.25, 0.2)
 
 
@@ -118,8 +118,7 @@ def _stddev_channel(x, subgroup_size=4):
         subgroup_size = size[0]
     if subgroup_size > 1:
         stat = ops.MbstdStat.apply(x, int(subgroup_size))                 # [N/G] fp32
-        y = stat.repeat_interleave(subgroup_size).view(size[0], 1, 1, 1)
-        return y.expand(size[0], 1, size[2], size[3]).to(x.dtype)
+        return ops.StatChannel.apply(stat, int(subgroup_size), size[0], size[2], size[3])
     return torch.zeros(size[0], 1, size[2], size[3], device=x.device, dtype=x.dtype)
 
 
@@ -127,7 +126,7 @@ def concatenate_stddev_channel(x, subgroup_size=4):
     """reference lib/blocks.py:204-233: unbiased variance over groups of `subgroup_size` consecutive
     samples, eps 1e-8 inside the sqrt, mean over (C,H,W); one group of N if N % size != 0; zeros if N == 1."""
     x = ops.feat(x)
-    return torch.cat([x, _stddev_channel(x, subgroup_size)], dim=1)
+    return ops.export_act(torch.cat([x, _stddev_channel(x, subgroup_size)], dim=1))
 
 
 class LastProgressiveDiscriminatorBlock(nn.Module):

@@ -31,6 +31,17 @@ void set_error(const char* fmt, ...);
         }                                                                          \
     } while (0)
 #define PG_LAUNCH_CHECK() PG_CUDA(cudaPeekAtLastError())
+// opt a kernel into > 48 KB of dynamic shared memory: the attribute is per (function, DEVICE), so remember it per device
+#define PG_SET_SMEM_ONCE(kern, bytes)                                                                         \
+    do {                                                                                                      \
+        static bool done_[64] = {};                                                                           \
+        int dev_ = 0;                                                                                         \
+        if (cudaGetDevice(&dev_) != cudaSuccess) dev_ = -1;                                                   \
+        if (dev_ < 0 || dev_ >= 64 || !done_[dev_]) {                                                         \
+            PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));   \
+            if (dev_ >= 0 && dev_ < 64) done_[dev_] = true;                                                   \
+        }                                                                                                     \
+    } while (0)
 
 int num_sms();
 
@@ -54,7 +65,11 @@ template <> struct DT<__nv_bfloat16> {
 template <> struct DT<__half> {
     static constexpr int kEnum = PG_F16;
     static __device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
-    static __device__ __forceinline__ __half from_f(float v) { return __float2half_rn(v); }
+    static __device__ __forceinline__ __half from_f(float v) {      // saturating (see pack16)
+        uint16_t h;
+        asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(v));
+        return __ushort_as_half(h);
+    }
 };
 template <> struct DT<float> {
     static constexpr int kEnum = PG_F32;
@@ -67,6 +82,11 @@ template <> struct DT<float> {
 // 16-byte vector of T
 template <typename T> struct Vec16 { static constexpr int kN = 16 / sizeof(T); };
 
+// value of a pg_coef: c0 + c1 * (*alpha) — alpha lives in device memory so a captured graph follows the fade-in
+__device__ __forceinline__ float coef_val(const pg_coef& c) {
+    return c.alpha != nullptr ? fmaf(c.c1, __ldg(c.alpha), c.c0) : c.c0;
+}
+
 __device__ __forceinline__ float lrelu_f(float v, float slope) { return v > 0.f ? v : v * slope; }
 
 // The tensor-core kernels are instantiated once for 16-bit operands (T = __nv_bfloat16) and told at run time whether
@@ -76,17 +96,24 @@ __device__ __forceinline__ float lrelu_f(float v, float slope) { return v > 0.f 
 //   3. the LeakyReLU-mask test "x > 0" on a stored activation: both formats are sign-magnitude, so it is the
 //      signed-integer test on the raw 16 bits                                 -> pos16()
 __host__ __device__ inline uint32_t fmt16(int dt) { return dt == PG_F16 ? 0u : 1u; }
+// fp32 -> IEEE half conversions SATURATE to +-65504 instead of producing inf (one F2FP.SATFINITE instruction): fp16
+// activations of the mixed-precision mode cannot overflow into inf/NaN; bf16 has fp32's exponent range and needs none.
 __device__ __forceinline__ uint32_t pack16(float a, float b, bool f16) {
     if (f16) {
-        __half2 h = __floats2half2_rn(a, b);
-        return *reinterpret_cast<uint32_t*>(&h);
+        uint32_t r;
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+        return r;
     }
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
 }
 __device__ __forceinline__ bool pos16(uint16_t bits) { return static_cast<int16_t>(bits) > 0; }
 __device__ __forceinline__ uint16_t cvt16(float v, bool f16) {
-    if (f16) return __half_as_ushort(__float2half_rn(v));
+    if (f16) {
+        uint16_t h;
+        asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(v));
+        return h;
+    }
     return __bfloat16_as_ushort(__float2bfloat16_rn(v));
 }
 __device__ __forceinline__ float f16bits_to_f(uint16_t bits, bool f16) {
@@ -271,10 +298,16 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
 }
 // Instruction descriptor for kind::f16 / kind::tf32, fp32 accumulate, dense.
 //   a_fmt/b_fmt: 1 = bf16, 2 = tf32; major: 0 = K-major, 1 = MN-major.
-__host__ __device__ constexpr uint32_t make_idesc(int fmt, int a_major, int b_major, int m, int n) {
-    return (1u << 4) | (uint32_t(fmt) << 7) | (uint32_t(fmt) << 10) | (uint32_t(a_major) << 15) |
+//   The A and B formats are independent fields (bits 7-9 / 10-12): kind::f16 multiplies a bf16 operand with an f16 one.
+__host__ __device__ constexpr uint32_t make_idesc2(int a_fmt, int b_fmt, int a_major, int b_major, int m, int n) {
+    return (1u << 4) | (uint32_t(a_fmt) << 7) | (uint32_t(b_fmt) << 10) | (uint32_t(a_major) << 15) |
            (uint32_t(b_major) << 16) | (uint32_t(n >> 3) << 17) | (uint32_t(m >> 4) << 24);
 }
+__host__ __device__ constexpr uint32_t make_idesc(int fmt, int a_major, int b_major, int m, int n) {
+    return make_idesc2(fmt, fmt, a_major, b_major, m, n);
+}
+// format of the second operand of a GEMM-class call: `other_fmt` field (0 = same as dtype, else PG_* + 1)
+__host__ __device__ inline int other_dtype(int dtype, int other_fmt) { return other_fmt == 0 ? dtype : other_fmt - 1; }
 
 // TMEM -> registers: 32 lanes x 32 consecutive fp32 columns (this warp's lane quarter)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {

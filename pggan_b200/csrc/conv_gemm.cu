@@ -8,11 +8,14 @@
 // B tile  = BLOCK_N rows of the K-major packed weights [N][taps*C].
 // Both land in the canonical SWIZZLE_128B K-major layout that tcgen05.mma consumes directly.
 //
-// Warp roles (192 threads, 1 CTA/SM, persistent over tiles):
-//   warp 0 : TMA producer        (one elected lane)
-//   warp 1 : TMEM allocator + MMA issuer (one elected lane)
-//   warps 2-5 : epilogue — tcgen05.ld the accumulator (double-buffered in TMEM so the next tile's
-//               mainloop overlaps), apply  scale*(acc+bias) -> LeakyReLU -> optional mask, store NHWC.
+// Warp roles of the plain kernel (352 threads, 1 CTA/SM, persistent over tiles):
+//   warp 0     : TMA producer        (one elected lane, elect.sync)
+//   warp 1     : TMEM allocator + MMA issuer of M tile 0 (one elected lane)
+//   warps 2-9  : epilogue, two groups of four warps taking alternate tiles — tcgen05.ld the accumulator
+//                (double-buffered in TMEM so the next tile's mainloop overlaps), apply
+//                scale*(acc+bias) -> LeakyReLU -> optional pixel norm / dgrad mask, store NHWC.
+//   warp 10    : MMA issuer of M tile 1 when the CTA tile is 256 x N (MT = 2)
+// The swapped-orientation kernel further down runs 192 threads (TMA warp, MMA warp, four epilogue warps).
 //
 // Replaces cuDNN fprop/dgrad behind EqualizedConv2d/EqualizedLinear (reference lib/layers.py:58-63)
 // with the He scale, bias and LeakyReLU (lib/blocks.py:127,137,185,192) folded into the epilogue.
@@ -60,7 +63,8 @@ struct ConvKArgs {
     int tiles_w, tiles_h, tiles_b, tiles_n;
     int kc_per_tap, taps;
     int out_dtype;
-    int f16;                 // 16-bit operands / outputs are IEEE half (else bf16); see common.cuh fmt16()
+    int f16;                 // 16-bit x / y are IEEE half (else bf16); see common.cuh fmt16()
+    int wf16;                // ... and the packed weights (may differ from f16: mixed precision, pg_conv_params.w_fmt)
     float scale, slope, mask_slope;
     float* pn_rnorm;         // fused pixel norm (plain kernel with tiles_n == 1 only): per-pixel rsqrt factor out
     float pn_eps;
@@ -151,7 +155,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         // -------------------------------------------------------------------- MMA issuer(s): M tile `mi`
         const int mi = warp == 1 ? 0 : 1;
         if (elect_one()) {    // (not lane == 0: ptxas keeps descriptors in uniform registers only under elect.sync)
-            const uint32_t idesc = make_idesc(kTF32 ? 2 : (a.f16 ? 0 : 1), 0, 0, kBlockM, BLOCK_N);
+            const uint32_t idesc = make_idesc2(kTF32 ? 2 : (a.f16 ? 0 : 1), kTF32 ? 2 : (a.wf16 ? 0 : 1), 0, 0, kBlockM, BLOCK_N);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -418,7 +422,7 @@ conv_gemm_swapped_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
         }
     } else if (warp == 1) {
         if (elect_one()) {    // (not lane == 0: ptxas keeps descriptors in uniform registers only under elect.sync)
-            const uint32_t idesc = make_idesc(kTF32 ? 2 : (a.f16 ? 0 : 1), 0, 0, 128, kSwPix);
+            const uint32_t idesc = make_idesc2(kTF32 ? 2 : (a.wf16 ? 0 : 1), kTF32 ? 2 : (a.f16 ? 0 : 1), 0, 0, 128, kSwPix);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -572,7 +576,17 @@ conv_gemm_swapped_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
 template <typename T>
 __global__ void conv_direct_kernel(const T* __restrict__ x, const T* __restrict__ wp, const float* __restrict__ bias,
                                    const T* __restrict__ mask_src, void* __restrict__ y, int B, int H, int W, int C,
-                                   int N, int taps, int out_dtype, float scale, float slope, float mask_slope) {
+                                   int N, int taps, int out_dtype, float scale, float slope, float mask_slope, int xf16,
+                                   int wf16) {
+    // 16-bit instantiation: the element formats (bf16 / IEEE half) of x (= y, mask) and wp are run-time flags
+    auto ldx = [&](const T* p) -> float {
+        if constexpr (sizeof(T) == 2) return f16bits_to_f(*reinterpret_cast<const uint16_t*>(p), xf16 != 0);
+        else return *p;
+    };
+    auto ldw = [&](const T* p) -> float {
+        if constexpr (sizeof(T) == 2) return f16bits_to_f(*reinterpret_cast<const uint16_t*>(p), wf16 != 0);
+        else return *p;
+    };
     const long long total = static_cast<long long>(B) * H * W * N;
     for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -588,14 +602,14 @@ __global__ void conv_direct_kernel(const T* __restrict__ x, const T* __restrict_
             if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
             const T* xp = x + ((static_cast<long long>(b) * H + hh) * W + ww) * C;
             const T* wr = wp + (static_cast<long long>(n) * taps + t) * C;
-            for (int c = 0; c < C; ++c) acc += DT<T>::to_f(xp[c]) * DT<T>::to_f(wr[c]);
+            for (int c = 0; c < C; ++c) acc += ldx(xp + c) * ldw(wr + c);
         }
         if (bias != nullptr) acc += bias[n];
         float v = lrelu_f(acc * scale, slope);
-        if (mask_src != nullptr && !(DT<T>::to_f(mask_src[idx]) > 0.f)) v *= mask_slope;
+        if (mask_src != nullptr && !act_pos(mask_src[idx])) v *= mask_slope;
         if constexpr (sizeof(T) == 2) {
             if (is16(out_dtype)) {
-                reinterpret_cast<T*>(y)[idx] = DT<T>::from_f(v);
+                reinterpret_cast<uint16_t*>(y)[idx] = cvt16(v, xf16 != 0);
                 continue;
             }
         }
@@ -645,6 +659,7 @@ static int launch_tc(const pg_conv_params* p, cudaStream_t stream) {
     a.taps = p->taps;
     a.out_dtype = p->out_dtype;
     a.f16 = p->dtype == PG_F16;
+    a.wf16 = other_dtype(p->dtype, p->w_fmt) == PG_F16;
     a.scale = p->scale; a.slope = p->slope; a.mask_slope = p->mask_slope;
     a.pn_rnorm = p->pn_rnorm; a.pn_eps = p->pn_eps;
     PG_CHECK(p->pn_rnorm == nullptr || a.tiles_n == 1, PG_ERR_UNSUPPORTED, "fused pixel norm needs one N tile (N=%d)", p->N);
@@ -663,15 +678,11 @@ static int launch_tc(const pg_conv_params* p, cudaStream_t stream) {
         uint64_t dims[2] = {K, (uint64_t)p->N};
         uint64_t strides[1] = {K * es};
         uint32_t box[2] = {(uint32_t)BK, (uint32_t)BLOCK_N};
-        int rc = encode_tmap(&tw, p->dtype, 2, p->wp, dims, strides, box, SPAN);
+        int rc = encode_tmap(&tw, other_dtype(p->dtype, p->w_fmt), 2, p->wp, dims, strides, box, SPAN);
         if (rc != PG_OK) return rc;
     }
     auto kern = conv_gemm_kernel<T, BLOCK_N, SPAN, MT>;
-    static bool attr_done = false;   // per template instantiation
-    if (!attr_done) {
-        PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-        attr_done = true;
-    }
+    PG_SET_SMEM_ONCE(kern, Cfg::kSmemBytes);
     const int num_tiles = a.tiles_w * a.tiles_h * a.tiles_b * a.tiles_n;
     int grid = num_tiles < num_sms() ? num_tiles : num_sms();
     kern<<<grid, kConvThreadsPlain, Cfg::kSmemBytes, stream>>>(tx, tw, a);
@@ -699,6 +710,7 @@ static int launch_swapped(const pg_conv_params* p, cudaStream_t stream) {
     a.taps = p->taps;
     a.out_dtype = p->out_dtype;
     a.f16 = p->dtype == PG_F16;
+    a.wf16 = other_dtype(p->dtype, p->w_fmt) == PG_F16;
     a.scale = p->scale; a.slope = p->slope; a.mask_slope = p->mask_slope;
     const uint64_t es = sizeof(T);
     CUtensorMap tx, tw;
@@ -714,15 +726,11 @@ static int launch_swapped(const pg_conv_params* p, cudaStream_t stream) {
         uint64_t dims[2] = {K, (uint64_t)p->N};
         uint64_t strides[1] = {K * es};
         uint32_t box[2] = {(uint32_t)BK, 128u};
-        int rc = encode_tmap(&tw, p->dtype, 2, p->wp, dims, strides, box, 128);
+        int rc = encode_tmap(&tw, other_dtype(p->dtype, p->w_fmt), 2, p->wp, dims, strides, box, 128);
         if (rc != PG_OK) return rc;
     }
     auto kern = conv_gemm_swapped_kernel<T>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSwSmemBytes));
-        attr_done = true;
-    }
+    PG_SET_SMEM_ONCE(kern, kSwSmemBytes);
     const int num_tiles = a.tiles_w * a.tiles_h * a.tiles_b * a.tiles_n;
     const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
     kern<<<grid, kConvThreads, kSwSmemBytes, stream>>>(tx, tw, a);
@@ -845,16 +853,10 @@ static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream, int* k
     if (total == 0) return PG_OK;
     long long blocks = (total + 255) / 256;
     if (blocks > 148LL * 32) blocks = 148LL * 32;
-    if (p->dtype == PG_F16)        // the SIMT kernel does arithmetic on the values: it needs the real element type
-        conv_direct_kernel<__half><<<(int)blocks, 256, 0, stream>>>(
-            reinterpret_cast<const __half*>(p->x), reinterpret_cast<const __half*>(p->wp), p->bias,
-            reinterpret_cast<const __half*>(p->mask_src), p->y, p->B, p->H, p->W, p->C, p->N, p->taps, p->out_dtype,
-            p->scale, p->slope, p->mask_slope);
-    else
-        conv_direct_kernel<T><<<(int)blocks, 256, 0, stream>>>(
-            reinterpret_cast<const T*>(p->x), reinterpret_cast<const T*>(p->wp), p->bias,
-            reinterpret_cast<const T*>(p->mask_src), p->y, p->B, p->H, p->W, p->C, p->N, p->taps, p->out_dtype, p->scale,
-            p->slope, p->mask_slope);
+    conv_direct_kernel<T><<<(int)blocks, 256, 0, stream>>>(
+        reinterpret_cast<const T*>(p->x), reinterpret_cast<const T*>(p->wp), p->bias,
+        reinterpret_cast<const T*>(p->mask_src), p->y, p->B, p->H, p->W, p->C, p->N, p->taps, p->out_dtype, p->scale,
+        p->slope, p->mask_slope, p->dtype == PG_F16, other_dtype(p->dtype, p->w_fmt) == PG_F16);
     PG_LAUNCH_CHECK();
     g_simt_launches++;
     return PG_OK;
@@ -893,6 +895,9 @@ extern "C" int pggan_conv_pn_fusable(const pg_conv_params* p) {
     return 0;
 }
 
+extern "C" int pggan_sizeof_conv_params(void) { return (int)sizeof(pg_conv_params); }
+extern "C" int pggan_sizeof_wgrad_params(void) { return (int)sizeof(pg_wgrad_params); }
+
 extern "C" int pggan_conv_fprop(const pg_conv_params* p, void* stream) {
     using namespace pg;
     PG_CHECK(p != nullptr, PG_ERR_ARG, "pggan_conv_fprop: null params");
@@ -903,6 +908,8 @@ extern "C" int pggan_conv_fprop(const pg_conv_params* p, void* stream) {
     PG_CHECK(p->dtype == PG_BF16 || p->dtype == PG_F16 || p->dtype == PG_F32, PG_ERR_ARG, "pggan_conv_fprop: bad dtype %d", p->dtype);
     PG_CHECK(p->out_dtype == p->dtype || p->out_dtype == PG_F32 || p->out_dtype == PG_F32_RAW, PG_ERR_ARG,
              "pggan_conv_fprop: bad out_dtype %d", p->out_dtype);
+    PG_CHECK(p->w_fmt == 0 || (is16(p->dtype) && (p->w_fmt == PG_BF16 + 1 || p->w_fmt == PG_F16 + 1)), PG_ERR_ARG,
+             "pggan_conv_fprop: bad w_fmt %d (mixed operand formats exist for the 16-bit types only)", p->w_fmt);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (is16(p->dtype)) return conv_dispatch<__nv_bfloat16>(p, s);      // bf16 and f16 share the 16-bit instantiation
     return conv_dispatch<float>(p, s);

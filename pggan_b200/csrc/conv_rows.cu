@@ -49,7 +49,8 @@ struct RowsKArgs {
     long long total;         // B * nseg * H row segments
     long long per_cta;
     int out_dtype;
-    int f16;                 // 16-bit operands / outputs are IEEE half (else bf16)
+    int f16;                 // 16-bit x / y are IEEE half (else bf16)
+    int wf16;                // ... and the packed weights (mixed precision: may differ)
     float scale, slope, mask_slope;
     float* pn_rnorm;         // fused pixel norm: per-pixel rsqrt factor out (NULL: none)
     float pn_eps;
@@ -178,7 +179,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     } else if (warp == 1) {
         // -------------------------------------------------------------------- MMA issuer
         if (u_begin < u_end && elect_one()) {
-            const uint32_t idesc = make_idesc(a.f16 ? 0 : 1, 0, 0, kRowPix, BLOCK_N);
+            const uint32_t idesc = make_idesc2(a.f16 ? 0 : 1, a.wf16 ? 0 : 1, 0, 0, kRowPix, BLOCK_N);
             if constexpr (J == 1) {
                 mbar_wait(w_bar, 0);
                 tc_fence_after();
@@ -419,6 +420,7 @@ static int launch_rows(const pg_conv_params* p_in, cudaStream_t stream) {
     a.total = static_cast<long long>(p->B) * a.nseg * p->H;
     a.out_dtype = p->out_dtype;
     a.f16 = p->dtype == PG_F16;
+    a.wf16 = other_dtype(p->dtype, p->w_fmt) == PG_F16;
     a.scale = p->scale; a.slope = p->slope; a.mask_slope = p->mask_slope;
     a.pn_rnorm = p->pn_rnorm; a.pn_eps = p->pn_eps;
     const int sms = num_sms();
@@ -439,17 +441,13 @@ static int launch_rows(const pg_conv_params* p_in, cudaStream_t stream) {
         uint64_t dims[2] = {K, (uint64_t)p->N};
         uint64_t strides[1] = {K * 2};
         uint32_t box[2] = {(uint32_t)p->C, (uint32_t)BLOCK_N};
-        int rc = encode_tmap(&tw, p->dtype, 2, p->wp, dims, strides, box, SPAN);
+        int rc = encode_tmap(&tw, other_dtype(p->dtype, p->w_fmt), 2, p->wp, dims, strides, box, SPAN);
         if (rc != PG_OK) return rc;
     } else {
         tw = tx;                      // unused by the grouped variant (it builds its weight tiles itself)
     }
     auto kern = conv_rows_kernel<SPAN, BLOCK_N, J>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-        attr_done = true;
-    }
+    PG_SET_SMEM_ONCE(kern, Cfg::kSmemBytes);
     kern<<<(int)grid, kRowsThreads, Cfg::kSmemBytes, stream>>>(tx, tw, a);
     PG_LAUNCH_CHECK();
     g_tc_launches++;

@@ -22,6 +22,9 @@ template <typename T> struct V16 {
     uint4 raw;
     __device__ __forceinline__ float get(int i) const { return DT<T>::to_f(reinterpret_cast<const T*>(&raw)[i]); }
     __device__ __forceinline__ void set(int i, float v) { reinterpret_cast<T*>(&raw)[i] = DT<T>::from_f(v); }
+    // "stored activation > 0" (LeakyReLU mask): the sign-magnitude test on the raw bits for the 16-bit types, so a mask
+    // source may be bf16 or IEEE half whatever T is (mixed precision)
+    __device__ __forceinline__ bool pos(int i) const { return act_pos(reinterpret_cast<const T*>(&raw)[i]); }
 };
 template <typename T> __device__ __forceinline__ V16<T> ld16(const T* p) {
     V16<T> v;
@@ -31,6 +34,7 @@ template <typename T> __device__ __forceinline__ V16<T> ld16(const T* p) {
 template <typename T> __device__ __forceinline__ void st16(T* p, const V16<T>& v) {
     *reinterpret_cast<uint4*>(p) = v.raw;
 }
+
 
 #define GRID_STRIDE(i, n)                                                                      \
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < (n); \
@@ -44,7 +48,7 @@ __global__ void lrelu_mask_mul_kernel(const T* __restrict__ g, const T* __restri
     GRID_STRIDE(i, nvec) {
         V16<T> gv = ld16(g + i * VN), yv = ld16(y + i * VN), o;
 #pragma unroll
-        for (int e = 0; e < VN; ++e) o.set(e, yv.get(e) > 0.f ? gv.get(e) : gv.get(e) * slope);
+        for (int e = 0; e < VN; ++e) o.set(e, yv.pos(e) ? gv.get(e) : gv.get(e) * slope);
         st16(out + i * VN, o);
     }
     // scalar tail
@@ -52,15 +56,16 @@ __global__ void lrelu_mask_mul_kernel(const T* __restrict__ g, const T* __restri
     GRID_STRIDE(i, n - tail0) {
         const long long k = tail0 + i;
         const float gv = DT<T>::to_f(g[k]);
-        out[k] = DT<T>::from_f(DT<T>::to_f(y[k]) > 0.f ? gv : gv * slope);
+        out[k] = DT<T>::from_f(act_pos(y[k]) ? gv : gv * slope);
     }
 }
 
 // --------------------------------------------------------------------------------- axpby
 template <typename T>
 __global__ void axpby_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, long long nvec,
-                             long long n, float sa, float sb) {
+                             long long n, pg_coef ca, pg_coef cb) {
     constexpr int VN = V16<T>::N;
+    const float sa = coef_val(ca), sb = coef_val(cb);
     GRID_STRIDE(i, nvec) {
         V16<T> av = ld16(a + i * VN), o;
         if (b != nullptr) {
@@ -107,8 +112,9 @@ __device__ __forceinline__ void idx_decomp(long long i, int CV, int W, int H, in
 // one thread per (input pixel, 16-byte channel vector): read once, write the 2x2 block
 template <typename T>
 __global__ void upsample2x_kernel(const T* __restrict__ x, const T* __restrict__ mask_src, T* __restrict__ out, int B,
-                                  int H, int W, int CV, float scale, float slope) {
+                                  int H, int W, int CV, pg_coef cscale, float slope) {
     constexpr int VN = V16<T>::N;
+    const float scale = coef_val(cscale);
     const long long total = static_cast<long long>(B) * H * W * CV;
     const long long C = static_cast<long long>(CV) * VN;
     GRID_STRIDE(i, total) {
@@ -136,7 +142,7 @@ __global__ void upsample2x_kernel(const T* __restrict__ x, const T* __restrict__
                 const V16<T> mv = ld16(mask_src + ooff + offs[k]);
                 V16<T> r;
 #pragma unroll
-                for (int e = 0; e < VN; ++e) r.set(e, mv.get(e) > 0.f ? v.get(e) : v.get(e) * slope);
+                for (int e = 0; e < VN; ++e) r.set(e, mv.pos(e) ? v.get(e) : v.get(e) * slope);
                 st16(o + offs[k], r);
             }
         }
@@ -146,8 +152,9 @@ __global__ void upsample2x_kernel(const T* __restrict__ x, const T* __restrict__
 // one thread per (output pixel, channel vector); x is [B,H,W,C], out [B,H/2,W/2,C]
 template <typename T>
 __global__ void pool2x2_kernel(const T* __restrict__ x, const T* __restrict__ blend, T* __restrict__ out, int B, int H,
-                               int W, int CV, float scale, float alpha) {
+                               int W, int CV, pg_coef cscale, pg_coef calpha) {
     constexpr int VN = V16<T>::N;
+    const float alpha = coef_val(calpha), scale = coef_val(cscale);
     const int Ho = H / 2, Wo = W / 2;
     const long long total = static_cast<long long>(B) * Ho * Wo * CV;
     const long long C = static_cast<long long>(CV) * VN;
@@ -214,9 +221,10 @@ __global__ void pixelnorm_fwd_kernel(const T* __restrict__ x, T* __restrict__ y,
 
 // gx = r * (gy - y * mean_c(gy*y)), then optional LeakyReLU mask by the sign of y; optionally the
 // bias gradient colsum[c] += cs_scale * sum_m gx[m,c] in the same pass (lanes own fixed channel vectors)
-template <typename T, int MAXV>
+// TY: element type of the saved activation y when it differs from the gradient type T (mixed precision: fp16 / bf16)
+template <typename T, int MAXV, typename TY = T>
 __global__ void __launch_bounds__(256)
-pixelnorm_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ y, const float* __restrict__ rnorm,
+pixelnorm_bwd_kernel(const T* __restrict__ gy, const TY* __restrict__ y, const float* __restrict__ rnorm,
                      T* __restrict__ gx, long long M, int C, float act_slope, float* __restrict__ colsum,
                      float cs_scale) {
     constexpr int VN = V16<T>::N;
@@ -231,7 +239,8 @@ pixelnorm_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ y, const fl
 #pragma unroll
         for (int e = 0; e < VN; ++e) cs[k][e] = 0.f;
     for (long long m = warp0; m < M; m += nwarps) {
-        V16<T> g[MAXV], yv[MAXV];
+        V16<T> g[MAXV];
+        V16<TY> yv[MAXV];
         float dot = 0.f;
 #pragma unroll
         for (int k = 0; k < MAXV; ++k) {
@@ -316,7 +325,7 @@ mask_colsum_kernel(const T* __restrict__ g, const T* __restrict__ y, T* __restri
 #pragma unroll
                 for (int e = 0; e < VN; ++e) {
                     float t = gv[u].get(e);
-                    if (y != nullptr && !(yv[u].get(e) > 0.f)) t *= slope;
+                    if (y != nullptr && !yv[u].pos(e)) t *= slope;
                     o.set(e, t);
                     acc[e] += o.get(e);
                 }
@@ -611,9 +620,9 @@ pixelnorm_fwd_small_kernel(const T* __restrict__ x, T* __restrict__ y, float* __
     }
 }
 
-template <typename T>
+template <typename T, typename TY = T>
 __global__ void __launch_bounds__(256)
-pixelnorm_bwd_small_kernel(const T* __restrict__ gy, const T* __restrict__ y, const float* __restrict__ rnorm,
+pixelnorm_bwd_small_kernel(const T* __restrict__ gy, const TY* __restrict__ y, const float* __restrict__ rnorm,
                            T* __restrict__ gx, long long M, int C, float act_slope, float* __restrict__ colsum,
                            float cs_scale, int LP) {
     constexpr int VN = V16<T>::N;
@@ -626,7 +635,8 @@ pixelnorm_bwd_small_kernel(const T* __restrict__ gy, const T* __restrict__ y, co
     // the grid stride is a multiple of 32 and of LP, so a lane always owns the same channel vector (lane % LP)
     GRID_STRIDE(i, (nvec_total + 31) / 32 * 32) {
         const bool live = i < nvec_total;
-        V16<T> g, yv;
+        V16<T> g;
+        V16<TY> yv;
         float dot = 0.f;
         if (live) {
             g = ld16(gy + i * VN);
@@ -706,7 +716,7 @@ extern "C" int pggan_lrelu_mask_mul(const void* g, const void* y, void* out, int
     return PG_OK;
 }
 
-extern "C" int pggan_axpby(const void* a, const void* b, void* out, int64_t n, float sa, float sb, int dtype,
+extern "C" int pggan_axpby(const void* a, const void* b, void* out, int64_t n, pg_coef sa, pg_coef sb, int dtype,
                            void* stream) {
     PG_CHECK(a && out && n >= 0, PG_ERR_ARG, "pggan_axpby: bad args");
     PG_CHECK(al16(a) && al16(out) && (b == nullptr || al16(b)), PG_ERR_ARG, "pggan_axpby: pointers must be 16-byte aligned");
@@ -721,7 +731,7 @@ extern "C" int pggan_axpby(const void* a, const void* b, void* out, int64_t n, f
     return PG_OK;
 }
 
-static int upsample2x_impl(const void* x, const void* mask_src, void* out, int B, int H, int W, int C, float scale,
+static int upsample2x_impl(const void* x, const void* mask_src, void* out, int B, int H, int W, int C, pg_coef scale,
                            float slope, int dtype, void* stream, const char* who) {
     PG_CHECK(x && out && B > 0 && H > 0 && W > 0 && C > 0, PG_ERR_ARG, "%s: bad args", who);
     PG_CHECK(al16(x) && al16(out) && (!mask_src || al16(mask_src)), PG_ERR_ARG, "%s: pointers must be 16-byte aligned", who);
@@ -737,19 +747,19 @@ static int upsample2x_impl(const void* x, const void* mask_src, void* out, int B
     return PG_OK;
 }
 
-extern "C" int pggan_upsample2x(const void* x, void* out, int B, int H, int W, int C, float scale, int dtype,
+extern "C" int pggan_upsample2x(const void* x, void* out, int B, int H, int W, int C, pg_coef scale, int dtype,
                                 void* stream) {
     return upsample2x_impl(x, nullptr, out, B, H, W, C, scale, 1.f, dtype, stream, "pggan_upsample2x");
 }
 
 extern "C" int pggan_upsample2x_mask(const void* x, const void* mask_src, void* out, int B, int H, int W, int C,
-                                     float scale, float slope, int dtype, void* stream) {
+                                     pg_coef scale, float slope, int dtype, void* stream) {
     PG_CHECK(mask_src != nullptr, PG_ERR_ARG, "pggan_upsample2x_mask: null mask_src");
     return upsample2x_impl(x, mask_src, out, B, H, W, C, scale, slope, dtype, stream, "pggan_upsample2x_mask");
 }
 
-extern "C" int pggan_pool2x2(const void* x, const void* blend_with, void* out, int B, int H, int W, int C, float scale,
-                             float alpha, int dtype, void* stream) {
+extern "C" int pggan_pool2x2(const void* x, const void* blend_with, void* out, int B, int H, int W, int C, pg_coef scale,
+                             pg_coef alpha, int dtype, void* stream) {
     PG_CHECK(x && out && B > 0 && H > 1 && W > 1 && C > 0, PG_ERR_ARG, "pggan_pool2x2: bad args");
     PG_CHECK(H % 2 == 0 && W % 2 == 0, PG_ERR_ARG, "pggan_pool2x2: H=%d W=%d must be even", H, W);
     PG_CHECK(al16(x) && al16(out) && (blend_with == nullptr || al16(blend_with)), PG_ERR_ARG,
@@ -796,34 +806,44 @@ extern "C" int pggan_pixelnorm_fwd(const void* x, void* y, float* rnorm, int64_t
     return PG_OK;
 }
 
+template <typename T, typename TY>
+static int pixelnorm_bwd_launch(const void* gy, const void* y, const float* rnorm, void* gx, int64_t m, int C,
+                                float act_slope, float* colsum, float cs_scale, cudaStream_t s) {
+    constexpr int VN = V16<T>::N;
+    PG_CHECK(C % VN == 0 && C <= 32 * VN * 4, PG_ERR_UNSUPPORTED,
+             "pggan_pixelnorm_bwd: C=%d must be a multiple of %d and <= %d", C, VN, 32 * VN * 4);
+    const int lp = C / VN;
+    if (lp <= 16 && (lp & (lp - 1)) == 0) {
+        pixelnorm_bwd_small_kernel<T, TY><<<ew_grid(m * lp / 4 + 1, 256), 256, 0, s>>>(
+            (const T*)gy, (const TY*)y, rnorm, (T*)gx, m, C, act_slope, colsum, cs_scale, lp);
+    } else {
+        const int grid = ew_grid(m * 32 / 4 + 1, 256);      // ~4 rows per warp
+        if (C <= 32 * VN)
+            pixelnorm_bwd_kernel<T, 1, TY><<<grid, 256, 0, s>>>((const T*)gy, (const TY*)y, rnorm, (T*)gx, m, C, act_slope, colsum, cs_scale);
+        else if (C <= 64 * VN)
+            pixelnorm_bwd_kernel<T, 2, TY><<<grid, 256, 0, s>>>((const T*)gy, (const TY*)y, rnorm, (T*)gx, m, C, act_slope, colsum, cs_scale);
+        else
+            pixelnorm_bwd_kernel<T, 4, TY><<<grid, 256, 0, s>>>((const T*)gy, (const TY*)y, rnorm, (T*)gx, m, C, act_slope, colsum, cs_scale);
+    }
+    PG_LAUNCH_CHECK();
+    g_other_launches++;
+    return PG_OK;
+}
+
 extern "C" int pggan_pixelnorm_bwd(const void* gy, const void* y, const float* rnorm, void* gx, int64_t m, int C,
-                                   float act_slope, float* colsum, float cs_scale, int dtype, void* stream) {
+                                   float act_slope, float* colsum, float cs_scale, int dtype, int y_dtype, void* stream) {
     PG_CHECK(gy && y && rnorm && gx && m >= 0 && C > 0, PG_ERR_ARG, "pggan_pixelnorm_bwd: bad args");
     PG_CHECK(al16(gy) && al16(y) && al16(gx), PG_ERR_ARG, "pggan_pixelnorm_bwd: pointers must be 16-byte aligned");
     if (m == 0) return PG_OK;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    DISPATCH_T(dtype, {
-        constexpr int VN = V16<T>::N;
-        PG_CHECK(C % VN == 0 && C <= 32 * VN * 4, PG_ERR_UNSUPPORTED,
-                 "pggan_pixelnorm_bwd: C=%d must be a multiple of %d and <= %d", C, VN, 32 * VN * 4);
-        const int lp = C / VN;
-        if (lp <= 16 && (lp & (lp - 1)) == 0) {
-            pixelnorm_bwd_small_kernel<T><<<ew_grid(m * lp / 4 + 1, 256), 256, 0, s>>>(
-                (const T*)gy, (const T*)y, rnorm, (T*)gx, m, C, act_slope, colsum, cs_scale, lp);
-            PG_LAUNCH_CHECK();
-            g_other_launches++;
-            return PG_OK;
-        }
-        const int grid = ew_grid(m * 32 / 4 + 1, 256);      // ~4 rows per warp
-        if (C <= 32 * VN)
-            pixelnorm_bwd_kernel<T, 1><<<grid, 256, 0, s>>>((const T*)gy, (const T*)y, rnorm, (T*)gx, m, C, act_slope, colsum, cs_scale);
-        else if (C <= 64 * VN)
-            pixelnorm_bwd_kernel<T, 2><<<grid, 256, 0, s>>>((const T*)gy, (const T*)y, rnorm, (T*)gx, m, C, act_slope, colsum, cs_scale);
-        else
-            pixelnorm_bwd_kernel<T, 4><<<grid, 256, 0, s>>>((const T*)gy, (const T*)y, rnorm, (T*)gx, m, C, act_slope, colsum, cs_scale);
-    });
-    PG_LAUNCH_CHECK();
-    g_other_launches++;
+    if (y_dtype != dtype) {
+        // mixed precision: bf16 gradients, fp16 saved activation (or the reverse)
+        PG_CHECK(is16(dtype) && is16(y_dtype), PG_ERR_ARG, "pggan_pixelnorm_bwd: dtype %d / y_dtype %d cannot be mixed", dtype, y_dtype);
+        if (dtype == PG_BF16)
+            return pixelnorm_bwd_launch<__nv_bfloat16, __half>(gy, y, rnorm, gx, m, C, act_slope, colsum, cs_scale, s);
+        return pixelnorm_bwd_launch<__half, __nv_bfloat16>(gy, y, rnorm, gx, m, C, act_slope, colsum, cs_scale, s);
+    }
+    DISPATCH_T(dtype, { return pixelnorm_bwd_launch<T, T>(gy, y, rnorm, gx, m, C, act_slope, colsum, cs_scale, s); });
     return PG_OK;
 }
 

@@ -73,13 +73,14 @@ __global__ void mbstd_fwd_kernel(const T* __restrict__ x, float* __restrict__ st
     if (threadIdx.x == 0) atomicAdd(stat + grp, tot / static_cast<float>(K));
 }
 
-template <typename T>
-__global__ void mbstd_bwd_kernel(const T* __restrict__ x, const float* __restrict__ gs, T* __restrict__ gx, long long K,
+// TG: element type of the gradient tensors when it differs from the activation type T (mixed precision)
+template <typename T, typename TG = T>
+__global__ void mbstd_bwd_kernel(const T* __restrict__ x, const float* __restrict__ gs, TG* __restrict__ gx, long long K,
                                  int n) {
     constexpr int VN = MV<T>::N;
     const int grp = blockIdx.y;
     const T* xg = x + static_cast<long long>(grp) * n * K;
-    T* gg = gx + static_cast<long long>(grp) * n * K;
+    TG* gg = gx + static_cast<long long>(grp) * n * K;
     const long long KV = K / VN;
     const float coef = gs[grp] / (static_cast<float>(K) * (n - 1));
     for (long long kv = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; kv < KV;
@@ -87,7 +88,8 @@ __global__ void mbstd_bwd_kernel(const T* __restrict__ x, const float* __restric
         float mu[VN], sg[VN];
         group_moments<T>(xg, K, n, kv * VN, mu, sg);
         for (int i = 0; i < n; ++i) {
-            MV<T> v = mld(xg + i * K + kv * VN), o;
+            MV<T> v = mld(xg + i * K + kv * VN);
+            MV<TG> o;
 #pragma unroll
             for (int e = 0; e < VN; ++e) o.set(e, coef * (v.get(e) - mu[e]) / sg[e]);
             *reinterpret_cast<uint4*>(gg + i * K + kv * VN) = o.raw;
@@ -97,16 +99,16 @@ __global__ void mbstd_bwd_kernel(const T* __restrict__ x, const float* __restric
 
 // u is the cotangent of gx.  ggs[grp] += sum_k S_k/(K(n-1)sigma_k),  S_k = sum_i u_ik d_ik
 // gx2_jk = gs/(K(n-1)) * [ (u_jk - ubar_k)/sigma_k - d_jk S_k / ((n-1) sigma_k^3) ]
-template <typename T>
-__global__ void mbstd_bwd2_kernel(const T* __restrict__ x, const T* __restrict__ u, const float* __restrict__ gs,
-                                  float* __restrict__ ggs, T* __restrict__ gx2, long long K, int n) {
+template <typename T, typename TG = T>
+__global__ void mbstd_bwd2_kernel(const T* __restrict__ x, const TG* __restrict__ u, const float* __restrict__ gs,
+                                  float* __restrict__ ggs, TG* __restrict__ gx2, long long K, int n) {
     constexpr int VN = MV<T>::N;
     __shared__ float red[32];
     const int grp = blockIdx.y;
     const long long goff = static_cast<long long>(grp) * n * K;
     const T* xg = x + goff;
-    const T* ug = u + goff;
-    T* og = gx2 + goff;
+    const TG* ug = u + goff;
+    TG* og = gx2 + goff;
     const long long KV = K / VN;
     const float inv = 1.f / (static_cast<float>(K) * (n - 1));
     const float coef = gs[grp] * inv;
@@ -118,7 +120,8 @@ __global__ void mbstd_bwd2_kernel(const T* __restrict__ x, const T* __restrict__
 #pragma unroll
         for (int e = 0; e < VN; ++e) ub[e] = S[e] = 0.f;
         for (int i = 0; i < n; ++i) {
-            MV<T> xv = mld(xg + i * K + kv * VN), uv = mld(ug + i * K + kv * VN);
+            MV<T> xv = mld(xg + i * K + kv * VN);
+            MV<TG> uv = mld(ug + i * K + kv * VN);
 #pragma unroll
             for (int e = 0; e < VN; ++e) {
                 ub[e] += uv.get(e);
@@ -131,7 +134,8 @@ __global__ void mbstd_bwd2_kernel(const T* __restrict__ x, const T* __restrict__
             local += S[e] / sg[e];
         }
         for (int i = 0; i < n; ++i) {
-            MV<T> xv = mld(xg + i * K + kv * VN), uv = mld(ug + i * K + kv * VN), o;
+            MV<T> xv = mld(xg + i * K + kv * VN);
+            MV<TG> uv = mld(ug + i * K + kv * VN), o;
 #pragma unroll
             for (int e = 0; e < VN; ++e) {
                 const float d = xv.get(e) - mu[e];
@@ -181,39 +185,50 @@ extern "C" int pggan_mbstd_fwd(const void* x, float* stat, int B, int64_t K, int
 }
 
 extern "C" int pggan_mbstd_bwd(const void* x, const float* gs, void* gx, int B, int64_t K, int group, int dtype,
-                               void* stream) {
+                               int g_dtype, void* stream) {
     PG_CHECK(x && gs && gx, PG_ERR_ARG, "pggan_mbstd_bwd: null pointer");
     int rc = mb_check("pggan_mbstd_bwd", B, K, group, dtype);
     if (rc != PG_OK) return rc;
+    PG_CHECK(g_dtype == dtype || (is16(dtype) && is16(g_dtype)), PG_ERR_ARG, "pggan_mbstd_bwd: dtype %d / g_dtype %d cannot be mixed", dtype, g_dtype);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    if (dtype == PG_BF16)
-        mbstd_bwd_kernel<__nv_bfloat16><<<mb_grid(K, 8, B / group), 256, 0, s>>>((const __nv_bfloat16*)x, gs,
-                                                                              (__nv_bfloat16*)gx, K, group);
+    const dim3 grid = mb_grid(K, is16(dtype) ? 8 : 4, B / group);
+    if (dtype == PG_BF16 && g_dtype == PG_BF16)
+        mbstd_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, gs, (__nv_bfloat16*)gx, K, group);
+    else if (dtype == PG_F16 && g_dtype == PG_F16)
+        mbstd_bwd_kernel<__half><<<grid, 256, 0, s>>>((const __half*)x, gs, (__half*)gx, K, group);
     else if (dtype == PG_F16)
-        mbstd_bwd_kernel<__half><<<mb_grid(K, 8, B / group), 256, 0, s>>>((const __half*)x, gs, (__half*)gx, K, group);
+        mbstd_bwd_kernel<__half, __nv_bfloat16><<<grid, 256, 0, s>>>((const __half*)x, gs, (__nv_bfloat16*)gx, K, group);
+    else if (dtype == PG_BF16)
+        mbstd_bwd_kernel<__nv_bfloat16, __half><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, gs, (__half*)gx, K, group);
     else
-        mbstd_bwd_kernel<float><<<mb_grid(K, 4, B / group), 256, 0, s>>>((const float*)x, gs, (float*)gx, K, group);
+        mbstd_bwd_kernel<float><<<grid, 256, 0, s>>>((const float*)x, gs, (float*)gx, K, group);
     PG_LAUNCH_CHECK();
     g_other_launches++;
     return PG_OK;
 }
 
 extern "C" int pggan_mbstd_bwd2(const void* x, const void* u, const float* gs, float* ggs, void* gx2, int B, int64_t K,
-                                int group, int dtype, void* stream) {
+                                int group, int dtype, int g_dtype, void* stream) {
     PG_CHECK(x && u && gs && ggs && gx2, PG_ERR_ARG, "pggan_mbstd_bwd2: null pointer");
     int rc = mb_check("pggan_mbstd_bwd2", B, K, group, dtype);
     if (rc != PG_OK) return rc;
+    PG_CHECK(g_dtype == dtype || (is16(dtype) && is16(g_dtype)), PG_ERR_ARG, "pggan_mbstd_bwd2: dtype %d / g_dtype %d cannot be mixed", dtype, g_dtype);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     PG_CUDA(cudaMemsetAsync(ggs, 0, sizeof(float) * (B / group), s));
-    if (dtype == PG_BF16)
-        mbstd_bwd2_kernel<__nv_bfloat16><<<mb_grid(K, 8, B / group), 256, 0, s>>>(
-            (const __nv_bfloat16*)x, (const __nv_bfloat16*)u, gs, ggs, (__nv_bfloat16*)gx2, K, group);
+    const dim3 grid = mb_grid(K, is16(dtype) ? 8 : 4, B / group);
+    if (dtype == PG_BF16 && g_dtype == PG_BF16)
+        mbstd_bwd2_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)u, gs, ggs,
+                                                             (__nv_bfloat16*)gx2, K, group);
+    else if (dtype == PG_F16 && g_dtype == PG_F16)
+        mbstd_bwd2_kernel<__half><<<grid, 256, 0, s>>>((const __half*)x, (const __half*)u, gs, ggs, (__half*)gx2, K, group);
     else if (dtype == PG_F16)
-        mbstd_bwd2_kernel<__half><<<mb_grid(K, 8, B / group), 256, 0, s>>>((const __half*)x, (const __half*)u, gs, ggs,
-                                                                         (__half*)gx2, K, group);
+        mbstd_bwd2_kernel<__half, __nv_bfloat16><<<grid, 256, 0, s>>>((const __half*)x, (const __nv_bfloat16*)u, gs, ggs,
+                                                                     (__nv_bfloat16*)gx2, K, group);
+    else if (dtype == PG_BF16)
+        mbstd_bwd2_kernel<__nv_bfloat16, __half><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, (const __half*)u, gs, ggs,
+                                                                     (__half*)gx2, K, group);
     else
-        mbstd_bwd2_kernel<float><<<mb_grid(K, 4, B / group), 256, 0, s>>>((const float*)x, (const float*)u, gs, ggs,
-                                                                        (float*)gx2, K, group);
+        mbstd_bwd2_kernel<float><<<grid, 256, 0, s>>>((const float*)x, (const float*)u, gs, ggs, (float*)gx2, K, group);
     PG_LAUNCH_CHECK();
     g_other_launches++;
     return PG_OK;

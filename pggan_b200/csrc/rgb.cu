@@ -378,9 +378,11 @@ rgb_wgrad_pixel_kernel(const T* __restrict__ f, const float* __restrict__ img, f
 }
 
 // ------------------------------------------------------------------------------ fp32 image kernels
+
 __global__ void image_fade_kernel(const float* __restrict__ x, const float* __restrict__ low, float* __restrict__ out,
-                                  long long planes, int H, int W, float alpha) {
+                                  long long planes, int H, int W, pg_coef calpha) {
     // one thread per 2x2 output block
+    const float alpha = coef_val(calpha);
     const int Hh = H / 2, Wh = W / 2;
     const long long total = planes * Hh * Wh;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -404,7 +406,8 @@ __global__ void image_fade_kernel(const float* __restrict__ x, const float* __re
 }
 
 __global__ void image_pool_sum_kernel(const float* __restrict__ x, float* __restrict__ out, long long planes, int H,
-                                      int W, float scale) {
+                                      int W, pg_coef cscale) {
+    const float scale = coef_val(cscale);
     const int Hh = H / 2, Wh = W / 2;
     const long long total = planes * Hh * Wh;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -576,7 +579,7 @@ extern "C" int pggan_rgb_wgrad(const void* f, const float* img, float* acc, floa
     return PG_OK;
 }
 
-extern "C" int pggan_image_fade(const float* x, const float* low, float* out, int B, int Cimg, int H, int W, float alpha,
+extern "C" int pggan_image_fade(const float* x, const float* low, float* out, int B, int Cimg, int H, int W, pg_coef alpha,
                                 void* stream) {
     PG_CHECK(x && out && B > 0 && Cimg > 0 && H > 1 && W > 1 && H % 2 == 0 && W % 2 == 0, PG_ERR_ARG,
              "pggan_image_fade: bad args (H=%d W=%d must be even)", H, W);
@@ -590,7 +593,7 @@ extern "C" int pggan_image_fade(const float* x, const float* low, float* out, in
     return PG_OK;
 }
 
-extern "C" int pggan_image_pool_sum(const float* x, float* out, int B, int Cimg, int H, int W, float scale, void* stream) {
+extern "C" int pggan_image_pool_sum(const float* x, float* out, int B, int Cimg, int H, int W, pg_coef scale, void* stream) {
     PG_CHECK(x && out && B > 0 && Cimg > 0 && H > 1 && W > 1 && H % 2 == 0 && W % 2 == 0, PG_ERR_ARG,
              "pggan_image_pool_sum: bad args");
     PG_CHECK((reinterpret_cast<uintptr_t>(x) & 7) == 0, PG_ERR_ARG, "pggan_image_pool_sum: misaligned pointer");

@@ -53,7 +53,8 @@ struct WgKArgs {
     int PW, PH, PB;                 // pixel box of one stage
     int chunks_w, chunks_h, chunks_b;
     int tiles_n, tiles_c, splits, chunks_per_split;
-    int f16;                        // 16-bit operands are IEEE half (else bf16)
+    int f16;                        // 16-bit g is IEEE half (else bf16)
+    int xf16;                       // ... and x (mixed precision: g bf16, x fp16)
     int span5d;                     // 1: tensor maps are 5-D (channel spans are the 5th dim): one TMA box per operand
     int tpu;                        // taps per unit: C < BLOCK_C layers stack tpu = BLOCK_C/C shifted x tiles side by
                                     // side along the MMA N dimension (one g tile feeds several taps at full N = 256)
@@ -175,7 +176,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
         }
     } else if (warp == 1) {
         if (elect_one()) {    // (not lane == 0: ptxas keeps descriptors in uniform registers only under elect.sync)
-            const uint32_t idesc = make_idesc(kTF32 ? 2 : (a.f16 ? 0 : 1), 1, 1, 128, BLOCK_C);
+            const uint32_t idesc = make_idesc2(kTF32 ? 2 : (a.f16 ? 0 : 1), kTF32 ? 2 : (a.xf16 ? 0 : 1), 1, 1, 128, BLOCK_C);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -264,8 +265,13 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
 // 16x16 output tile per block, pixels split across blockIdx.x, partial sums via atomics.
 template <typename T>
 __global__ void wgrad_direct_kernel(const T* __restrict__ g, const T* __restrict__ x, float* __restrict__ acc, int B,
-                                    int H, int W, int C, int N, int taps, long long pix_per_block) {
+                                    int H, int W, int C, int N, int taps, long long pix_per_block, int gf16, int xf16) {
     __shared__ float gs[16][17], xs[16][17];
+    // 16-bit instantiation: bf16 / IEEE half per operand are run-time flags
+    auto ldv = [](const T* p, int f16) -> float {
+        if constexpr (sizeof(T) == 2) return f16bits_to_f(*reinterpret_cast<const uint16_t*>(p), f16 != 0);
+        else return *p;
+    };
     const long long P = static_cast<long long>(B) * H * W;
     const long long p0 = blockIdx.x * pix_per_block;
     long long p1 = p0 + pix_per_block;
@@ -280,12 +286,12 @@ __global__ void wgrad_direct_kernel(const T* __restrict__ g, const T* __restrict
         const long long pp = p + ty;
         float gv = 0.f, xv = 0.f;
         if (pp < p1) {
-            if (n0 + tx < N) gv = DT<T>::to_f(g[pp * N + n0 + tx]);
+            if (n0 + tx < N) gv = ldv(g + pp * N + n0 + tx, gf16);
             const int w = static_cast<int>(pp % W), h = static_cast<int>((pp / W) % H);
             const long long b = pp / (static_cast<long long>(W) * H);
             const int hh = h + dh, ww = w + dw;
             if (hh >= 0 && hh < H && ww >= 0 && ww < W && c0 + tx < C)
-                xv = DT<T>::to_f(x[((b * H + hh) * W + ww) * C + c0 + tx]);
+                xv = ldv(x + ((b * H + hh) * W + ww) * C + c0 + tx, xf16);
         }
         __syncthreads();
         gs[ty][tx] = gv;
@@ -305,8 +311,12 @@ __global__ void wgrad_direct_kernel(const T* __restrict__ g, const T* __restrict
 template <typename T, int TW, int NT>
 __global__ void __launch_bounds__(256)
 wgrad_small_kernel(const T* __restrict__ g, const T* __restrict__ x, float* __restrict__ acc, int B, int H, int W, int C,
-                   int N) {
+                   int N, int gf16, int xf16) {
     extern __shared__ float sm[];
+    auto cvt = [](const T& v, int f16) -> float {
+        if constexpr (sizeof(T) == 2) return f16bits_to_f(*reinterpret_cast<const uint16_t*>(&v), f16 != 0);
+        else return v;
+    };
     float* sg = sm;                                   // [TW][N]
     float* sx = sm + TW * N;                          // [3][TW + 2][C]
     constexpr int VN = 16 / sizeof(T);
@@ -336,7 +346,7 @@ wgrad_small_kernel(const T* __restrict__ g, const T* __restrict__ x, float* __re
             const uint4 raw = __ldg(reinterpret_cast<const uint4*>(gsrc) + k);
             const T* v = reinterpret_cast<const T*>(&raw);
 #pragma unroll
-            for (int e = 0; e < VN; ++e) sg[k * VN + e] = DT<T>::to_f(v[e]);
+            for (int e = 0; e < VN; ++e) sg[k * VN + e] = cvt(v[e], gf16);
         }
         const int nvx = xrow / VN;
         for (int k = threadIdx.x; k < 3 * nvx; k += blockDim.x) {
@@ -349,7 +359,7 @@ wgrad_small_kernel(const T* __restrict__ g, const T* __restrict__ x, float* __re
                 raw = __ldg(reinterpret_cast<const uint4*>(x + ((b * H + hh) * W + ww) * C + (kv * VN) % C));
             const T* v = reinterpret_cast<const T*>(&raw);
 #pragma unroll
-            for (int e = 0; e < VN; ++e) sx[r * xrow + kv * VN + e] = DT<T>::to_f(v[e]);
+            for (int e = 0; e < VN; ++e) sx[r * xrow + kv * VN + e] = cvt(v[e], xf16);
         }
         __syncthreads();
         if (lane_id < PL) {
@@ -433,6 +443,8 @@ static int launch_wg(const pg_wgrad_params* p, cudaStream_t stream) {
     CUtensorMap tg, tx;
     const int sw = sizeof(T) == 4 ? 12832 : 128;
     a.f16 = p->dtype == PG_F16;
+    a.xf16 = other_dtype(p->dtype, p->x_fmt) == PG_F16;
+    const int xdt = sizeof(T) == 4 ? PG_F32 : other_dtype(p->dtype, p->x_fmt);
     a.span5d = (p->N % Cfg::CPS == 0 && p->C % Cfg::CPS == 0) ? 1 : 0;
     if (a.span5d) {
         // dims: (channel within span, w, h, b, span); the span stride is one 128-byte span
@@ -449,7 +461,7 @@ static int launch_wg(const pg_wgrad_params* p, cudaStream_t stream) {
             uint64_t strides[4] = {(uint64_t)p->C * es, (uint64_t)p->W * p->C * es, (uint64_t)p->H * p->W * p->C * es, span_bytes};
             uint32_t box[5] = {(uint32_t)Cfg::CPS, (uint32_t)a.PW, (uint32_t)a.PH, (uint32_t)a.PB,
                                (uint32_t)(a.tpu > 1 ? Cfg::GB / a.tpu : Cfg::GB)};
-            int rc = encode_tmap(&tx, p->dtype == PG_F16 ? PG_F16 : DT<T>::kEnum, 5, p->x, dims, strides, box, sw);
+            int rc = encode_tmap(&tx, xdt, 5, p->x, dims, strides, box, sw);
             if (rc != PG_OK) return rc;
         }
     } else {
@@ -463,16 +475,12 @@ static int launch_wg(const pg_wgrad_params* p, cudaStream_t stream) {
         {
             uint64_t dims[4] = {(uint64_t)p->C, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
             uint64_t strides[3] = {(uint64_t)p->C * es, (uint64_t)p->W * p->C * es, (uint64_t)p->H * p->W * p->C * es};
-            int rc = encode_tmap(&tx, p->dtype == PG_F16 ? PG_F16 : DT<T>::kEnum, 4, p->x, dims, strides, box, sw);
+            int rc = encode_tmap(&tx, xdt, 4, p->x, dims, strides, box, sw);
             if (rc != PG_OK) return rc;
         }
     }
     auto kern = wgrad_gemm_kernel<T, BLOCK_C>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-        attr_done = true;
-    }
+    PG_SET_SMEM_ONCE(kern, Cfg::kSmemBytes);
     const int num_units = base_units * a.splits;
     const int grid = num_units < num_sms() ? num_units : num_sms();
     kern<<<grid, kWgThreads, Cfg::kSmemBytes, stream>>>(tg, tx, a);
@@ -488,10 +496,11 @@ static int slices_wg(const pg_wgrad_params* p) {
     return a.splits;
 }
 
-// SIMT kernels do arithmetic on the element values: templated on the REAL element type (the tensor-core path serves
-// bf16 and f16 from one 16-bit instantiation)
+// SIMT kernels do arithmetic on the element values: the 16-bit instantiation takes the element formats of g and x
+// (bf16 / IEEE half, possibly different: mixed precision) as run-time flags
 template <typename T>
 static int wgrad_simt(const pg_wgrad_params* p, cudaStream_t stream) {
+    const int gf16 = p->dtype == PG_F16, xf16 = other_dtype(p->dtype, p->x_fmt) == PG_F16;
     // SIMT path: one slice, partial sums meet through atomics on a zeroed accumulator
     PG_CUDA(cudaMemsetAsync(p->acc, 0, sizeof(float) * (size_t)p->N * p->taps * p->C, stream));
     constexpr int VNT = 16 / sizeof(T);
@@ -505,9 +514,9 @@ static int wgrad_simt(const pg_wgrad_params* p, cudaStream_t stream) {
         const T* gp = reinterpret_cast<const T*>(p->g);
         const T* xp = reinterpret_cast<const T*>(p->x);
         if (p->C * (p->N / 4) <= 256)
-            wgrad_small_kernel<T, TW, 4><<<(int)grid, 256, smem, stream>>>(gp, xp, p->acc, p->B, p->H, p->W, p->C, p->N);
+            wgrad_small_kernel<T, TW, 4><<<(int)grid, 256, smem, stream>>>(gp, xp, p->acc, p->B, p->H, p->W, p->C, p->N, gf16, xf16);
         else
-            wgrad_small_kernel<T, TW, 8><<<(int)grid, 256, smem, stream>>>(gp, xp, p->acc, p->B, p->H, p->W, p->C, p->N);
+            wgrad_small_kernel<T, TW, 8><<<(int)grid, 256, smem, stream>>>(gp, xp, p->acc, p->B, p->H, p->W, p->C, p->N, gf16, xf16);
         PG_LAUNCH_CHECK();
         g_simt_launches++;
         return PG_OK;
@@ -518,7 +527,7 @@ static int wgrad_simt(const pg_wgrad_params* p, cudaStream_t stream) {
     dim3 grid((unsigned)((P + pix_per_block - 1) / pix_per_block), (unsigned)p->taps,
               (unsigned)(((p->N + 15) / 16) * ((p->C + 15) / 16)));
     wgrad_direct_kernel<T><<<grid, 256, 0, stream>>>(reinterpret_cast<const T*>(p->g), reinterpret_cast<const T*>(p->x),
-                                                      p->acc, p->B, p->H, p->W, p->C, p->N, p->taps, pix_per_block);
+                                                      p->acc, p->B, p->H, p->W, p->C, p->N, p->taps, pix_per_block, gf16, xf16);
     PG_LAUNCH_CHECK();
     g_simt_launches++;
     return PG_OK;
@@ -580,7 +589,6 @@ static int wgrad_dispatch(const pg_wgrad_params* p_in, cudaStream_t stream, int*
             if (p->C % 32 == 0) return launch_wg<T, 32>(p, stream);
         }
     }
-    if (p->dtype == PG_F16) return wgrad_simt<__half>(p, stream);
     return wgrad_simt<T>(p, stream);
 }
 
@@ -593,6 +601,8 @@ extern "C" int pggan_conv_wgrad(const pg_wgrad_params* p, void* stream) {
              "pggan_conv_wgrad: bad dims B=%d H=%d W=%d C=%d N=%d", p->B, p->H, p->W, p->C, p->N);
     PG_CHECK(p->taps == 1 || p->taps == 9, PG_ERR_ARG, "pggan_conv_wgrad: taps must be 1 or 9 (got %d)", p->taps);
     PG_CHECK(p->dtype == PG_BF16 || p->dtype == PG_F16 || p->dtype == PG_F32, PG_ERR_ARG, "pggan_conv_wgrad: bad dtype %d", p->dtype);
+    PG_CHECK(p->x_fmt == 0 || (is16(p->dtype) && (p->x_fmt == PG_BF16 + 1 || p->x_fmt == PG_F16 + 1)), PG_ERR_ARG,
+             "pggan_conv_wgrad: bad x_fmt %d (mixed operand formats exist for the 16-bit types only)", p->x_fmt);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (is16(p->dtype)) return wgrad_dispatch<__nv_bfloat16>(p, s, nullptr);
     return wgrad_dispatch<float>(p, s, nullptr);

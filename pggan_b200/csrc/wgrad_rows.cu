@@ -33,7 +33,8 @@ struct WrKArgs {
     long long slice_elems;
     int B, H, W, C, N;
     int nseg;
-    int f16;                 // operands are IEEE half (else bf16)
+    int f16;                 // g is IEEE half (else bf16)
+    int xf16;                // ... and x (mixed precision: g bf16, x fp16)
     long long total, per_cta;
 };
 
@@ -149,7 +150,7 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         // -------------------------------------------------------------------- MMA issuer(s)
         const int iss = warp == 1 ? 0 : 1;
         if (elect_one()) {    // (not lane == 0: ptxas keeps descriptors in uniform registers only under elect.sync)
-            const uint32_t idesc = make_idesc(a.f16 ? 0 : 1, 1, 1, 128, NCOLS);
+            const uint32_t idesc = make_idesc2(a.xf16 ? 0 : 1, a.f16 ? 0 : 1, 1, 1, 128, NCOLS);
             const uint32_t xring_addr = smem_u32(xring), gring_addr = smem_u32(gring);
             uint32_t LX = 0, LG = 0;
             bool first = true;
@@ -270,6 +271,7 @@ static int launch_wr(const pg_wgrad_params* p, cudaStream_t stream) {
     a.B = p->B; a.H = p->H; a.W = p->W; a.C = p->C; a.N = p->N;
     a.nseg = p->W / 128;
     a.f16 = p->dtype == PG_F16;
+    a.xf16 = other_dtype(p->dtype, p->x_fmt) == PG_F16;
     int grid;
     wr_plan(p, a.total, a.per_cta, grid);
     CUtensorMap tx, tg;
@@ -277,7 +279,7 @@ static int launch_wr(const pg_wgrad_params* p, cudaStream_t stream) {
         uint64_t dims[4] = {(uint64_t)p->C, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
         uint64_t strides[3] = {(uint64_t)p->C * 2, (uint64_t)p->W * p->C * 2, (uint64_t)p->H * p->W * p->C * 2};
         uint32_t box[4] = {(uint32_t)p->C, (uint32_t)Cfg::kXPW, 1u, 1u};
-        int rc = encode_tmap(&tx, p->dtype, 4, p->x, dims, strides, box, XSPAN);
+        int rc = encode_tmap(&tx, other_dtype(p->dtype, p->x_fmt), 4, p->x, dims, strides, box, XSPAN);
         if (rc != PG_OK) return rc;
     }
     {
@@ -288,11 +290,7 @@ static int launch_wr(const pg_wgrad_params* p, cudaStream_t stream) {
         if (rc != PG_OK) return rc;
     }
     auto kern = wgrad_rows_kernel<XSPAN, GSPAN>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-        attr_done = true;
-    }
+    PG_SET_SMEM_ONCE(kern, Cfg::kSmemBytes);
     kern<<<grid, kWrThreads, Cfg::kSmemBytes, stream>>>(tx, tg, a);
     PG_LAUNCH_CHECK();
     g_tc_launches++;

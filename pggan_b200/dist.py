@@ -5,8 +5,8 @@ actually runs (it keeps only `.module`): every rank holds a full r
 batch, gradients are summed across ranks once per optimizer step and the 1/world_size is folded into
 the Adam kernel.  Buckets are contiguous slices of the flat gradient buffer (optim.FlatGrads) in
 gradient-ready order; a bucket's all-reduce is launched (async, on NCCL's stream over NVLink/NVSwitch)
-from the autograd hook of the last parameter that completes it, so communication overlaps the rest of
-the backward pass.  Only live parameters are registered.
+by the gradient contribution that completes it, so communication overlaps the rest of the backward
+pass.  Only live parameters are registered.
 
 The D step of the WGAN-GP variant has two backward calls (GP's own, then loss_D's): arm() is called
 before the LAST one only, so each bucket is reduced once per step.  Backend-agnostic (gloo on CPU in
@@ -32,6 +32,14 @@ def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None) -> N
 
 
 class GradSync:
+    """Bucket readiness is COUNTED, not hooked: the training step is a fixed program, so every parameter receives the
+    same number of gradient contributions in every armed backward.  A contribution is either an in-place accumulation
+    by a wgrad / bias kernel (ops._GRAD_SINK: reported through ops.add_sink_listener) or autograd's own accumulation
+    (post-accumulate-grad hook: the RGB layers and whatever else is not sunk).  The first armed backward LEARNS the
+    counts (its buckets are all reduced in finish()); from then on a bucket's all-reduce is launched by the
+    contribution that completes it, so the in-place gradient sink stays on under data parallelism and NCCL overlaps
+    the rest of backward."""
+
     def __init__(self, grads: FlatGrads, bucket_bytes: int = 32 << 20, group=None):
         self.grads = grads
         self.group = group
@@ -51,20 +59,19 @@ class GradSync:
             for p in b["params"]:
                 self._param_bucket[id(p)] = bi
         self._armed = False
-        self._pending: List[int] = []
+        self._expected = None            # learned: contributions per bucket in one armed backward
+        self._seen: List[int] = []
         self._launched: List[bool] = []
         self._handles = []
-        self._hooks = [p.register_post_accumulate_grad_hook(self._hook) for p in grads.params]
-        if self.world > 1:
-            # bucket readiness relies on autograd's post-accumulate hooks: keep gradients on the autograd path
-            from . import ops
-            ops.unregister_grad_sink(grads.params)
+        self._hooks = [p.register_post_accumulate_grad_hook(self._notify) for p in grads.params]
+        from . import ops
+        ops.add_sink_listener(self._notify)
 
     # ------------------------------------------------------------------------------------
     def arm(self):
         """call right before the last backward of the optimizer step"""
         self._armed = self.world > 1
-        self._pending = [len(b["params"]) for b in self.buckets]
+        self._seen = [0] * len(self.buckets)
         self._launched = [False] * len(self.buckets)
         self._handles = []
 
@@ -74,26 +81,40 @@ class GradSync:
         view = self.grads.flat[b["lo"]:b["hi"]]
         self._handles.append(dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
-    def _hook(self, p):
+    def _notify(self, p):
         if not self._armed:
             return
-        bi = self._param_bucket[id(p)]
-        self._pending[bi] -= 1
-        if self._pending[bi] == 0:
-            # identical launch order on every rank: buckets go out strictly in index order
-            for j in range(len(self.buckets)):
-                if self._launched[j]:
-                    continue
-                if self._pending[j] == 0:
-                    self._launch(j)
-                else:
-                    break
+        bi = self._param_bucket.get(id(p))
+        if bi is None:
+            return
+        if self._launched[bi]:
+            raise RuntimeError("GradSync: a gradient contribution arrived after its bucket was reduced — the step's "
+                               "structure changed; create a new GradSync (set_optimizers) or call relearn()")
+        self._seen[bi] += 1
+        if self._expected is None or self._seen[bi] < self._expected[bi]:
+            return
+        # identical launch order on every rank: buckets go out strictly in index order
+        for j in range(len(self.buckets)):
+            if self._launched[j]:
+                continue
+            if self._seen[j] >= self._expected[j]:          # (a bucket that expects nothing is complete as it is)
+                self._launch(j)
+            else:
+                break
+
+    def relearn(self):
+        self._expected = None
 
     def finish(self):
-        """after the backward: launch whatever did not fire (unused parameters), wait for all.
+        """after the backward: launch whatever did not fire (unused parameters, the learning pass), wait for all.
         Gradients then hold the SUM over ranks; pass grad_scale = 1/world to the optimizer."""
         if not self._armed:
             return
+        if self._expected is None:
+            self._expected = list(self._seen)
+        elif self._expected != self._seen:
+            # fewer contributions than learned (more would have raised above): learn again, reduce the rest now
+            self._expected = list(self._seen)
         for bi in range(len(self.buckets)):
             if not self._launched[bi]:
                 self._launch(bi)
@@ -105,3 +126,5 @@ class GradSync:
         for h in self._hooks:
             h.remove()
         self._hooks = []
+        from . import ops
+        ops.remove_sink_listener(self._notify)

@@ -2,9 +2,8 @@
 (and, through custom_layers.py, of its dead duplicate lib/custom_layers.py).
 
 Same classes, constructor signatures, attribute names (`.module.weight/.bias`, float `.weight`) and
-state_dict keys; the arithmetic runs in libpggan_b200.so.  Outputs are channels_last tensors in the
-compute dtype (ops.get_compute_dtype()), like an autocast region; the networks in nets.py convert
-their final outputs back to fp32.
+state_dict keys; the arithmetic runs in libpggan_b200.so.  Outputs are channels_last 16-bit (or fp32) tensors, like an
+autocast region (see the precision modes in ops.py); the networks in nets.py convert their final outputs back to fp32.
 """
 from __future__ import annotations
 
@@ -24,7 +23,7 @@ class PixelwiseVectorNorm(nn.Module):
         super().__init__()
 
     def forward(self, x, epsilon=1e-8):
-        return ops.PixelNorm.apply(x, float(epsilon))
+        return ops.export_act(ops.PixelNorm.apply(x, float(epsilon)))
 
 
 def getLayerNormalizationFactor(x):
@@ -80,7 +79,9 @@ class ConstrainedLayer(nn.Module):
         return ops.ConvF.apply(x, W, b, c, float(slope), raw_out, layout, x_act_slope, bool(defer_mask))
 
     def forward(self, x):
-        return self.fused(x, 1.0)
+        """the reference's public call: c * module(x).  (In mixed-precision mode the result is exported as an honest
+        fp16 tensor; the blocks / networks call `fused`, whose results stay in the kernels' internal container.)"""
+        return ops.export_act(self.fused(x, 1.0))
 
 
 class EqualizedConv2d(ConstrainedLayer):

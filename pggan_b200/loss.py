@@ -18,21 +18,28 @@ from . import ops
 
 
 class LazyLossDict(dict):
-    """dict whose tensor values are turned into round(x.item(), 4) on read (the reference stores the
-    rounded float eagerly, which costs 4-6 host syncs per step — pggan/loss.py:12,23-25)."""
+    """dict whose tensor values are read as round(x.item(), 4) (the reference stores the rounded float eagerly, which
+    costs 4-6 host syncs per step — pggan/loss.py:12,23-25).  The TENSOR stays stored: under CUDA-graph replay the
+    Python loss code does not run again, the graph refreshes the same tensors, and every read sees the current step."""
 
     def __getitem__(self, key):
         v = dict.__getitem__(self, key)
         if isinstance(v, torch.Tensor):
-            v = round(float(v.item()), 4)
-            dict.__setitem__(self, key, v)
+            return round(float(v.item()), 4)
         return v
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
 
     def items(self):
         return [(k, self[k]) for k in dict.keys(self)]
 
     def values(self):
         return [self[k] for k in dict.keys(self)]
+
+    def tensors(self):
+        """the raw stored values (0-dim device tensors), no host sync"""
+        return dict(dict.items(self))
 
 
 class LossInterface(metaclass=abc.ABCMeta):

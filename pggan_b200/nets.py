@@ -17,7 +17,32 @@ from .layers import EqualizedLinear, PixelwiseVectorNorm
 from .utils import num_flat_features
 
 
-class Generator(nn.Module):
+class _AlphaMixin:
+    """`alpha` stays the plain mutable float attribute of the reference (pggan/model.py:146-147,179-182 assign it from
+    outside).  The kernels read it from a one-element device tensor that is refreshed whenever the float changed, so a
+    captured CUDA graph follows change_alpha() without being captured again."""
+
+    def alpha_ref(self) -> "ops.AlphaRef":
+        dev = next(self.parameters()).device
+        a = float(self.alpha)
+        if dev.type != "cuda":
+            return ops.AlphaRef(a, None)
+        st = self.__dict__
+        t = st.get("_alpha_dev")
+        if t is None or t.device != dev:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("call alpha_ref() once before capturing a CUDA graph (the device scalar must exist)")
+            st["_alpha_dev"] = t = torch.full((1,), a, dtype=torch.float32, device=dev)
+            st["_alpha_host"] = a
+        elif st["_alpha_host"] != a:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("alpha changed inside a CUDA graph capture")
+            t.fill_(a)
+            st["_alpha_host"] = a
+        return ops.AlphaRef(a, t)
+
+
+class Generator(_AlphaMixin, nn.Module):
     """reference pggan/nets.py:10-161"""
 
     def __init__(self, latent_dim, first_depth, init_bias_to_zero=True, LReLU_slope=0.2, apply_pixel_norm=True,
@@ -80,7 +105,7 @@ class Generator(nn.Module):
         pn = self.pixel_norm if self.apply_pixel_norm else None
         x = x.reshape(-1, num_flat_features(x))
         if pn is not None:
-            x = pn(x)
+            x = ops.PixelNorm.apply(x, 1e-8)
         # format layer: Linear(latent -> 16*C) + LReLU, written directly in NHWC order by permuting the
         # output rows of the weight ((c,h,w) -> (h,w,c)); views only, so gradients map back for free
         lin = self.latent_format_layer.module
@@ -92,7 +117,7 @@ class Generator(nn.Module):
             # of the (h,w,c)-ordered output: run the fused conv+act+PN on a [B*16, C0] view
             x = ops.ConvF.apply(x, lin.weight, lin.bias, self.latent_format_layer.scale(), slope, False, layout)
             x = x.view(x.shape[0], 4, 4, C0).permute(0, 3, 1, 2)       # [B,C,4,4] logical, NHWC physical
-            x = pn(x)
+            x = ops.PixelNorm.apply(x, 1e-8)
         else:
             x = ops.ConvF.apply(x, lin.weight, lin.bias, self.latent_format_layer.scale(), slope, False, layout)
             x = x.view(x.shape[0], 4, 4, C0).permute(0, 3, 1, 2)
@@ -108,13 +133,13 @@ class Generator(nn.Module):
         x = self.toRGB_blocks[-1](x)
         if nb:
             # (1-alpha) * upscale2d(low) + alpha * x in one pass (pggan/nets.py:155-156)
-            x = ops.ImageFade.apply(x, low, float(self.alpha))
+            x = ops.ImageFade.apply(x, low, self.alpha_ref())
         if self.last_activation is not None:
             x = self.last_activation(x)
         return x
 
 
-class Discriminator(nn.Module):
+class Discriminator(_AlphaMixin, nn.Module):
     """reference pggan/nets.py:164-276"""
 
     def __init__(self, last_depth, init_bias_to_zero=True, LReLU_slope=0.2, decision_layer_size=1,
@@ -174,11 +199,11 @@ class Discriminator(nn.Module):
         for block in reversed(self.blocks):
             if apply_merge:
                 apply_merge = False
-                x = block(x, blend_with=x_down, alpha=float(self.alpha), x_act_slope=0.2 if fuse_rgb else None)
+                x = block(x, blend_with=x_down, alpha=self.alpha_ref(), x_act_slope=0.2 if fuse_rgb else None)
             else:
                 x = block(x)
         x = self.minibatch_normalization_block(x)
         out = self.decision_layer.fused(x, 1.0, raw_out=True)
         if not get_feature:
             return out
-        return out, x.float()
+        return out, ops.ExportFloat.apply(x)

@@ -6,8 +6,23 @@ reference pggan/loss.py:78-90) can be differentiated again: {fprop, dgrad, wgrad
 differentiation, LeakyReLU contributes only its mask, pooling / up-sampling /
 blends are linear, and minibatch-stddev has a true second-order kernel.
 
-Feature maps are channels_last tensors ([B,C,H,W] logical, NHWC physical) in the compute dtype
-(torch.bfloat16, or torch.float32 which runs on kind::tf32 MMAs); images/logits/parameters are fp32.
+Feature maps are channels_last tensors ([B,C,H,W] logical, NHWC physical); images/logits/parameters are fp32.
+
+Precision modes (set_compute_dtype):
+  "mixed" (default, the benchmarked mode)  ACTIVATIONS and packed weights are IEEE half (11-bit significand: meets
+          north_star's 1e-2 / 1e-3 bars), GRADIENT tensors are bf16 (fp32's exponent range: no loss scaling); the
+          tensor cores multiply the two directly (kind::f16, independent A/B operand formats), accumulate in fp32.
+          Conversions to half saturate at +-65504.
+  torch.bfloat16 / torch.float16           everything in that one 16-bit format
+  torch.float32                            3xTF32 operands, fp32 accumulate: the parity mode
+
+Two tensor CLASSES therefore exist: "a" (activation-like: produced by a forward pass) and "g" (gradient-like: produced
+by a backward pass, including everything the double backward derives from gradients).  Every 16-bit feature tensor
+carries the torch dtype of the GRADIENT class (`get_compute_dtype()`), so autograd's own gradient accumulation and
+dtype checks act on honestly-labelled tensors; in mixed mode an activation tensor is therefore a bf16-LABELLED
+container of fp16 bits.  Only kernels of this library read activations; `to_float()` / the networks' fp32 outputs are
+the way out, and the per-layer public `forward()` of layers.py exports honest fp16.  The class of every operand is
+static at each call site and passed down as `xc` / `cls` arguments.
 """
 from __future__ import annotations
 
@@ -19,7 +34,12 @@ import torch
 
 from . import _lib as L
 
-_COMPUTE_DTYPE = torch.bfloat16
+A, G = "a", "g"                # tensor classes, see the module docstring
+MIXED = "mixed"
+_MODE = MIXED
+_COMPUTE_DTYPE = torch.bfloat16          # torch label of 16-bit feature tensors == real format of the gradient class
+_ACT_FMT, _GRAD_FMT = L.PG_F16, L.PG_BF16
+_REAL = {L.PG_BF16: torch.bfloat16, L.PG_F16: torch.float16, L.PG_F32: torch.float32}
 _SKIP_PARAM_GRADS = False      # see input_grad_only()
 PROFILE = None                 # bench.py sets a dict: (kind, shape) -> [(start_event, end_event), ...]
 
@@ -43,18 +63,36 @@ class _Timed:
             PROFILE.setdefault(self.key, []).append((self.e0, self.e1))
 
 
-def set_compute_dtype(dtype: torch.dtype) -> None:
-    """torch.bfloat16 (bf16 operands, fp32 accumulate — the default), torch.float16 (same kernels and speed, 11-bit
-    significand: meets the 1e-2 forward bar bf16 misses beyond 16x16; 5-bit exponent, so activations / gradients
-    must stay inside +-65504 / above ~6e-8) or torch.float32 (3xTF32 operands, fp32 accumulate: the parity mode)."""
-    global _COMPUTE_DTYPE
-    if dtype not in (torch.bfloat16, torch.float16, torch.float32):
-        raise ValueError("compute dtype must be torch.bfloat16, torch.float16 or torch.float32 (3xTF32)")
-    _COMPUTE_DTYPE = dtype
+def set_compute_dtype(dtype) -> None:
+    """"mixed" (fp16 activations/weights, bf16 gradients — the default), torch.bfloat16, torch.float16 (one 16-bit
+    format for everything; same kernels and speed) or torch.float32 (3xTF32 operands: the parity mode)."""
+    global _COMPUTE_DTYPE, _ACT_FMT, _GRAD_FMT, _MODE
+    if dtype == MIXED:
+        _MODE, _COMPUTE_DTYPE, _ACT_FMT, _GRAD_FMT = MIXED, torch.bfloat16, L.PG_F16, L.PG_BF16
+    elif dtype == torch.bfloat16:
+        _MODE, _COMPUTE_DTYPE, _ACT_FMT, _GRAD_FMT = "bf16", torch.bfloat16, L.PG_BF16, L.PG_BF16
+    elif dtype == torch.float16:
+        _MODE, _COMPUTE_DTYPE, _ACT_FMT, _GRAD_FMT = "fp16", torch.float16, L.PG_F16, L.PG_F16
+    elif dtype == torch.float32:
+        _MODE, _COMPUTE_DTYPE, _ACT_FMT, _GRAD_FMT = "fp32", torch.float32, L.PG_F32, L.PG_F32
+    else:
+        raise ValueError('compute dtype must be "mixed", torch.bfloat16, torch.float16 or torch.float32 (3xTF32)')
+    _KIND_CACHE.clear()
+    _PACK_CACHE.clear()
 
 
 def get_compute_dtype() -> torch.dtype:
+    """torch dtype that 16-bit feature tensors carry (the real format of the gradient class)"""
     return _COMPUTE_DTYPE
+
+
+def get_precision_mode() -> str:
+    """one of "mixed", "bf16", "fp16", "fp32" """
+    return _MODE
+
+
+def _fmt(cls: str) -> int:
+    return _ACT_FMT if cls == A else _GRAD_FMT
 
 
 @contextlib.contextmanager
@@ -72,12 +110,16 @@ def input_grad_only():
 
 
 # ------------------------------------------------------------------------------- gradient sinks
-# Parameters registered here (by optim.FlatGrads) own a persistent fp32 `.grad` view into a flat buffer.
-# In a plain backward (no create_graph) the GEMM-class Functions then ACCUMULATE weight / bias gradients
-# straight into that view (pggan_unpack_wgrad accumulate=1, atomics of the bias column sums) and return
-# None to autograd: no temporary gradient tensor, no AccumulateGrad add kernel, no zero-fill.
-# Not used under data parallelism (GradSync needs autograd's post-accumulate hooks for bucket readiness).
+# Parameters registered here (by optim.FlatGrads) own a persistent fp32 `.grad` view into a flat buffer.  Inside a
+# `grad_sink()` context (the trainer opens one around its own backward() calls) a plain backward (no create_graph)
+# lets the GEMM-class Functions ACCUMULATE weight / bias gradients straight into that view (pggan_unpack_wgrad
+# accumulate=1, atomics of the bias column sums) and return None to autograd: no temporary gradient tensor, no
+# AccumulateGrad add kernel, no zero-fill.  Outside the context the Functions behave like any autograd Function
+# (gradients are returned), so torch.autograd.grad / hooks / backward(inputs=...) see what they expect.
+# Every in-place accumulation is reported to the listeners (dist.GradSync counts them for bucket readiness).
 _GRAD_SINK: dict = {}
+_SINK_ENABLED = False
+_SINK_LISTENERS: list = []
 
 
 def register_grad_sink(params):
@@ -91,9 +133,29 @@ def unregister_grad_sink(params):
         _GRAD_SINK.pop(id(p), None)
 
 
+@contextlib.contextmanager
+def grad_sink(enabled: bool = True):
+    global _SINK_ENABLED
+    prev = _SINK_ENABLED
+    _SINK_ENABLED = enabled
+    try:
+        yield
+    finally:
+        _SINK_ENABLED = prev
+
+
+def add_sink_listener(fn):
+    _SINK_LISTENERS.append(fn)
+
+
+def remove_sink_listener(fn):
+    if fn in _SINK_LISTENERS:
+        _SINK_LISTENERS.remove(fn)
+
+
 def _sink(p):
     """the parameter's .grad if gradients may be accumulated into it in place, else None"""
-    if p is None:
+    if p is None or not _SINK_ENABLED:
         return None
     ref = _GRAD_SINK.get(id(p))
     if ref is None or ref() is not p:
@@ -104,17 +166,13 @@ def _sink(p):
     return g
 
 
+def _sunk(p):
+    """a gradient contribution of `p` has just been accumulated in place"""
+    for fn in _SINK_LISTENERS:
+        fn(p)
+
+
 # ------------------------------------------------------------------------------------ helpers
-def _enum(dtype: torch.dtype) -> int:
-    if dtype == torch.bfloat16:
-        return L.PG_BF16
-    if dtype == torch.float16:
-        return L.PG_F16
-    if dtype == torch.float32:
-        return L.PG_F32
-    raise TypeError(f"unsupported feature dtype {dtype}")
-
-
 def _p(t: Optional[torch.Tensor]):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
@@ -135,11 +193,105 @@ def cl(x: torch.Tensor) -> torch.Tensor:
     return x.contiguous()
 
 
-def feat(x: torch.Tensor) -> torch.Tensor:
-    """cl() + cast to the compute dtype."""
+class _Import(torch.autograd.Function):
+    """external tensor -> internal feature tensor of class `cls` whose real format differs from the label
+    (mixed mode activations); the gradient goes back honestly labelled"""
+
+    @staticmethod
+    def forward(ctx, x, cls):
+        ctx.dtype = x.dtype
+        return x.to(_REAL[_fmt(cls)]).view(_COMPUTE_DTYPE)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(ctx.dtype), None
+
+
+def feat(x: torch.Tensor, cls: str = A) -> torch.Tensor:
+    """feature tensor of class `cls` in the kernels' layout.  A tensor that already carries the feature dtype is
+    trusted to BE of that class; anything else (fp32 inputs, honest fp16 in mixed mode) is converted."""
     if x.dtype != _COMPUTE_DTYPE:
-        x = x.to(_COMPUTE_DTYPE)
+        real = _REAL[_fmt(cls)]
+        if real == _COMPUTE_DTYPE:
+            x = x.to(real)
+        elif torch.is_grad_enabled() and x.requires_grad:
+            x = _Import.apply(x, cls)
+        else:
+            x = x.to(real).view(_COMPUTE_DTYPE)
     return cl(x)
+
+
+def to_float(x: torch.Tensor, cls: str = A) -> torch.Tensor:
+    """fp32 values of an internal feature tensor (no autograd; see ExportFloat)"""
+    real = _REAL[_fmt(cls)]
+    if x.dtype == _COMPUTE_DTYPE and real != _COMPUTE_DTYPE:
+        x = x.view(real)
+    return x.float()
+
+
+def to_honest(x: torch.Tensor, cls: str = A) -> torch.Tensor:
+    """the same bits under their real torch dtype"""
+    real = _REAL[_fmt(cls)]
+    if x.dtype == _COMPUTE_DTYPE and real != _COMPUTE_DTYPE:
+        return x.view(real)
+    return x
+
+
+class ExportFloat(torch.autograd.Function):
+    """internal activation -> fp32 tensor for the caller (D's `feature` output); differentiable"""
+
+    @staticmethod
+    def forward(ctx, x):
+        return to_float(x, A)
+
+    @staticmethod
+    def backward(ctx, g):
+        return feat(g, G)
+
+
+class ExportAct(torch.autograd.Function):
+    """internal activation -> honestly-labelled 16-bit tensor (the public per-layer forward() in mixed mode)"""
+
+    @staticmethod
+    def forward(ctx, x):
+        return to_honest(x, A)
+
+    @staticmethod
+    def backward(ctx, g):
+        return feat(g, G)
+
+
+def export_act(x: torch.Tensor) -> torch.Tensor:
+    if _REAL[_ACT_FMT] == _COMPUTE_DTYPE or x.dtype != _COMPUTE_DTYPE:
+        return x
+    return ExportAct.apply(x)
+
+
+# fade-in alpha: a float, optionally mirrored in a 1-element fp32 device tensor the kernels read at run time
+class AlphaRef:
+    __slots__ = ("value", "dev")
+
+    def __init__(self, value, dev=None):
+        self.value, self.dev = float(value), dev
+
+    def __float__(self):
+        return float(self.value)
+
+
+def _coef(c0, c1=0.0, alpha=None) -> L.Coef:
+    """pg_coef for  c0 + c1*alpha;  alpha: None, a float or an AlphaRef"""
+    if isinstance(c0, tuple):
+        c0, c1, alpha = c0
+    if alpha is None or c1 == 0.0:
+        return L.Coef(float(c0), 0.0, None)
+    if isinstance(alpha, AlphaRef) and alpha.dev is not None:
+        return L.Coef(float(c0), float(c1), alpha.dev.data_ptr())
+    return L.Coef(float(c0) + float(c1) * float(alpha), 0.0, None)
+
+
+def _affine(c0, c1, alpha):
+    """coefficient (c0 + c1*alpha) as the tuple the kernel wrappers accept in place of a float"""
+    return (float(c0), float(c1), alpha)
 
 
 def _dims(x: torch.Tensor):
@@ -201,12 +353,13 @@ def _packmap(args):
     return m
 
 
-def _pack(W: torch.Tensor, kind: str, dtype: torch.dtype, layout=None) -> torch.Tensor:
-    """fp32 parameter -> K-major packed operand in `dtype`; kind 'f' = fprop [N][taps*C], 't' = dgrad
-    [C][taps*N] with the taps reversed.  Cached per (parameter, version) for nn.Parameters."""
+def _pack(W: torch.Tensor, kind: str, dtype=None, layout=None) -> torch.Tensor:
+    """fp32 parameter -> K-major packed operand in the ACTIVATION format (weights are O(1) numbers: fp16 in mixed mode);
+    kind 'f' = fprop [N][taps*C], 't' = dgrad [C][taps*N] with the taps reversed.  Cached per (parameter, version) for
+    nn.Parameters.  (`dtype` is accepted for compatibility and ignored: the precision mode decides.)"""
     _need_cuda(W)
     cacheable = isinstance(W, torch.nn.Parameter)
-    key = (id(W), W._version, kind, dtype, layout) if cacheable else None
+    key = (id(W), W._version, kind, _ACT_FMT, layout) if cacheable else None
     if cacheable:
         hit = _PACK_CACHE.get(key)
         if hit is not None and hit[0] is W:
@@ -216,9 +369,9 @@ def _pack(W: torch.Tensor, kind: str, dtype: torch.dtype, layout=None) -> torch.
         Wc = Wc.float().contiguous()
     N, C, T, fmap, tmap = _maps(Wc.shape, layout)
     args = fmap if kind == "f" else tmap
-    out = torch.empty((args[0], args[3] * args[4]), dtype=dtype, device=W.device)
+    out = torch.empty((args[0], args[3] * args[4]), dtype=_COMPUTE_DTYPE, device=W.device)
     m = _packmap(args)
-    L.check(L.load().pggan_pack_weight(_p(Wc), _p(out), _enum(dtype), ctypes.byref(m), _s()), "pggan_pack_weight")
+    L.check(L.load().pggan_pack_weight(_p(Wc), _p(out), _ACT_FMT, ctypes.byref(m), _s()), "pggan_pack_weight")
     if cacheable:
         if len(_PACK_CACHE) > 1024:
             _PACK_CACHE.clear()
@@ -241,25 +394,32 @@ def clear_pack_cache(params=None):
 _KIND_CACHE: dict = {}
 
 
+def _other(fmt_main: int, fmt_other: int) -> int:
+    """the `w_fmt` / `x_fmt` field: 0 = same as dtype, else PG_* + 1"""
+    return 0 if fmt_main == fmt_other else fmt_other + 1
+
+
 def conv_pn_fusable(x, N, taps) -> bool:
     """may k_conv(..., pn_eps=...) fuse the pixel norm into this layer's epilogue? (one epilogue thread must own all
     N channels of a pixel: the rows kernel, or the plain kernel when one N tile covers the layer)"""
     b, c, h, w = _dims(x)
-    key = ("pn", b, h, w, c, N, taps, x.dtype)
+    key = ("pn", b, h, w, c, N, taps, _ACT_FMT)
     hit = _KIND_CACHE.get(key)
     if hit is None:
         p = L.ConvParams()
         p.B, p.H, p.W, p.C, p.N, p.taps = b, h, w, c, N, taps
-        p.dtype = p.out_dtype = _enum(x.dtype)
+        p.dtype = p.out_dtype = _ACT_FMT
         hit = bool(L.load().pggan_conv_pn_fusable(ctypes.byref(p)))
         _KIND_CACHE[key] = hit
     return hit
 
 
-def k_conv(x, wp, bias, N, taps, scale, slope=1.0, mask_src=None, mask_slope=1.0, raw_out=False, pn_eps=None):
-    """pn_eps: also apply the pixel norm in the epilogue; returns (y, rnorm[pixels] fp32) then."""
+def k_conv(x, wp, bias, N, taps, scale, slope=1.0, mask_src=None, mask_slope=1.0, raw_out=False, pn_eps=None, xc=A):
+    """pn_eps: also apply the pixel norm in the epilogue; returns (y, rnorm[pixels] fp32) then.
+    xc: class of x (and of y); wp is always in the activation format."""
     _need_cuda(x)
     b, c, h, w = _dims(x)
+    xf = _fmt(xc)
     out_dtype = torch.float32 if raw_out else x.dtype
     y = _new_like_layout(x, N, out_dtype)
     p = L.ConvParams()
@@ -270,11 +430,12 @@ def k_conv(x, wp, bias, N, taps, scale, slope=1.0, mask_src=None, mask_slope=1.0
     p.x, p.wp, p.bias, p.mask_src, p.y = x.data_ptr(), wp.data_ptr(), (bias.data_ptr() if bias is not None else None), \
         (mask_src.data_ptr() if mask_src is not None else None), y.data_ptr()
     p.B, p.H, p.W, p.C, p.N, p.taps = b, h, w, c, N, taps
-    p.dtype = _enum(x.dtype)
-    p.out_dtype = L.PG_F32_RAW if raw_out else _enum(x.dtype)
+    p.dtype = xf
+    p.w_fmt = _other(xf, _ACT_FMT)
+    p.out_dtype = L.PG_F32_RAW if raw_out else xf
     p.scale, p.slope, p.mask_slope = float(scale), float(slope), float(mask_slope)
     ws = None
-    if x.dtype == torch.float32:          # fp32 mode = 3xTF32: the library splits operands into these
+    if xf == L.PG_F32:          # fp32 mode = 3xTF32: the library splits operands into these
         ws = (torch.empty(3 * x.numel(), dtype=torch.float32, device=x.device),
               torch.empty(3 * wp.numel(), dtype=torch.float32, device=x.device))
         p.ws_x, p.ws_w = ws[0].data_ptr(), ws[1].data_ptr()
@@ -287,21 +448,21 @@ def dgrad_mask_fusable(batch, h, w, fwd_in_channels, fwd_out_channels, taps=9, d
     """True if the dgrad of a (fwd_in_channels -> fwd_out_channels) conv at this size runs on a kernel whose epilogue
     applies a LeakyReLU-backward mask for free (see pggan_conv_kernel_kind); the blocks use it to decide whether a
     producer may defer its mask to this layer's dgrad."""
-    dtype = dtype or _COMPUTE_DTYPE
-    key = (batch, h, w, fwd_in_channels, fwd_out_channels, taps, dtype)
+    key = (batch, h, w, fwd_in_channels, fwd_out_channels, taps, _GRAD_FMT)
     hit = _KIND_CACHE.get(key)
     if hit is None:
         p = L.ConvParams()
         p.B, p.H, p.W, p.C, p.N, p.taps = batch, h, w, fwd_out_channels, fwd_in_channels, taps     # dgrad: roles swapped
-        p.dtype = _enum(dtype)
-        p.out_dtype = _enum(dtype)
+        p.dtype = _GRAD_FMT
+        p.out_dtype = _GRAD_FMT
         hit = L.load().pggan_conv_kernel_kind(ctypes.byref(p)) in (L.PG_CONV_KIND_PLAIN, L.PG_CONV_KIND_ROWS)
         _KIND_CACHE[key] = hit
     return hit
 
 
-def k_wgrad(g, x, scale, wshape, layout=None, accumulate_into=None):
-    """weight gradient in the parameter's own fp32 layout: a new tensor, or added into `accumulate_into`"""
+def k_wgrad(g, x, scale, wshape, layout=None, accumulate_into=None, xc=A):
+    """weight gradient in the parameter's own fp32 layout: a new tensor, or added into `accumulate_into`.
+    g is a gradient-class tensor, x of class `xc`."""
     _need_cuda(g)
     b, n, h, w = _dims(g)
     c = _dims(x)[1]
@@ -311,12 +472,13 @@ def k_wgrad(g, x, scale, wshape, layout=None, accumulate_into=None):
     p = L.WgradParams()
     p.g, p.x = g.data_ptr(), x.data_ptr()
     p.B, p.H, p.W, p.C, p.N, p.taps = b, h, w, c, n, taps
-    p.dtype = _enum(g.dtype)
+    p.dtype = _GRAD_FMT
+    p.x_fmt = _other(_GRAD_FMT, _fmt(xc))
     slices = L.load().pggan_conv_wgrad_slices(ctypes.byref(p))
     acc = torch.empty((slices, n, taps, c), dtype=torch.float32, device=g.device)
     p.acc = acc.data_ptr()
     ws = None
-    if g.dtype == torch.float32:
+    if _GRAD_FMT == L.PG_F32:
         ws = (torch.empty(3 * g.numel(), dtype=torch.float32, device=g.device),
               torch.empty(3 * x.numel(), dtype=torch.float32, device=g.device))
         p.ws_g, p.ws_x = ws[0].data_ptr(), ws[1].data_ptr()
@@ -334,15 +496,19 @@ def k_wgrad(g, x, scale, wshape, layout=None, accumulate_into=None):
     return out
 
 
-def k_mask_colsum(g, y, slope, want_out, colsum_scale, colsum_into=None):
+def _vn(fmt: int) -> int:
+    return 4 if fmt == L.PG_F32 else 8
+
+
+def k_mask_colsum(g, y, slope, want_out, colsum_scale, colsum_into=None, cls=G):
     """fused LeakyReLU backward (+ bias gradient): returns (g*mask(y) or None, colsum or None).
     colsum_into: an fp32 [C] tensor the column sums are ADDED to (then the second result is None)."""
     b, c, h, w = _dims(g)
-    vn = 16 // g.element_size()
+    vn = _vn(_fmt(cls))
     if c % vn != 0 or (c // vn) > 256 or 256 % (c // vn) != 0:          # odd widths: two plain passes
-        out = k_mask_mul(g, y, slope) if (want_out and y is not None) else (g if want_out else None)
-        src = out if out is not None else (k_mask_mul(g, y, slope) if y is not None else g)
-        cs = k_colsum(src, colsum_scale) if colsum_scale is not None else None
+        out = k_mask_mul(g, y, slope, cls) if (want_out and y is not None) else (g if want_out else None)
+        src = out if out is not None else (k_mask_mul(g, y, slope, cls) if y is not None else g)
+        cs = k_colsum(src, colsum_scale, cls) if colsum_scale is not None else None
         if cs is not None and colsum_into is not None:
             colsum_into.add_(cs)
             cs = None
@@ -354,53 +520,57 @@ def k_mask_colsum(g, y, slope, want_out, colsum_scale, colsum_into=None):
     if out is None and cs is None:
         return (g if want_out else None), None
     L.check(L.load().pggan_mask_colsum(_p(g), _p(y), _p(out), _p(cs), b * h * w, c, float(slope),
-                                       float(colsum_scale or 0.0), _enum(g.dtype), _s()), "pggan_mask_colsum")
+                                       float(colsum_scale or 0.0), _fmt(cls), _s()), "pggan_mask_colsum")
     if want_out and out is None:
         out = g
     return out, (None if colsum_into is not None else cs)
 
 
-def k_mask_mul(g, y, slope):
+def k_mask_mul(g, y, slope, cls=G):
     out = torch.empty_like(g)
-    L.check(L.load().pggan_lrelu_mask_mul(_p(g), _p(y), _p(out), g.numel(), float(slope), _enum(g.dtype), _s()),
+    L.check(L.load().pggan_lrelu_mask_mul(_p(g), _p(y), _p(out), g.numel(), float(slope), _fmt(cls), _s()),
             "pggan_lrelu_mask_mul")
     return out
 
 
-def k_colsum(g, scale):
+def k_colsum(g, scale, cls=G):
     b, c, h, w = _dims(g)
-    if c % (16 // g.element_size()) != 0:      # e.g. the 1-logit decision layer: a [B,1] column
-        g2 = g.float().reshape(b, c) if g.dim() == 2 else g.float().permute(0, 2, 3, 1).reshape(-1, c)
+    if c % _vn(_fmt(cls)) != 0:      # e.g. the 1-logit decision layer: a [B,1] column
+        gf = to_float(g, cls)
+        g2 = gf.reshape(b, c) if g.dim() == 2 else gf.permute(0, 2, 3, 1).reshape(-1, c)
         return g2.sum(0) * scale
     out = torch.zeros((c,), dtype=torch.float32, device=g.device)
-    L.check(L.load().pggan_colsum(_p(g), _p(out), b * h * w, c, float(scale), _enum(g.dtype), _s()), "pggan_colsum")
+    L.check(L.load().pggan_colsum(_p(g), _p(out), b * h * w, c, float(scale), _fmt(cls), _s()), "pggan_colsum")
     return out
 
 
-def k_upsample(x, scale, mask_src=None, slope=1.0):
+def k_upsample(x, scale, mask_src=None, slope=1.0, cls=A):
+    """scale: a float or an _affine() coefficient"""
     b, c, h, w = _dims(x)
     out = _new_like_layout(x, c, x.dtype, 2 * h, 2 * w)
     if mask_src is not None:
-        L.check(L.load().pggan_upsample2x_mask(_p(x), _p(mask_src), _p(out), b, h, w, c, float(scale), float(slope),
-                                               _enum(x.dtype), _s()), "pggan_upsample2x_mask")
+        L.check(L.load().pggan_upsample2x_mask(_p(x), _p(mask_src), _p(out), b, h, w, c, _coef(scale), float(slope),
+                                               _fmt(cls), _s()), "pggan_upsample2x_mask")
         return out
-    L.check(L.load().pggan_upsample2x(_p(x), _p(out), b, h, w, c, float(scale), _enum(x.dtype), _s()),
+    L.check(L.load().pggan_upsample2x(_p(x), _p(out), b, h, w, c, _coef(scale), _fmt(cls), _s()),
             "pggan_upsample2x")
     return out
 
 
-def k_pool(x, scale, blend_with=None, alpha=1.0):
+def k_pool(x, scale, blend_with=None, alpha=1.0, cls=A):
+    """scale: a float or an _affine() coefficient; alpha: a float or an AlphaRef"""
     b, c, h, w = _dims(x)
     out = _new_like_layout(x, c, x.dtype, h // 2, w // 2)
-    L.check(L.load().pggan_pool2x2(_p(x), _p(blend_with), _p(out), b, h, w, c, float(scale), float(alpha),
-                                   _enum(x.dtype), _s()), "pggan_pool2x2")
+    L.check(L.load().pggan_pool2x2(_p(x), _p(blend_with), _p(out), b, h, w, c, _coef(scale), _coef(0.0, 1.0, alpha),
+                                   _fmt(cls), _s()), "pggan_pool2x2")
     return out
 
 
-def k_axpby(a, b, sa, sb):
+def k_axpby(a, b, sa, sb, cls=A):
+    """sa / sb: floats or _affine() coefficients; fp32 tensors run as fp32 whatever the class"""
     out = torch.empty_like(a)
-    L.check(L.load().pggan_axpby(_p(a), _p(b), _p(out), a.numel(), float(sa), float(sb), _enum(a.dtype), _s()),
-            "pggan_axpby")
+    fmt = L.PG_F32 if a.dtype == torch.float32 else _fmt(cls)
+    L.check(L.load().pggan_axpby(_p(a), _p(b), _p(out), a.numel(), _coef(sa), _coef(sb), fmt, _s()), "pggan_axpby")
     return out
 
 
@@ -421,25 +591,29 @@ class ConvF(torch.autograd.Function):
       x_act_slope : x is the LeakyReLU output of a producer that was run with defer_mask=True; this layer's dgrad
                     epilogue then applies that producer's mask to gx (no separate leaky_relu_backward pass).
       defer_mask  : the consumer of y applies THIS layer's mask (a ConvF with x_act_slope, or a pooling Function
-                    with act_slope): the incoming gradient is already masked and y need not be saved."""
+                    with act_slope): the incoming gradient is already masked and y need not be saved.
+      xc          : tensor class of x (and of y): "a" in a forward pass, "g" when the double backward runs an fprop
+                    on a gradient-like tensor (ConvT.backward)."""
 
     @staticmethod
-    def forward(ctx, x, W, b, scale, slope, raw_out, layout=None, x_act_slope=None, defer_mask=False):
-        x = feat(x)
+    def forward(ctx, x, W, b, scale, slope, raw_out, layout=None, x_act_slope=None, defer_mask=False, xc=A):
+        x = feat(x, xc)
         N, C, taps, _, _ = _maps(W.shape, layout)
         bias = None if b is None else _perm_bias(b.detach().float(), layout).contiguous()
-        y = k_conv(x, _pack(W, "f", x.dtype, layout), bias, N, taps, scale, slope, raw_out=raw_out)
+        y = k_conv(x, _pack(W, "f", None, layout), bias, N, taps, scale, slope, raw_out=raw_out, xc=xc)
         ctx.mask_here = slope != 1.0 and not defer_mask
         ctx.save_for_backward(x, W, y if ctx.mask_here else None)
         ctx.scale, ctx.slope, ctx.has_bias, ctx.layout = scale, slope, b is not None, layout
         ctx.x_act_slope = x_act_slope
+        ctx.xc = xc
+        ctx.w_param = W if isinstance(W, torch.nn.Parameter) else None
         ctx.bias_param = b if isinstance(b, torch.nn.Parameter) else None
         return y
 
     @staticmethod
     def backward(ctx, gy):
         x, W, y = ctx.saved_tensors
-        g = feat(gy)
+        g = feat(gy, G)
         need_w = ctx.needs_input_grad[1] and not _SKIP_PARAM_GRADS
         need_b = ctx.has_bias and ctx.needs_input_grad[2] and not _SKIP_PARAM_GRADS
         gx = gW = gb = None
@@ -456,20 +630,25 @@ class ConvF(torch.autograd.Function):
             b_sink = _sink(ctx.bias_param) if (need_b and not (ctx.layout and ctx.layout[0] == "lin_out_perm")) else None
             g, gb = k_mask_colsum(g, y if ctx.mask_here else None, ctx.slope, True,
                                   ctx.scale if need_b else None, colsum_into=b_sink)
+            if b_sink is not None:
+                _sunk(ctx.bias_param)
             if gb is not None:
                 gb = _perm_bias(gb, ctx.layout, inverse=True)
             if ctx.needs_input_grad[0]:
                 gx = ConvT.apply(g, W, ctx.scale, ctx.layout, xm, xs)
             if need_w:
-                gW = k_wgrad(g, x, ctx.scale, tuple(W.shape), ctx.layout, accumulate_into=_sink(W))
-            return gx, gW, gb, None, None, None, None, None, None
+                w_sink = _sink(ctx.w_param)
+                gW = k_wgrad(g, x, ctx.scale, tuple(W.shape), ctx.layout, accumulate_into=w_sink, xc=ctx.xc)
+                if w_sink is not None:
+                    _sunk(ctx.w_param)
+            return gx, gW, gb, None, None, None, None, None, None, None
         if gb is not None:
             gb = _perm_bias(gb, ctx.layout, inverse=True)
         if ctx.needs_input_grad[0]:
             gx = ConvT.apply(g, W, ctx.scale, ctx.layout, xm, xs)
         if need_w:
-            gW = ConvW.apply(g, x, ctx.scale, tuple(W.shape), ctx.layout)
-        return gx, gW, gb, None, None, None, None, None, None
+            gW = ConvW.apply(g, x, ctx.scale, tuple(W.shape), ctx.layout, ctx.xc)
+        return gx, gW, gb, None, None, None, None, None, None, None
 
 
 class ConvActPN(torch.autograd.Function):
@@ -480,21 +659,22 @@ class ConvActPN(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, W, b, scale, slope, eps, layout=None):
-        x = feat(x)
+        x = feat(x, A)
         N, C, taps, _, _ = _maps(W.shape, layout)
         bias = None if b is None else _perm_bias(b.detach().float(), layout).contiguous()
         if x.dim() == 4 and conv_pn_fusable(x, N, taps):
             # conv + He scale + bias + LeakyReLU + pixel norm in ONE kernel (the epilogue thread owns the whole pixel)
-            y, r = k_conv(x, _pack(W, "f", x.dtype, layout), bias, N, taps, scale, slope, pn_eps=eps)
+            y, r = k_conv(x, _pack(W, "f", None, layout), bias, N, taps, scale, slope, pn_eps=eps)
         else:
-            a = k_conv(x, _pack(W, "f", x.dtype, layout), bias, N, taps, scale, slope)
+            a = k_conv(x, _pack(W, "f", None, layout), bias, N, taps, scale, slope)
             bb, c, h, w = _dims(a)
             y = torch.empty_like(a)
             r = torch.empty((bb * h * w,), dtype=torch.float32, device=a.device)
-            L.check(L.load().pggan_pixelnorm_fwd(_p(a), _p(y), _p(r), bb * h * w, c, float(eps), _enum(a.dtype), _s()),
+            L.check(L.load().pggan_pixelnorm_fwd(_p(a), _p(y), _p(r), bb * h * w, c, float(eps), _ACT_FMT, _s()),
                     "pggan_pixelnorm_fwd")
         ctx.save_for_backward(x, W, y, r)
         ctx.scale, ctx.slope, ctx.has_bias, ctx.layout = scale, slope, b is not None, layout
+        ctx.w_param = W if isinstance(W, torch.nn.Parameter) else None
         ctx.bias_param = b if isinstance(b, torch.nn.Parameter) else None
         return y
 
@@ -502,22 +682,27 @@ class ConvActPN(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, gy):
         x, W, y, r = ctx.saved_tensors
-        gy = feat(gy)
+        gy = feat(gy, G)
         bb, c, h, w = _dims(y)
         need_b = ctx.has_bias and ctx.needs_input_grad[2] and not _SKIP_PARAM_GRADS
-        g = torch.empty_like(y)
+        g = torch.empty_like(gy)
         b_sink = _sink(ctx.bias_param) if (need_b and not (ctx.layout and ctx.layout[0] == "lin_out_perm")) else None
         gb = None
         if need_b:
             gb = b_sink if b_sink is not None else torch.zeros((c,), dtype=torch.float32, device=y.device)
         L.check(L.load().pggan_pixelnorm_bwd(_p(gy), _p(y), _p(r), _p(g), bb * h * w, c, float(ctx.slope), _p(gb),
-                                             float(ctx.scale), _enum(y.dtype), _s()), "pggan_pixelnorm_bwd")
+                                             float(ctx.scale), _GRAD_FMT, _ACT_FMT, _s()), "pggan_pixelnorm_bwd")
+        if b_sink is not None:
+            _sunk(ctx.bias_param)
         gx = gW = None
         if ctx.needs_input_grad[0]:
             N, C, taps, _, _ = _maps(W.shape, ctx.layout)
-            gx = k_conv(g, _pack(W, "t", g.dtype, ctx.layout), None, C, taps, ctx.scale)
+            gx = k_conv(g, _pack(W, "t", None, ctx.layout), None, C, taps, ctx.scale, xc=G)
         if ctx.needs_input_grad[1] and not _SKIP_PARAM_GRADS:
-            gW = k_wgrad(g, x, ctx.scale, tuple(W.shape), ctx.layout, accumulate_into=_sink(W))
+            w_sink = _sink(ctx.w_param)
+            gW = k_wgrad(g, x, ctx.scale, tuple(W.shape), ctx.layout, accumulate_into=w_sink, xc=A)
+            if w_sink is not None:
+                _sunk(ctx.w_param)
         if b_sink is not None:
             gb = None
         elif gb is not None:
@@ -532,9 +717,10 @@ class ConvT(torch.autograd.Function):
     def forward(ctx, g, W, scale, layout=None, mask_src=None, mask_slope=1.0):
         """mask_src: gx is additionally multiplied by (mask_src > 0 ? 1 : mask_slope) in the GEMM epilogue
         (the LeakyReLU backward of the layer that produced this conv's input)."""
-        g = feat(g)
+        g = feat(g, G)
         N, C, taps, _, _ = _maps(W.shape, layout)
-        gx = k_conv(g, _pack(W, "t", g.dtype, layout), None, C, taps, scale, mask_src=mask_src, mask_slope=mask_slope)
+        gx = k_conv(g, _pack(W, "t", None, layout), None, C, taps, scale, mask_src=mask_src, mask_slope=mask_slope,
+                    xc=G)
         ctx.save_for_backward(g, W, mask_src)
         ctx.scale, ctx.layout, ctx.mask_slope = scale, layout, mask_slope
         return gx
@@ -542,26 +728,26 @@ class ConvT(torch.autograd.Function):
     @staticmethod
     def backward(ctx, ggx):
         g, W, mask_src = ctx.saved_tensors
-        ggx = feat(ggx)
+        ggx = feat(ggx, G)
         if mask_src is not None:
             ggx = MaskMul.apply(ggx, mask_src, ctx.mask_slope)
         dg = dW = None
         if ctx.needs_input_grad[0]:
-            dg = ConvF.apply(ggx, W, None, ctx.scale, 1.0, False, ctx.layout)
+            dg = ConvF.apply(ggx, W, None, ctx.scale, 1.0, False, ctx.layout, None, False, G)
         if ctx.needs_input_grad[1] and not _SKIP_PARAM_GRADS:
-            dW = ConvW.apply(g, ggx, ctx.scale, tuple(W.shape), ctx.layout)
+            dW = ConvW.apply(g, ggx, ctx.scale, tuple(W.shape), ctx.layout, G)
         return dg, dW, None, None, None, None
 
 
 class ConvW(torch.autograd.Function):
-    """gW = scale * wgrad(g, x)   in the parameter's layout"""
+    """gW = scale * wgrad(g, x)   in the parameter's layout; g gradient-class, x of class xc"""
 
     @staticmethod
-    def forward(ctx, g, x, scale, wshape, layout=None):
-        g, x = feat(g), feat(x)
+    def forward(ctx, g, x, scale, wshape, layout=None, xc=A):
+        g, x = feat(g, G), feat(x, xc)
         ctx.save_for_backward(g, x)
-        ctx.scale, ctx.layout = scale, layout
-        return k_wgrad(g, x, scale, wshape, layout)
+        ctx.scale, ctx.layout, ctx.xc = scale, layout, xc
+        return k_wgrad(g, x, scale, wshape, layout, xc=xc)
 
     @staticmethod
     def backward(ctx, ggW):
@@ -569,10 +755,13 @@ class ConvW(torch.autograd.Function):
         dg = dx = None
         ggW = ggW.contiguous()
         if ctx.needs_input_grad[0]:
-            dg = ConvF.apply(x, ggW, None, ctx.scale, 1.0, False, ctx.layout)
+            dg = ConvF.apply(x, ggW, None, ctx.scale, 1.0, False, ctx.layout, None, False, ctx.xc)
+            if ctx.xc != G:
+                # conv(x, ggW) came out in x's class; it is the gradient of g
+                dg = feat(to_float(dg, ctx.xc), G)
         if ctx.needs_input_grad[1]:
             dx = ConvT.apply(g, ggW, ctx.scale, ctx.layout)
-        return dg, dx, None, None, None
+        return dg, dx, None, None, None, None
 
 
 class ColSum(torch.autograd.Function):
@@ -580,9 +769,9 @@ class ColSum(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, g, scale):
-        g = feat(g)
+        g = feat(g, G)
         ctx.shape, ctx.scale, ctx.dtype = tuple(g.shape), scale, g.dtype
-        return k_colsum(g, scale)
+        return k_colsum(g, scale, G)
 
     @staticmethod
     def backward(ctx, ggb):
@@ -596,29 +785,29 @@ class MaskMul(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, g, y, slope):
-        g = feat(g)
+        g = feat(g, G)
         ctx.save_for_backward(y)
         ctx.slope = slope
-        return k_mask_mul(g, y, slope)
+        return k_mask_mul(g, y, slope, G)
 
     @staticmethod
     def backward(ctx, gg):
         (y,) = ctx.saved_tensors
-        return MaskMul.apply(feat(gg), y, ctx.slope), None, None
+        return MaskMul.apply(feat(gg, G), y, ctx.slope), None, None
 
 
 # ------------------------------------------------------------------ resampling / blend Functions
 class Upsample2x(torch.autograd.Function):
-    """nearest 2x (reference lib/utils.py:106-118), times `scale`"""
+    """nearest 2x (reference lib/utils.py:106-118), times `scale` (a float or an _affine() coefficient)"""
 
     @staticmethod
-    def forward(ctx, x, scale):
+    def forward(ctx, x, scale, cls=A):
         ctx.scale = scale
-        return k_upsample(feat(x), scale)
+        return k_upsample(feat(x, cls), scale, cls=cls)
 
     @staticmethod
     def backward(ctx, g):
-        return Pool2x2.apply(feat(g), ctx.scale), None
+        return Pool2x2.apply(feat(g, G), ctx.scale, None, G), None, None
 
 
 class UpsampleMask(torch.autograd.Function):
@@ -629,100 +818,99 @@ class UpsampleMask(torch.autograd.Function):
     def forward(ctx, g, y, scale, slope):
         ctx.save_for_backward(y)
         ctx.scale, ctx.slope = scale, slope
-        return k_upsample(feat(g), scale, mask_src=y, slope=slope)
+        return k_upsample(feat(g, G), scale, mask_src=y, slope=slope, cls=G)
 
     @staticmethod
     def backward(ctx, gg):
         (y,) = ctx.saved_tensors
-        return Pool2x2.apply(MaskMul.apply(feat(gg), y, ctx.slope), ctx.scale), None, None, None
+        return Pool2x2.apply(MaskMul.apply(feat(gg, G), y, ctx.slope), ctx.scale, None, G), None, None, None
 
 
 class Pool2x2(torch.autograd.Function):
-    """scale * (2x2 window sum); scale = 0.25 is nn.AvgPool2d(2) (reference lib/blocks.py:193).
-    act_slope: x is the LeakyReLU output of a ConvF run with defer_mask=True — its mask is applied here, in backward."""
+    """scale * (2x2 window sum); scale = 0.25 is nn.AvgPool2d(2) (reference lib/blocks.py:193); scale may be an
+    _affine() coefficient.  act_slope: x is the LeakyReLU output of a ConvF run with defer_mask=True — its mask is
+    applied here, in backward."""
 
     @staticmethod
-    def forward(ctx, x, scale, act_slope=None):
-        x = feat(x)
+    def forward(ctx, x, scale, act_slope=None, cls=A):
+        x = feat(x, cls)
         ctx.scale, ctx.act_slope = scale, act_slope
         if act_slope is not None:
             ctx.save_for_backward(x)
-        return k_pool(x, scale)
+        return k_pool(x, scale, cls=cls)
 
     @staticmethod
     def backward(ctx, g):
         if ctx.act_slope is not None:
             (x,) = ctx.saved_tensors
-            return UpsampleMask.apply(feat(g), x, ctx.scale, ctx.act_slope), None, None
-        return Upsample2x.apply(feat(g), ctx.scale), None, None
+            return UpsampleMask.apply(feat(g, G), x, ctx.scale, ctx.act_slope), None, None, None
+        return Upsample2x.apply(feat(g, G), ctx.scale, G), None, None, None
 
 
 class PoolBlend(torch.autograd.Function):
     """(1-alpha) * low + alpha * avgpool2(x): D's feature-space fade fused with the pooling
-    (reference lib/blocks.py:193 + pggan/nets.py:262-265).  act_slope as in Pool2x2."""
+    (reference lib/blocks.py:193 + pggan/nets.py:262-265).  act_slope as in Pool2x2; alpha a float or an AlphaRef."""
 
     @staticmethod
     def forward(ctx, x, low, alpha, act_slope=None):
-        x = feat(x)
+        x = feat(x, A)
         ctx.alpha, ctx.act_slope = alpha, act_slope
         if act_slope is not None:
             ctx.save_for_backward(x)
-        return k_pool(x, 0.25, blend_with=feat(low), alpha=alpha)
+        return k_pool(x, 0.25, blend_with=feat(low, A), alpha=alpha)
 
     @staticmethod
     def backward(ctx, g):
-        g = feat(g)
+        g = feat(g, G)
         gx = None
         if ctx.needs_input_grad[0]:
             if ctx.act_slope is not None:
                 (x,) = ctx.saved_tensors
-                gx = UpsampleMask.apply(g, x, 0.25 * ctx.alpha, ctx.act_slope)
+                gx = UpsampleMask.apply(g, x, _affine(0.0, 0.25, ctx.alpha), ctx.act_slope)
             else:
-                gx = Upsample2x.apply(g, 0.25 * ctx.alpha)
-        gl = Scale.apply(g, 1.0 - ctx.alpha) if ctx.needs_input_grad[1] else None
+                gx = Upsample2x.apply(g, _affine(0.0, 0.25, ctx.alpha), G)
+        gl = Scale.apply(g, _affine(1.0, -1.0, ctx.alpha), G) if ctx.needs_input_grad[1] else None
         return gx, gl, None, None
 
 
 class Scale(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, s):
-        ctx.s = s
-        return k_axpby(feat(x), None, s, 0.0)
+    def forward(ctx, x, s, cls=A):
+        ctx.s, ctx.cls = s, cls
+        return k_axpby(feat(x, cls), None, s, 0.0, cls)
 
     @staticmethod
     def backward(ctx, g):
-        return Scale.apply(feat(g), ctx.s), None
+        return Scale.apply(feat(g, G), ctx.s, G), None, None
 
 
 class Lerp(torch.autograd.Function):
     """(1-alpha) * a + alpha * b on feature maps"""
 
     @staticmethod
-    def forward(ctx, a, b, alpha):
+    def forward(ctx, a, b, alpha, cls=A):
         ctx.alpha = alpha
-        return k_axpby(feat(a), feat(b), 1.0 - alpha, alpha)
+        return k_axpby(feat(a, cls), feat(b, cls), _affine(1.0, -1.0, alpha), _affine(0.0, 1.0, alpha), cls)
 
     @staticmethod
     def backward(ctx, g):
-        g = feat(g)
-        ga = Scale.apply(g, 1.0 - ctx.alpha) if ctx.needs_input_grad[0] else None
-        gb = Scale.apply(g, ctx.alpha) if ctx.needs_input_grad[1] else None
-        return ga, gb, None
+        g = feat(g, G)
+        ga = Scale.apply(g, _affine(1.0, -1.0, ctx.alpha), G) if ctx.needs_input_grad[0] else None
+        gb = Scale.apply(g, _affine(0.0, 1.0, ctx.alpha), G) if ctx.needs_input_grad[1] else None
+        return ga, gb, None, None
 
 
 # ---------------------------------------------------------------------------------- pixel norm
 class PixelNorm(torch.autograd.Function):
-    """x * rsqrt(mean_c(x^2) + eps)  (reference lib/layers.py:13-14).  `act_slope` != 1 declares that
-    x is a LeakyReLU output whose mask should be folded into THIS backward (the producing ConvF was
-    then run with its own mask disabled) — sign(y) == sign(x) == sign(pre-activation)."""
+    """x * rsqrt(mean_c(x^2) + eps)  (reference lib/layers.py:13-14)."""
 
     @staticmethod
     def forward(ctx, x, eps):
-        x = feat(x)
+        x = feat(x, A)
         b, c, h, w = _dims(x)
         y = torch.empty_like(x)
         r = torch.empty((b * h * w,), dtype=torch.float32, device=x.device)
-        L.check(L.load().pggan_pixelnorm_fwd(_p(x), _p(y), _p(r), b * h * w, c, float(eps), _enum(x.dtype), _s()),
+        L.check(L.load().pggan_pixelnorm_fwd(_p(x), _p(y), _p(r), b * h * w, c, float(eps), _ACT_FMT, _s()),
                 "pggan_pixelnorm_fwd")
         ctx.save_for_backward(y, r)
         return y
@@ -731,40 +919,40 @@ class PixelNorm(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, gy):
         y, r = ctx.saved_tensors
-        gy = feat(gy)
+        gy = feat(gy, G)
         b, c, h, w = _dims(y)
-        gx = torch.empty_like(y)
+        gx = torch.empty_like(gy)
         L.check(L.load().pggan_pixelnorm_bwd(_p(gy), _p(y), _p(r), _p(gx), b * h * w, c, 1.0, None, 0.0,
-                                             _enum(y.dtype), _s()), "pggan_pixelnorm_bwd")
+                                             _GRAD_FMT, _ACT_FMT, _s()), "pggan_pixelnorm_bwd")
         return gx, None
 
 
 # ------------------------------------------------------------------------------------ RGB 1x1
-def _k_rgb_expand(img, wc, bias, C, pool, scale, slope, dtype):
+def _k_rgb_expand(img, wc, bias, C, pool, scale, slope, cls):
     b, cimg, hi, wi = img.shape
     h, w = (hi // 2, wi // 2) if pool else (hi, wi)
-    out = torch.empty((b, C, h, w), dtype=dtype, device=img.device, memory_format=torch.channels_last)
+    out = torch.empty((b, C, h, w), dtype=_COMPUTE_DTYPE, device=img.device, memory_format=torch.channels_last)
     L.check(L.load().pggan_rgb_expand(_p(img), _p(wc), _p(bias), _p(out), b, h, w, C, cimg, int(pool), float(scale),
-                                      float(slope), _enum(dtype), _s()), "pggan_rgb_expand")
+                                      float(slope), _fmt(cls), _s()), "pggan_rgb_expand")
     return out
 
 
-def _k_rgb_reduce(x, wr, bias, cimg, up, scale, up_scale):
+def _k_rgb_reduce(x, wr, bias, cimg, up, scale, up_scale, cls):
     b, c, h, w = _dims(x)
     ho, wo = (2 * h, 2 * w) if up else (h, w)
     out = torch.empty((b, cimg, ho, wo), dtype=torch.float32, device=x.device)
     L.check(L.load().pggan_rgb_reduce(_p(x), _p(wr), _p(bias), _p(out), b, h, w, c, cimg, int(up), float(scale),
-                                      float(up_scale), _enum(x.dtype), _s()), "pggan_rgb_reduce")
+                                      float(up_scale), _fmt(cls), _s()), "pggan_rgb_reduce")
     return out
 
 
-def _k_rgb_wgrad(f, img, pool, scale, want_bias=False):
+def _k_rgb_wgrad(f, img, pool, scale, cls, want_bias=False):
     b, c, h, w = _dims(f)
     cimg = img.shape[1]
     acc = torch.zeros((c, cimg), dtype=torch.float32, device=f.device)
     bs = torch.zeros((c,), dtype=torch.float32, device=f.device) if want_bias else None
     L.check(L.load().pggan_rgb_wgrad(_p(f), _p(img), _p(acc), _p(bs), b, h, w, c, cimg, int(pool), float(scale),
-                                     _enum(f.dtype), _s()), "pggan_rgb_wgrad")
+                                     _fmt(cls), _s()), "pggan_rgb_wgrad")
     return (acc, bs) if want_bias else acc
 
 
@@ -774,16 +962,17 @@ def _img(t):
 
 class RgbExpand(torch.autograd.Function):
     """NHWC[b,h,w,c] = lrelu(scale*(sum_j Wc[c,j]*p_j + bias[c]), slope); p = image pixel or its 2x2 mean.
-    Wc is [C, cimg] fp32.  (fromRGBBlock, reference lib/blocks.py:285-292)"""
+    Wc is [C, cimg] fp32.  (fromRGBBlock, reference lib/blocks.py:285-292)
+    out_cls: class of the produced feature map ("g" when this is the dgrad of a toRGB layer)."""
 
     @staticmethod
-    def forward(ctx, img, Wc, bias, pool, scale, slope, defer_mask=False):
+    def forward(ctx, img, Wc, bias, pool, scale, slope, defer_mask=False, out_cls=A):
         """defer_mask: the consumer (a ConvF with x_act_slope) applies this layer's LeakyReLU mask in its dgrad"""
         img = _img(img)
         _need_cuda(img)
         wc = Wc.detach().float().contiguous()
         bs = None if bias is None else bias.detach().float().contiguous()
-        y = _k_rgb_expand(img, wc, bs, wc.shape[0], pool, scale, slope, _COMPUTE_DTYPE)
+        y = _k_rgb_expand(img, wc, bs, wc.shape[0], pool, scale, slope, out_cls)
         ctx.mask_here = slope != 1.0 and not defer_mask
         ctx.save_for_backward(img, Wc, y if ctx.mask_here else None)
         ctx.pool, ctx.scale, ctx.slope, ctx.has_bias = pool, scale, slope, bias is not None
@@ -792,7 +981,7 @@ class RgbExpand(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         img, Wc, y = ctx.saved_tensors
-        g = feat(gy)
+        g = feat(gy, G)
         need_w = ctx.needs_input_grad[1] and not _SKIP_PARAM_GRADS
         need_b = ctx.has_bias and ctx.needs_input_grad[2] and not _SKIP_PARAM_GRADS
         gimg = gW = gb = None
@@ -800,38 +989,38 @@ class RgbExpand(torch.autograd.Function):
             if ctx.mask_here:
                 g = MaskMul.apply(g, y, ctx.slope)
             if ctx.needs_input_grad[0]:
-                gimg = RgbReduce.apply(g, Wc, None, ctx.pool, ctx.scale, 0.25)
+                gimg = RgbReduce.apply(g, Wc, None, ctx.pool, ctx.scale, 0.25, G)
             if need_w:
-                gW = RgbWgrad.apply(g, img, ctx.pool, ctx.scale)
+                gW = RgbWgrad.apply(g, img, ctx.pool, ctx.scale, G)
             if need_b:
                 gb = ColSum.apply(g, ctx.scale)
-            return gimg, gW, gb, None, None, None, None
+            return gimg, gW, gb, None, None, None, None, None
         if ctx.mask_here:
-            g = k_mask_mul(g, y, ctx.slope)
+            g = k_mask_mul(g, y, ctx.slope, G)
         if ctx.needs_input_grad[0]:
             wr = Wc.detach().float().t().contiguous()
-            gimg = _k_rgb_reduce(g, wr, None, wr.shape[0], ctx.pool, ctx.scale, 0.25)
+            gimg = _k_rgb_reduce(g, wr, None, wr.shape[0], ctx.pool, ctx.scale, 0.25, G)
         if need_w or need_b:                   # weight and bias gradients share one pass over g
-            gW, gb = _k_rgb_wgrad(g, img, ctx.pool, ctx.scale, want_bias=True)
+            gW, gb = _k_rgb_wgrad(g, img, ctx.pool, ctx.scale, G, want_bias=True)
             if not need_w:
                 gW = None
             if not need_b:
                 gb = None
-        return gimg, gW, gb, None, None, None, None
+        return gimg, gW, gb, None, None, None, None, None
 
 
 class RgbReduce(torch.autograd.Function):
     """img[b,j,h,w] = scale*(sum_c Wc[c,j]*x[b,h,w,c] + bias[j]); if up, written (times up_scale) to
-    the 2x2 block of a 2x larger image.  (toRGBBlock, reference lib/blocks.py:164-170)"""
+    the 2x2 block of a 2x larger image.  (toRGBBlock, reference lib/blocks.py:164-170); xc: class of x"""
 
     @staticmethod
-    def forward(ctx, x, Wc, bias, up, scale, up_scale):
-        x = feat(x)
+    def forward(ctx, x, Wc, bias, up, scale, up_scale, xc=A):
+        x = feat(x, xc)
         wr = Wc.detach().float().t().contiguous()          # [cimg, C]
         bs = None if bias is None else bias.detach().float().contiguous()
-        out = _k_rgb_reduce(x, wr, bs, wr.shape[0], up, scale, up_scale)
+        out = _k_rgb_reduce(x, wr, bs, wr.shape[0], up, scale, up_scale, xc)
         ctx.save_for_backward(x, Wc)
-        ctx.up, ctx.scale, ctx.up_scale, ctx.has_bias = up, scale, up_scale, bias is not None
+        ctx.up, ctx.scale, ctx.up_scale, ctx.has_bias, ctx.xc = up, scale, up_scale, bias is not None, xc
         return out
 
     @staticmethod
@@ -841,39 +1030,40 @@ class RgbReduce(torch.autograd.Function):
         s = ctx.scale * (4.0 * ctx.up_scale if ctx.up else 1.0)    # adjoint of "write 4 copies * up_scale"
         gx = gW = gb = None
         if ctx.needs_input_grad[0]:
-            gx = RgbExpand.apply(gout, Wc, None, ctx.up, s, 1.0)
+            gx = RgbExpand.apply(gout, Wc, None, ctx.up, s, 1.0, False, G)
         if not _SKIP_PARAM_GRADS:
             if ctx.needs_input_grad[1]:
-                gW = RgbWgrad.apply(x, gout, ctx.up, s)
+                gW = RgbWgrad.apply(x, gout, ctx.up, s, ctx.xc)
             if ctx.has_bias and ctx.needs_input_grad[2]:
                 gb = gout.sum(dim=(0, 2, 3)) * (ctx.scale * (ctx.up_scale if ctx.up else 1.0))
-        return gx, gW, gb, None, None, None
+        return gx, gW, gb, None, None, None, None
 
 
 class RgbWgrad(torch.autograd.Function):
-    """gWc[c,j] = scale * sum_pixels f[.,c] * p_j"""
+    """gWc[c,j] = scale * sum_pixels f[.,c] * p_j;  fc: class of f"""
 
     @staticmethod
-    def forward(ctx, f, img, pool, scale):
-        f, img = feat(f), _img(img)
+    def forward(ctx, f, img, pool, scale, fc=G):
+        f, img = feat(f, fc), _img(img)
         ctx.save_for_backward(f, img)
-        ctx.pool, ctx.scale = pool, scale
-        return _k_rgb_wgrad(f, img, pool, scale)
+        ctx.pool, ctx.scale, ctx.fc = pool, scale, fc
+        return _k_rgb_wgrad(f, img, pool, scale, fc)
 
     @staticmethod
     def backward(ctx, ggW):
         f, img = ctx.saved_tensors
         df = dimg = None
         if ctx.needs_input_grad[0]:
-            df = RgbExpand.apply(img, ggW, None, ctx.pool, ctx.scale, 1.0)
+            df = RgbExpand.apply(img, ggW, None, ctx.pool, ctx.scale, 1.0, False, G)
         if ctx.needs_input_grad[1]:
-            dimg = RgbReduce.apply(f, ggW, None, ctx.pool, ctx.scale, 0.25)
-        return df, dimg, None, None
+            dimg = RgbReduce.apply(f, ggW, None, ctx.pool, ctx.scale, 0.25, ctx.fc)
+        return df, dimg, None, None, None
 
 
 class ImageFade(torch.autograd.Function):
     """(1-alpha) * up2(low) + alpha * x on fp32 NCHW images; low=None -> low = avgpool2(x)
-    (G's RGB fade, reference pggan/nets.py:155-156; real-image fade, pggan/model.py:217-221)."""
+    (G's RGB fade, reference pggan/nets.py:155-156; real-image fade, pggan/model.py:217-221).
+    alpha: a float or an AlphaRef (device scalar: a captured graph follows the fade-in)."""
 
     @staticmethod
     def forward(ctx, x, low, alpha):
@@ -882,7 +1072,8 @@ class ImageFade(torch.autograd.Function):
         lo = None if low is None else _img(low)
         b, c, h, w = x.shape
         out = torch.empty_like(x)
-        L.check(L.load().pggan_image_fade(_p(x), _p(lo), _p(out), b, c, h, w, float(alpha), _s()), "pggan_image_fade")
+        L.check(L.load().pggan_image_fade(_p(x), _p(lo), _p(out), b, c, h, w, _coef(0.0, 1.0, alpha), _s()),
+                "pggan_image_fade")
         ctx.alpha, ctx.self_low = alpha, low is None
         return out
 
@@ -890,14 +1081,17 @@ class ImageFade(torch.autograd.Function):
     def backward(ctx, g):
         g = _img(g)
         b, c, h, w = g.shape
-        pooled = torch.empty((b, c, h // 2, w // 2), dtype=torch.float32, device=g.device)
-        L.check(L.load().pggan_image_pool_sum(_p(g), _p(pooled), b, c, h, w, 1.0 - ctx.alpha, _s()),
-                "pggan_image_pool_sum")
         if ctx.self_low:
-            # d/dx of (1-a)*up(pool(x)): up(pooled)/4
-            gx = ctx.alpha * g + pooled.repeat_interleave(2, 2).repeat_interleave(2, 3) * 0.25
-            return gx, None, None
-        return ctx.alpha * g, pooled, None
+            # F(x) = (1-a)*up(avgpool(x)) + a*x is self-adjoint (up o avgpool = 0.25 * up o up^T)
+            return ImageFade.apply(g, None, ctx.alpha), None, None
+        gx = glow = None
+        if ctx.needs_input_grad[0]:
+            gx = k_axpby(g, None, _affine(0.0, 1.0, ctx.alpha), 0.0)
+        if ctx.needs_input_grad[1]:
+            glow = torch.empty((b, c, h // 2, w // 2), dtype=torch.float32, device=g.device)
+            L.check(L.load().pggan_image_pool_sum(_p(g), _p(glow), b, c, h, w, _coef(1.0, -1.0, ctx.alpha), _s()),
+                    "pggan_image_pool_sum")
+        return gx, glow, None
 
 
 # -------------------------------------------------------------------------- minibatch stddev
@@ -906,11 +1100,11 @@ class MbstdStat(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, group):
-        x = feat(x)
+        x = feat(x, A)
         B = x.shape[0]
         K = x.numel() // B
         stat = torch.empty((B // group,), dtype=torch.float32, device=x.device)
-        L.check(L.load().pggan_mbstd_fwd(_p(x), _p(stat), B, K, group, _enum(x.dtype), _s()), "pggan_mbstd_fwd")
+        L.check(L.load().pggan_mbstd_fwd(_p(x), _p(stat), B, K, group, _ACT_FMT, _s()), "pggan_mbstd_fwd")
         ctx.save_for_backward(x)
         ctx.group = group
         return stat
@@ -927,7 +1121,8 @@ class MbstdBwd(torch.autograd.Function):
         B = x.shape[0]
         K = x.numel() // B
         gx = torch.empty_like(x)
-        L.check(L.load().pggan_mbstd_bwd(_p(x), _p(gs), _p(gx), B, K, group, _enum(x.dtype), _s()), "pggan_mbstd_bwd")
+        L.check(L.load().pggan_mbstd_bwd(_p(x), _p(gs), _p(gx), B, K, group, _ACT_FMT, _GRAD_FMT, _s()),
+                "pggan_mbstd_bwd")
         ctx.save_for_backward(x, gs)
         ctx.group = group
         return gx
@@ -936,14 +1131,32 @@ class MbstdBwd(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, u):
         x, gs = ctx.saved_tensors
-        u = feat(u)
+        u = feat(u, G)
+        if u.stride() != x.stride():
+            u = u.contiguous(memory_format=torch.channels_last) if x.dim() == 4 else u.contiguous()
         B = x.shape[0]
         K = x.numel() // B
         ggs = torch.empty_like(gs)
-        gx2 = torch.empty_like(x)
-        L.check(L.load().pggan_mbstd_bwd2(_p(x), _p(u), _p(gs), _p(ggs), _p(gx2), B, K, ctx.group, _enum(x.dtype),
+        gx2 = torch.empty_like(u)
+        L.check(L.load().pggan_mbstd_bwd2(_p(x), _p(u), _p(gs), _p(ggs), _p(gx2), B, K, ctx.group, _ACT_FMT, _GRAD_FMT,
                                           _s()), "pggan_mbstd_bwd2")
         return gx2, ggs, None
+
+
+class StatChannel(torch.autograd.Function):
+    """per-group statistic [B/G] fp32 -> the constant extra channel [B,1,H,W] of the activation class
+    (the expand/cat half of reference lib/blocks.py:226-231)"""
+
+    @staticmethod
+    def forward(ctx, stat, group, batch, h, w):
+        ctx.group = group
+        y = stat.repeat_interleave(group).view(batch, 1, 1, 1).expand(batch, 1, h, w)
+        return feat(y.contiguous(), A)
+
+    @staticmethod
+    def backward(ctx, g):
+        gs = to_float(g, G).sum(dim=(1, 2, 3)).view(-1, ctx.group).sum(dim=1)
+        return gs, None, None, None, None
 
 
 # ------------------------------------------------------------------------- loss reductions

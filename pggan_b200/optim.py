@@ -61,8 +61,12 @@ class FlatGrads:
 class FusedAdam:
     """drop-in for the two `torch.optim.Adam` objects of reference lib/model.py:95-97"""
 
-    def __init__(self, params, lr, betas=(0.0, 0.99), eps=1e-8, grad_scale=1.0):
+    def __init__(self, params, lr, betas=(0.0, 0.99), eps=1e-8, grad_scale=1.0, all_params=None):
+        """all_params: every parameter of the network in `module.parameters()` order (the order in which the
+        reference's torch.optim.Adam indexes them) — gives state_dict() / load_state_dict() the reference's indices;
+        parameters that are not registered here (stale RGB layers) simply have no state, as in torch."""
         self.grads = params if isinstance(params, FlatGrads) else FlatGrads(params)
+        self.all_params = list(all_params) if all_params is not None else list(self.grads.params)
         self.lr, self.betas, self.eps, self.grad_scale = float(lr), (float(betas[0]), float(betas[1])), float(eps), \
             float(grad_scale)
         g = self.grads
@@ -110,6 +114,53 @@ class FusedAdam:
                                          self.grad_scale, ops._s()), "pggan_adam_step")
         ops.clear_pack_cache(self.grads.params)     # packed bf16/tf32 copies of THESE weights are stale now
 
+    # ---- torch.optim.Adam wire format (reference lib/checkpoint.py:24-25, pggan/model.py:97-101) ----------------
     def state_dict(self):
-        return {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "step": self.step_count,
-                "lr": self.lr, "betas": self.betas, "eps": self.eps}
+        """the dict torch.optim.Adam(module.parameters(), ...).state_dict() would hold: per-parameter
+        {step, exp_avg, exp_avg_sq} keyed by the parameter's index in module.parameters(), plus one param_group"""
+        index = {id(p): i for i, p in enumerate(self.all_params)}
+        step = int(self.step_count.item())
+        state = {}
+        if step > 0:
+            for p, off in zip(self.grads.params, self.grads.offsets):
+                n = p.numel()
+                state[index[id(p)]] = {"step": torch.tensor(float(step)),
+                                       "exp_avg": self.exp_avg[off:off + n].view_as(p).clone(),
+                                       "exp_avg_sq": self.exp_avg_sq[off:off + n].view_as(p).clone()}
+        group = {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": 0, "amsgrad": False,
+                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "decoupled_weight_decay": False, "params": list(range(len(self.all_params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        """accepts the format above (written by this class or by torch.optim.Adam over the same module)"""
+        if "state" not in sd or "param_groups" not in sd:
+            raise ValueError("FusedAdam.load_state_dict: not a torch.optim.Adam state dict (no 'state'/'param_groups')")
+        group = sd["param_groups"][0]
+        if len(group["params"]) != len(self.all_params):
+            raise ValueError(f"FusedAdam.load_state_dict: the checkpoint's optimizer covers {len(group['params'])} "
+                             f"parameters, this network has {len(self.all_params)} (grow it to the checkpoint's "
+                             "scale_index first)")
+        self.lr = float(group["lr"])
+        self.betas = (float(group["betas"][0]), float(group["betas"][1]))
+        self.eps = float(group["eps"])
+        pos = {pid: i for i, pid in enumerate(group["params"])}        # saved id -> position in module.parameters()
+        by_pos = {pos[k]: v for k, v in sd["state"].items()}
+        index = {id(p): i for i, p in enumerate(self.all_params)}
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        steps = set()
+        for p, off in zip(self.grads.params, self.grads.offsets):
+            st = by_pos.get(index[id(p)])
+            if st is None:
+                continue
+            n = p.numel()
+            if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                raise ValueError("FusedAdam.load_state_dict: moment shape mismatch for a parameter of shape "
+                                 f"{tuple(p.shape)}")
+            self.exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1))
+            self.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+            steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise ValueError(f"FusedAdam.load_state_dict: parameters carry different step counts {sorted(steps)}")
+        self.step_count.fill_(steps.pop() if steps else 0)

@@ -18,7 +18,7 @@ from typing import Optional
 import torch
 import torch.distributed as dist
 
-from . import ops
+from . import checkpoint, ops
 from .dist import GradSync, broadcast_parameters
 from .loss import WGANGPLoss
 from .nets import Discriminator, Generator
@@ -94,8 +94,10 @@ class ProgressiveGAN:
             p.grad = None
         gG, gD = FlatGrads(self.G.live_parameters()), FlatGrads(self.D.live_parameters())
         scale = 1.0 / self.world
-        self.opt_G = FusedAdam(gG, lr=a.lr_G, betas=(float(a.beta1), float(a.beta2)), grad_scale=scale)
-        self.opt_D = FusedAdam(gD, lr=a.lr_D, betas=(float(a.beta1), float(a.beta2)), grad_scale=scale)
+        self.opt_G = FusedAdam(gG, lr=a.lr_G, betas=(float(a.beta1), float(a.beta2)), grad_scale=scale,
+                               all_params=self.G.parameters())
+        self.opt_D = FusedAdam(gD, lr=a.lr_D, betas=(float(a.beta1), float(a.beta2)), grad_scale=scale,
+                               all_params=self.D.parameters())
         self.sync_G = GradSync(gG, self.bucket_bytes) if self.data_parallel else None
         self.sync_D = GradSync(gD, self.bucket_bytes) if self.data_parallel else None
 
@@ -105,6 +107,50 @@ class ProgressiveGAN:
     @property
     def loss_collector(self):
         return self._loss_collector
+
+    # ------------------------------------------------------------------ checkpoints (model.py:50-101)
+    def save_checkpoint(self, global_step):
+        """reference pggan/model.py:50-67: {G,D}_{step}.pt and _latest.pt under {save_root}/{run_id}/ckpt"""
+        ckpt_dict = {
+            "args": dict(vars(self.args)),
+            "global_step": global_step,
+            "alpha_G": self.G.alpha,
+            "alpha_D": self.D.alpha,
+            "alpha_index": self.alpha_index,
+            "alpha_jump_value": self.alpha_jump_value,
+            "next_alpha_jump_step": self.next_alpha_jump_step,
+            "scale_index": self.scale_index,
+            "next_scale_jump_step": self.next_scale_jump_step,
+        }
+        checkpoint.save_checkpoint(self.G, self.opt_G, name="G", ckpt_dict=ckpt_dict)
+        checkpoint.save_checkpoint(self.D, self.opt_D, name="D", ckpt_dict=ckpt_dict)
+
+    def load_checkpoint(self):
+        """reference pggan/model.py:70-101: schedule variables, add_block replay, new optimizers, weights, moments.
+        Works for checkpoints written by this class and by the reference (torch.optim.Adam state)."""
+        G_ckpt_dict, D_ckpt_dict = checkpoint.load_checkpoint(self.args, name="G"), \
+            checkpoint.load_checkpoint(self.args, name="D")
+        for k, v in G_ckpt_dict["args"].items():
+            if k not in ("ckpt_id", "ckpt_step", "save_root", "run_id"):
+                setattr(self.args, k, v)
+        self.global_step = G_ckpt_dict["global_step"]
+        self.alpha_index = G_ckpt_dict["alpha_index"]
+        self.alpha_jump_value = G_ckpt_dict["alpha_jump_value"]
+        self.next_alpha_jump_step = G_ckpt_dict["next_alpha_jump_step"]
+        self.scale_index = G_ckpt_dict["scale_index"]
+        self.next_scale_jump_step = G_ckpt_dict["next_scale_jump_step"]
+        checkpoint.grow_to_checkpoint(self.G, self.D, self.args.depths, self.scale_index)
+        self.G.to(self.device)
+        self.D.to(self.device)
+        self.G.alpha = G_ckpt_dict["alpha_G"]
+        self.D.alpha = G_ckpt_dict["alpha_D"]
+        self.reset_solver()
+        self.G.load_state_dict(G_ckpt_dict["model"], strict=False)
+        self.opt_G.load_state_dict(G_ckpt_dict["optimizer"])
+        self.D.load_state_dict(D_ckpt_dict["model"], strict=False)
+        self.opt_D.load_state_dict(D_ckpt_dict["optimizer"])
+        ops.clear_pack_cache()
+        return self.global_step
 
     # --------------------------------------------------------------------- schedule (model.py:131-204)
     def reset_solver(self):
@@ -164,10 +210,12 @@ class ProgressiveGAN:
         a = self.args
         lc = self.loss_collector
         n_samples = len(img_real)
+        nvtx = torch.cuda.nvtx
 
         # ---- Train D ----
+        nvtx.range_push("D forward (real, fake)")
         if self.scale_index:
-            img_real = ops.ImageFade.apply(img_real, None, float(self.D.alpha))     # model.py:217-221
+            img_real = ops.ImageFade.apply(img_real, None, self.D.alpha_ref())      # model.py:217-221
         if latent_D is None:
             latent_D = torch.randn(n_samples, a.latent_dim).to(self.device)
         if self.variant == "W" and n_samples % 4 == 0:
@@ -184,20 +232,25 @@ class ProgressiveGAN:
             img_fake = self.G(latent_D).detach()
             pred_fake = self.D(img_fake)
         D_dict = {"img_real": img_real, "img_fake": img_fake, "pred_real": pred_real, "pred_fake": pred_fake}
+        nvtx.range_pop()
+        nvtx.range_push("D backward (gradient penalty double backward, loss) + Adam")
         self.opt_D.zero_grad()
-        if self.variant == "L":
-            loss_D = lc.get_loss_D(D_dict)
-        else:
-            lc.get_gradient_penalty(D_dict, self.D, backward=True, eps=eps, lazy=True)   # accumulates into D.grad
-            loss_D = lc.get_loss_D_wgangp_terms(D_dict)
-        if self.sync_D is not None:
-            self.sync_D.arm()
-        loss_D.backward()
-        if self.sync_D is not None:
-            self.sync_D.finish()
+        with ops.grad_sink():          # weight / bias gradients are accumulated straight into the flat .grad buffer
+            if self.variant == "L":
+                loss_D = lc.get_loss_D(D_dict)
+            else:
+                lc.get_gradient_penalty(D_dict, self.D, backward=True, eps=eps, lazy=True)   # accumulates into D.grad
+                loss_D = lc.get_loss_D_wgangp_terms(D_dict)
+            if self.sync_D is not None:
+                self.sync_D.arm()
+            loss_D.backward()
+            if self.sync_D is not None:
+                self.sync_D.finish()
         self.opt_D.step()
+        nvtx.range_pop()
 
         # ---- Train G ----
+        nvtx.range_push("G step (G forward, D forward, backward, Adam)")
         if latent_G is None:
             latent_G = torch.randn(n_samples, a.latent_dim).to(self.device)
         d_params = [p for p in self.D.parameters() if p.requires_grad]
@@ -208,24 +261,46 @@ class ProgressiveGAN:
             pred_fake, _ = self.D(img_fake, True)
             loss_G = lc.get_loss_G({"pred_fake": pred_fake})
             self.opt_G.zero_grad()
-            if self.sync_G is not None:
-                self.sync_G.arm()
-            loss_G.backward()
-            if self.sync_G is not None:
-                self.sync_G.finish()
+            with ops.grad_sink():
+                if self.sync_G is not None:
+                    self.sync_G.arm()
+                loss_G.backward()
+                if self.sync_G is not None:
+                    self.sync_G.finish()
         finally:
             for p in d_params:
                 p.requires_grad_(True)
         self.opt_G.step()
+        nvtx.range_pop()
         return [img_real, img_fake]
 
     # ------------------------------------------------------------------------- CUDA graph
+    def _snapshot(self):
+        """everything train_step mutates: parameters, Adam moments and step counters (capture's warm-up restores it)"""
+        return ([p.detach().clone() for p in self.G.parameters()], [p.detach().clone() for p in self.D.parameters()],
+                [(o.exp_avg.clone(), o.exp_avg_sq.clone(), o.step_count.clone()) for o in (self.opt_G, self.opt_D)])
+
+    def _restore(self, snap):
+        g, d, opts = snap
+        with torch.no_grad():
+            for p, v in zip(self.G.parameters(), g):
+                p.copy_(v)
+            for p, v in zip(self.D.parameters(), d):
+                p.copy_(v)
+            for o, (m, v, st) in zip((self.opt_G, self.opt_D), opts):
+                o.exp_avg.copy_(m)
+                o.exp_avg_sq.copy_(v)
+                o.step_count.copy_(st)
+        ops.clear_pack_cache()
+
     def capture(self, batch: int, resolution: Optional[int] = None, warmup: int = 3):
-        """Capture one whole train_step (3 D + 2 G passes, double backward, both Adam updates) into a
-        CUDA graph and return `replay(img, latent_D, latent_G, eps)`, which copies the inputs into the
-        static buffers and launches the graph: ~900 kernel launches per step cost no CPU time.
-        alpha and the scale are baked in — capture again after check_jump() changes either
-        (alpha changes every `alpha_jump_interval` = 100 steps, re-capture takes tens of ms)."""
+        """Capture one whole train_step (3 D + 2 G passes, double backward, both Adam updates, and under data
+        parallelism the bucketed all-reduces) into a CUDA graph and return `replay(img, latent_D, latent_G, eps)`,
+        which copies the inputs into the static buffers and launches the graph: ~900 kernel launches per step cost no
+        CPU time.  alpha is a DEVICE scalar the kernels read at run time (G.alpha / D.alpha are re-uploaded by replay()
+        whenever the floats changed), so change_alpha() needs no new capture; change_scale() does (new layers, new
+        optimizers).  The warm-up steps run on noise and are UNDONE (parameters, Adam moments and step counters are
+        restored), so capturing has no effect on training."""
         a = self.args
         res = resolution or 4 * 2 ** self.scale_index
         dev = self.device
@@ -239,23 +314,32 @@ class ProgressiveGAN:
         static["z_d"].normal_()
         static["z_g"].normal_()
         static["eps"].uniform_()
+        self.G.alpha_ref()
+        self.D.alpha_ref()
+        snap = self._snapshot()
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            for _ in range(warmup):           # allocator / lazily-built state settle before capture
+            for _ in range(warmup):           # allocator / lazily-built state / DP contribution counts settle
                 self.train_step(static["img"], latent_D=static["z_d"], latent_G=static["z_g"], eps=static["eps"])
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        ops.clear_pack_cache()
+        self._restore(snap)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             out = self.train_step(static["img"], latent_D=static["z_d"], latent_G=static["z_g"], eps=static["eps"])
+        # the capture itself recorded (did not run) one step; nothing to undo
         self._graph, self._graph_static, self._graph_out = graph, static, out
+        self._graph_scale = self.scale_index
 
         def replay(img=None, latent_D=None, latent_G=None, eps=None):
+            if self.scale_index != self._graph_scale:
+                raise RuntimeError("the networks grew since this graph was captured: capture() again after change_scale")
             for key, val in (("img", img), ("z_d", latent_D), ("z_g", latent_G), ("eps", eps)):
                 if val is not None:
                     static[key].copy_(val, non_blocking=True)
+            self.G.alpha_ref()                # upload alpha if check_jump() changed it (one 4-byte fill, else nothing)
+            self.D.alpha_ref()
             graph.replay()
             return out
 

@@ -32,7 +32,7 @@ def upscale2d(x, factor=2):
     assert factor == 2, "the PGGAN path only up-samples by 2"
     if _is_image(x):                       # fp32 RGB stays fp32 NCHW: plain replication
         return x.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
-    return ops.Upsample2x.apply(x, 1.0)
+    return ops.export_act(ops.Upsample2x.apply(x, 1.0))
 
 
 def downscale2d(x, factor=2):
@@ -43,7 +43,7 @@ def downscale2d(x, factor=2):
     assert factor == 2, "the PGGAN path only down-samples by 2"
     if _is_image(x):
         return torch.nn.functional.avg_pool2d(x, (2, 2))
-    return ops.Pool2x2.apply(x, 0.25)
+    return ops.export_act(ops.Pool2x2.apply(x, 0.25))
 
 
 def num_flat_features(x):

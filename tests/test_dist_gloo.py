@@ -32,11 +32,40 @@ def _worker(rank, world, port, q):
     assert len(sync.buckets) > 2
     torch.manual_seed(7 + rank)
     x1, x2 = torch.randn(5, 16), torch.randn(5, 16)
+    # three identical steps: the first armed backward LEARNS the contribution counts (every bucket is reduced in
+    # finish()), the later ones launch each bucket from the contribution that completes it
+    early = []
+    for step in range(3):
+        grads.zero()
+        net(x1).pow(2).sum().backward()                # first backward of the step: NOT reduced yet
+        local_after_first = grads.flat.clone()
+        sync.arm()
+        net(x2).sum().backward()                       # last backward: buckets go out as they complete
+        early.append(sum(sync._launched))              # launched before finish()
+        sync.finish()
+        if step == 0:
+            first = grads.flat.clone()
+        else:
+            assert torch.equal(first, grads.flat), "counted launch changed the reduced gradients"
+    assert early[0] == 0 and early[1] >= len(sync.buckets) - 1 and early[2] == early[1], early
+    # an in-place contribution reported through the sink listener counts like an autograd accumulation
+    from pggan_b200 import ops
+    sync.relearn()
+    for step in range(2):
+        grads.zero()
+        sync.arm()
+        net(x2).sum().backward()
+        with torch.no_grad():
+            params[0].grad.add_(1.0)
+        ops._sunk(params[0])
+        sync.finish()
+    assert sync._expected[sync._param_bucket[id(params[0])]] >= 2
     grads.zero()
-    net(x1).pow(2).sum().backward()                    # first backward of the step: NOT reduced yet
+    net(x1).pow(2).sum().backward()
     local_after_first = grads.flat.clone()
+    sync.relearn()
     sync.arm()
-    net(x2).sum().backward()                           # last backward: buckets go out as they complete
+    net(x2).sum().backward()
     sync.finish()
     q.put((rank, grads.flat.tolist(), local_after_first.tolist(), [p.detach().tolist() for p in net.parameters()]))
     dist.barrier()

@@ -1,5 +1,6 @@
 """The committed golden fixtures (outputs of the REFERENCE's own modules, oracle/make_golden.py)
-replayed through the CUDA path in fp32 (3xTF32) mode."""
+replayed through the CUDA path in the fp32 (3xTF32) parity mode (<= 1e-3) and in the benchmarked mixed-precision mode
+(north_star: <= 1e-2 for images / logits, <= 1e-3 for the gradient-penalty value)."""
 import pytest
 import torch
 
@@ -22,31 +23,32 @@ def _build(g):
     return G.cuda(), D.cuda()
 
 
+@pytest.mark.parametrize("mode,tol", [(torch.float32, 1e-3), ("mixed", 1e-2)])
 @pytest.mark.parametrize("name", ["nets_s0.pt", "nets_s1_w64.pt", "nets_s2.pt"])
-def test_reference_fixtures_fp32_mode(name):
+def test_reference_fixtures(name, mode, tol):
     import pggan_b200 as pg
-    pg.set_compute_dtype(torch.float32)
+    pg.set_compute_dtype(mode)
     try:
         g = load_golden(name)
         G, D = _build(g)
         img = G(g["z"].cuda())
-        assert rel_l2(img, g["img"]) < 1e-3, rel_l2(img, g["img"])
+        assert rel_l2(img, g["img"]) < tol, rel_l2(img, g["img"])
         x = g["x"].cuda().requires_grad_()
         logit, feat = D(x, True)
-        assert rel_l2(logit, g["logit"]) < 1e-3 and rel_l2(feat, g["feat"]) < 1e-3
+        assert rel_l2(logit, g["logit"]) < tol and rel_l2(feat, g["feat"]) < tol
         # WGAN-GP value through the reference-shaped API, eps as the reference drew it
         lc = pg.WGANGPLoss(pg.make_args())
         D.zero_grad()
         gp = lc.get_gradient_penalty({"img_real": x, "img_fake": g["img"].cuda(), "pred_real": logit}, D,
                                      backward=True, eps=g["gp_eps"])
         assert abs(gp - float(g["gp_value"])) < 1e-3 * abs(float(g["gp_value"])), (gp, float(g["gp_value"]))
-        assert abs(lc.get_drift_loss({"pred_real": logit}) - float(g["drift"])) < 1e-3 * abs(float(g["drift"])) + 1e-7
+        assert abs(lc.get_drift_loss({"pred_real": logit}) - float(g["drift"])) < 2 * tol * abs(float(g["drift"])) + 1e-7
         lg = lc.get_loss_G({"pred_fake": D(g["img"].cuda())})
-        assert rel_l2(lg, g["loss_G"]) < 1e-3
+        assert rel_l2(lg, g["loss_G"]) < tol
         # live loss value
         x2 = g["x"].cuda().requires_grad_()
         L_D = lc.get_loss_D({"pred_real": D(x2), "pred_fake": D(g["img"].cuda()), "img_real": x2,
                              "img_fake": g["img"].cuda()})
-        assert rel_l2(L_D, g["live_L_D"]) < 1e-3
+        assert rel_l2(L_D, g["live_L_D"]) < tol
     finally:
-        pg.set_compute_dtype(torch.bfloat16)
+        pg.set_compute_dtype("mixed")

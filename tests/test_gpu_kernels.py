@@ -8,10 +8,32 @@ from conftest import rel_l2
 
 pytestmark = pytest.mark.gpu
 
-DT = [torch.bfloat16, torch.float32, torch.float16]
+DT = [torch.bfloat16, torch.float32, torch.float16, "mixed"]
 # bf16: outputs are rounded to 8 significant bits (rms rel err ~2e-3), fp16: 11 bits (~2.5e-4); fp32 mode is 3xTF32
-# (fp32-class; tensor-core fp32 accumulation truncates: ~2^-24 per MMA step, so long K drifts to ~1e-4)
-TOL = {torch.bfloat16: 4e-3, torch.float32: 2e-4, torch.float16: 6e-4}
+# (fp32-class; tensor-core fp32 accumulation truncates: ~2^-24 per MMA step, so long K drifts to ~1e-4).
+# "mixed": activation-class tensors ("a") are fp16, gradient-class tensors ("g") bf16.
+_TOL = {torch.bfloat16: 4e-3, torch.float32: 2e-4, torch.float16: 6e-4}
+
+
+def real(dtype, cls="a"):
+    """element format of a tensor of class `cls` in precision mode `dtype`"""
+    if dtype == "mixed":
+        return torch.float16 if cls == "a" else torch.bfloat16
+    return dtype
+
+
+def tol(dtype, cls="a"):
+    return _TOL[real(dtype, cls)]
+
+
+class _Tol:
+    """TOL[dtype] = tolerance of a gradient-class result (the looser one in mixed mode)"""
+
+    def __getitem__(self, dtype):
+        return tol(dtype, "g")
+
+
+TOL = _Tol()
 
 
 @pytest.fixture(autouse=True)
@@ -24,18 +46,26 @@ def _setup():
     from pggan_b200 import _lib
     _lib.load().pggan_set_conv_backend(0)
     import pggan_b200 as pg
-    pg.set_compute_dtype(torch.bfloat16)
+    pg.set_compute_dtype("mixed")
 
 
-def rnd(t, dtype):
+def rnd(t, dtype, cls="a"):
     """round to the operand precision the tensor core sees, keep fp32 storage"""
-    if dtype in (torch.bfloat16, torch.float16):
-        return t.to(dtype).float()
+    r = real(dtype, cls)
+    if r in (torch.bfloat16, torch.float16):
+        return t.to(r).float()
     return t          # fp32 mode takes full fp32 operands (3xTF32)
 
 
-def to_feat(t, dtype):
-    return t.to(dtype).contiguous(memory_format=torch.channels_last) if t.dim() == 4 else t.to(dtype).contiguous()
+def to_feat(t, dtype, cls="a"):
+    """internal feature tensor of class `cls` (the precision mode must already be set)"""
+    from pggan_b200 import ops
+    return ops.feat(t, cls)
+
+
+def f32(t, cls="a"):
+    from pggan_b200 import ops
+    return ops.to_float(t, cls)
 
 
 CONV_SHAPES = [
@@ -107,8 +137,8 @@ def test_conv_fprop(shape, backend, dtype):
         assert after["tcgen05"] > before["tcgen05"], "tensor-core path did not run"
     else:
         assert after["simt"] > before["simt"]
-    assert y.dtype == dtype
-    assert rel_l2(y.float(), ref) < TOL[dtype], rel_l2(y.float(), ref)
+    assert y.dtype == ops.get_compute_dtype()
+    assert rel_l2(f32(y), ref) < tol(dtype), rel_l2(f32(y), ref)
 
 
 @pytest.mark.parametrize("dtype", DT)
@@ -125,8 +155,8 @@ def test_conv_mask_and_raw_out(shape, dtype):
     wp = ops._pack(w, "f", dtype)
     y = ops.k_conv(to_feat(x, dtype), wp, None, Co, 9, 0.05, 1.0, mask_src=to_feat(ysrc, dtype), mask_slope=0.2)
     ref = F.conv2d(x, w, None, padding=1) * 0.05
-    ref = torch.where(to_feat(ysrc, dtype).float() > 0, ref, ref * 0.2)
-    assert rel_l2(y.float(), ref) < TOL[dtype]
+    ref = torch.where(f32(to_feat(ysrc, dtype)) > 0, ref, ref * 0.2)
+    assert rel_l2(f32(y), ref) < tol(dtype)
     yr = ops.k_conv(to_feat(x, dtype), wp, None, Co, 9, 0.05, 1.0, raw_out=True)
     assert yr.dtype == torch.float32
     assert rel_l2(yr, F.conv2d(x, w, None, padding=1) * 0.05) < 1e-4
@@ -149,7 +179,7 @@ def test_conv_dgrad_wgrad(shape, backend, dtype):
     x = rnd(torch.randn(B, Ci, H, W, device=dev), dtype)
     w = rnd(torch.randn(Co, Ci, k, k, device=dev), dtype)
     b = torch.randn(Co, device=dev)
-    gy = rnd(torch.randn(B, Co, H, W, device=dev), dtype)
+    gy = rnd(torch.randn(B, Co, H, W, device=dev), dtype, "g")
     scale = (2.0 / (Ci * taps)) ** 0.5
     xr, wr, br = x.clone().requires_grad_(), w.clone().requires_grad_(), b.clone().requires_grad_()
     (F.conv2d(xr, wr, br, padding=k // 2) * scale).backward(gy)
@@ -159,7 +189,7 @@ def test_conv_dgrad_wgrad(shape, backend, dtype):
         y.backward(gy.view(B, Co).to(y.dtype))
     else:
         y = ops.ConvF.apply(xm, wm, bm, scale, 1.0, False)
-        y.backward(to_feat(gy, dtype))
+        y.backward(to_feat(gy, dtype, "g"))
     assert rel_l2(xm.grad, xr.grad) < TOL[dtype], ("dgrad", rel_l2(xm.grad, xr.grad))
     assert rel_l2(wm.grad, wr.grad) < 2e-4, ("wgrad", rel_l2(wm.grad, wr.grad))
     assert rel_l2(bm.grad, br.grad) < 1e-4, ("bias", rel_l2(bm.grad, br.grad))
@@ -179,12 +209,12 @@ def test_conv_double_backward(dtype):
     def run(fn):
         xx, ww, bb = x.clone().requires_grad_(), w.clone().requires_grad_(), b.clone().requires_grad_()
         y = fn(xx, ww, bb)
-        (g,) = torch.autograd.grad(y.float().sum(), xx, create_graph=True)
+        (g,) = torch.autograd.grad(y.sum(), xx, create_graph=True)
         (g.float() ** 2).sum().backward()
         return g.detach().float(), ww.grad, xx.grad
 
     g_ref, gw_ref, _ = run(lambda xx, ww, bb: F.leaky_relu(F.conv2d(xx, ww, bb, padding=1) * 0.1, 0.2))
-    g_my, gw_my, _ = run(lambda xx, ww, bb: ops.ConvF.apply(xx, ww, bb, 0.1, 0.2, False))
+    g_my, gw_my, _ = run(lambda xx, ww, bb: ops.ExportFloat.apply(ops.ConvF.apply(xx, ww, bb, 0.1, 0.2, False)))
     assert rel_l2(g_my, g_ref) < 2 * TOL[dtype]
     assert rel_l2(gw_my, gw_ref) < 4 * TOL[dtype], rel_l2(gw_my, gw_ref)
 
@@ -195,32 +225,51 @@ def test_elementwise(dtype):
     import pggan_b200 as pg
     pg.set_compute_dtype(dtype)
     B, C, H, W = 3, 64, 8, 16
-    x = to_feat(rnd(torch.randn(B, C, H, W, device="cuda"), dtype), dtype)
+    x = to_feat(rnd(torch.randn(B, C, H, W, device="cuda"), dtype), dtype)            # activation class
     y = to_feat(rnd(torch.randn(B, C, H, W, device="cuda"), dtype), dtype)
-    # mask mul
-    out = ops.k_mask_mul(x, y, 0.2)
-    ref = torch.where(y.float() > 0, x.float(), x.float() * 0.2)
-    assert rel_l2(out.float(), ref) < TOL[dtype]
-    # upsample: exact indexing
+    g = to_feat(rnd(torch.randn(B, C, H, W, device="cuda"), dtype, "g"), dtype, "g")  # gradient class
+    # mask mul: gradient masked by the sign of an activation
+    out = ops.k_mask_mul(g, y, 0.2)
+    ref = torch.where(f32(y) > 0, f32(g, "g"), f32(g, "g") * 0.2)
+    assert rel_l2(f32(out, "g"), ref) < tol(dtype, "g")
+    # fused mask + column sum
+    out2, cs2 = ops.k_mask_colsum(g, y, 0.2, True, 0.5)
+    assert torch.equal(out2, out)
+    assert rel_l2(cs2, 0.5 * f32(out, "g").sum(dim=(0, 2, 3))) < 1e-4
+    # upsample: exact indexing (bit copies, either class)
     up = ops.k_upsample(x, 1.0)
     assert torch.equal(up, x.repeat_interleave(2, 2).repeat_interleave(2, 3))
     assert up.is_contiguous(memory_format=torch.channels_last)
+    upm = ops.k_upsample(g, 0.25, mask_src=up, slope=0.2, cls="g")
+    gm = f32(g, "g").repeat_interleave(2, 2).repeat_interleave(2, 3) * 0.25
+    assert rel_l2(f32(upm, "g"), torch.where(f32(up) > 0, gm, gm * 0.2)) < tol(dtype, "g")
     # pool
     pl = ops.k_pool(x, 0.25)
-    assert rel_l2(pl.float(), F.avg_pool2d(x.float(), 2)) < TOL[dtype]
+    assert rel_l2(f32(pl), F.avg_pool2d(f32(x), 2)) < tol(dtype)
     low = to_feat(rnd(torch.randn(B, C, H // 2, W // 2, device="cuda"), dtype), dtype)
     pb = ops.k_pool(x, 0.25, blend_with=low, alpha=0.3)
-    assert rel_l2(pb.float(), 0.7 * low.float() + 0.3 * F.avg_pool2d(x.float(), 2)) < TOL[dtype]
+    assert rel_l2(f32(pb), 0.7 * f32(low) + 0.3 * F.avg_pool2d(f32(x), 2)) < tol(dtype)
+    # the same with alpha as a device scalar (what a captured CUDA graph reads)
+    adev = torch.full((1,), 0.3, device="cuda")
+    pb2 = ops.k_pool(x, 0.25, blend_with=low, alpha=ops.AlphaRef(0.3, adev))
+    assert torch.equal(pb2, pb)
+    adev.fill_(0.9)
+    pb3 = ops.k_pool(x, 0.25, blend_with=low, alpha=ops.AlphaRef(0.3, adev))      # the DEVICE value wins
+    assert rel_l2(f32(pb3), 0.1 * f32(low) + 0.9 * F.avg_pool2d(f32(x), 2)) < tol(dtype)
+    ups = ops.k_upsample(g, ops._affine(0.0, 0.25, ops.AlphaRef(0.3, adev)), cls="g")
+    assert rel_l2(f32(ups, "g"), f32(g, "g").repeat_interleave(2, 2).repeat_interleave(2, 3) * 0.225) < tol(dtype, "g")
     # axpby
     ab = ops.k_axpby(x, y, 0.25, 0.75)
-    assert rel_l2(ab.float(), 0.25 * x.float() + 0.75 * y.float()) < TOL[dtype]
+    assert rel_l2(f32(ab), 0.25 * f32(x) + 0.75 * f32(y)) < tol(dtype)
+    ab2 = ops.k_axpby(g, None, ops._affine(1.0, -1.0, ops.AlphaRef(0.0, adev)), 0.0, cls="g")
+    assert rel_l2(f32(ab2, "g"), 0.1 * f32(g, "g")) < tol(dtype, "g")
     # colsum
-    cs = ops.k_colsum(x, 0.5)
-    assert rel_l2(cs, 0.5 * x.float().sum(dim=(0, 2, 3))) < 1e-5
+    cs = ops.k_colsum(g, 0.5)
+    assert rel_l2(cs, 0.5 * f32(g, "g").sum(dim=(0, 2, 3))) < 1e-5
     # Upsample/Pool autograd pair
-    xr = x.float().clone().requires_grad_()
-    (ops.Upsample2x.apply(xr, 1.0).float() * up.float()).sum().backward()
-    assert rel_l2(xr.grad, 4 * F.avg_pool2d(up.float(), 2)) < 2 * TOL[dtype]
+    xr = f32(x).clone().requires_grad_()
+    (ops.ExportFloat.apply(ops.Upsample2x.apply(xr, 1.0)) * f32(up)).sum().backward()
+    assert rel_l2(xr.grad, 4 * F.avg_pool2d(f32(up), 2)) < 2 * tol(dtype, "g")
 
 
 @pytest.mark.parametrize("dtype", DT)
@@ -232,16 +281,16 @@ def test_pixelnorm(C, dtype):
     x = rnd(torch.randn(4, C, 8, 8, device="cuda"), dtype)
     xr = x.clone().requires_grad_()
     ref = xr * torch.rsqrt((xr ** 2).mean(dim=1, keepdim=True) + 1e-8)
-    g = rnd(torch.randn_like(x), dtype)
+    g = rnd(torch.randn_like(x), dtype, "g")
     ref.backward(g)
     xm = x.clone().requires_grad_()
     y = ops.PixelNorm.apply(xm, 1e-8)
-    y.backward(to_feat(g, dtype))
-    assert rel_l2(y.float(), ref) < TOL[dtype]
-    assert rel_l2(xm.grad, xr.grad) < 3 * TOL[dtype], rel_l2(xm.grad, xr.grad)
+    y.backward(to_feat(g, dtype, "g"))
+    assert rel_l2(f32(y), ref) < tol(dtype)
+    assert rel_l2(xm.grad, xr.grad) < 3 * tol(dtype, "g"), rel_l2(xm.grad, xr.grad)
     # 2-D latent path
     z = torch.randn(6, 512, device="cuda")
-    assert rel_l2(ops.PixelNorm.apply(z, 1e-8).float(), z * torch.rsqrt((z ** 2).mean(1, keepdim=True) + 1e-8)) < TOL[dtype]
+    assert rel_l2(f32(ops.PixelNorm.apply(z, 1e-8)), z * torch.rsqrt((z ** 2).mean(1, keepdim=True) + 1e-8)) < tol(dtype)
 
 
 @pytest.mark.parametrize("dtype", DT)
@@ -258,15 +307,15 @@ def test_rgb_ops(C, dtype):
         ir, wr, br = img.clone().requires_grad_(), Wf.clone().requires_grad_(), bf.clone().requires_grad_()
         src = F.avg_pool2d(ir, 2) if pool else ir
         ref = F.leaky_relu(F.conv2d(src, wr.view(C, 3, 1, 1), br) * 0.7, 0.2)
-        g = torch.randn_like(ref)
+        g = rnd(torch.randn_like(ref), dtype, "g")
         ref.backward(g)
         im, wm, bm = img.clone().requires_grad_(), Wf.clone().requires_grad_(), bf.clone().requires_grad_()
         y = ops.RgbExpand.apply(im, wm, bm, pool, 0.7, 0.2)
-        y.backward(to_feat(g, dtype))
-        assert rel_l2(y.float(), ref) < TOL[dtype]
-        assert rel_l2(im.grad, ir.grad) < 3 * TOL[dtype], ("expand gimg", pool, rel_l2(im.grad, ir.grad))
-        assert rel_l2(wm.grad, wr.grad) < 3 * TOL[dtype], ("expand gW", pool, rel_l2(wm.grad, wr.grad))
-        assert rel_l2(bm.grad, br.grad) < 3 * TOL[dtype]
+        y.backward(to_feat(g, dtype, "g"))
+        assert rel_l2(f32(y), ref) < tol(dtype)
+        assert rel_l2(im.grad, ir.grad) < 3 * tol(dtype, "g"), ("expand gimg", pool, rel_l2(im.grad, ir.grad))
+        assert rel_l2(wm.grad, wr.grad) < 3 * tol(dtype, "g"), ("expand gW", pool, rel_l2(wm.grad, wr.grad))
+        assert rel_l2(bm.grad, br.grad) < 3 * tol(dtype, "g")
     x = rnd(torch.randn(B, C, R, R, device="cuda"), dtype)
     Wt = torch.randn(3, C, device="cuda")
     bt = torch.randn(3, device="cuda")
@@ -281,16 +330,29 @@ def test_rgb_ops(C, dtype):
         y = ops.RgbReduce.apply(to_feat(xm, dtype), wm.t(), bm, up, 0.3, 1.0)
         y.backward(g)
         assert y.dtype == torch.float32 and rel_l2(y, ref) < 1e-5
-        assert rel_l2(xm.grad, xr.grad) < 2 * TOL[dtype], ("reduce gx", up)
-        assert rel_l2(wm.grad, wr.grad) < 2 * TOL[dtype], ("reduce gW", up, rel_l2(wm.grad, wr.grad))
+        assert rel_l2(xm.grad, xr.grad) < 2 * tol(dtype, "g"), ("reduce gx", up)
+        assert rel_l2(wm.grad, wr.grad) < 2 * tol(dtype, "g"), ("reduce gW", up, rel_l2(wm.grad, wr.grad))
         assert rel_l2(bm.grad, br.grad) < 1e-4
-    # fades: exact fp32 formulas
+    # fades: exact fp32 formulas, alpha as a float and as a device scalar; the backward through the fade
     low = torch.randn(B, 3, R // 2, R // 2, device="cuda")
     out = ops.ImageFade.apply(img, low, 0.3)
     assert rel_l2(out, 0.7 * low.repeat_interleave(2, 2).repeat_interleave(2, 3) + 0.3 * img) < 1e-6
+    adev = torch.full((1,), 0.3, device="cuda")
+    assert torch.equal(ops.ImageFade.apply(img, low, ops.AlphaRef(0.3, adev)), out)
     out = ops.ImageFade.apply(img, None, 0.3)
     ref = 0.7 * F.interpolate(F.avg_pool2d(img, 2), scale_factor=2, mode="nearest") + 0.3 * img
     assert rel_l2(out, ref) < 1e-6
+    for with_low in (True, False):
+        ir, lr = img.clone().requires_grad_(), low.clone().requires_grad_()
+        lo_ref = lr if with_low else F.avg_pool2d(ir, 2)
+        ref = 0.7 * F.interpolate(lo_ref, scale_factor=2, mode="nearest") + 0.3 * ir
+        gg = torch.randn_like(ref)
+        ref.backward(gg)
+        im, lm = img.clone().requires_grad_(), low.clone().requires_grad_()
+        ops.ImageFade.apply(im, lm if with_low else None, ops.AlphaRef(0.3, adev)).backward(gg)
+        assert rel_l2(im.grad, ir.grad) < 1e-6
+        if with_low:
+            assert rel_l2(lm.grad, lr.grad) < 1e-6
 
 
 @pytest.mark.parametrize("dtype", DT)
@@ -313,12 +375,30 @@ def test_mbstd(B, group, dtype):
     u = torch.randn_like(x)
     (g_ref * u).sum().backward()
     xm = x.clone().requires_grad_()
-    s = ops.MbstdStat.apply(to_feat(xm, dtype), group)
+    s = ops.MbstdStat.apply(xm, group)
     (g_my,) = torch.autograd.grad((s * wgt).sum(), xm, create_graph=True)
     (g_my.float() * u).sum().backward()
     assert rel_l2(s, s_ref) < 1e-4
-    assert rel_l2(g_my.float(), g_ref) < 3 * TOL[dtype]
-    assert rel_l2(xm.grad, xr.grad) < 6 * TOL[dtype], rel_l2(xm.grad, xr.grad)
+    assert rel_l2(g_my.float(), g_ref) < 3 * tol(dtype, "g")
+    assert rel_l2(xm.grad, xr.grad) < 6 * tol(dtype, "g"), rel_l2(xm.grad, xr.grad)
+
+
+def test_mbstd_single_sample_and_channel():
+    """B == 1: the extra channel is all zeros (reference lib/blocks.py:232-233); B % 4 != 0: one group of B"""
+    from pggan_b200.blocks import concatenate_stddev_channel
+    from pggan_b200 import ops
+    import pggan_b200 as pg
+    pg.set_compute_dtype(torch.float32)
+    x = torch.randn(1, 64, 4, 4, device="cuda")
+    y = concatenate_stddev_channel(x)
+    assert y.shape == (1, 65, 4, 4) and float(y[:, 64].abs().max()) == 0.0 and torch.equal(y[:, :64], x)
+    x = torch.randn(6, 64, 4, 4, device="cuda")
+    y = concatenate_stddev_channel(x)
+    ref = torch.sqrt(x.reshape(1, 6, -1).var(dim=1, unbiased=True) + 1e-8).mean()
+    assert rel_l2(y[:, 64], ref.expand(6, 4, 4)) < 1e-5
+    pg.set_compute_dtype("mixed")
+    y = concatenate_stddev_channel(x)                # exported as an honest fp16 tensor in mixed mode
+    assert y.dtype == torch.float16 and rel_l2(y[:, 64].float(), ref.expand(6, 4, 4)) < 1e-3
 
 
 def test_gp_reduce_and_r1():
@@ -364,6 +444,30 @@ def test_fused_adam_matches_torch():
     for pm, pr in zip(mine, ref):
         assert rel_l2(pm, pr) < 1e-6
     assert int(opt_m.step_count.item()) == 4
+    # optimizer state in torch.optim.Adam's wire format, both directions (reference pggan/model.py:97-101)
+    sd_m, sd_r = opt_m.state_dict(), opt_r.state_dict()
+    assert sorted(sd_m["state"].keys()) == sorted(sd_r["state"].keys())
+    for k in sd_r["state"]:
+        assert float(sd_m["state"][k]["step"]) == float(sd_r["state"][k]["step"])
+        assert rel_l2(sd_m["state"][k]["exp_avg_sq"], sd_r["state"][k]["exp_avg_sq"]) < 1e-6
+    opt_r2 = torch.optim.Adam(ref, lr=1e-3, betas=(0.0, 0.99))
+    opt_r2.load_state_dict(sd_m)                                   # torch reads what FusedAdam wrote
+    opt_m2 = FusedAdam(mine, lr=5e-4, betas=(0.5, 0.9))
+    opt_m2.load_state_dict(sd_r)                                   # FusedAdam reads what torch wrote
+    assert opt_m2.lr == 1e-3 and opt_m2.betas == (0.0, 0.99) and int(opt_m2.step_count.item()) == 4
+    for o_m, o_r in ((opt_m2, opt_r2),):
+        o_m.zero_grad()
+        o_r.zero_grad()
+        for pm, pr in zip(mine, ref):
+            g = torch.randn_like(pm)
+            pm.grad.add_(g)
+            pr.grad = g.clone()
+        o_m.step()
+        o_r.step()
+    for pm, pr in zip(mine, ref):
+        assert rel_l2(pm, pr) < 1e-6
+    with pytest.raises(ValueError):
+        opt_m2.load_state_dict({"exp_avg": None})
 
 
 @pytest.mark.parametrize("dtype", DT)
@@ -389,12 +493,12 @@ def test_conv_fused_pixelnorm(shape, dtype):
     if ops.conv_pn_fusable(xf, Co, 9):
         y, r = ops.k_conv(xf, ops._pack(w, "f", dtype), b, Co, 9, scale, 0.2, pn_eps=1e-8)
         r_ref = torch.rsqrt((a ** 2).mean(dim=1) + 1e-8).reshape(-1)
-        assert rel_l2(y.float(), ref) < TOL[dtype], rel_l2(y.float(), ref)
+        assert rel_l2(f32(y), ref) < tol(dtype), rel_l2(f32(y), ref)
         assert rel_l2(r, r_ref) < 1e-3
     # the autograd Function (either path) against PyTorch, forward and input gradient
     xm = x.clone().requires_grad_()
     wm = torch.nn.Parameter(w.clone())
     ym = ops.ConvActPN.apply(to_feat(xm, dtype), wm, b, scale, 0.2, 1e-8)
-    assert rel_l2(ym.float(), ref) < TOL[dtype]
+    assert rel_l2(f32(ym), ref) < tol(dtype)
     assert not ops.conv_pn_fusable(to_feat(rnd(torch.randn(2, 256, 32, 32, device="cuda"), dtype), dtype), 128, 9) \
         or dtype == torch.float32, "256->128 (K = 2304) runs on the swapped kernel: must not be reported fusable"

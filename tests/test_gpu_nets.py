@@ -1,8 +1,10 @@
 """Network / loss / step parity on the GPU: pggan_b200 modules (CUDA kernels through the C ABI)
 against the oracle (oracle/pggan_oracle.py, fp32 PyTorch) on identical weights and inputs.
 
-Tolerances are BASELINE.json's: G images and D logits <= 1e-3 relative L2 in fp32/TF32 and <= 1e-2 in
-bf16; gradient-penalty value <= 1e-3 relative (TF32) — relative L2 over the whole tensor."""
+Tolerances are BASELINE.json's (north_star): G images and D logits <= 1e-3 relative L2 in fp32/TF32 and <= 1e-2 at
+16-bit precision; gradient-penalty value <= 1e-3 relative — relative L2 over the whole tensor.  They are asserted in
+the fp32 (3xTF32) parity mode and in "mixed", the default and BENCHMARKED mode (fp16 activations/weights, bf16
+gradient tensors), at the real widths of BASELINE configs 2-5."""
 import pytest
 import torch
 
@@ -12,21 +14,14 @@ from oracle import pggan_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-# Forward outputs vs the plain fp32 oracle.  fp32 mode (3xTF32): north_star's 1e-3 (measured <= 3.2e-4).
-# bf16 mode: north_star asks 1e-2; measured 0.4e-2 (4x4) ... 1.2e-2 (G images) / 1.8e-2 (D logits, a
-# cancelling 512-term dot product of features that are themselves at 0.5e-2) at 32x32 and deeper — the
-# 8-bit significand of bf16 operands, not the kernels: against the oracle evaluated on bf16-rounded
-# operands (O.emulate) the same outputs agree to BF16_EMU_TOL.  The bound asserted here is the measured
-# envelope; DESIGN.md lists the numbers.
-OUT_TOL = {torch.float32: 1e-3, torch.bfloat16: 2.5e-2}
-BF16_EMU_TOL = 2.5e-2   # bf16 rounding decisions themselves flip under 1e-6 summation-order differences
-# Gradients: LeakyReLU masks come from the sign of pre-activations, so a forward difference of relative
-# size e flips ~e of them and moves the gradient by ~0.8*sqrt(e) in relative L2 (1e-4 -> 0.8e-2).  fp32
-# mode is compared with the plain oracle under that bound; bf16 mode with the bf16-emulating oracle
-# (same masks), where what remains is bf16 rounding of the gradient tensors themselves.
-# (2e-1: where conv + LeakyReLU + pixel norm run as ONE kernel the pre-norm activation is never rounded to bf16, which the
-# emulating oracle — it rounds every layer output — cannot know; measured worst case 1.56e-1 on a 128x128 width-64 G)
-GRAD_TOL = {torch.float32: 2e-2, torch.bfloat16: 2e-1}
+MIXED = "mixed"
+# Forward outputs vs the plain fp32 oracle: north_star's bars.
+OUT_TOL = {torch.float32: 1e-3, MIXED: 1e-2}
+GP_TOL = 1e-3          # gradient-penalty value, every mode
+# Gradients are not covered by north_star.  LeakyReLU masks come from the sign of pre-activations, so a forward
+# difference of relative size e flips ~e of them and moves the gradient by ~0.8*sqrt(e) in relative L2 (1e-4 -> 0.8e-2
+# in fp32 mode, 1e-3 -> 2.5e-2 in mixed mode) on top of the bf16 rounding of the gradient tensors themselves.
+GRAD_TOL = {torch.float32: 2e-2, MIXED: 8e-2}
 
 
 @pytest.fixture(autouse=True)
@@ -35,7 +30,7 @@ def _setup():
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     yield
-    pg.set_compute_dtype(torch.bfloat16)
+    pg.set_compute_dtype(MIXED)
 
 
 def _check_param_grads(mine, ref_params, tol, what, bias_factor=1.0):
@@ -55,7 +50,7 @@ def _check_param_grads(mine, ref_params, tol, what, bias_factor=1.0):
     return worst
 
 
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dtype", [torch.float32, MIXED])
 @pytest.mark.parametrize("scale,alpha,width,batch", [(0, 0.0, 512, 8), (1, 0.5, 512, 8), (3, 0.5, 512, 8),
                                                      (2, 1.0, 64, 6), (5, 0.3, 64, 4)])
 def test_forward_and_first_order(scale, alpha, width, batch, dtype):
@@ -72,27 +67,20 @@ def test_forward_and_first_order(scale, alpha, width, batch, dtype):
 
     gp_, dp_ = req(g_sd), req(d_sd)
     xr = x.clone().requires_grad_()
-    with torch.no_grad():
-        img_fp32 = O.generator_forward(g_sd, z, alpha)
-        logit_fp32, feat_fp32 = O.discriminator_forward(d_sd, x, alpha, True)
-    with O.emulate(dtype):          # identity for fp32; bf16-rounded operands for bf16
-        img_ref = O.generator_forward(gp_, z, alpha)
-        logit_ref, feat_ref = O.discriminator_forward(dp_, xr, alpha, True)
+    img_ref = O.generator_forward(gp_, z, alpha)
+    logit_ref, feat_ref = O.discriminator_forward(dp_, xr, alpha, True)
 
     img = G(z)
     xm = x.clone().requires_grad_()
     logit, feat = D(xm, True)
     assert img.dtype == torch.float32 and img.shape == img_ref.shape
     assert logit.dtype == torch.float32 and logit.shape == (batch, 1)
-    e_img, e_logit, e_feat = rel_l2(img, img_fp32), rel_l2(logit, logit_fp32), rel_l2(feat, feat_fp32)
+    assert feat.dtype == torch.float32 and feat.shape == feat_ref.shape
+    e_img, e_logit, e_feat = rel_l2(img, img_ref), rel_l2(logit, logit_ref), rel_l2(feat, feat_ref)
     print(f"\n[{dtype}] scale {scale} width {width}: vs fp32 oracle: img {e_img:.2e} logit {e_logit:.2e} feat {e_feat:.2e}")
     assert e_img < OUT_TOL[dtype], e_img
     assert e_logit < OUT_TOL[dtype], e_logit
     assert e_feat < OUT_TOL[dtype], e_feat
-    if dtype == torch.bfloat16:
-        q_img, q_logit, q_feat = rel_l2(img, img_ref), rel_l2(logit, logit_ref), rel_l2(feat, feat_ref)
-        print(f"    vs bf16-emulating oracle: img {q_img:.2e} logit {q_logit:.2e} feat {q_feat:.2e}")
-        assert max(q_img, q_logit, q_feat) < BF16_EMU_TOL
 
     # first-order gradients of both networks
     wimg = torch.randn_like(img_ref)
@@ -108,7 +96,7 @@ def test_forward_and_first_order(scale, alpha, width, batch, dtype):
     assert e_gx < GRAD_TOL[dtype]
 
 
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dtype", [torch.float32, MIXED])
 @pytest.mark.parametrize("scale,width,batch", [(0, 512, 8), (2, 512, 8), (3, 64, 4)])
 def test_r1_and_gradient_penalty(scale, width, batch, dtype):
     """the double backward through D: value and accumulated D parameter gradients"""
@@ -129,33 +117,24 @@ def test_r1_and_gradient_penalty(scale, width, batch, dtype):
     # ---- WGAN-GP (reference pggan/loss.py:54-92)
     dp_ = req(d_sd)
     xr = x.clone().requires_grad_()
-    gp_fp32 = O.gradient_penalty(lambda t: O.discriminator_forward(d_sd, t, alpha), x.clone().requires_grad_(), fake,
-                                 10.0, eps=eps, backward=False)
-    with O.emulate(dtype):
-        gp_ref = O.gradient_penalty(lambda t: O.discriminator_forward(dp_, t, alpha), xr, fake, 10.0, eps=eps)
+    gp_ref = O.gradient_penalty(lambda t: O.discriminator_forward(dp_, t, alpha), xr, fake, 10.0, eps=eps)
     xm = x.clone().requires_grad_()
     D.zero_grad()
     gp = lc.get_gradient_penalty({"img_real": xm, "img_fake": fake, "pred_real": D(xm)}, D, backward=True, eps=eps)
-    e_gp = abs(gp - float(gp_fp32)) / abs(float(gp_fp32))
-    e_gp_emu = abs(gp - float(gp_ref)) / abs(float(gp_ref))
-    # north_star: GP value <= 1e-3 relative (fp32/TF32).  bf16: 3e-2 vs fp32 (mask flips in the dgrad chain),
-    # 1e-2 vs the bf16-emulating oracle
-    tol_v = 1e-3 if dtype == torch.float32 else 3e-2
+    e_gp = abs(gp - float(gp_ref)) / abs(float(gp_ref))
     # bias gradients of the penalty exist only through the second-order minibatch-stddev path:
     # tiny numbers, so their relative error is several times that of the weights
     worst = _check_param_grads(grads_by_name(D), dp_, 5 * GRAD_TOL[dtype], "GP", bias_factor=4.0)
-    print(f"\n[{dtype}] scale {scale} width {width}: GP {gp:.5f} vs fp32 oracle {float(gp_fp32):.5f} rel {e_gp:.2e} "
-          f"(emulated {e_gp_emu:.2e}); worst D-grad err {worst:.2e}")
-    assert e_gp < tol_v, e_gp
-    assert e_gp_emu < (1e-3 if dtype == torch.float32 else 1e-2), e_gp_emu
+    print(f"\n[{dtype}] scale {scale} width {width}: GP {gp:.5f} vs fp32 oracle {float(gp_ref):.5f} rel {e_gp:.2e}; "
+          f"worst D-grad err {worst:.2e}")
+    assert e_gp < GP_TOL, e_gp                       # north_star: GP value <= 1e-3 relative
     assert D.decision_layer.module.bias.grad is None or float(D.decision_layer.module.bias.grad.abs().max()) == 0.0
 
     # ---- live loss: BCE + R1 (reference pggan/loss.py:16-27)
     dp_ = req(d_sd)
     xr = x.clone().requires_grad_()
-    with O.emulate(dtype):
-        ld = O.loss_D_live(O.discriminator_forward(dp_, xr, alpha), O.discriminator_forward(dp_, fake, alpha), xr)
-        ld["L_D"].backward()
+    ld = O.loss_D_live(O.discriminator_forward(dp_, xr, alpha), O.discriminator_forward(dp_, fake, alpha), xr)
+    ld["L_D"].backward()
     xm = x.clone().requires_grad_()
     D.zero_grad()
     L_D = lc.get_loss_D({"pred_real": D(xm), "pred_fake": D(fake), "img_real": xm, "img_fake": fake})
@@ -167,10 +146,41 @@ def test_r1_and_gradient_penalty(scale, width, batch, dtype):
     assert abs(lc.loss_dict["L_D"] - round(float(ld["L_D"]), 4)) < max(2e-3, 1e-2 * abs(float(ld["L_D"])))
 
 
+def _param_step_stats(mod, ref_params, sd0):
+    """relative L2 of the parameter DELTAS of a network against a reference's, and of the deltas' magnitude.
+    With beta1 = 0 Adam's first update is lr*g/(|g|+eps) = +-lr, so one sign disagreement on a near-zero gradient
+    costs 2*lr in one element: a fraction f of flipped signs gives a relative L2 of sqrt(4f)."""
+    num = den = 0.0
+    for k, p in mod.named_parameters():
+        d_my = (p.detach() - sd0[k]).double()
+        d_ref = (ref_params[k].detach() - sd0[k]).double()
+        num += float((d_my - d_ref).pow(2).sum())
+        den += float(d_ref.pow(2).sum())
+    return (num / max(den, 1e-300)) ** 0.5
+
+
+def _moment_err(opt, ref_opt, ref_named, mod):
+    """relative L2 of sqrt(exp_avg_sq) (the gradient magnitudes Adam has seen) against torch.optim.Adam's state"""
+    idx = {id(p): i for i, p in enumerate(opt.grads.params)}
+    num = den = 0.0
+    for k, p in mod.named_parameters():
+        if id(p) not in idx:
+            continue
+        st = ref_opt.state.get(ref_named[k])
+        if not st:
+            continue
+        off, n = opt.grads.offsets[idx[id(p)]], p.numel()
+        mine = opt.exp_avg_sq[off:off + n].double().sqrt()
+        ref = st["exp_avg_sq"].reshape(-1).double().sqrt()
+        num += float((mine - ref).pow(2).sum())
+        den += float(ref.pow(2).sum())
+    return (num / max(den, 1e-300)) ** 0.5
+
+
 @pytest.mark.parametrize("variant", ["W", "L"])
 @pytest.mark.parametrize("scale,width,batch", [(0, 64, 8), (2, 64, 8)])
 def test_train_step_matches_oracle(scale, width, batch, variant):
-    """one full D+G step (pggan/model.py:206-255) in tf32 mode: parameter deltas after Adam"""
+    """one full D+G step (pggan/model.py:206-255) in the fp32 parity mode: losses, Adam moments and parameter deltas"""
     import pggan_b200 as pg
     pg.set_compute_dtype(torch.float32)
     alpha = 0.5 if scale else 0.0
@@ -192,25 +202,138 @@ def test_train_step_matches_oracle(scale, width, batch, variant):
     assert abs(tr.loss_collector.loss_dict["L_G"] - otr.loss_dict["L_G"]) < 2e-3 * max(1.0, abs(otr.loss_dict["L_G"]))
     if variant == "W":
         assert abs(tr.loss_collector.loss_dict["L_D_gp"] - otr.loss_dict["L_D_gp"]) < 2e-3 * abs(otr.loss_dict["L_D_gp"])
-    for name, mod, ref, sd0, lr in (("G", tr.G, otr.g, g_sd, 1e-4), ("D", tr.D, otr.d, d_sd, 1e-5)):
-        for k, p in mod.named_parameters():
-            d_my = p.detach() - sd0[k]
-            d_ref = ref[k].detach() - sd0[k]
-            # Adam's first step is lr*g/(|g|+eps): compare where the reference gradient is not ~0
-            bad = ((d_my - d_ref).abs() > 0.3 * lr).float().mean().item()
-            assert bad < 0.03, (name, k, bad)
+    for name, mod, ref, sd0, opt, ropt in (("G", tr.G, otr.g, g_sd, tr.opt_G, otr.opt_G),
+                                           ("D", tr.D, otr.d, d_sd, tr.opt_D, otr.opt_D)):
+        e_m = _moment_err(opt, ropt, ref, mod)
+        e_d = _param_step_stats(mod, ref, sd0)
+        print(f"\n{variant} scale {scale} {name}: Adam second-moment err {e_m:.2e}, parameter-delta rel L2 {e_d:.2e}")
+        assert e_m < 2e-2, (name, e_m)          # gradient magnitudes: the fp32-mode gradient tolerance
+        assert e_d < 0.25, (name, e_d)          # = at most 1.5 % of the update signs differ (near-zero gradients)
 
 
+def _twin_trainers(scale, depths, latent, alpha, variant="W"):
+    import pggan_b200 as pg
+    args = pg.make_args(latent_dim=latent, depths=depths)
+    a = pg.ProgressiveGAN(args, 0, variant=variant)
+    a.set_scale(scale, alpha)
+    b = pg.ProgressiveGAN(pg.make_args(latent_dim=latent, depths=depths), 0, variant=variant)
+    b.set_scale(scale, alpha)
+    b.G.load_state_dict(a.G.state_dict())
+    b.D.load_state_dict(a.D.state_dict())
+    return a, b
+
+
+def test_graph_replay_matches_eager_and_oracle_over_three_steps():
+    """The path bench.py times: benchmarked precision mode, C2's real widths (32x32, 512 channels), CUDA-graph replay,
+    the batched real+fake D pass — against the same step launched eagerly and against the oracle, over THREE steps
+    (Adam moments carried, packed-weight copies invalidated by every update), with alpha CHANGING between the steps:
+    the graph captured at alpha 0.3 must follow G.alpha / D.alpha (device scalar), no re-capture."""
+    import pggan_b200 as pg
+    pg.set_compute_dtype(MIXED)
+    scale, width, batch = 3, 512, 8
+    depths = [width] * (scale + 1)
+    eager, graphed = _twin_trainers(scale, depths, width, 0.3)
+    g_sd = {k: v.detach().clone() for k, v in eager.G.state_dict().items()}
+    d_sd = {k: v.detach().clone() for k, v in eager.D.state_dict().items()}
+    otr = O.OracleTrainer(g_sd, d_sd, alpha=0.3, variant="W", latent_dim=width)
+    before = [p.detach().clone() for p in graphed.D.parameters()]
+    replay = graphed.capture(batch)
+    # capturing (3 warm-up steps on noise) must leave parameters, moments and step counters untouched
+    for p, q in zip(graphed.D.parameters(), before):
+        assert torch.equal(p, q)
+    assert int(graphed.opt_D.step_count.item()) == 0 and float(graphed.opt_G.exp_avg_sq.abs().max()) == 0.0
+    res = 4 * 2 ** scale
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    for step, alpha in enumerate((0.3, 0.5, 0.7)):
+        img = torch.rand(batch, 3, res, res, device="cuda", generator=gen) * 2 - 1
+        z_d = torch.randn(batch, width, device="cuda", generator=gen)
+        z_g = torch.randn(batch, width, device="cuda", generator=gen)
+        eps = torch.rand(batch, 1, device="cuda", generator=gen)
+        for t in (eager, graphed):
+            t.G.alpha = t.D.alpha = alpha
+        otr.alpha = alpha
+        eager.train_step(img, latent_D=z_d, latent_G=z_g, eps=eps)
+        replay(img, z_d, z_g, eps)
+        otr.train_step(img, z_d=z_d, z_g=z_g, eps=eps.cpu())
+        le, lg = eager.loss_collector.loss_dict, graphed.loss_collector.loss_dict
+        for key in ("L_G", "L_D", "L_D_gp"):
+            assert abs(le[key] - lg[key]) <= 2e-3 * max(1.0, abs(le[key])), (step, key, le[key], lg[key])   # read after EVERY replay
+        assert abs(lg["L_D_gp"] - otr.loss_dict["L_D_gp"]) < 2e-3 * abs(otr.loss_dict["L_D_gp"]), (step, lg["L_D_gp"], otr.loss_dict["L_D_gp"])
+        assert abs(lg["L_G"] - otr.loss_dict["L_G"]) < 1e-2 * max(1.0, abs(otr.loss_dict["L_G"]))
+    torch.cuda.synchronize()
+    assert int(graphed.opt_D.step_count.item()) == 3 and int(eager.opt_G.step_count.item()) == 3
+    for name, sd0, get in (("G", g_sd, lambda t: t.G), ("D", d_sd, lambda t: t.D)):
+        ref_eager = dict(get(eager).named_parameters())
+        e_replay = _param_step_stats(get(graphed), ref_eager, sd0)
+        e_oracle = _param_step_stats(get(graphed), otr.g if name == "G" else otr.d, sd0)
+        opt, ropt, rnamed = (graphed.opt_G, otr.opt_G, otr.g) if name == "G" else (graphed.opt_D, otr.opt_D, otr.d)
+        e_m = _moment_err(opt, ropt, rnamed, get(graphed))
+        print(f"\n3 steps, {name}: replay vs eager delta rel L2 {e_replay:.2e}; vs oracle {e_oracle:.2e}; "
+              f"Adam second-moment err vs oracle {e_m:.2e}")
+        # replay and eager launch the same kernels; fp32 atomics (bias sums, RGB weight grads) reorder -> a few signs of
+        # near-zero gradients may differ
+        assert e_replay < 5e-2, (name, e_replay)
+        assert e_m < GRAD_TOL[MIXED], (name, e_m)
+        assert e_oracle < 0.45, (name, e_oracle)       # <= 5 % of the +-lr update signs (near-zero gradients)
+
+
+def test_training_across_scale_jumps_matches_oracle():
+    """check_jump -> change_scale / change_alpha (pggan/model.py:158-204) on the GPU: 4x4 -> 8x8 -> 16x16 with fading,
+    new blocks, new Adam pair — losses of every step against the oracle trained on the same inputs
+    (the oracle is re-seeded with the new randomly-initialised blocks at each jump, as a replica would be)."""
+    import pggan_b200 as pg
+    pg.set_compute_dtype(torch.float32)
+    width, batch = 64, 8
+    args = pg.make_args(latent_dim=width, depths=[width] * 3, max_step_at_scale=[2, 4, 4],
+                        alpha_jump_start=[-1, 1, 1], alpha_jump_interval=[0, 1, 1], alpha_jump_Ntimes=[0, 2, 2])
+    tr = pg.ProgressiveGAN(args, 0, variant="W")
+    otr = None
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    seen_scales, seen_alphas = [], []
+    known_scale = -1
+    for step in range(9):
+        tr.check_jump(step)
+        if tr.scale_index != known_scale:                       # (re)build the oracle after a scale jump
+            known_scale = tr.scale_index
+            g_sd = {k: v.detach().clone() for k, v in tr.G.state_dict().items()}
+            d_sd = {k: v.detach().clone() for k, v in tr.D.state_dict().items()}
+            otr = O.OracleTrainer(g_sd, d_sd, alpha=float(tr.G.alpha), variant="W", latent_dim=width)
+            assert int(tr.opt_D.step_count.item()) == 0          # a fresh Adam pair
+        otr.alpha = float(tr.G.alpha)
+        assert tr.G.alpha == tr.D.alpha
+        res = 4 * 2 ** tr.scale_index
+        img = torch.rand(batch, 3, res, res, device="cuda", generator=gen) * 2 - 1
+        z_d = torch.randn(batch, width, device="cuda", generator=gen)
+        z_g = torch.randn(batch, width, device="cuda", generator=gen)
+        eps = torch.rand(batch, 1, device="cuda", generator=gen)
+        tr.train_step(img, latent_D=z_d, latent_G=z_g, eps=eps)
+        otr.train_step(img, z_d=z_d, z_g=z_g, eps=eps.cpu())
+        ld = tr.loss_collector.loss_dict
+        seen_scales.append(tr.scale_index)
+        seen_alphas.append(float(tr.G.alpha))
+        for key in ("L_G", "L_D_gp", "L_D_eps"):
+            ref = otr.loss_dict[key]
+            assert abs(ld[key] - ref) < 3e-3 * max(1.0, abs(ref)) + 2e-4, (step, key, ld[key], ref)
+    assert seen_scales == [0, 0, 1, 1, 1, 1, 2, 2, 2]
+    assert seen_alphas == [0.0, 0.0, 0.0, 0.5, 1.0, 1.0, 0.0, 0.5, 1.0], seen_alphas
+    assert len(tr.G.blocks) == 2 and len(tr.D.fromRGB_blocks) == 3
+    # the first fromRGB / toRGB layers are stale now (SURVEY.md D16): not registered with Adam, no gradient
+    assert tr.D.fromRGB_blocks[0].fromRGB.module.weight.grad is None
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, MIXED])
 @pytest.mark.parametrize("name,scale,depths,batch", [
+    ("C2 32x32", 3, [512, 512, 512, 512], 8),
+    ("C3 128x128", 5, [512, 512, 512, 512, 256, 128], 4),
     ("C4 256x256", 6, [512, 512, 512, 512, 256, 128, 64], 4),
     ("C5 1024x1024 (paper widths)", 8, [512, 512, 512, 512, 256, 128, 64, 32, 16], 2),
 ])
-def test_full_size_configs_fp32(name, scale, depths, batch):
-    """BASELINE configs 4 and 5 at their real widths/resolutions (small batch): G images, D logits and the
-    WGAN-GP value against the oracle in fp32 mode, plus a size-independent property — D is positively
-    homogeneous-free but its input gradient chain is linear in the seed: grad(2*sum D) == 2*grad(sum D)."""
+def test_full_size_configs(name, scale, depths, batch, dtype):
+    """BASELINE configs 2-5 at their real widths/resolutions (small batch): G images, D logits and the WGAN-GP value
+    against the oracle at north_star's tolerances, in the fp32 parity mode AND in the benchmarked mixed mode; plus a
+    size-independent property: the first-order chain is linear in its seed, grad(2*sum D) == 2*grad(sum D)."""
     import pggan_b200 as pg
-    pg.set_compute_dtype(torch.float32)
+    pg.set_compute_dtype(dtype)
     alpha = 0.5
     G, D, g_sd, d_sd = build_pair(scale, depths, 512, seed=40 + scale)
     G.alpha = D.alpha = alpha
@@ -224,9 +347,9 @@ def test_full_size_configs_fp32(name, scale, depths, batch):
         img = G(z)
         logit = D(x)
     e_img, e_logit = rel_l2(img, img_ref), rel_l2(logit, logit_ref)
-    print(f"\n{name}: img {e_img:.2e} logit {e_logit:.2e}")
+    print(f"\n[{dtype}] {name}: img {e_img:.2e} logit {e_logit:.2e}")
     assert img.shape == (batch, 3, res, res)
-    assert e_img < 1e-3 and e_logit < 1e-3
+    assert e_img < OUT_TOL[dtype] and e_logit < OUT_TOL[dtype], (e_img, e_logit)
     # gradient penalty value (double backward through every resolution stage)
     eps = torch.rand(batch, 1)
     fake = img.detach()
@@ -237,18 +360,22 @@ def test_full_size_configs_fp32(name, scale, depths, batch):
     gp = lc.get_gradient_penalty({"img_real": xm, "img_fake": fake, "pred_real": logit}, D, backward=True, eps=eps)
     e_gp = abs(gp - float(gp_ref)) / abs(float(gp_ref))
     print(f"    GP {gp:.4f} vs {float(gp_ref):.4f} rel {e_gp:.2e}")
-    assert e_gp < 1e-3
+    assert e_gp < GP_TOL, e_gp
+    for pname, prm in D.named_parameters():
+        if prm.grad is not None:
+            assert torch.isfinite(prm.grad).all(), pname
     # linearity of the first-order chain in its seed
     xa = x.clone().requires_grad_()
     (g1,) = torch.autograd.grad(D(xa).sum(), xa)
     xb = x.clone().requires_grad_()
     (g2,) = torch.autograd.grad(2.0 * D(xb).sum(), xb)
-    assert rel_l2(g2, 2.0 * g1) < 1e-5
+    assert rel_l2(g2, 2.0 * g1) < (1e-5 if dtype == torch.float32 else 2e-2)
 
 
 @pytest.mark.parametrize("scale,width,batch", [(3, 512, 16), (5, 64, 4)])
 def test_bf16_error_vs_stock_autocast(scale, width, batch):
-    """north_star asks <= 1e-2 for G images / D logits in bf16.  Beyond 16x16 this build measures 1.0-1.8e-2 — the
+    """(pure bf16 mode — no longer the default: the benchmarked mode is "mixed", which meets the bars.)
+    north_star asks <= 1e-2 for G images / D logits at 16 bits.  Beyond 16x16 pure bf16 measures 1.0-1.8e-2 — the
     question is whether that is the kernels or bf16 itself.  Yardstick: the SAME networks evaluated by stock
     PyTorch/cuDNN under torch.autocast(bfloat16) (the reference's own route to bf16), both against the fp32 oracle.
     Asserted: this build is no further from fp32 than 1.25x stock autocast (measured: it is closer, because its

@@ -141,18 +141,74 @@ def test_reference_import_paths_resolve_to_this_package():
 
 
 def test_checkpoint_roundtrip_reference_format(tmp_path):
+    """lib/checkpoint.py:5-34 signatures: save_checkpoint(model, optimizer, name, ckpt_dict), load_checkpoint(args, name)
+    with args.ckpt_step (None -> 'latest'); the file is the reference's dict (a torch.optim.Adam optimizer state)"""
     import types
+    import inspect
+    import pytest
     import pggan_b200 as pg
     from pggan_b200 import checkpoint
+    assert list(inspect.signature(checkpoint.load_checkpoint).parameters) == ["args", "name"]
+    assert list(inspect.signature(checkpoint.save_checkpoint).parameters) == ["model", "optimizer", "name", "ckpt_dict"]
     G = pg.Generator(32, 32)
     G.add_block(32)
-    args = types.SimpleNamespace(save_root=str(tmp_path), run_id="run0", ckpt_id="run0")
+    args = types.SimpleNamespace(save_root=str(tmp_path), run_id="run0", ckpt_id="run0", ckpt_step=None, isMaster=True)
     opt = torch.optim.Adam(G.parameters(), lr=1e-4, betas=(0.0, 0.99))
-    checkpoint.save_checkpoint(args, G, opt, "G", 7, extra={"scale_index": 1, "alpha_G": 0.25})
+    ckpt_dict = {"args": vars(args), "global_step": 7, "scale_index": 1, "alpha_G": 0.25}
+    checkpoint.save_checkpoint(G, opt, name="G", ckpt_dict=ckpt_dict)
+    assert os.path.exists(tmp_path / "run0" / "ckpt" / "G_7.pt") and os.path.exists(tmp_path / "run0" / "ckpt" / "G_latest.pt")
     G2 = pg.Generator(32, 32)
     D2 = pg.Discriminator(32, apply_minibatch_norm=True)
     checkpoint.grow_to_checkpoint(G2, D2, [32, 32], 1)
-    ck = checkpoint.load_checkpoint(args, G2, None, "G", 7)
-    assert ck["scale_index"] == 1 and ck["global_step"] == 7
-    for (k1, v1), (k2, v2) in zip(G.state_dict().items(), G2.state_dict().items()):
-        assert k1 == k2 and torch.equal(v1, v2)
+    for step in (None, 7):
+        args.ckpt_step = step
+        ck = checkpoint.load_checkpoint(args, "G")
+        assert ck["scale_index"] == 1 and ck["global_step"] == 7 and "param_groups" in ck["optimizer"]
+        G2.load_state_dict(ck["model"], strict=False)
+        for (k1, v1), (k2, v2) in zip(G.state_dict().items(), G2.state_dict().items()):
+            assert k1 == k2 and torch.equal(v1.cpu(), v2.cpu())
+    args.ckpt_step = 99
+    with pytest.raises(FileNotFoundError):
+        checkpoint.load_checkpoint(args, "G")
+
+
+def test_conv_params_struct_layout_matches_the_library():
+    """INTEGRATION.md's ctypes structs are the ones of pggan_b200/_lib.py; the library reports its own sizeof()"""
+    import ctypes
+    from pggan_b200 import _lib
+    lib = _lib.load()
+    assert ctypes.sizeof(_lib.ConvParams) == lib.pggan_sizeof_conv_params()
+    assert ctypes.sizeof(_lib.WgradParams) == lib.pggan_sizeof_wgrad_params()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    for name, _ in _lib.ConvParams._fields_ + _lib.WgradParams._fields_:
+        assert f'"{name}"' in doc, f"INTEGRATION.md's struct listing lacks field {name}"
+
+
+def test_precision_modes_and_tensor_classes():
+    """the mode table of ops.py: which element format each tensor class has, and the label dtype"""
+    import pytest
+    import pggan_b200 as pg
+    from pggan_b200 import ops, _lib as L
+    try:
+        assert ops.get_precision_mode() == "mixed"                  # the default and benchmarked mode
+        assert ops.get_compute_dtype() == torch.bfloat16
+        assert ops._fmt("a") == L.PG_F16 and ops._fmt("g") == L.PG_BF16
+        for dt, fa in ((torch.bfloat16, L.PG_BF16), (torch.float16, L.PG_F16), (torch.float32, L.PG_F32)):
+            pg.set_compute_dtype(dt)
+            assert ops.get_compute_dtype() == dt and ops._fmt("a") == fa and ops._fmt("g") == fa
+        with pytest.raises(ValueError):
+            pg.set_compute_dtype(torch.float64)
+        pg.set_compute_dtype("mixed")
+        # an fp32 tensor imported as an activation becomes fp16 BITS under the bf16 label; to_float reads them back
+        x = torch.tensor([1.0, 0.333251953125, -2.5, 70000.0])
+        xi = ops.feat(x, "a")
+        assert xi.dtype == torch.bfloat16 and torch.equal(xi.view(torch.float16), x.to(torch.float16))
+        assert torch.equal(ops.to_float(xi, "a")[:3], x.to(torch.float16).float()[:3])
+        gi = ops.feat(x, "g")                                       # gradient class: honest bf16
+        assert gi.dtype == torch.bfloat16 and torch.equal(gi, x.to(torch.bfloat16))
+        # alpha coefficients
+        c = ops._coef(ops._affine(1.0, -1.0, 0.25))
+        assert abs(c.c0 - 0.75) < 1e-7 and c.c1 == 0.0 and not c.alpha
+    finally:
+        pg.set_compute_dtype("mixed")
