@@ -73,6 +73,12 @@ int pggan_pack_weight(const float* in, void* out, int dtype, const pg_pack_map* 
 int pggan_unpack_wgrad(const float* in, float* out, const pg_pack_map* map, int slices, float scale, int accumulate,
                        void* stream);
 
+/* out (to_dtype) = in (from_dtype), elementwise, between PG_BF16 / PG_F16 / PG_F32 (conversions to IEEE half saturate).
+ * The mixed-precision mode keeps activations in fp16 and gradient tensors in bf16; tcgen05.mma kind::f16 needs BOTH
+ * operands in one format (a bf16 x fp16 instruction descriptor raises an illegal-instruction fault — measured,
+ * tools/probe_mixed.py), so the activation operand of a weight-gradient GEMM is re-rounded to bf16 by this kernel. */
+int pggan_convert(const void* in, void* out, int64_t n, int from_dtype, int to_dtype, void* stream);
+
 /* fp32 mode = 3xTF32.  The tensor core truncates fp32 operands to tf32 (hi); this writes three copies
  * of in [m][c], one of them (slot lo_slot) holding lo = x - trunc_tf32(x), concatenated along channels
  * ([m][3c]) or along rows ([3m][c]).  A GEMM over (x,x,x_lo) x (w,w_lo,w) then yields
@@ -109,10 +115,6 @@ typedef struct {
      * one epilogue thread owns all N channels of a pixel (pggan_conv_pn_fusable(p) != 0); PG_ERR_UNSUPPORTED elsewhere. */
     float* pn_rnorm;
     float pn_eps;
-    /* Operand format of wp when it differs from `dtype` (mixed precision: fp16 activations and weights, bf16 gradient
-     * tensors — a dgrad runs bf16 x fp16): 0 = same as dtype, else PG_BF16+1 / PG_F16+1.  Both are kind::f16 MMAs; the
-     * A and B operand formats are independent fields of the tcgen05 instruction descriptor. */
-    int32_t w_fmt;
 } pg_conv_params;
 int pggan_conv_fprop(const pg_conv_params* p, void* stream);
 /* which kernel pggan_conv_fprop would run this shape on (pointers may be NULL): lets the host decide where fusing a
@@ -140,9 +142,6 @@ typedef struct {
     /* PG_F32 only — 3xTF32 workspaces: ws_g: 3*B*H*W*N floats, ws_x: 3*B*H*W*C floats */
     void* ws_g;
     void* ws_x;
-    /* format of x when it differs from `dtype` (= the format of g): 0 = same, else PG_BF16+1 / PG_F16+1 (mixed precision:
-     * g is a bf16 gradient tensor, x an fp16 activation) */
-    int32_t x_fmt;
 } pg_wgrad_params;
 int pggan_conv_wgrad(const pg_wgrad_params* p, void* stream);
 int pggan_conv_wgrad_slices(const pg_wgrad_params* p); /* how many slices the call above will write (>= 1) */

@@ -24,7 +24,6 @@ class ConvParams(Structure):
         ("scale", c_float), ("slope", c_float), ("mask_slope", c_float),
         ("ws_x", c_void_p), ("ws_w", c_void_p),
         ("pn_rnorm", c_void_p), ("pn_eps", c_float),
-        ("w_fmt", c_int32),
     ]
 
 
@@ -34,7 +33,6 @@ class WgradParams(Structure):
         ("B", c_int32), ("H", c_int32), ("W", c_int32), ("C", c_int32), ("N", c_int32), ("taps", c_int32),
         ("dtype", c_int32),
         ("ws_g", c_void_p), ("ws_x", c_void_p),
-        ("x_fmt", c_int32),
     ]
 
 
@@ -65,6 +63,7 @@ SIGNATURES = {
     "pggan_sizeof_wgrad_params": (c_int, []),
     "pggan_pack_weight": (c_int, [c_void_p, c_void_p, c_int, POINTER(PackMap), c_void_p]),
     "pggan_unpack_wgrad": (c_int, [c_void_p, c_void_p, POINTER(PackMap), c_int, c_float, c_int, c_void_p]),
+    "pggan_convert": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "pggan_split3": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
     "pggan_conv_fprop": (c_int, [POINTER(ConvParams), c_void_p]),
     "pggan_conv_kernel_kind": (c_int, [POINTER(ConvParams)]),

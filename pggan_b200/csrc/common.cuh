@@ -298,7 +298,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
 }
 // Instruction descriptor for kind::f16 / kind::tf32, fp32 accumulate, dense.
 //   a_fmt/b_fmt: 1 = bf16, 2 = tf32; major: 0 = K-major, 1 = MN-major.
-//   The A and B formats are independent fields (bits 7-9 / 10-12): kind::f16 multiplies a bf16 operand with an f16 one.
+//   The A and B formats are separate fields (bits 7-9 / 10-12), but kind::f16 wants them EQUAL: a bf16 x f16 descriptor
+//   raises an illegal-instruction fault on B200 (measured with tools/probe_mixed.py) — callers pass one format.
 __host__ __device__ constexpr uint32_t make_idesc2(int a_fmt, int b_fmt, int a_major, int b_major, int m, int n) {
     return (1u << 4) | (uint32_t(a_fmt) << 7) | (uint32_t(b_fmt) << 10) | (uint32_t(a_major) << 15) |
            (uint32_t(b_major) << 16) | (uint32_t(n >> 3) << 17) | (uint32_t(m >> 4) << 24);
@@ -306,8 +307,7 @@ __host__ __device__ constexpr uint32_t make_idesc2(int a_fmt, int b_fmt, int a_m
 __host__ __device__ constexpr uint32_t make_idesc(int fmt, int a_major, int b_major, int m, int n) {
     return make_idesc2(fmt, fmt, a_major, b_major, m, n);
 }
-// format of the second operand of a GEMM-class call: `other_fmt` field (0 = same as dtype, else PG_* + 1)
-__host__ __device__ inline int other_dtype(int dtype, int other_fmt) { return other_fmt == 0 ? dtype : other_fmt - 1; }
+
 
 // TMEM -> registers: 32 lanes x 32 consecutive fp32 columns (this warp's lane quarter)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {

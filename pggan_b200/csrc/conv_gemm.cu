@@ -659,7 +659,7 @@ static int launch_tc(const pg_conv_params* p, cudaStream_t stream) {
     a.taps = p->taps;
     a.out_dtype = p->out_dtype;
     a.f16 = p->dtype == PG_F16;
-    a.wf16 = other_dtype(p->dtype, p->w_fmt) == PG_F16;
+    a.wf16 = p->dtype == PG_F16;
     a.scale = p->scale; a.slope = p->slope; a.mask_slope = p->mask_slope;
     a.pn_rnorm = p->pn_rnorm; a.pn_eps = p->pn_eps;
     PG_CHECK(p->pn_rnorm == nullptr || a.tiles_n == 1, PG_ERR_UNSUPPORTED, "fused pixel norm needs one N tile (N=%d)", p->N);
@@ -678,7 +678,7 @@ static int launch_tc(const pg_conv_params* p, cudaStream_t stream) {
         uint64_t dims[2] = {K, (uint64_t)p->N};
         uint64_t strides[1] = {K * es};
         uint32_t box[2] = {(uint32_t)BK, (uint32_t)BLOCK_N};
-        int rc = encode_tmap(&tw, other_dtype(p->dtype, p->w_fmt), 2, p->wp, dims, strides, box, SPAN);
+        int rc = encode_tmap(&tw, p->dtype, 2, p->wp, dims, strides, box, SPAN);
         if (rc != PG_OK) return rc;
     }
     auto kern = conv_gemm_kernel<T, BLOCK_N, SPAN, MT>;
@@ -710,7 +710,7 @@ static int launch_swapped(const pg_conv_params* p, cudaStream_t stream) {
     a.taps = p->taps;
     a.out_dtype = p->out_dtype;
     a.f16 = p->dtype == PG_F16;
-    a.wf16 = other_dtype(p->dtype, p->w_fmt) == PG_F16;
+    a.wf16 = p->dtype == PG_F16;
     a.scale = p->scale; a.slope = p->slope; a.mask_slope = p->mask_slope;
     const uint64_t es = sizeof(T);
     CUtensorMap tx, tw;
@@ -726,7 +726,7 @@ static int launch_swapped(const pg_conv_params* p, cudaStream_t stream) {
         uint64_t dims[2] = {K, (uint64_t)p->N};
         uint64_t strides[1] = {K * es};
         uint32_t box[2] = {(uint32_t)BK, 128u};
-        int rc = encode_tmap(&tw, other_dtype(p->dtype, p->w_fmt), 2, p->wp, dims, strides, box, 128);
+        int rc = encode_tmap(&tw, p->dtype, 2, p->wp, dims, strides, box, 128);
         if (rc != PG_OK) return rc;
     }
     auto kern = conv_gemm_swapped_kernel<T>;
@@ -856,7 +856,7 @@ static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream, int* k
     conv_direct_kernel<T><<<(int)blocks, 256, 0, stream>>>(
         reinterpret_cast<const T*>(p->x), reinterpret_cast<const T*>(p->wp), p->bias,
         reinterpret_cast<const T*>(p->mask_src), p->y, p->B, p->H, p->W, p->C, p->N, p->taps, p->out_dtype, p->scale,
-        p->slope, p->mask_slope, p->dtype == PG_F16, other_dtype(p->dtype, p->w_fmt) == PG_F16);
+        p->slope, p->mask_slope, p->dtype == PG_F16, p->dtype == PG_F16);
     PG_LAUNCH_CHECK();
     g_simt_launches++;
     return PG_OK;
@@ -908,8 +908,6 @@ extern "C" int pggan_conv_fprop(const pg_conv_params* p, void* stream) {
     PG_CHECK(p->dtype == PG_BF16 || p->dtype == PG_F16 || p->dtype == PG_F32, PG_ERR_ARG, "pggan_conv_fprop: bad dtype %d", p->dtype);
     PG_CHECK(p->out_dtype == p->dtype || p->out_dtype == PG_F32 || p->out_dtype == PG_F32_RAW, PG_ERR_ARG,
              "pggan_conv_fprop: bad out_dtype %d", p->out_dtype);
-    PG_CHECK(p->w_fmt == 0 || (is16(p->dtype) && (p->w_fmt == PG_BF16 + 1 || p->w_fmt == PG_F16 + 1)), PG_ERR_ARG,
-             "pggan_conv_fprop: bad w_fmt %d (mixed operand formats exist for the 16-bit types only)", p->w_fmt);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (is16(p->dtype)) return conv_dispatch<__nv_bfloat16>(p, s);      // bf16 and f16 share the 16-bit instantiation
     return conv_dispatch<float>(p, s);

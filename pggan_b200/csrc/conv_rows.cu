@@ -420,7 +420,7 @@ static int launch_rows(const pg_conv_params* p_in, cudaStream_t stream) {
     a.total = static_cast<long long>(p->B) * a.nseg * p->H;
     a.out_dtype = p->out_dtype;
     a.f16 = p->dtype == PG_F16;
-    a.wf16 = other_dtype(p->dtype, p->w_fmt) == PG_F16;
+    a.wf16 = p->dtype == PG_F16;
     a.scale = p->scale; a.slope = p->slope; a.mask_slope = p->mask_slope;
     a.pn_rnorm = p->pn_rnorm; a.pn_eps = p->pn_eps;
     const int sms = num_sms();
@@ -441,7 +441,7 @@ static int launch_rows(const pg_conv_params* p_in, cudaStream_t stream) {
         uint64_t dims[2] = {K, (uint64_t)p->N};
         uint64_t strides[1] = {K * 2};
         uint32_t box[2] = {(uint32_t)p->C, (uint32_t)BLOCK_N};
-        int rc = encode_tmap(&tw, other_dtype(p->dtype, p->w_fmt), 2, p->wp, dims, strides, box, SPAN);
+        int rc = encode_tmap(&tw, p->dtype, 2, p->wp, dims, strides, box, SPAN);
         if (rc != PG_OK) return rc;
     } else {
         tw = tx;                      // unused by the grouped variant (it builds its weight tiles itself)

@@ -564,6 +564,39 @@ __global__ void __launch_bounds__(256) pack_oihw_t_kernel(const float* __restric
     }
 }
 
+// ------------------------------------------------------------------------------ format conversion
+template <typename TI, typename TO>
+__global__ void convert_kernel(const TI* __restrict__ in, TO* __restrict__ out, long long n) {
+    // 8 elements per thread: one or two 16-byte loads, one or two 16-byte stores
+    const long long nvec = n / 8;
+    GRID_STRIDE(i, nvec) {
+        float v[8];
+        if constexpr (sizeof(TI) == 2) {
+            const uint4 raw = __ldg(reinterpret_cast<const uint4*>(in) + i);
+            const TI* e = reinterpret_cast<const TI*>(&raw);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = DT<TI>::to_f(e[k]);
+        } else {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(in) + 2 * i), b = __ldg(reinterpret_cast<const float4*>(in) + 2 * i + 1);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        }
+        if constexpr (sizeof(TO) == 2) {
+            uint4 o;
+            TO* e = reinterpret_cast<TO*>(&o);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) e[k] = DT<TO>::from_f(v[k]);
+            reinterpret_cast<uint4*>(out)[i] = o;
+        } else {
+            reinterpret_cast<float4*>(out)[2 * i] = make_float4(v[0], v[1], v[2], v[3]);
+            reinterpret_cast<float4*>(out)[2 * i + 1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
+    }
+    GRID_STRIDE(i, n - nvec * 8) {
+        const long long k = nvec * 8 + i;
+        out[k] = DT<TO>::from_f(DT<TI>::to_f(in[k]));
+    }
+}
+
 // ------------------------------------------------------------------------------ 3xTF32 operand split
 // in [M][C] fp32 -> three copies, one of which holds lo = x - trunc_tf32(x) (the tensor core truncates
 // fp32 operands to tf32, so the plain copies act as hi).  Concatenated along channels ([M][3C]) for the
@@ -971,6 +1004,30 @@ extern "C" int pggan_unpack_wgrad(const float* in, float* out, const pg_pack_map
     PG_LAUNCH_CHECK();
     g_other_launches++;
     return PG_OK;
+}
+
+extern "C" int pggan_convert(const void* in, void* out, int64_t n, int from_dtype, int to_dtype, void* stream) {
+    PG_CHECK(in && out && n >= 0, PG_ERR_ARG, "pggan_convert: bad args");
+    PG_CHECK(al16(in) && al16(out), PG_ERR_ARG, "pggan_convert: pointers must be 16-byte aligned");
+    if (n == 0) return PG_OK;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const int grid = ew_grid(n / 8 + 1, 256);
+#define PG_CVT(FI, TI, FO, TO)                                                                             \
+    if (from_dtype == FI && to_dtype == FO) {                                                              \
+        convert_kernel<TI, TO><<<grid, 256, 0, s>>>((const TI*)in, (TO*)out, n);                           \
+        PG_LAUNCH_CHECK();                                                                                 \
+        g_other_launches++;                                                                                \
+        return PG_OK;                                                                                      \
+    }
+    PG_CVT(PG_F16, __half, PG_BF16, __nv_bfloat16)
+    PG_CVT(PG_BF16, __nv_bfloat16, PG_F16, __half)
+    PG_CVT(PG_F32, float, PG_BF16, __nv_bfloat16)
+    PG_CVT(PG_F32, float, PG_F16, __half)
+    PG_CVT(PG_BF16, __nv_bfloat16, PG_F32, float)
+    PG_CVT(PG_F16, __half, PG_F32, float)
+#undef PG_CVT
+    pg::set_error("pggan_convert: unsupported conversion %d -> %d", from_dtype, to_dtype);
+    return PG_ERR_ARG;
 }
 
 namespace pg {

@@ -5,6 +5,7 @@
 #include "common.cuh"
 
 #include <atomic>
+#include <stdlib.h>
 
 namespace pg {
 extern std::atomic<long long> g_other_launches;
@@ -377,6 +378,211 @@ rgb_wgrad_pixel_kernel(const T* __restrict__ f, const float* __restrict__ img, f
     }
 }
 
+// ------------------------------------------------------------------------------ tile kernels (round 2)
+// ncu on the kernels above (profiles/r1_ncu_elementwise.md): 19-34 % of the HBM peak with the issue slots 50-60 % busy —
+// every (pixel, channel-vector) visit paid the pixel's index arithmetic and its three image loads again.  The tile
+// kernels below stage the image values of a 256-pixel tile ONCE in shared memory (coalesced plane loads, one float4
+// per pixel), keep each thread on a FIXED channel vector (its weights live in registers) and walk the tile's pixels
+// with purely linear addressing: per 16-byte feature vector one LDS.128, one LDG/STG.128 and the 24 FMAs the math
+// needs.  A warp touches 512 contiguous bytes of the feature map per instruction.
+constexpr int kTilePix = 256;
+
+template <bool POOL>
+__device__ __forceinline__ void stage_tile(const float* __restrict__ img, int cimg, int B, int H, int W, long long tile,
+                                           int P, float4* spix) {
+    const int pix = static_cast<int>(tile * kTilePix) + threadIdx.x;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pix < P) {
+        int b, hh, ww;
+        pix_decomp(pix, H, W, b, hh, ww);
+        float p[kMaxImgC];
+        load_pixel(img, cimg, POOL ? 1 : 0, b, hh, ww, H, W, p);
+        q = make_float4(p[0], p[1], p[2], p[3]);
+    }
+    spix[threadIdx.x] = q;
+}
+
+// out[pix][c] = lrelu(scale*(sum_j w[c][j]*p_j + bias[c]))        (fromRGB; also the dgrad of toRGB)
+template <typename T, bool POOL>
+__global__ void __launch_bounds__(256)
+rgb_expand_tile_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias,
+                       T* __restrict__ out, int B, int H, int W, int C, int cimg, float scale, float slope, int TX) {
+    constexpr int VN = RV<T>::N;
+    __shared__ float4 spix[kTilePix];
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX, TY = kTilePix / TX;
+    float w0[VN], w1[VN], w2[VN], br[VN];               // cimg <= 3 (RGB)
+#pragma unroll
+    for (int e = 0; e < VN; ++e) {
+        const int c = tx * VN + e;
+        w0[e] = __ldg(w + c * cimg) * scale;
+        w1[e] = cimg > 1 ? __ldg(w + c * cimg + 1) * scale : 0.f;
+        w2[e] = cimg > 2 ? __ldg(w + c * cimg + 2) * scale : 0.f;
+        br[e] = bias ? __ldg(bias + c) * scale : 0.f;
+    }
+    const bool act = slope != 1.f;
+    const int P = B * H * W;
+    const long long tiles = (P + kTilePix - 1) / kTilePix;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        __syncthreads();
+        stage_tile<POOL>(img, cimg, B, H, W, tile, P, spix);
+        __syncthreads();
+        const int npx = (P - tile * kTilePix) < kTilePix ? static_cast<int>(P - tile * kTilePix) : kTilePix;
+        T* obase = out + static_cast<size_t>(tile) * kTilePix * C + tx * VN;
+#pragma unroll 4
+        for (int p = ty; p < npx; p += TY) {
+            const float4 q = spix[p];
+            RV<T> o;
+#pragma unroll
+            for (int e = 0; e < VN; ++e) {
+                float t = fmaf(w0[e], q.x, br[e]);
+                t = fmaf(w1[e], q.y, t);
+                t = fmaf(w2[e], q.z, t);
+                if (act) t = t > 0.f ? t : t * slope;
+                o.set(e, t);
+            }
+            *reinterpret_cast<uint4*>(obase + static_cast<size_t>(p) * C) = o.raw;
+        }
+    }
+}
+
+// out[b][j][h][w] = scale*(sum_c w[j][c]*x[pix][c] + bias[j])  (toRGB; also the dgrad of fromRGB), optionally written
+// to the 2x2 block of a twice larger image.  A pixel's C/VN vectors are spread over LX = min(TX, 32) consecutive lanes
+// (NV = TX/LX vectors per lane), partial dot products meet through shuffles, results are staged in shared memory and
+// written as coalesced plane rows.
+template <typename T, int NV>
+__global__ void __launch_bounds__(256)
+rgb_reduce_tile_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                       float* __restrict__ out, int B, int H, int W, int C, int cimg, int up, float scale,
+                       float up_scale, int LX) {
+    constexpr int VN = RV<T>::N;
+    __shared__ float sout[3][kTilePix];
+    const int tx = threadIdx.x % LX, ty = threadIdx.x / LX, TY = kTilePix / LX;
+    float w0[NV][VN], w1[NV][VN], w2[NV][VN];
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+#pragma unroll
+        for (int e = 0; e < VN; ++e) {
+            const int c = (tx + k * LX) * VN + e;
+            w0[k][e] = __ldg(w + c);
+            w1[k][e] = cimg > 1 ? __ldg(w + C + c) : 0.f;
+            w2[k][e] = cimg > 2 ? __ldg(w + 2 * C + c) : 0.f;
+        }
+    const int P = B * H * W;
+    const long long tiles = (P + kTilePix - 1) / kTilePix;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int npx = (P - tile * kTilePix) < kTilePix ? static_cast<int>(P - tile * kTilePix) : kTilePix;
+        const T* xbase = x + static_cast<size_t>(tile) * kTilePix * C + tx * VN;
+        __syncthreads();                              // sout of the previous tile has been written out
+#pragma unroll 2
+        for (int p0 = ty; p0 < kTilePix; p0 += TY) {  // whole warps stay converged for the shuffles
+            const bool live = p0 < npx;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+            RV<T> v[NV];
+#pragma unroll
+            for (int k = 0; k < NV; ++k)
+                v[k].raw = live ? __ldg(reinterpret_cast<const uint4*>(xbase + static_cast<size_t>(p0) * C + k * LX * VN))
+                                : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int k = 0; k < NV; ++k)
+#pragma unroll
+                for (int e = 0; e < VN; ++e) {
+                    const float xv = v[k].get(e);
+                    a0 = fmaf(xv, w0[k][e], a0);
+                    a1 = fmaf(xv, w1[k][e], a1);
+                    a2 = fmaf(xv, w2[k][e], a2);
+                }
+            for (int o = LX >> 1; o > 0; o >>= 1) {
+                a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+                a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+                a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+            }
+            if (tx == 0 && live) {
+                sout[0][p0] = a0;
+                sout[1][p0] = a1;
+                sout[2][p0] = a2;
+            }
+        }
+        __syncthreads();
+        if (static_cast<int>(threadIdx.x) < npx) {
+            const int pix = static_cast<int>(tile * kTilePix) + threadIdx.x;
+            int b, hh, ww;
+            pix_decomp(pix, H, W, b, hh, ww);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                if (j < cimg) {
+                    float r = (sout[j][threadIdx.x] + (bias ? __ldg(bias + j) : 0.f)) * scale;
+                    if (!up) {
+                        out[(static_cast<size_t>(b * cimg + j) * H + hh) * W + ww] = r;
+                    } else {
+                        r *= up_scale;
+                        float* o = out + (static_cast<size_t>(b * cimg + j) * 2 * H + 2 * hh) * 2 * W + 2 * ww;
+                        *reinterpret_cast<float2*>(o) = make_float2(r, r);
+                        *reinterpret_cast<float2*>(o + 2 * W) = make_float2(r, r);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// acc[c][j] += scale * sum_pix f[pix][c]*p_j,  bsum[c] += scale * sum_pix f[pix][c]
+template <typename T, bool POOL>
+__global__ void __launch_bounds__(256)
+rgb_wgrad_tile_kernel(const T* __restrict__ f, const float* __restrict__ img, float* __restrict__ acc,
+                      float* __restrict__ bsum, int B, int H, int W, int C, int cimg, float scale, int TX) {
+    constexpr int VN = RV<T>::N;
+    __shared__ float4 spix[kTilePix];
+    __shared__ float red[kTilePix][4 * VN + 1];
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX, TY = kTilePix / TX;
+    float a0[VN], a1[VN], a2[VN], as[VN];
+#pragma unroll
+    for (int e = 0; e < VN; ++e) a0[e] = a1[e] = a2[e] = as[e] = 0.f;
+    const int P = B * H * W;
+    const long long tiles = (P + kTilePix - 1) / kTilePix;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        __syncthreads();
+        stage_tile<POOL>(img, cimg, B, H, W, tile, P, spix);
+        __syncthreads();
+        const int npx = (P - tile * kTilePix) < kTilePix ? static_cast<int>(P - tile * kTilePix) : kTilePix;
+        const T* fbase = f + static_cast<size_t>(tile) * kTilePix * C + tx * VN;
+#pragma unroll 4
+        for (int p = ty; p < npx; p += TY) {
+            RV<T> v;
+            v.raw = __ldg(reinterpret_cast<const uint4*>(fbase + static_cast<size_t>(p) * C));
+            const float4 q = spix[p];
+#pragma unroll
+            for (int e = 0; e < VN; ++e) {
+                const float fv = v.get(e);
+                a0[e] = fmaf(fv, q.x, a0[e]);
+                a1[e] = fmaf(fv, q.y, a1[e]);
+                a2[e] = fmaf(fv, q.z, a2[e]);
+                as[e] += fv;
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < VN; ++e) {
+        red[threadIdx.x][4 * e + 0] = a0[e];
+        red[threadIdx.x][4 * e + 1] = a1[e];
+        red[threadIdx.x][4 * e + 2] = a2[e];
+        red[threadIdx.x][4 * e + 3] = as[e];
+    }
+    __syncthreads();
+    // TX*VN*4 outputs per block, each the sum over the TY threads that share a channel vector
+    for (int o = threadIdx.x; o < TX * VN * 4; o += blockDim.x) {
+        const int j = o & 3, ce = o >> 2;               // ce = tx*VN + e
+        const int txx = ce / VN, e = ce - txx * VN;
+        float t = 0.f;
+        for (int yy = 0; yy < TY; ++yy) t += red[yy * TX + txx][4 * e + j];
+        if (j < 3) {
+            if (j < cimg) atomicAdd(acc + ce * cimg + j, t * scale);
+        } else if (bsum != nullptr) {
+            atomicAdd(bsum + ce, t * scale);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------ fp32 image kernels
 
 __global__ void image_fade_kernel(const float* __restrict__ x, const float* __restrict__ low, float* __restrict__ out,
@@ -457,6 +663,25 @@ extern "C" int pggan_rgb_expand(const float* img, const float* w, const float* b
     const long long P = (long long)B * H * W;
     const int TY = 256 / TX;
     PG_CHECK(P * (long long)C < (1LL << 40) && P < (1LL << 31), PG_ERR_UNSUPPORTED, "pggan_rgb_expand: tensor too large");
+    static const bool rgb_old = getenv("PGGAN_RGB_OLD") != nullptr;
+    if (!rgb_old && cimg <= 3) {
+        // tile kernel: image values of 256 pixels staged once in smem, fixed channel vector per thread
+        const long long tiles = (P + kTilePix - 1) / kTilePix;
+        const int grid_t = (int)(tiles < (long long)num_sms() * 8 ? tiles : (long long)num_sms() * 8);
+        auto launch_t = [&](auto tag) {
+            using TT = decltype(tag);
+            if (pool)
+                rgb_expand_tile_kernel<TT, true><<<grid_t, 256, 0, s>>>(img, w, bias, (TT*)out, B, H, W, C, cimg, scale, slope, TX);
+            else
+                rgb_expand_tile_kernel<TT, false><<<grid_t, 256, 0, s>>>(img, w, bias, (TT*)out, B, H, W, C, cimg, scale, slope, TX);
+        };
+        if (dtype == PG_BF16) launch_t(__nv_bfloat16());
+        else if (dtype == PG_F16) launch_t(__half());
+        else launch_t(float());
+        PG_LAUNCH_CHECK();
+        g_other_launches++;
+        return PG_OK;
+    }
     const int CVn = C / vn;
     const int g2 = grid_for(P, 256, 8);
     const int grid = grid_for((P + TY - 1) / TY * 256 / 8 + 1, 256, 4);     // >= 8 pixels per thread
@@ -483,6 +708,21 @@ static int rgb_reduce_launch(const void* x, const float* w, const float* bias, f
                              int cimg, int up, float scale, float up_scale, cudaStream_t s) {
     constexpr int VN = 16 / sizeof(T);
     const int CV = C / VN;
+    static const bool rgb_old = getenv("PGGAN_RGB_OLD") != nullptr;
+    if (!rgb_old && cimg <= 3 && CV >= 1 && CV <= 128 && (CV & (CV - 1)) == 0 && (long long)B * H * W < (1LL << 31)) {
+        // tile kernel: LX = min(CV, 32) lanes per pixel, NV = CV / LX vectors per lane
+        const int LX = CV < 32 ? CV : 32, nv = CV / LX;
+        const long long Pn = (long long)B * H * W;
+        const long long tiles = (Pn + kTilePix - 1) / kTilePix;
+        const int grid_t = (int)(tiles < (long long)num_sms() * 8 ? tiles : (long long)num_sms() * 8);
+        const T* xq = reinterpret_cast<const T*>(x);
+        if (nv == 1) rgb_reduce_tile_kernel<T, 1><<<grid_t, 256, 0, s>>>(xq, w, bias, out, B, H, W, C, cimg, up, scale, up_scale, LX);
+        else if (nv == 2) rgb_reduce_tile_kernel<T, 2><<<grid_t, 256, 0, s>>>(xq, w, bias, out, B, H, W, C, cimg, up, scale, up_scale, LX);
+        else rgb_reduce_tile_kernel<T, 4><<<grid_t, 256, 0, s>>>(xq, w, bias, out, B, H, W, C, cimg, up, scale, up_scale, LX);
+        PG_LAUNCH_CHECK();
+        g_other_launches++;
+        return PG_OK;
+    }
     if (cimg <= 3 && (CV == 2 || CV == 4 || CV == 8) && (long long)B * H * W < (1LL << 31)) {
         const T* xq = reinterpret_cast<const T*>(x);
         const int P = B * H * W;
@@ -542,6 +782,25 @@ extern "C" int pggan_rgb_wgrad(const void* f, const float* img, float* acc, floa
     PG_CHECK(TX <= 256 && 256 % TX == 0, PG_ERR_UNSUPPORTED, "pggan_rgb_wgrad: C/%d = %d must divide 256", vn, TX);
     const long long P = (long long)B * H * W;
     PG_CHECK(P < (1LL << 31), PG_ERR_UNSUPPORTED, "pggan_rgb_wgrad: tensor too large");
+    static const bool rgb_old = getenv("PGGAN_RGB_OLD") != nullptr;
+    if (!rgb_old && cimg <= 3) {
+        const long long tiles = (P + kTilePix - 1) / kTilePix;
+        long long want = (long long)num_sms() * 4;          // each block ends with TX*VN*4 atomics: keep the count moderate
+        const int grid_t = (int)(tiles < want ? tiles : want);
+        auto launch_t = [&](auto tag) {
+            using TT = decltype(tag);
+            if (pool)
+                rgb_wgrad_tile_kernel<TT, true><<<grid_t, 256, 0, s>>>((const TT*)f, img, acc, bsum, B, H, W, C, cimg, scale, TX);
+            else
+                rgb_wgrad_tile_kernel<TT, false><<<grid_t, 256, 0, s>>>((const TT*)f, img, acc, bsum, B, H, W, C, cimg, scale, TX);
+        };
+        if (dtype == PG_BF16) launch_t(__nv_bfloat16());
+        else if (dtype == PG_F16) launch_t(__half());
+        else launch_t(float());
+        PG_LAUNCH_CHECK();
+        g_other_launches++;
+        return PG_OK;
+    }
     const int TY = 256 / TX;
     long long ppb = (long long)TY * 16;                   // 16 pixels per thread
     long long blocks = (P + ppb - 1) / ppb;
@@ -562,11 +821,7 @@ extern "C" int pggan_rgb_wgrad(const void* f, const float* img, float* acc, floa
             return;
         }
         if (smem > 48 * 1024) {
-            static bool attr = false;        // per element type (the lambda body is instantiated per TT)
-            if (!attr) {
-                attr_err = cudaFuncSetAttribute(rgb_wgrad_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
-                attr = true;
-            }
+            attr_err = cudaFuncSetAttribute(rgb_wgrad_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
         }
         rgb_wgrad_kernel<TT><<<grid, 256, smem, s>>>((const TT*)f, img, acc, bsum, B, H, W, C, cimg, pool, scale, TX, ppb);
     };

@@ -443,8 +443,8 @@ static int launch_wg(const pg_wgrad_params* p, cudaStream_t stream) {
     CUtensorMap tg, tx;
     const int sw = sizeof(T) == 4 ? 12832 : 128;
     a.f16 = p->dtype == PG_F16;
-    a.xf16 = other_dtype(p->dtype, p->x_fmt) == PG_F16;
-    const int xdt = sizeof(T) == 4 ? PG_F32 : other_dtype(p->dtype, p->x_fmt);
+    a.xf16 = p->dtype == PG_F16;
+    const int xdt = sizeof(T) == 4 ? PG_F32 : p->dtype;
     a.span5d = (p->N % Cfg::CPS == 0 && p->C % Cfg::CPS == 0) ? 1 : 0;
     if (a.span5d) {
         // dims: (channel within span, w, h, b, span); the span stride is one 128-byte span
@@ -500,7 +500,7 @@ static int slices_wg(const pg_wgrad_params* p) {
 // (bf16 / IEEE half, possibly different: mixed precision) as run-time flags
 template <typename T>
 static int wgrad_simt(const pg_wgrad_params* p, cudaStream_t stream) {
-    const int gf16 = p->dtype == PG_F16, xf16 = other_dtype(p->dtype, p->x_fmt) == PG_F16;
+    const int gf16 = p->dtype == PG_F16, xf16 = p->dtype == PG_F16;
     // SIMT path: one slice, partial sums meet through atomics on a zeroed accumulator
     PG_CUDA(cudaMemsetAsync(p->acc, 0, sizeof(float) * (size_t)p->N * p->taps * p->C, stream));
     constexpr int VNT = 16 / sizeof(T);
@@ -601,8 +601,6 @@ extern "C" int pggan_conv_wgrad(const pg_wgrad_params* p, void* stream) {
              "pggan_conv_wgrad: bad dims B=%d H=%d W=%d C=%d N=%d", p->B, p->H, p->W, p->C, p->N);
     PG_CHECK(p->taps == 1 || p->taps == 9, PG_ERR_ARG, "pggan_conv_wgrad: taps must be 1 or 9 (got %d)", p->taps);
     PG_CHECK(p->dtype == PG_BF16 || p->dtype == PG_F16 || p->dtype == PG_F32, PG_ERR_ARG, "pggan_conv_wgrad: bad dtype %d", p->dtype);
-    PG_CHECK(p->x_fmt == 0 || (is16(p->dtype) && (p->x_fmt == PG_BF16 + 1 || p->x_fmt == PG_F16 + 1)), PG_ERR_ARG,
-             "pggan_conv_wgrad: bad x_fmt %d (mixed operand formats exist for the 16-bit types only)", p->x_fmt);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (is16(p->dtype)) return wgrad_dispatch<__nv_bfloat16>(p, s, nullptr);
     return wgrad_dispatch<float>(p, s, nullptr);

@@ -271,7 +271,7 @@ static int launch_wr(const pg_wgrad_params* p, cudaStream_t stream) {
     a.B = p->B; a.H = p->H; a.W = p->W; a.C = p->C; a.N = p->N;
     a.nseg = p->W / 128;
     a.f16 = p->dtype == PG_F16;
-    a.xf16 = other_dtype(p->dtype, p->x_fmt) == PG_F16;
+    a.xf16 = p->dtype == PG_F16;
     int grid;
     wr_plan(p, a.total, a.per_cta, grid);
     CUtensorMap tx, tg;
@@ -279,7 +279,7 @@ static int launch_wr(const pg_wgrad_params* p, cudaStream_t stream) {
         uint64_t dims[4] = {(uint64_t)p->C, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
         uint64_t strides[3] = {(uint64_t)p->C * 2, (uint64_t)p->W * p->C * 2, (uint64_t)p->H * p->W * p->C * 2};
         uint32_t box[4] = {(uint32_t)p->C, (uint32_t)Cfg::kXPW, 1u, 1u};
-        int rc = encode_tmap(&tx, other_dtype(p->dtype, p->x_fmt), 4, p->x, dims, strides, box, XSPAN);
+        int rc = encode_tmap(&tx, p->dtype, 4, p->x, dims, strides, box, XSPAN);
         if (rc != PG_OK) return rc;
     }
     {

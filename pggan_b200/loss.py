@@ -139,11 +139,12 @@ class WGANGPLoss(LossInterface):
         self.loss_dict["L_D"] = total
         return L_D
 
-    def get_gradient_penalty(self, D_dict, discriminator, backward=True, eps=None, lazy=False):
+    def get_gradient_penalty(self, D_dict, discriminator, backward=True, eps=None, lazy=False, loss_scale=1.0):
         """reference pggan/loss.py:54-92.  W_gp * sum_b (||grad_xhat D(xhat)_b||_2 - 1)^2 on
         xhat = eps*real + (1-eps)*fake, eps ~ U(0,1) per sample drawn on the CPU generator exactly where
         the reference draws it (pass `eps` [B,1] to supply it).  Back-propagates itself when
-        `backward`.  Returns the float the reference returns (or a 0-dim tensor if `lazy`)."""
+        `backward` (of loss_scale * penalty: the trainer's static loss scale; the returned value is unscaled).
+        Returns the float the reference returns (or a 0-dim tensor if `lazy`)."""
         gradient_penalty = None
         if self.args.W_gp:
             img_real, img_fake = D_dict["img_real"], D_dict["img_fake"]
@@ -156,17 +157,20 @@ class WGANGPLoss(LossInterface):
                 interpolates.requires_grad_(True)
             decisionInterpolate = discriminator(interpolates)
             decisionInterpolate = decisionInterpolate[:, 0].sum()
+            # half-precision gradient tensors: seed the first-order chain with a power of two instead of 1 (at 1024x1024
+            # the per-element gradients are ~1e-7, deep in fp16's subnormal range); the reduction divides it out
+            seed = 1024.0 if (interpolates.is_cuda and ops._REAL[ops._fmt(ops.G)] == torch.float16) else 1.0
             with ops.input_grad_only():
-                gradients = torch.autograd.grad(outputs=decisionInterpolate, inputs=interpolates, create_graph=True,
-                                                retain_graph=True)[0]
+                gradients = torch.autograd.grad(outputs=decisionInterpolate * seed if seed != 1.0 else decisionInterpolate,
+                                                inputs=interpolates, create_graph=True, retain_graph=True)[0]
             pred = D_dict.get("pred_real") if self.args.W_drift_D else None
             res = ops.GradientPenalty.apply(gradients, None if pred is None else pred[:, 0], float(self.args.W_gp),
-                                            float(self.args.W_drift_D or 0.0))
+                                            float(self.args.W_drift_D or 0.0), seed)
             gradient_penalty = res[0]
             self._last_gp = res[0].detach()
             self._fused_drift = res[1].detach() if pred is not None else None
             if backward:
-                gradient_penalty.backward(retain_graph=True)
+                (gradient_penalty * loss_scale if loss_scale != 1.0 else gradient_penalty).backward(retain_graph=True)
         if gradient_penalty is None:
             return None
         return gradient_penalty.detach() if lazy else gradient_penalty.item()

@@ -9,11 +9,20 @@ blends are linear, and minibatch-stddev has a true second-order kernel.
 Feature maps are channels_last tensors ([B,C,H,W] logical, NHWC physical); images/logits/parameters are fp32.
 
 Precision modes (set_compute_dtype):
-  "mixed" (default, the benchmarked mode)  ACTIVATIONS and packed weights are IEEE half (11-bit significand: meets
-          north_star's 1e-2 / 1e-3 bars), GRADIENT tensors are bf16 (fp32's exponent range: no loss scaling); the
-          tensor cores multiply the two directly (kind::f16, independent A/B operand formats), accumulate in fp32.
-          Conversions to half saturate at +-65504.
-  torch.bfloat16 / torch.float16           everything in that one 16-bit format
+  torch.float16 (default, the benchmarked mode)  activations, packed weights AND gradient tensors are IEEE half
+          (11-bit significand: meets north_star's 1e-2 image/logit and 1e-3 gradient-penalty bars with margin), fp32
+          accumulate and epilogues, conversions saturate at +-65504 (never inf).  Range: the trainer applies a STATIC
+          LOSS SCALE (trainer.ProgressiveGAN.loss_scale = 1024) that the fused Adam kernel divides out; the penalty's
+          first-order chain is seeded with 1 and is kept near unit norm by the penalty itself.
+  "mixed"  ACTIVATIONS and packed weights are IEEE half (11-bit significand: meets
+          north_star's 1e-2 / 1e-3 bars), GRADIENT tensors are bf16 (fp32's exponent range: no loss scaling), fp32
+          accumulate.  tcgen05.mma kind::f16 wants BOTH operands in one format (a bf16 x fp16 instruction descriptor
+          faults: measured, tools/probe_mixed.py), so every GEMM runs in the format of its activation/gradient operand:
+          forward fp16 x fp16; dgrad and the double backward's fprop bf16 x bf16 (the weights have a second, bf16
+          packed copy); wgrad bf16 x bf16 with the saved activation re-rounded to bf16 on the way in (pggan_convert).
+          No loss scaling needed, but the bf16 rounding of the penalty's first-order gradient chain leaves the GP value
+          at 1e-3..2e-3 where ||grad|| is near 1 (measured), and the conversions cost ~4 % of a 256x256 step.
+  torch.bfloat16                           everything bf16
   torch.float32                            3xTF32 operands, fp32 accumulate: the parity mode
 
 Two tensor CLASSES therefore exist: "a" (activation-like: produced by a forward pass) and "g" (gradient-like: produced
@@ -36,9 +45,9 @@ from . import _lib as L
 
 A, G = "a", "g"                # tensor classes, see the module docstring
 MIXED = "mixed"
-_MODE = MIXED
-_COMPUTE_DTYPE = torch.bfloat16          # torch label of 16-bit feature tensors == real format of the gradient class
-_ACT_FMT, _GRAD_FMT = L.PG_F16, L.PG_BF16
+_MODE = "fp16"
+_COMPUTE_DTYPE = torch.float16           # torch label of 16-bit feature tensors == real format of the gradient class
+_ACT_FMT, _GRAD_FMT = L.PG_F16, L.PG_F16
 _REAL = {L.PG_BF16: torch.bfloat16, L.PG_F16: torch.float16, L.PG_F32: torch.float32}
 _SKIP_PARAM_GRADS = False      # see input_grad_only()
 PROFILE = None                 # bench.py sets a dict: (kind, shape) -> [(start_event, end_event), ...]
@@ -64,8 +73,8 @@ class _Timed:
 
 
 def set_compute_dtype(dtype) -> None:
-    """"mixed" (fp16 activations/weights, bf16 gradients — the default), torch.bfloat16, torch.float16 (one 16-bit
-    format for everything; same kernels and speed) or torch.float32 (3xTF32 operands: the parity mode)."""
+    """torch.float16 (the default), "mixed" (fp16 activations/weights, bf16 gradients), torch.bfloat16 (same kernels
+    and speed, 8-bit significand) or torch.float32 (3xTF32 operands: the parity mode)."""
     global _COMPUTE_DTYPE, _ACT_FMT, _GRAD_FMT, _MODE
     if dtype == MIXED:
         _MODE, _COMPUTE_DTYPE, _ACT_FMT, _GRAD_FMT = MIXED, torch.bfloat16, L.PG_F16, L.PG_BF16
@@ -353,13 +362,15 @@ def _packmap(args):
     return m
 
 
-def _pack(W: torch.Tensor, kind: str, dtype=None, layout=None) -> torch.Tensor:
-    """fp32 parameter -> K-major packed operand in the ACTIVATION format (weights are O(1) numbers: fp16 in mixed mode);
+def _pack(W: torch.Tensor, kind: str, dtype=None, layout=None, fmt=None) -> torch.Tensor:
+    """fp32 parameter -> K-major packed operand in element format `fmt` (default: the activation format; a dgrad /
+    double-backward GEMM asks for the gradient format — both operands of a tensor-core GEMM share one format);
     kind 'f' = fprop [N][taps*C], 't' = dgrad [C][taps*N] with the taps reversed.  Cached per (parameter, version) for
     nn.Parameters.  (`dtype` is accepted for compatibility and ignored: the precision mode decides.)"""
     _need_cuda(W)
+    fmt = _ACT_FMT if fmt is None else fmt
     cacheable = isinstance(W, torch.nn.Parameter)
-    key = (id(W), W._version, kind, _ACT_FMT, layout) if cacheable else None
+    key = (id(W), W._version, kind, fmt, layout) if cacheable else None
     if cacheable:
         hit = _PACK_CACHE.get(key)
         if hit is not None and hit[0] is W:
@@ -371,11 +382,21 @@ def _pack(W: torch.Tensor, kind: str, dtype=None, layout=None) -> torch.Tensor:
     args = fmap if kind == "f" else tmap
     out = torch.empty((args[0], args[3] * args[4]), dtype=_COMPUTE_DTYPE, device=W.device)
     m = _packmap(args)
-    L.check(L.load().pggan_pack_weight(_p(Wc), _p(out), _ACT_FMT, ctypes.byref(m), _s()), "pggan_pack_weight")
+    L.check(L.load().pggan_pack_weight(_p(Wc), _p(out), fmt, ctypes.byref(m), _s()), "pggan_pack_weight")
     if cacheable:
         if len(_PACK_CACHE) > 1024:
             _PACK_CACHE.clear()
         _PACK_CACHE[key] = (W, out)
+    return out
+
+
+def k_convert(x: torch.Tensor, from_fmt: int, to_fmt: int) -> torch.Tensor:
+    """the same values in another element format (same torch label for the 16-bit formats)"""
+    if from_fmt == to_fmt:
+        return x
+    out_dtype = torch.float32 if to_fmt == L.PG_F32 else (_COMPUTE_DTYPE if _COMPUTE_DTYPE != torch.float32 else _REAL[to_fmt])
+    out = torch.empty_like(x, dtype=out_dtype)
+    L.check(L.load().pggan_convert(_p(x), _p(out), x.numel(), from_fmt, to_fmt, _s()), "pggan_convert")
     return out
 
 
@@ -392,11 +413,6 @@ def clear_pack_cache(params=None):
 
 # ------------------------------------------------------------------------------- raw kernels
 _KIND_CACHE: dict = {}
-
-
-def _other(fmt_main: int, fmt_other: int) -> int:
-    """the `w_fmt` / `x_fmt` field: 0 = same as dtype, else PG_* + 1"""
-    return 0 if fmt_main == fmt_other else fmt_other + 1
 
 
 def conv_pn_fusable(x, N, taps) -> bool:
@@ -416,7 +432,7 @@ def conv_pn_fusable(x, N, taps) -> bool:
 
 def k_conv(x, wp, bias, N, taps, scale, slope=1.0, mask_src=None, mask_slope=1.0, raw_out=False, pn_eps=None, xc=A):
     """pn_eps: also apply the pixel norm in the epilogue; returns (y, rnorm[pixels] fp32) then.
-    xc: class of x (and of y); wp is always in the activation format."""
+    xc: class of x (and of y); wp must be packed in the same element format (_pack(..., fmt=_fmt(xc)))."""
     _need_cuda(x)
     b, c, h, w = _dims(x)
     xf = _fmt(xc)
@@ -431,7 +447,6 @@ def k_conv(x, wp, bias, N, taps, scale, slope=1.0, mask_src=None, mask_slope=1.0
         (mask_src.data_ptr() if mask_src is not None else None), y.data_ptr()
     p.B, p.H, p.W, p.C, p.N, p.taps = b, h, w, c, N, taps
     p.dtype = xf
-    p.w_fmt = _other(xf, _ACT_FMT)
     p.out_dtype = L.PG_F32_RAW if raw_out else xf
     p.scale, p.slope, p.mask_slope = float(scale), float(slope), float(mask_slope)
     ws = None
@@ -462,7 +477,7 @@ def dgrad_mask_fusable(batch, h, w, fwd_in_channels, fwd_out_channels, taps=9, d
 
 def k_wgrad(g, x, scale, wshape, layout=None, accumulate_into=None, xc=A):
     """weight gradient in the parameter's own fp32 layout: a new tensor, or added into `accumulate_into`.
-    g is a gradient-class tensor, x of class `xc`."""
+    g is a gradient-class tensor, x of class `xc` (converted to the gradient format when that differs)."""
     _need_cuda(g)
     b, n, h, w = _dims(g)
     c = _dims(x)[1]
@@ -473,7 +488,10 @@ def k_wgrad(g, x, scale, wshape, layout=None, accumulate_into=None, xc=A):
     p.g, p.x = g.data_ptr(), x.data_ptr()
     p.B, p.H, p.W, p.C, p.N, p.taps = b, h, w, c, n, taps
     p.dtype = _GRAD_FMT
-    p.x_fmt = _other(_GRAD_FMT, _fmt(xc))
+    if _fmt(xc) != _GRAD_FMT:
+        # both GEMM operands must share one element format: the saved fp16 activation is re-rounded to bf16
+        x = k_convert(x, _fmt(xc), _GRAD_FMT)
+    p.x = x.data_ptr()
     slices = L.load().pggan_conv_wgrad_slices(ctypes.byref(p))
     acc = torch.empty((slices, n, taps, c), dtype=torch.float32, device=g.device)
     p.acc = acc.data_ptr()
@@ -600,7 +618,7 @@ class ConvF(torch.autograd.Function):
         x = feat(x, xc)
         N, C, taps, _, _ = _maps(W.shape, layout)
         bias = None if b is None else _perm_bias(b.detach().float(), layout).contiguous()
-        y = k_conv(x, _pack(W, "f", None, layout), bias, N, taps, scale, slope, raw_out=raw_out, xc=xc)
+        y = k_conv(x, _pack(W, "f", None, layout, _fmt(xc)), bias, N, taps, scale, slope, raw_out=raw_out, xc=xc)
         ctx.mask_here = slope != 1.0 and not defer_mask
         ctx.save_for_backward(x, W, y if ctx.mask_here else None)
         ctx.scale, ctx.slope, ctx.has_bias, ctx.layout = scale, slope, b is not None, layout
@@ -697,7 +715,7 @@ class ConvActPN(torch.autograd.Function):
         gx = gW = None
         if ctx.needs_input_grad[0]:
             N, C, taps, _, _ = _maps(W.shape, ctx.layout)
-            gx = k_conv(g, _pack(W, "t", None, ctx.layout), None, C, taps, ctx.scale, xc=G)
+            gx = k_conv(g, _pack(W, "t", None, ctx.layout, _GRAD_FMT), None, C, taps, ctx.scale, xc=G)
         if ctx.needs_input_grad[1] and not _SKIP_PARAM_GRADS:
             w_sink = _sink(ctx.w_param)
             gW = k_wgrad(g, x, ctx.scale, tuple(W.shape), ctx.layout, accumulate_into=w_sink, xc=A)
@@ -719,8 +737,8 @@ class ConvT(torch.autograd.Function):
         (the LeakyReLU backward of the layer that produced this conv's input)."""
         g = feat(g, G)
         N, C, taps, _, _ = _maps(W.shape, layout)
-        gx = k_conv(g, _pack(W, "t", None, layout), None, C, taps, scale, mask_src=mask_src, mask_slope=mask_slope,
-                    xc=G)
+        gx = k_conv(g, _pack(W, "t", None, layout, _GRAD_FMT), None, C, taps, scale, mask_src=mask_src,
+                    mask_slope=mask_slope, xc=G)
         ctx.save_for_backward(g, W, mask_src)
         ctx.scale, ctx.layout, ctx.mask_slope = scale, layout, mask_slope
         return gx
@@ -1186,10 +1204,12 @@ class RowsSumSq(torch.autograd.Function):
 
 class GradientPenalty(torch.autograd.Function):
     """w_gp * sum_b (||g_b||_2 - 1)^2 and, fused, w_drift * sum_b pred_b^2 (value only)
-    (reference pggan/loss.py:85-87, 98-100).  Returns a 2-vector [gp, drift]."""
+    (reference pggan/loss.py:85-87, 98-100).  Returns a 2-vector [gp, drift].
+    seed_scale: g is seed_scale times the true gradient (the first-order chain was seeded with seed_scale instead of 1
+    to keep its half-precision tensors in the normal range); the norm is taken of g / seed_scale."""
 
     @staticmethod
-    def forward(ctx, g, pred, w_gp, w_drift):
+    def forward(ctx, g, pred, w_gp, w_drift, seed_scale=1.0):
         g = _img(g)
         _need_cuda(g)
         B = g.shape[0]
@@ -1199,9 +1219,13 @@ class GradientPenalty(torch.autograd.Function):
         res = torch.empty((2,), dtype=torch.float32, device=g.device)
         pr = None if pred is None else pred.detach().float().contiguous()
         L.check(L.load().pggan_rows_sumsq(_p(g), _p(sumsq), B, n, _s()), "pggan_rows_sumsq")
+        inv2 = 1.0 / (float(seed_scale) * float(seed_scale))
+        if inv2 != 1.0:
+            sumsq.mul_(inv2)
         L.check(L.load().pggan_gp_finalize(_p(sumsq), _p(pr), _p(res), _p(coef), B, float(w_gp), float(w_drift), _s()),
                 "pggan_gp_finalize")
         ctx.save_for_backward(g, coef)
+        ctx.inv2 = inv2
         return res
 
     @staticmethod
@@ -1209,7 +1233,7 @@ class GradientPenalty(torch.autograd.Function):
     def backward(ctx, gres):
         g, coef = ctx.saved_tensors
         B = g.shape[0]
-        c = (coef * gres[0]).contiguous()
+        c = (coef * gres[0] * ctx.inv2).contiguous()          # d/dg of f(||g/s||): coef(||g/s||) * (g/s) / s
         out = torch.empty_like(g)
         L.check(L.load().pggan_rows_scale(_p(g), _p(c), _p(out), B, g.numel() // B, _s()), "pggan_rows_scale")
-        return out, None, None, None
+        return out, None, None, None, None

@@ -62,6 +62,9 @@ class ProgressiveGAN:
             data_parallel = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         self.data_parallel = data_parallel
         self.world = dist.get_world_size() if data_parallel else 1
+        # static loss scale for the half-precision gradient tensors: both losses (and the penalty's own backward) are
+        # multiplied by it, the fused Adam kernel divides it out together with the 1/world of the gradient mean
+        self.loss_scale = 1024.0 if ops._REAL[ops._fmt(ops.G)] == torch.float16 else 1.0
         self.bucket_bytes = bucket_bytes
         self.initialize_models()
         self.set_multi_GPU()
@@ -93,7 +96,7 @@ class ProgressiveGAN:
         for p in list(self.G.parameters()) + list(self.D.parameters()):
             p.grad = None
         gG, gD = FlatGrads(self.G.live_parameters()), FlatGrads(self.D.live_parameters())
-        scale = 1.0 / self.world
+        scale = 1.0 / (self.world * self.loss_scale)
         self.opt_G = FusedAdam(gG, lr=a.lr_G, betas=(float(a.beta1), float(a.beta2)), grad_scale=scale,
                                all_params=self.G.parameters())
         self.opt_D = FusedAdam(gD, lr=a.lr_D, betas=(float(a.beta1), float(a.beta2)), grad_scale=scale,
@@ -239,11 +242,12 @@ class ProgressiveGAN:
             if self.variant == "L":
                 loss_D = lc.get_loss_D(D_dict)
             else:
-                lc.get_gradient_penalty(D_dict, self.D, backward=True, eps=eps, lazy=True)   # accumulates into D.grad
+                lc.get_gradient_penalty(D_dict, self.D, backward=True, eps=eps, lazy=True,
+                                        loss_scale=self.loss_scale)                  # accumulates into D.grad
                 loss_D = lc.get_loss_D_wgangp_terms(D_dict)
             if self.sync_D is not None:
                 self.sync_D.arm()
-            loss_D.backward()
+            (loss_D * self.loss_scale if self.loss_scale != 1.0 else loss_D).backward()
             if self.sync_D is not None:
                 self.sync_D.finish()
         self.opt_D.step()
@@ -264,7 +268,7 @@ class ProgressiveGAN:
             with ops.grad_sink():
                 if self.sync_G is not None:
                     self.sync_G.arm()
-                loss_G.backward()
+                (loss_G * self.loss_scale if self.loss_scale != 1.0 else loss_G).backward()
                 if self.sync_G is not None:
                     self.sync_G.finish()
         finally:

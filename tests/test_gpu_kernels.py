@@ -46,7 +46,7 @@ def _setup():
     from pggan_b200 import _lib
     _lib.load().pggan_set_conv_backend(0)
     import pggan_b200 as pg
-    pg.set_compute_dtype("mixed")
+    pg.set_compute_dtype(torch.float16)
 
 
 def rnd(t, dtype, cls="a"):
@@ -191,7 +191,9 @@ def test_conv_dgrad_wgrad(shape, backend, dtype):
         y = ops.ConvF.apply(xm, wm, bm, scale, 1.0, False)
         y.backward(to_feat(gy, dtype, "g"))
     assert rel_l2(xm.grad, xr.grad) < TOL[dtype], ("dgrad", rel_l2(xm.grad, xr.grad))
-    assert rel_l2(wm.grad, wr.grad) < 2e-4, ("wgrad", rel_l2(wm.grad, wr.grad))
+    # (mixed mode: the fp16 activation operand of the weight-gradient GEMM is re-rounded to bf16 — both tensor-core
+    # operands must share one format — so the weight gradient carries bf16's input rounding)
+    assert rel_l2(wm.grad, wr.grad) < (4e-3 if dtype == "mixed" else 2e-4), ("wgrad", rel_l2(wm.grad, wr.grad))
     assert rel_l2(bm.grad, br.grad) < 1e-4, ("bias", rel_l2(bm.grad, br.grad))
 
 
@@ -375,7 +377,7 @@ def test_mbstd(B, group, dtype):
     u = torch.randn_like(x)
     (g_ref * u).sum().backward()
     xm = x.clone().requires_grad_()
-    s = ops.MbstdStat.apply(xm, group)
+    s = ops.MbstdStat.apply(to_feat(xm, dtype), group)
     (g_my,) = torch.autograd.grad((s * wgt).sum(), xm, create_graph=True)
     (g_my.float() * u).sum().backward()
     assert rel_l2(s, s_ref) < 1e-4

@@ -191,9 +191,11 @@ def test_precision_modes_and_tensor_classes():
     import pggan_b200 as pg
     from pggan_b200 import ops, _lib as L
     try:
-        assert ops.get_precision_mode() == "mixed"                  # the default and benchmarked mode
-        assert ops.get_compute_dtype() == torch.bfloat16
-        assert ops._fmt("a") == L.PG_F16 and ops._fmt("g") == L.PG_BF16
+        assert ops.get_precision_mode() == "fp16"                   # the default and benchmarked mode
+        assert ops.get_compute_dtype() == torch.float16
+        assert ops._fmt("a") == L.PG_F16 and ops._fmt("g") == L.PG_F16
+        pg.set_compute_dtype("mixed")
+        assert ops.get_compute_dtype() == torch.bfloat16 and ops._fmt("a") == L.PG_F16 and ops._fmt("g") == L.PG_BF16
         for dt, fa in ((torch.bfloat16, L.PG_BF16), (torch.float16, L.PG_F16), (torch.float32, L.PG_F32)):
             pg.set_compute_dtype(dt)
             assert ops.get_compute_dtype() == dt and ops._fmt("a") == fa and ops._fmt("g") == fa
@@ -211,4 +213,4 @@ def test_precision_modes_and_tensor_classes():
         c = ops._coef(ops._affine(1.0, -1.0, 0.25))
         assert abs(c.c0 - 0.75) < 1e-7 and c.c1 == 0.0 and not c.alpha
     finally:
-        pg.set_compute_dtype("mixed")
+        pg.set_compute_dtype(torch.float16)

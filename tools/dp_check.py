@@ -21,7 +21,7 @@ import pggan_b200 as pg  # noqa: E402
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-pg.set_compute_dtype("mixed")
+pg.set_compute_dtype(torch.float16)
 torch.manual_seed(0)
 width, scale, B = 64, 3, 8
 res = 4 * 2 ** scale

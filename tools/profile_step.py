@@ -15,7 +15,7 @@ from bench import WORKLOADS  # noqa: E402
 mode = sys.argv[1] if len(sys.argv) > 1 else "graph"
 workload = sys.argv[2] if len(sys.argv) > 2 else "c2_32x32_b64_fade"
 scale, B, depths, _ = WORKLOADS[workload]
-pg.set_compute_dtype("mixed")
+pg.set_compute_dtype(torch.float16)
 torch.manual_seed(0)
 tr = pg.ProgressiveGAN(pg.make_args(latent_dim=512, depths=depths), 0, variant="W")
 tr.set_scale(scale, 0.5 if scale else 0.0)
