@@ -246,6 +246,12 @@ typedef struct {
     float* exp_avg;
     float* exp_avg_sq;
     int64_t numel;
+    /* optional 16-bit copy of the updated parameter, same element order (NULL: none), written in the same pass: the
+     * tensor cores' packed fprop operand of a conv weight stored [O][kh][kw][I] (channels_last) IS that copy, so the
+     * fp32 -> fp16/bf16 re-pack of lib/model.py:95-97's update costs no extra pass */
+    void* shadow;
+    int32_t shadow_dtype; /* PG_BF16 / PG_F16 */
+    int32_t pad_;
 } pg_adam_entry;
 int pggan_adam_chunk_size(void); /* elements handled per chunk-table entry */
 int pggan_adam_step(const pg_adam_entry* table, int n_tensors, int64_t total_chunks, const int32_t* chunk_tensor,

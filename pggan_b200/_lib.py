@@ -50,7 +50,7 @@ class Coef(Structure):
 
 class AdamEntry(Structure):
     _fields_ = [("param", c_void_p), ("grad", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p),
-                ("numel", c_int64)]
+                ("numel", c_int64), ("shadow", c_void_p), ("shadow_dtype", c_int32), ("pad_", c_int32)]
 
 
 # name -> (restype, argtypes); exactly the symbols include/pggan_b200.h declares

@@ -564,6 +564,48 @@ __global__ void __launch_bounds__(256) pack_oihw_t_kernel(const float* __restric
     }
 }
 
+// ------------------------------------------------------------------------------ channels_last (OHWI) weights
+// A 3x3 conv weight kept in torch.channels_last memory format is physically [O][kh][kw][I] = the packed fprop operand
+// [n][t][c] itself: the fprop pack is a cast (fused into the Adam kernel), the weight gradient un-pack a plain sum of
+// the split-K slices.  Only the dgrad operand [i][8-t][o] needs a transpose: one 32x32 tile per block through smem.
+template <typename T>
+__global__ void __launch_bounds__(256) pack_ohwi_t_kernel(const float* __restrict__ W, T* __restrict__ out, int O, int I,
+                                                          int Ip, int taps) {
+    __shared__ float tile[32][33];
+    const int t = blockIdx.z, i0 = blockIdx.x * 32, o0 = blockIdx.y * 32;
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;           // 32 x 8
+#pragma unroll
+    for (int r = ly; r < 32; r += 8) {                                 // read W[o0+r][t][i0+lx] (i contiguous)
+        const int o = o0 + r, i = i0 + lx;
+        tile[r][lx] = (o < O && i < I) ? __ldg(W + (static_cast<size_t>(o) * taps + t) * I + i) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ly; r < 32; r += 8) {                                 // write out[i0+r][taps-1-t][o0+lx] (o contiguous)
+        const int i = i0 + r, o = o0 + lx;
+        if (i < Ip && o < O) out[(static_cast<size_t>(i) * taps + (taps - 1 - t)) * O + o] = DT<T>::from_f(tile[lx][r]);
+    }
+}
+
+// gW[k] (+)= scale * sum_s acc[s][k]  for a dense [N][taps][C] slice layout that equals the gradient's own layout
+__global__ void __launch_bounds__(256) unpack_dense_kernel(const float* __restrict__ acc, float* __restrict__ gW,
+                                                           long long n4, float scale, int accumulate, int slices,
+                                                           long long slice_elems) {
+    GRID_STRIDE(i, n4) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(acc) + i);
+        for (int sl = 1; sl < slices; ++sl) {
+            const float4 u = __ldg(reinterpret_cast<const float4*>(acc + sl * slice_elems) + i);
+            v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+        }
+        v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+        if (accumulate) {
+            const float4 u = reinterpret_cast<const float4*>(gW)[i];
+            v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+        }
+        reinterpret_cast<float4*>(gW)[i] = v;
+    }
+}
+
 // ------------------------------------------------------------------------------ format conversion
 template <typename TI, typename TO>
 __global__ void convert_kernel(const TI* __restrict__ in, TO* __restrict__ out, long long n) {
@@ -954,7 +996,15 @@ extern "C" int pggan_pack_weight(const float* in, void* out, int dtype, const pg
                         m.s_n1 == 9LL * m.c_valid && m.n_valid == m.n_total && m.c_total <= kPackMaxI;
     const bool oihw_t = m.taps == 9 && m.n2 == 1 && m.c2 == 1 && m.base == 8 && m.s_t == -1 && m.s_n1 == 9 &&
                         m.s_c1 == 9LL * m.n_valid && m.c_valid == m.c_total && m.c_total % 64 == 0;
-    if (oihw_f) {
+    // channels_last parameter, dgrad operand: out[i][T-1-t][o] = W[o][t][i]
+    const bool ohwi_t = m.taps > 1 && m.n2 == 1 && m.c2 == 1 && m.s_n1 == 1 && m.s_t == -(long long)m.n_valid && m.c_valid == m.c_total &&
+                        m.s_c1 == (long long)m.taps * m.n_valid && m.base == (long long)(m.taps - 1) * m.n_valid;
+    if (ohwi_t) {
+        DISPATCH_T(dtype, {
+            pack_ohwi_t_kernel<T><<<dim3((m.n_total + 31) / 32, (m.c_total + 31) / 32, m.taps), 256, 0, s>>>(
+                in, (T*)out, m.c_total, m.n_valid, m.n_total, m.taps);
+        });
+    } else if (oihw_f) {
         DISPATCH_T(dtype, {
             pack_oihw_f_kernel<T><<<m.n_total, 256, 9 * m.c_valid * sizeof(float), s>>>(in, (T*)out, m.c_valid, m.c_total);
         });
@@ -982,7 +1032,14 @@ extern "C" int pggan_unpack_wgrad(const float* in, float* out, const pg_pack_map
     const bool oihw_f = m.taps == 9 && m.n2 == 1 && m.c2 == 1 && m.base == 0 && m.s_t == 1 && m.s_c1 == 9 &&
                         m.s_n1 == 9LL * m.c_valid && m.n_valid == m.n_total && m.c_total <= kPackMaxI;
     const long long slice_elems = (long long)m.n_total * m.taps * m.c_total;
-    if (oihw_f) {
+    // the gradient's own layout is the slice layout (channels_last conv weight, plain [out,in] linear weight)
+    const bool dense = m.n2 == 1 && m.c2 == 1 && m.base == 0 && m.s_c1 == 1 && (m.taps == 1 || m.s_t == (long long)m.c_total) &&
+                       m.s_n1 == (long long)m.taps * m.c_total && m.n_valid == m.n_total && m.c_valid == m.c_total &&
+                       slice_elems % 4 == 0 && al16(in) && al16(out);
+    if (dense) {
+        unpack_dense_kernel<<<ew_grid(slice_elems / 4, 256), 256, 0, s>>>(in, out, slice_elems / 4, scale, accumulate, slices,
+                                                                          slice_elems);
+    } else if (oihw_f) {
         int zchunks = 1;                 // channel chunks of >= 128 (a multiple of 4 keeps the float4 path)
         while (zchunks < 4 && m.c_valid / (zchunks * 2) >= 128 && m.c_valid % (zchunks * 2 * 4) == 0) zchunks *= 2;
         // few output rows but several slices (narrow layers: ncu showed 64 blocks summing 29 slices in 38 us): split

@@ -84,7 +84,10 @@ __global__ void adam_kernel(const pg_adam_entry* __restrict__ table, const int32
         p = p - step_size * (m / denom);
     };
     const bool vec = ((reinterpret_cast<uintptr_t>(e.param) | reinterpret_cast<uintptr_t>(e.grad) |
-                       reinterpret_cast<uintptr_t>(e.exp_avg) | reinterpret_cast<uintptr_t>(e.exp_avg_sq)) & 15) == 0;
+                       reinterpret_cast<uintptr_t>(e.exp_avg) | reinterpret_cast<uintptr_t>(e.exp_avg_sq)) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(e.shadow) & 7) == 0;
+    uint16_t* sh = reinterpret_cast<uint16_t*>(e.shadow);        // packed 16-bit copy of the new value (may be NULL)
+    const bool sh_f16 = e.shadow_dtype == PG_F16;
     int64_t i0 = off;
     if (vec) {                                        // chunk offsets are multiples of 4 elements
         const int64_t vend = off + ((end - off) & ~int64_t(3));
@@ -100,6 +103,8 @@ __global__ void adam_kernel(const pg_adam_entry* __restrict__ table, const int32
             *reinterpret_cast<float4*>(e.param + i) = p;
             *reinterpret_cast<float4*>(e.exp_avg + i) = m;
             *reinterpret_cast<float4*>(e.exp_avg_sq + i) = v;
+            if (sh != nullptr)
+                *reinterpret_cast<uint2*>(sh + i) = make_uint2(pack16(p.x, p.y, sh_f16), pack16(p.z, p.w, sh_f16));
         }
         i0 = vend;
     }
@@ -109,6 +114,7 @@ __global__ void adam_kernel(const pg_adam_entry* __restrict__ table, const int32
         e.param[i] = p;
         e.exp_avg[i] = m;
         e.exp_avg_sq[i] = v;
+        if (sh != nullptr) sh[i] = cvt16(p, sh_f16);
     }
 }
 __global__ void adam_incr_step_kernel(int64_t* step) { *step += 1; }

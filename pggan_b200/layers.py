@@ -47,6 +47,12 @@ class ConstrainedLayer(nn.Module):
             self.module.weight.data.normal_(0, 1)
             self.module.weight.data /= lrMul
             self.weight = getLayerNormalizationFactor(self.module) * lrMul
+        if isinstance(module, nn.Conv2d) and module.kernel_size == (3, 3):
+            # Memory format only: the 3x3 weight is kept channels_last, i.e. physically [O][kh][kw][I] — the K-major
+            # operand the tensor cores consume — while shape, values, state_dict keys and checkpoints stay OIHW.  The
+            # packed fprop copy is then an elementwise cast (written by the fused Adam kernel) and weight gradients land
+            # in the parameter's own layout without a transpose.
+            self.module.weight.data = self.module.weight.data.contiguous(memory_format=torch.channels_last)
 
     # -- fused entry used by blocks / nets: lrelu(c * (W x + b), slope) in one kernel ------------
     def scale(self) -> float:

@@ -25,6 +25,13 @@ Precision modes (set_compute_dtype):
   torch.bfloat16                           everything bf16
   torch.float32                            3xTF32 operands, fp32 accumulate: the parity mode
 
+fp32 islands: in the 16-bit modes the NARROW END of both networks — 4x4 feature maps and the 2-D features of the three
+linear layers, < 0.3 % of the FLOPs — stays fp32 (3xTF32 GEMMs).  Every rounding and every LeakyReLU-mask flip there
+acts coherently on the WHOLE image gradient (at 4x4 it has 48 elements per sample and ||grad|| ~ 0.8, where
+GP = 10*(||g||-1)^2 amplifies a norm error 8x: measured 2.6e-3..6e-3 GP error with a 16-bit tail against 1e-3 asked).
+The rule is stateless — a Function computes in fp32 iff its feature tensor is "small" (_small) — so forward, backward
+and double backward agree without bookkeeping; autograd's own dtype checks cast at the island's edge.
+
 Two tensor CLASSES therefore exist: "a" (activation-like: produced by a forward pass) and "g" (gradient-like: produced
 by a backward pass, including everything the double backward derives from gradients).  Every 16-bit feature tensor
 carries the torch dtype of the GRADIENT class (`get_compute_dtype()`), so autograd's own gradient accumulation and
@@ -170,7 +177,8 @@ def _sink(p):
     if ref is None or ref() is not p:
         return None
     g = p.grad
-    if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.shape != p.shape:
+    if g is None or g.dtype != torch.float32 or g.shape != p.shape or g.stride() != p.stride() or \
+            not (g.is_contiguous() or is_ohwi(g)):
         return None
     return g
 
@@ -216,9 +224,49 @@ class _Import(torch.autograd.Function):
         return g.to(ctx.dtype), None
 
 
-def feat(x: torch.Tensor, cls: str = A) -> torch.Tensor:
-    """feature tensor of class `cls` in the kernels' layout.  A tensor that already carries the feature dtype is
-    trusted to BE of that class; anything else (fp32 inputs, honest fp16 in mixed mode) is converted."""
+SMALL_HW = 16            # feature maps with H*W <= this (4x4) and all 2-D features are fp32 islands in the 16-bit modes
+F32_ISLANDS = True
+
+
+def _small_hw(h: int, w: int) -> bool:
+    return F32_ISLANDS and h * w <= SMALL_HW
+
+
+def _small(x: torch.Tensor) -> bool:
+    return F32_ISLANDS and (x.dim() == 2 or (x.dim() == 4 and x.shape[-1] * x.shape[-2] <= SMALL_HW))
+
+
+def _fmt_of(x: torch.Tensor, cls: str) -> int:
+    """element format of a feature tensor: fp32 tensors are fp32 (an island, or the fp32 mode), 16-bit ones carry the
+    format of their class"""
+    return L.PG_F32 if x.dtype == torch.float32 else _fmt(cls)
+
+
+class _ToF32(torch.autograd.Function):
+    """internal 16-bit feature tensor -> fp32 (entering an fp32 island outside a Function, mixed mode)"""
+
+    @staticmethod
+    def forward(ctx, x, cls):
+        return to_float(x, cls)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(_COMPUTE_DTYPE), None
+
+
+def feat(x: torch.Tensor, cls: str = A, small=None) -> torch.Tensor:
+    """feature tensor of class `cls` in the kernels' layout and precision: fp32 if the tensor is small (an fp32 island;
+    `small` overrides the decision, e.g. for the partner of a larger tensor) or the mode is fp32, else the 16-bit
+    format of its class.  A tensor that already carries the feature dtype is trusted to BE of that class."""
+    if small is None:
+        small = _small(x)
+    if small or _COMPUTE_DTYPE == torch.float32:
+        if x.dtype != torch.float32:
+            if x.dtype == _COMPUTE_DTYPE and _REAL[_fmt(cls)] != _COMPUTE_DTYPE:      # mixed mode: relabelled bits
+                x = _ToF32.apply(x, cls) if (torch.is_grad_enabled() and x.requires_grad) else to_float(x, cls)
+            else:
+                x = x.float()
+        return cl(x)
     if x.dtype != _COMPUTE_DTYPE:
         real = _REAL[_fmt(cls)]
         if real == _COMPUTE_DTYPE:
@@ -330,19 +378,28 @@ def _new_like_layout(x: torch.Tensor, channels: int, dtype: torch.dtype, h=None,
 _PACK_CACHE: dict = {}
 
 
-def _maps(wshape, layout):
+def is_ohwi(W: torch.Tensor) -> bool:
+    """a 4-D weight kept in torch.channels_last memory format: physically [O][kh][kw][I] (layers.py stores the 3x3 conv
+    weights that way; the logical shape, state_dict values and checkpoints stay OIHW)"""
+    return W.dim() == 4 and W.shape[2] * W.shape[3] > 1 and not W.is_contiguous() and \
+        W.is_contiguous(memory_format=torch.channels_last)
+
+
+def _maps(wshape, layout, ohwi=False):
     """-> (N, C, taps, fmap, tmap): logical dims of the fprop GEMM and the pg_pack_map argument tuples
     (n_total, n_valid, n2, taps, c_total, c_valid, c2, base, s_n1, s_n2, s_t, s_c1, s_c2) for the
-    fprop operand [N][taps][C] and the dgrad operand [C][taps][N] (taps reversed)."""
+    fprop operand [N][taps][C] and the dgrad operand [C][taps][N] (taps reversed).
+    ohwi: the parameter memory is [O][taps][I] (channels_last) instead of [O][I][taps]."""
     O, I = int(wshape[0]), int(wshape[1])
     T = 1
     for d in wshape[2:]:
         T *= int(d)
     kind = layout[0] if layout else "oihw"
-    if kind == "oihw":
-        return O, I, T, (O, O, 1, T, I, I, 1, 0, I * T, 0, 1, T, 0), (I, I, 1, T, O, O, 1, T - 1, T, 0, -1, I * T, 0)
-    if kind == "pad_c":
-        Cp = int(layout[1])
+    if kind in ("oihw", "pad_c"):
+        Cp = int(layout[1]) if kind == "pad_c" else I
+        if ohwi:      # off(o, t, i) = o*T*I + t*I + i
+            return O, Cp, T, (O, O, 1, T, Cp, I, 1, 0, I * T, 0, I, 1, 0), \
+                (Cp, I, 1, T, O, O, 1, (T - 1) * I, 1, 0, -I, I * T, 0)
         return O, Cp, T, (O, O, 1, T, Cp, I, 1, 0, I * T, 0, 1, T, 0), (Cp, I, 1, T, O, O, 1, T - 1, T, 0, -1, I * T, 0)
     if kind == "lin_out_perm":
         C0 = int(layout[1])
@@ -362,25 +419,62 @@ def _packmap(args):
     return m
 
 
+# Packed copies that somebody else keeps in sync with the parameter: optim.FusedAdam writes the fprop operand of a
+# channels_last conv weight in the same pass that updates it.  (id(W), kind, fmt, layout) -> [W, tensor, version];
+# the entry is valid while W._version equals the version recorded when the copy was last written.
+_SHADOWS: dict = {}
+
+
+def register_shadow(W, kind, fmt, layout, tensor):
+    _SHADOWS[(id(W), kind, fmt, layout)] = [W, tensor, None]
+
+
+def shadows_synced(params):
+    """the owner has just rewritten the shadow copies of `params` from their current values"""
+    ids = {id(p): p for p in params}
+    for key, ent in _SHADOWS.items():
+        if key[0] in ids and ent[0] is ids[key[0]]:
+            ent[2] = ent[0]._version
+
+
+def drop_shadows(params=None):
+    if params is None:
+        _SHADOWS.clear()
+        return
+    ids = {id(p) for p in params}
+    for k in [k for k in _SHADOWS if k[0] in ids]:
+        del _SHADOWS[k]
+
+
 def _pack(W: torch.Tensor, kind: str, dtype=None, layout=None, fmt=None) -> torch.Tensor:
     """fp32 parameter -> K-major packed operand in element format `fmt` (default: the activation format; a dgrad /
     double-backward GEMM asks for the gradient format — both operands of a tensor-core GEMM share one format);
     kind 'f' = fprop [N][taps*C], 't' = dgrad [C][taps*N] with the taps reversed.  Cached per (parameter, version) for
-    nn.Parameters.  (`dtype` is accepted for compatibility and ignored: the precision mode decides.)"""
+    nn.Parameters.  (`dtype` is accepted for compatibility and ignored: the precision mode decides.)
+    A channels_last ([O][kh][kw][I]) conv weight IS its fprop operand: fp32 mode uses the parameter memory itself, the
+    16-bit modes the copy the fused Adam kernel maintains (register_shadow), else a cast."""
     _need_cuda(W)
     fmt = _ACT_FMT if fmt is None else fmt
     cacheable = isinstance(W, torch.nn.Parameter)
+    if cacheable:
+        ent = _SHADOWS.get((id(W), kind, fmt, layout))
+        if ent is not None and ent[0] is W and ent[2] == W._version:
+            return ent[1]
     key = (id(W), W._version, kind, fmt, layout) if cacheable else None
     if cacheable:
         hit = _PACK_CACHE.get(key)
         if hit is not None and hit[0] is W:
             return hit[1]
     Wc = W.detach()
-    if Wc.dtype != torch.float32 or not Wc.is_contiguous():
+    ohwi = is_ohwi(Wc) and Wc.dtype == torch.float32
+    if not ohwi and (Wc.dtype != torch.float32 or not Wc.is_contiguous()):
         Wc = Wc.float().contiguous()
-    N, C, T, fmap, tmap = _maps(Wc.shape, layout)
+    N, C, T, fmap, tmap = _maps(Wc.shape, layout, ohwi)
     args = fmap if kind == "f" else tmap
-    out = torch.empty((args[0], args[3] * args[4]), dtype=_COMPUTE_DTYPE, device=W.device)
+    if ohwi and kind == "f" and fmt == L.PG_F32 and args[4] == args[5]:
+        return Wc.permute(0, 2, 3, 1).reshape(args[0], args[3] * args[4])      # a view: no copy at all
+    out = torch.empty((args[0], args[3] * args[4]), dtype=torch.float32 if fmt == L.PG_F32 else _COMPUTE_DTYPE,
+                      device=W.device)
     m = _packmap(args)
     L.check(L.load().pggan_pack_weight(_p(Wc), _p(out), fmt, ctypes.byref(m), _s()), "pggan_pack_weight")
     if cacheable:
@@ -419,12 +513,13 @@ def conv_pn_fusable(x, N, taps) -> bool:
     """may k_conv(..., pn_eps=...) fuse the pixel norm into this layer's epilogue? (one epilogue thread must own all
     N channels of a pixel: the rows kernel, or the plain kernel when one N tile covers the layer)"""
     b, c, h, w = _dims(x)
-    key = ("pn", b, h, w, c, N, taps, _ACT_FMT)
+    fmt = _fmt_of(x, A)
+    key = ("pn", b, h, w, c, N, taps, fmt)
     hit = _KIND_CACHE.get(key)
     if hit is None:
         p = L.ConvParams()
         p.B, p.H, p.W, p.C, p.N, p.taps = b, h, w, c, N, taps
-        p.dtype = p.out_dtype = _ACT_FMT
+        p.dtype = p.out_dtype = fmt
         hit = bool(L.load().pggan_conv_pn_fusable(ctypes.byref(p)))
         _KIND_CACHE[key] = hit
     return hit
@@ -435,7 +530,7 @@ def k_conv(x, wp, bias, N, taps, scale, slope=1.0, mask_src=None, mask_slope=1.0
     xc: class of x (and of y); wp must be packed in the same element format (_pack(..., fmt=_fmt(xc)))."""
     _need_cuda(x)
     b, c, h, w = _dims(x)
-    xf = _fmt(xc)
+    xf = _fmt_of(x, xc)
     out_dtype = torch.float32 if raw_out else x.dtype
     y = _new_like_layout(x, N, out_dtype)
     p = L.ConvParams()
@@ -463,13 +558,14 @@ def dgrad_mask_fusable(batch, h, w, fwd_in_channels, fwd_out_channels, taps=9, d
     """True if the dgrad of a (fwd_in_channels -> fwd_out_channels) conv at this size runs on a kernel whose epilogue
     applies a LeakyReLU-backward mask for free (see pggan_conv_kernel_kind); the blocks use it to decide whether a
     producer may defer its mask to this layer's dgrad."""
-    key = (batch, h, w, fwd_in_channels, fwd_out_channels, taps, _GRAD_FMT)
+    gfmt = L.PG_F32 if _small_hw(h, w) else _GRAD_FMT
+    key = (batch, h, w, fwd_in_channels, fwd_out_channels, taps, gfmt)
     hit = _KIND_CACHE.get(key)
     if hit is None:
         p = L.ConvParams()
         p.B, p.H, p.W, p.C, p.N, p.taps = batch, h, w, fwd_out_channels, fwd_in_channels, taps     # dgrad: roles swapped
-        p.dtype = _GRAD_FMT
-        p.out_dtype = _GRAD_FMT
+        p.dtype = gfmt
+        p.out_dtype = gfmt
         hit = L.load().pggan_conv_kernel_kind(ctypes.byref(p)) in (L.PG_CONV_KIND_PLAIN, L.PG_CONV_KIND_ROWS)
         _KIND_CACHE[key] = hit
     return hit
@@ -481,22 +577,24 @@ def k_wgrad(g, x, scale, wshape, layout=None, accumulate_into=None, xc=A):
     _need_cuda(g)
     b, n, h, w = _dims(g)
     c = _dims(x)[1]
-    N, C, taps, fmap, _ = _maps(wshape, layout)
+    ohwi = accumulate_into is not None and is_ohwi(accumulate_into)       # the gradient view has the parameter's strides
+    N, C, taps, fmap, _ = _maps(wshape, layout, ohwi)
     if (n, c) != (N, C):
         raise ValueError(f"wgrad operand channels ({n},{c}) do not match the layer ({N},{C})")
     p = L.WgradParams()
     p.g, p.x = g.data_ptr(), x.data_ptr()
     p.B, p.H, p.W, p.C, p.N, p.taps = b, h, w, c, n, taps
-    p.dtype = _GRAD_FMT
-    if _fmt(xc) != _GRAD_FMT:
-        # both GEMM operands must share one element format: the saved fp16 activation is re-rounded to bf16
-        x = k_convert(x, _fmt(xc), _GRAD_FMT)
+    gfmt = _fmt_of(g, G)
+    p.dtype = gfmt
+    if _fmt_of(x, xc) != gfmt:
+        # both GEMM operands must share one element format: the saved fp16 activation is re-rounded to bf16 (mixed mode)
+        x = k_convert(x, _fmt_of(x, xc), gfmt)
     p.x = x.data_ptr()
     slices = L.load().pggan_conv_wgrad_slices(ctypes.byref(p))
     acc = torch.empty((slices, n, taps, c), dtype=torch.float32, device=g.device)
     p.acc = acc.data_ptr()
     ws = None
-    if _GRAD_FMT == L.PG_F32:
+    if gfmt == L.PG_F32:
         ws = (torch.empty(3 * g.numel(), dtype=torch.float32, device=g.device),
               torch.empty(3 * x.numel(), dtype=torch.float32, device=g.device))
         p.ws_g, p.ws_x = ws[0].data_ptr(), ws[1].data_ptr()
@@ -522,7 +620,7 @@ def k_mask_colsum(g, y, slope, want_out, colsum_scale, colsum_into=None, cls=G):
     """fused LeakyReLU backward (+ bias gradient): returns (g*mask(y) or None, colsum or None).
     colsum_into: an fp32 [C] tensor the column sums are ADDED to (then the second result is None)."""
     b, c, h, w = _dims(g)
-    vn = _vn(_fmt(cls))
+    vn = _vn(_fmt_of(g, cls))
     if c % vn != 0 or (c // vn) > 256 or 256 % (c // vn) != 0:          # odd widths: two plain passes
         out = k_mask_mul(g, y, slope, cls) if (want_out and y is not None) else (g if want_out else None)
         src = out if out is not None else (k_mask_mul(g, y, slope, cls) if y is not None else g)
@@ -538,7 +636,7 @@ def k_mask_colsum(g, y, slope, want_out, colsum_scale, colsum_into=None, cls=G):
     if out is None and cs is None:
         return (g if want_out else None), None
     L.check(L.load().pggan_mask_colsum(_p(g), _p(y), _p(out), _p(cs), b * h * w, c, float(slope),
-                                       float(colsum_scale or 0.0), _fmt(cls), _s()), "pggan_mask_colsum")
+                                       float(colsum_scale or 0.0), _fmt_of(g, cls), _s()), "pggan_mask_colsum")
     if want_out and out is None:
         out = g
     return out, (None if colsum_into is not None else cs)
@@ -546,19 +644,19 @@ def k_mask_colsum(g, y, slope, want_out, colsum_scale, colsum_into=None, cls=G):
 
 def k_mask_mul(g, y, slope, cls=G):
     out = torch.empty_like(g)
-    L.check(L.load().pggan_lrelu_mask_mul(_p(g), _p(y), _p(out), g.numel(), float(slope), _fmt(cls), _s()),
+    L.check(L.load().pggan_lrelu_mask_mul(_p(g), _p(y), _p(out), g.numel(), float(slope), _fmt_of(g, cls), _s()),
             "pggan_lrelu_mask_mul")
     return out
 
 
 def k_colsum(g, scale, cls=G):
     b, c, h, w = _dims(g)
-    if c % _vn(_fmt(cls)) != 0:      # e.g. the 1-logit decision layer: a [B,1] column
+    if c % _vn(_fmt_of(g, cls)) != 0:      # e.g. the 1-logit decision layer: a [B,1] column
         gf = to_float(g, cls)
         g2 = gf.reshape(b, c) if g.dim() == 2 else gf.permute(0, 2, 3, 1).reshape(-1, c)
         return g2.sum(0) * scale
     out = torch.zeros((c,), dtype=torch.float32, device=g.device)
-    L.check(L.load().pggan_colsum(_p(g), _p(out), b * h * w, c, float(scale), _fmt(cls), _s()), "pggan_colsum")
+    L.check(L.load().pggan_colsum(_p(g), _p(out), b * h * w, c, float(scale), _fmt_of(g, cls), _s()), "pggan_colsum")
     return out
 
 
@@ -568,9 +666,9 @@ def k_upsample(x, scale, mask_src=None, slope=1.0, cls=A):
     out = _new_like_layout(x, c, x.dtype, 2 * h, 2 * w)
     if mask_src is not None:
         L.check(L.load().pggan_upsample2x_mask(_p(x), _p(mask_src), _p(out), b, h, w, c, _coef(scale), float(slope),
-                                               _fmt(cls), _s()), "pggan_upsample2x_mask")
+                                               _fmt_of(x, cls), _s()), "pggan_upsample2x_mask")
         return out
-    L.check(L.load().pggan_upsample2x(_p(x), _p(out), b, h, w, c, _coef(scale), _fmt(cls), _s()),
+    L.check(L.load().pggan_upsample2x(_p(x), _p(out), b, h, w, c, _coef(scale), _fmt_of(x, cls), _s()),
             "pggan_upsample2x")
     return out
 
@@ -580,14 +678,14 @@ def k_pool(x, scale, blend_with=None, alpha=1.0, cls=A):
     b, c, h, w = _dims(x)
     out = _new_like_layout(x, c, x.dtype, h // 2, w // 2)
     L.check(L.load().pggan_pool2x2(_p(x), _p(blend_with), _p(out), b, h, w, c, _coef(scale), _coef(0.0, 1.0, alpha),
-                                   _fmt(cls), _s()), "pggan_pool2x2")
+                                   _fmt_of(x, cls), _s()), "pggan_pool2x2")
     return out
 
 
 def k_axpby(a, b, sa, sb, cls=A):
     """sa / sb: floats or _affine() coefficients; fp32 tensors run as fp32 whatever the class"""
     out = torch.empty_like(a)
-    fmt = L.PG_F32 if a.dtype == torch.float32 else _fmt(cls)
+    fmt = _fmt_of(a, cls)
     L.check(L.load().pggan_axpby(_p(a), _p(b), _p(out), a.numel(), _coef(sa), _coef(sb), fmt, _s()), "pggan_axpby")
     return out
 
@@ -618,7 +716,7 @@ class ConvF(torch.autograd.Function):
         x = feat(x, xc)
         N, C, taps, _, _ = _maps(W.shape, layout)
         bias = None if b is None else _perm_bias(b.detach().float(), layout).contiguous()
-        y = k_conv(x, _pack(W, "f", None, layout, _fmt(xc)), bias, N, taps, scale, slope, raw_out=raw_out, xc=xc)
+        y = k_conv(x, _pack(W, "f", None, layout, _fmt_of(x, xc)), bias, N, taps, scale, slope, raw_out=raw_out, xc=xc)
         ctx.mask_here = slope != 1.0 and not defer_mask
         ctx.save_for_backward(x, W, y if ctx.mask_here else None)
         ctx.scale, ctx.slope, ctx.has_bias, ctx.layout = scale, slope, b is not None, layout
@@ -682,13 +780,13 @@ class ConvActPN(torch.autograd.Function):
         bias = None if b is None else _perm_bias(b.detach().float(), layout).contiguous()
         if x.dim() == 4 and conv_pn_fusable(x, N, taps):
             # conv + He scale + bias + LeakyReLU + pixel norm in ONE kernel (the epilogue thread owns the whole pixel)
-            y, r = k_conv(x, _pack(W, "f", None, layout), bias, N, taps, scale, slope, pn_eps=eps)
+            y, r = k_conv(x, _pack(W, "f", None, layout, _fmt_of(x, A)), bias, N, taps, scale, slope, pn_eps=eps)
         else:
-            a = k_conv(x, _pack(W, "f", None, layout), bias, N, taps, scale, slope)
+            a = k_conv(x, _pack(W, "f", None, layout, _fmt_of(x, A)), bias, N, taps, scale, slope)
             bb, c, h, w = _dims(a)
             y = torch.empty_like(a)
             r = torch.empty((bb * h * w,), dtype=torch.float32, device=a.device)
-            L.check(L.load().pggan_pixelnorm_fwd(_p(a), _p(y), _p(r), bb * h * w, c, float(eps), _ACT_FMT, _s()),
+            L.check(L.load().pggan_pixelnorm_fwd(_p(a), _p(y), _p(r), bb * h * w, c, float(eps), _fmt_of(a, A), _s()),
                     "pggan_pixelnorm_fwd")
         ctx.save_for_backward(x, W, y, r)
         ctx.scale, ctx.slope, ctx.has_bias, ctx.layout = scale, slope, b is not None, layout
@@ -709,13 +807,13 @@ class ConvActPN(torch.autograd.Function):
         if need_b:
             gb = b_sink if b_sink is not None else torch.zeros((c,), dtype=torch.float32, device=y.device)
         L.check(L.load().pggan_pixelnorm_bwd(_p(gy), _p(y), _p(r), _p(g), bb * h * w, c, float(ctx.slope), _p(gb),
-                                             float(ctx.scale), _GRAD_FMT, _ACT_FMT, _s()), "pggan_pixelnorm_bwd")
+                                             float(ctx.scale), _fmt_of(gy, G), _fmt_of(y, A), _s()), "pggan_pixelnorm_bwd")
         if b_sink is not None:
             _sunk(ctx.bias_param)
         gx = gW = None
         if ctx.needs_input_grad[0]:
             N, C, taps, _, _ = _maps(W.shape, ctx.layout)
-            gx = k_conv(g, _pack(W, "t", None, ctx.layout, _GRAD_FMT), None, C, taps, ctx.scale, xc=G)
+            gx = k_conv(g, _pack(W, "t", None, ctx.layout, _fmt_of(g, G)), None, C, taps, ctx.scale, xc=G)
         if ctx.needs_input_grad[1] and not _SKIP_PARAM_GRADS:
             w_sink = _sink(ctx.w_param)
             gW = k_wgrad(g, x, ctx.scale, tuple(W.shape), ctx.layout, accumulate_into=w_sink, xc=A)
@@ -737,7 +835,7 @@ class ConvT(torch.autograd.Function):
         (the LeakyReLU backward of the layer that produced this conv's input)."""
         g = feat(g, G)
         N, C, taps, _, _ = _maps(W.shape, layout)
-        gx = k_conv(g, _pack(W, "t", None, layout, _GRAD_FMT), None, C, taps, scale, mask_src=mask_src,
+        gx = k_conv(g, _pack(W, "t", None, layout, _fmt_of(g, G)), None, C, taps, scale, mask_src=mask_src,
                     mask_slope=mask_slope, xc=G)
         ctx.save_for_backward(g, W, mask_src)
         ctx.scale, ctx.layout, ctx.mask_slope = scale, layout, mask_slope
@@ -816,16 +914,19 @@ class MaskMul(torch.autograd.Function):
 
 # ------------------------------------------------------------------ resampling / blend Functions
 class Upsample2x(torch.autograd.Function):
-    """nearest 2x (reference lib/utils.py:106-118), times `scale` (a float or an _affine() coefficient)"""
+    """nearest 2x (reference lib/utils.py:106-118), times `scale` (a float or an _affine() coefficient).
+    Precision family (fp32 island or 16 bit) = that of the LARGER tensor, the output."""
 
     @staticmethod
     def forward(ctx, x, scale, cls=A):
         ctx.scale = scale
-        return k_upsample(feat(x, cls), scale, cls=cls)
+        x = feat(x, cls, small=_small_hw(2 * x.shape[-2], 2 * x.shape[-1]))
+        ctx.f32 = x.dtype == torch.float32
+        return k_upsample(x, scale, cls=cls)
 
     @staticmethod
     def backward(ctx, g):
-        return Pool2x2.apply(feat(g, G), ctx.scale, None, G), None, None
+        return Pool2x2.apply(feat(g, G, small=ctx.f32), ctx.scale, None, G), None, None
 
 
 class UpsampleMask(torch.autograd.Function):
@@ -836,33 +937,35 @@ class UpsampleMask(torch.autograd.Function):
     def forward(ctx, g, y, scale, slope):
         ctx.save_for_backward(y)
         ctx.scale, ctx.slope = scale, slope
-        return k_upsample(feat(g, G), scale, mask_src=y, slope=slope, cls=G)
+        return k_upsample(feat(g, G, small=(y.dtype == torch.float32)), scale, mask_src=y, slope=slope, cls=G)
 
     @staticmethod
     def backward(ctx, gg):
         (y,) = ctx.saved_tensors
-        return Pool2x2.apply(MaskMul.apply(feat(gg, G), y, ctx.slope), ctx.scale, None, G), None, None, None
+        f32 = y.dtype == torch.float32
+        return Pool2x2.apply(MaskMul.apply(feat(gg, G, small=f32), y, ctx.slope), ctx.scale, None, G), None, None, None
 
 
 class Pool2x2(torch.autograd.Function):
     """scale * (2x2 window sum); scale = 0.25 is nn.AvgPool2d(2) (reference lib/blocks.py:193); scale may be an
     _affine() coefficient.  act_slope: x is the LeakyReLU output of a ConvF run with defer_mask=True — its mask is
-    applied here, in backward."""
+    applied here, in backward.  Precision family = that of the larger tensor, the input."""
 
     @staticmethod
     def forward(ctx, x, scale, act_slope=None, cls=A):
         x = feat(x, cls)
-        ctx.scale, ctx.act_slope = scale, act_slope
+        ctx.scale, ctx.act_slope, ctx.f32 = scale, act_slope, x.dtype == torch.float32
         if act_slope is not None:
             ctx.save_for_backward(x)
         return k_pool(x, scale, cls=cls)
 
     @staticmethod
     def backward(ctx, g):
+        g = feat(g, G, small=ctx.f32)
         if ctx.act_slope is not None:
             (x,) = ctx.saved_tensors
-            return UpsampleMask.apply(feat(g, G), x, ctx.scale, ctx.act_slope), None, None, None
-        return Upsample2x.apply(feat(g, G), ctx.scale, G), None, None, None
+            return UpsampleMask.apply(g, x, ctx.scale, ctx.act_slope), None, None, None
+        return Upsample2x.apply(g, ctx.scale, G), None, None, None
 
 
 class PoolBlend(torch.autograd.Function):
@@ -872,14 +975,14 @@ class PoolBlend(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, low, alpha, act_slope=None):
         x = feat(x, A)
-        ctx.alpha, ctx.act_slope = alpha, act_slope
+        ctx.alpha, ctx.act_slope, ctx.f32 = alpha, act_slope, x.dtype == torch.float32
         if act_slope is not None:
             ctx.save_for_backward(x)
-        return k_pool(x, 0.25, blend_with=feat(low, A), alpha=alpha)
+        return k_pool(x, 0.25, blend_with=feat(low, A, small=ctx.f32), alpha=alpha)
 
     @staticmethod
     def backward(ctx, g):
-        g = feat(g, G)
+        g = feat(g, G, small=ctx.f32)
         gx = None
         if ctx.needs_input_grad[0]:
             if ctx.act_slope is not None:
@@ -895,11 +998,14 @@ class Scale(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, s, cls=A):
         ctx.s, ctx.cls = s, cls
-        return k_axpby(feat(x, cls), None, s, 0.0, cls)
+        # a tensor that is already in a feature dtype keeps its precision family
+        x = feat(x, cls, small=(x.dtype == torch.float32) if x.dtype in (torch.float32, _COMPUTE_DTYPE) else None)
+        ctx.f32 = x.dtype == torch.float32
+        return k_axpby(x, None, s, 0.0, cls)
 
     @staticmethod
     def backward(ctx, g):
-        return Scale.apply(feat(g, G), ctx.s, G), None, None
+        return Scale.apply(feat(g, G, small=ctx.f32), ctx.s, G), None, None
 
 
 class Lerp(torch.autograd.Function):
@@ -928,7 +1034,7 @@ class PixelNorm(torch.autograd.Function):
         b, c, h, w = _dims(x)
         y = torch.empty_like(x)
         r = torch.empty((b * h * w,), dtype=torch.float32, device=x.device)
-        L.check(L.load().pggan_pixelnorm_fwd(_p(x), _p(y), _p(r), b * h * w, c, float(eps), _ACT_FMT, _s()),
+        L.check(L.load().pggan_pixelnorm_fwd(_p(x), _p(y), _p(r), b * h * w, c, float(eps), _fmt_of(x, A), _s()),
                 "pggan_pixelnorm_fwd")
         ctx.save_for_backward(y, r)
         return y
@@ -941,7 +1047,7 @@ class PixelNorm(torch.autograd.Function):
         b, c, h, w = _dims(y)
         gx = torch.empty_like(gy)
         L.check(L.load().pggan_pixelnorm_bwd(_p(gy), _p(y), _p(r), _p(gx), b * h * w, c, 1.0, None, 0.0,
-                                             _GRAD_FMT, _ACT_FMT, _s()), "pggan_pixelnorm_bwd")
+                                             _fmt_of(gy, G), _fmt_of(y, A), _s()), "pggan_pixelnorm_bwd")
         return gx, None
 
 
@@ -949,9 +1055,11 @@ class PixelNorm(torch.autograd.Function):
 def _k_rgb_expand(img, wc, bias, C, pool, scale, slope, cls):
     b, cimg, hi, wi = img.shape
     h, w = (hi // 2, wi // 2) if pool else (hi, wi)
-    out = torch.empty((b, C, h, w), dtype=_COMPUTE_DTYPE, device=img.device, memory_format=torch.channels_last)
+    f32 = _small_hw(h, w) or _COMPUTE_DTYPE == torch.float32              # the fp32 island at 4x4
+    out = torch.empty((b, C, h, w), dtype=torch.float32 if f32 else _COMPUTE_DTYPE, device=img.device,
+                      memory_format=torch.channels_last)
     L.check(L.load().pggan_rgb_expand(_p(img), _p(wc), _p(bias), _p(out), b, h, w, C, cimg, int(pool), float(scale),
-                                      float(slope), _fmt(cls), _s()), "pggan_rgb_expand")
+                                      float(slope), _fmt_of(out, cls), _s()), "pggan_rgb_expand")
     return out
 
 
@@ -960,7 +1068,7 @@ def _k_rgb_reduce(x, wr, bias, cimg, up, scale, up_scale, cls):
     ho, wo = (2 * h, 2 * w) if up else (h, w)
     out = torch.empty((b, cimg, ho, wo), dtype=torch.float32, device=x.device)
     L.check(L.load().pggan_rgb_reduce(_p(x), _p(wr), _p(bias), _p(out), b, h, w, c, cimg, int(up), float(scale),
-                                      float(up_scale), _fmt(cls), _s()), "pggan_rgb_reduce")
+                                      float(up_scale), _fmt_of(x, cls), _s()), "pggan_rgb_reduce")
     return out
 
 
@@ -970,7 +1078,7 @@ def _k_rgb_wgrad(f, img, pool, scale, cls, want_bias=False):
     acc = torch.zeros((c, cimg), dtype=torch.float32, device=f.device)
     bs = torch.zeros((c,), dtype=torch.float32, device=f.device) if want_bias else None
     L.check(L.load().pggan_rgb_wgrad(_p(f), _p(img), _p(acc), _p(bs), b, h, w, c, cimg, int(pool), float(scale),
-                                     _fmt(cls), _s()), "pggan_rgb_wgrad")
+                                     _fmt_of(f, cls), _s()), "pggan_rgb_wgrad")
     return (acc, bs) if want_bias else acc
 
 
@@ -1122,7 +1230,7 @@ class MbstdStat(torch.autograd.Function):
         B = x.shape[0]
         K = x.numel() // B
         stat = torch.empty((B // group,), dtype=torch.float32, device=x.device)
-        L.check(L.load().pggan_mbstd_fwd(_p(x), _p(stat), B, K, group, _ACT_FMT, _s()), "pggan_mbstd_fwd")
+        L.check(L.load().pggan_mbstd_fwd(_p(x), _p(stat), B, K, group, _fmt_of(x, A), _s()), "pggan_mbstd_fwd")
         ctx.save_for_backward(x)
         ctx.group = group
         return stat
@@ -1139,7 +1247,7 @@ class MbstdBwd(torch.autograd.Function):
         B = x.shape[0]
         K = x.numel() // B
         gx = torch.empty_like(x)
-        L.check(L.load().pggan_mbstd_bwd(_p(x), _p(gs), _p(gx), B, K, group, _ACT_FMT, _GRAD_FMT, _s()),
+        L.check(L.load().pggan_mbstd_bwd(_p(x), _p(gs), _p(gx), B, K, group, _fmt_of(x, A), _fmt_of(gx, G), _s()),
                 "pggan_mbstd_bwd")
         ctx.save_for_backward(x, gs)
         ctx.group = group
@@ -1156,7 +1264,7 @@ class MbstdBwd(torch.autograd.Function):
         K = x.numel() // B
         ggs = torch.empty_like(gs)
         gx2 = torch.empty_like(u)
-        L.check(L.load().pggan_mbstd_bwd2(_p(x), _p(u), _p(gs), _p(ggs), _p(gx2), B, K, ctx.group, _ACT_FMT, _GRAD_FMT,
+        L.check(L.load().pggan_mbstd_bwd2(_p(x), _p(u), _p(gs), _p(ggs), _p(gx2), B, K, ctx.group, _fmt_of(x, A), _fmt_of(u, G),
                                           _s()), "pggan_mbstd_bwd2")
         return gx2, ggs, None
 

@@ -45,17 +45,26 @@ class FlatGrads:
         if dev.type == "cuda":
             ops.register_grad_sink(self.params)      # kernels may accumulate straight into these views
 
+    def _view(self, p, off):
+        """the slice of the flat buffer as a gradient with the PARAMETER's strides (channels_last conv weights are
+        physically [O][kh][kw][I]: element k of the slice is the gradient of element k of the parameter's memory)"""
+        flat = self.flat[off:off + p.numel()]
+        if ops.is_ohwi(p):
+            o, i, kh, kw = p.shape
+            return flat.view(o, kh, kw, i).permute(0, 3, 1, 2)
+        return flat.view_as(p)
+
     def attach(self):
         for p, off in zip(self.params, self.offsets):
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            p.grad = self._view(p, off)
 
     def zero(self):
         self.flat.zero_()
         # a backward with create_graph=True (or set_to_none) may have replaced the views: re-attach
         for p, off in zip(self.params, self.offsets):
             g = p.grad
-            if g is None or g.data_ptr() != self.flat.data_ptr() + 4 * off:
-                p.grad = self.flat[off:off + p.numel()].view_as(p)
+            if g is None or g.data_ptr() != self.flat.data_ptr() + 4 * off or g.stride() != p.stride():
+                p.grad = self._view(p, off)
 
 
 class FusedAdam:
@@ -79,9 +88,26 @@ class FusedAdam:
         chunk = L.load().pggan_adam_chunk_size()
         entries = (L.AdamEntry * len(g.params))()
         chunk_tensor, chunk_offset = [], []
+        # 16-bit packed fprop operands of the channels_last conv weights, rewritten by the Adam kernel itself
+        self._shadowed = [p for p in g.params if ops.is_ohwi(p)] if ops._ACT_FMT != L.PG_F32 else []
+        self.shadow = None
+        shadow_off = {}
+        if self._shadowed:
+            tot = 0
+            for p in self._shadowed:
+                shadow_off[id(p)] = tot
+                tot += (p.numel() + 7) // 8 * 8
+            self.shadow = torch.zeros(tot, dtype=ops.get_compute_dtype(), device=dev)
+            for p in self._shadowed:
+                o, i, kh, kw = p.shape
+                t = self.shadow[shadow_off[id(p)]:shadow_off[id(p)] + p.numel()].view(o, kh * kw * i)
+                ops.register_shadow(p, "f", ops._ACT_FMT, None, t)
         for i, (p, off) in enumerate(zip(g.params, g.offsets)):
-            if not p.is_contiguous():
-                raise ValueError("parameters must be contiguous")
+            if not (p.is_contiguous() or ops.is_ohwi(p)):
+                raise ValueError("parameters must be dense (contiguous or channels_last)")
+            if id(p) in shadow_off:
+                entries[i].shadow = self.shadow.data_ptr() + 2 * shadow_off[id(p)]
+                entries[i].shadow_dtype = ops._ACT_FMT
             entries[i].param = p.data_ptr()
             entries[i].grad = g.flat.data_ptr() + 4 * off
             entries[i].exp_avg = self.exp_avg.data_ptr() + 4 * off
@@ -112,7 +138,8 @@ class FusedAdam:
                                          ctypes.c_void_p(self._chunk_offset.data_ptr()),
                                          ctypes.c_void_p(self.step_count.data_ptr()), self.lr, b1, b2, self.eps,
                                          self.grad_scale, ops._s()), "pggan_adam_step")
-        ops.clear_pack_cache(self.grads.params)     # packed bf16/tf32 copies of THESE weights are stale now
+        ops.clear_pack_cache(self.grads.params)     # packed bf16/tf32 copies of THESE weights are stale now ...
+        ops.shadows_synced(self._shadowed)          # ... except the fprop operands this kernel has just rewritten
 
     # ---- torch.optim.Adam wire format (reference lib/checkpoint.py:24-25, pggan/model.py:97-101) ----------------
     def state_dict(self):

@@ -137,8 +137,10 @@ def test_conv_fprop(shape, backend, dtype):
         assert after["tcgen05"] > before["tcgen05"], "tensor-core path did not run"
     else:
         assert after["simt"] > before["simt"]
-    assert y.dtype == ops.get_compute_dtype()
-    assert rel_l2(f32(y), ref) < tol(dtype), rel_l2(f32(y), ref)
+    # 4x4 maps and linear layers are fp32 islands in the 16-bit modes (ops.py): fp32 in, 3xTF32 GEMM, fp32 out
+    island = taps == 1 or H * W <= ops.SMALL_HW
+    assert y.dtype == (torch.float32 if island else ops.get_compute_dtype())
+    assert rel_l2(f32(y), ref) < (_TOL[torch.float32] if island else tol(dtype)), rel_l2(f32(y), ref)
 
 
 @pytest.mark.parametrize("dtype", DT)
