@@ -115,6 +115,13 @@ typedef struct {
      * one epilogue thread owns all N channels of a pixel (pggan_conv_pn_fusable(p) != 0); PG_ERR_UNSUPPORTED elsewhere. */
     float* pn_rnorm;
     float pn_eps;
+    /* Fused nearest-2x up-sampling (upscale2d + conv of ProgressiveGeneratorBlock, lib/blocks.py:145-151 with
+     * lib/utils.py:106-118): if up2 != 0, x is the LOW-resolution tensor [B, H/2, W/2, C] and the convolution reads
+     * up2(x) — H, W stay the OUTPUT dims.  Output tiles are formed per pixel parity (h%2, w%2): for a fixed parity the
+     * tap (dh,dw) of every pixel of the tile reads low-res pixel (h/2 + floor((h%2+dh)/2), w/2 + floor((w%2+dw)/2)), a
+     * plain shifted TMA box of x, so the up-sampled tensor is never written to HBM.  Available where
+     * pggan_conv_up2_fusable(p) != 0 (tensor-core plain kernel); PG_ERR_UNSUPPORTED elsewhere. */
+    int32_t up2;
 } pg_conv_params;
 int pggan_conv_fprop(const pg_conv_params* p, void* stream);
 /* which kernel pggan_conv_fprop would run this shape on (pointers may be NULL): lets the host decide where fusing a
@@ -126,6 +133,7 @@ int pggan_conv_fprop(const pg_conv_params* p, void* stream);
 #define PG_CONV_KIND_ROWS 3
 int pggan_conv_kernel_kind(const pg_conv_params* p);
 int pggan_conv_pn_fusable(const pg_conv_params* p); /* 1 if the call may carry pn_rnorm */
+int pggan_conv_up2_fusable(const pg_conv_params* p); /* 1 if the call may carry up2 (dims as for the fused call) */
 
 /* Weight-gradient GEMM:  sum_s acc[s][n][t][c] = sum_{b,h,w} g[b,h,w,n] * x[b, h+dh(t), w+dw(t), c]
  * acc holds pggan_conv_wgrad_slices(p) dense fp32 [N][taps][C] slices (split-K over pixels writes one slice per

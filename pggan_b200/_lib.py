@@ -24,6 +24,7 @@ class ConvParams(Structure):
         ("scale", c_float), ("slope", c_float), ("mask_slope", c_float),
         ("ws_x", c_void_p), ("ws_w", c_void_p),
         ("pn_rnorm", c_void_p), ("pn_eps", c_float),
+        ("up2", c_int32),
     ]
 
 
@@ -68,6 +69,7 @@ SIGNATURES = {
     "pggan_conv_fprop": (c_int, [POINTER(ConvParams), c_void_p]),
     "pggan_conv_kernel_kind": (c_int, [POINTER(ConvParams)]),
     "pggan_conv_pn_fusable": (c_int, [POINTER(ConvParams)]),
+    "pggan_conv_up2_fusable": (c_int, [POINTER(ConvParams)]),
     "pggan_conv_wgrad": (c_int, [POINTER(WgradParams), c_void_p]),
     "pggan_conv_wgrad_slices": (c_int, [POINTER(WgradParams)]),
     "pggan_lrelu_mask_mul": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_int, c_void_p]),

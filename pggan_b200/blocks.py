@@ -13,11 +13,11 @@ from .layers import EqualizedConv2d, EqualizedLinear, PixelwiseVectorNorm
 from .utils import downscale2d, upscale2d, num_flat_features  # noqa: F401
 
 
-def _conv_act_norm(layer, x, norm):
-    """conv3x3 -> c*(.+b) -> LeakyReLU(0.2) [-> pixel norm]   (reference lib/blocks.py:119-139)"""
+def _conv_act_norm(layer, x, norm, upscale_input=False):
+    """[upscale2d ->] conv3x3 -> c*(.+b) -> LeakyReLU(0.2) [-> pixel norm]   (reference lib/blocks.py:119-151)"""
     if isinstance(norm, PixelwiseVectorNorm):
-        return layer.fused(x, 0.2, pixel_norm_eps=1e-8)
-    x = layer.fused(x, 0.2)
+        return layer.fused(x, 0.2, pixel_norm_eps=1e-8, upscale_input=upscale_input)
+    x = layer.fused(x, 0.2, upscale_input=upscale_input)
     if norm is not None:
         x = norm(x)
     return x
@@ -50,10 +50,9 @@ class ProgressiveGeneratorBlock(nn.Module):
 
     def forward(self, x):
         convs, norm = self._convs_and_norm()
-        if not self.is_first:
-            x = ops.Upsample2x.apply(x, 1.0)                   # upscale2d, lib/utils.py:106-118
-        for conv in convs:
-            x = _conv_act_norm(conv, x, norm)
+        for i, conv in enumerate(convs):
+            # upscale2d (lib/utils.py:106-118) is the PROLOGUE of the block's first convolution
+            x = _conv_act_norm(conv, x, norm, upscale_input=(i == 0 and not self.is_first))
         return x
 
 
@@ -102,7 +101,7 @@ class ProgressiveDiscriminatorBlock(nn.Module):
         # ...where that epilogue is free; a dgrad that runs on the swapped-orientation kernel keeps the separate pass
         b, _, h, w = x.shape
         c2 = self.block[2].module
-        fuse2 = ops.dgrad_mask_fusable(b, h, w, c2.in_channels, c2.out_channels)
+        fuse2 = ops.dgrad_mask_fusable(b, h, w, c2.in_channels, c2.out_channels, f32=(x.dtype == torch.float32))
         x = self.block[0].fused(x, 0.2, x_act_slope=x_act_slope, defer_mask=fuse2)
         x = self.block[2].fused(x, 0.2, x_act_slope=0.2 if fuse2 else None, defer_mask=True)
         if blend_with is not None:
@@ -118,7 +117,7 @@ def _stddev_channel(x, subgroup_size=4):
         subgroup_size = size[0]
     if subgroup_size > 1:
         stat = ops.MbstdStat.apply(x, int(subgroup_size))                 # [N/G] fp32
-        return ops.StatChannel.apply(stat, int(subgroup_size), size[0], size[2], size[3])
+        return ops.StatChannel.apply(stat, int(subgroup_size), size[0], size[2], size[3], x.dtype == torch.float32)
     return torch.zeros(size[0], 1, size[2], size[3], device=x.device, dtype=x.dtype)
 
 
@@ -177,8 +176,9 @@ class fromRGBBlock(nn.Module):
                                        init_bias_to_zero=init_bias_to_zero)
         self.activ = nn.LeakyReLU(0.2)
 
-    def forward(self, x, apply_downscale=False, defer_mask=False):
+    def forward(self, x, apply_downscale=False, defer_mask=False, f32=False):
+        """f32: produce fp32 features (the fp32 family: a 4x4 discriminator) instead of the mode's 16-bit format"""
         m = self.fromRGB.module
         W = m.weight
         return ops.RgbExpand.apply(x, W.view(W.shape[0], W.shape[1]), m.bias, bool(apply_downscale),
-                                   self.fromRGB.scale(), 0.2, bool(defer_mask))
+                                   self.fromRGB.scale(), 0.2, bool(defer_mask), ops.A, bool(f32))

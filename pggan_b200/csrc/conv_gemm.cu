@@ -68,6 +68,8 @@ struct ConvKArgs {
     float scale, slope, mask_slope;
     float* pn_rnorm;         // fused pixel norm (plain kernel with tiles_n == 1 only): per-pixel rsqrt factor out
     float pn_eps;
+    int up2;                 // fused nearest-2x up-sampling: the tile geometry (BW/BH/BB, tiles_*) is in LOW-RES pixels,
+                             // every box yields four tiles (one per output-pixel parity); H, W are the output dims
 };
 
 template <typename T, int BLOCK_N, int SPAN = 128, int MT = 1>
@@ -115,7 +117,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int num_m_tiles = a.tiles_w * a.tiles_h * a.tiles_b;
+    const int num_m_tiles = a.tiles_w * a.tiles_h * a.tiles_b * (a.up2 ? 4 : 1);
     const int num_tiles = num_m_tiles * a.tiles_n;
     const int num_kc = a.taps * a.kc_per_tap;
 
@@ -126,7 +128,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int nt = tile % a.tiles_n;
-                const int mt = tile / a.tiles_n;
+                int mt = tile / a.tiles_n;
+                int pi = 0, pj = 0;                    // output-pixel parity of this tile (fused up-sampling)
+                if (a.up2) {
+                    pj = mt & 1;
+                    pi = (mt >> 1) & 1;
+                    mt >>= 2;
+                }
                 const int w0 = (mt % a.tiles_w) * a.BW;
                 const int h0 = ((mt / a.tiles_w) % a.tiles_h) * a.BH;
                 const int b0 = (mt / (a.tiles_w * a.tiles_h)) * a.BB;
@@ -138,6 +146,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     if (a.taps == 9) {
                         dh = tap / 3 - 1;
                         dw = tap % 3 - 1;
+                    }
+                    if (a.up2) {                       // low-res source offset: floor((parity + d) / 2) in {-1, 0, 1}
+                        dh = (pi + dh + 2) / 2 - 1;
+                        dw = (pj + dw + 2) / 2 - 1;
                     }
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * Cfg::kStageBytes;
@@ -199,7 +211,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const int nt = tile % a.tiles_n;
-            const int mt = tile / a.tiles_n;
+            int mt = tile / a.tiles_n;
+            int pi = 0, pj = 0;
+            if (a.up2) {
+                pj = mt & 1;
+                pi = (mt >> 1) & 1;
+                mt >>= 2;
+            }
             const int w0 = (mt % a.tiles_w) * a.BW;
             const int h0 = ((mt / a.tiles_w) % a.tiles_h) * a.BH;
             const int b0 = (mt / (a.tiles_w * a.tiles_h)) * a.BB;
@@ -212,7 +230,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             const int bo = row / (a.BW * a.BH);
             const int b = b0 + bo;
             const bool valid = b < a.B;
-            const size_t pix = (static_cast<size_t>(b) * a.H + (h0 + ho)) * a.W + (w0 + wo);
+            // fused up-sampling: the box is in low-res pixels, this tile owns the output pixels of parity (pi, pj)
+            const int hout = a.up2 ? 2 * (h0 + ho) + pi : (h0 + ho);
+            const int wout = a.up2 ? 2 * (w0 + wo) + pj : (w0 + wo);
+            const size_t pix = (static_cast<size_t>(b) * a.H + hout) * a.W + wout;
             const size_t off = pix * a.N + n0;
 
             constexpr int CH = BLOCK_N >= 32 ? 32 : 16;      // accumulator columns handled per step
@@ -630,12 +651,14 @@ static bool swap_pays(int n, long long k, bool big) {
 }
 // the 256 x 128 tile (MT = 2) applies to N % 128 == 0 layers with at least 4 tiles per SM
 static bool m2_applies(const pg_conv_params* p, int sms, int bn = 128) {
-    const int bw = p->W < 128 ? p->W : 128;
-    const int bh = p->H < (128 / bw) ? p->H : (128 / bw);
+    // (fused up-sampling: the pixel boxes are cut from the low-resolution tensor, four parity tiles per box)
+    const int XW = p->up2 ? p->W / 2 : p->W, XH = p->up2 ? p->H / 2 : p->H, mult = p->up2 ? 4 : 1;
+    const int bw = XW < 128 ? XW : 128;
+    const int bh = XH < (128 / bw) ? XH : (128 / bw);
     const int bb = 128 / (bw * bh);
-    const long long m_tiles = (long long)(p->W / bw) * (p->H / bh) * ((p->B + bb - 1) / bb);
-    return p->N % bn == 0 && m_tiles * (p->N / bn) >= 4LL * sms && (long long)p->W * p->H * p->B >= 512 &&
-           (p->W >= 256 || (256 % p->W == 0));
+    const long long m_tiles = (long long)(XW / bw) * (XH / bh) * ((p->B + bb - 1) / bb) * mult;
+    return p->N % bn == 0 && m_tiles * (p->N / bn) >= 4LL * sms && (long long)XW * XH * p->B >= 512 &&
+           (XW >= 256 || (256 % XW == 0));
 }
 
 template <typename T, int BLOCK_N, int SPAN = 128, int MT = 1>
@@ -648,11 +671,13 @@ static int launch_tc(const pg_conv_params* p, cudaStream_t stream) {
     a.mask_src = p->mask_src;
     a.y = p->y;
     a.B = p->B; a.H = p->H; a.W = p->W; a.N = p->N;
-    a.BW = p->W < kTileM ? p->W : kTileM;
-    a.BH = p->H < (kTileM / a.BW) ? p->H : (kTileM / a.BW);
+    a.up2 = p->up2 ? 1 : 0;
+    const int XW = a.up2 ? p->W / 2 : p->W, XH = a.up2 ? p->H / 2 : p->H;      // dims of the tensor x is read from
+    a.BW = XW < kTileM ? XW : kTileM;
+    a.BH = XH < (kTileM / a.BW) ? XH : (kTileM / a.BW);
     a.BB = kTileM / (a.BW * a.BH);
-    a.tiles_w = p->W / a.BW;
-    a.tiles_h = p->H / a.BH;
+    a.tiles_w = XW / a.BW;
+    a.tiles_h = XH / a.BH;
     a.tiles_b = (p->B + a.BB - 1) / a.BB;
     a.tiles_n = p->N / BLOCK_N;
     a.kc_per_tap = p->C / BK;
@@ -667,8 +692,8 @@ static int launch_tc(const pg_conv_params* p, cudaStream_t stream) {
     const uint64_t es = sizeof(T);
     CUtensorMap tx, tw;
     {
-        uint64_t dims[4] = {(uint64_t)p->C, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
-        uint64_t strides[3] = {(uint64_t)p->C * es, (uint64_t)p->W * p->C * es, (uint64_t)p->H * p->W * p->C * es};
+        uint64_t dims[4] = {(uint64_t)p->C, (uint64_t)XW, (uint64_t)XH, (uint64_t)p->B};
+        uint64_t strides[3] = {(uint64_t)p->C * es, (uint64_t)XW * p->C * es, (uint64_t)XH * XW * p->C * es};
         uint32_t box[4] = {(uint32_t)BK, (uint32_t)a.BW, (uint32_t)a.BH, (uint32_t)a.BB};
         int rc = encode_tmap(&tx, p->dtype, 4, p->x, dims, strides, box, SPAN);
         if (rc != PG_OK) return rc;
@@ -683,7 +708,7 @@ static int launch_tc(const pg_conv_params* p, cudaStream_t stream) {
     }
     auto kern = conv_gemm_kernel<T, BLOCK_N, SPAN, MT>;
     PG_SET_SMEM_ONCE(kern, Cfg::kSmemBytes);
-    const int num_tiles = a.tiles_w * a.tiles_h * a.tiles_b * a.tiles_n;
+    const int num_tiles = a.tiles_w * a.tiles_h * a.tiles_b * a.tiles_n * (a.up2 ? 4 : 1);
     int grid = num_tiles < num_sms() ? num_tiles : num_sms();
     kern<<<grid, kConvThreadsPlain, Cfg::kSmemBytes, stream>>>(tx, tw, a);
     PG_LAUNCH_CHECK();
@@ -754,13 +779,19 @@ static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream, int* k
                        (reinterpret_cast<uintptr_t>(p->x) % 16 == 0) && (reinterpret_cast<uintptr_t>(p->wp) % 16 == 0) &&
                        (reinterpret_cast<uintptr_t>(p->y) % 16 == 0) &&
                        (p->mask_src == nullptr || reinterpret_cast<uintptr_t>(p->mask_src) % 16 == 0);
+    if (p->up2 && kind_out == nullptr)
+        PG_CHECK(tc_ok && p->taps == 9 && p->H % 2 == 0 && p->W % 2 == 0 && p->mask_src == nullptr, PG_ERR_UNSUPPORTED,
+                 "fused up-sampling needs the tensor-core path (3x3, even H/W, no mask): B=%d H=%d W=%d C=%d N=%d", p->B,
+                 p->H, p->W, p->C, p->N);
     if (kind_out != nullptr) {
         *kind_out = PG_CONV_KIND_SIMT;
         if (tc_ok) {
             const int osz_k = is16(p->out_dtype) ? 2 : 4;
             static const bool no_rows_k = getenv("PGGAN_NO_ROWS") != nullptr;
             static const bool no_swap_k = getenv("PGGAN_NO_SWAP") != nullptr;
-            if (!kF32 && !no_rows_k && conv_rows_supported(p))
+            if (p->up2)
+                *kind_out = PG_CONV_KIND_PLAIN;          // the fused up-sampling prologue exists in the plain kernel only
+            else if (!kF32 && !no_rows_k && conv_rows_supported(p))
                 *kind_out = PG_CONV_KIND_ROWS;
             else if (!no_swap_k && span == 128 && swap_pays(p->N, (long long)Ceff * p->taps, m2_applies(p, num_sms(), p->N == 64 ? 64 : 128)) && (p->N * osz_k) % 16 == 0 &&
                      (long long)p->B * p->H * p->W >= 2 * kSwPix)
@@ -772,8 +803,9 @@ static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream, int* k
     }
     if (tc_ok) {
         if (kF32) {
+            const long long xpix = (long long)p->B * p->H * p->W / (p->up2 ? 4 : 1);
             int rc = split3_launch(reinterpret_cast<const float*>(p->x), reinterpret_cast<float*>(p->ws_x),
-                                   (long long)p->B * p->H * p->W, p->C, 1, 2, stream);
+                                   xpix, p->C, 1, 2, stream);
             if (rc != PG_OK) return rc;
             rc = split3_launch(reinterpret_cast<const float*>(p->wp), reinterpret_cast<float*>(p->ws_w),
                                (long long)p->N * p->taps, p->C, 1, 1, stream);
@@ -784,20 +816,21 @@ static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream, int* k
         }
         // narrow layers on wide images: input rows resident in smem, taps as shifted views (conv_rows.cu)
         static const bool no_rows = getenv("PGGAN_NO_ROWS") != nullptr;
-        if (!kF32 && !no_rows && conv_rows_supported(p)) return conv_rows_launch(p, stream);
+        if (!kF32 && !no_rows && !p->up2 && conv_rows_supported(p)) return conv_rows_launch(p, stream);
         // few output channels: swapped orientation (channels on M, 256 pixels on N) keeps the tensor pipe fed
         const int osz = is16(p->out_dtype) ? 2 : 4;
         const bool mask_ok = p->mask_src == nullptr || osz == (int)sizeof(T);
         static const bool no_swap = getenv("PGGAN_NO_SWAP") != nullptr;
         // (its transposing epilogue costs a fixed ~5k cycles per 128x256 tile: only worth it when K is long enough)
-        if (!no_swap && span == 128 && swap_pays(p->N, (long long)p->C * p->taps, m2_applies(p, num_sms(), p->N == 64 ? 64 : 128)) && (p->N * osz) % 16 == 0 && mask_ok &&
+        if (!no_swap && !p->up2 && span == 128 && swap_pays(p->N, (long long)p->C * p->taps, m2_applies(p, num_sms(), p->N == 64 ? 64 : 128)) && (p->N * osz) % 16 == 0 && mask_ok &&
             (long long)p->B * p->H * p->W >= 2 * kSwPix && p->pn_rnorm == nullptr)
             return launch_swapped<T>(p, stream);
         // largest N tile that still yields enough CTAs to occupy the machine
-        const int bw = p->W < 128 ? p->W : 128;
-        const int bh = p->H < (128 / bw) ? p->H : (128 / bw);
+        const int XW = p->up2 ? p->W / 2 : p->W, XH = p->up2 ? p->H / 2 : p->H;
+        const int bw = XW < 128 ? XW : 128;
+        const int bh = XH < (128 / bw) ? XH : (128 / bw);
         const int bb = 128 / (bw * bh);
-        const long long m_tiles = (long long)(p->W / bw) * (p->H / bh) * ((p->B + bb - 1) / bb);
+        const long long m_tiles = (long long)(XW / bw) * (XH / bh) * ((p->B + bb - 1) / bb) * (p->up2 ? 4 : 1);
         const int sms = num_sms();
         // N tile: minimise (waves over the SMs) x (per-tile cost).  Per-tile cost is the MMA time (~N) until the
         // fixed 16 KB A-tile shared-memory read per k-step dominates (N <= 64).
@@ -882,6 +915,16 @@ extern "C" int pggan_conv_kernel_kind(const pg_conv_params* p) {
     else if (q.dtype == PG_F32)
         conv_dispatch<float>(&q, nullptr, &kind);
     return kind;
+}
+
+extern "C" int pggan_conv_up2_fusable(const pg_conv_params* p) {
+    // the fused call is offered where the UNFUSED convolution of the up-sampled tensor would run on the plain
+    // tensor-core kernel anyway (the rows / swapped kernels of the narrow layers have no up-sampling prologue)
+    if (p == nullptr || p->taps != 9 || p->H % 2 != 0 || p->W % 2 != 0 || p->H < 2 || p->W < 2) return 0;
+    pg_conv_params q = *p;
+    q.up2 = 0;
+    q.mask_src = nullptr;
+    return pggan_conv_kernel_kind(&q) == PG_CONV_KIND_PLAIN ? 1 : 0;
 }
 
 extern "C" int pggan_conv_pn_fusable(const pg_conv_params* p) {

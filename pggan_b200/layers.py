@@ -59,9 +59,10 @@ class ConstrainedLayer(nn.Module):
         return float(self.weight) if self.equalized else 1.0
 
     def fused(self, x, slope=1.0, raw_out=False, pixel_norm_eps=None, layout=None, x_act_slope=None,
-              defer_mask=False):
+              defer_mask=False, upscale_input=False):
         """lrelu(c*(W x + b), slope) [+ pixel norm if pixel_norm_eps is given] on the fused kernels.
-        x_act_slope / defer_mask: LeakyReLU-backward fusion hints, see ops.ConvF."""
+        x_act_slope / defer_mask: LeakyReLU-backward fusion hints, see ops.ConvF.
+        upscale_input: the layer reads upscale2d(x) (nearest 2x) — fused into the GEMM where ops.conv_up2_fusable."""
         m = self.module
         W, b = m.weight, m.bias
         c = self.scale()
@@ -81,7 +82,9 @@ class ConstrainedLayer(nn.Module):
                 raise NotImplementedError("toRGB-shaped 1x1 convolutions have no fused activation")
             return ops.RgbReduce.apply(x, W.view(W.shape[0], W.shape[1]).t(), b, False, c, 1.0)
         if pixel_norm_eps is not None:
-            return ops.ConvActPN.apply(x, W, b, c, float(slope), float(pixel_norm_eps), layout)
+            return ops.ConvActPN.apply(x, W, b, c, float(slope), float(pixel_norm_eps), layout, bool(upscale_input))
+        if upscale_input:
+            x = ops.Upsample2x.apply(x, 1.0)
         return ops.ConvF.apply(x, W, b, c, float(slope), raw_out, layout, x_act_slope, bool(defer_mask))
 
     def forward(self, x):

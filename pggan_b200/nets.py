@@ -90,6 +90,10 @@ class Generator(_AlphaMixin, nn.Module):
         self.toRGB_blocks.append(toRGBBlock(new_depth, output_dim=self.output_dim, equalized_lr=self.equalized_lr,
                                             init_bias_to_zero=self.init_bias_to_zero).to(dev))
 
+    def tiny(self) -> bool:
+        """4x4 output: the network runs in the fp32 family whatever the precision mode (see ops.py)"""
+        return len(self.blocks) == 0
+
     def live_parameters(self):
         """parameters that take part in forward at the current scale (RGB layers older than [-2] are
         stale — SURVEY.md D16), in reverse execution order (the order their gradients become ready)."""
@@ -104,6 +108,9 @@ class Generator(_AlphaMixin, nn.Module):
         """reference pggan/nets.py:121-161"""
         pn = self.pixel_norm if self.apply_pixel_norm else None
         x = x.reshape(-1, num_flat_features(x))
+        # the one place where the latent turns into the precision mode's 16-bit format; a 4x4 network (no blocks yet)
+        # stays in fp32 (ops.py: precision follows the tensor)
+        x = ops.enter(x, ops.A, f32=self.tiny())
         if pn is not None:
             x = ops.PixelNorm.apply(x, 1e-8)
         # format layer: Linear(latent -> 16*C) + LReLU, written directly in NHWC order by permuting the
@@ -177,6 +184,10 @@ class Discriminator(_AlphaMixin, nn.Module):
         self.decision_layer = EqualizedLinear(self.depths[0], decision_layer_size, equalized=self.equalized_lr,
                                               init_bias_to_zero=self.init_bias_to_zero)
 
+    def tiny(self) -> bool:
+        """4x4 input: the network runs in the fp32 family whatever the precision mode (see ops.py)"""
+        return len(self.blocks) == 0
+
     def live_parameters(self):
         """live parameters in reverse execution order (decision layer first) — SURVEY.md D16 / §5"""
         rgb = list(self.fromRGB_blocks[-2:]) if len(self.blocks) else [self.fromRGB_blocks[-1]]
@@ -194,7 +205,7 @@ class Discriminator(_AlphaMixin, nn.Module):
             x_down = self.fromRGB_blocks[-2](img, apply_downscale=True)
         # with blocks present, fromRGB's LeakyReLU backward is applied by the first block's conv1 dgrad epilogue
         fuse_rgb = len(self.blocks) > 0 and self.blocks[-1].first_dgrad_fuses_mask(img.shape[0], img.shape[2], img.shape[3])
-        x = self.fromRGB_blocks[-1](img, defer_mask=fuse_rgb)
+        x = self.fromRGB_blocks[-1](img, defer_mask=fuse_rgb, f32=self.tiny())
         apply_merge = len(self.blocks) > 0
         for block in reversed(self.blocks):
             if apply_merge:

@@ -25,12 +25,13 @@ Precision modes (set_compute_dtype):
   torch.bfloat16                           everything bf16
   torch.float32                            3xTF32 operands, fp32 accumulate: the parity mode
 
-fp32 islands: in the 16-bit modes the NARROW END of both networks — 4x4 feature maps and the 2-D features of the three
-linear layers, < 0.3 % of the FLOPs — stays fp32 (3xTF32 GEMMs).  Every rounding and every LeakyReLU-mask flip there
-acts coherently on the WHOLE image gradient (at 4x4 it has 48 elements per sample and ||grad|| ~ 0.8, where
-GP = 10*(||g||-1)^2 amplifies a norm error 8x: measured 2.6e-3..6e-3 GP error with a 16-bit tail against 1e-3 asked).
-The rule is stateless — a Function computes in fp32 iff its feature tensor is "small" (_small) — so forward, backward
-and double backward agree without bookkeeping; autograd's own dtype checks cast at the island's edge.
+Precision follows the TENSOR: every Function computes in the family of its input feature tensor — an fp32 tensor runs
+the fp32 (3xTF32) path and yields fp32, a 16-bit tensor the 16-bit path — in forward, backward and double backward
+alike (the backward reads the family off its saved tensors, autograd's own dtype checks cast at a family boundary).
+The precision MODE only decides what `enter()` converts external fp32 inputs to; the networks call it once at their
+entry.  In the 16-bit modes they stay in fp32 while the image is 4x4 (scale 0): there the image gradient has 48
+elements per sample and ||grad|| ~ 0.8, where GP = 10*(||g||-1)^2 amplifies a norm error 8x (measured 2.6e-3..6e-3 GP
+error at 16 bits against 1e-3 asked), and a 2 ms latency-bound step gains nothing from 16 bits anyway.
 
 Two tensor CLASSES therefore exist: "a" (activation-like: produced by a forward pass) and "g" (gradient-like: produced
 by a backward pass, including everything the double backward derives from gradients).  Every 16-bit feature tensor
@@ -224,16 +225,9 @@ class _Import(torch.autograd.Function):
         return g.to(ctx.dtype), None
 
 
-SMALL_HW = 16            # feature maps with H*W <= this (4x4) and all 2-D features are fp32 islands in the 16-bit modes
-F32_ISLANDS = True
-
-
-def _small_hw(h: int, w: int) -> bool:
-    return F32_ISLANDS and h * w <= SMALL_HW
-
-
 def _small(x: torch.Tensor) -> bool:
-    return F32_ISLANDS and (x.dim() == 2 or (x.dim() == 4 and x.shape[-1] * x.shape[-2] <= SMALL_HW))
+    """the fp32 family: a feature tensor that already is fp32 stays fp32 (see the module docstring)"""
+    return x.dtype == torch.float32
 
 
 def _fmt_of(x: torch.Tensor, cls: str) -> int:
@@ -255,9 +249,10 @@ class _ToF32(torch.autograd.Function):
 
 
 def feat(x: torch.Tensor, cls: str = A, small=None) -> torch.Tensor:
-    """feature tensor of class `cls` in the kernels' layout and precision: fp32 if the tensor is small (an fp32 island;
-    `small` overrides the decision, e.g. for the partner of a larger tensor) or the mode is fp32, else the 16-bit
-    format of its class.  A tensor that already carries the feature dtype is trusted to BE of that class."""
+    """feature tensor of class `cls` in the kernels' layout.  Precision family: fp32 stays fp32 (and the fp32 mode is
+    all fp32); `small` overrides — True forces fp32, False forces the mode's 16-bit format (a gradient arriving in
+    fp32 for a 16-bit layer, the partner of a 16-bit tensor).  A tensor that already carries the 16-bit feature dtype
+    is trusted to BE of class `cls`."""
     if small is None:
         small = _small(x)
     if small or _COMPUTE_DTYPE == torch.float32:
@@ -276,6 +271,12 @@ def feat(x: torch.Tensor, cls: str = A, small=None) -> torch.Tensor:
         else:
             x = x.to(real).view(_COMPUTE_DTYPE)
     return cl(x)
+
+
+def enter(x: torch.Tensor, cls: str = A, f32: bool = False) -> torch.Tensor:
+    """an external tensor (latents, test inputs) as a feature tensor of the current precision mode — or of the fp32
+    family if `f32`.  This is the ONE place where fp32 is turned into 16 bits; differentiable."""
+    return feat(x, cls, small=bool(f32) or _COMPUTE_DTYPE == torch.float32)
 
 
 def to_float(x: torch.Tensor, cls: str = A) -> torch.Tensor:
@@ -299,11 +300,12 @@ class ExportFloat(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x):
+        ctx.f32 = x.dtype == torch.float32
         return to_float(x, A)
 
     @staticmethod
     def backward(ctx, g):
-        return feat(g, G)
+        return feat(g, G, small=ctx.f32)
 
 
 class ExportAct(torch.autograd.Function):
@@ -315,7 +317,7 @@ class ExportAct(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        return feat(g, G)
+        return feat(g, G, small=False)
 
 
 def export_act(x: torch.Tensor) -> torch.Tensor:
@@ -509,30 +511,53 @@ def clear_pack_cache(params=None):
 _KIND_CACHE: dict = {}
 
 
-def conv_pn_fusable(x, N, taps) -> bool:
+def conv_pn_fusable(x, N, taps, up2=False) -> bool:
     """may k_conv(..., pn_eps=...) fuse the pixel norm into this layer's epilogue? (one epilogue thread must own all
     N channels of a pixel: the rows kernel, or the plain kernel when one N tile covers the layer)"""
     b, c, h, w = _dims(x)
+    if up2:
+        h, w = 2 * h, 2 * w
     fmt = _fmt_of(x, A)
-    key = ("pn", b, h, w, c, N, taps, fmt)
+    key = ("pn", b, h, w, c, N, taps, fmt, up2)
     hit = _KIND_CACHE.get(key)
     if hit is None:
         p = L.ConvParams()
         p.B, p.H, p.W, p.C, p.N, p.taps = b, h, w, c, N, taps
         p.dtype = p.out_dtype = fmt
+        p.up2 = 1 if up2 else 0
         hit = bool(L.load().pggan_conv_pn_fusable(ctypes.byref(p)))
         _KIND_CACHE[key] = hit
     return hit
 
 
-def k_conv(x, wp, bias, N, taps, scale, slope=1.0, mask_src=None, mask_slope=1.0, raw_out=False, pn_eps=None, xc=A):
+def conv_up2_fusable(x_low, N, taps=9) -> bool:
+    """may conv3x3(upscale2d(x_low)) run as ONE kernel (k_conv(..., up2=True))?  Offered where the plain tensor-core
+    kernel would take the unfused layer; the 16-bit modes only (the fp32 island rule looks at the OUTPUT size)."""
+    b, c, h, w = _dims(x_low)
+    fmt = _fmt_of(x_low, A)
+    key = ("up2", b, h, w, c, N, taps, fmt)
+    hit = _KIND_CACHE.get(key)
+    if hit is None:
+        p = L.ConvParams()
+        p.B, p.H, p.W, p.C, p.N, p.taps = b, 2 * h, 2 * w, c, N, taps
+        p.dtype = p.out_dtype = fmt
+        hit = x_low.dim() == 4 and bool(L.load().pggan_conv_up2_fusable(ctypes.byref(p)))
+        _KIND_CACHE[key] = hit
+    return hit
+
+
+def k_conv(x, wp, bias, N, taps, scale, slope=1.0, mask_src=None, mask_slope=1.0, raw_out=False, pn_eps=None, xc=A,
+           up2=False):
     """pn_eps: also apply the pixel norm in the epilogue; returns (y, rnorm[pixels] fp32) then.
-    xc: class of x (and of y); wp must be packed in the same element format (_pack(..., fmt=_fmt(xc)))."""
+    xc: class of x (and of y); wp must be packed in the same element format (_pack(..., fmt=_fmt(xc))).
+    up2: x is the low-resolution tensor; the convolution reads its nearest-2x up-sampling (never materialised)."""
     _need_cuda(x)
     b, c, h, w = _dims(x)
+    if up2:
+        h, w = 2 * h, 2 * w
     xf = _fmt_of(x, xc)
     out_dtype = torch.float32 if raw_out else x.dtype
-    y = _new_like_layout(x, N, out_dtype)
+    y = _new_like_layout(x, N, out_dtype, h, w)
     p = L.ConvParams()
     rn = None
     if pn_eps is not None:
@@ -544,6 +569,7 @@ def k_conv(x, wp, bias, N, taps, scale, slope=1.0, mask_src=None, mask_slope=1.0
     p.dtype = xf
     p.out_dtype = L.PG_F32_RAW if raw_out else xf
     p.scale, p.slope, p.mask_slope = float(scale), float(slope), float(mask_slope)
+    p.up2 = 1 if up2 else 0
     ws = None
     if xf == L.PG_F32:          # fp32 mode = 3xTF32: the library splits operands into these
         ws = (torch.empty(3 * x.numel(), dtype=torch.float32, device=x.device),
@@ -554,11 +580,11 @@ def k_conv(x, wp, bias, N, taps, scale, slope=1.0, mask_src=None, mask_slope=1.0
     return y if pn_eps is None else (y, rn)
 
 
-def dgrad_mask_fusable(batch, h, w, fwd_in_channels, fwd_out_channels, taps=9, dtype=None) -> bool:
+def dgrad_mask_fusable(batch, h, w, fwd_in_channels, fwd_out_channels, taps=9, dtype=None, f32=False) -> bool:
     """True if the dgrad of a (fwd_in_channels -> fwd_out_channels) conv at this size runs on a kernel whose epilogue
     applies a LeakyReLU-backward mask for free (see pggan_conv_kernel_kind); the blocks use it to decide whether a
     producer may defer its mask to this layer's dgrad."""
-    gfmt = L.PG_F32 if _small_hw(h, w) else _GRAD_FMT
+    gfmt = L.PG_F32 if f32 else _GRAD_FMT
     key = (batch, h, w, fwd_in_channels, fwd_out_channels, taps, gfmt)
     hit = _KIND_CACHE.get(key)
     if hit is None:
@@ -729,7 +755,7 @@ class ConvF(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         x, W, y = ctx.saved_tensors
-        g = feat(gy, G)
+        g = feat(gy, G, small=(x.dtype == torch.float32))      # (the fp32 logits' gradient of a 16-bit layer: converted)
         need_w = ctx.needs_input_grad[1] and not _SKIP_PARAM_GRADS
         need_b = ctx.has_bias and ctx.needs_input_grad[2] and not _SKIP_PARAM_GRADS
         gx = gW = gb = None
@@ -768,21 +794,35 @@ class ConvF(torch.autograd.Function):
 
 
 class ConvActPN(torch.autograd.Function):
-    """G's  conv3x3 -> c*(.+b) -> LeakyReLU -> pixel norm  (reference lib/blocks.py:119-139 with
-    lib/layers.py:13-14): two kernels forward (GEMM with fused bias/He/LReLU epilogue, pixel norm) and a
-    backward whose first pass fuses pixel-norm backward, the LeakyReLU mask (sign(y_pn) == sign(pre))
-    and the bias gradient.  The generator is never differentiated twice."""
+    """G's  [upscale2d ->] conv3x3 -> c*(.+b) -> LeakyReLU -> pixel norm  (reference lib/blocks.py:119-151 with
+    lib/layers.py:13-14 and lib/utils.py:106-118).  Forward: ONE kernel where the epilogue thread owns the pixel (GEMM
+    with bias/He/LReLU/pixel-norm epilogue), two otherwise; with up2 the nearest-2x up-sampling is the GEMM's PROLOGUE
+    (parity tiles read shifted boxes of the low-resolution tensor: the up-sampled tensor is never written).  Backward:
+    first pass fuses pixel-norm backward, the LeakyReLU mask (sign(y_pn) == sign(pre)) and the bias gradient; the
+    up-sampled input is re-materialised only for the weight gradient, its gradient is pooled back.
+    The generator is never differentiated twice."""
 
     @staticmethod
-    def forward(ctx, x, W, b, scale, slope, eps, layout=None):
-        x = feat(x, A)
+    def forward(ctx, x, W, b, scale, slope, eps, layout=None, up2=False):
+        if up2:
+            x = feat(x, A)
+            if not conv_up2_fusable(x, int(W.shape[0])):       # the fused prologue where the plain kernel takes the layer
+                x = k_upsample(x, 1.0)
+                up2 = False
+                ctx.up_input = True
+            else:
+                ctx.up_input = False
+        else:
+            x = feat(x, A)
+            ctx.up_input = False
+        ctx.up2 = up2
         N, C, taps, _, _ = _maps(W.shape, layout)
         bias = None if b is None else _perm_bias(b.detach().float(), layout).contiguous()
-        if x.dim() == 4 and conv_pn_fusable(x, N, taps):
+        if x.dim() == 4 and conv_pn_fusable(x, N, taps, up2):
             # conv + He scale + bias + LeakyReLU + pixel norm in ONE kernel (the epilogue thread owns the whole pixel)
-            y, r = k_conv(x, _pack(W, "f", None, layout, _fmt_of(x, A)), bias, N, taps, scale, slope, pn_eps=eps)
+            y, r = k_conv(x, _pack(W, "f", None, layout, _fmt_of(x, A)), bias, N, taps, scale, slope, pn_eps=eps, up2=up2)
         else:
-            a = k_conv(x, _pack(W, "f", None, layout, _fmt_of(x, A)), bias, N, taps, scale, slope)
+            a = k_conv(x, _pack(W, "f", None, layout, _fmt_of(x, A)), bias, N, taps, scale, slope, up2=up2)
             bb, c, h, w = _dims(a)
             y = torch.empty_like(a)
             r = torch.empty((bb * h * w,), dtype=torch.float32, device=a.device)
@@ -798,7 +838,7 @@ class ConvActPN(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, gy):
         x, W, y, r = ctx.saved_tensors
-        gy = feat(gy, G)
+        gy = feat(gy, G, small=(y.dtype == torch.float32))
         bb, c, h, w = _dims(y)
         need_b = ctx.has_bias and ctx.needs_input_grad[2] and not _SKIP_PARAM_GRADS
         g = torch.empty_like(gy)
@@ -811,19 +851,23 @@ class ConvActPN(torch.autograd.Function):
         if b_sink is not None:
             _sunk(ctx.bias_param)
         gx = gW = None
+        upsampled = ctx.up2 or ctx.up_input           # the conv's input was upscale2d(x_low)
         if ctx.needs_input_grad[0]:
             N, C, taps, _, _ = _maps(W.shape, ctx.layout)
             gx = k_conv(g, _pack(W, "t", None, ctx.layout, _fmt_of(g, G)), None, C, taps, ctx.scale, xc=G)
+            if upsampled:
+                gx = k_pool(gx, 1.0, cls=G)           # adjoint of the nearest up-sampling: 2x2 window sum
         if ctx.needs_input_grad[1] and not _SKIP_PARAM_GRADS:
             w_sink = _sink(ctx.w_param)
-            gW = k_wgrad(g, x, ctx.scale, tuple(W.shape), ctx.layout, accumulate_into=w_sink, xc=A)
+            xw = k_upsample(x, 1.0) if ctx.up2 else x          # fused forward: re-materialise up2(x) for this GEMM only
+            gW = k_wgrad(g, xw, ctx.scale, tuple(W.shape), ctx.layout, accumulate_into=w_sink, xc=A)
             if w_sink is not None:
                 _sunk(ctx.w_param)
         if b_sink is not None:
             gb = None
         elif gb is not None:
             gb = _perm_bias(gb, ctx.layout, inverse=True)
-        return gx, gW, gb, None, None, None, None
+        return gx, gW, gb, None, None, None, None, None
 
 
 class ConvT(torch.autograd.Function):
@@ -844,7 +888,7 @@ class ConvT(torch.autograd.Function):
     @staticmethod
     def backward(ctx, ggx):
         g, W, mask_src = ctx.saved_tensors
-        ggx = feat(ggx, G)
+        ggx = feat(ggx, G, small=(g.dtype == torch.float32))
         if mask_src is not None:
             ggx = MaskMul.apply(ggx, mask_src, ctx.mask_slope)
         dg = dW = None
@@ -901,7 +945,7 @@ class MaskMul(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, g, y, slope):
-        g = feat(g, G)
+        g = feat(g, G, small=(y.dtype == torch.float32))
         ctx.save_for_backward(y)
         ctx.slope = slope
         return k_mask_mul(g, y, slope, G)
@@ -909,18 +953,17 @@ class MaskMul(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gg):
         (y,) = ctx.saved_tensors
-        return MaskMul.apply(feat(gg, G), y, ctx.slope), None, None
+        return MaskMul.apply(feat(gg, G, small=(y.dtype == torch.float32)), y, ctx.slope), None, None
 
 
 # ------------------------------------------------------------------ resampling / blend Functions
 class Upsample2x(torch.autograd.Function):
-    """nearest 2x (reference lib/utils.py:106-118), times `scale` (a float or an _affine() coefficient).
-    Precision family (fp32 island or 16 bit) = that of the LARGER tensor, the output."""
+    """nearest 2x (reference lib/utils.py:106-118), times `scale` (a float or an _affine() coefficient)"""
 
     @staticmethod
     def forward(ctx, x, scale, cls=A):
         ctx.scale = scale
-        x = feat(x, cls, small=_small_hw(2 * x.shape[-2], 2 * x.shape[-1]))
+        x = feat(x, cls)
         ctx.f32 = x.dtype == torch.float32
         return k_upsample(x, scale, cls=cls)
 
@@ -949,7 +992,7 @@ class UpsampleMask(torch.autograd.Function):
 class Pool2x2(torch.autograd.Function):
     """scale * (2x2 window sum); scale = 0.25 is nn.AvgPool2d(2) (reference lib/blocks.py:193); scale may be an
     _affine() coefficient.  act_slope: x is the LeakyReLU output of a ConvF run with defer_mask=True — its mask is
-    applied here, in backward.  Precision family = that of the larger tensor, the input."""
+    applied here, in backward."""
 
     @staticmethod
     def forward(ctx, x, scale, act_slope=None, cls=A):
@@ -1043,7 +1086,7 @@ class PixelNorm(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, gy):
         y, r = ctx.saved_tensors
-        gy = feat(gy, G)
+        gy = feat(gy, G, small=(y.dtype == torch.float32))
         b, c, h, w = _dims(y)
         gx = torch.empty_like(gy)
         L.check(L.load().pggan_pixelnorm_bwd(_p(gy), _p(y), _p(r), _p(gx), b * h * w, c, 1.0, None, 0.0,
@@ -1052,10 +1095,10 @@ class PixelNorm(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------ RGB 1x1
-def _k_rgb_expand(img, wc, bias, C, pool, scale, slope, cls):
+def _k_rgb_expand(img, wc, bias, C, pool, scale, slope, cls, f32=False):
     b, cimg, hi, wi = img.shape
     h, w = (hi // 2, wi // 2) if pool else (hi, wi)
-    f32 = _small_hw(h, w) or _COMPUTE_DTYPE == torch.float32              # the fp32 island at 4x4
+    f32 = f32 or _COMPUTE_DTYPE == torch.float32
     out = torch.empty((b, C, h, w), dtype=torch.float32 if f32 else _COMPUTE_DTYPE, device=img.device,
                       memory_format=torch.channels_last)
     L.check(L.load().pggan_rgb_expand(_p(img), _p(wc), _p(bias), _p(out), b, h, w, C, cimg, int(pool), float(scale),
@@ -1092,13 +1135,14 @@ class RgbExpand(torch.autograd.Function):
     out_cls: class of the produced feature map ("g" when this is the dgrad of a toRGB layer)."""
 
     @staticmethod
-    def forward(ctx, img, Wc, bias, pool, scale, slope, defer_mask=False, out_cls=A):
-        """defer_mask: the consumer (a ConvF with x_act_slope) applies this layer's LeakyReLU mask in its dgrad"""
+    def forward(ctx, img, Wc, bias, pool, scale, slope, defer_mask=False, out_cls=A, f32=False):
+        """defer_mask: the consumer (a ConvF with x_act_slope) applies this layer's LeakyReLU mask in its dgrad
+        f32: produce an fp32 feature map (the fp32 family) instead of the mode's 16-bit format"""
         img = _img(img)
         _need_cuda(img)
         wc = Wc.detach().float().contiguous()
         bs = None if bias is None else bias.detach().float().contiguous()
-        y = _k_rgb_expand(img, wc, bs, wc.shape[0], pool, scale, slope, out_cls)
+        y = _k_rgb_expand(img, wc, bs, wc.shape[0], pool, scale, slope, out_cls, f32)
         ctx.mask_here = slope != 1.0 and not defer_mask
         ctx.save_for_backward(img, Wc, y if ctx.mask_here else None)
         ctx.pool, ctx.scale, ctx.slope, ctx.has_bias = pool, scale, slope, bias is not None
@@ -1120,7 +1164,7 @@ class RgbExpand(torch.autograd.Function):
                 gW = RgbWgrad.apply(g, img, ctx.pool, ctx.scale, G)
             if need_b:
                 gb = ColSum.apply(g, ctx.scale)
-            return gimg, gW, gb, None, None, None, None, None
+            return gimg, gW, gb, None, None, None, None, None, None
         if ctx.mask_here:
             g = k_mask_mul(g, y, ctx.slope, G)
         if ctx.needs_input_grad[0]:
@@ -1132,7 +1176,7 @@ class RgbExpand(torch.autograd.Function):
                 gW = None
             if not need_b:
                 gb = None
-        return gimg, gW, gb, None, None, None, None, None
+        return gimg, gW, gb, None, None, None, None, None, None
 
 
 class RgbReduce(torch.autograd.Function):
@@ -1156,7 +1200,7 @@ class RgbReduce(torch.autograd.Function):
         s = ctx.scale * (4.0 * ctx.up_scale if ctx.up else 1.0)    # adjoint of "write 4 copies * up_scale"
         gx = gW = gb = None
         if ctx.needs_input_grad[0]:
-            gx = RgbExpand.apply(gout, Wc, None, ctx.up, s, 1.0, False, G)
+            gx = RgbExpand.apply(gout, Wc, None, ctx.up, s, 1.0, False, G, x.dtype == torch.float32)
         if not _SKIP_PARAM_GRADS:
             if ctx.needs_input_grad[1]:
                 gW = RgbWgrad.apply(x, gout, ctx.up, s, ctx.xc)
@@ -1180,7 +1224,7 @@ class RgbWgrad(torch.autograd.Function):
         f, img = ctx.saved_tensors
         df = dimg = None
         if ctx.needs_input_grad[0]:
-            df = RgbExpand.apply(img, ggW, None, ctx.pool, ctx.scale, 1.0, False, G)
+            df = RgbExpand.apply(img, ggW, None, ctx.pool, ctx.scale, 1.0, False, G, f.dtype == torch.float32)
         if ctx.needs_input_grad[1]:
             dimg = RgbReduce.apply(f, ggW, None, ctx.pool, ctx.scale, 0.25, ctx.fc)
         return df, dimg, None, None, None
@@ -1257,7 +1301,7 @@ class MbstdBwd(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, u):
         x, gs = ctx.saved_tensors
-        u = feat(u, G)
+        u = feat(u, G, small=(x.dtype == torch.float32))
         if u.stride() != x.stride():
             u = u.contiguous(memory_format=torch.channels_last) if x.dim() == 4 else u.contiguous()
         B = x.shape[0]
@@ -1274,15 +1318,15 @@ class StatChannel(torch.autograd.Function):
     (the expand/cat half of reference lib/blocks.py:226-231)"""
 
     @staticmethod
-    def forward(ctx, stat, group, batch, h, w):
+    def forward(ctx, stat, group, batch, h, w, f32=False):
         ctx.group = group
         y = stat.repeat_interleave(group).view(batch, 1, 1, 1).expand(batch, 1, h, w)
-        return feat(y.contiguous(), A)
+        return enter(y.contiguous(), A, f32)
 
     @staticmethod
     def backward(ctx, g):
         gs = to_float(g, G).sum(dim=(1, 2, 3)).view(-1, ctx.group).sum(dim=1)
-        return gs, None, None, None, None
+        return gs, None, None, None, None, None
 
 
 # ------------------------------------------------------------------------- loss reductions

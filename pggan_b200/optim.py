@@ -45,14 +45,19 @@ class FlatGrads:
         if dev.type == "cuda":
             ops.register_grad_sink(self.params)      # kernels may accumulate straight into these views
 
-    def _view(self, p, off):
-        """the slice of the flat buffer as a gradient with the PARAMETER's strides (channels_last conv weights are
-        physically [O][kh][kw][I]: element k of the slice is the gradient of element k of the parameter's memory)"""
-        flat = self.flat[off:off + p.numel()]
+    @staticmethod
+    def view_like(buf, p, off):
+        """the slice of a flat per-element buffer (gradients, Adam moments) as a tensor of the parameter's logical shape
+        WITH THE PARAMETER'S STRIDES (channels_last conv weights are physically [O][kh][kw][I]: element k of the slice
+        belongs to element k of the parameter's memory)"""
+        flat = buf[off:off + p.numel()]
         if ops.is_ohwi(p):
             o, i, kh, kw = p.shape
             return flat.view(o, kh, kw, i).permute(0, 3, 1, 2)
         return flat.view_as(p)
+
+    def _view(self, p, off):
+        return self.view_like(self.flat, p, off)
 
     def attach(self):
         for p, off in zip(self.params, self.offsets):
@@ -152,8 +157,8 @@ class FusedAdam:
             for p, off in zip(self.grads.params, self.grads.offsets):
                 n = p.numel()
                 state[index[id(p)]] = {"step": torch.tensor(float(step)),
-                                       "exp_avg": self.exp_avg[off:off + n].view_as(p).clone(),
-                                       "exp_avg_sq": self.exp_avg_sq[off:off + n].view_as(p).clone()}
+                                       "exp_avg": FlatGrads.view_like(self.exp_avg, p, off).clone(),
+                                       "exp_avg_sq": FlatGrads.view_like(self.exp_avg_sq, p, off).clone()}
         group = {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": 0, "amsgrad": False,
                  "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
                  "decoupled_weight_decay": False, "params": list(range(len(self.all_params)))}
@@ -185,8 +190,8 @@ class FusedAdam:
             if tuple(st["exp_avg"].shape) != tuple(p.shape):
                 raise ValueError("FusedAdam.load_state_dict: moment shape mismatch for a parameter of shape "
                                  f"{tuple(p.shape)}")
-            self.exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1))
-            self.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+            FlatGrads.view_like(self.exp_avg, p, off).copy_(st["exp_avg"])
+            FlatGrads.view_like(self.exp_avg_sq, p, off).copy_(st["exp_avg_sq"])
             steps.add(int(float(st["step"])))
         if len(steps) > 1:
             raise ValueError(f"FusedAdam.load_state_dict: parameters carry different step counts {sorted(steps)}")

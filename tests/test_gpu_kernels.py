@@ -58,9 +58,10 @@ def rnd(t, dtype, cls="a"):
 
 
 def to_feat(t, dtype, cls="a"):
-    """internal feature tensor of class `cls` (the precision mode must already be set)"""
+    """external tensor -> internal feature tensor of class `cls` in the current precision mode's 16-bit format
+    (Functions handed a plain fp32 tensor compute in the fp32 family: precision follows the tensor)"""
     from pggan_b200 import ops
-    return ops.feat(t, cls)
+    return ops.enter(t, cls)
 
 
 def f32(t, cls="a"):
@@ -127,7 +128,7 @@ def test_conv_fprop(shape, backend, dtype):
     scale = (2.0 / (Ci * taps)) ** 0.5
     ref = F.leaky_relu((F.conv2d(x, w, b, padding=k // 2)) * scale, 0.2)
     if taps == 1:
-        y = ops.ConvF.apply(x.view(B, Ci), w.view(Co, Ci), b, scale, 0.2, False)
+        y = ops.ConvF.apply(to_feat(x.view(B, Ci), dtype), w.view(Co, Ci), b, scale, 0.2, False)
         ref = ref.view(B, Co)
     else:
         y = ops.ConvF.apply(to_feat(x, dtype), w, b, scale, 0.2, False)
@@ -137,10 +138,12 @@ def test_conv_fprop(shape, backend, dtype):
         assert after["tcgen05"] > before["tcgen05"], "tensor-core path did not run"
     else:
         assert after["simt"] > before["simt"]
-    # 4x4 maps and linear layers are fp32 islands in the 16-bit modes (ops.py): fp32 in, 3xTF32 GEMM, fp32 out
-    island = taps == 1 or H * W <= ops.SMALL_HW
-    assert y.dtype == (torch.float32 if island else ops.get_compute_dtype())
-    assert rel_l2(f32(y), ref) < (_TOL[torch.float32] if island else tol(dtype)), rel_l2(f32(y), ref)
+    assert y.dtype == ops.get_compute_dtype()
+    assert rel_l2(f32(y), ref) < tol(dtype), rel_l2(f32(y), ref)
+    if taps == 9 and dtype != torch.float32 and backend == 0 and B * H * W * Co * Ci < 2e8:
+        # precision follows the tensor: the same call on an fp32 tensor runs the 3xTF32 path and returns fp32
+        y32 = ops.ConvF.apply(x.contiguous(memory_format=torch.channels_last), w, b, scale, 0.2, False)
+        assert y32.dtype == torch.float32 and rel_l2(y32, ref) < _TOL[torch.float32]
 
 
 @pytest.mark.parametrize("dtype", DT)
@@ -187,10 +190,10 @@ def test_conv_dgrad_wgrad(shape, backend, dtype):
     (F.conv2d(xr, wr, br, padding=k // 2) * scale).backward(gy)
     xm, wm, bm = x.clone().requires_grad_(), w.clone().requires_grad_(), b.clone().requires_grad_()
     if taps == 1:
-        y = ops.ConvF.apply(xm.view(B, Ci), wm.view(Co, Ci), bm, scale, 1.0, False)
-        y.backward(gy.view(B, Co).to(y.dtype))
+        y = ops.ConvF.apply(to_feat(xm.view(B, Ci), dtype), wm.view(Co, Ci), bm, scale, 1.0, False)
+        y.backward(to_feat(gy.view(B, Co), dtype, "g"))
     else:
-        y = ops.ConvF.apply(xm, wm, bm, scale, 1.0, False)
+        y = ops.ConvF.apply(to_feat(xm, dtype), wm, bm, scale, 1.0, False)
         y.backward(to_feat(gy, dtype, "g"))
     assert rel_l2(xm.grad, xr.grad) < TOL[dtype], ("dgrad", rel_l2(xm.grad, xr.grad))
     # (mixed mode: the fp16 activation operand of the weight-gradient GEMM is re-rounded to bf16 — both tensor-core
@@ -218,7 +221,7 @@ def test_conv_double_backward(dtype):
         return g.detach().float(), ww.grad, xx.grad
 
     g_ref, gw_ref, _ = run(lambda xx, ww, bb: F.leaky_relu(F.conv2d(xx, ww, bb, padding=1) * 0.1, 0.2))
-    g_my, gw_my, _ = run(lambda xx, ww, bb: ops.ExportFloat.apply(ops.ConvF.apply(xx, ww, bb, 0.1, 0.2, False)))
+    g_my, gw_my, _ = run(lambda xx, ww, bb: ops.ExportFloat.apply(ops.ConvF.apply(to_feat(xx, dtype), ww, bb, 0.1, 0.2, False)))
     assert rel_l2(g_my, g_ref) < 2 * TOL[dtype]
     assert rel_l2(gw_my, gw_ref) < 4 * TOL[dtype], rel_l2(gw_my, gw_ref)
 
@@ -272,7 +275,7 @@ def test_elementwise(dtype):
     assert rel_l2(cs, 0.5 * f32(g, "g").sum(dim=(0, 2, 3))) < 1e-5
     # Upsample/Pool autograd pair
     xr = f32(x).clone().requires_grad_()
-    (ops.ExportFloat.apply(ops.Upsample2x.apply(xr, 1.0)) * f32(up)).sum().backward()
+    (ops.ExportFloat.apply(ops.Upsample2x.apply(to_feat(xr, dtype), 1.0)) * f32(up)).sum().backward()
     assert rel_l2(xr.grad, 4 * F.avg_pool2d(f32(up), 2)) < 2 * tol(dtype, "g")
 
 
@@ -288,7 +291,7 @@ def test_pixelnorm(C, dtype):
     g = rnd(torch.randn_like(x), dtype, "g")
     ref.backward(g)
     xm = x.clone().requires_grad_()
-    y = ops.PixelNorm.apply(xm, 1e-8)
+    y = ops.PixelNorm.apply(to_feat(xm, dtype), 1e-8)
     y.backward(to_feat(g, dtype, "g"))
     assert rel_l2(f32(y), ref) < tol(dtype)
     assert rel_l2(xm.grad, xr.grad) < 3 * tol(dtype, "g"), rel_l2(xm.grad, xr.grad)
@@ -401,7 +404,7 @@ def test_mbstd_single_sample_and_channel():
     ref = torch.sqrt(x.reshape(1, 6, -1).var(dim=1, unbiased=True) + 1e-8).mean()
     assert rel_l2(y[:, 64], ref.expand(6, 4, 4)) < 1e-5
     pg.set_compute_dtype("mixed")
-    y = concatenate_stddev_channel(x)                # exported as an honest fp16 tensor in mixed mode
+    y = concatenate_stddev_channel(ops.enter(x))     # exported as an honest fp16 tensor in mixed mode
     assert y.dtype == torch.float16 and rel_l2(y[:, 64].float(), ref.expand(6, 4, 4)) < 1e-3
 
 
@@ -428,12 +431,24 @@ def test_gp_reduce_and_r1():
     assert rel_l2(ops.RowsSumSq.apply(h), (h ** 2).sum(1)) < 1e-5
 
 
+def _lib_other_launches():
+    from pggan_b200 import _lib
+    return _lib.launch_counts()["other"]
+
+
 def test_fused_adam_matches_torch():
     from pggan_b200 import FusedAdam
     torch.manual_seed(1)
-    shapes = [(512, 512, 3, 3), (512,), (3, 64, 1, 1), (1, 512), (1,), (70000,)]
+    from pggan_b200 import ops
+    import pggan_b200 as pg
+    pg.set_compute_dtype(torch.float16)
+    shapes = [(512, 512, 3, 3), (512,), (3, 64, 1, 1), (1, 512), (1,), (70000,), (64, 32, 3, 3)]
     mine = [torch.nn.Parameter(torch.randn(s, device="cuda")) for s in shapes]
-    ref = [torch.nn.Parameter(p.detach().clone()) for p in mine]
+    # 3x3 conv weights live in channels_last memory ([O][kh][kw][I]) as layers.py keeps them
+    mine[0].data = mine[0].data.contiguous(memory_format=torch.channels_last)
+    mine[6].data = mine[6].data.contiguous(memory_format=torch.channels_last)
+    assert ops.is_ohwi(mine[0]) and not ops.is_ohwi(mine[2])
+    ref = [torch.nn.Parameter(p.detach().clone().contiguous()) for p in mine]
     opt_m = FusedAdam(mine, lr=1e-3, betas=(0.0, 0.99))
     opt_r = torch.optim.Adam(ref, lr=1e-3, betas=(0.0, 0.99))
     for step in range(4):
@@ -448,6 +463,18 @@ def test_fused_adam_matches_torch():
     for pm, pr in zip(mine, ref):
         assert rel_l2(pm, pr) < 1e-6
     assert int(opt_m.step_count.item()) == 4
+    # the Adam kernel maintains the packed fp16 fprop operand of the channels_last conv weights (no pack kernel)
+    for k in (0, 6):
+        before = _lib_other_launches()
+        wp = ops._pack(mine[k], "f")
+        assert _lib_other_launches() == before, "the shadow copy must be served without a pack launch"
+        O_, I_ = mine[k].shape[:2]
+        assert torch.equal(wp, mine[k].detach().permute(0, 2, 3, 1).reshape(O_, 9 * I_).to(torch.float16))
+        # ... the dgrad operand [i][8-t][o] comes from the tiled transpose kernel
+        wt = ops._pack(mine[k], "t", fmt=ops._fmt("g"))
+        assert torch.equal(wt, mine[k].detach().flip(2, 3).permute(1, 2, 3, 0).reshape(I_, 9 * O_).to(torch.float16))
+    mine[6].data.mul_(1.0)                              # a version bump (e.g. load_state_dict) invalidates the shadow
+    assert torch.equal(ops._pack(mine[6], "f"), mine[6].detach().permute(0, 2, 3, 1).reshape(64, 9 * 32).to(torch.float16))
     # optimizer state in torch.optim.Adam's wire format, both directions (reference pggan/model.py:97-101)
     sd_m, sd_r = opt_m.state_dict(), opt_r.state_dict()
     assert sorted(sd_m["state"].keys()) == sorted(sd_r["state"].keys())
@@ -506,3 +533,43 @@ def test_conv_fused_pixelnorm(shape, dtype):
     assert rel_l2(f32(ym), ref) < tol(dtype)
     assert not ops.conv_pn_fusable(to_feat(rnd(torch.randn(2, 256, 32, 32, device="cuda"), dtype), dtype), 128, 9) \
         or dtype == torch.float32, "256->128 (K = 2304) runs on the swapped kernel: must not be reported fusable"
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("shape", [(2, 8, 8, 64, 64), (3, 4, 4, 512, 512), (2, 16, 16, 512, 256), (1, 64, 64, 256, 128),
+                                   (2, 64, 64, 128, 64), (5, 32, 32, 128, 128), (1, 128, 128, 128, 64)])
+def test_conv_fused_upsample(shape, dtype):
+    """conv3x3(upscale2d(x)) as ONE kernel (the up-sampling is the GEMM's prologue: parity tiles reading shifted boxes
+    of the low-resolution tensor) against F.conv2d on the materialised up-sampled tensor; then G's whole
+    upscale -> conv -> LeakyReLU -> pixel norm chain (ops.ConvActPN with up2) with its gradients."""
+    from pggan_b200 import ops
+    import pggan_b200 as pg
+    pg.set_compute_dtype(dtype)
+    B, H, W, Ci, Co = shape                      # H, W: LOW resolution
+    x = rnd(torch.randn(B, Ci, H, W, device="cuda"), dtype)
+    w = rnd(torch.randn(Co, Ci, 3, 3, device="cuda"), dtype)
+    b = torch.randn(Co, device="cuda")
+    scale = (2.0 / (Ci * 9)) ** 0.5
+    xf = to_feat(x, dtype)
+    assert ops.conv_up2_fusable(xf, Co), "these shapes run on the plain tensor-core kernel"
+    up = x.repeat_interleave(2, 2).repeat_interleave(2, 3)
+    ref = F.leaky_relu(F.conv2d(up, w, b, padding=1) * scale, 0.2)
+    y = ops.k_conv(xf, ops._pack(w, "f", fmt=ops._fmt_of(xf, "a")), b, Co, 9, scale, 0.2, up2=True)
+    assert y.shape == (B, Co, 2 * H, 2 * W) and y.is_contiguous(memory_format=torch.channels_last)
+    assert rel_l2(f32(y), ref) < tol(dtype), rel_l2(f32(y), ref)
+    # the unfused pair gives the same bits (same MMAs in the same order on the same operands)
+    y2 = ops.k_conv(ops.k_upsample(xf, 1.0), ops._pack(w, "f", fmt=ops._fmt_of(xf, "a")), b, Co, 9, scale, 0.2)
+    assert torch.equal(y, y2)
+    # the whole G-block chain and its backward
+    xr, wr, br = x.clone().requires_grad_(), w.clone().requires_grad_(), b.clone().requires_grad_()
+    a = F.leaky_relu(F.conv2d(xr.repeat_interleave(2, 2).repeat_interleave(2, 3), wr, br, padding=1) * scale, 0.2)
+    r = a * torch.rsqrt((a ** 2).mean(dim=1, keepdim=True) + 1e-8)
+    gy = rnd(torch.randn_like(r), dtype, "g")
+    r.backward(gy)
+    xm, wm, bm = x.clone().requires_grad_(), w.clone().requires_grad_(), b.clone().requires_grad_()
+    ym = ops.ConvActPN.apply(to_feat(xm, dtype), wm, bm, scale, 0.2, 1e-8, None, True)
+    ym.backward(to_feat(gy, dtype, "g"))
+    assert rel_l2(f32(ym), r) < tol(dtype)
+    assert rel_l2(xm.grad, xr.grad) < 4 * tol(dtype, "g"), rel_l2(xm.grad, xr.grad)
+    assert rel_l2(wm.grad, wr.grad) < 4 * tol(dtype, "g"), rel_l2(wm.grad, wr.grad)
+    assert rel_l2(bm.grad, br.grad) < 4 * tol(dtype, "g")

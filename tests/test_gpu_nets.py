@@ -181,9 +181,10 @@ def _moment_err(opt, ref_opt, ref_named, mod):
         st = ref_opt.state.get(ref_named[k])
         if not st:
             continue
-        off, n = opt.grads.offsets[idx[id(p)]], p.numel()
-        mine = opt.exp_avg_sq[off:off + n].double().sqrt()
-        ref = st["exp_avg_sq"].reshape(-1).double().sqrt()
+        from pggan_b200.optim import FlatGrads
+        off = opt.grads.offsets[idx[id(p)]]
+        mine = FlatGrads.view_like(opt.exp_avg_sq, p, off).double().sqrt()      # logical shape (channels_last strides)
+        ref = st["exp_avg_sq"].double().sqrt()
         num += float((mine - ref).pow(2).sum())
         den += float(ref.pow(2).sum())
     return (num / max(den, 1e-300)) ** 0.5

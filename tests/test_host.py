@@ -204,10 +204,11 @@ def test_precision_modes_and_tensor_classes():
         pg.set_compute_dtype("mixed")
         # an fp32 tensor imported as an activation becomes fp16 BITS under the bf16 label; to_float reads them back
         x = torch.tensor([1.0, 0.333251953125, -2.5, 70000.0])
-        xi = ops.feat(x, "a")
+        xi = ops.enter(x, "a")
         assert xi.dtype == torch.bfloat16 and torch.equal(xi.view(torch.float16), x.to(torch.float16))
         assert torch.equal(ops.to_float(xi, "a")[:3], x.to(torch.float16).float()[:3])
-        gi = ops.feat(x, "g")                                       # gradient class: honest bf16
+        gi = ops.enter(x, "g")                                      # gradient class: honest bf16
+        assert ops.feat(x, "a").dtype == torch.float32              # precision follows the tensor: fp32 stays fp32
         assert gi.dtype == torch.bfloat16 and torch.equal(gi, x.to(torch.bfloat16))
         # alpha coefficients
         c = ops._coef(ops._affine(1.0, -1.0, 0.25))
