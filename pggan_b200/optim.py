@@ -127,6 +127,22 @@ class FusedAdam:
         self._chunk_offset = torch.tensor(chunk_offset, dtype=torch.int64, device=dev)
         self._n_tensors, self._n_chunks = len(g.params), len(chunk_tensor)
         self._param_ptrs = [p.data_ptr() for p in g.params]
+        self.sync_shadows()
+
+    def sync_shadows(self):
+        """(re)write the packed 16-bit fprop copies from the current parameter values and mark them valid — at
+        construction, and after anything but this optimizer's own step changed the parameters (load_state_dict,
+        the capture warm-up's restore)"""
+        for p in self._shadowed:
+            key = (id(p), "f", ops._ACT_FMT, None)
+            ent = ops._SHADOWS.get(key)
+            if ent is None or ent[0] is not p:
+                continue
+            o, i, kh, kw = p.shape
+            src = p.detach().permute(0, 2, 3, 1).reshape(-1)           # the parameter's memory, in order
+            L.check(L.load().pggan_convert(ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(ent[1].data_ptr()),
+                                           p.numel(), L.PG_F32, ops._ACT_FMT, ops._s()), "pggan_convert")
+        ops.shadows_synced(self._shadowed)
 
     # torch.optim.Optimizer-like surface used by update_net (reference lib/utils.py:72-75)
     def zero_grad(self, set_to_none: bool = False):
@@ -196,3 +212,4 @@ class FusedAdam:
         if len(steps) > 1:
             raise ValueError(f"FusedAdam.load_state_dict: parameters carry different step counts {sorted(steps)}")
         self.step_count.fill_(steps.pop() if steps else 0)
+        self.sync_shadows()

@@ -153,6 +153,8 @@ class ProgressiveGAN:
         self.D.load_state_dict(D_ckpt_dict["model"], strict=False)
         self.opt_D.load_state_dict(D_ckpt_dict["optimizer"])
         ops.clear_pack_cache()
+        self.opt_G.sync_shadows()
+        self.opt_D.sync_shadows()
         return self.global_step
 
     # --------------------------------------------------------------------- schedule (model.py:131-204)
@@ -296,6 +298,8 @@ class ProgressiveGAN:
                 o.exp_avg_sq.copy_(v)
                 o.step_count.copy_(st)
         ops.clear_pack_cache()
+        self.opt_G.sync_shadows()          # the copy_ above bumped the parameters' versions
+        self.opt_D.sync_shadows()
 
     def capture(self, batch: int, resolution: Optional[int] = None, warmup: int = 3):
         """Capture one whole train_step (3 D + 2 G passes, double backward, both Adam updates, and under data
