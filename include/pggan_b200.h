@@ -219,6 +219,24 @@ int pggan_image_fade(const float* x, const float* low, float* out, int B, int Ci
 int pggan_image_pool_sum(const float* x, float* out, int B, int Cimg, int H, int W, pg_coef scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * GPU input pipeline: the transform chain of UnsupervisedDataset (lib/dataset.py:100-111) and the
+ * real-image fade of train_step (pggan/model.py:217-221) on decoded image batches.  Arithmetic = torchvision's
+ * float-tensor backend (same formulas and operation order, fp32; the PIL backend the reference uses quantises to uint8
+ * after every operation).
+ */
+/* anti-aliased bilinear resize (transforms.Resize((Ho,Wo)) — the triangle filter of half-width max(scale,1) that PIL /
+ * torchvision apply): src [planes][Hs][Ws] uint8 (src_is_u8) or fp32, times in_mul (1/255 for uint8 -> [0,1]);
+ * tmp: planes*Hs*Wo floats; dst [planes][Ho][Wo] fp32 */
+int pggan_resize_aa(const void* src, int src_is_u8, float* tmp, float* dst, int planes, int Hs, int Ws, int Ho, int Wo,
+                    float in_mul, void* stream);
+/* out [B,3,S,S] = fade( Normalize(0.5,0.5)( hflip?( ColorJitter(img) ) ) ), img [B,3,S,S] fp32 in [0,1].
+ * iparams [B][5] = {flip, op0..op3} (op: 0 brightness, 1 contrast, 2 saturation, 3 hue — the sample's random order,
+ * transforms.ColorJitter.forward), fparams [B][4] = the four factors; mean_ws: B floats of workspace (the grey mean
+ * contrast blends with).  fade != 0: out = (1-alpha)*up2(avgpool2(.)) + alpha*(.)  (pggan/model.py:217-221). */
+int pggan_jitter_normalize_fade(const float* img, const int32_t* iparams, const float* fparams, float* mean_ws, float* out,
+                                int B, int S, int fade, pg_coef alpha, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Minibatch standard deviation (lib/blocks.py:204-233): groups of `group` consecutive samples,
  * unbiased variance, eps inside sqrt, mean over (C,H,W).  x is [B][K] (K = H*W*C, any order).
  */

@@ -17,5 +17,7 @@ from .optim import FusedAdam, FlatGrads  # noqa: F401
 from .dist import GradSync, broadcast_parameters  # noqa: F401
 from .trainer import ProgressiveGAN, make_args, DEPTHS_1024  # noqa: F401
 from . import demo  # noqa: F401
+from .data import GPUInputPipeline  # noqa: F401
+from .ops import get_precision_mode  # noqa: F401
 
 __version__ = "0.1.0"

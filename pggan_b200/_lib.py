@@ -93,6 +93,9 @@ SIGNATURES = {
                                 c_float, c_int, c_void_p]),
     "pggan_image_fade": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, Coef, c_void_p]),
     "pggan_image_pool_sum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, Coef, c_void_p]),
+    "pggan_resize_aa": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "pggan_jitter_normalize_fade": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, Coef,
+                                            c_void_p]),
     "pggan_mbstd_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p]),
     "pggan_mbstd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int, c_void_p]),
     "pggan_mbstd_bwd2": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int,

@@ -760,6 +760,8 @@ class ConvF(torch.autograd.Function):
         need_b = ctx.has_bias and ctx.needs_input_grad[2] and not _SKIP_PARAM_GRADS
         gx = gW = gb = None
         xm, xs = (x, ctx.x_act_slope) if ctx.x_act_slope is not None else (None, 1.0)
+        if ctx.w_param is not None:
+            W = ctx.w_param              # the Parameter object itself (gradient sink / packed-copy cache are keyed by it)
         if torch.is_grad_enabled():
             # create_graph=True: stay composable (every piece is a differentiable Function)
             if ctx.mask_here:
@@ -883,6 +885,7 @@ class ConvT(torch.autograd.Function):
                     mask_slope=mask_slope, xc=G)
         ctx.save_for_backward(g, W, mask_src)
         ctx.scale, ctx.layout, ctx.mask_slope = scale, layout, mask_slope
+        ctx.w_param = W if isinstance(W, torch.nn.Parameter) else None
         return gx
 
     @staticmethod
@@ -892,10 +895,18 @@ class ConvT(torch.autograd.Function):
         if mask_src is not None:
             ggx = MaskMul.apply(ggx, mask_src, ctx.mask_slope)
         dg = dW = None
+        if ctx.w_param is not None:
+            W = ctx.w_param
         if ctx.needs_input_grad[0]:
             dg = ConvF.apply(ggx, W, None, ctx.scale, 1.0, False, ctx.layout, None, False, G)
         if ctx.needs_input_grad[1] and not _SKIP_PARAM_GRADS:
-            dW = ConvW.apply(g, ggx, ctx.scale, tuple(W.shape), ctx.layout, G)
+            w_sink = _sink(ctx.w_param) if not torch.is_grad_enabled() else None
+            if w_sink is not None:
+                # the penalty's own backward (plain, no higher order): accumulate d/dW of the dgrad straight into .grad
+                k_wgrad(g, ggx, ctx.scale, tuple(W.shape), ctx.layout, accumulate_into=w_sink, xc=G)
+                _sunk(ctx.w_param)
+            else:
+                dW = ConvW.apply(g, ggx, ctx.scale, tuple(W.shape), ctx.layout, G)
         return dg, dW, None, None, None, None
 
 
