@@ -250,20 +250,23 @@ class ProgressiveGAN:
             if self.sync_D is not None:
                 self.sync_D.arm()
             (loss_D * self.loss_scale if self.loss_scale != 1.0 else loss_D).backward()
-            if self.sync_D is not None:
-                self.sync_D.finish()
-        self.opt_D.step()
         nvtx.range_pop()
 
         # ---- Train G ----
         nvtx.range_push("G step (G forward, D forward, backward, Adam)")
         if latent_G is None:
             latent_G = torch.randn(n_samples, a.latent_dim).to(self.device)
+        # G's forward does not read D: under data parallelism it runs while the tail of D's gradient all-reduce is still
+        # on the wire; D's Adam step (which needs the reduced gradients) follows it.  Same arithmetic, same order of
+        # parameter updates as pggan/model.py:238-253.
+        img_fake = self.G(latent_G)
+        if self.sync_D is not None:
+            self.sync_D.finish()
+        self.opt_D.step()
         d_params = [p for p in self.D.parameters() if p.requires_grad]
         for p in d_params:
             p.requires_grad_(False)
         try:
-            img_fake = self.G(latent_G)
             pred_fake, _ = self.D(img_fake, True)
             loss_G = lc.get_loss_G({"pred_fake": pred_fake})
             self.opt_G.zero_grad()
