@@ -177,6 +177,11 @@ def bench_config(args, workload, steps, warm, full, rank, world, local):
     import pggan_b200 as pg
     from pggan_b200 import _lib, ops
     dev = torch.device("cuda", local)
+    # nvidia-smi needs up to a second before its first sample: start it now (model build, eager steps and the graph
+    # capture follow), so that it is streaming long before the timed region
+    sampler = ClockSampler(local)
+    if rank == 0 and full:
+        sampler.start()
     scale, batch, depths, gflop_img = WORKLOADS[workload]
     if args.batch and full:
         batch = args.batch
@@ -259,9 +264,6 @@ def bench_config(args, workload, steps, warm, full, rank, world, local):
             ms = float(t.item())
         return ms
 
-    sampler = ClockSampler(local)
-    if rank == 0 and full:
-        sampler.start()
     for _ in range(warm):
         step_resident()
     torch.cuda.synchronize()
