@@ -173,6 +173,10 @@ int pggan_upsample2x(const void* x, void* out, int B, int H, int W, int C, pg_co
  * avg_pool2d_backward + leaky_relu_backward */
 int pggan_upsample2x_mask(const void* x, const void* mask_src, void* out, int B, int H, int W, int C, pg_coef scale,
                           float slope, int dtype, void* stream);
+/* ... and with the bias gradient of that conv in the same pass: colsum[c] += cs_scale * sum over output pixels of
+ * out[.,c] (autograd's bias gradient of lib/layers.py:62 for the second conv of a D block); C/VN must divide 256 */
+int pggan_upsample2x_mask_colsum(const void* x, const void* mask_src, void* out, float* colsum, int B, int H, int W,
+                                 int C, pg_coef scale, float slope, float cs_scale, int dtype, void* stream);
 /* out[b,h,w,c] = scale * sum_{i,j<2} x[b,2h+i,2w+j,c]; if blend_with != NULL:
  * out = (1-alpha)*blend_with + alpha*that   — nn.AvgPool2d(2) lib/blocks.py:193 (+ fade pggan/nets.py:265) */
 int pggan_pool2x2(const void* x, const void* blend_with, void* out, int B, int H, int W, int C, pg_coef scale,

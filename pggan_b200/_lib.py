@@ -76,6 +76,8 @@ SIGNATURES = {
     "pggan_upsample2x": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, Coef, c_int, c_void_p]),
     "pggan_upsample2x_mask": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, Coef, c_float, c_int,
                                       c_void_p]),
+    "pggan_upsample2x_mask_colsum": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, Coef,
+                                             c_float, c_float, c_int, c_void_p]),
     "pggan_pool2x2": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, Coef, Coef, c_int,
                               c_void_p]),
     "pggan_axpby": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, Coef, Coef, c_int, c_void_p]),

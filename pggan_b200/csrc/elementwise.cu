@@ -149,6 +149,63 @@ __global__ void upsample2x_kernel(const T* __restrict__ x, const T* __restrict__
     }
 }
 
+// avg-pool backward + LeakyReLU mask as above, plus the bias gradient of the conv that produced the pooled activation:
+// colsum[c] += cs_scale * sum over OUTPUT pixels of out[., c] (the values as rounded to T, so the result equals a
+// separate column-sum pass over `out` — which this kernel saves).  Threads: tx = fixed channel vector, ty = input-pixel
+// lane; per-thread partial sums meet in shared memory, one atomicAdd per (block, channel).
+template <typename T>
+__global__ void __launch_bounds__(256)
+upsample2x_mask_colsum_kernel(const T* __restrict__ x, const T* __restrict__ mask_src, T* __restrict__ out,
+                              float* __restrict__ colsum, int B, int H, int W, int C, pg_coef cscale, float slope,
+                              float cs_scale, int TX, long long rows_per_block) {
+    constexpr int VN = V16<T>::N;
+    __shared__ float red[256 * VN];
+    const float scale = coef_val(cscale);
+    const int TY = blockDim.x / TX;
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    const long long M = static_cast<long long>(B) * H * W;
+    const long long r0 = blockIdx.x * rows_per_block;
+    long long r1 = r0 + rows_per_block;
+    if (r1 > M) r1 = M;
+    const long long Cl = C;
+    const long long offs[4] = {0, Cl, 2LL * W * Cl, 2LL * W * Cl + Cl};
+    float acc[VN];
+#pragma unroll
+    for (int e = 0; e < VN; ++e) acc[e] = 0.f;
+    for (long long m = r0 + ty; m < r1; m += TY) {
+        const int w = static_cast<int>(m % W);
+        const long long t = m / W;
+        const int h = static_cast<int>(t % H);
+        const long long b = t / H;
+        V16<T> v = ld16(x + m * Cl + tx * VN);
+        const long long ooff = ((b * 2 * H + 2 * h) * 2 * W + 2 * w) * Cl + tx * VN;
+        V16<T> mv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mv[k] = ld16(mask_src + ooff + offs[k]);
+        float vs[VN];
+#pragma unroll
+        for (int e = 0; e < VN; ++e) vs[e] = v.get(e) * scale;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            V16<T> r;
+#pragma unroll
+            for (int e = 0; e < VN; ++e) {
+                r.set(e, mv[k].pos(e) ? vs[e] : vs[e] * slope);
+                acc[e] += r.get(e);
+            }
+            st16(out + ooff + offs[k], r);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < VN; ++e) red[threadIdx.x * VN + e] = acc[e];
+    __syncthreads();
+    for (int o = threadIdx.x; o < TX * VN; o += blockDim.x) {
+        float t = 0.f;
+        for (int yy = 0; yy < TY; ++yy) t += red[yy * TX * VN + o];
+        atomicAdd(colsum + o, t * cs_scale);
+    }
+}
+
 // one thread per (output pixel, channel vector); x is [B,H,W,C], out [B,H/2,W/2,C]
 template <typename T>
 __global__ void pool2x2_kernel(const T* __restrict__ x, const T* __restrict__ blend, T* __restrict__ out, int B, int H,
@@ -831,6 +888,35 @@ extern "C" int pggan_upsample2x_mask(const void* x, const void* mask_src, void* 
                                      pg_coef scale, float slope, int dtype, void* stream) {
     PG_CHECK(mask_src != nullptr, PG_ERR_ARG, "pggan_upsample2x_mask: null mask_src");
     return upsample2x_impl(x, mask_src, out, B, H, W, C, scale, slope, dtype, stream, "pggan_upsample2x_mask");
+}
+
+extern "C" int pggan_upsample2x_mask_colsum(const void* x, const void* mask_src, void* out, float* colsum, int B, int H,
+                                            int W, int C, pg_coef scale, float slope, float cs_scale, int dtype,
+                                            void* stream) {
+    PG_CHECK(x && mask_src && out && colsum && B > 0 && H > 0 && W > 0 && C > 0, PG_ERR_ARG,
+             "pggan_upsample2x_mask_colsum: bad args");
+    PG_CHECK(al16(x) && al16(mask_src) && al16(out), PG_ERR_ARG, "pggan_upsample2x_mask_colsum: pointers must be 16-byte aligned");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    DISPATCH_T(dtype, {
+        constexpr int VN = V16<T>::N;
+        PG_CHECK(C % VN == 0 && (C / VN) <= 256 && 256 % (C / VN) == 0, PG_ERR_UNSUPPORTED,
+                 "pggan_upsample2x_mask_colsum: C/%d = %d must divide 256", VN, C / VN);
+        const int TX = C / VN, TY = 256 / TX;
+        const long long m = (long long)B * H * W;
+        long long rpb = (long long)TY * 8;
+        long long blocks = (m + rpb - 1) / rpb;
+        const long long cap = (long long)num_sms() * 16;
+        if (blocks > cap) {
+            blocks = cap;
+            rpb = (m + blocks - 1) / blocks;
+        }
+        const int grid = (int)((m + rpb - 1) / rpb);
+        upsample2x_mask_colsum_kernel<T><<<grid, 256, 0, s>>>((const T*)x, (const T*)mask_src, (T*)out, colsum, B, H, W, C,
+                                                              scale, slope, cs_scale, TX, rpb);
+    });
+    PG_LAUNCH_CHECK();
+    g_other_launches++;
+    return PG_OK;
 }
 
 extern "C" int pggan_pool2x2(const void* x, const void* blend_with, void* out, int B, int H, int W, int C, pg_coef scale,

@@ -507,6 +507,40 @@ def clear_pack_cache(params=None):
         del _PACK_CACHE[k]
 
 
+# ------------------------------------------------------------------------------- mask hand-shake (double backward)
+FUSE_DOUBLE_BACKWARD_MASKS = True       # tests switch it off to compare against the unfused composition
+
+
+class _MaskLink:
+    """Hand-shake between a Function that multiplies its output by a LeakyReLU mask in the FIRST backward (the producer:
+    a ConvT with mask_src, UpsampleMask, MaskMul) and the ConvT that consumes that output.  In the double backward the
+    roles swap: the producer's backward starts by masking the incoming gradient, and that gradient is the output of the
+    consumer's backward conv — so the consumer applies the mask in its GEMM epilogue and leaves its output's address in
+    `token`; the producer then skips its own pass (one read + one write of the feature map saved per layer).
+    Only offered when the consumer is the producer output's only user (`sole`), so autograd cannot have summed anything
+    into the gradient in between; a token that does not match the incoming gradient raises."""
+    __slots__ = ("token",)
+
+    def __init__(self):
+        self.token = None
+
+
+def _tag_masked(out, link, y, slope):
+    out._pg_mask = (link, y, slope)
+    return out
+
+
+def _premasked(link, gg) -> bool:
+    """did the consumer's backward already apply this producer's mask to gg?"""
+    if link is None or link.token is None:
+        return False
+    tok, link.token = link.token, None
+    if tok != (gg.data_ptr(), tuple(gg.shape)):
+        raise RuntimeError("pggan_b200: a pre-masked gradient was replaced before it reached the masking Function "
+                           "(the dgrad's output has more than one user?)")
+    return True
+
+
 # ------------------------------------------------------------------------------- raw kernels
 _KIND_CACHE: dict = {}
 
@@ -686,10 +720,16 @@ def k_colsum(g, scale, cls=G):
     return out
 
 
-def k_upsample(x, scale, mask_src=None, slope=1.0, cls=A):
-    """scale: a float or an _affine() coefficient"""
+def k_upsample(x, scale, mask_src=None, slope=1.0, cls=A, colsum=None, colsum_scale=1.0):
+    """scale: a float or an _affine() coefficient.  colsum (with mask_src): an fp32 [C] tensor that receives
+    += colsum_scale * (column sums of the result) in the same pass."""
     b, c, h, w = _dims(x)
     out = _new_like_layout(x, c, x.dtype, 2 * h, 2 * w)
+    if mask_src is not None and colsum is not None:
+        L.check(L.load().pggan_upsample2x_mask_colsum(_p(x), _p(mask_src), _p(out), _p(colsum), b, h, w, c, _coef(scale),
+                                                      float(slope), float(colsum_scale), _fmt_of(x, cls), _s()),
+                "pggan_upsample2x_mask_colsum")
+        return out
     if mask_src is not None:
         L.check(L.load().pggan_upsample2x_mask(_p(x), _p(mask_src), _p(out), b, h, w, c, _coef(scale), float(slope),
                                                _fmt_of(x, cls), _s()), "pggan_upsample2x_mask")
@@ -697,6 +737,12 @@ def k_upsample(x, scale, mask_src=None, slope=1.0, cls=A):
     L.check(L.load().pggan_upsample2x(_p(x), _p(out), b, h, w, c, _coef(scale), _fmt_of(x, cls), _s()),
             "pggan_upsample2x")
     return out
+
+
+def upsample_colsum_fusable(x, cls=G) -> bool:
+    c = _dims(x)[1]
+    vn = _vn(_fmt_of(x, cls))
+    return x.dim() == 4 and c % vn == 0 and (c // vn) <= 256 and 256 % (c // vn) == 0
 
 
 def k_pool(x, scale, blend_with=None, alpha=1.0, cls=A):
@@ -765,15 +811,24 @@ class ConvF(torch.autograd.Function):
         if torch.is_grad_enabled():
             # create_graph=True: stay composable (every piece is a differentiable Function)
             if ctx.mask_here:
-                g = MaskMul.apply(g, y, ctx.slope)
+                link = _MaskLink()
+                g = _tag_masked(MaskMul.apply(g, y, ctx.slope, link), link, y, ctx.slope)
             if need_b:
                 gb = ColSum.apply(g, ctx.scale)
         else:
             # plain backward: LeakyReLU mask and bias gradient in one pass over g; gradients of registered
             # parameters are accumulated in place (see _GRAD_SINK)
             b_sink = _sink(ctx.bias_param) if (need_b and not (ctx.layout and ctx.layout[0] == "lin_out_perm")) else None
-            g, gb = k_mask_colsum(g, y if ctx.mask_here else None, ctx.slope, True,
-                                  ctx.scale if need_b else None, colsum_into=b_sink)
+            pre = getattr(gy, "_pg_colsum", None) if (need_b and not ctx.mask_here and g is gy) else None
+            if pre is not None:
+                # the pool backward that produced gy already summed its columns (_upsample_mask)
+                if b_sink is not None:
+                    b_sink.add_(pre, alpha=ctx.scale)
+                else:
+                    gb = pre * ctx.scale
+            else:
+                g, gb = k_mask_colsum(g, y if ctx.mask_here else None, ctx.slope, True,
+                                      ctx.scale if need_b else None, colsum_into=b_sink)
             if b_sink is not None:
                 _sunk(ctx.bias_param)
             if gb is not None:
@@ -789,7 +844,10 @@ class ConvF(torch.autograd.Function):
         if gb is not None:
             gb = _perm_bias(gb, ctx.layout, inverse=True)
         if ctx.needs_input_grad[0]:
-            gx = ConvT.apply(g, W, ctx.scale, ctx.layout, xm, xs)
+            link = _MaskLink() if xm is not None else None
+            gx = ConvT.apply(g, W, ctx.scale, ctx.layout, xm, xs, link, not (need_w or need_b))
+            if link is not None:
+                _tag_masked(gx, link, xm, xs)
         if need_w:
             gW = ConvW.apply(g, x, ctx.scale, tuple(W.shape), ctx.layout, ctx.xc)
         return gx, gW, gb, None, None, None, None, None, None, None
@@ -876,29 +934,42 @@ class ConvT(torch.autograd.Function):
     """gx = scale * conv_transpose(g, W)   [dgrad: the same kernel on flipped/transposed weights]"""
 
     @staticmethod
-    def forward(ctx, g, W, scale, layout=None, mask_src=None, mask_slope=1.0):
+    def forward(ctx, g, W, scale, layout=None, mask_src=None, mask_slope=1.0, link=None, sole=False):
         """mask_src: gx is additionally multiplied by (mask_src > 0 ? 1 : mask_slope) in the GEMM epilogue
-        (the LeakyReLU backward of the layer that produced this conv's input)."""
+        (the LeakyReLU backward of the layer that produced this conv's input); link: this Function's _MaskLink then.
+        sole: this Function is the only user of g — if g's producer masked it (tag left by _tag_masked), the double
+        backward applies that mask in the epilogue of the conv below instead of in a pass of its own."""
+        ctx.out_mask = getattr(g, "_pg_mask", None) if (sole and FUSE_DOUBLE_BACKWARD_MASKS) else None
         g = feat(g, G)
+        if ctx.out_mask is not None and ctx.out_mask[1].element_size() != g.element_size():
+            ctx.out_mask = None
         N, C, taps, _, _ = _maps(W.shape, layout)
         gx = k_conv(g, _pack(W, "t", None, layout, _fmt_of(g, G)), None, C, taps, scale, mask_src=mask_src,
                     mask_slope=mask_slope, xc=G)
         ctx.save_for_backward(g, W, mask_src)
-        ctx.scale, ctx.layout, ctx.mask_slope = scale, layout, mask_slope
+        ctx.scale, ctx.layout, ctx.mask_slope, ctx.link = scale, layout, mask_slope, link
         ctx.w_param = W if isinstance(W, torch.nn.Parameter) else None
         return gx
 
     @staticmethod
     def backward(ctx, ggx):
         g, W, mask_src = ctx.saved_tensors
+        pre = mask_src is not None and _premasked(ctx.link, ggx)
         ggx = feat(ggx, G, small=(g.dtype == torch.float32))
-        if mask_src is not None:
+        if mask_src is not None and not pre:
             ggx = MaskMul.apply(ggx, mask_src, ctx.mask_slope)
         dg = dW = None
         if ctx.w_param is not None:
             W = ctx.w_param
         if ctx.needs_input_grad[0]:
-            dg = ConvF.apply(ggx, W, None, ctx.scale, 1.0, False, ctx.layout, None, False, G)
+            if ctx.out_mask is not None and not torch.is_grad_enabled() and ggx.dtype == g.dtype:
+                link, ym, sl = ctx.out_mask
+                N, C, taps, _, _ = _maps(W.shape, ctx.layout)
+                dg = k_conv(ggx, _pack(W, "f", None, ctx.layout, _fmt_of(ggx, G)), None, N, taps, ctx.scale, mask_src=ym,
+                            mask_slope=sl, xc=G)
+                link.token = (dg.data_ptr(), tuple(dg.shape))
+            else:
+                dg = ConvF.apply(ggx, W, None, ctx.scale, 1.0, False, ctx.layout, None, False, G)
         if ctx.needs_input_grad[1] and not _SKIP_PARAM_GRADS:
             w_sink = _sink(ctx.w_param) if not torch.is_grad_enabled() else None
             if w_sink is not None:
@@ -907,7 +978,7 @@ class ConvT(torch.autograd.Function):
                 _sunk(ctx.w_param)
             else:
                 dW = ConvW.apply(g, ggx, ctx.scale, tuple(W.shape), ctx.layout, G)
-        return dg, dW, None, None, None, None
+        return dg, dW, None, None, None, None, None, None
 
 
 class ConvW(torch.autograd.Function):
@@ -952,19 +1023,21 @@ class ColSum(torch.autograd.Function):
 
 
 class MaskMul(torch.autograd.Function):
-    """g * (y > 0 ? 1 : slope): LeakyReLU backward from the saved OUTPUT (sign(y) == sign(pre))."""
+    """g * (y > 0 ? 1 : slope): LeakyReLU backward from the saved OUTPUT (sign(y) == sign(pre)).  link: see _MaskLink."""
 
     @staticmethod
-    def forward(ctx, g, y, slope):
+    def forward(ctx, g, y, slope, link=None):
         g = feat(g, G, small=(y.dtype == torch.float32))
         ctx.save_for_backward(y)
-        ctx.slope = slope
+        ctx.slope, ctx.link = slope, link
         return k_mask_mul(g, y, slope, G)
 
     @staticmethod
     def backward(ctx, gg):
         (y,) = ctx.saved_tensors
-        return MaskMul.apply(feat(gg, G, small=(y.dtype == torch.float32)), y, ctx.slope), None, None
+        if _premasked(ctx.link, gg):
+            return gg, None, None, None
+        return MaskMul.apply(feat(gg, G, small=(y.dtype == torch.float32)), y, ctx.slope), None, None, None
 
 
 # ------------------------------------------------------------------ resampling / blend Functions
@@ -985,19 +1058,36 @@ class Upsample2x(torch.autograd.Function):
 
 class UpsampleMask(torch.autograd.Function):
     """scale * up2(g) * (y > 0 ? 1 : slope): avg-pool backward fused with the LeakyReLU backward of the pooled
-    activation y (one pass instead of two)"""
+    activation y (one pass instead of two).  link: see _MaskLink (use _upsample_mask())."""
 
     @staticmethod
-    def forward(ctx, g, y, scale, slope):
+    def forward(ctx, g, y, scale, slope, link=None):
         ctx.save_for_backward(y)
-        ctx.scale, ctx.slope = scale, slope
+        ctx.scale, ctx.slope, ctx.link = scale, slope, link
         return k_upsample(feat(g, G, small=(y.dtype == torch.float32)), scale, mask_src=y, slope=slope, cls=G)
 
     @staticmethod
     def backward(ctx, gg):
         (y,) = ctx.saved_tensors
         f32 = y.dtype == torch.float32
-        return Pool2x2.apply(MaskMul.apply(feat(gg, G, small=f32), y, ctx.slope), ctx.scale, None, G), None, None, None
+        if not _premasked(ctx.link, gg):
+            gg = MaskMul.apply(feat(gg, G, small=f32), y, ctx.slope)
+        return Pool2x2.apply(gg, ctx.scale, None, G), None, None, None, None
+
+
+def _upsample_mask(g, y, scale, slope):
+    if not torch.is_grad_enabled():
+        g = feat(g, G, small=(y.dtype == torch.float32))
+        if _SKIP_PARAM_GRADS or not upsample_colsum_fusable(g):
+            return k_upsample(g, scale, mask_src=y, slope=slope, cls=G)
+        # plain backward: y is the output of a conv whose bias gradient is the column sum of this result — taken in
+        # the same pass and handed to that conv's backward through the tensor (ConvF.backward picks up `_pg_colsum`)
+        cs = torch.zeros((g.shape[1],), dtype=torch.float32, device=g.device)
+        out = k_upsample(g, scale, mask_src=y, slope=slope, cls=G, colsum=cs)
+        out._pg_colsum = cs
+        return out
+    link = _MaskLink()
+    return _tag_masked(UpsampleMask.apply(g, y, scale, slope, link), link, y, slope)
 
 
 class Pool2x2(torch.autograd.Function):
@@ -1018,7 +1108,7 @@ class Pool2x2(torch.autograd.Function):
         g = feat(g, G, small=ctx.f32)
         if ctx.act_slope is not None:
             (x,) = ctx.saved_tensors
-            return UpsampleMask.apply(g, x, ctx.scale, ctx.act_slope), None, None, None
+            return _upsample_mask(g, x, ctx.scale, ctx.act_slope), None, None, None
         return Upsample2x.apply(g, ctx.scale, G), None, None, None
 
 
@@ -1041,7 +1131,7 @@ class PoolBlend(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             if ctx.act_slope is not None:
                 (x,) = ctx.saved_tensors
-                gx = UpsampleMask.apply(g, x, _affine(0.0, 0.25, ctx.alpha), ctx.act_slope)
+                gx = _upsample_mask(g, x, _affine(0.0, 0.25, ctx.alpha), ctx.act_slope)
             else:
                 gx = Upsample2x.apply(g, _affine(0.0, 0.25, ctx.alpha), G)
         gl = Scale.apply(g, _affine(1.0, -1.0, ctx.alpha), G) if ctx.needs_input_grad[1] else None

@@ -250,6 +250,11 @@ def test_elementwise(dtype):
     upm = ops.k_upsample(g, 0.25, mask_src=up, slope=0.2, cls="g")
     gm = f32(g, "g").repeat_interleave(2, 2).repeat_interleave(2, 3) * 0.25
     assert rel_l2(f32(upm, "g"), torch.where(f32(up) > 0, gm, gm * 0.2)) < tol(dtype, "g")
+    # ... and with the column sums of the result taken in the same pass (bias gradient of the conv above the pool)
+    cs3 = torch.zeros(C, device="cuda")
+    upm2 = ops.k_upsample(g, 0.25, mask_src=up, slope=0.2, cls="g", colsum=cs3, colsum_scale=0.5)
+    assert torch.equal(upm2, upm)
+    assert rel_l2(cs3, 0.5 * f32(upm, "g").sum(dim=(0, 2, 3))) < 1e-5
     # pool
     pl = ops.k_pool(x, 0.25)
     assert rel_l2(f32(pl), F.avg_pool2d(f32(x), 2)) < tol(dtype)

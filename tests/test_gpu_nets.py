@@ -158,6 +158,72 @@ def test_r1_and_gradient_penalty(scale, width, batch, dtype, bias_std):
     assert abs(lc.loss_dict["L_D"] - round(float(ld["L_D"]), 4)) < max(2e-3, 1e-2 * abs(float(ld["L_D"])))
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, BENCH])
+def test_double_backward_masks_ride_in_gemm_epilogues(dtype, monkeypatch):
+    """the penalty's backward: the LeakyReLU masks of D's conv layers are applied by the epilogue of the conv that
+    produces the masked gradient (ops._MaskLink), not by passes of their own — same gradients as the unfused
+    composition, and no mask kernel left for the conv blocks; the bias gradient of each block's second conv comes out
+    of the pool-backward kernel in the plain backward"""
+    import pggan_b200 as pg
+    from pggan_b200 import ops
+    pg.set_compute_dtype(dtype)
+    scale, width, batch = 3, 64, 4
+    G, D, g_sd, d_sd = build_pair(scale, [width] * (scale + 1), width, seed=3, bias_std=0.3)
+    G.alpha = D.alpha = 0.5
+    res = 4 * 2 ** scale
+    torch.manual_seed(11)
+    x = torch.rand(batch, 3, res, res, device="cuda") * 2 - 1
+    fake = torch.rand(batch, 3, res, res, device="cuda") * 2 - 1
+    eps = torch.rand(batch, 1)
+    lc = pg.WGANGPLoss(pg.make_args())
+    calls = {"mask": 0, "colsum": 0}
+    real_mask, real_mc = ops.k_mask_mul, ops.k_mask_colsum
+
+    def count_mask(*a, **k):
+        calls["mask"] += 1
+        return real_mask(*a, **k)
+
+    def count_mc(*a, **k):
+        calls["colsum"] += 1
+        return real_mc(*a, **k)
+
+    monkeypatch.setattr(ops, "k_mask_mul", count_mask)
+    monkeypatch.setattr(ops, "k_mask_colsum", count_mc)
+
+    def run(fuse):
+        monkeypatch.setattr(ops, "FUSE_DOUBLE_BACKWARD_MASKS", fuse)
+        calls["mask"] = calls["colsum"] = 0
+        D.zero_grad()
+        xm = x.clone().requires_grad_()
+        gp = lc.get_gradient_penalty({"img_real": xm, "img_fake": fake, "pred_real": D(xm)}, D, backward=True, eps=eps)
+        return gp, {k: v.clone() for k, v in grads_by_name(D).items()}, dict(calls)
+
+    gp1, g1, c1 = run(True)
+    gp0, g0, c0 = run(False)
+    print(f"\n[{dtype}] mask passes in the penalty's forward+backward: fused {c1['mask']}, unfused {c0['mask']}")
+    assert abs(gp1 - gp0) <= 1e-5 * abs(gp0)                    # the first backward is the same program
+    n_conv = 2 * scale                                           # conv layers of the blocks below the 4x4 head
+    assert c0["mask"] - c1["mask"] >= n_conv, (c0, c1)
+    for k in g0:
+        if g0[k] is None or float(g0[k].abs().max()) == 0.0:
+            continue
+        assert rel_l2(g1[k], g0[k]) < (1e-5 if dtype == torch.float32 else 2e-3), (k, rel_l2(g1[k], g0[k]))
+    # plain backward of a critic loss: the second conv of every block gets its bias gradient from the pool backward
+    calls["colsum"] = 0
+    D.zero_grad()
+    D(x).sum().backward()
+    with_fused = calls["colsum"]
+    gb1 = {k: v.clone() for k, v in grads_by_name(D).items() if v is not None}
+    monkeypatch.setattr(ops, "upsample_colsum_fusable", lambda *a, **k: False)
+    calls["colsum"] = 0
+    D.zero_grad()
+    D(x).sum().backward()
+    assert calls["colsum"] - with_fused >= scale, (calls["colsum"], with_fused)
+    for k, v in grads_by_name(D).items():
+        if v is not None and k.endswith("bias") and float(v.abs().max()) > 0:
+            assert rel_l2(gb1[k], v) < 1e-5, (k, rel_l2(gb1[k], v))
+
+
 def _param_step_stats(mod, ref_params, sd0):
     """relative L2 of the parameter DELTAS of a network against a reference's, and of the deltas' magnitude.
     With beta1 = 0 Adam's first update is lr*g/(|g|+eps) = +-lr, so one sign disagreement on a near-zero gradient

@@ -19,6 +19,10 @@ if len(sys.argv) > 2 and sys.argv[2] == "c4":       # the 128^2 / 256^2 stage la
 if len(sys.argv) > 2 and sys.argv[2] == "narrow":   # the 256^2 / 512^2 / 1024^2 narrow layers (conv_rows.cu)
     SHAPES = [(16, 256, 256, 64, 64), (16, 256, 256, 64, 128), (4, 512, 512, 32, 32), (4, 512, 512, 32, 64),
               (4, 512, 512, 64, 32), (4, 1024, 1024, 16, 16), (4, 1024, 1024, 16, 32), (4, 1024, 1024, 32, 16)]
+if len(sys.argv) > 2 and sys.argv[2] == "small":    # the 4^2 .. 32^2 trunk layers at the C4 / C3 / C5 batch sizes (few M tiles, long K)
+    SHAPES = [(16, 4, 4, 512, 512), (16, 8, 8, 512, 512), (16, 16, 16, 512, 512), (32, 4, 4, 512, 512),
+              (32, 8, 8, 512, 512), (4, 8, 8, 512, 512), (4, 16, 16, 512, 512), (4, 32, 32, 512, 512),
+              (4, 64, 64, 256, 256), (4, 64, 64, 512, 256)]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 for (B, H, W, C, N) in SHAPES:
     x = torch.randn(B, C, H, W, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
