@@ -122,6 +122,15 @@ typedef struct {
      * plain shifted TMA box of x, so the up-sampled tensor is never written to HBM.  Available where
      * pggan_conv_up2_fusable(p) != 0 (tensor-core plain kernel); PG_ERR_UNSUPPORTED elsewhere. */
     int32_t up2;
+    /* Optional split-K workspace (any dtype; NULL: never split).  A layer with few output tiles and a long K — the
+     * 4x4 / 8x8 trunk layers — is cut into several K ranges per output tile so that idle SMs share the operand traffic;
+     * partial accumulators meet in ws_k and the CTA that arrives last at a tile runs the epilogue (partials summed in
+     * split order: results do not depend on arrival order).  ws_k: 16-byte aligned, ws_k_bytes >= 4096; its first 4096
+     * bytes are arrival counters that must be ZERO before the first call and are left zero by every call; calls that
+     * share a workspace must be stream-ordered.  The library decides per shape whether (and how far) to split within
+     * ws_k_bytes. */
+    void* ws_k;
+    int64_t ws_k_bytes;
 } pg_conv_params;
 int pggan_conv_fprop(const pg_conv_params* p, void* stream);
 /* which kernel pggan_conv_fprop would run this shape on (pointers may be NULL): lets the host decide where fusing a

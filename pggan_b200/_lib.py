@@ -25,6 +25,7 @@ class ConvParams(Structure):
         ("ws_x", c_void_p), ("ws_w", c_void_p),
         ("pn_rnorm", c_void_p), ("pn_eps", c_float),
         ("up2", c_int32),
+        ("ws_k", c_void_p), ("ws_k_bytes", ctypes.c_int64),
     ]
 
 

@@ -70,6 +70,14 @@ struct ConvKArgs {
     float pn_eps;
     int up2;                 // fused nearest-2x up-sampling: the tile geometry (BW/BH/BB, tiles_*) is in LOW-RES pixels,
                              // every box yields four tiles (one per output-pixel parity); H, W are the output dims
+    // split-K (plain kernel, MT = 1): a layer with few output tiles and a long K (the 4^2 / 8^2 trunk layers: each CTA
+    // would pull its whole K extent through ONE SM's ~64 B/clk L2 port — 25 us whatever the tile, tools/gemm_micro.py
+    // small) is cut into ksplit K ranges per output tile.  Every CTA writes its fp32 partial accumulator to `ws_part`
+    // ([tile][split][column][row]); the CTA that arrives last at the tile's counter sums the partials in split order
+    // (deterministic) and runs the epilogue.  Counters return to zero.
+    int ksplit;
+    float* ws_part;
+    unsigned int* ws_count;
 };
 
 template <typename T, int BLOCK_N, int SPAN = 128, int MT = 1>
@@ -118,8 +126,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     const uint32_t tmem_base = *tmem_slot;
 
     const int num_m_tiles = a.tiles_w * a.tiles_h * a.tiles_b * (a.up2 ? 4 : 1);
-    const int num_tiles = num_m_tiles * a.tiles_n;
+    const int num_tiles = num_m_tiles * a.tiles_n * a.ksplit;      // a tile index = (output tile, K split), split fastest
     const int num_kc = a.taps * a.kc_per_tap;
+    const int kc_per_split = num_kc / a.ksplit;
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
@@ -127,8 +136,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int nt = tile % a.tiles_n;
-                int mt = tile / a.tiles_n;
+                const int ks = tile % a.ksplit, mn = tile / a.ksplit;
+                const int nt = mn % a.tiles_n;
+                int mt = mn / a.tiles_n;
                 int pi = 0, pj = 0;                    // output-pixel parity of this tile (fused up-sampling)
                 if (a.up2) {
                     pj = mt & 1;
@@ -139,7 +149,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 const int h0 = ((mt / a.tiles_w) % a.tiles_h) * a.BH;
                 const int b0 = (mt / (a.tiles_w * a.tiles_h)) * a.BB;
                 const int n0 = nt * BLOCK_N;
-                for (int kc = 0; kc < num_kc; ++kc) {
+                for (int kc = ks * kc_per_split; kc < (ks + 1) * kc_per_split; ++kc) {
                     const int tap = kc / a.kc_per_tap;
                     const int cc = kc - tap * a.kc_per_tap;
                     int dh = 0, dw = 0;
@@ -177,7 +187,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * (MT * BLOCK_N);
-                for (int kc = 0; kc < num_kc; ++kc) {
+                for (int kc = 0; kc < kc_per_split; ++kc) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
@@ -210,8 +220,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             if ((it & 1) != egroup) continue;
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            const int nt = tile % a.tiles_n;
-            int mt = tile / a.tiles_n;
+            const int ks = tile % a.ksplit, mn = tile / a.ksplit;
+            const int nt = mn % a.tiles_n;
+            int mt = mn / a.tiles_n;
             int pi = 0, pj = 0;
             if (a.up2) {
                 pj = mt & 1;
@@ -251,11 +262,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * (MT * BLOCK_N) + m * BLOCK_N;
-            // fused pixel norm (one N tile covers the layer: this thread owns all channels of its pixel): a first pass
-            // over the accumulator for mean(lrelu(..)^2), then the normal pass multiplies by the factor
-            float rn = 1.f;
-            if (a.pn_rnorm != nullptr) {
-                float ss = 0.f;
+            // split-K: park this CTA's partial accumulator, count the arrival; only the last CTA of the tile goes on,
+            // reading the sum of all partials (in split order) where the code below reads the accumulator
+            const float* part0 = nullptr;
+            if (a.ksplit > 1) {
+                float* part = a.ws_part + (static_cast<size_t>(mn) * a.ksplit + ks) * (kBlockM * BLOCK_N) + q * 32 + lane;
 #pragma unroll 1
                 for (int j = 0; j < BLOCK_N / CH; ++j) {
                     __syncwarp();
@@ -266,6 +277,58 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         tmem_ld16(taddr + j * 16, r);
                     }
                     tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < CH; ++i) __stcg(part + static_cast<size_t>(j * CH + i) * kBlockM, __uint_as_float(r[i]));
+                }
+                __threadfence();
+                uint32_t* flag = tmem_slot + 1 + egroup;
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + egroup) : "memory");
+                if (q == 0 && lane == 0) {
+                    const unsigned int prev = atomicAdd(a.ws_count + mn, 1u);
+                    if (prev == static_cast<unsigned int>(a.ksplit - 1)) a.ws_count[mn] = 0u;     // ready for the next launch
+                    *flag = prev;
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + egroup) : "memory");
+                const bool last = *flag == static_cast<unsigned int>(a.ksplit - 1);
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + egroup) : "memory");          // flag may be rewritten for the next tile
+                if (!last) continue;              // (MT == 1: leaves the m loop; the accumulator is released below)
+                __threadfence();
+                part0 = a.ws_part + static_cast<size_t>(mn) * a.ksplit * (kBlockM * BLOCK_N) + q * 32 + lane;
+            }
+            // accumulator chunk j -> r: from TMEM, or (split-K, last CTA) the sum of the parked partials
+            auto load_acc = [&](int j, uint32_t (&r)[32]) {
+                if (part0 == nullptr) {
+                    tmem_ld_wait();
+                    return;
+                }
+                float t[CH];
+#pragma unroll
+                for (int i = 0; i < CH; ++i) t[i] = 0.f;
+                for (int sidx = 0; sidx < a.ksplit; ++sidx) {
+                    const float* pp = part0 + static_cast<size_t>(sidx) * (kBlockM * BLOCK_N) + static_cast<size_t>(j * CH) * kBlockM;
+#pragma unroll
+                    for (int i = 0; i < CH; ++i) t[i] += __ldcg(pp + static_cast<size_t>(i) * kBlockM);
+                }
+#pragma unroll
+                for (int i = 0; i < CH; ++i) r[i] = __float_as_uint(t[i]);
+            };
+            // fused pixel norm (one N tile covers the layer: this thread owns all channels of its pixel): a first pass
+            // over the accumulator for mean(lrelu(..)^2), then the normal pass multiplies by the factor
+            float rn = 1.f;
+            if (a.pn_rnorm != nullptr) {
+                float ss = 0.f;
+#pragma unroll 1
+                for (int j = 0; j < BLOCK_N / CH; ++j) {
+                    __syncwarp();
+                    uint32_t r[32];
+                    if (part0 == nullptr) {
+                        if constexpr (CH == 32) {
+                            tmem_ld32(taddr + j * 32, r);
+                        } else {
+                            tmem_ld16(taddr + j * 16, r);
+                        }
+                    }
+                    load_acc(j, r);
 #pragma unroll
                     for (int i = 0; i < CH; ++i) {
                         float t = __uint_as_float(r[i]);
@@ -281,10 +344,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             for (int j = 0; j < BLOCK_N / CH; ++j) {
                 __syncwarp();
                 uint32_t r[32];
-                if constexpr (CH == 32) {
-                    tmem_ld32(taddr + j * 32, r);
-                } else {
-                    tmem_ld16(taddr + j * 16, r);
+                if (part0 == nullptr) {
+                    if constexpr (CH == 32) {
+                        tmem_ld32(taddr + j * 32, r);
+                    } else {
+                        tmem_ld16(taddr + j * 16, r);
+                    }
                 }
                 uint4 mnxt[MV];
                 if (masked && j + 1 < BLOCK_N / CH) {
@@ -292,7 +357,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #pragma unroll
                     for (int c = 0; c < MV; ++c) mnxt[c] = __ldg(mp + c);
                 }
-                tmem_ld_wait();
+                load_acc(j, r);
                 float v[32];
 #pragma unroll
                 for (int i = 0; i < CH; ++i) {
@@ -661,8 +726,12 @@ static bool m2_applies(const pg_conv_params* p, int sms, int bn = 128) {
            (XW >= 256 || (256 % XW == 0));
 }
 
+// split-K workspace layout (pg_conv_params.ws_k): kSplitCounters zero-initialised arrival counters, then the partials
+constexpr int kSplitCounters = 1024;
+constexpr size_t kSplitHeader = kSplitCounters * sizeof(unsigned int);
+
 template <typename T, int BLOCK_N, int SPAN = 128, int MT = 1>
-static int launch_tc(const pg_conv_params* p, cudaStream_t stream) {
+static int launch_tc(const pg_conv_params* p, cudaStream_t stream, int ksplit = 1) {
     using Cfg = ConvCfg<BLOCK_N, SPAN, MT>;
     constexpr int kTileM = MT * kBlockM;
     constexpr int BK = SPAN / sizeof(T);
@@ -688,6 +757,19 @@ static int launch_tc(const pg_conv_params* p, cudaStream_t stream) {
     a.scale = p->scale; a.slope = p->slope; a.mask_slope = p->mask_slope;
     a.pn_rnorm = p->pn_rnorm; a.pn_eps = p->pn_eps;
     PG_CHECK(p->pn_rnorm == nullptr || a.tiles_n == 1, PG_ERR_UNSUPPORTED, "fused pixel norm needs one N tile (N=%d)", p->N);
+    a.ksplit = 1;
+    a.ws_part = nullptr;
+    a.ws_count = nullptr;
+    if (ksplit > 1) {
+        const long long mn_tiles = (long long)a.tiles_w * a.tiles_h * a.tiles_b * a.tiles_n * (a.up2 ? 4 : 1);
+        const size_t need = kSplitHeader + (size_t)mn_tiles * ksplit * kBlockM * BLOCK_N * sizeof(float);
+        PG_CHECK(MT == 1 && p->ws_k != nullptr && (size_t)p->ws_k_bytes >= need && mn_tiles <= kSplitCounters &&
+                     (p->taps * a.kc_per_tap) % ksplit == 0,
+                 PG_ERR_ARG, "split-K: internal dispatch error (ksplit=%d)", ksplit);
+        a.ksplit = ksplit;
+        a.ws_count = reinterpret_cast<unsigned int*>(p->ws_k);
+        a.ws_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(p->ws_k) + kSplitHeader);
+    }
 
     const uint64_t es = sizeof(T);
     CUtensorMap tx, tw;
@@ -708,7 +790,7 @@ static int launch_tc(const pg_conv_params* p, cudaStream_t stream) {
     }
     auto kern = conv_gemm_kernel<T, BLOCK_N, SPAN, MT>;
     PG_SET_SMEM_ONCE(kern, Cfg::kSmemBytes);
-    const int num_tiles = a.tiles_w * a.tiles_h * a.tiles_b * a.tiles_n * (a.up2 ? 4 : 1);
+    const int num_tiles = a.tiles_w * a.tiles_h * a.tiles_b * a.tiles_n * (a.up2 ? 4 : 1) * a.ksplit;
     int grid = num_tiles < num_sms() ? num_tiles : num_sms();
     kern<<<grid, kConvThreadsPlain, Cfg::kSmemBytes, stream>>>(tx, tw, a);
     PG_LAUNCH_CHECK();
@@ -844,6 +926,54 @@ static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream, int* k
             if (p->N % 64 == 0) return launch_tc<T, 64, 32>(p, stream);
             if (p->N % 32 == 0) return launch_tc<T, 32, 32>(p, stream);
             return launch_tc<T, 16, 32>(p, stream);
+        }
+        // Few output tiles, long K: every CTA pulls its K extent through one SM's L2 port (~118 GB/s measured: 25-28 us
+        // for 72 k-steps whatever the tile shape, tools/gemm_micro.py small).  With a workspace the K extent is split
+        // over the idle SMs instead: choose (N tile, splits) minimising   k-steps/S * bytes per k-step  +  S partial
+        // tiles re-read by the CTA that finishes the tile,  all CTAs in one wave.
+        static const bool no_splitk = getenv("PGGAN_NO_SPLITK") != nullptr;
+        if (!no_splitk && p->ws_k != nullptr && reinterpret_cast<uintptr_t>(p->ws_k) % 16 == 0 && !p->up2 && span == 128) {
+            const int num_kc = p->taps * (p->C / (128 / (int)sizeof(T)));
+            const double port = 118e3;                                   // bytes per microsecond into one SM
+            double t_best = 1e30;
+            int bn_best = 0, s_best = 1;
+            const int bns[3] = {256, 128, 64};
+            for (int i = 0; i < 3; ++i) {
+                const int b = bns[i];
+                if (p->N % b != 0) continue;
+                if (p->pn_rnorm != nullptr && b != p->N) continue;
+                const long long mn = m_tiles * (p->N / b);
+                if (mn > sms || mn > kSplitCounters) continue;
+                const double kstep = (16384.0 + b * 128.0) / port;
+                for (int S = 1; S <= 16; ++S) {
+                    if (num_kc % S != 0 || mn * S > sms) continue;
+                    const size_t need = kSplitHeader + (size_t)mn * S * kBlockM * b * sizeof(float);
+                    if (S > 1 && need > (size_t)p->ws_k_bytes) continue;
+                    const double t = (num_kc / S) * kstep + (S > 1 ? S * (b * 512.0) / port + 1.5 : 0.0);
+                    if (t < t_best - 1e-9) {
+                        t_best = t;
+                        bn_best = b;
+                        s_best = S;
+                    }
+                }
+            }
+            if (const char* f = getenv("PGGAN_FORCE_SPLITK")) {          // tuning experiments only: "bn,S"
+                int fb = 0, fs = 0;
+                if (sscanf(f, "%d,%d", &fb, &fs) == 2 && (fb == 64 || fb == 128 || fb == 256) && p->N % fb == 0 && fs >= 1 &&
+                    (p->pn_rnorm == nullptr || fb == p->N) &&
+                    num_kc % fs == 0 && m_tiles * (p->N / fb) * fs <= 2LL * sms &&
+                    kSplitHeader + (size_t)m_tiles * (p->N / fb) * fs * kBlockM * fb * sizeof(float) <= (size_t)p->ws_k_bytes) {
+                    bn_best = fb;
+                    s_best = fs;
+                }
+            }
+            if (s_best > 1) {
+                switch (bn_best) {
+                    case 256: return launch_tc<T, 256>(p, stream, s_best);
+                    case 128: return launch_tc<T, 128>(p, stream, s_best);
+                    default: return launch_tc<T, 64>(p, stream, s_best);
+                }
+            }
         }
         int bn = 16;
         double best = 1e30;

@@ -580,6 +580,22 @@ def conv_up2_fusable(x_low, N, taps=9) -> bool:
     return hit
 
 
+_SPLITK_WS: dict = {}
+SPLITK_WS_BYTES = 4096 + (24 << 20)
+
+
+def _splitk_ws(device) -> torch.Tensor:
+    """the split-K workspace of pg_conv_params.ws_k for the current stream of `device`: one buffer per (device, stream) —
+    launches that share it are stream-ordered —, its counter header zeroed once (the library leaves it zero)"""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _SPLITK_WS.get(key)
+    if ws is None:
+        ws = torch.empty(SPLITK_WS_BYTES, dtype=torch.uint8, device=device)
+        ws[:4096].zero_()
+        _SPLITK_WS[key] = ws
+    return ws
+
+
 def k_conv(x, wp, bias, N, taps, scale, slope=1.0, mask_src=None, mask_slope=1.0, raw_out=False, pn_eps=None, xc=A,
            up2=False):
     """pn_eps: also apply the pixel norm in the epilogue; returns (y, rnorm[pixels] fp32) then.
@@ -604,6 +620,8 @@ def k_conv(x, wp, bias, N, taps, scale, slope=1.0, mask_src=None, mask_slope=1.0
     p.out_dtype = L.PG_F32_RAW if raw_out else xf
     p.scale, p.slope, p.mask_slope = float(scale), float(slope), float(mask_slope)
     p.up2 = 1 if up2 else 0
+    wk = _splitk_ws(x.device)
+    p.ws_k, p.ws_k_bytes = wk.data_ptr(), wk.numel()
     ws = None
     if xf == L.PG_F32:          # fp32 mode = 3xTF32: the library splits operands into these
         ws = (torch.empty(3 * x.numel(), dtype=torch.float32, device=x.device),

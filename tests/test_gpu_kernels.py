@@ -146,6 +146,59 @@ def test_conv_fprop(shape, backend, dtype):
         assert y32.dtype == torch.float32 and rel_l2(y32, ref) < _TOL[torch.float32]
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+@pytest.mark.parametrize("shape,force", [((16, 4, 4, 512, 512), None), ((16, 8, 8, 512, 512), None), ((4, 16, 16, 512, 256), None),
+                                         ((3, 8, 8, 256, 128), "128,9"), ((16, 4, 4, 512, 512), "256,4"),
+                                         ((5, 8, 8, 128, 64), "64,3"), ((32, 4, 4, 256, 256), "64,12")])
+def test_conv_split_k(shape, force, dtype, monkeypatch):
+    """few output tiles, long K: the K extent is split over otherwise idle SMs (pg_conv_params.ws_k), partial
+    accumulators meet in the workspace and the last CTA of a tile runs the (mask / bias / LeakyReLU / pixel-norm)
+    epilogue — same result as the unsplit kernel, run-to-run identical bits, counters left at zero"""
+    from pggan_b200 import ops, _lib
+    import pggan_b200 as pg
+    pg.set_compute_dtype(dtype)
+    _lib.load().pggan_set_conv_backend(0)
+    B, H, W, Ci, Co = shape
+    if force and dtype == torch.float32 and (9 * 3 * Ci // 32) % int(force.split(",")[1]) != 0:
+        pytest.skip("split count does not divide the 3xTF32 K extent")
+    dev = "cuda"
+    x = rnd(torch.randn(B, Ci, H, W, device=dev), dtype)
+    w = rnd(torch.randn(Co, Ci, 3, 3, device=dev), dtype)
+    b = torch.randn(Co, device=dev)
+    m = rnd(torch.randn(B, Co, H, W, device=dev), dtype)
+    scale = (2.0 / (Ci * 9)) ** 0.5
+    xf, mf = to_feat(x, dtype), to_feat(m, dtype)
+    wp = ops._pack(w, "f", None, None, ops._fmt_of(xf, "a"))
+
+    def run(env):
+        if env is None:
+            monkeypatch.delenv("PGGAN_FORCE_SPLITK", raising=False)
+        else:
+            monkeypatch.setenv("PGGAN_FORCE_SPLITK", env)
+        y = ops.k_conv(xf, wp, b, Co, 9, scale, 0.2, mask_src=mf, mask_slope=0.2)
+        torch.cuda.synchronize()
+        return y
+
+    y1 = run(force)
+    y2 = run(force)
+    assert torch.equal(y1, y2)                                    # fixed summation order, counters back at zero
+    y0 = run("64,1" if Co % 64 == 0 else None)                    # one K range: the unsplit kernel
+    ref = F.leaky_relu(F.conv2d(x, w, b, padding=1) * scale, 0.2)
+    ref = torch.where(m > 0, ref, ref * 0.2)
+    assert rel_l2(f32(y1), ref) < tol(dtype), rel_l2(f32(y1), ref)
+    assert rel_l2(f32(y1), f32(y0)) < (1e-6 if dtype == torch.float32 else 1e-3)
+    ws = ops._splitk_ws(xf.device)
+    assert int(ws[:4096].view(torch.int32).abs().sum()) == 0
+    if Co <= 256 and dtype != torch.float32:
+        # fused pixel norm on a split layer (two passes over the summed partials)
+        monkeypatch.delenv("PGGAN_FORCE_SPLITK", raising=False)
+        yp, r = ops.k_conv(xf, wp, b, Co, 9, scale, 0.2, pn_eps=1e-8) if ops.conv_pn_fusable(xf, Co, 9) else (None, None)
+        if yp is not None:
+            a = F.leaky_relu(F.conv2d(x, w, b, padding=1) * scale, 0.2)
+            refp = a * torch.rsqrt((a ** 2).mean(dim=1, keepdim=True) + 1e-8)
+            assert rel_l2(f32(yp), refp) < tol(dtype), rel_l2(f32(yp), refp)
+
+
 @pytest.mark.parametrize("dtype", DT)
 @pytest.mark.parametrize("shape", [(2, 16, 16, 64, 128), (1, 32, 128, 64, 64), (1, 16, 256, 16, 32), (2, 32, 32, 128, 64)])
 def test_conv_mask_and_raw_out(shape, dtype):
@@ -282,6 +335,52 @@ def test_elementwise(dtype):
     xr = f32(x).clone().requires_grad_()
     (ops.ExportFloat.apply(ops.Upsample2x.apply(to_feat(xr, dtype), 1.0)) * f32(up)).sum().backward()
     assert rel_l2(xr.grad, 4 * F.avg_pool2d(f32(up), 2)) < 2 * tol(dtype, "g")
+
+
+def _emulate_map(n_elems, args, device):
+    """index tensor [n_total, taps, c_total] into the flat parameter (-1 = zero padding) of a pg_pack_map tuple"""
+    n_total, n_valid, n2, taps, c_total, c_valid, c2, base, s_n1, s_n2, s_t, s_c1, s_c2 = args
+    n = torch.arange(n_total, device=device).view(-1, 1, 1)
+    t = torch.arange(taps, device=device).view(1, -1, 1)
+    c = torch.arange(c_total, device=device).view(1, 1, -1)
+    off = base + (n // n2) * s_n1 + (n % n2) * s_n2 + t * s_t + (c // c2) * s_c1 + (c % c2) * s_c2
+    valid = ((n < n_valid) & (c < c_valid)).expand(n_total, taps, c_total)
+    return torch.where(valid, off.expand(n_total, taps, c_total), torch.full_like(off, -1).expand(n_total, taps, c_total))
+
+
+@pytest.mark.parametrize("shape,layout", [((512, 8192), ("lin_in_perm", 512)), ((8192, 512), ("lin_out_perm", 512)),
+                                          ((512, 2048), ("lin_in_perm", 128)), ((256, 384), None),
+                                          ((96, 33, 3, 3), ("pad_c", 64)), ((1, 512), None)])
+def test_pack_and_unpack_through_the_layout_maps(shape, layout):
+    """operand packing / gradient un-packing of the permuting layouts (row-span kernels for the big linear layers, the
+    generic kernel for the rest) against the index map evaluated in torch: bit-exact copies"""
+    from pggan_b200 import ops, _lib as L
+    import pggan_b200 as pg
+    pg.set_compute_dtype(torch.float16)
+    torch.manual_seed(3)
+    W = torch.nn.Parameter(torch.randn(*shape, device="cuda"))
+    N, C, T, fm, tm = ops._maps(W.shape, layout)
+    flat = W.detach().reshape(-1)
+    for kind, args in (("f", fm), ("t", tm)):
+        idx = _emulate_map(flat.numel(), args, "cuda")
+        want = torch.where(idx >= 0, flat[idx.clamp(min=0)], torch.zeros((), device="cuda")).to(torch.float16)
+        got = ops._pack(W, kind, None, layout, L.PG_F16)
+        assert torch.equal(got.reshape(want.shape), want), (kind, layout)
+    # gradient slices [S][N][taps][C] -> the parameter's layout, overwrite and accumulate
+    idx = _emulate_map(flat.numel(), fm, "cuda")
+    slices = 3
+    acc = torch.randn(slices, *idx.shape, device="cuda")
+    want = torch.zeros_like(flat)
+    want[idx[idx >= 0]] = (acc.sum(0) * 0.5)[idx >= 0]
+    m = ops._packmap(fm)
+    import ctypes
+    out = torch.full_like(flat, 7.0) if not (fm[1] < fm[0] or fm[5] < fm[4]) else torch.zeros_like(flat)
+    L.check(L.load().pggan_unpack_wgrad(acc.data_ptr(), out.data_ptr(), ctypes.byref(m), slices, 0.5, 0,
+                                        torch.cuda.current_stream().cuda_stream), "unpack")
+    assert rel_l2(out, want) < 1e-6
+    L.check(L.load().pggan_unpack_wgrad(acc.data_ptr(), out.data_ptr(), ctypes.byref(m), slices, 0.5, 1,
+                                        torch.cuda.current_stream().cuda_stream), "unpack")
+    assert rel_l2(out, 2 * want) < 1e-6
 
 
 @pytest.mark.parametrize("dtype", DT)

@@ -1,0 +1,17 @@
+#!/bin/bash
+# split-K + row-span pack kernels + fusion tests, then timing of the small layers and the bench line
+TAG=${1:-r2b}
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests/test_gpu_kernels.py -q -x -p no:cacheprovider -k "split_k or pack_and_unpack or elementwise" 2>&1 | tail -15 > gpurun_out/tests_k_${TAG}.log
+echo "kernel tests rc ${PIPESTATUS[0]}"; tail -6 gpurun_out/tests_k_${TAG}.log | cut -c1-220
+timeout 1500 python -m pytest tests -m gpu -q --maxfail=20 -rf -p no:cacheprovider > gpurun_out/tests_${TAG}.log 2>&1
+echo "pytest rc $?"; tail -8 gpurun_out/tests_${TAG}.log | cut -c1-220
+echo "== auto"; timeout 200 python tools/gemm_micro.py 10 small 2>&1 | grep conv_fprop > gpurun_out/small_${TAG}.txt; cat gpurun_out/small_${TAG}.txt
+timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err; echo "bench rc $?"; tail -3 gpurun_out/bench_${TAG}.err
+python - <<PY
+import json
+d=json.loads([l for l in open("gpurun_out/bench_${TAG}.json") if l.startswith("{")][-1])
+print("HEADLINE", d["config"]["workload"], d["value"], "img/s", d["ms_per_step"], "ms", d["clocks"], "launches", d["gpu_launches"])
+for p in d["per_config"]:
+    print("  ", p.get("workload"), p.get("value"), p.get("ms_per_step"), p.get("error"))
+PY
