@@ -72,9 +72,9 @@ struct ConvKArgs {
                              // every box yields four tiles (one per output-pixel parity); H, W are the output dims
     // split-K (plain kernel, MT = 1): a layer with few output tiles and a long K (the 4^2 / 8^2 trunk layers: each CTA
     // would pull its whole K extent through ONE SM's ~64 B/clk L2 port — 25 us whatever the tile, tools/gemm_micro.py
-    // small) is cut into ksplit K ranges per output tile.  Every CTA writes its fp32 partial accumulator to `ws_part`
-    // ([tile][split][column][row]); the CTA that arrives last at the tile's counter sums the partials in split order
-    // (deterministic) and runs the epilogue.  Counters return to zero.
+    // small) is cut into ksplit K ranges per output tile.  Every CTA adds its fp32 partial accumulator into the tile's
+    // sum in `ws_part` ([tile][column][row], zero between launches) with red.global; the CTA that arrives last at the
+    // tile's counter reads the sum, clears it and runs the epilogue.  Counters return to zero.
     int ksplit;
     float* ws_part;
     unsigned int* ws_count;
@@ -262,11 +262,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * (MT * BLOCK_N) + m * BLOCK_N;
-            // split-K: park this CTA's partial accumulator, count the arrival; only the last CTA of the tile goes on,
-            // reading the sum of all partials (in split order) where the code below reads the accumulator
-            const float* part0 = nullptr;
+            // split-K: add this CTA's partial accumulator to the tile's fp32 sum in the workspace (red.global: fire and
+            // forget, the L2 does the adds), count the arrival; only the last CTA of the tile goes on, reading the sum
+            // where the code below reads the accumulator and leaving zeros behind for the next launch
+            float* part0 = nullptr;
             if (a.ksplit > 1) {
-                float* part = a.ws_part + (static_cast<size_t>(mn) * a.ksplit + ks) * (kBlockM * BLOCK_N) + q * 32 + lane;
+                float* part = a.ws_part + static_cast<size_t>(mn) * (kBlockM * BLOCK_N) + q * 32 + lane;
 #pragma unroll 1
                 for (int j = 0; j < BLOCK_N / CH; ++j) {
                     __syncwarp();
@@ -278,7 +279,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     }
                     tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < CH; ++i) __stcg(part + static_cast<size_t>(j * CH + i) * kBlockM, __uint_as_float(r[i]));
+                    for (int i = 0; i < CH; ++i)
+                        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(part + static_cast<size_t>(j * CH + i) * kBlockM),
+                                     "f"(__uint_as_float(r[i]))
+                                     : "memory");
                 }
                 __threadfence();
                 uint32_t* flag = tmem_slot + 1 + egroup;
@@ -293,24 +297,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + egroup) : "memory");          // flag may be rewritten for the next tile
                 if (!last) continue;              // (MT == 1: leaves the m loop; the accumulator is released below)
                 __threadfence();
-                part0 = a.ws_part + static_cast<size_t>(mn) * a.ksplit * (kBlockM * BLOCK_N) + q * 32 + lane;
+                part0 = part;
             }
-            // accumulator chunk j -> r: from TMEM, or (split-K, last CTA) the sum of the parked partials
-            auto load_acc = [&](int j, uint32_t (&r)[32]) {
+            // accumulator chunk j -> r: from TMEM, or (split-K, last CTA) the tile's sum in the workspace
+            auto load_acc = [&](int j, uint32_t (&r)[32], bool clear) {
                 if (part0 == nullptr) {
                     tmem_ld_wait();
                     return;
                 }
-                float t[CH];
+                float* pp = part0 + static_cast<size_t>(j * CH) * kBlockM;
 #pragma unroll
-                for (int i = 0; i < CH; ++i) t[i] = 0.f;
-                for (int sidx = 0; sidx < a.ksplit; ++sidx) {
-                    const float* pp = part0 + static_cast<size_t>(sidx) * (kBlockM * BLOCK_N) + static_cast<size_t>(j * CH) * kBlockM;
+                for (int i = 0; i < CH; ++i) r[i] = __float_as_uint(__ldcg(pp + static_cast<size_t>(i) * kBlockM));
+                if (clear) {
 #pragma unroll
-                    for (int i = 0; i < CH; ++i) t[i] += __ldcg(pp + static_cast<size_t>(i) * kBlockM);
+                    for (int i = 0; i < CH; ++i) __stcg(pp + static_cast<size_t>(i) * kBlockM, 0.f);
                 }
-#pragma unroll
-                for (int i = 0; i < CH; ++i) r[i] = __float_as_uint(t[i]);
             };
             // fused pixel norm (one N tile covers the layer: this thread owns all channels of its pixel): a first pass
             // over the accumulator for mean(lrelu(..)^2), then the normal pass multiplies by the factor
@@ -328,7 +329,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                             tmem_ld16(taddr + j * 16, r);
                         }
                     }
-                    load_acc(j, r);
+                    load_acc(j, r, false);
 #pragma unroll
                     for (int i = 0; i < CH; ++i) {
                         float t = __uint_as_float(r[i]);
@@ -357,7 +358,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #pragma unroll
                     for (int c = 0; c < MV; ++c) mnxt[c] = __ldg(mp + c);
                 }
-                load_acc(j, r);
+                load_acc(j, r, true);
                 float v[32];
 #pragma unroll
                 for (int i = 0; i < CH; ++i) {
@@ -762,7 +763,7 @@ static int launch_tc(const pg_conv_params* p, cudaStream_t stream, int ksplit = 
     a.ws_count = nullptr;
     if (ksplit > 1) {
         const long long mn_tiles = (long long)a.tiles_w * a.tiles_h * a.tiles_b * a.tiles_n * (a.up2 ? 4 : 1);
-        const size_t need = kSplitHeader + (size_t)mn_tiles * ksplit * kBlockM * BLOCK_N * sizeof(float);
+        const size_t need = kSplitHeader + (size_t)mn_tiles * kBlockM * BLOCK_N * sizeof(float);
         PG_CHECK(MT == 1 && p->ws_k != nullptr && (size_t)p->ws_k_bytes >= need && mn_tiles <= kSplitCounters &&
                      (p->taps * a.kc_per_tap) % ksplit == 0,
                  PG_ERR_ARG, "split-K: internal dispatch error (ksplit=%d)", ksplit);
@@ -929,8 +930,8 @@ static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream, int* k
         }
         // Few output tiles, long K: every CTA pulls its K extent through one SM's L2 port (~118 GB/s measured: 25-28 us
         // for 72 k-steps whatever the tile shape, tools/gemm_micro.py small).  With a workspace the K extent is split
-        // over the idle SMs instead: choose (N tile, splits) minimising   k-steps/S * bytes per k-step  +  S partial
-        // tiles re-read by the CTA that finishes the tile,  all CTAs in one wave.
+        // over the idle SMs instead: choose (N tile, splits) minimising   k-steps/S * bytes per k-step  +  the tile's
+        // sum added to and re-read from the workspace,  all CTAs in one wave.
         static const bool no_splitk = getenv("PGGAN_NO_SPLITK") != nullptr;
         if (!no_splitk && p->ws_k != nullptr && reinterpret_cast<uintptr_t>(p->ws_k) % 16 == 0 && !p->up2 && span == 128) {
             const int num_kc = p->taps * (p->C / (128 / (int)sizeof(T)));
@@ -947,9 +948,9 @@ static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream, int* k
                 const double kstep = (16384.0 + b * 128.0) / port;
                 for (int S = 1; S <= 16; ++S) {
                     if (num_kc % S != 0 || mn * S > sms) continue;
-                    const size_t need = kSplitHeader + (size_t)mn * S * kBlockM * b * sizeof(float);
+                    const size_t need = kSplitHeader + (size_t)mn * kBlockM * b * sizeof(float);
                     if (S > 1 && need > (size_t)p->ws_k_bytes) continue;
-                    const double t = (num_kc / S) * kstep + (S > 1 ? S * (b * 512.0) / port + 1.5 : 0.0);
+                    const double t = (num_kc / S) * kstep + (S > 1 ? 2.0 * (b * 512.0) / port + 1.5 : 0.0);
                     if (t < t_best - 1e-9) {
                         t_best = t;
                         bn_best = b;
@@ -959,10 +960,11 @@ static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream, int* k
             }
             if (const char* f = getenv("PGGAN_FORCE_SPLITK")) {          // tuning experiments only: "bn,S"
                 int fb = 0, fs = 0;
+                if (sscanf(f, "%d,%d", &fb, &fs) == 2 && fs == 1) s_best = 1;               // "x,1": never split
                 if (sscanf(f, "%d,%d", &fb, &fs) == 2 && (fb == 64 || fb == 128 || fb == 256) && p->N % fb == 0 && fs >= 1 &&
                     (p->pn_rnorm == nullptr || fb == p->N) &&
                     num_kc % fs == 0 && m_tiles * (p->N / fb) * fs <= 2LL * sms &&
-                    kSplitHeader + (size_t)m_tiles * (p->N / fb) * fs * kBlockM * fb * sizeof(float) <= (size_t)p->ws_k_bytes) {
+                    kSplitHeader + (size_t)m_tiles * (p->N / fb) * kBlockM * fb * sizeof(float) <= (size_t)p->ws_k_bytes) {
                     bn_best = fb;
                     s_best = fs;
                 }

@@ -581,17 +581,16 @@ def conv_up2_fusable(x_low, N, taps=9) -> bool:
 
 
 _SPLITK_WS: dict = {}
-SPLITK_WS_BYTES = 4096 + (24 << 20)
+SPLITK_WS_BYTES = 4096 + (20 << 20)
 
 
 def _splitk_ws(device) -> torch.Tensor:
     """the split-K workspace of pg_conv_params.ws_k for the current stream of `device`: one buffer per (device, stream) —
-    launches that share it are stream-ordered —, its counter header zeroed once (the library leaves it zero)"""
+    launches that share it are stream-ordered —, zeroed once (the library leaves it zero)"""
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
     ws = _SPLITK_WS.get(key)
     if ws is None:
-        ws = torch.empty(SPLITK_WS_BYTES, dtype=torch.uint8, device=device)
-        ws[:4096].zero_()
+        ws = torch.zeros(SPLITK_WS_BYTES, dtype=torch.uint8, device=device)
         _SPLITK_WS[key] = ws
     return ws
 

@@ -152,8 +152,8 @@ def test_conv_fprop(shape, backend, dtype):
                                          ((5, 8, 8, 128, 64), "64,3"), ((32, 4, 4, 256, 256), "64,12")])
 def test_conv_split_k(shape, force, dtype, monkeypatch):
     """few output tiles, long K: the K extent is split over otherwise idle SMs (pg_conv_params.ws_k), partial
-    accumulators meet in the workspace and the last CTA of a tile runs the (mask / bias / LeakyReLU / pixel-norm)
-    epilogue — same result as the unsplit kernel, run-to-run identical bits, counters left at zero"""
+    accumulators are summed in the workspace and the last CTA of a tile runs the (mask / bias / LeakyReLU / pixel-norm)
+    epilogue — same result as the unsplit kernel, workspace left at zero"""
     from pggan_b200 import ops, _lib
     import pggan_b200 as pg
     pg.set_compute_dtype(dtype)
@@ -180,15 +180,15 @@ def test_conv_split_k(shape, force, dtype, monkeypatch):
         return y
 
     y1 = run(force)
-    y2 = run(force)
-    assert torch.equal(y1, y2)                                    # fixed summation order, counters back at zero
-    y0 = run("64,1" if Co % 64 == 0 else None)                    # one K range: the unsplit kernel
+    y2 = run(force)                                               # the workspace is back at zero: same result again
+    assert rel_l2(f32(y1), f32(y2)) < (1e-6 if dtype == torch.float32 else 1e-4)
+    y0 = run("0,1")                                               # one K range: the unsplit kernel
     ref = F.leaky_relu(F.conv2d(x, w, b, padding=1) * scale, 0.2)
     ref = torch.where(m > 0, ref, ref * 0.2)
     assert rel_l2(f32(y1), ref) < tol(dtype), rel_l2(f32(y1), ref)
-    assert rel_l2(f32(y1), f32(y0)) < (1e-6 if dtype == torch.float32 else 1e-3)
+    assert rel_l2(f32(y1), f32(y0)) < (1e-4 if dtype == torch.float32 else 1e-3)
     ws = ops._splitk_ws(xf.device)
-    assert int(ws[:4096].view(torch.int32).abs().sum()) == 0
+    assert int(ws.view(torch.int32).abs().max()) == 0
     if Co <= 256 and dtype != torch.float32:
         # fused pixel norm on a split layer (two passes over the summed partials)
         monkeypatch.delenv("PGGAN_FORCE_SPLITK", raising=False)
@@ -642,7 +642,7 @@ def test_conv_fused_pixelnorm(shape, dtype):
 @pytest.mark.parametrize("dtype", DT)
 @pytest.mark.parametrize("shape", [(2, 8, 8, 64, 64), (3, 4, 4, 512, 512), (2, 16, 16, 512, 256), (1, 64, 64, 256, 128),
                                    (2, 64, 64, 128, 64), (5, 32, 32, 128, 128), (1, 128, 128, 128, 64)])
-def test_conv_fused_upsample(shape, dtype):
+def test_conv_fused_upsample(shape, dtype, monkeypatch):
     """conv3x3(upscale2d(x)) as ONE kernel (the up-sampling is the GEMM's prologue: parity tiles reading shifted boxes
     of the low-resolution tensor) against F.conv2d on the materialised up-sampled tensor; then G's whole
     upscale -> conv -> LeakyReLU -> pixel norm chain (ops.ConvActPN with up2) with its gradients."""
@@ -665,7 +665,8 @@ def test_conv_fused_upsample(shape, dtype):
         y = ops.k_conv(xf, ops._pack(w, "f", fmt=ops._fmt_of(xf, "a")), b, Co, 9, scale, 0.2, up2=True)
         assert y.shape == (B, Co, 2 * H, 2 * W) and y.is_contiguous(memory_format=torch.channels_last)
         assert rel_l2(f32(y), ref) < tol(dtype), rel_l2(f32(y), ref)
-        # the unfused pair gives the same bits (same MMAs in the same order on the same operands)
+        # the unfused pair gives the same bits (same MMAs in the same order on the same operands; K kept in one range)
+        monkeypatch.setenv("PGGAN_FORCE_SPLITK", "0,1")
         y2 = ops.k_conv(ops.k_upsample(xf, 1.0), ops._pack(w, "f", fmt=ops._fmt_of(xf, "a")), b, Co, 9, scale, 0.2)
         assert torch.equal(y, y2)
     # the whole G-block chain and its backward
