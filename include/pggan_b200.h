@@ -124,11 +124,12 @@ typedef struct {
     int32_t up2;
     /* Optional split-K workspace (any dtype; NULL: never split).  A layer with few output tiles and a long K — the
      * 4x4 / 8x8 trunk layers — is cut into several K ranges per output tile so that idle SMs share the operand traffic;
-     * the partial accumulators are added (fp32 red.global) into per-tile sums in ws_k and the CTA that arrives last at a
-     * tile reads the sum and runs the epilogue (so the last bits of a result may depend on arrival order, as with any
-     * fp32 atomic reduction).  ws_k: 16-byte aligned, ws_k_bytes >= 4096, ALL ZERO before the first call; every call
-     * leaves it all zero again; calls that share a workspace must be stream-ordered.  The library decides per shape
-     * whether (and how far) to split within ws_k_bytes. */
+     * the partial accumulators are added (fp32 red.global) into per-tile pair buffers in ws_k — at most two addends per
+     * buffer, so a buffer's content does not depend on arrival order — and the CTA that arrives last at a tile adds the
+     * buffers in a fixed order and runs the epilogue: results are reproducible bit for bit.  ws_k: 16-byte aligned,
+     * ws_k_bytes >= 4096, ALL ZERO before the first call; every call leaves it all zero again; calls that share a
+     * workspace must be stream-ordered.  The library decides per shape whether (and how far) to split within
+     * ws_k_bytes. */
     void* ws_k;
     int64_t ws_k_bytes;
 } pg_conv_params;

@@ -71,10 +71,12 @@ struct ConvKArgs {
     int up2;                 // fused nearest-2x up-sampling: the tile geometry (BW/BH/BB, tiles_*) is in LOW-RES pixels,
                              // every box yields four tiles (one per output-pixel parity); H, W are the output dims
     // split-K (plain kernel, MT = 1): a layer with few output tiles and a long K (the 4^2 / 8^2 trunk layers: each CTA
-    // would pull its whole K extent through ONE SM's ~64 B/clk L2 port — 25 us whatever the tile, tools/gemm_micro.py
-    // small) is cut into ksplit K ranges per output tile.  Every CTA adds its fp32 partial accumulator into the tile's
-    // sum in `ws_part` ([tile][column][row], zero between launches) with red.global; the CTA that arrives last at the
-    // tile's counter reads the sum, clears it and runs the epilogue.  Counters return to zero.
+    // would pull its whole K extent through ONE SM's L2 port — ~0.2-0.35 us per k-step whatever the tile,
+    // tools/splitk_micro.py) is cut into ksplit K ranges per output tile.  CTA ks adds its fp32 partial accumulator into
+    // pair buffer ks/2 of the tile in `ws_part` ([tile][pair][column][row], zero between launches) with red.global: a
+    // buffer receives at most two addends, so its content does not depend on their order.  The CTA that arrives last at
+    // the tile's counter adds the pair buffers in pair order, clears them and runs the epilogue: results are
+    // reproducible bit for bit.  Counters return to zero.
     int ksplit;
     float* ws_part;
     unsigned int* ws_count;
@@ -267,7 +269,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             // where the code below reads the accumulator and leaving zeros behind for the next launch
             float* part0 = nullptr;
             if (a.ksplit > 1) {
-                float* part = a.ws_part + static_cast<size_t>(mn) * (kBlockM * BLOCK_N) + q * 32 + lane;
+                const int npairs = (a.ksplit + 1) >> 1;
+                float* part = a.ws_part + (static_cast<size_t>(mn) * npairs + (ks >> 1)) * (kBlockM * BLOCK_N) + q * 32 + lane;
 #pragma unroll 1
                 for (int j = 0; j < BLOCK_N / CH; ++j) {
                     __syncwarp();
@@ -297,21 +300,41 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + egroup) : "memory");          // flag may be rewritten for the next tile
                 if (!last) continue;              // (MT == 1: leaves the m loop; the accumulator is released below)
                 __threadfence();
-                part0 = part;
+                part0 = a.ws_part + static_cast<size_t>(mn) * npairs * (kBlockM * BLOCK_N) + q * 32 + lane;
             }
-            // accumulator chunk j -> r: from TMEM, or (split-K, last CTA) the tile's sum in the workspace
+            // accumulator chunk j -> r: from TMEM, or (split-K, last CTA) the pair sums of the workspace added in pair order
             auto load_acc = [&](int j, uint32_t (&r)[32], bool clear) {
                 if (part0 == nullptr) {
                     tmem_ld_wait();
                     return;
                 }
-                float* pp = part0 + static_cast<size_t>(j * CH) * kBlockM;
+                const int npairs = (a.ksplit + 1) >> 1;
+                constexpr size_t kTile = static_cast<size_t>(kBlockM) * BLOCK_N;
+                float t[CH];
 #pragma unroll
-                for (int i = 0; i < CH; ++i) r[i] = __float_as_uint(__ldcg(pp + static_cast<size_t>(i) * kBlockM));
-                if (clear) {
+                for (int i = 0; i < CH; ++i) t[i] = 0.f;
+#pragma unroll 1
+                for (int pr = 0; pr < npairs; pr += 2) {          // two pair buffers in flight per round
+                    float* pa = part0 + pr * kTile + static_cast<size_t>(j * CH) * kBlockM;
+                    const bool two = pr + 1 < npairs;
+                    float ua[CH], ub[CH];
 #pragma unroll
-                    for (int i = 0; i < CH; ++i) __stcg(pp + static_cast<size_t>(i) * kBlockM, 0.f);
+                    for (int i = 0; i < CH; ++i) ua[i] = __ldcg(pa + static_cast<size_t>(i) * kBlockM);
+#pragma unroll
+                    for (int i = 0; i < CH; ++i) ub[i] = two ? __ldcg(pa + kTile + static_cast<size_t>(i) * kBlockM) : 0.f;
+#pragma unroll
+                    for (int i = 0; i < CH; ++i) t[i] = (t[i] + ua[i]) + ub[i];
+                    if (clear) {
+#pragma unroll
+                        for (int i = 0; i < CH; ++i) __stcg(pa + static_cast<size_t>(i) * kBlockM, 0.f);
+                        if (two) {
+#pragma unroll
+                            for (int i = 0; i < CH; ++i) __stcg(pa + kTile + static_cast<size_t>(i) * kBlockM, 0.f);
+                        }
+                    }
                 }
+#pragma unroll
+                for (int i = 0; i < CH; ++i) r[i] = __float_as_uint(t[i]);
             };
             // fused pixel norm (one N tile covers the layer: this thread owns all channels of its pixel): a first pass
             // over the accumulator for mean(lrelu(..)^2), then the normal pass multiplies by the factor
@@ -763,7 +786,7 @@ static int launch_tc(const pg_conv_params* p, cudaStream_t stream, int ksplit = 
     a.ws_count = nullptr;
     if (ksplit > 1) {
         const long long mn_tiles = (long long)a.tiles_w * a.tiles_h * a.tiles_b * a.tiles_n * (a.up2 ? 4 : 1);
-        const size_t need = kSplitHeader + (size_t)mn_tiles * kBlockM * BLOCK_N * sizeof(float);
+        const size_t need = kSplitHeader + (size_t)mn_tiles * ((ksplit + 1) / 2) * kBlockM * BLOCK_N * sizeof(float);
         PG_CHECK(MT == 1 && p->ws_k != nullptr && (size_t)p->ws_k_bytes >= need && mn_tiles <= kSplitCounters &&
                      (p->taps * a.kc_per_tap) % ksplit == 0,
                  PG_ERR_ARG, "split-K: internal dispatch error (ksplit=%d)", ksplit);
@@ -928,29 +951,32 @@ static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream, int* k
             if (p->N % 32 == 0) return launch_tc<T, 32, 32>(p, stream);
             return launch_tc<T, 16, 32>(p, stream);
         }
-        // Few output tiles, long K: every CTA pulls its K extent through one SM's L2 port (~118 GB/s measured: 25-28 us
-        // for 72 k-steps whatever the tile shape, tools/gemm_micro.py small).  With a workspace the K extent is split
-        // over the idle SMs instead: choose (N tile, splits) minimising   k-steps/S * bytes per k-step  +  the tile's
-        // sum added to and re-read from the workspace,  all CTAs in one wave.
+        // Few output tiles, long K: every CTA pulls its K extent through one SM's L2 port (measured per k-step, GPU time
+        // inside a CUDA graph, tools/splitk_micro.py: 0.21 / 0.33 / 0.62 us at N tile 64 / 128 / 256 — 21-24 us for the
+        // 72 k-steps of a 512-channel 3x3 layer however few pixels it has).  With a workspace the K extent is split over
+        // the idle SMs instead: choose (N tile, splits) minimising   k-steps/S * time per k-step  +  the latency rounds
+        // of the CTA that adds the pair buffers,  all CTAs in one wave; only for layers with at most ~40 tiles at N = 128
+        // (beyond that the unsplit kernel already covers the machine: 16^2 x 16 measured 26.8 us unsplit, 30 us split).
         static const bool no_splitk = getenv("PGGAN_NO_SPLITK") != nullptr;
         if (!no_splitk && p->ws_k != nullptr && reinterpret_cast<uintptr_t>(p->ws_k) % 16 == 0 && !p->up2 && span == 128) {
             const int num_kc = p->taps * (p->C / (128 / (int)sizeof(T)));
-            const double port = 118e3;                                   // bytes per microsecond into one SM
             double t_best = 1e30;
             int bn_best = 0, s_best = 1;
-            const int bns[3] = {256, 128, 64};
-            for (int i = 0; i < 3; ++i) {
+            const int bns[3] = {64, 128, 256};
+            const double tks[3] = {0.21, 0.33, 0.62};
+            const bool few = m_tiles * ((p->N + 127) / 128) <= 40 && num_kc >= 16;
+            for (int i = 0; i < 3 && few; ++i) {
                 const int b = bns[i];
                 if (p->N % b != 0) continue;
                 if (p->pn_rnorm != nullptr && b != p->N) continue;
                 const long long mn = m_tiles * (p->N / b);
                 if (mn > sms || mn > kSplitCounters) continue;
-                const double kstep = (16384.0 + b * 128.0) / port;
-                for (int S = 1; S <= 16; ++S) {
+                for (int S = 2; S <= 8; ++S) {
                     if (num_kc % S != 0 || mn * S > sms) continue;
-                    const size_t need = kSplitHeader + (size_t)mn * kBlockM * b * sizeof(float);
-                    if (S > 1 && need > (size_t)p->ws_k_bytes) continue;
-                    const double t = (num_kc / S) * kstep + (S > 1 ? 2.0 * (b * 512.0) / port + 1.5 : 0.0);
+                    const int npairs = (S + 1) / 2;
+                    const size_t need = kSplitHeader + (size_t)mn * npairs * kBlockM * b * sizeof(float);
+                    if (need > (size_t)p->ws_k_bytes) continue;
+                    const double t = (num_kc / S) * tks[i] + 0.7 * (b / 32) * ((npairs + 1) / 2) * 0.5 + 0.1 * S * (b / 64);
                     if (t < t_best - 1e-9) {
                         t_best = t;
                         bn_best = b;
@@ -958,13 +984,13 @@ static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream, int* k
                     }
                 }
             }
-            if (const char* f = getenv("PGGAN_FORCE_SPLITK")) {          // tuning experiments only: "bn,S"
+            if (const char* f = getenv("PGGAN_FORCE_SPLITK")) {          // tuning experiments only: "bn,S"; "x,1": never split
                 int fb = 0, fs = 0;
-                if (sscanf(f, "%d,%d", &fb, &fs) == 2 && fs == 1) s_best = 1;               // "x,1": never split
-                if (sscanf(f, "%d,%d", &fb, &fs) == 2 && (fb == 64 || fb == 128 || fb == 256) && p->N % fb == 0 && fs >= 1 &&
+                if (sscanf(f, "%d,%d", &fb, &fs) == 2 && fs == 1) s_best = 1;
+                if (sscanf(f, "%d,%d", &fb, &fs) == 2 && (fb == 64 || fb == 128 || fb == 256) && p->N % fb == 0 && fs >= 2 &&
                     (p->pn_rnorm == nullptr || fb == p->N) &&
-                    num_kc % fs == 0 && m_tiles * (p->N / fb) * fs <= 2LL * sms &&
-                    kSplitHeader + (size_t)m_tiles * (p->N / fb) * kBlockM * fb * sizeof(float) <= (size_t)p->ws_k_bytes) {
+                    num_kc % fs == 0 && m_tiles * (p->N / fb) * fs <= 2LL * sms && m_tiles * (p->N / fb) <= kSplitCounters &&
+                    kSplitHeader + (size_t)m_tiles * (p->N / fb) * ((fs + 1) / 2) * kBlockM * fb * sizeof(float) <= (size_t)p->ws_k_bytes) {
                     bn_best = fb;
                     s_best = fs;
                 }

@@ -148,12 +148,12 @@ def test_conv_fprop(shape, backend, dtype):
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
 @pytest.mark.parametrize("shape,force", [((16, 4, 4, 512, 512), None), ((16, 8, 8, 512, 512), None), ((4, 16, 16, 512, 256), None),
-                                         ((3, 8, 8, 256, 128), "128,9"), ((16, 4, 4, 512, 512), "256,4"),
+                                         ((3, 8, 8, 256, 128), "128,9"), ((16, 4, 4, 512, 512), "256,3"),
                                          ((5, 8, 8, 128, 64), "64,3"), ((32, 4, 4, 256, 256), "64,12")])
 def test_conv_split_k(shape, force, dtype, monkeypatch):
     """few output tiles, long K: the K extent is split over otherwise idle SMs (pg_conv_params.ws_k), partial
     accumulators are summed in the workspace and the last CTA of a tile runs the (mask / bias / LeakyReLU / pixel-norm)
-    epilogue — same result as the unsplit kernel, workspace left at zero"""
+    epilogue — same result as the unsplit kernel, reproducible bits, workspace left at zero"""
     from pggan_b200 import ops, _lib
     import pggan_b200 as pg
     pg.set_compute_dtype(dtype)
@@ -180,8 +180,8 @@ def test_conv_split_k(shape, force, dtype, monkeypatch):
         return y
 
     y1 = run(force)
-    y2 = run(force)                                               # the workspace is back at zero: same result again
-    assert rel_l2(f32(y1), f32(y2)) < (1e-6 if dtype == torch.float32 else 1e-4)
+    y2 = run(force)                                               # the workspace is back at zero, the sum order fixed
+    assert torch.equal(y1, y2)
     y0 = run("0,1")                                               # one K range: the unsplit kernel
     ref = F.leaky_relu(F.conv2d(x, w, b, padding=1) * scale, 0.2)
     ref = torch.where(m > 0, ref, ref * 0.2)

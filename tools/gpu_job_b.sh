@@ -6,7 +6,7 @@ timeout 1200 python -m pytest tests/test_gpu_kernels.py -q -x -p no:cacheprovide
 echo "kernel tests rc ${PIPESTATUS[0]}"; tail -6 gpurun_out/tests_k_${TAG}.log | cut -c1-220
 timeout 1500 python -m pytest tests -m gpu -q --maxfail=20 -rf -p no:cacheprovider > gpurun_out/tests_${TAG}.log 2>&1
 echo "pytest rc $?"; tail -8 gpurun_out/tests_${TAG}.log | cut -c1-220
-echo "== auto"; timeout 200 python tools/gemm_micro.py 10 small 2>&1 | grep conv_fprop > gpurun_out/small_${TAG}.txt; cat gpurun_out/small_${TAG}.txt
+timeout 600 python tools/splitk_micro.py > gpurun_out/splitk_${TAG}.txt 2>&1; cut -c1-400 gpurun_out/splitk_${TAG}.txt
 timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err; echo "bench rc $?"; tail -3 gpurun_out/bench_${TAG}.err
 python - <<PY
 import json
