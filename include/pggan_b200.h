@@ -160,9 +160,19 @@ typedef struct {
     /* PG_F32 only — 3xTF32 workspaces: ws_g: 3*B*H*W*N floats, ws_x: 3*B*H*W*C floats */
     void* ws_g;
     void* ws_x;
+    /* Optional direct accumulation (NULL: off).  If `direct` != NULL and pggan_conv_wgrad_direct_ok(p) != 0, every
+     * unit of the launch ADDS direct_scale * (its partial sums) straight into direct[N][taps][C] (fp32, red.global) —
+     * autograd's accumulation into a .grad that has the operand's own layout (a channels_last conv weight, a plain
+     * [out,in] linear weight) — and `acc` is not touched: no slice buffer, no pggan_unpack_wgrad pass. */
+    float* direct;
+    float direct_scale;
+    int32_t reserved_;
 } pg_wgrad_params;
 int pggan_conv_wgrad(const pg_wgrad_params* p, void* stream);
-int pggan_conv_wgrad_slices(const pg_wgrad_params* p); /* how many slices the call above will write (>= 1) */
+int pggan_conv_wgrad_slices(const pg_wgrad_params* p);
+/* 1 if pggan_conv_wgrad honours p->direct for this shape (the tensor-core kernels), 0 if the caller must use acc +
+ * pggan_unpack_wgrad (SIMT fallback shapes) */
+int pggan_conv_wgrad_direct_ok(const pg_wgrad_params* p); /* how many slices the call above will write (>= 1) */
 
 /* ------------------------------------------------------------------------------------------
  * Elementwise / reduction kernels on NHWC feature maps (n = element count, m = pixels).

@@ -35,6 +35,7 @@ class WgradParams(Structure):
         ("B", c_int32), ("H", c_int32), ("W", c_int32), ("C", c_int32), ("N", c_int32), ("taps", c_int32),
         ("dtype", c_int32),
         ("ws_g", c_void_p), ("ws_x", c_void_p),
+        ("direct", c_void_p), ("direct_scale", c_float), ("reserved_", c_int32),
     ]
 
 
@@ -73,6 +74,7 @@ SIGNATURES = {
     "pggan_conv_up2_fusable": (c_int, [POINTER(ConvParams)]),
     "pggan_conv_wgrad": (c_int, [POINTER(WgradParams), c_void_p]),
     "pggan_conv_wgrad_slices": (c_int, [POINTER(WgradParams)]),
+    "pggan_conv_wgrad_direct_ok": (c_int, [POINTER(WgradParams)]),
     "pggan_lrelu_mask_mul": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_int, c_void_p]),
     "pggan_upsample2x": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, Coef, c_int, c_void_p]),
     "pggan_upsample2x_mask": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, Coef, c_float, c_int,

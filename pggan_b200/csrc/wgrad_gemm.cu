@@ -49,6 +49,8 @@ template <typename T, int BLOCK_C> struct WgCfg {
 struct WgKArgs {
     float* acc;
     long long slice_elems;          // N*taps*C: split s writes its partial sums to acc + s*slice_elems
+    float* direct;                  // != NULL: add dscale * partial sums straight into this [N][taps][C] tensor instead
+    float dscale;
     int B, H, W, C, N, taps;
     int PW, PH, PB;                 // pixel box of one stage
     int chunks_w, chunks_h, chunks_b;
@@ -238,7 +240,16 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
                     t = tap * a.tpu + (j * 32) / a.C;
                     c0 = (j * 32) % a.C;
                 }
-                if (valid && t < a.taps) {     // every (split, tap, n, c) element is owned by exactly one unit: plain stores
+                if (valid && t < a.taps && a.direct != nullptr) {
+                    // gradient accumulation in place: the splits (and earlier backward passes) meet through fp32 reductions
+                    float* dst = a.direct + (static_cast<size_t>(n) * a.taps + t) * a.C + c0;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c * 4),
+                                     "f"(__uint_as_float(r[c * 4 + 0]) * a.dscale), "f"(__uint_as_float(r[c * 4 + 1]) * a.dscale),
+                                     "f"(__uint_as_float(r[c * 4 + 2]) * a.dscale), "f"(__uint_as_float(r[c * 4 + 3]) * a.dscale)
+                                     : "memory");
+                } else if (valid && t < a.taps) {     // every (split, tap, n, c) element is owned by exactly one unit: plain stores
                     float* dst = slice + (static_cast<size_t>(n) * a.taps + t) * a.C + c0;
 #pragma unroll
                     for (int c = 0; c < 8; ++c)
@@ -393,6 +404,8 @@ template <typename T, int BLOCK_C>
 static void plan_wg(const pg_wgrad_params* p, WgKArgs& a) {
     using Cfg = WgCfg<T, BLOCK_C>;
     a.acc = p->acc;
+    a.direct = p->direct;
+    a.dscale = p->direct_scale;
     a.B = p->B; a.H = p->H; a.W = p->W; a.C = p->C; a.N = p->N; a.taps = p->taps;
     a.slice_elems = (long long)p->N * p->taps * p->C;
     a.PW = p->W < Cfg::BKP ? p->W : Cfg::BKP;
@@ -543,11 +556,13 @@ static int wgrad_dispatch(const pg_wgrad_params* p_in, cudaStream_t stream, int*
     const bool tc_ok = g_conv_backend == PG_BACKEND_AUTO && is_pow2(p->H) && is_pow2(p->W) && (p->C % CPS == 0) &&
                        (p->N % 8 == 0) && (!kF32 || slices_out || (p->ws_g && p->ws_x)) &&
                        (reinterpret_cast<uintptr_t>(p->g) % 16 == 0) &&
-                       (reinterpret_cast<uintptr_t>(p->x) % 16 == 0) && (reinterpret_cast<uintptr_t>(p->acc) % 16 == 0);
+                       (reinterpret_cast<uintptr_t>(p->x) % 16 == 0) && (reinterpret_cast<uintptr_t>(p->acc) % 16 == 0) &&
+                       (reinterpret_cast<uintptr_t>(p->direct) % 16 == 0);
     if constexpr (!kF32) {
         static const bool no_rows = getenv("PGGAN_NO_WROWS") != nullptr;
         const bool rows_ok = g_conv_backend == PG_BACKEND_AUTO && (reinterpret_cast<uintptr_t>(p->g) % 16 == 0) &&
-                             (reinterpret_cast<uintptr_t>(p->x) % 16 == 0) && (reinterpret_cast<uintptr_t>(p->acc) % 16 == 0);
+                             (reinterpret_cast<uintptr_t>(p->x) % 16 == 0) && (reinterpret_cast<uintptr_t>(p->acc) % 16 == 0) &&
+                             (reinterpret_cast<uintptr_t>(p->direct) % 16 == 0);
         if (rows_ok && !no_rows && wgrad_rows_supported(p)) {
             if (slices_out) {
                 *slices_out = wgrad_rows_slices(p);
@@ -589,6 +604,8 @@ static int wgrad_dispatch(const pg_wgrad_params* p_in, cudaStream_t stream, int*
             if (p->C % 32 == 0) return launch_wg<T, 32>(p, stream);
         }
     }
+    PG_CHECK(p->direct == nullptr, PG_ERR_UNSUPPORTED,
+             "pggan_conv_wgrad: direct accumulation is not available for this shape (ask pggan_conv_wgrad_direct_ok)");
     return wgrad_simt<T>(p, stream);
 }
 
@@ -596,7 +613,7 @@ static int wgrad_dispatch(const pg_wgrad_params* p_in, cudaStream_t stream, int*
 
 extern "C" int pggan_conv_wgrad(const pg_wgrad_params* p, void* stream) {
     using namespace pg;
-    PG_CHECK(p != nullptr && p->g && p->x && p->acc, PG_ERR_ARG, "pggan_conv_wgrad: null pointer");
+    PG_CHECK(p != nullptr && p->g && p->x && (p->acc || p->direct), PG_ERR_ARG, "pggan_conv_wgrad: null pointer");
     PG_CHECK(p->B > 0 && p->H > 0 && p->W > 0 && p->C > 0 && p->N > 0, PG_ERR_ARG,
              "pggan_conv_wgrad: bad dims B=%d H=%d W=%d C=%d N=%d", p->B, p->H, p->W, p->C, p->N);
     PG_CHECK(p->taps == 1 || p->taps == 9, PG_ERR_ARG, "pggan_conv_wgrad: taps must be 1 or 9 (got %d)", p->taps);
@@ -619,4 +636,19 @@ extern "C" int pggan_conv_wgrad_slices(const pg_wgrad_params* p) {
     else if (q.dtype == PG_F32)
         wgrad_dispatch<float>(&q, nullptr, &slices);
     return slices;
+}
+
+extern "C" int pggan_conv_wgrad_direct_ok(const pg_wgrad_params* p) {
+    using namespace pg;
+    if (p == nullptr || p->B <= 0 || p->H <= 0 || p->W <= 0 || p->C <= 0 || p->N <= 0 || g_conv_backend != PG_BACKEND_AUTO) return 0;
+    if (reinterpret_cast<uintptr_t>(p->direct) % 16 != 0 || reinterpret_cast<uintptr_t>(p->g) % 16 != 0 ||
+        reinterpret_cast<uintptr_t>(p->x) % 16 != 0)
+        return 0;
+    if (p->taps != 1 && p->taps != 9) return 0;
+    if (p->dtype == PG_F32) {
+        return is_pow2(p->H) && is_pow2(p->W) && p->C % 32 == 0 && p->N % 8 == 0;
+    }
+    if (!is16(p->dtype)) return 0;
+    if (wgrad_rows_supported(p)) return 1;
+    return is_pow2(p->H) && is_pow2(p->W) && p->C % 64 == 0 && p->N % 8 == 0;
 }

@@ -31,6 +31,8 @@ constexpr int kWrThreads = 224;      // TMA warp, MMA warp, 4 epilogue warps, se
 struct WrKArgs {
     float* acc;
     long long slice_elems;
+    float* direct;           // != NULL: add dscale * partial sums straight into this [N][9][C] tensor (no slices)
+    float dscale;
     int B, H, W, C, N;
     int nseg;
     int f16;                 // g is IEEE half (else bf16)
@@ -223,9 +225,17 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                 const int n0 = (j * 16) % NCH;
                 if (dx < 3 && u_begin < u_end) {
                     const int t = (2 - i) * 3 + dx;
+                    if (a.direct != nullptr) {
 #pragma unroll
-                    for (int e = 0; e < 16; ++e)
-                        slice[(static_cast<size_t>(n0 + e) * 9 + t) * C + c] = __uint_as_float(r[e]);
+                        for (int e = 0; e < 16; ++e)
+                            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(a.direct + (static_cast<size_t>(n0 + e) * 9 + t) * C + c),
+                                         "f"(__uint_as_float(r[e]) * a.dscale)
+                                         : "memory");
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e)
+                            slice[(static_cast<size_t>(n0 + e) * 9 + t) * C + c] = __uint_as_float(r[e]);
+                    }
                 }
             }
         }
@@ -267,6 +277,8 @@ static int launch_wr(const pg_wgrad_params* p, cudaStream_t stream) {
     using Cfg = WrCfg<XSPAN, GSPAN>;
     WrKArgs a;
     a.acc = p->acc;
+    a.direct = p->direct;
+    a.dscale = p->direct_scale;
     a.slice_elems = static_cast<long long>(p->N) * 9 * p->C;
     a.B = p->B; a.H = p->H; a.W = p->W; a.C = p->C; a.N = p->N;
     a.nseg = p->W / 128;

@@ -648,6 +648,16 @@ def dgrad_mask_fusable(batch, h, w, fwd_in_channels, fwd_out_channels, taps=9, d
     return hit
 
 
+DIRECT_WGRAD = True      # tests switch it off to compare against the slice buffer + un-pack path
+
+
+def _dense_map(fmap) -> bool:
+    """does the logical operand [N][taps][C] coincide with the parameter memory (no permutation, no padding)?"""
+    n_total, n_valid, n2, taps, c_total, c_valid, c2, base, s_n1, s_n2, s_t, s_c1, s_c2 = fmap
+    return n2 == 1 and c2 == 1 and base == 0 and s_c1 == 1 and (taps == 1 or s_t == c_total) and \
+        s_n1 == taps * c_total and n_valid == n_total and c_valid == c_total
+
+
 def k_wgrad(g, x, scale, wshape, layout=None, accumulate_into=None, xc=A):
     """weight gradient in the parameter's own fp32 layout: a new tensor, or added into `accumulate_into`.
     g is a gradient-class tensor, x of class `xc` (converted to the gradient format when that differs)."""
@@ -667,14 +677,24 @@ def k_wgrad(g, x, scale, wshape, layout=None, accumulate_into=None, xc=A):
         # both GEMM operands must share one element format: the saved fp16 activation is re-rounded to bf16 (mixed mode)
         x = k_convert(x, _fmt_of(x, xc), gfmt)
     p.x = x.data_ptr()
-    slices = L.load().pggan_conv_wgrad_slices(ctypes.byref(p))
-    acc = torch.empty((slices, n, taps, c), dtype=torch.float32, device=g.device)
-    p.acc = acc.data_ptr()
     ws = None
     if gfmt == L.PG_F32:
         ws = (torch.empty(3 * g.numel(), dtype=torch.float32, device=g.device),
               torch.empty(3 * x.numel(), dtype=torch.float32, device=g.device))
         p.ws_g, p.ws_x = ws[0].data_ptr(), ws[1].data_ptr()
+    if accumulate_into is not None and DIRECT_WGRAD and _dense_map(fmap):
+        p.direct, p.direct_scale = accumulate_into.data_ptr(), float(scale)
+        if not L.load().pggan_conv_wgrad_direct_ok(ctypes.byref(p)):
+            p.direct, p.direct_scale = None, 0.0
+    if p.direct:
+        # the gradient has the operand's own layout (channels_last conv weight, plain linear weight): the GEMM's epilogue
+        # adds its scaled partial sums straight into .grad — no slice buffer, no un-pack pass
+        with _Timed("wgrad_gemm", (b, h, w, c, n, taps)):
+            L.check(L.load().pggan_conv_wgrad(ctypes.byref(p), _s()), "pggan_conv_wgrad")
+        return None
+    slices = L.load().pggan_conv_wgrad_slices(ctypes.byref(p))
+    acc = torch.empty((slices, n, taps, c), dtype=torch.float32, device=g.device)
+    p.acc = acc.data_ptr()
     with _Timed("wgrad_gemm", (b, h, w, c, n, taps)):
         L.check(L.load().pggan_conv_wgrad(ctypes.byref(p), _s()), "pggan_conv_wgrad")
     m = _packmap(fmap)

@@ -337,6 +337,49 @@ def test_elementwise(dtype):
     assert rel_l2(xr.grad, 4 * F.avg_pool2d(f32(up), 2)) < 2 * tol(dtype, "g")
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+@pytest.mark.parametrize("shape", [(4, 16, 16, 128, 256, 9), (16, 4, 4, 512, 512, 9), (2, 32, 128, 64, 64, 9),
+                                   (1, 16, 256, 32, 16, 9), (8, 1, 1, 8192, 512, 1), (3, 8, 8, 64, 128, 9)])
+def test_wgrad_accumulates_straight_into_the_gradient(shape, dtype, monkeypatch):
+    """a weight gradient whose layout is the GEMM's own ([N][taps][C]: channels_last conv weight, plain linear weight)
+    is accumulated by the kernel's epilogue (pg_wgrad_params.direct): same numbers as slices + un-pack, added on top
+    of what the gradient held"""
+    from pggan_b200 import ops
+    import pggan_b200 as pg
+    pg.set_compute_dtype(dtype)
+    B, H, W, Ci, Co, taps = shape
+    if dtype == torch.float32 and B * H * W * Ci * Co > 3e8:
+        pytest.skip("fp32 cross-check kept to small shapes")
+    dev = "cuda"
+    k = 3 if taps == 9 else 1
+    torch.manual_seed(5)
+    x = rnd(torch.randn(B, Ci, H, W, device=dev), dtype)
+    g = rnd(torch.randn(B, Co, H, W, device=dev), dtype, "g")
+    if taps == 1:
+        xf, gf = to_feat(x.view(B, Ci), dtype), to_feat(g.view(B, Co), dtype, "g")
+        wshape = (Co, Ci)
+        grad0 = torch.randn(Co, Ci, device=dev)
+        ref = g.view(B, Co).t() @ x.view(B, Ci)
+    else:
+        xf, gf = to_feat(x, dtype), to_feat(g, dtype, "g")
+        wshape = (Co, Ci, k, k)
+        grad0 = torch.randn(Co, Ci, k, k, device=dev).contiguous(memory_format=torch.channels_last)
+        ref = torch.nn.grad.conv2d_weight(x, wshape, g, padding=1)
+    outs = []
+    for direct in (True, False):
+        monkeypatch.setattr(ops, "DIRECT_WGRAD", direct)
+        acc = grad0.clone(memory_format=torch.preserve_format)
+        before = _lib_other_launches()
+        ops.k_wgrad(gf, xf, 0.25, wshape, None, accumulate_into=acc)
+        torch.cuda.synchronize()
+        if direct and dtype != torch.float32:            # (fp32: the 3xTF32 operand splits are counted there too)
+            assert _lib_other_launches() == before, "no un-pack launch on the direct path"
+        outs.append(acc)
+    want = grad0 + 0.25 * ref
+    assert rel_l2(outs[0], want) < (2e-4 if dtype == torch.float32 else 3e-3), rel_l2(outs[0], want)
+    assert rel_l2(outs[0], outs[1]) < 1e-5, rel_l2(outs[0], outs[1])
+
+
 def _emulate_map(n_elems, args, device):
     """index tensor [n_total, taps, c_total] into the flat parameter (-1 = zero padding) of a pg_pack_map tuple"""
     n_total, n_valid, n2, taps, c_total, c_valid, c2, base, s_n1, s_n2, s_t, s_c1, s_c2 = args
