@@ -92,3 +92,14 @@ extern "C" int pggan_launch_counts(int64_t* tc, int64_t* simt, int64_t* other) {
     if (other) *other = pg::g_other_launches.load();
     return PG_OK;
 }
+
+namespace pg {
+bool pdl_enabled() {
+    // programmatic dependent launch of this library's kernels; PGGAN_PDL=0 switches it off
+    static const bool on = [] {
+        const char* e = getenv("PGGAN_PDL");
+        return e == nullptr ? true : (e[0] != '0');
+    }();
+    return on;
+}
+}  // namespace pg

@@ -31,6 +31,37 @@ void set_error(const char* fmt, ...);
         }                                                                          \
     } while (0)
 #define PG_LAUNCH_CHECK() PG_CUDA(cudaPeekAtLastError())
+// Programmatic dependent launch (griddepcontrol): a kernel launched through pg::launch() with PGGAN_PDL=1 may be
+// SCHEDULED while its predecessor in the stream is still running — its CTAs take an SM as soon as one is free, run their
+// prologue (barrier init, TMEM allocation, descriptor prefetch) and block in pdl_wait() until the predecessor has
+// completed and its writes are visible.  Every kernel calls PG_PDL_ENTER() before its first global-memory access:
+// wait for the predecessor, then allow the successor to be scheduled.  Without the launch attribute both instructions
+// are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#define PG_PDL_ENTER()     \
+    do {                   \
+        pg::pdl_wait();    \
+        pg::pdl_trigger(); \
+    } while (0)
+
+bool pdl_enabled();        // common.cu: env PGGAN_PDL (default on/off decided there)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // opt a kernel into > 48 KB of dynamic shared memory: the attribute is per (function, DEVICE), so remember it per device
 #define PG_SET_SMEM_ONCE(kern, bytes)                                                                         \
     do {                                                                                                      \

@@ -126,6 +126,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    PG_PDL_ENTER();        // prologue done (barriers, TMEM, descriptor prefetch): now wait for the predecessor's data
 
     const int num_m_tiles = a.tiles_w * a.tiles_h * a.tiles_b * (a.up2 ? 4 : 1);
     const int num_tiles = num_m_tiles * a.tiles_n * a.ksplit;      // a tile index = (output tile, K split), split fastest
@@ -495,6 +496,7 @@ conv_gemm_swapped_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    PG_PDL_ENTER();        // prologue done (barriers, TMEM, descriptor prefetch): now wait for the predecessor's data
 
     const int num_m_tiles = a.tiles_w * a.tiles_h * a.tiles_b;      // pixel tiles (256 pixels each)
     const int num_tiles = num_m_tiles * a.tiles_n;                  // x channel tiles (128 channels each)
@@ -688,6 +690,7 @@ __global__ void conv_direct_kernel(const T* __restrict__ x, const T* __restrict_
                                    const T* __restrict__ mask_src, void* __restrict__ y, int B, int H, int W, int C,
                                    int N, int taps, int out_dtype, float scale, float slope, float mask_slope, int xf16,
                                    int wf16) {
+    PG_PDL_ENTER();
     // 16-bit instantiation: the element formats (bf16 / IEEE half) of x (= y, mask) and wp are run-time flags
     auto ldx = [&](const T* p) -> float {
         if constexpr (sizeof(T) == 2) return f16bits_to_f(*reinterpret_cast<const uint16_t*>(p), xf16 != 0);
@@ -816,7 +819,7 @@ static int launch_tc(const pg_conv_params* p, cudaStream_t stream, int ksplit = 
     PG_SET_SMEM_ONCE(kern, Cfg::kSmemBytes);
     const int num_tiles = a.tiles_w * a.tiles_h * a.tiles_b * a.tiles_n * (a.up2 ? 4 : 1) * a.ksplit;
     int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-    kern<<<grid, kConvThreadsPlain, Cfg::kSmemBytes, stream>>>(tx, tw, a);
+    PG_CUDA(pg::launch(kern, grid, kConvThreadsPlain, Cfg::kSmemBytes, stream, tx, tw, a));
     PG_LAUNCH_CHECK();
     g_tc_launches++;
     return PG_OK;
@@ -864,7 +867,7 @@ static int launch_swapped(const pg_conv_params* p, cudaStream_t stream) {
     PG_SET_SMEM_ONCE(kern, kSwSmemBytes);
     const int num_tiles = a.tiles_w * a.tiles_h * a.tiles_b * a.tiles_n;
     const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-    kern<<<grid, kConvThreads, kSwSmemBytes, stream>>>(tx, tw, a);
+    PG_CUDA(pg::launch(kern, grid, kConvThreads, kSwSmemBytes, stream, tx, tw, a));
     PG_LAUNCH_CHECK();
     g_tc_launches++;
     return PG_OK;
@@ -1044,10 +1047,10 @@ static int conv_dispatch(const pg_conv_params* p_in, cudaStream_t stream, int* k
     if (total == 0) return PG_OK;
     long long blocks = (total + 255) / 256;
     if (blocks > 148LL * 32) blocks = 148LL * 32;
-    conv_direct_kernel<T><<<(int)blocks, 256, 0, stream>>>(
+    PG_CUDA(pg::launch(conv_direct_kernel<T>, (int)blocks, 256, 0, stream, 
         reinterpret_cast<const T*>(p->x), reinterpret_cast<const T*>(p->wp), p->bias,
         reinterpret_cast<const T*>(p->mask_src), p->y, p->B, p->H, p->W, p->C, p->N, p->taps, p->out_dtype, p->scale,
-        p->slope, p->mask_slope, p->dtype == PG_F16, p->dtype == PG_F16);
+        p->slope, p->mask_slope, p->dtype == PG_F16, p->dtype == PG_F16));
     PG_LAUNCH_CHECK();
     g_simt_launches++;
     return PG_OK;

@@ -119,6 +119,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    PG_PDL_ENTER();        // barriers and TMEM are set up: wait for the predecessor's data before the first global read
     if constexpr (J > 1) {
         // Toeplitz weight tiles, written straight into the SWIZZLE_128B K-major layout (16-byte chunk q of row r
         // lives at chunk q ^ (r & 7)); tile t = (dy, group tap gx), row = (pixel j of the group, n),
@@ -448,7 +449,7 @@ static int launch_rows(const pg_conv_params* p_in, cudaStream_t stream) {
     }
     auto kern = conv_rows_kernel<SPAN, BLOCK_N, J>;
     PG_SET_SMEM_ONCE(kern, Cfg::kSmemBytes);
-    kern<<<(int)grid, kRowsThreads, Cfg::kSmemBytes, stream>>>(tx, tw, a);
+    PG_CUDA(pg::launch(kern, (int)grid, kRowsThreads, Cfg::kSmemBytes, stream, tx, tw, a));
     PG_LAUNCH_CHECK();
     g_tc_launches++;
     return PG_OK;

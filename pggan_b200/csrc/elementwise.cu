@@ -44,6 +44,7 @@ template <typename T> __device__ __forceinline__ void st16(T* p, const V16<T>& v
 template <typename T>
 __global__ void lrelu_mask_mul_kernel(const T* __restrict__ g, const T* __restrict__ y, T* __restrict__ out,
                                       long long nvec, long long n, float slope) {
+    PG_PDL_ENTER();
     constexpr int VN = V16<T>::N;
     GRID_STRIDE(i, nvec) {
         V16<T> gv = ld16(g + i * VN), yv = ld16(y + i * VN), o;
@@ -64,6 +65,7 @@ __global__ void lrelu_mask_mul_kernel(const T* __restrict__ g, const T* __restri
 template <typename T>
 __global__ void axpby_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, long long nvec,
                              long long n, pg_coef ca, pg_coef cb) {
+    PG_PDL_ENTER();
     constexpr int VN = V16<T>::N;
     const float sa = coef_val(ca), sb = coef_val(cb);
     GRID_STRIDE(i, nvec) {
@@ -113,6 +115,7 @@ __device__ __forceinline__ void idx_decomp(long long i, int CV, int W, int H, in
 template <typename T>
 __global__ void upsample2x_kernel(const T* __restrict__ x, const T* __restrict__ mask_src, T* __restrict__ out, int B,
                                   int H, int W, int CV, pg_coef cscale, float slope) {
+    PG_PDL_ENTER();
     constexpr int VN = V16<T>::N;
     const float scale = coef_val(cscale);
     const long long total = static_cast<long long>(B) * H * W * CV;
@@ -158,6 +161,7 @@ __global__ void __launch_bounds__(256)
 upsample2x_mask_colsum_kernel(const T* __restrict__ x, const T* __restrict__ mask_src, T* __restrict__ out,
                               float* __restrict__ colsum, int B, int H, int W, int C, pg_coef cscale, float slope,
                               float cs_scale, int TX, long long rows_per_block) {
+    PG_PDL_ENTER();
     constexpr int VN = V16<T>::N;
     __shared__ float red[256 * VN];
     const float scale = coef_val(cscale);
@@ -210,6 +214,7 @@ upsample2x_mask_colsum_kernel(const T* __restrict__ x, const T* __restrict__ mas
 template <typename T>
 __global__ void pool2x2_kernel(const T* __restrict__ x, const T* __restrict__ blend, T* __restrict__ out, int B, int H,
                                int W, int CV, pg_coef cscale, pg_coef calpha) {
+    PG_PDL_ENTER();
     constexpr int VN = V16<T>::N;
     const float alpha = coef_val(calpha), scale = coef_val(cscale);
     const int Ho = H / 2, Wo = W / 2;
@@ -241,6 +246,7 @@ __global__ void pool2x2_kernel(const T* __restrict__ x, const T* __restrict__ bl
 template <typename T, int MAXV>
 __global__ void pixelnorm_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, float* __restrict__ rnorm,
                                      long long M, int C, float eps) {
+    PG_PDL_ENTER();
     constexpr int VN = V16<T>::N;
     const int lane = threadIdx.x & 31;
     const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
@@ -284,6 +290,7 @@ __global__ void __launch_bounds__(256)
 pixelnorm_bwd_kernel(const T* __restrict__ gy, const TY* __restrict__ y, const float* __restrict__ rnorm,
                      T* __restrict__ gx, long long M, int C, float act_slope, float* __restrict__ colsum,
                      float cs_scale) {
+    PG_PDL_ENTER();
     constexpr int VN = V16<T>::N;
     __shared__ float red[8][32 * VN + 1];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -354,6 +361,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 mask_colsum_kernel(const T* __restrict__ g, const T* __restrict__ y, T* __restrict__ out, float* __restrict__ colsum,
                    long long M, int C, float slope, float scale, int TX, long long rows_per_block) {
+    PG_PDL_ENTER();
     constexpr int VN = V16<T>::N;
     __shared__ float red[256 * VN];
     const int TY = blockDim.x / TX;
@@ -409,6 +417,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 colsum_only_kernel(const T* __restrict__ g, float* __restrict__ colsum, long long M, int C, float scale, int TX,
                    long long rows_per_block) {
+    PG_PDL_ENTER();
     constexpr int VN = V16<T>::N;
     __shared__ float red[256 * VN];
     const int TY = blockDim.x / TX;
@@ -450,6 +459,7 @@ colsum_only_kernel(const T* __restrict__ g, float* __restrict__ colsum, long lon
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ g, float* __restrict__ out, long long M, int C, float scale,
                               int TX, long long rows_per_block) {
+    PG_PDL_ENTER();
     constexpr int VN = V16<T>::N;
     __shared__ float red[256 * VN];
     const int CV = C / VN;
@@ -498,6 +508,7 @@ __device__ __forceinline__ long long pack_off(const PackMap& m, int n, int t, in
 
 template <typename T>
 __global__ void pack_weight_kernel(const float* __restrict__ in, T* __restrict__ out, PackMap m, long long total) {
+    PG_PDL_ENTER();
     GRID_STRIDE(i, total) {
         const int c = static_cast<int>(i % m.c_total);
         const long long r = i / m.c_total;
@@ -511,6 +522,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ in, T* __restrict__
 
 __global__ void unpack_wgrad_kernel(const float* __restrict__ in, float* __restrict__ out, PackMap m, long long total,
                                     float scale, int accumulate, int slices, long long slice_elems) {
+    PG_PDL_ENTER();
     GRID_STRIDE(i, total) {
         const int c = static_cast<int>(i % m.c_valid);
         const long long r = i / m.c_valid;
@@ -550,6 +562,7 @@ __device__ __forceinline__ int rel_off(const PackMap& m, int t, int c, long long
 template <typename T>
 __global__ void __launch_bounds__(256) pack_rowspan_kernel(const float* __restrict__ in, T* __restrict__ out, PackMap m,
                                                            RowSpan rs) {
+    PG_PDL_ENTER();
     extern __shared__ float srow[];
     const int n = blockIdx.x;
     T* orow = out + static_cast<size_t>(n) * m.taps * m.c_total;
@@ -577,6 +590,7 @@ __global__ void __launch_bounds__(256) pack_rowspan_kernel(const float* __restri
 __global__ void __launch_bounds__(256) unpack_rowspan_kernel(const float* __restrict__ in, float* __restrict__ out, PackMap m,
                                                              RowSpan rs, float scale, int accumulate, int slices,
                                                              long long slice_elems) {
+    PG_PDL_ENTER();
     extern __shared__ float srow[];
     const int n = blockIdx.x;                    // < n_valid
     const int rowlen = m.taps * m.c_total;
@@ -607,6 +621,7 @@ constexpr int kPackMaxI = 1024;         // fast paths handle up to 1024 (padded)
 // The parameter row is copied linearly (stride-9 reads from the tile are bank-conflict free: 9 is odd).
 template <typename T>
 __global__ void __launch_bounds__(256) pack_oihw_f_kernel(const float* __restrict__ W, T* __restrict__ out, int I, int Ip) {
+    PG_PDL_ENTER();
     extern __shared__ float tile[];                        // [I][9] exactly as in the parameter
     const int o = blockIdx.x;
     const float* src = W + static_cast<size_t>(o) * I * 9;
@@ -628,6 +643,7 @@ __global__ void __launch_bounds__(256) pack_oihw_f_kernel(const float* __restric
 __global__ void __launch_bounds__(256) unpack_oihw_kernel(const float* __restrict__ acc, float* __restrict__ gW, int I,
                                                           int Ip, float scale, int accumulate, int slices,
                                                           long long slice_elems, int slices_per_block) {
+    PG_PDL_ENTER();
     extern __shared__ float tile[];                        // [I][9]
     const int o = blockIdx.x;
     const float* src = acc + static_cast<size_t>(o) * 9 * Ip;
@@ -679,6 +695,7 @@ __global__ void __launch_bounds__(256) unpack_oihw_kernel(const float* __restric
 template <typename T>
 __global__ void __launch_bounds__(256) pack_oihw_t_kernel(const float* __restrict__ W, T* __restrict__ out, int O, int I,
                                                           int Np) {
+    PG_PDL_ENTER();
     __shared__ float tile[64][73];
     const int i0 = blockIdx.x * 8, o0 = blockIdx.y * 64;
     const int ni = min(8, I - i0);
@@ -702,6 +719,7 @@ __global__ void __launch_bounds__(256) pack_oihw_t_kernel(const float* __restric
 template <typename T>
 __global__ void __launch_bounds__(256) pack_ohwi_t_kernel(const float* __restrict__ W, T* __restrict__ out, int O, int I,
                                                           int Ip, int taps) {
+    PG_PDL_ENTER();
     __shared__ float tile[32][33];
     const int t = blockIdx.z, i0 = blockIdx.x * 32, o0 = blockIdx.y * 32;
     const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;           // 32 x 8
@@ -722,6 +740,7 @@ __global__ void __launch_bounds__(256) pack_ohwi_t_kernel(const float* __restric
 __global__ void __launch_bounds__(256) unpack_dense_kernel(const float* __restrict__ acc, float* __restrict__ gW,
                                                            long long n4, float scale, int accumulate, int slices,
                                                            long long slice_elems) {
+    PG_PDL_ENTER();
     GRID_STRIDE(i, n4) {
         float4 v = __ldg(reinterpret_cast<const float4*>(acc) + i);
         for (int sl = 1; sl < slices; ++sl) {
@@ -740,6 +759,7 @@ __global__ void __launch_bounds__(256) unpack_dense_kernel(const float* __restri
 // ------------------------------------------------------------------------------ format conversion
 template <typename TI, typename TO>
 __global__ void convert_kernel(const TI* __restrict__ in, TO* __restrict__ out, long long n) {
+    PG_PDL_ENTER();
     // 8 elements per thread: one or two 16-byte loads, one or two 16-byte stores
     const long long nvec = n / 8;
     GRID_STRIDE(i, nvec) {
@@ -776,6 +796,7 @@ __global__ void convert_kernel(const TI* __restrict__ in, TO* __restrict__ out, 
 // K-major operands of the fprop-style GEMM, or along rows ([3M][C]) for the pixel-reduction of wgrad.
 __global__ void split3_kernel(const float* __restrict__ in, float* __restrict__ out, long long M, int CV,
                               int along_channels, int lo_slot) {
+    PG_PDL_ENTER();
     const long long total = M * CV;
     const long long C = 4LL * CV;
     GRID_STRIDE(i, total) {
@@ -802,6 +823,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 pixelnorm_fwd_small_kernel(const T* __restrict__ x, T* __restrict__ y, float* __restrict__ rnorm, long long M, int C,
                            float eps, int LP) {
+    PG_PDL_ENTER();
     constexpr int VN = V16<T>::N;
     const long long nvec_total = M * LP;
     const float inv_c = 1.f / C;
@@ -831,6 +853,7 @@ __global__ void __launch_bounds__(256)
 pixelnorm_bwd_small_kernel(const T* __restrict__ gy, const TY* __restrict__ y, const float* __restrict__ rnorm,
                            T* __restrict__ gx, long long M, int C, float act_slope, float* __restrict__ colsum,
                            float cs_scale, int LP) {
+    PG_PDL_ENTER();
     constexpr int VN = V16<T>::N;
     __shared__ float red[8][16 * VN];
     const long long nvec_total = M * LP;
@@ -915,7 +938,7 @@ extern "C" int pggan_lrelu_mask_mul(const void* g, const void* y, void* out, int
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     DISPATCH_T(dtype, {
         const long long nvec = n / V16<T>::N;
-        lrelu_mask_mul_kernel<T><<<ew_grid(nvec + 1, 256), 256, 0, s>>>((const T*)g, (const T*)y, (T*)out, nvec, n, slope);
+        PG_CUDA(pg::launch(lrelu_mask_mul_kernel<T>, ew_grid(nvec + 1, 256), 256, 0, s, (const T*)g, (const T*)y, (T*)out, nvec, n, slope));
     });
     PG_LAUNCH_CHECK();
     g_other_launches++;
@@ -930,7 +953,7 @@ extern "C" int pggan_axpby(const void* a, const void* b, void* out, int64_t n, p
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     DISPATCH_T(dtype, {
         const long long nvec = n / V16<T>::N;
-        axpby_kernel<T><<<ew_grid(nvec + 1, 256), 256, 0, s>>>((const T*)a, (const T*)b, (T*)out, nvec, n, sa, sb);
+        PG_CUDA(pg::launch(axpby_kernel<T>, ew_grid(nvec + 1, 256), 256, 0, s, (const T*)a, (const T*)b, (T*)out, nvec, n, sa, sb));
     });
     PG_LAUNCH_CHECK();
     g_other_launches++;
@@ -945,8 +968,8 @@ static int upsample2x_impl(const void* x, const void* mask_src, void* out, int B
     DISPATCH_T(dtype, {
         PG_CHECK(C % V16<T>::N == 0, PG_ERR_UNSUPPORTED, "%s: C=%d must be a multiple of %d", who, C, V16<T>::N);
         const int CV = C / V16<T>::N;
-        upsample2x_kernel<T><<<ew_grid((long long)B * H * W * CV, 256), 256, 0, s>>>((const T*)x, (const T*)mask_src, (T*)out,
-                                                                                     B, H, W, CV, scale, slope);
+        PG_CUDA(pg::launch(upsample2x_kernel<T>, ew_grid((long long)B * H * W * CV, 256), 256, 0, s, (const T*)x, (const T*)mask_src, (T*)out,
+                                                                                     B, H, W, CV, scale, slope));
     });
     PG_LAUNCH_CHECK();
     g_other_launches++;
@@ -985,8 +1008,8 @@ extern "C" int pggan_upsample2x_mask_colsum(const void* x, const void* mask_src,
             rpb = (m + blocks - 1) / blocks;
         }
         const int grid = (int)((m + rpb - 1) / rpb);
-        upsample2x_mask_colsum_kernel<T><<<grid, 256, 0, s>>>((const T*)x, (const T*)mask_src, (T*)out, colsum, B, H, W, C,
-                                                              scale, slope, cs_scale, TX, rpb);
+        PG_CUDA(pg::launch(upsample2x_mask_colsum_kernel<T>, grid, 256, 0, s, (const T*)x, (const T*)mask_src, (T*)out, colsum, B, H, W, C,
+                                                              scale, slope, cs_scale, TX, rpb));
     });
     PG_LAUNCH_CHECK();
     g_other_launches++;
@@ -1003,8 +1026,8 @@ extern "C" int pggan_pool2x2(const void* x, const void* blend_with, void* out, i
     DISPATCH_T(dtype, {
         PG_CHECK(C % V16<T>::N == 0, PG_ERR_UNSUPPORTED, "pggan_pool2x2: C=%d must be a multiple of %d", C, V16<T>::N);
         const int CV = C / V16<T>::N;
-        pool2x2_kernel<T><<<ew_grid((long long)B * (H / 2) * (W / 2) * CV, 256), 256, 0, s>>>(
-            (const T*)x, (const T*)blend_with, (T*)out, B, H, W, CV, scale, alpha);
+        PG_CUDA(pg::launch(pool2x2_kernel<T>, ew_grid((long long)B * (H / 2) * (W / 2) * CV, 256), 256, 0, s, 
+            (const T*)x, (const T*)blend_with, (T*)out, B, H, W, CV, scale, alpha));
     });
     PG_LAUNCH_CHECK();
     g_other_launches++;
@@ -1023,18 +1046,18 @@ extern "C" int pggan_pixelnorm_fwd(const void* x, void* y, float* rnorm, int64_t
                  "pggan_pixelnorm_fwd: C=%d must be a multiple of %d and <= %d", C, VN, 32 * VN * 4);
         const int lp = C / VN;
         if (lp <= 16 && (lp & (lp - 1)) == 0) {
-            pixelnorm_fwd_small_kernel<T><<<ew_grid(m * lp, 256), 256, 0, s>>>((const T*)x, (T*)y, rnorm, m, C, eps, lp);
+            PG_CUDA(pg::launch(pixelnorm_fwd_small_kernel<T>, ew_grid(m * lp, 256), 256, 0, s, (const T*)x, (T*)y, rnorm, m, C, eps, lp));
             PG_LAUNCH_CHECK();
             g_other_launches++;
             return PG_OK;
         }
         const int grid = ew_grid(m * 32, 256);
         if (C <= 32 * VN)
-            pixelnorm_fwd_kernel<T, 1><<<grid, 256, 0, s>>>((const T*)x, (T*)y, rnorm, m, C, eps);
+            PG_CUDA(pg::launch(pixelnorm_fwd_kernel<T, 1>, grid, 256, 0, s, (const T*)x, (T*)y, rnorm, m, C, eps));
         else if (C <= 64 * VN)
-            pixelnorm_fwd_kernel<T, 2><<<grid, 256, 0, s>>>((const T*)x, (T*)y, rnorm, m, C, eps);
+            PG_CUDA(pg::launch(pixelnorm_fwd_kernel<T, 2>, grid, 256, 0, s, (const T*)x, (T*)y, rnorm, m, C, eps));
         else
-            pixelnorm_fwd_kernel<T, 4><<<grid, 256, 0, s>>>((const T*)x, (T*)y, rnorm, m, C, eps);
+            PG_CUDA(pg::launch(pixelnorm_fwd_kernel<T, 4>, grid, 256, 0, s, (const T*)x, (T*)y, rnorm, m, C, eps));
     });
     PG_LAUNCH_CHECK();
     g_other_launches++;
@@ -1049,16 +1072,16 @@ static int pixelnorm_bwd_launch(const void* gy, const void* y, const float* rnor
              "pggan_pixelnorm_bwd: C=%d must be a multiple of %d and <= %d", C, VN, 32 * VN * 4);
     const int lp = C / VN;
     if (lp <= 16 && (lp & (lp - 1)) == 0) {
-        pixelnorm_bwd_small_kernel<T, TY><<<ew_grid(m * lp / 4 + 1, 256), 256, 0, s>>>(
-            (const T*)gy, (const TY*)y, rnorm, (T*)gx, m, C, act_slope, colsum, cs_scale, lp);
+        PG_CUDA(pg::launch(pixelnorm_bwd_small_kernel<T, TY>, ew_grid(m * lp / 4 + 1, 256), 256, 0, s, 
+            (const T*)gy, (const TY*)y, rnorm, (T*)gx, m, C, act_slope, colsum, cs_scale, lp));
     } else {
         const int grid = ew_grid(m * 32 / 4 + 1, 256);      // ~4 rows per warp
         if (C <= 32 * VN)
-            pixelnorm_bwd_kernel<T, 1, TY><<<grid, 256, 0, s>>>((const T*)gy, (const TY*)y, rnorm, (T*)gx, m, C, act_slope, colsum, cs_scale);
+            PG_CUDA(pg::launch(pixelnorm_bwd_kernel<T, 1, TY>, grid, 256, 0, s, (const T*)gy, (const TY*)y, rnorm, (T*)gx, m, C, act_slope, colsum, cs_scale));
         else if (C <= 64 * VN)
-            pixelnorm_bwd_kernel<T, 2, TY><<<grid, 256, 0, s>>>((const T*)gy, (const TY*)y, rnorm, (T*)gx, m, C, act_slope, colsum, cs_scale);
+            PG_CUDA(pg::launch(pixelnorm_bwd_kernel<T, 2, TY>, grid, 256, 0, s, (const T*)gy, (const TY*)y, rnorm, (T*)gx, m, C, act_slope, colsum, cs_scale));
         else
-            pixelnorm_bwd_kernel<T, 4, TY><<<grid, 256, 0, s>>>((const T*)gy, (const TY*)y, rnorm, (T*)gx, m, C, act_slope, colsum, cs_scale);
+            PG_CUDA(pg::launch(pixelnorm_bwd_kernel<T, 4, TY>, grid, 256, 0, s, (const T*)gy, (const TY*)y, rnorm, (T*)gx, m, C, act_slope, colsum, cs_scale));
     }
     PG_LAUNCH_CHECK();
     g_other_launches++;
@@ -1102,9 +1125,9 @@ extern "C" int pggan_mask_colsum(const void* g, const void* y, void* out, float*
         }
         const int grid = (int)((m + rpb - 1) / rpb);
         if (y == nullptr && out == nullptr)
-            colsum_only_kernel<T><<<grid, 256, 0, s>>>((const T*)g, colsum, m, C, scale, TX, rpb);
+            PG_CUDA(pg::launch(colsum_only_kernel<T>, grid, 256, 0, s, (const T*)g, colsum, m, C, scale, TX, rpb));
         else
-            mask_colsum_kernel<T><<<grid, 256, 0, s>>>((const T*)g, (const T*)y, (T*)out, colsum, m, C, slope, scale, TX, rpb);
+            PG_CUDA(pg::launch(mask_colsum_kernel<T>, grid, 256, 0, s, (const T*)g, (const T*)y, (T*)out, colsum, m, C, slope, scale, TX, rpb));
     });
     PG_LAUNCH_CHECK();
     g_other_launches++;
@@ -1127,7 +1150,7 @@ extern "C" int pggan_colsum(const void* g, float* out, int64_t m, int C, float s
         if (blocks > cap) blocks = cap;
         const long long rows_per_block = (m + blocks - 1) / blocks;
         const int grid = (int)((m + rows_per_block - 1) / rows_per_block);
-        colsum_kernel<T><<<grid, 256, 0, s>>>((const T*)g, out, m, C, scale, TX, rows_per_block);
+        PG_CUDA(pg::launch(colsum_kernel<T>, grid, 256, 0, s, (const T*)g, out, m, C, scale, TX, rows_per_block));
     });
     PG_LAUNCH_CHECK();
     g_other_launches++;
@@ -1187,23 +1210,23 @@ extern "C" int pggan_pack_weight(const float* in, void* out, int dtype, const pg
                         m.s_c1 == (long long)m.taps * m.n_valid && m.base == (long long)(m.taps - 1) * m.n_valid;
     if (ohwi_t) {
         DISPATCH_T(dtype, {
-            pack_ohwi_t_kernel<T><<<dim3((m.n_total + 31) / 32, (m.c_total + 31) / 32, m.taps), 256, 0, s>>>(
-                in, (T*)out, m.c_total, m.n_valid, m.n_total, m.taps);
+            PG_CUDA(pg::launch(pack_ohwi_t_kernel<T>, dim3((m.n_total + 31) / 32, (m.c_total + 31) / 32, m.taps), 256, 0, s, 
+                in, (T*)out, m.c_total, m.n_valid, m.n_total, m.taps));
         });
     } else if (oihw_f) {
         DISPATCH_T(dtype, {
-            pack_oihw_f_kernel<T><<<m.n_total, 256, 9 * m.c_valid * sizeof(float), s>>>(in, (T*)out, m.c_valid, m.c_total);
+            PG_CUDA(pg::launch(pack_oihw_f_kernel<T>, m.n_total, 256, 9 * m.c_valid * sizeof(float), s, in, (T*)out, m.c_valid, m.c_total));
         });
     } else if (oihw_t) {
         DISPATCH_T(dtype, {
-            pack_oihw_t_kernel<T><<<dim3((m.n_total + 7) / 8, m.c_total / 64), 256, 0, s>>>(in, (T*)out, m.c_total, m.n_valid,
-                                                                                          m.n_total);
+            PG_CUDA(pg::launch(pack_oihw_t_kernel<T>, dim3((m.n_total + 7) / 8, m.c_total / 64), 256, 0, s, in, (T*)out, m.c_total, m.n_valid,
+                                                                                          m.n_total));
         });
     } else if (RowSpan rs; rowspan_ok(m, rs) && m.n_total >= 64) {
         const size_t smem = sizeof(float) * (size_t)(rs.span + (rs.span >> 5) + 1);
-        DISPATCH_T(dtype, { pack_rowspan_kernel<T><<<m.n_total, 256, smem, s>>>(in, (T*)out, m, rs); });
+        DISPATCH_T(dtype, { PG_CUDA(pg::launch(pack_rowspan_kernel<T>, m.n_total, 256, smem, s, in, (T*)out, m, rs)); });
     } else {
-        DISPATCH_T(dtype, { pack_weight_kernel<T><<<ew_grid(total, 256), 256, 0, s>>>(in, (T*)out, m, total); });
+        DISPATCH_T(dtype, { PG_CUDA(pg::launch(pack_weight_kernel<T>, ew_grid(total, 256), 256, 0, s, in, (T*)out, m, total)); });
     }
     PG_LAUNCH_CHECK();
     g_other_launches++;
@@ -1226,8 +1249,8 @@ extern "C" int pggan_unpack_wgrad(const float* in, float* out, const pg_pack_map
                        m.s_n1 == (long long)m.taps * m.c_total && m.n_valid == m.n_total && m.c_valid == m.c_total &&
                        slice_elems % 4 == 0 && al16(in) && al16(out);
     if (dense) {
-        unpack_dense_kernel<<<ew_grid(slice_elems / 4, 256), 256, 0, s>>>(in, out, slice_elems / 4, scale, accumulate, slices,
-                                                                          slice_elems);
+        PG_CUDA(pg::launch(unpack_dense_kernel, ew_grid(slice_elems / 4, 256), 256, 0, s, in, out, slice_elems / 4, scale, accumulate, slices,
+                                                                          slice_elems));
     } else if (oihw_f) {
         int zchunks = 1;                 // channel chunks of >= 128 (a multiple of 4 keeps the float4 path)
         while (zchunks < 4 && m.c_valid / (zchunks * 2) >= 128 && m.c_valid % (zchunks * 2 * 4) == 0) zchunks *= 2;
@@ -1243,13 +1266,13 @@ extern "C" int pggan_unpack_wgrad(const float* in, float* out, const pg_pack_map
             if (groups > 1 && !accumulate)
                 PG_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)m.n_total * 9 * m.c_valid, s));
         }
-        unpack_oihw_kernel<<<dim3(m.n_total, groups, zchunks), 256, 9 * m.c_valid * sizeof(float), s>>>(
-            in, out, m.c_valid, m.c_total, scale, accumulate, slices, slice_elems, spb);
+        PG_CUDA(pg::launch(unpack_oihw_kernel, dim3(m.n_total, groups, zchunks), 256, 9 * m.c_valid * sizeof(float), s, 
+            in, out, m.c_valid, m.c_total, scale, accumulate, slices, slice_elems, spb));
     } else if (RowSpan rs; rowspan_ok(m, rs) && m.n_valid >= 64) {
         const size_t smem = sizeof(float) * (size_t)(rs.span + (rs.span >> 5) + 1);
-        unpack_rowspan_kernel<<<m.n_valid, 256, smem, s>>>(in, out, m, rs, scale, accumulate, slices, slice_elems);
+        PG_CUDA(pg::launch(unpack_rowspan_kernel, m.n_valid, 256, smem, s, in, out, m, rs, scale, accumulate, slices, slice_elems));
     } else
-        unpack_wgrad_kernel<<<ew_grid(total, 256), 256, 0, s>>>(in, out, m, total, scale, accumulate, slices, slice_elems);
+        PG_CUDA(pg::launch(unpack_wgrad_kernel, ew_grid(total, 256), 256, 0, s, in, out, m, total, scale, accumulate, slices, slice_elems));
     PG_LAUNCH_CHECK();
     g_other_launches++;
     return PG_OK;
@@ -1263,7 +1286,7 @@ extern "C" int pggan_convert(const void* in, void* out, int64_t n, int from_dtyp
     const int grid = ew_grid(n / 8 + 1, 256);
 #define PG_CVT(FI, TI, FO, TO)                                                                             \
     if (from_dtype == FI && to_dtype == FO) {                                                              \
-        convert_kernel<TI, TO><<<grid, 256, 0, s>>>((const TI*)in, (TO*)out, n);                           \
+        PG_CUDA(pg::launch(convert_kernel<TI, TO>, grid, 256, 0, s, (const TI*)in, (TO*)out, n));                           \
         PG_LAUNCH_CHECK();                                                                                 \
         g_other_launches++;                                                                                \
         return PG_OK;                                                                                      \
@@ -1284,7 +1307,7 @@ int split3_launch(const float* in, float* out, long long m, int c, int along_cha
     PG_CHECK(in && out && m > 0 && c > 0 && c % 4 == 0 && lo_slot >= 0 && lo_slot < 3, PG_ERR_ARG,
              "pggan_split3: bad args (c=%d must be a multiple of 4)", c);
     PG_CHECK(al16(in) && al16(out), PG_ERR_ARG, "pggan_split3: pointers must be 16-byte aligned");
-    split3_kernel<<<ew_grid(m * (c / 4), 256), 256, 0, s>>>(in, out, m, c / 4, along_channels, lo_slot);
+    PG_CUDA(pg::launch(split3_kernel, ew_grid(m * (c / 4), 256), 256, 0, s, in, out, m, c / 4, along_channels, lo_slot));
     PG_LAUNCH_CHECK();
     g_other_launches++;
     return PG_OK;

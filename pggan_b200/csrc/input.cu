@@ -45,6 +45,7 @@ __device__ __forceinline__ AaSpan aa_span(int i, int in_size, float scale) {
 template <typename TI>
 __global__ void resize_axis_kernel(const TI* __restrict__ in, float* __restrict__ out, long long planes, int in_size,
                                    int out_size, long long inner, float scale, float in_mul) {
+    PG_PDL_ENTER();
     const long long total = planes * out_size * inner;
     for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -134,6 +135,7 @@ __device__ __forceinline__ void apply_jitter(float& r, float& g, float& b, const
 // mean grey level of every image at the moment its contrast op runs
 __global__ void jitter_stats_kernel(const float* __restrict__ img, const int* __restrict__ ip, const float* __restrict__ fp,
                                     float* __restrict__ mean, int HW) {
+    PG_PDL_ENTER();
     __shared__ float red[32];
     const int b = blockIdx.y;
     const Jit j = load_jit(ip, fp, b);
@@ -152,6 +154,7 @@ __global__ void jitter_stats_kernel(const float* __restrict__ img, const int* __
 __global__ void jitter_apply_kernel(const float* __restrict__ img, const int* __restrict__ ip, const float* __restrict__ fp,
                                     const float* __restrict__ mean, float* __restrict__ out, int B, int S, int fade,
                                     pg_coef calpha) {
+    PG_PDL_ENTER();
     const float alpha = coef_val(calpha);
     const int Sh = S / 2, HW = S * S;
     const long long total = static_cast<long long>(B) * Sh * Sh;
@@ -209,14 +212,14 @@ extern "C" int pggan_resize_aa(const void* src, int src_is_u8, float* tmp, float
     const float sw = static_cast<float>(Ws) / Wo, sh = static_cast<float>(Hs) / Ho;
     const long long rows = static_cast<long long>(planes) * Hs;
     if (src_is_u8)
-        resize_axis_kernel<uint8_t><<<grid_of(rows * Wo, 256, 8), 256, 0, s>>>(reinterpret_cast<const uint8_t*>(src), tmp, rows,
-                                                                               Ws, Wo, 1, sw, in_mul);
+        PG_CUDA(pg::launch(resize_axis_kernel<uint8_t>, grid_of(rows * Wo, 256, 8), 256, 0, s, reinterpret_cast<const uint8_t*>(src), tmp, rows,
+                                                                               Ws, Wo, 1, sw, in_mul));
     else
-        resize_axis_kernel<float><<<grid_of(rows * Wo, 256, 8), 256, 0, s>>>(reinterpret_cast<const float*>(src), tmp, rows, Ws,
-                                                                             Wo, 1, sw, in_mul);
+        PG_CUDA(pg::launch(resize_axis_kernel<float>, grid_of(rows * Wo, 256, 8), 256, 0, s, reinterpret_cast<const float*>(src), tmp, rows, Ws,
+                                                                             Wo, 1, sw, in_mul));
     PG_LAUNCH_CHECK();
-    resize_axis_kernel<float><<<grid_of(static_cast<long long>(planes) * Ho * Wo, 256, 8), 256, 0, s>>>(tmp, dst, planes, Hs, Ho,
-                                                                                                       Wo, sh, 1.f);
+    PG_CUDA(pg::launch(resize_axis_kernel<float>, grid_of(static_cast<long long>(planes) * Ho * Wo, 256, 8), 256, 0, s, tmp, dst, planes, Hs, Ho,
+                                                                                                       Wo, sh, 1.f));
     PG_LAUNCH_CHECK();
     g_other_launches += 2;
     return PG_OK;
@@ -231,11 +234,11 @@ extern "C" int pggan_jitter_normalize_fade(const float* img, const int32_t* ipar
     const int HW = S * S;
     int bx = (HW + 255) / 256;
     if (bx > 64) bx = 64;
-    jitter_stats_kernel<<<dim3(bx, B), 256, 0, s>>>(img, iparams, fparams, mean_ws, HW);
+    PG_CUDA(pg::launch(jitter_stats_kernel, dim3(bx, B), 256, 0, s, img, iparams, fparams, mean_ws, HW));
     PG_LAUNCH_CHECK();
-    jitter_apply_kernel<<<grid_of(static_cast<long long>(B) * (S / 2) * (S / 2), 256, 8), 256, 0, s>>>(img, iparams, fparams,
+    PG_CUDA(pg::launch(jitter_apply_kernel, grid_of(static_cast<long long>(B) * (S / 2) * (S / 2), 256, 8), 256, 0, s, img, iparams, fparams,
                                                                                                        mean_ws, out, B, S, fade,
-                                                                                                       alpha);
+                                                                                                       alpha));
     PG_LAUNCH_CHECK();
     g_other_launches += 2;
     return PG_OK;

@@ -56,6 +56,7 @@ __device__ __forceinline__ void group_moments(const T* __restrict__ xg, long lon
 
 template <typename T>
 __global__ void mbstd_fwd_kernel(const T* __restrict__ x, float* __restrict__ stat, long long K, int n) {
+    PG_PDL_ENTER();
     constexpr int VN = MV<T>::N;
     __shared__ float red[32];
     const int grp = blockIdx.y;
@@ -77,6 +78,7 @@ __global__ void mbstd_fwd_kernel(const T* __restrict__ x, float* __restrict__ st
 template <typename T, typename TG = T>
 __global__ void mbstd_bwd_kernel(const T* __restrict__ x, const float* __restrict__ gs, TG* __restrict__ gx, long long K,
                                  int n) {
+    PG_PDL_ENTER();
     constexpr int VN = MV<T>::N;
     const int grp = blockIdx.y;
     const T* xg = x + static_cast<long long>(grp) * n * K;
@@ -102,6 +104,7 @@ __global__ void mbstd_bwd_kernel(const T* __restrict__ x, const float* __restric
 template <typename T, typename TG = T>
 __global__ void mbstd_bwd2_kernel(const T* __restrict__ x, const TG* __restrict__ u, const float* __restrict__ gs,
                                   float* __restrict__ ggs, TG* __restrict__ gx2, long long K, int n) {
+    PG_PDL_ENTER();
     constexpr int VN = MV<T>::N;
     __shared__ float red[32];
     const int grp = blockIdx.y;
@@ -174,11 +177,11 @@ extern "C" int pggan_mbstd_fwd(const void* x, float* stat, int B, int64_t K, int
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     PG_CUDA(cudaMemsetAsync(stat, 0, sizeof(float) * (B / group), s));
     if (dtype == PG_BF16)
-        mbstd_fwd_kernel<__nv_bfloat16><<<mb_grid(K, 8, B / group), 256, 0, s>>>((const __nv_bfloat16*)x, stat, K, group);
+        PG_CUDA(pg::launch(mbstd_fwd_kernel<__nv_bfloat16>, mb_grid(K, 8, B / group), 256, 0, s, (const __nv_bfloat16*)x, stat, K, group));
     else if (dtype == PG_F16)
-        mbstd_fwd_kernel<__half><<<mb_grid(K, 8, B / group), 256, 0, s>>>((const __half*)x, stat, K, group);
+        PG_CUDA(pg::launch(mbstd_fwd_kernel<__half>, mb_grid(K, 8, B / group), 256, 0, s, (const __half*)x, stat, K, group));
     else
-        mbstd_fwd_kernel<float><<<mb_grid(K, 4, B / group), 256, 0, s>>>((const float*)x, stat, K, group);
+        PG_CUDA(pg::launch(mbstd_fwd_kernel<float>, mb_grid(K, 4, B / group), 256, 0, s, (const float*)x, stat, K, group));
     PG_LAUNCH_CHECK();
     g_other_launches++;
     return PG_OK;
@@ -193,15 +196,15 @@ extern "C" int pggan_mbstd_bwd(const void* x, const float* gs, void* gx, int B, 
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const dim3 grid = mb_grid(K, is16(dtype) ? 8 : 4, B / group);
     if (dtype == PG_BF16 && g_dtype == PG_BF16)
-        mbstd_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, gs, (__nv_bfloat16*)gx, K, group);
+        PG_CUDA(pg::launch(mbstd_bwd_kernel<__nv_bfloat16>, grid, 256, 0, s, (const __nv_bfloat16*)x, gs, (__nv_bfloat16*)gx, K, group));
     else if (dtype == PG_F16 && g_dtype == PG_F16)
-        mbstd_bwd_kernel<__half><<<grid, 256, 0, s>>>((const __half*)x, gs, (__half*)gx, K, group);
+        PG_CUDA(pg::launch(mbstd_bwd_kernel<__half>, grid, 256, 0, s, (const __half*)x, gs, (__half*)gx, K, group));
     else if (dtype == PG_F16)
-        mbstd_bwd_kernel<__half, __nv_bfloat16><<<grid, 256, 0, s>>>((const __half*)x, gs, (__nv_bfloat16*)gx, K, group);
+        PG_CUDA(pg::launch(mbstd_bwd_kernel<__half, __nv_bfloat16>, grid, 256, 0, s, (const __half*)x, gs, (__nv_bfloat16*)gx, K, group));
     else if (dtype == PG_BF16)
-        mbstd_bwd_kernel<__nv_bfloat16, __half><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, gs, (__half*)gx, K, group);
+        PG_CUDA(pg::launch(mbstd_bwd_kernel<__nv_bfloat16, __half>, grid, 256, 0, s, (const __nv_bfloat16*)x, gs, (__half*)gx, K, group));
     else
-        mbstd_bwd_kernel<float><<<grid, 256, 0, s>>>((const float*)x, gs, (float*)gx, K, group);
+        PG_CUDA(pg::launch(mbstd_bwd_kernel<float>, grid, 256, 0, s, (const float*)x, gs, (float*)gx, K, group));
     PG_LAUNCH_CHECK();
     g_other_launches++;
     return PG_OK;
@@ -217,18 +220,18 @@ extern "C" int pggan_mbstd_bwd2(const void* x, const void* u, const float* gs, f
     PG_CUDA(cudaMemsetAsync(ggs, 0, sizeof(float) * (B / group), s));
     const dim3 grid = mb_grid(K, is16(dtype) ? 8 : 4, B / group);
     if (dtype == PG_BF16 && g_dtype == PG_BF16)
-        mbstd_bwd2_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)u, gs, ggs,
-                                                             (__nv_bfloat16*)gx2, K, group);
+        PG_CUDA(pg::launch(mbstd_bwd2_kernel<__nv_bfloat16>, grid, 256, 0, s, (const __nv_bfloat16*)x, (const __nv_bfloat16*)u, gs, ggs,
+                                                             (__nv_bfloat16*)gx2, K, group));
     else if (dtype == PG_F16 && g_dtype == PG_F16)
-        mbstd_bwd2_kernel<__half><<<grid, 256, 0, s>>>((const __half*)x, (const __half*)u, gs, ggs, (__half*)gx2, K, group);
+        PG_CUDA(pg::launch(mbstd_bwd2_kernel<__half>, grid, 256, 0, s, (const __half*)x, (const __half*)u, gs, ggs, (__half*)gx2, K, group));
     else if (dtype == PG_F16)
-        mbstd_bwd2_kernel<__half, __nv_bfloat16><<<grid, 256, 0, s>>>((const __half*)x, (const __nv_bfloat16*)u, gs, ggs,
-                                                                     (__nv_bfloat16*)gx2, K, group);
+        PG_CUDA(pg::launch(mbstd_bwd2_kernel<__half, __nv_bfloat16>, grid, 256, 0, s, (const __half*)x, (const __nv_bfloat16*)u, gs, ggs,
+                                                                     (__nv_bfloat16*)gx2, K, group));
     else if (dtype == PG_BF16)
-        mbstd_bwd2_kernel<__nv_bfloat16, __half><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, (const __half*)u, gs, ggs,
-                                                                     (__half*)gx2, K, group);
+        PG_CUDA(pg::launch(mbstd_bwd2_kernel<__nv_bfloat16, __half>, grid, 256, 0, s, (const __nv_bfloat16*)x, (const __half*)u, gs, ggs,
+                                                                     (__half*)gx2, K, group));
     else
-        mbstd_bwd2_kernel<float><<<grid, 256, 0, s>>>((const float*)x, (const float*)u, gs, ggs, (float*)gx2, K, group);
+        PG_CUDA(pg::launch(mbstd_bwd2_kernel<float>, grid, 256, 0, s, (const float*)x, (const float*)u, gs, ggs, (float*)gx2, K, group));
     PG_LAUNCH_CHECK();
     g_other_launches++;
     return PG_OK;

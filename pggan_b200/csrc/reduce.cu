@@ -10,6 +10,7 @@ extern std::atomic<long long> g_other_launches;
 
 __global__ void rows_sumsq_kernel(const float* __restrict__ g, float* __restrict__ sumsq, long long n,
                                   long long per_block) {
+    PG_PDL_ENTER();
     __shared__ float red[32];
     const int b = blockIdx.y;
     const float* row = g + static_cast<long long>(b) * n;
@@ -34,6 +35,7 @@ __global__ void rows_sumsq_kernel(const float* __restrict__ g, float* __restrict
 
 __global__ void rows_scale_kernel(const float* __restrict__ g, const float* __restrict__ coef, float* __restrict__ out,
                                   long long n, long long total) {
+    PG_PDL_ENTER();
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x)
         out[i] = g[i] * __ldg(coef + i / n);
@@ -41,6 +43,7 @@ __global__ void rows_scale_kernel(const float* __restrict__ g, const float* __re
 
 __global__ void gp_finalize_kernel(const float* __restrict__ sumsq, const float* __restrict__ pred,
                                    float* __restrict__ res, float* __restrict__ coef, int B, float w_gp, float w_drift) {
+    PG_PDL_ENTER();
     __shared__ float red[32];
     float gp = 0.f, dr = 0.f;
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
@@ -63,6 +66,7 @@ constexpr int kAdamChunk = 16384;    // elements per block
 __global__ void adam_kernel(const pg_adam_entry* __restrict__ table, const int32_t* __restrict__ chunk_tensor,
                             const int64_t* __restrict__ chunk_offset, const int64_t* __restrict__ step, float lr,
                             float beta1, float beta2, float eps, float grad_scale) {
+    PG_PDL_ENTER();
     __shared__ float s_c[2];
     if (threadIdx.x == 0) {
         const double t = static_cast<double>(*step + 1);
@@ -117,7 +121,8 @@ __global__ void adam_kernel(const pg_adam_entry* __restrict__ table, const int32
         if (sh != nullptr) sh[i] = cvt16(p, sh_f16);
     }
 }
-__global__ void adam_incr_step_kernel(int64_t* step) { *step += 1; }
+__global__ void adam_incr_step_kernel(int64_t* step) {
+    PG_PDL_ENTER(); *step += 1; }
 
 }  // namespace pg
 
@@ -133,7 +138,7 @@ extern "C" int pggan_rows_sumsq(const float* g, float* sumsq, int B, int64_t n, 
     long long per_block = (n + bx - 1) / bx;
     per_block = (per_block + 3) & ~3LL;
     bx = (n + per_block - 1) / per_block;
-    rows_sumsq_kernel<<<dim3((unsigned)bx, (unsigned)B), 256, 0, s>>>(g, sumsq, n, per_block);
+    PG_CUDA(pg::launch(rows_sumsq_kernel, dim3((unsigned)bx, (unsigned)B), 256, 0, s, g, sumsq, n, per_block));
     PG_LAUNCH_CHECK();
     g_other_launches++;
     return PG_OK;
@@ -146,7 +151,7 @@ extern "C" int pggan_rows_scale(const float* g, const float* coef, float* out, i
     long long blocks = (total + 255) / 256;
     const long long cap = (long long)num_sms() * 16;
     if (blocks > cap) blocks = cap;
-    rows_scale_kernel<<<(int)blocks, 256, 0, s>>>(g, coef, out, n, total);
+    PG_CUDA(pg::launch(rows_scale_kernel, (int)blocks, 256, 0, s, g, coef, out, n, total));
     PG_LAUNCH_CHECK();
     g_other_launches++;
     return PG_OK;
@@ -156,7 +161,7 @@ extern "C" int pggan_gp_finalize(const float* sumsq, const float* pred, float* r
                                  float w_drift, void* stream) {
     PG_CHECK(sumsq && res && B > 0, PG_ERR_ARG, "pggan_gp_finalize: bad args");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    gp_finalize_kernel<<<1, 256, 0, s>>>(sumsq, pred, res, coef, B, w_gp, w_drift);
+    PG_CUDA(pg::launch(gp_finalize_kernel, 1, 256, 0, s, sumsq, pred, res, coef, B, w_gp, w_drift));
     PG_LAUNCH_CHECK();
     g_other_launches++;
     return PG_OK;
@@ -170,10 +175,10 @@ extern "C" int pggan_adam_step(const pg_adam_entry* table, int n_tensors, int64_
     PG_CHECK(table && chunk_tensor && chunk_offset && step && n_tensors > 0 && total_chunks > 0, PG_ERR_ARG,
              "pggan_adam_step: bad args");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    adam_kernel<<<(unsigned)total_chunks, 256, 0, s>>>(table, chunk_tensor, chunk_offset, step, lr, beta1, beta2, eps,
-                                                       grad_scale);
+    PG_CUDA(pg::launch(adam_kernel, (unsigned)total_chunks, 256, 0, s, table, chunk_tensor, chunk_offset, step, lr, beta1, beta2, eps,
+                                                       grad_scale));
     PG_LAUNCH_CHECK();
-    adam_incr_step_kernel<<<1, 1, 0, s>>>(step);
+    PG_CUDA(pg::launch(adam_incr_step_kernel, 1, 1, 0, s, step));
     PG_LAUNCH_CHECK();
     g_other_launches += 2;
     return PG_OK;

@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(256)
 rgb_expand_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias,
                   T* __restrict__ out, int B, int H, int W, int C, int cimg, int pool, float scale, float slope,
                   int TX) {
+    PG_PDL_ENTER();
     constexpr int VN = RV<T>::N;
     const int tx = threadIdx.x % TX, ty = threadIdx.x / TX, TY = blockDim.x / TX;
     float wr[VN][kMaxImgC], br[VN];
@@ -106,6 +107,7 @@ template <typename T, int CV>
 __global__ void __launch_bounds__(256)
 rgb_expand_pixel_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias,
                         T* __restrict__ out, int B, int H, int W, int cimg, int pool, float scale, float slope) {
+    PG_PDL_ENTER();
     constexpr int VN = RV<T>::N;
     constexpr int C = CV * VN;
     __shared__ float4 ws[C];
@@ -143,6 +145,7 @@ __global__ void __launch_bounds__(256)
 rgb_reduce_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                   float* __restrict__ out, int B, int H, int W, int C, int cimg, int up, float scale, float up_scale,
                   int LP) {
+    PG_PDL_ENTER();
     constexpr int VN = RV<T>::N;
     constexpr int UNR = 4;
     const int lane = threadIdx.x & 31;
@@ -224,6 +227,7 @@ template <typename T, int CV>
 __global__ void __launch_bounds__(256)
 rgb_reduce_pixel_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                         float* __restrict__ out, int B, int H, int W, int cimg, int up, float scale, float up_scale) {
+    PG_PDL_ENTER();
     constexpr int VN = RV<T>::N;
     constexpr int C = CV * VN;
     __shared__ float4 ws[C];                // per channel: the (up to) three image-channel weights, one LDS.128
@@ -274,6 +278,7 @@ __global__ void __launch_bounds__(256)
 rgb_wgrad_kernel(const T* __restrict__ f, const float* __restrict__ img, float* __restrict__ acc,
                  float* __restrict__ bsum, int B, int H, int W, int C, int cimg, int pool, float scale, int TX,
                  long long pix_per_block) {
+    PG_PDL_ENTER();
     constexpr int VN = RV<T>::N;
     constexpr int NA = kMaxImgC + 1;
     extern __shared__ float red[];         // [blockDim][VN*NA]
@@ -329,6 +334,7 @@ template <typename T, int CV>
 __global__ void __launch_bounds__(256)
 rgb_wgrad_pixel_kernel(const T* __restrict__ f, const float* __restrict__ img, float* __restrict__ acc,
                        float* __restrict__ bsum, int B, int H, int W, int cimg, int pool, float scale) {
+    PG_PDL_ENTER();
     constexpr int VN = RV<T>::N;
     constexpr int C = CV * VN;
     __shared__ float red[8][C * 4];
@@ -407,6 +413,7 @@ template <typename T, bool POOL>
 __global__ void __launch_bounds__(256)
 rgb_expand_tile_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias,
                        T* __restrict__ out, int B, int H, int W, int C, int cimg, float scale, float slope, int TX) {
+    PG_PDL_ENTER();
     constexpr int VN = RV<T>::N;
     __shared__ float4 spix[kTilePix];
     const int tx = threadIdx.x % TX, ty = threadIdx.x / TX, TY = kTilePix / TX;
@@ -454,6 +461,7 @@ __global__ void __launch_bounds__(256)
 rgb_reduce_tile_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                        float* __restrict__ out, int B, int H, int W, int C, int cimg, int up, float scale,
                        float up_scale, int LX) {
+    PG_PDL_ENTER();
     constexpr int VN = RV<T>::N;
     __shared__ float sout[3][kTilePix];
     const int tx = threadIdx.x % LX, ty = threadIdx.x / LX, TY = kTilePix / LX;
@@ -530,6 +538,7 @@ template <typename T, bool POOL>
 __global__ void __launch_bounds__(256, 4)
 rgb_wgrad_tile_kernel(const T* __restrict__ f, const float* __restrict__ img, float* __restrict__ acc,
                       float* __restrict__ bsum, int B, int H, int W, int C, int cimg, float scale, int TX) {
+    PG_PDL_ENTER();
     constexpr int VN = RV<T>::N;
     __shared__ float4 spix[kTilePix];
     __shared__ float red[kTilePix][4 * VN + 1];
@@ -587,6 +596,7 @@ rgb_wgrad_tile_kernel(const T* __restrict__ f, const float* __restrict__ img, fl
 
 __global__ void image_fade_kernel(const float* __restrict__ x, const float* __restrict__ low, float* __restrict__ out,
                                   long long planes, int H, int W, pg_coef calpha) {
+    PG_PDL_ENTER();
     // one thread per 2x2 output block
     const float alpha = coef_val(calpha);
     const int Hh = H / 2, Wh = W / 2;
@@ -613,6 +623,7 @@ __global__ void image_fade_kernel(const float* __restrict__ x, const float* __re
 
 __global__ void image_pool_sum_kernel(const float* __restrict__ x, float* __restrict__ out, long long planes, int H,
                                       int W, pg_coef cscale) {
+    PG_PDL_ENTER();
     const float scale = coef_val(cscale);
     const int Hh = H / 2, Wh = W / 2;
     const long long total = planes * Hh * Wh;
@@ -677,18 +688,18 @@ extern "C" int pggan_rgb_expand(const float* img, const float* w, const float* b
     if (!rgb_old && cimg <= 3) {
         // tile kernel: image values of 256 pixels staged once in smem, fixed channel vector per thread
         const long long tiles = (P + kTilePix - 1) / kTilePix;
-        auto launch_t = [&](auto tag) {
+        auto launch_t = [&](auto tag) -> int {
             using TT = decltype(tag);
             if (pool)
-                rgb_expand_tile_kernel<TT, true><<<resident_grid(rgb_expand_tile_kernel<TT, true>, tiles), 256, 0, s>>>(
-                    img, w, bias, (TT*)out, B, H, W, C, cimg, scale, slope, TX);
+                PG_CUDA(pg::launch(rgb_expand_tile_kernel<TT, true>, resident_grid(rgb_expand_tile_kernel<TT, true>, tiles), 256, 0, s, 
+                    img, w, bias, (TT*)out, B, H, W, C, cimg, scale, slope, TX));
             else
-                rgb_expand_tile_kernel<TT, false><<<resident_grid(rgb_expand_tile_kernel<TT, false>, tiles), 256, 0, s>>>(
-                    img, w, bias, (TT*)out, B, H, W, C, cimg, scale, slope, TX);
+                PG_CUDA(pg::launch(rgb_expand_tile_kernel<TT, false>, resident_grid(rgb_expand_tile_kernel<TT, false>, tiles), 256, 0, s, 
+                    img, w, bias, (TT*)out, B, H, W, C, cimg, scale, slope, TX));
+            return PG_OK;
         };
-        if (dtype == PG_BF16) launch_t(__nv_bfloat16());
-        else if (dtype == PG_F16) launch_t(__half());
-        else launch_t(float());
+        const int lrc = dtype == PG_BF16 ? launch_t(__nv_bfloat16()) : (dtype == PG_F16 ? launch_t(__half()) : launch_t(float()));
+        if (lrc != PG_OK) return lrc;
         PG_LAUNCH_CHECK();
         g_other_launches++;
         return PG_OK;
@@ -696,19 +707,19 @@ extern "C" int pggan_rgb_expand(const float* img, const float* w, const float* b
     const int CVn = C / vn;
     const int g2 = grid_for(P, 256, 8);
     const int grid = grid_for((P + TY - 1) / TY * 256 / 8 + 1, 256, 4);     // >= 8 pixels per thread
-    auto launch = [&](auto tag) {
+    auto launch = [&](auto tag) -> int {
         using TT = decltype(tag);
         // thread-per-pixel for C <= 32 (measured: at C = 64 the vector-lane kernel is faster, 67 vs 98 us)
         if (cimg <= 3 && CVn == 2)
-            rgb_expand_pixel_kernel<TT, 2><<<g2, 256, 0, s>>>(img, w, bias, (TT*)out, B, H, W, cimg, pool, scale, slope);
+            PG_CUDA(pg::launch(rgb_expand_pixel_kernel<TT, 2>, g2, 256, 0, s, img, w, bias, (TT*)out, B, H, W, cimg, pool, scale, slope));
         else if (cimg <= 3 && CVn == 4)
-            rgb_expand_pixel_kernel<TT, 4><<<g2, 256, 0, s>>>(img, w, bias, (TT*)out, B, H, W, cimg, pool, scale, slope);
+            PG_CUDA(pg::launch(rgb_expand_pixel_kernel<TT, 4>, g2, 256, 0, s, img, w, bias, (TT*)out, B, H, W, cimg, pool, scale, slope));
         else
-            rgb_expand_kernel<TT><<<grid, 256, 0, s>>>(img, w, bias, (TT*)out, B, H, W, C, cimg, pool, scale, slope, TX);
+            PG_CUDA(pg::launch(rgb_expand_kernel<TT>, grid, 256, 0, s, img, w, bias, (TT*)out, B, H, W, C, cimg, pool, scale, slope, TX));
+        return PG_OK;
     };
-    if (dtype == PG_BF16) launch(__nv_bfloat16());
-    else if (dtype == PG_F16) launch(__half());
-    else launch(float());
+    const int lrc2 = dtype == PG_BF16 ? launch(__nv_bfloat16()) : (dtype == PG_F16 ? launch(__half()) : launch(float()));
+    if (lrc2 != PG_OK) return lrc2;
     PG_LAUNCH_CHECK();
     g_other_launches++;
     return PG_OK;
@@ -727,14 +738,14 @@ static int rgb_reduce_launch(const void* x, const float* w, const float* bias, f
         const long long tiles = (Pn + kTilePix - 1) / kTilePix;
         const T* xq = reinterpret_cast<const T*>(x);
         if (nv == 1)
-            rgb_reduce_tile_kernel<T, 1><<<resident_grid(rgb_reduce_tile_kernel<T, 1>, tiles), 256, 0, s>>>(
-                xq, w, bias, out, B, H, W, C, cimg, up, scale, up_scale, LX);
+            PG_CUDA(pg::launch(rgb_reduce_tile_kernel<T, 1>, resident_grid(rgb_reduce_tile_kernel<T, 1>, tiles), 256, 0, s, 
+                xq, w, bias, out, B, H, W, C, cimg, up, scale, up_scale, LX));
         else if (nv == 2)
-            rgb_reduce_tile_kernel<T, 2><<<resident_grid(rgb_reduce_tile_kernel<T, 2>, tiles), 256, 0, s>>>(
-                xq, w, bias, out, B, H, W, C, cimg, up, scale, up_scale, LX);
+            PG_CUDA(pg::launch(rgb_reduce_tile_kernel<T, 2>, resident_grid(rgb_reduce_tile_kernel<T, 2>, tiles), 256, 0, s, 
+                xq, w, bias, out, B, H, W, C, cimg, up, scale, up_scale, LX));
         else
-            rgb_reduce_tile_kernel<T, 4><<<resident_grid(rgb_reduce_tile_kernel<T, 4>, tiles), 256, 0, s>>>(
-                xq, w, bias, out, B, H, W, C, cimg, up, scale, up_scale, LX);
+            PG_CUDA(pg::launch(rgb_reduce_tile_kernel<T, 4>, resident_grid(rgb_reduce_tile_kernel<T, 4>, tiles), 256, 0, s, 
+                xq, w, bias, out, B, H, W, C, cimg, up, scale, up_scale, LX));
         PG_LAUNCH_CHECK();
         g_other_launches++;
         return PG_OK;
@@ -743,9 +754,9 @@ static int rgb_reduce_launch(const void* x, const float* w, const float* bias, f
         const T* xq = reinterpret_cast<const T*>(x);
         const int P = B * H * W;
         const int grid = grid_for(P, 256, 8);
-        if (CV == 2) rgb_reduce_pixel_kernel<T, 2><<<grid, 256, 0, s>>>(xq, w, bias, out, B, H, W, cimg, up, scale, up_scale);
-        else if (CV == 4) rgb_reduce_pixel_kernel<T, 4><<<grid, 256, 0, s>>>(xq, w, bias, out, B, H, W, cimg, up, scale, up_scale);
-        else rgb_reduce_pixel_kernel<T, 8><<<grid, 256, 0, s>>>(xq, w, bias, out, B, H, W, cimg, up, scale, up_scale);
+        if (CV == 2) PG_CUDA(pg::launch(rgb_reduce_pixel_kernel<T, 2>, grid, 256, 0, s, xq, w, bias, out, B, H, W, cimg, up, scale, up_scale));
+        else if (CV == 4) PG_CUDA(pg::launch(rgb_reduce_pixel_kernel<T, 4>, grid, 256, 0, s, xq, w, bias, out, B, H, W, cimg, up, scale, up_scale));
+        else PG_CUDA(pg::launch(rgb_reduce_pixel_kernel<T, 8>, grid, 256, 0, s, xq, w, bias, out, B, H, W, cimg, up, scale, up_scale));
         PG_LAUNCH_CHECK();
         g_other_launches++;
         return PG_OK;
@@ -759,9 +770,9 @@ static int rgb_reduce_launch(const void* x, const float* w, const float* bias, f
     const int grid = grid_for(warps * 32 / 8 + 1, 256, nv >= 2 ? 1 : 2);   // >= 8 iterations per warp; register-heavy
     const T* xp = reinterpret_cast<const T*>(x);
     switch (nv) {
-        case 1: rgb_reduce_kernel<T, 1><<<grid, 256, 0, s>>>(xp, w, bias, out, B, H, W, C, cimg, up, scale, up_scale, LP); break;
-        case 2: rgb_reduce_kernel<T, 2><<<grid, 256, 0, s>>>(xp, w, bias, out, B, H, W, C, cimg, up, scale, up_scale, LP); break;
-        default: rgb_reduce_kernel<T, 4><<<grid, 256, 0, s>>>(xp, w, bias, out, B, H, W, C, cimg, up, scale, up_scale, LP); break;
+        case 1: PG_CUDA(pg::launch(rgb_reduce_kernel<T, 1>, grid, 256, 0, s, xp, w, bias, out, B, H, W, C, cimg, up, scale, up_scale, LP)); break;
+        case 2: PG_CUDA(pg::launch(rgb_reduce_kernel<T, 2>, grid, 256, 0, s, xp, w, bias, out, B, H, W, C, cimg, up, scale, up_scale, LP)); break;
+        default: PG_CUDA(pg::launch(rgb_reduce_kernel<T, 4>, grid, 256, 0, s, xp, w, bias, out, B, H, W, C, cimg, up, scale, up_scale, LP)); break;
     }
     PG_LAUNCH_CHECK();
     g_other_launches++;
@@ -802,18 +813,18 @@ extern "C" int pggan_rgb_wgrad(const void* f, const float* img, float* acc, floa
     if (!rgb_old && cimg <= 3) {
         const long long tiles = (P + kTilePix - 1) / kTilePix;
         // (each block ends with TX*VN*4 atomics; one resident wave keeps their count at a few per SM)
-        auto launch_t = [&](auto tag) {
+        auto launch_t = [&](auto tag) -> int {
             using TT = decltype(tag);
             if (pool)
-                rgb_wgrad_tile_kernel<TT, true><<<resident_grid(rgb_wgrad_tile_kernel<TT, true>, tiles), 256, 0, s>>>(
-                    (const TT*)f, img, acc, bsum, B, H, W, C, cimg, scale, TX);
+                PG_CUDA(pg::launch(rgb_wgrad_tile_kernel<TT, true>, resident_grid(rgb_wgrad_tile_kernel<TT, true>, tiles), 256, 0, s, 
+                    (const TT*)f, img, acc, bsum, B, H, W, C, cimg, scale, TX));
             else
-                rgb_wgrad_tile_kernel<TT, false><<<resident_grid(rgb_wgrad_tile_kernel<TT, false>, tiles), 256, 0, s>>>(
-                    (const TT*)f, img, acc, bsum, B, H, W, C, cimg, scale, TX);
+                PG_CUDA(pg::launch(rgb_wgrad_tile_kernel<TT, false>, resident_grid(rgb_wgrad_tile_kernel<TT, false>, tiles), 256, 0, s, 
+                    (const TT*)f, img, acc, bsum, B, H, W, C, cimg, scale, TX));
+            return PG_OK;
         };
-        if (dtype == PG_BF16) launch_t(__nv_bfloat16());
-        else if (dtype == PG_F16) launch_t(__half());
-        else launch_t(float());
+        const int lrc = dtype == PG_BF16 ? launch_t(__nv_bfloat16()) : (dtype == PG_F16 ? launch_t(__half()) : launch_t(float()));
+        if (lrc != PG_OK) return lrc;
         PG_LAUNCH_CHECK();
         g_other_launches++;
         return PG_OK;
@@ -830,21 +841,21 @@ extern "C" int pggan_rgb_wgrad(const void* f, const float* img, float* acc, floa
     const size_t smem = (size_t)256 * vn * (kMaxImgC + 1) * sizeof(float);
     const int g2 = grid_for(P / 8 + 1, 256, 4);          // pixel kernel: >= 8 pixels per thread, <= 4 blocks per SM
     cudaError_t attr_err = cudaSuccess;
-    auto launch = [&](auto tag) {
+    auto launch = [&](auto tag) -> int {
         using TT = decltype(tag);
         // thread-per-pixel-stream for C = 16 (C = 32 would need 128 accumulators per thread: 203 registers, slower)
         if (cimg <= 3 && TX == 2) {
-            rgb_wgrad_pixel_kernel<TT, 2><<<g2, 256, 0, s>>>((const TT*)f, img, acc, bsum, B, H, W, cimg, pool, scale);
-            return;
+            PG_CUDA(pg::launch(rgb_wgrad_pixel_kernel<TT, 2>, g2, 256, 0, s, (const TT*)f, img, acc, bsum, B, H, W, cimg, pool, scale));
+            return PG_OK;
         }
         if (smem > 48 * 1024) {
             attr_err = cudaFuncSetAttribute(rgb_wgrad_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
         }
-        rgb_wgrad_kernel<TT><<<grid, 256, smem, s>>>((const TT*)f, img, acc, bsum, B, H, W, C, cimg, pool, scale, TX, ppb);
+        PG_CUDA(pg::launch(rgb_wgrad_kernel<TT>, grid, 256, smem, s, (const TT*)f, img, acc, bsum, B, H, W, C, cimg, pool, scale, TX, ppb));
+        return PG_OK;
     };
-    if (dtype == PG_BF16) launch(__nv_bfloat16());
-    else if (dtype == PG_F16) launch(__half());
-    else launch(float());
+    const int lrc2 = dtype == PG_BF16 ? launch(__nv_bfloat16()) : (dtype == PG_F16 ? launch(__half()) : launch(float()));
+    if (lrc2 != PG_OK) return lrc2;
     PG_CUDA(attr_err);
     PG_LAUNCH_CHECK();
     g_other_launches++;
@@ -859,7 +870,7 @@ extern "C" int pggan_image_fade(const float* x, const float* low, float* out, in
              "pggan_image_fade: misaligned pointer");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const long long planes = (long long)B * Cimg;
-    image_fade_kernel<<<grid_for(planes * (H / 2) * (W / 2), 256, 8), 256, 0, s>>>(x, low, out, planes, H, W, alpha);
+    PG_CUDA(pg::launch(image_fade_kernel, grid_for(planes * (H / 2) * (W / 2), 256, 8), 256, 0, s, x, low, out, planes, H, W, alpha));
     PG_LAUNCH_CHECK();
     g_other_launches++;
     return PG_OK;
@@ -871,7 +882,7 @@ extern "C" int pggan_image_pool_sum(const float* x, float* out, int B, int Cimg,
     PG_CHECK((reinterpret_cast<uintptr_t>(x) & 7) == 0, PG_ERR_ARG, "pggan_image_pool_sum: misaligned pointer");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const long long planes = (long long)B * Cimg;
-    image_pool_sum_kernel<<<grid_for(planes * (H / 2) * (W / 2), 256, 8), 256, 0, s>>>(x, out, planes, H, W, scale);
+    PG_CUDA(pg::launch(image_pool_sum_kernel, grid_for(planes * (H / 2) * (W / 2), 256, 8), 256, 0, s, x, out, planes, H, W, scale));
     PG_LAUNCH_CHECK();
     g_other_launches++;
     return PG_OK;

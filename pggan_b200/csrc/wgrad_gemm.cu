@@ -104,6 +104,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    PG_PDL_ENTER();        // prologue done (barriers, TMEM, descriptor prefetch): now wait for the predecessor's data
 
     const int total_chunks = a.chunks_w * a.chunks_h * a.chunks_b;
     const int num_units = a.tap_groups * a.tiles_n * a.tiles_c * a.splits;
@@ -277,6 +278,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
 template <typename T>
 __global__ void wgrad_direct_kernel(const T* __restrict__ g, const T* __restrict__ x, float* __restrict__ acc, int B,
                                     int H, int W, int C, int N, int taps, long long pix_per_block, int gf16, int xf16) {
+    PG_PDL_ENTER();
     __shared__ float gs[16][17], xs[16][17];
     // 16-bit instantiation: bf16 / IEEE half per operand are run-time flags
     auto ldv = [](const T* p, int f16) -> float {
@@ -323,6 +325,7 @@ template <typename T, int TW, int NT>
 __global__ void __launch_bounds__(256)
 wgrad_small_kernel(const T* __restrict__ g, const T* __restrict__ x, float* __restrict__ acc, int B, int H, int W, int C,
                    int N, int gf16, int xf16) {
+    PG_PDL_ENTER();
     extern __shared__ float sm[];
     auto cvt = [](const T& v, int f16) -> float {
         if constexpr (sizeof(T) == 2) return f16bits_to_f(*reinterpret_cast<const uint16_t*>(&v), f16 != 0);
@@ -496,7 +499,7 @@ static int launch_wg(const pg_wgrad_params* p, cudaStream_t stream) {
     PG_SET_SMEM_ONCE(kern, Cfg::kSmemBytes);
     const int num_units = base_units * a.splits;
     const int grid = num_units < num_sms() ? num_units : num_sms();
-    kern<<<grid, kWgThreads, Cfg::kSmemBytes, stream>>>(tg, tx, a);
+    PG_CUDA(pg::launch(kern, grid, kWgThreads, Cfg::kSmemBytes, stream, tg, tx, a));
     PG_LAUNCH_CHECK();
     g_tc_launches++;
     return PG_OK;
@@ -527,9 +530,9 @@ static int wgrad_simt(const pg_wgrad_params* p, cudaStream_t stream) {
         const T* gp = reinterpret_cast<const T*>(p->g);
         const T* xp = reinterpret_cast<const T*>(p->x);
         if (p->C * (p->N / 4) <= 256)
-            wgrad_small_kernel<T, TW, 4><<<(int)grid, 256, smem, stream>>>(gp, xp, p->acc, p->B, p->H, p->W, p->C, p->N, gf16, xf16);
+            PG_CUDA(pg::launch(wgrad_small_kernel<T, TW, 4>, (int)grid, 256, smem, stream, gp, xp, p->acc, p->B, p->H, p->W, p->C, p->N, gf16, xf16));
         else
-            wgrad_small_kernel<T, TW, 8><<<(int)grid, 256, smem, stream>>>(gp, xp, p->acc, p->B, p->H, p->W, p->C, p->N, gf16, xf16);
+            PG_CUDA(pg::launch(wgrad_small_kernel<T, TW, 8>, (int)grid, 256, smem, stream, gp, xp, p->acc, p->B, p->H, p->W, p->C, p->N, gf16, xf16));
         PG_LAUNCH_CHECK();
         g_simt_launches++;
         return PG_OK;
@@ -539,8 +542,8 @@ static int wgrad_simt(const pg_wgrad_params* p, cudaStream_t stream) {
     while ((P + pix_per_block - 1) / pix_per_block > 2048) pix_per_block *= 2;
     dim3 grid((unsigned)((P + pix_per_block - 1) / pix_per_block), (unsigned)p->taps,
               (unsigned)(((p->N + 15) / 16) * ((p->C + 15) / 16)));
-    wgrad_direct_kernel<T><<<grid, 256, 0, stream>>>(reinterpret_cast<const T*>(p->g), reinterpret_cast<const T*>(p->x),
-                                                      p->acc, p->B, p->H, p->W, p->C, p->N, p->taps, pix_per_block, gf16, xf16);
+    PG_CUDA(pg::launch(wgrad_direct_kernel<T>, grid, 256, 0, stream, reinterpret_cast<const T*>(p->g), reinterpret_cast<const T*>(p->x),
+                                                      p->acc, p->B, p->H, p->W, p->C, p->N, p->taps, pix_per_block, gf16, xf16));
     PG_LAUNCH_CHECK();
     g_simt_launches++;
     return PG_OK;

@@ -109,6 +109,7 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    PG_PDL_ENTER();        // prologue done (barriers, TMEM, descriptor prefetch): now wait for the predecessor's data
 
     const long long u_begin = static_cast<long long>(blockIdx.x) * a.per_cta;
     const long long u_end = (u_begin + a.per_cta < a.total) ? (u_begin + a.per_cta) : a.total;
@@ -303,7 +304,7 @@ static int launch_wr(const pg_wgrad_params* p, cudaStream_t stream) {
     }
     auto kern = wgrad_rows_kernel<XSPAN, GSPAN>;
     PG_SET_SMEM_ONCE(kern, Cfg::kSmemBytes);
-    kern<<<grid, kWrThreads, Cfg::kSmemBytes, stream>>>(tx, tg, a);
+    PG_CUDA(pg::launch(kern, grid, kWrThreads, Cfg::kSmemBytes, stream, tx, tg, a));
     PG_LAUNCH_CHECK();
     g_tc_launches++;
     return PG_OK;

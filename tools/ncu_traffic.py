@@ -32,6 +32,13 @@ def klass(name):
     return None
 
 
+# one training step = the launches between the 2nd and the 4th Adam launch of the capture (a step ends with the G
+# optimizer's Adam kernel; D's comes mid-step)
+order = list(rows.values())
+adam = [i for i, d in enumerate(order) if "adam_kernel" in d["name"]]
+if len(adam) >= 4:
+    order = order[adam[1] + 1: adam[3] + 1]
+    rows = collections.OrderedDict((i, d) for i, d in enumerate(order))
 agg = collections.OrderedDict()
 tot = 0.0
 for d in rows.values():
@@ -44,10 +51,13 @@ for d in rows.values():
     tot += d.get("gpu__time_duration.sum", 0.0)
 print(f"# r2 — ncu launch list of the {workload} step (eager launches, serialised by the profiler, cold caches)\n")
 print("Command: `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none "
-      "--launch-skip 2400 --launch-count 1100 --csv python bench.py --steps 1 --warmup 1 --no-graph --no-per-config "
-      "--no-cpu-baseline --no-timeline` (tools/gpu_evidence.sh).  Per-launch times under ncu are cold-cache and serialised:\n"
+      "--launch-skip S --launch-count N --csv python bench.py --workload W --steps 1 --warmup 1 --no-graph --no-per-config "
+      "--no-cpu-baseline --no-timeline` (tools/gpu_evidence2.sh); the table covers ONE step (between two G-optimizer Adam launches).\n"
+      "Per-launch times under ncu are cold-cache and serialised:\n"
       "the kernel's SHARE of the step is what must agree with the live CUPTI timeline (profiles/r2_step_breakdown.md), not the absolute.\n")
-print(f"{len(rows)} launches, {tot/1e6:.2f} ms of kernel time\n")
+tot_bytes = sum(a["rd"] + a["wr"] for a in agg.values())
+print(f"{len(rows)} launches, {tot/1e6:.2f} ms of kernel time, {tot_bytes/1e9:.2f} GB of DRAM traffic in the step "
+      f"(= {tot_bytes/6549.1e9*1e3:.2f} ms at the measured 6549 GB/s)\n")
 print("| kernel | launches | share of kernel time | avg us | DRAM read MB / launch | DRAM write MB / launch | achieved DRAM GB/s |")
 print("|---|---|---|---|---|---|---|")
 classes = collections.defaultdict(lambda: {"launches": 0, "bytes": 0.0, "ns": 0.0})
