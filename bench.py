@@ -213,6 +213,16 @@ def bench_config(args, workload, steps, warm, full, rank, world, local):
     torch.cuda.synchronize()
     c1 = _lib.launch_counts()
     launches_per_step = {k: c1[k] - c0[k] for k in c1}
+    if os.environ.get("PGGAN_PROFILE_ONE_STEP"):
+        # profiler hook (tools/gpu_ncu_step.sh): exactly ONE warm eager step between cudaProfilerStart/Stop, then exit —
+        # `ncu --profile-from-start off` then lists the launches of one step and nothing else.  Not a bench value.
+        torch.cuda.profiler.start()
+        step_eager()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        if rank == 0:
+            print(json.dumps({"profiled_one_step": workload, "launches_per_step": launches_per_step}))
+        sys.exit(0)
 
     replay, graph_err = None, None
     if args.graph and (world == 1 or not args.no_graph_dp):

@@ -10,7 +10,7 @@ so = sys.argv[1] if len(sys.argv) > 1 else "pggan_b200/lib/libpggan_b200.so"
 txt = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
 names = subprocess.run(["cu++filt"], input="\n".join(re.findall(r"Function : (\S+)", txt)), capture_output=True, text=True).stdout.splitlines()
 blocks = re.split(r"\s+Function : \S+\n", txt)[1:]
-ops_of_interest = ["UTCHMMA", "UTCQMMA", "UTMALDG", "LDTM", "UTCBAR", "SYNCS", "HMMA", "IMMA", "F2FP.SATFINITE", "ELECT", "RED", "ATOMG", "LDG", "STG", "LDS", "STS", "SHFL"]
+ops_of_interest = ["UTCHMMA", "UTCQMMA", "UTMALDG", "LDTM", "UTCBAR", "SYNCS", "HMMA", "IMMA", "F2FP.SATFINITE", "ELECT", "RED", "ATOMG", "LDG", "STG", "LDS", "STS", "SHFL", "ACQBULK", "PREEXIT"]
 rows = collections.OrderedDict()
 for name, body in zip(names, blocks):
     short = re.sub(r"^void ", "", name)
@@ -33,8 +33,8 @@ for name, body in zip(names, blocks):
     r["cnt"].update(cnt)
 print("# r2 — SASS opcode counts per kernel (all template instantiations summed), `cuobjdump -sass libpggan_b200.so`\n")
 print("UTCHMMA = tcgen05.mma (kind::f16 / tf32), LDTM = tcgen05.ld (TMEM -> registers), UTMALDG = cp.async.bulk.tensor (TMA) loads,")
-print("SYNCS = mbarrier ops, ELECT = elect.sync, F2FP.SATFINITE = saturating fp32 -> half conversion.  HMMA/IMMA (legacy mma.sync) must be 0.\n")
-cols = ["UTCHMMA", "UTMALDG", "LDTM", "SYNCS", "ELECT", "HMMA", "IMMA", "F2FP.SATFINITE", "RED", "ATOMG", "SHFL"]
+print("SYNCS = mbarrier ops, ELECT = elect.sync, F2FP.SATFINITE = saturating fp32 -> half conversion, ACQBULK / PREEXIT = griddepcontrol.wait / .launch_dependents (programmatic dependent launch).  HMMA/IMMA (legacy mma.sync) must be 0.\n")
+cols = ["UTCHMMA", "UTMALDG", "LDTM", "SYNCS", "ELECT", "HMMA", "IMMA", "F2FP.SATFINITE", "RED", "ATOMG", "SHFL", "ACQBULK", "PREEXIT"]
 print("| kernel | variants | SASS instr | " + " | ".join(cols) + " |")
 print("|---|---|---|" + "---|" * len(cols))
 tot = collections.Counter()
