@@ -413,8 +413,14 @@ def cupti_breakdown(step, n):
         agg[name][1] += e - s
     rows = [{"kernel": k, "ms_per_step": round(t / n / 1e3, 3), "launches_per_step": round(c / n, 1),
              "share": round(t / busy, 4)} for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:24]]
-    return {"span_ms_per_step": round((t1 - t0) / n / 1e3, 3), "kernel_busy_ms_per_step": round(busy / n / 1e3, 3),
-            "launches_per_step": round(len(kern) / n, 1), "kernels": rows}
+    pdl = os.environ.get("PGGAN_PDL", "1") != "0"
+    out = {"span_ms_per_step": round((t1 - t0) / n / 1e3, 3), "kernel_busy_ms_per_step": round(busy / n / 1e3, 3),
+           "launches_per_step": round(len(kern) / n, 1), "programmatic_dependent_launch": pdl, "kernels": rows}
+    if pdl:
+        out["note"] = ("kernels are pre-launched under programmatic dependent launch: a kernel's duration here includes its "
+                       "wait for the predecessor, so durations overlap (kernel-busy > span); run with PGGAN_PDL=0 for "
+                       "exclusive per-kernel times (profiles/r2_step_breakdown.md)")
+    return out
 
 
 def run_ours(args):

@@ -5,7 +5,7 @@ lib/blocks.py, lib/utils.py, lib/loss.py, pggan/nets.py, pggan/loss.py, pggan/mo
 all arithmetic runs in hand-written sm_100a CUDA kernels behind the C ABI of include/pggan_b200.h.
 """
 from . import _lib
-from .ops import set_compute_dtype, get_compute_dtype, input_grad_only  # noqa: F401
+from .ops import set_compute_dtype, get_compute_dtype, input_grad_only, set_deterministic  # noqa: F401
 from .layers import (PixelwiseVectorNorm, ConstrainedLayer, EqualizedConv2d, EqualizedLinear,  # noqa: F401
                      getLayerNormalizationFactor)
 from .blocks import (ProgressiveGeneratorBlock, ProgressiveDiscriminatorBlock, LastProgressiveDiscriminatorBlock,  # noqa: F401

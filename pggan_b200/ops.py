@@ -45,6 +45,7 @@ from __future__ import annotations
 
 import contextlib
 import ctypes
+import os
 from typing import Optional
 
 import torch
@@ -648,7 +649,16 @@ def dgrad_mask_fusable(batch, h, w, fwd_in_channels, fwd_out_channels, taps=9, d
     return hit
 
 
-DIRECT_WGRAD = True      # tests switch it off to compare against the slice buffer + un-pack path
+DIRECT_WGRAD = os.environ.get("PGGAN_DETERMINISTIC", "0") in ("", "0")     # see set_deterministic()
+
+
+def set_deterministic(flag: bool = True) -> None:
+    """True: keep the summation order of every weight gradient fixed — the wgrad GEMMs write per-split slices that an
+    un-pack pass adds in order (+0.4 ms per C4 step) instead of adding their partial sums to .grad with fp32 reductions.
+    Conv / split-K results are order-independent in both modes; what remains unordered are the fp32 atomics of the bias
+    and RGB-layer gradients.  Also settable with PGGAN_DETERMINISTIC=1."""
+    global DIRECT_WGRAD
+    DIRECT_WGRAD = not flag
 
 
 def _dense_map(fmap) -> bool:

@@ -305,12 +305,16 @@ def _twin_trainers(scale, depths, latent, alpha, variant="W"):
     return a, b
 
 
-def test_graph_replay_matches_eager_and_oracle_over_three_steps():
-    """The path bench.py times: benchmarked precision mode, C2's real widths (32x32, 512 channels), CUDA-graph replay,
+@pytest.mark.parametrize("deterministic", [True, False])
+def test_graph_replay_matches_eager_and_oracle_over_three_steps(deterministic):
+    """deterministic: pg.set_deterministic(True) keeps every weight gradient's summation order fixed (slice buffers summed
+    in order instead of fp32 reductions from the GEMM epilogues): replay and eager then agree to rounding noise.
+    The path bench.py times: benchmarked precision mode, C2's real widths (32x32, 512 channels), CUDA-graph replay,
     the batched real+fake D pass — against the same step launched eagerly and against the oracle, over THREE steps
     (Adam moments carried, packed-weight copies invalidated by every update), with alpha CHANGING between the steps:
     the graph captured at alpha 0.3 must follow G.alpha / D.alpha (device scalar), no re-capture."""
     import pggan_b200 as pg
+    pg.set_deterministic(deterministic)
     pg.set_compute_dtype(BENCH)
     scale, width, batch = 3, 512, 8
     depths = [width] * (scale + 1)
@@ -354,9 +358,12 @@ def test_graph_replay_matches_eager_and_oracle_over_three_steps():
               f"Adam second-moment err vs oracle {e_m:.2e}")
         # replay and eager launch the same kernels; fp32 atomics (bias sums, RGB weight grads) reorder -> a few signs of
         # near-zero gradients may differ
-        assert e_replay < 5e-2, (name, e_replay)
+        # (default mode: the weight-gradient reductions reorder too — with beta1 = 0 a 1e-7 difference in a near-zero
+        # gradient flips an update of +-lr)
+        assert e_replay < (1e-4 if deterministic else 5e-2), (name, e_replay)
         assert e_m < GRAD_TOL[BENCH], (name, e_m)
         assert e_oracle < 0.45, (name, e_oracle)       # <= 5 % of the +-lr update signs (near-zero gradients)
+    pg.set_deterministic(False)
 
 
 def test_training_across_scale_jumps_matches_oracle():

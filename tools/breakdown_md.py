@@ -5,7 +5,10 @@ import json
 import sys
 
 print("# r2 — kernel-time breakdown of one training step per BASELINE config (CUPTI timeline inside bench.py,\n"
-      "# CUDA-graph replay, warm; fp16 mode, W step).  `span` = first kernel start to last kernel end per step.\n")
+      "# CUDA-graph replay, warm; fp16 mode, W step).  `span` = first kernel start to last kernel end per step.\n"
+      "# Collected with PGGAN_PDL=0 (tools/gpu_final2.sh): with programmatic dependent launch on, a pre-launched kernel's\n"
+      "# CUPTI duration includes its wait for the predecessor.  The two replays in the CUPTI window run at burst clocks; the\n"
+      "# ms/step in each heading is the CUDA-event time over 10 back-to-back replays (power-capped clocks).\n")
 for path in sys.argv[1:]:
     try:
         d = json.loads([ln for ln in open(path) if ln.startswith("{")][-1])
@@ -20,7 +23,8 @@ for path in sys.argv[1:]:
     if not sb or "kernels" not in sb:
         print(f"(no timeline: {sb})\n")
         continue
-    print(f"span {sb['span_ms_per_step']} ms, kernel-busy {sb['kernel_busy_ms_per_step']} ms, {sb['launches_per_step']} launches per step\n")
+    print(f"span {sb['span_ms_per_step']} ms, kernel-busy {sb['kernel_busy_ms_per_step']} ms, {sb['launches_per_step']} launches per step"
+          f" (programmatic dependent launch {'ON: durations overlap' if sb.get('programmatic_dependent_launch') else 'off: exclusive kernel times'})\n")
     print("```")
     for k in sb["kernels"]:
         print("%5.1f%% %8.3f ms/step n/step=%6.1f avg %8.1f us  %s" % (100 * k["share"], k["ms_per_step"], k["launches_per_step"],

@@ -28,7 +28,7 @@ c_regs = find(r"^launch__registers_per_thread$")
 c_smem = find(r"^launch__shared_mem_per_block_dynamic$")
 c_issue = find(r"sm__inst_executed.avg.per_cycle_elapsed$") or find(r"smsp__issue_active.avg.pct")
 print("# r2 — `ncu --set full --clock-control none --import-source on` of the tensor-core kernels inside the C4 step\n")
-print("Command: see tools/gpu_evidence.sh (16 launches of conv_gemm / wgrad_gemm / conv_rows after 250 skipped, eager C4 step, fp16 mode).")
+print("Command: see tools/gpu_evidence2.sh (20 launches of conv_gemm / wgrad_gemm / conv_rows / wgrad_rows after 250 skipped: D's forward over the real + fake batch (B = 32) and the interpolates (B = 16) of an eager C4 step, fp16 mode; the split-K launches of the 4^2 / 8^2 layers are the 64-wide tiles with 64-128 CTAs).")
 print("Every kernel is replayed ~40 times by ncu with cold caches: durations are NOT bench values; the tensor-pipe activity and the\n"
       "DRAM byte counts are what this capture is for.  (The kernel template argument `__nv_bfloat16` is the shared 16-bit instantiation;\n"
       "the operand format — IEEE half here — is a run-time field of the instruction descriptor.)\n")
