@@ -509,7 +509,7 @@ def clear_pack_cache(params=None):
 
 
 # ------------------------------------------------------------------------------- mask hand-shake (double backward)
-FUSE_DOUBLE_BACKWARD_MASKS = True       # tests switch it off to compare against the unfused composition
+FUSE_DOUBLE_BACKWARD_MASKS = os.environ.get("PGGAN_NO_MASK_FUSE", "0") in ("", "0")   # tests switch it off to compare against the unfused composition
 
 
 class _MaskLink:
@@ -655,8 +655,9 @@ DIRECT_WGRAD = os.environ.get("PGGAN_DETERMINISTIC", "0") in ("", "0")     # see
 def set_deterministic(flag: bool = True) -> None:
     """True: keep the summation order of every weight gradient fixed — the wgrad GEMMs write per-split slices that an
     un-pack pass adds in order (+0.4 ms per C4 step) instead of adding their partial sums to .grad with fp32 reductions.
-    Conv / split-K results are order-independent in both modes; what remains unordered are the fp32 atomics of the bias
-    and RGB-layer gradients.  Also settable with PGGAN_DETERMINISTIC=1."""
+    Conv / split-K results are order-independent in both modes; what remains unordered in either mode are the fp32
+    atomics of the bias and RGB-layer gradients (column sums), so two runs still differ in the last bit of those.
+    Also settable with PGGAN_DETERMINISTIC=1."""
     global DIRECT_WGRAD
     DIRECT_WGRAD = not flag
 
@@ -787,6 +788,8 @@ def k_upsample(x, scale, mask_src=None, slope=1.0, cls=A, colsum=None, colsum_sc
 
 
 def upsample_colsum_fusable(x, cls=G) -> bool:
+    if os.environ.get("PGGAN_NO_POOL_COLSUM", "0") not in ("", "0"):
+        return False
     c = _dims(x)[1]
     vn = _vn(_fmt_of(x, cls))
     return x.dim() == 4 and c % vn == 0 and (c // vn) <= 256 and 256 % (c // vn) == 0
