@@ -4,6 +4,9 @@
 // (pggan/nets.py:155-156), the real-image fade (pggan/model.py:217-221).
 #include "common.cuh"
 
+#include <mutex>
+#include <unordered_map>
+
 #include <atomic>
 #include <stdlib.h>
 
@@ -652,8 +655,20 @@ static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) 
 // runs 1.6 waves — the second one on 60 % of the slots; ncu on the tile kernels: 30-50 % achieved occupancy)
 template <typename K>
 static int resident_grid(K kern, long long tiles, int threads = 256) {
+    // (the occupancy of a kernel does not change: asked once per kernel, the boxes' GPUs being identical)
+    static std::mutex mu;
+    static std::unordered_map<const void*, int> cache;
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = cache.find(reinterpret_cast<const void*>(kern));
+        if (it != cache.end()) {
+            per_sm = it->second;
+        } else {
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+            cache.emplace(reinterpret_cast<const void*>(kern), per_sm);
+        }
+    }
     const long long cap = static_cast<long long>(num_sms()) * per_sm;
     return static_cast<int>(tiles < cap ? (tiles < 1 ? 1 : tiles) : cap);
 }
