@@ -846,6 +846,9 @@ class ConvF(torch.autograd.Function):
         ctx.xc = xc
         ctx.w_param = W if isinstance(W, torch.nn.Parameter) else None
         ctx.bias_param = b if isinstance(b, torch.nn.Parameter) else None
+        if defer_mask and ctx.bias_param is not None and not (layout and layout[0] == "lin_out_perm"):
+            # whoever applies this layer's mask in the backward (the pool's adjoint) may take the bias gradient along
+            y._pg_bias = (ctx.bias_param, scale)
         return y
 
     @staticmethod
@@ -869,9 +872,17 @@ class ConvF(torch.autograd.Function):
             # plain backward: LeakyReLU mask and bias gradient in one pass over g; gradients of registered
             # parameters are accumulated in place (see _GRAD_SINK)
             b_sink = _sink(ctx.bias_param) if (need_b and not (ctx.layout and ctx.layout[0] == "lin_out_perm")) else None
-            pre = getattr(gy, "_pg_colsum", None) if (need_b and not ctx.mask_here and g is gy) else None
-            if pre is not None:
-                # the pool backward that produced gy already summed its columns (_upsample_mask)
+            pre = getattr(gy, "_pg_colsum", None) if need_b else None
+            if pre is not None and not isinstance(pre, str) and (ctx.mask_here or g is not gy):
+                pre = None                  # (a buffer of column sums of a tensor that is not what this layer sums)
+            if isinstance(pre, str):
+                # "sunk": the pool backward that produced gy added this layer's bias gradient to .grad itself (and told the
+                # sink listeners) — never add it a second time
+                b_sink = None
+                if ctx.mask_here:
+                    g, _ = k_mask_colsum(g, y, ctx.slope, True, None)
+            elif pre is not None:
+                # ... or summed the columns into a buffer of its own (no gradient sink in this context)
                 if b_sink is not None:
                     b_sink.add_(pre, alpha=ctx.scale)
                 else:
@@ -1125,13 +1136,22 @@ class UpsampleMask(torch.autograd.Function):
         return Pool2x2.apply(gg, ctx.scale, None, G), None, None, None, None
 
 
-def _upsample_mask(g, y, scale, slope):
+def _upsample_mask(g, y, scale, slope, bias_info=None):
+    """bias_info: (bias parameter, He scale) of the conv that produced y (tag left by ConvF.forward), or None"""
     if not torch.is_grad_enabled():
         g = feat(g, G, small=(y.dtype == torch.float32))
-        if _SKIP_PARAM_GRADS or not upsample_colsum_fusable(g):
+        if _SKIP_PARAM_GRADS or bias_info is None or not bias_info[0].requires_grad or not upsample_colsum_fusable(g):
             return k_upsample(g, scale, mask_src=y, slope=slope, cls=G)
-        # plain backward: y is the output of a conv whose bias gradient is the column sum of this result — taken in
-        # the same pass and handed to that conv's backward through the tensor (ConvF.backward picks up `_pg_colsum`)
+        # plain backward: y is the output of a conv whose bias gradient is the column sum of this result — taken in the
+        # same pass: straight into .grad inside a gradient-sink context, else into a buffer handed to that conv's backward
+        # through the tensor (ConvF.backward picks up `_pg_colsum`)
+        bparam, bscale = bias_info
+        sink = _sink(bparam)
+        if sink is not None:
+            out = k_upsample(g, scale, mask_src=y, slope=slope, cls=G, colsum=sink, colsum_scale=bscale)
+            _sunk(bparam)
+            out._pg_colsum = "sunk"
+            return out
         cs = torch.zeros((g.shape[1],), dtype=torch.float32, device=g.device)
         out = k_upsample(g, scale, mask_src=y, slope=slope, cls=G, colsum=cs)
         out._pg_colsum = cs
@@ -1147,6 +1167,7 @@ class Pool2x2(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, scale, act_slope=None, cls=A):
+        ctx.bias_info = getattr(x, "_pg_bias", None) if act_slope is not None else None
         x = feat(x, cls)
         ctx.scale, ctx.act_slope, ctx.f32 = scale, act_slope, x.dtype == torch.float32
         if act_slope is not None:
@@ -1158,7 +1179,7 @@ class Pool2x2(torch.autograd.Function):
         g = feat(g, G, small=ctx.f32)
         if ctx.act_slope is not None:
             (x,) = ctx.saved_tensors
-            return _upsample_mask(g, x, ctx.scale, ctx.act_slope), None, None, None
+            return _upsample_mask(g, x, ctx.scale, ctx.act_slope, ctx.bias_info), None, None, None
         return Upsample2x.apply(g, ctx.scale, G), None, None, None
 
 
@@ -1168,6 +1189,7 @@ class PoolBlend(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, low, alpha, act_slope=None):
+        ctx.bias_info = getattr(x, "_pg_bias", None) if act_slope is not None else None
         x = feat(x, A)
         ctx.alpha, ctx.act_slope, ctx.f32 = alpha, act_slope, x.dtype == torch.float32
         if act_slope is not None:
@@ -1181,7 +1203,7 @@ class PoolBlend(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             if ctx.act_slope is not None:
                 (x,) = ctx.saved_tensors
-                gx = _upsample_mask(g, x, _affine(0.0, 0.25, ctx.alpha), ctx.act_slope)
+                gx = _upsample_mask(g, x, _affine(0.0, 0.25, ctx.alpha), ctx.act_slope, ctx.bias_info)
             else:
                 gx = Upsample2x.apply(g, _affine(0.0, 0.25, ctx.alpha), G)
         gl = Scale.apply(g, _affine(1.0, -1.0, ctx.alpha), G) if ctx.needs_input_grad[1] else None
