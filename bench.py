@@ -413,7 +413,7 @@ def cupti_breakdown(step, n):
         agg[name][1] += e - s
     rows = [{"kernel": k, "ms_per_step": round(t / n / 1e3, 3), "launches_per_step": round(c / n, 1),
              "share": round(t / busy, 4)} for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:24]]
-    pdl = os.environ.get("PGGAN_PDL", "1") != "0"
+    pdl = os.environ.get("PGGAN_PDL", "0") not in ("", "0")
     out = {"span_ms_per_step": round((t1 - t0) / n / 1e3, 3), "kernel_busy_ms_per_step": round(busy / n / 1e3, 3),
            "launches_per_step": round(len(kern) / n, 1), "programmatic_dependent_launch": pdl, "kernels": rows}
     if pdl:

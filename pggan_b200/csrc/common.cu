@@ -94,12 +94,17 @@ extern "C" int pggan_launch_counts(int64_t* tc, int64_t* simt, int64_t* other) {
 }
 
 namespace pg {
-bool pdl_enabled() {
-    // programmatic dependent launch of this library's kernels; PGGAN_PDL=0 switches it off
-    static const bool on = [] {
+int pdl_mode() {
+    // programmatic dependent launch of this library's kernels: PGGAN_PDL = 0 (default) off, 1 every kernel, 2 the
+    // tensor-core kernels only.  Measured on whole steps (tools/gpu_pdl_modes.sh, one box, C5 at full clocks): 20.67 ms off,
+    // 20.90 ms mode 2, 21.37 ms mode 1; C4 27.1-27.6 ms in every mode; C1 3.20 / 3.18 / 3.13 ms — the 0.5-0.7 us per
+    // launch it saves in back-to-back micro-benchmarks does not survive in the step (pre-launched CTAs take their SMs in
+    // the order SMs happen to free up, which unbalances the bandwidth kernels), so it stays off.
+    static const int mode = [] {
         const char* e = getenv("PGGAN_PDL");
-        return e == nullptr ? true : (e[0] != '0');
+        if (e == nullptr || e[0] == '\0') return 0;
+        return (e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0;
     }();
-    return on;
+    return mode;
 }
 }  // namespace pg

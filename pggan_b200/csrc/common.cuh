@@ -31,12 +31,12 @@ void set_error(const char* fmt, ...);
         }                                                                          \
     } while (0)
 #define PG_LAUNCH_CHECK() PG_CUDA(cudaPeekAtLastError())
-// Programmatic dependent launch (griddepcontrol): a kernel launched through pg::launch() with PGGAN_PDL=1 may be
-// SCHEDULED while its predecessor in the stream is still running — its CTAs take an SM as soon as one is free, run their
-// prologue (barrier init, TMEM allocation, descriptor prefetch) and block in pdl_wait() until the predecessor has
-// completed and its writes are visible.  Every kernel calls PG_PDL_ENTER() before its first global-memory access:
-// wait for the predecessor, then allow the successor to be scheduled.  Without the launch attribute both instructions
-// are no-ops.
+// Programmatic dependent launch (griddepcontrol), OPT-IN (PGGAN_PDL=1|2, see pdl_mode() in common.cu for the measurements
+// that keep it off by default): a kernel launched with the attribute may be SCHEDULED while its predecessor in the stream
+// is still running — its CTAs take an SM as soon as one is free, run their prologue (barrier init, TMEM allocation,
+// descriptor prefetch) and block in pdl_wait() until the predecessor has completed and its writes are visible.  Every
+// kernel calls PG_PDL_ENTER() before its first global-memory access: wait for the predecessor, then allow the successor
+// to be scheduled.  Without the launch attribute both instructions are no-ops.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #define PG_PDL_ENTER()     \
@@ -45,10 +45,11 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
         pg::pdl_trigger(); \
     } while (0)
 
-bool pdl_enabled();        // common.cu: env PGGAN_PDL (default on/off decided there)
+int pdl_mode();            // common.cu: env PGGAN_PDL — 0 off, 1 every kernel, 2 the tensor-core kernels only
 
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+inline cudaError_t launch_attr(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                               Args&&... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
@@ -58,8 +59,18 @@ inline cudaError_t launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t 
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cfg.numAttrs = pdl ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+// bandwidth / glue kernels
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    return launch_attr(pdl_mode() == 1, kern, grid, block, smem, stream, static_cast<Args&&>(args)...);
+}
+// tcgen05 kernels (one persistent CTA per SM with a prologue worth overlapping: barrier init, TMEM allocation)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_tc(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    return launch_attr(pdl_mode() >= 1, kern, grid, block, smem, stream, static_cast<Args&&>(args)...);
 }
 
 // opt a kernel into > 48 KB of dynamic shared memory: the attribute is per (function, DEVICE), so remember it per device

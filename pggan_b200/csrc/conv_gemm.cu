@@ -819,7 +819,7 @@ static int launch_tc(const pg_conv_params* p, cudaStream_t stream, int ksplit = 
     PG_SET_SMEM_ONCE(kern, Cfg::kSmemBytes);
     const int num_tiles = a.tiles_w * a.tiles_h * a.tiles_b * a.tiles_n * (a.up2 ? 4 : 1) * a.ksplit;
     int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-    PG_CUDA(pg::launch(kern, grid, kConvThreadsPlain, Cfg::kSmemBytes, stream, tx, tw, a));
+    PG_CUDA(pg::launch_tc(kern, grid, kConvThreadsPlain, Cfg::kSmemBytes, stream, tx, tw, a));
     PG_LAUNCH_CHECK();
     g_tc_launches++;
     return PG_OK;
@@ -867,7 +867,7 @@ static int launch_swapped(const pg_conv_params* p, cudaStream_t stream) {
     PG_SET_SMEM_ONCE(kern, kSwSmemBytes);
     const int num_tiles = a.tiles_w * a.tiles_h * a.tiles_b * a.tiles_n;
     const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-    PG_CUDA(pg::launch(kern, grid, kConvThreads, kSwSmemBytes, stream, tx, tw, a));
+    PG_CUDA(pg::launch_tc(kern, grid, kConvThreads, kSwSmemBytes, stream, tx, tw, a));
     PG_LAUNCH_CHECK();
     g_tc_launches++;
     return PG_OK;

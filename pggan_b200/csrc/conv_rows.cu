@@ -449,7 +449,7 @@ static int launch_rows(const pg_conv_params* p_in, cudaStream_t stream) {
     }
     auto kern = conv_rows_kernel<SPAN, BLOCK_N, J>;
     PG_SET_SMEM_ONCE(kern, Cfg::kSmemBytes);
-    PG_CUDA(pg::launch(kern, (int)grid, kRowsThreads, Cfg::kSmemBytes, stream, tx, tw, a));
+    PG_CUDA(pg::launch_tc(kern, (int)grid, kRowsThreads, Cfg::kSmemBytes, stream, tx, tw, a));
     PG_LAUNCH_CHECK();
     g_tc_launches++;
     return PG_OK;

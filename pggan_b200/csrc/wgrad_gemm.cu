@@ -499,7 +499,7 @@ static int launch_wg(const pg_wgrad_params* p, cudaStream_t stream) {
     PG_SET_SMEM_ONCE(kern, Cfg::kSmemBytes);
     const int num_units = base_units * a.splits;
     const int grid = num_units < num_sms() ? num_units : num_sms();
-    PG_CUDA(pg::launch(kern, grid, kWgThreads, Cfg::kSmemBytes, stream, tg, tx, a));
+    PG_CUDA(pg::launch_tc(kern, grid, kWgThreads, Cfg::kSmemBytes, stream, tg, tx, a));
     PG_LAUNCH_CHECK();
     g_tc_launches++;
     return PG_OK;

@@ -304,7 +304,7 @@ static int launch_wr(const pg_wgrad_params* p, cudaStream_t stream) {
     }
     auto kern = wgrad_rows_kernel<XSPAN, GSPAN>;
     PG_SET_SMEM_ONCE(kern, Cfg::kSmemBytes);
-    PG_CUDA(pg::launch(kern, grid, kWrThreads, Cfg::kSmemBytes, stream, tx, tg, a));
+    PG_CUDA(pg::launch_tc(kern, grid, kWrThreads, Cfg::kSmemBytes, stream, tx, tg, a));
     PG_LAUNCH_CHECK();
     g_tc_launches++;
     return PG_OK;

@@ -6,8 +6,8 @@ import sys
 
 print("# r2 — kernel-time breakdown of one training step per BASELINE config (CUPTI timeline inside bench.py,\n"
       "# CUDA-graph replay, warm; fp16 mode, W step).  `span` = first kernel start to last kernel end per step.\n"
-      "# Collected with PGGAN_PDL=0 (tools/gpu_final2.sh): with programmatic dependent launch on, a pre-launched kernel's\n"
-      "# CUPTI duration includes its wait for the predecessor.  The two replays in the CUPTI window run at burst clocks; the\n"
+      "# (With PGGAN_PDL=1|2 a pre-launched kernel's CUPTI duration would include its wait for the predecessor; it is off.)\n"
+      "# The two replays in the CUPTI window run at burst clocks; the\n"
       "# ms/step in each heading is the CUDA-event time over 10 back-to-back replays (power-capped clocks).\n")
 for path in sys.argv[1:]:
     try:
