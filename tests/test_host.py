@@ -3,6 +3,7 @@ exports every declared symbol, schedule bookkeeping."""
 import os
 import re
 
+import pytest
 import torch
 
 from oracle import pggan_oracle as O
@@ -215,3 +216,33 @@ def test_precision_modes_and_tensor_classes():
         assert abs(c.c0 - 0.75) < 1e-7 and c.c1 == 0.0 and not c.alpha
     finally:
         pg.set_compute_dtype(torch.float16)
+
+
+def test_dense_map_and_switches():
+    """which weight gradients may be accumulated by the GEMM epilogue (ops._dense_map), the deterministic switch, and the
+    mask hand-shake's token (ops._premasked) — host logic only"""
+    from pggan_b200 import ops
+    import pggan_b200 as pg
+    # channels_last 3x3 conv weight and plain [out,in] linear weight: the operand IS the parameter memory
+    assert ops._dense_map(ops._maps((64, 32, 3, 3), None, ohwi=True)[3])
+    assert ops._dense_map(ops._maps((512, 128), None)[3])
+    # OIHW 3x3, the permuted linear layers, the padded conv: not dense
+    assert not ops._dense_map(ops._maps((64, 32, 3, 3), None, ohwi=False)[3])
+    assert not ops._dense_map(ops._maps((512, 8192), ("lin_in_perm", 512))[3])
+    assert not ops._dense_map(ops._maps((8192, 512), ("lin_out_perm", 512))[3])
+    assert not ops._dense_map(ops._maps((512, 513, 3, 3), ("pad_c", 576), ohwi=True)[3])
+    before = ops.DIRECT_WGRAD
+    pg.set_deterministic(True)
+    assert ops.DIRECT_WGRAD is False
+    pg.set_deterministic(False)
+    assert ops.DIRECT_WGRAD is True
+    ops.DIRECT_WGRAD = before
+    # the token protocol: no token -> mask as usual; matching token -> skip once; foreign token -> loud failure
+    link = ops._MaskLink()
+    t = torch.zeros(2, 3)
+    assert ops._premasked(None, t) is False and ops._premasked(link, t) is False
+    link.token = (t.data_ptr(), tuple(t.shape))
+    assert ops._premasked(link, t) is True and link.token is None
+    link.token = (t.data_ptr() + 64, tuple(t.shape))
+    with pytest.raises(RuntimeError):
+        ops._premasked(link, t)
